@@ -1,0 +1,301 @@
+// ORACLE (test infrastructure, NOT product code) -- see lfo_base.h header.
+// lib/lf/assemble: dofhandler.h:112-228,260-503, dofhandler.cc:86-338, coomatrix.h:52-225, assembler.h:114-186,298-327
+#ifndef LFO_ASSEMBLE_H
+#define LFO_ASSEMBLE_H
+
+#include <algorithm>
+#include <map>
+
+#include "lfo_mesh.h"
+
+namespace lfo::assemble {
+
+// lib/lf/assemble/dofhandler.h:112-228
+class DofHandler {
+ public:
+  virtual ~DofHandler() = default;
+  [[nodiscard]] virtual size_type NumDofs() const = 0;
+  [[nodiscard]] virtual size_type NumLocalDofs(const mesh::Entity& entity) const = 0;
+  [[nodiscard]] virtual size_type NumInteriorDofs(const mesh::Entity& entity) const = 0;
+  [[nodiscard]] virtual std::span<const gdof_idx_t> GlobalDofIndices(const mesh::Entity& entity) const = 0;
+  [[nodiscard]] virtual std::span<const gdof_idx_t> InteriorGlobalDofIndices(const mesh::Entity& entity) const = 0;
+  [[nodiscard]] virtual const mesh::Entity& Entity(gdof_idx_t dofnum) const = 0;
+  [[nodiscard]] virtual std::shared_ptr<const mesh::Mesh> Mesh() const = 0;
+};
+
+// lib/lf/assemble/dofhandler.h:260-503, dofhandler.cc:86-338
+class UniformFEDofHandler final : public DofHandler {
+ public:
+  using dof_map_t = std::map<RefEl, size_type>;
+  UniformFEDofHandler(std::shared_ptr<const mesh::Mesh> mesh, const dof_map_t& dofmap, bool check_edge_orientation = true)
+      : mesh_(std::move(mesh)), check_edge_orientation_(check_edge_orientation) {
+    auto get = [&](RefEl r) {
+      auto it = dofmap.find(r);
+      return it == dofmap.end() ? 0U : it->second;
+    };
+    num_loc_dof_point_ = get(RefEl::kPoint());
+    num_loc_dof_segment_ = get(RefEl::kSegment());
+    num_loc_dof_tria_ = get(RefEl::kTria());
+    num_loc_dof_quad_ = get(RefEl::kQuad());
+    // dofhandler.cc:130-138
+    num_dofs_[kNodeOrd] = num_loc_dof_point_;
+    num_dofs_[kEdgeOrd] = 2 * num_loc_dof_point_ + num_loc_dof_segment_;
+    num_dofs_tria_ = 3 * num_loc_dof_point_ + 3 * num_loc_dof_segment_ + num_loc_dof_tria_;
+    num_dofs_quad_ = 4 * num_loc_dof_point_ + 4 * num_loc_dof_segment_ + num_loc_dof_quad_;
+    num_dofs_[kCellOrd] = std::max(num_dofs_tria_, num_dofs_quad_);
+    initIndexArrays();
+  }
+
+  [[nodiscard]] size_type NumDofs() const override { return num_dof_; }
+  [[nodiscard]] size_type NumLocalDofs(const mesh::Entity& e) const override { return NumCoveredDofs(e.RefElem()); }
+  [[nodiscard]] size_type NumInteriorDofs(const mesh::Entity& e) const override { return NumInterior(e.RefElem()); }
+  [[nodiscard]] std::span<const gdof_idx_t> GlobalDofIndices(const mesh::Entity& e) const override {
+    return GlobalDofIndices(e.RefElem(), mesh_->Index(e));
+  }
+  // dofhandler.cc:286-300
+  [[nodiscard]] std::span<const gdof_idx_t> GlobalDofIndices(RefEl ref_el, glb_idx_t entity_index) const {
+    const dim_t codim = 2 - ref_el.Dimension();
+    const size_type no_covered = NumCoveredDofs(ref_el);
+    const gdof_idx_t* begin = dofs_[codim].data() + (static_cast<std::size_t>(num_dofs_[codim]) * entity_index);
+    return {begin, begin + no_covered};
+  }
+  [[nodiscard]] std::span<const gdof_idx_t> InteriorGlobalDofIndices(const mesh::Entity& e) const override {
+    const RefEl ref_el = e.RefElem();
+    const dim_t codim = 2 - ref_el.Dimension();
+    const size_type no_covered = NumCoveredDofs(ref_el), no_loc = NumInterior(ref_el);
+    const gdof_idx_t* begin = dofs_[codim].data() + (static_cast<std::size_t>(num_dofs_[codim]) * mesh_->Index(e));
+    return {begin + (no_covered - no_loc), begin + no_covered};
+  }
+  [[nodiscard]] const mesh::Entity& Entity(gdof_idx_t dofnum) const override { return *dof_entities_[dofnum]; }
+  [[nodiscard]] std::shared_ptr<const mesh::Mesh> Mesh() const override { return mesh_; }
+  [[nodiscard]] size_type CellStride() const { return num_dofs_[kCellOrd]; }
+  [[nodiscard]] const std::vector<gdof_idx_t>& CellDofArray() const { return dofs_[kCellOrd]; }
+
+ private:
+  static constexpr int kNodeOrd = 2, kEdgeOrd = 1, kCellOrd = 0;
+  [[nodiscard]] size_type NumCoveredDofs(RefEl r) const {
+    switch (r.Id()) {
+      case 1: return num_dofs_[kNodeOrd];
+      case 2: return num_dofs_[kEdgeOrd];
+      case 3: return num_dofs_tria_;
+      default: return num_dofs_quad_;
+    }
+  }
+  [[nodiscard]] size_type NumInterior(RefEl r) const {
+    switch (r.Id()) {
+      case 1: return num_loc_dof_point_;
+      case 2: return num_loc_dof_segment_;
+      case 3: return num_loc_dof_tria_;
+      default: return num_loc_dof_quad_;
+    }
+  }
+  // dofhandler.cc:141-284
+  void initIndexArrays() {
+    gdof_idx_t dof_idx = 0;
+    // Step I: nodes in index order
+    const size_type no_nodes = mesh_->NumEntities(2);
+    dofs_[kNodeOrd].resize(static_cast<std::size_t>(no_nodes) * num_dofs_[kNodeOrd]);
+    for (glb_idx_t node_idx = 0; node_idx < no_nodes; node_idx++) {
+      const mesh::Entity* node_p = mesh_->EntityByIndex(2, node_idx);
+      std::size_t off = static_cast<std::size_t>(node_idx) * num_dofs_[kNodeOrd];
+      for (unsigned j = 0; j < num_loc_dof_point_; j++) {
+        dofs_[kNodeOrd][off++] = dof_idx;
+        dof_entities_.push_back(node_p);
+        dof_idx++;
+      }
+    }
+    // Step II: edges in index order
+    const size_type no_edges = mesh_->NumEntities(1);
+    dofs_[kEdgeOrd].resize(static_cast<std::size_t>(no_edges) * num_dofs_[kEdgeOrd]);
+    for (glb_idx_t edge_idx = 0; edge_idx < no_edges; edge_idx++) {
+      const mesh::Entity* edge_p = mesh_->EntityByIndex(1, edge_idx);
+      std::size_t off = static_cast<std::size_t>(edge_idx) * num_dofs_[kEdgeOrd];
+      for (const mesh::Entity* endpoint : edge_p->SubEntities(1)) {
+        const glb_idx_t ep_idx = mesh_->Index(*endpoint);
+        std::size_t ep_off = static_cast<std::size_t>(ep_idx) * num_dofs_[kNodeOrd];
+        for (unsigned j = 0; j < num_dofs_[kNodeOrd]; j++) dofs_[kEdgeOrd][off++] = dofs_[kNodeOrd][ep_off++];
+      }
+      for (unsigned j = 0; j < num_loc_dof_segment_; j++) {
+        dofs_[kEdgeOrd][off++] = dof_idx;
+        dof_entities_.push_back(edge_p);
+        dof_idx++;
+      }
+    }
+    // Step III: cells in index order
+    const size_type no_cells = mesh_->NumEntities(0);
+    dofs_[kCellOrd].resize(static_cast<std::size_t>(no_cells) * num_dofs_[kCellOrd]);
+    const size_type no_int_dof_edge = num_loc_dof_segment_;
+    const size_type num_ext_dof_edge = num_dofs_[kEdgeOrd] - no_int_dof_edge;
+    for (glb_idx_t cell_idx = 0; cell_idx < no_cells; cell_idx++) {
+      const mesh::Entity* cell_p = mesh_->EntityByIndex(0, cell_idx);
+      std::size_t off = static_cast<std::size_t>(cell_idx) * num_dofs_[kCellOrd];
+      for (const mesh::Entity* vertex : cell_p->SubEntities(2)) {
+        const glb_idx_t vt_idx = mesh_->Index(*vertex);
+        std::size_t vt_off = static_cast<std::size_t>(vt_idx) * num_dofs_[kNodeOrd];
+        for (unsigned j = 0; j < num_dofs_[kNodeOrd]; j++) dofs_[kCellOrd][off++] = dofs_[kNodeOrd][vt_off++];
+      }
+      const auto edge_orientations = cell_p->RelativeOrientations();
+      const auto edges = cell_p->SubEntities(1);
+      const size_type no_edges_cell = cell_p->RefElem().NumSubEntities(1);
+      for (size_type ed_sub_idx = 0; ed_sub_idx < no_edges_cell; ed_sub_idx++) {
+        const glb_idx_t edge_idx = mesh_->Index(*edges[ed_sub_idx]);
+        const std::size_t edge_int_off = static_cast<std::size_t>(edge_idx) * num_dofs_[kEdgeOrd] + num_ext_dof_edge;
+        if (!check_edge_orientation_ || edge_orientations[ed_sub_idx] == mesh::Orientation::positive) {
+          for (size_type j = 0; j < no_int_dof_edge; j++) dofs_[kCellOrd][off++] = dofs_[kEdgeOrd][edge_int_off + j];
+        } else {
+          // dofhandler.cc:252-258: reversed numbering of the edge-interior dofs
+          for (int j = static_cast<int>(no_int_dof_edge) - 1; j >= 0; j--) dofs_[kCellOrd][off++] = dofs_[kEdgeOrd][edge_int_off + j];
+        }
+      }
+      const size_type num_int = (cell_p->RefElem() == RefEl::kTria()) ? num_loc_dof_tria_ : num_loc_dof_quad_;
+      for (unsigned j = 0; j < num_int; j++) {
+        dofs_[kCellOrd][off++] = dof_idx;
+        dof_entities_.push_back(cell_p);
+        dof_idx++;
+      }
+    }
+    num_dof_ = static_cast<size_type>(dof_idx);
+  }
+
+  std::shared_ptr<const mesh::Mesh> mesh_;
+  size_type num_dof_ = 0;
+  std::array<size_type, 3> num_dofs_{};
+  size_type num_dofs_tria_ = 0, num_dofs_quad_ = 0;
+  size_type num_loc_dof_point_ = 0, num_loc_dof_segment_ = 0, num_loc_dof_tria_ = 0, num_loc_dof_quad_ = 0;
+  bool check_edge_orientation_;
+  std::array<std::vector<gdof_idx_t>, 3> dofs_;
+  std::vector<const mesh::Entity*> dof_entities_;
+};
+
+// Eigen::Triplet<double> : int row, int col, double value (16 bytes)
+struct Triplet {
+  int row, col;
+  double value;
+};
+
+// Compressed column-major matrix with int32 indices == Eigen::SparseMatrix<double> (ColMajor, StorageIndex=int)
+struct CompressedMatrix {
+  long rows = 0, cols = 0;
+  std::vector<int> outer;  // cols + 1
+  std::vector<int> inner;  // nnz, ascending within each column
+  std::vector<double> values;
+};
+
+// lib/lf/assemble/coomatrix.h:52-225
+class COOMatrix {
+ public:
+  COOMatrix(size_type num_rows, size_type num_cols) : rows_(num_rows), cols_(num_cols) {}
+  [[nodiscard]] gdof_idx_t rows() const { return rows_; }
+  [[nodiscard]] gdof_idx_t cols() const { return cols_; }
+  // coomatrix.h:87-91
+  void AddToEntry(gdof_idx_t i, gdof_idx_t j, double increment) {
+    rows_ = (i + 1 > rows_) ? i + 1 : rows_;
+    cols_ = (j + 1 > cols_) ? j + 1 : cols_;
+    triplets_.push_back(Triplet{static_cast<int>(i), static_cast<int>(j), increment});
+  }
+  void setZero() { triplets_.clear(); }
+  [[nodiscard]] const std::vector<Triplet>& triplets() const { return triplets_; }
+
+  // coomatrix.h:172-180 -> Eigen 3.4.0 SparseMatrix::setFromTriplets (set_from_triplets in SparseMatrix.h):
+  //  pass 1 count entries per row; pass 2 fill a ROW-major temporary in triplet order (insertBackUncompressed);
+  //  pass 3 collapseDuplicates: within each row keep the FIRST occurrence of a column and add later duplicates
+  //  to it (sum in insertion order), explicit zeros are kept; pass 4 transposed copy into the column-major result,
+  //  which orders the inner (row) indices of every column ascending.
+  [[nodiscard]] CompressedMatrix makeSparse() const {
+    LFO_VERIFY(rows_ > 0 && cols_ > 0, "matrix has zero rows or columns, this is probably an error.");
+    const long R = rows_, C = cols_;
+    std::vector<int> wi(R, 0);
+    for (const auto& t : triplets_) wi[t.row]++;
+    std::vector<long> rstart(R + 1, 0);
+    for (long r = 0; r < R; ++r) rstart[r + 1] = rstart[r] + wi[r];
+    std::vector<int> tcol(triplets_.size());
+    std::vector<double> tval(triplets_.size());
+    std::vector<long> fill(rstart.begin(), rstart.end() - 1);
+    for (const auto& t : triplets_) {
+      const long p = fill[t.row]++;
+      tcol[p] = t.col;
+      tval[p] = t.value;
+    }
+    // collapseDuplicates
+    std::vector<long> mark(C, -1);
+    std::vector<long> rend(R);
+    long count = 0;
+    std::vector<long> new_rstart(R + 1, 0);
+    for (long r = 0; r < R; ++r) {
+      const long start = count;
+      for (long k = rstart[r]; k < rstart[r + 1]; ++k) {
+        const int c = tcol[k];
+        if (mark[c] >= start) {
+          tval[mark[c]] += tval[k];
+        } else {
+          tval[count] = tval[k];
+          tcol[count] = c;
+          mark[c] = count;
+          ++count;
+        }
+      }
+      new_rstart[r] = start;
+    }
+    new_rstart[R] = count;
+    // transposed copy (row-major temp -> column-major result)
+    CompressedMatrix m;
+    m.rows = R;
+    m.cols = C;
+    m.outer.assign(C + 1, 0);
+    for (long k = 0; k < count; ++k) m.outer[tcol[k] + 1]++;
+    for (long c = 0; c < C; ++c) m.outer[c + 1] += m.outer[c];
+    m.inner.resize(count);
+    m.values.resize(count);
+    std::vector<int> pos(m.outer.begin(), m.outer.end() - 1);
+    for (long r = 0; r < R; ++r) {
+      for (long k = new_rstart[r]; k < new_rstart[r + 1]; ++k) {
+        const int p = pos[tcol[k]]++;
+        m.inner[p] = static_cast<int>(r);
+        m.values[p] = tval[k];
+      }
+    }
+    return m;
+  }
+
+ private:
+  gdof_idx_t rows_, cols_;
+  std::vector<Triplet> triplets_;
+};
+
+// lib/lf/assemble/assembler.h:114-186
+template <typename TMPMATRIX, typename ENTITY_MATRIX_PROVIDER>
+void AssembleMatrixLocally(dim_t codim, const DofHandler& dof_handler_trial, const DofHandler& dof_handler_test,
+                           ENTITY_MATRIX_PROVIDER& entity_matrix_provider, TMPMATRIX& matrix) {
+  auto mesh = dof_handler_trial.Mesh();
+  LFO_VERIFY(mesh == dof_handler_test.Mesh(), "Trial and test space must be defined on the same mesh");
+  for (const mesh::Entity* entity : mesh->Entities(codim)) {
+    if (entity_matrix_provider.isActive(*entity)) {
+      const size_type nrows_loc = dof_handler_test.NumLocalDofs(*entity);
+      const size_type ncols_loc = dof_handler_trial.NumLocalDofs(*entity);
+      std::span<const gdof_idx_t> row_idx(dof_handler_test.GlobalDofIndices(*entity));
+      std::span<const gdof_idx_t> col_idx(dof_handler_trial.GlobalDofIndices(*entity));
+      const auto elem_mat{entity_matrix_provider.Eval(*entity)};
+      for (size_type i = 0; i < nrows_loc; i++) {
+        for (size_type j = 0; j < ncols_loc; j++) matrix.AddToEntry(row_idx[i], col_idx[j], elem_mat(i, j));
+      }
+    }
+  }
+}
+
+// lib/lf/assemble/assembler.h:298-327
+template <typename VECTOR, typename ENTITY_VECTOR_PROVIDER>
+void AssembleVectorLocally(dim_t codim, const DofHandler& dof_handler, ENTITY_VECTOR_PROVIDER& entity_vector_provider,
+                           VECTOR& resultvector) {
+  auto mesh = dof_handler.Mesh();
+  for (const mesh::Entity* entity : mesh->Entities(codim)) {
+    if (entity_vector_provider.isActive(*entity)) {
+      const size_type veclen = dof_handler.NumLocalDofs(*entity);
+      const std::span<const gdof_idx_t> dof_idx(dof_handler.GlobalDofIndices(*entity));
+      const auto elem_vec{entity_vector_provider.Eval(*entity)};
+      for (size_type i = 0; i < veclen; i++) resultvector[dof_idx[i]] += elem_vec[i];
+    }
+  }
+}
+
+}  // namespace lfo::assemble
+#endif

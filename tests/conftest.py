@@ -1,0 +1,25 @@
+import json
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden_meshes():
+    with open(os.path.join(ROOT, "tests", "golden", "test_meshes.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def assembly_goldens():
+    with open(os.path.join(ROOT, "tests", "golden", "assembly_goldens.json")) as f:
+        return json.load(f)
