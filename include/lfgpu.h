@@ -1,0 +1,186 @@
+/* lfgpu.h -- C ABI of liblfgpu.so: B200-native (sm_100a) finite-element assembly behind LehrFEM++'s assembler API.
+ *
+ * The reference (craffael/lehrfempp) has no FFI; its seam for this path is the C++ call
+ *     lf::assemble::AssembleMatrixLocally(codim, dofh_trial, dofh_test, provider, matrix)   lib/lf/assemble/assembler.h:114-186
+ *     lf::assemble::AssembleVectorLocally(codim, dofh, provider, vector)                    lib/lf/assemble/assembler.h:298-327
+ * with the lf::uscalfe providers (lib/lf/uscalfe/loc_comp_ellbvp.h:85-339, 562-746).  Every entry point below names the
+ * reference interface it stands in for.  The header-only C++ shim include/lf_gpu_shim.hpp keeps the reference call
+ * signatures and forwards to these functions; INTEGRATION.md shows the binding a LehrFEM++ maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns every host array; handles own device memory
+ *   - every function returns 0 on success and a negative lfgpu_status otherwise; nothing throws or aborts
+ *     (the shim turns LFGPU_ERR_MISSING_RULE into lf::base::LfException, mirroring loc_comp_ellbvp.h:278-287)
+ *   - one lfgpu_ctx per host thread and GPU; calls on one ctx are issued on its single CUDA stream, in order
+ *   - there is NO CPU fallback: without a CUDA device lfgpu_ctx_create fails with LFGPU_ERR_NO_DEVICE
+ *   - index types follow the reference: entity indices uint32 (lib/lf/base/types.h:20-36, 0xFFFFFFFF = "no 4th vertex"),
+ *     global dof indices int64 on the host side (lib/lf/assemble/assembly_types.h:22), int32 in the compressed
+ *     pattern like Eigen::SparseMatrix<double> (StorageIndex = int, lib/lf/assemble/coomatrix.h:172-180)
+ */
+#ifndef LFGPU_H
+#define LFGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lfgpu_ctx lfgpu_ctx;
+typedef struct lfgpu_mesh lfgpu_mesh;       /* flattened lf::mesh::Mesh (cells, nodes, optional edges) on the device      */
+typedef struct lfgpu_dofmap lfgpu_dofmap;   /* flattened lf::assemble::DofHandler: cell -> global dof table on the device  */
+typedef struct lfgpu_pattern lfgpu_pattern; /* compressed sparsity pattern + scatter/gather plan (symbolic pass result)    */
+
+typedef enum {
+  LFGPU_OK = 0,
+  LFGPU_ERR_INVALID = -1,      /* bad argument                                                        */
+  LFGPU_ERR_CUDA = -2,         /* CUDA runtime error, text in lfgpu_last_error                        */
+  LFGPU_ERR_NO_DEVICE = -3,    /* no CUDA device: there is no CPU fallback                            */
+  LFGPU_ERR_MISSING_RULE = -4, /* no quadrature rule / shape functions for a cell type that occurs    */
+  LFGPU_ERR_DEGENERATE = -5,   /* degenerate cell geometry (tria_o1.cc:10-48, quad_o1.cc:14-59)       */
+  LFGPU_ERR_OVERFLOW = -6,     /* nnz or an index does not fit the reference's int32 storage index    */
+  LFGPU_ERR_UNSUPPORTED = -7,
+  LFGPU_ERR_NCCL = -8
+} lfgpu_status;
+
+#define LFGPU_IDX_NIL 0xFFFFFFFFu
+
+/* storage order of the compressed matrix */
+#define LFGPU_COL_MAJOR 0 /* Eigen::SparseMatrix default = what COOMatrix::makeSparse returns (coomatrix.h:172-180) */
+#define LFGPU_ROW_MAJOR 1 /* CSR */
+
+/* numeric-pass algorithm */
+#define LFGPU_ALGO_AUTO 0
+#define LFGPU_ALGO_ATOMIC 1 /* one thread per (cell, local row), FP64 atomics into the values (supports beta = 1)       */
+#define LFGPU_ALGO_GATHER 2 /* owner-computes: one thread per matrix row gathers its cells, deterministic, no atomics    */
+
+/* ---- context ------------------------------------------------------------------------------------------------------ */
+int lfgpu_ctx_create(int device, lfgpu_ctx** out);
+void lfgpu_ctx_destroy(lfgpu_ctx* ctx);
+const char* lfgpu_last_error(const lfgpu_ctx* ctx); /* ctx may be NULL: last error of the calling thread */
+int lfgpu_ctx_synchronize(lfgpu_ctx* ctx);
+void* lfgpu_ctx_stream(lfgpu_ctx* ctx);       /* the cudaStream_t all work of this ctx is issued on */
+int64_t lfgpu_ctx_kernel_launches(const lfgpu_ctx* ctx); /* number of lfgpu kernels launched so far on this ctx */
+const char* lfgpu_version(void);
+
+/* ---- device memory (plain helpers so that hosts without a CUDA binding can hold results) -------------------------- */
+int lfgpu_malloc(lfgpu_ctx* ctx, int64_t bytes, void** d_ptr);
+int lfgpu_free(lfgpu_ctx* ctx, void* d_ptr);
+int lfgpu_memset(lfgpu_ctx* ctx, void* d_ptr, int value, int64_t bytes);
+int lfgpu_memcpy_h2d(lfgpu_ctx* ctx, void* d_dst, const void* h_src, int64_t bytes); /* async on the ctx stream */
+int lfgpu_memcpy_d2h(lfgpu_ctx* ctx, void* h_dst, const void* d_src, int64_t bytes); /* async on the ctx stream */
+int lfgpu_host_alloc_pinned(lfgpu_ctx* ctx, int64_t bytes, void** h_ptr);
+int lfgpu_host_free_pinned(lfgpu_ctx* ctx, void* h_ptr);
+
+/* ---- mesh: stands in for lf::mesh::Mesh as the assembler sees it -------------------------------------------------- */
+/* Upload a flattened mesh.  cell_nodes is [n_cells][4] with LFGPU_IDX_NIL in slot 3 of a triangle (hybrid2d/
+ * mesh_factory.cc:97-100); cells are in lf::mesh::Mesh::Entities(0) order.  node_coords is [n_nodes][2].
+ * cell_coords ([n_cells][4][2], nullable) are the corners taken from cell.Geometry()->Global(RefEl.NodeCoords());
+ * pass them when they are not bitwise equal to the node positions (e.g. refined meshes, tria_o1.cc:99-151).      */
+int lfgpu_mesh_upload(lfgpu_ctx* ctx, int64_t n_nodes, const double* node_coords, int64_t n_cells,
+                      const uint32_t* cell_nodes, const double* cell_coords, lfgpu_mesh** out);
+/* Device-side mesh generators with the reference's numbering.
+ * tp_tria: lf::mesh::utils::TPTriagMeshBuilder (mesh/utils/tp_triag_mesh_builder.cc:18-178)
+ * tp_quad: lf::mesh::utils::TPQuadMeshBuilder  (mesh/utils/tp_quad_mesh_builder.cc:19-95)
+ * hybrid : synthetic jittered tri/quad mesh of benchmark config C2 (spec in DESIGN.md)                               */
+int lfgpu_mesh_tp_tria(lfgpu_ctx* ctx, uint32_t nx, uint32_t ny, double x0, double y0, double x1, double y1, lfgpu_mesh** out);
+int lfgpu_mesh_tp_quad(lfgpu_ctx* ctx, uint32_t nx, uint32_t ny, double x0, double y0, double x1, double y1, lfgpu_mesh** out);
+int lfgpu_mesh_hybrid(lfgpu_ctx* ctx, uint32_t n, double jitter, uint64_t seed, lfgpu_mesh** out);
+/* Edge numbering and orientations exactly as the lf::mesh::hybrid2d::Mesh constructor assigns them
+ * (mesh/hybrid2d/mesh.cc:178-810): the n_explicit edges (edge_nodes [n][2], nullable) keep their position as index and
+ * their direction; the remaining edges are numbered in ascending (min,max) endpoint order and point along the local
+ * direction of the lowest-index adjacent cell.  Needed by lfgpu_dofmap_uniform when edges carry dofs.
+ * cell_has_geometry (host uint8 [n_cells], nullable = same policy for all cells) mirrors MeshFactory::AddEntity's
+ * optional geometry argument: an edge first met in a cell WITHOUT geometry is reversed when the first later cell WITH
+ * geometry runs along it the other way (mesh.cc:413-428, 532-534).
+ * The tp_tria generator supplies its explicit edge list itself.                                                       */
+int lfgpu_mesh_build_topology(lfgpu_ctx* ctx, lfgpu_mesh* mesh, int64_t n_explicit, const uint32_t* edge_nodes,
+                              const uint8_t* cell_has_geometry);
+int lfgpu_mesh_counts(const lfgpu_mesh* mesh, int64_t* n_nodes, int64_t* n_edges, int64_t* n_cells, int64_t* n_tria, int64_t* n_quad);
+/* every output nullable; layouts as in lfgpu_mesh_upload, cell_edges [n_cells][4], cell_edge_ori int8 [n_cells][4] (+1/-1) */
+int lfgpu_mesh_download(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, uint8_t* cell_type, uint32_t* cell_nodes, double* cell_coords,
+                        uint32_t* cell_edges, int8_t* cell_edge_ori, uint32_t* edge_nodes, double* node_coords);
+/* replace the node positions (per-step input of a moving-mesh / re-assembly loop); host array [n_nodes][2] */
+int lfgpu_mesh_update_node_coords(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const double* node_coords);
+void lfgpu_mesh_destroy(lfgpu_mesh* mesh);
+
+/* ---- dof maps: stand in for lf::assemble::DofHandler (assemble/dofhandler.h:112-228) ------------------------------- */
+/* From any DofHandler: cell_dofs [n_cells][stride] = GlobalDofIndices(cell), n_ldof [n_cells] = NumLocalDofs(cell)
+ * (nullable: then 3/4 * ... is derived as the count of non-negative entries).                                         */
+int lfgpu_dofmap_upload(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, int64_t n_dofs, int stride, const int64_t* cell_dofs,
+                        const uint8_t* n_ldof, lfgpu_dofmap** out);
+/* lf::assemble::UniformFEDofHandler(mesh, {{kPoint,n_pt},{kSegment,n_seg},{kTria,n_tria},{kQuad,n_quad}})
+ * (assemble/dofhandler.cc:86-284), numbered on the device.                                                            */
+int lfgpu_dofmap_uniform(lfgpu_ctx* ctx, lfgpu_mesh* mesh, int n_pt, int n_seg, int n_tria, int n_quad, lfgpu_dofmap** out);
+/* dof layout of lf::uscalfe::FeSpaceLagrangeO{1,2,3} (uscalfe/uniform_scalar_fe_space.h:241-342) */
+int lfgpu_dofmap_lagrange(lfgpu_ctx* ctx, lfgpu_mesh* mesh, int degree, lfgpu_dofmap** out);
+int64_t lfgpu_dofmap_num_dofs(const lfgpu_dofmap* d);
+int lfgpu_dofmap_stride(const lfgpu_dofmap* d);
+int lfgpu_dofmap_download(lfgpu_ctx* ctx, const lfgpu_dofmap* d, int64_t* cell_dofs, uint8_t* n_ldof);
+void lfgpu_dofmap_destroy(lfgpu_dofmap* d);
+
+/* ---- symbolic pass: COOMatrix + makeSparse structure (assemble/coomatrix.h:87-91,172-180) -------------------------- */
+/* Builds the compressed pattern Eigen's setFromTriplets would produce for the triplets AssembleMatrixLocally emits
+ * (one stored entry per (row dof, col dof) pair that shares a cell, explicit zeros kept, inner indices ascending,
+ * int32 indices) plus the per-cell scatter map and the per-row gather lists of the numeric pass.                     */
+int lfgpu_symbolic(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* test, const lfgpu_dofmap* trial, int major,
+                   lfgpu_pattern** out);
+int64_t lfgpu_pattern_nnz(const lfgpu_pattern* p);
+int64_t lfgpu_pattern_rows(const lfgpu_pattern* p);
+int64_t lfgpu_pattern_cols(const lfgpu_pattern* p);
+int lfgpu_pattern_download(lfgpu_ctx* ctx, const lfgpu_pattern* p, int32_t* outer, int32_t* inner);
+const int32_t* lfgpu_pattern_outer_device(const lfgpu_pattern* p);
+const int32_t* lfgpu_pattern_inner_device(const lfgpu_pattern* p);
+void lfgpu_pattern_destroy(lfgpu_pattern* p);
+
+/* ---- numeric pass ---------------------------------------------------------------------------------------------------- */
+/* quadrature rule = lf::quad::QuadRule (quad/quad_rule.h): host arrays, points [2][n] (row 0 = x0, row 1 = x1) */
+typedef struct {
+  int n;
+  const double* points;
+  const double* weights;
+} lfgpu_quad;
+
+/* coefficient = a MeshFunction evaluated at the quadrature points (mesh/utils/mesh_function_traits.h:148-154) */
+#define LFGPU_COEFF_CONST 0        /* MeshFunctionConstant<double>        : c[0]                                     */
+#define LFGPU_COEFF_CONST_2X2 1    /* MeshFunctionConstant<Matrix2d>      : c[0..3] row-major                        */
+#define LFGPU_COEFF_PER_CELL 2     /* data[n_cells]                                                                  */
+#define LFGPU_COEFF_PER_QP 3       /* data[n_cells][stride], value at quadrature point k of the cell's rule          */
+#define LFGPU_COEFF_PER_QP_2X2 4   /* data[n_cells][stride][4] row-major 2x2                                         */
+typedef struct {
+  int kind;
+  double c[4];
+  const double* data; /* DEVICE pointer for PER_* kinds (lfgpu_malloc / any CUDA allocation on the ctx device)      */
+  int64_t stride;     /* values per cell for PER_QP kinds (>= max number of quadrature points)                      */
+} lfgpu_coeff;
+
+/* lf::uscalfe::ReactionDiffusionElementMatrixProvider<double,ALPHA,GAMMA>::Eval (uscalfe/loc_comp_ellbvp.h:266-339)
+ * for every active cell + AssembleMatrixLocally's scatter (assembler.h:166-179), fused.
+ *   degree 1..3 selects FeLagrangeO{1,2,3}{Tria,Quad} (uscalfe/lagr_fe.h); qr_tria / qr_quad NULL = the provider's
+ *   default rule make_QuadRule(ref_el, 2*degree) (loc_comp_ellbvp.h:227-228); active (device uint8 [n_cells],
+ *   nullable) = provider.isActive(cell); beta = 0 overwrites d_values, beta = 1 accumulates like the reference's
+ *   void overload (assembler.h:84-88).  d_values: device array [nnz] in the pattern's order.                        */
+int lfgpu_assemble_reaction_diffusion(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* pattern, int degree,
+                                      const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad, const lfgpu_coeff* alpha,
+                                      const lfgpu_coeff* gamma, const uint8_t* active, double beta, double* d_values,
+                                      int algo);
+/* lf::uscalfe::ScalarLoadElementVectorProvider<double,F>::Eval (loc_comp_ellbvp.h:691-746) + AssembleVectorLocally's
+ * scatter (assembler.h:322-324).  d_vec: device array [n_dofs].                                                      */
+int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* dofmap, int degree,
+                        const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad, const lfgpu_coeff* f, const uint8_t* active,
+                        double beta, double* d_vec, int algo);
+/* global coordinates of every cell's quadrature points, Geometry::Global (tria_o1.cc:70-74, quad_o1.cc:68-83):
+ * d_out device [n_cells][nq_stride][2]; lets a host evaluate MeshFunctionGlobal lambdas into PER_QP tables.         */
+int lfgpu_qp_coords(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, int degree, const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad,
+                    int nq_stride, double* d_out);
+/* tabulated reference element data the numeric pass uses (PrecomputedScalarReferenceFiniteElement,
+ * uscalfe/precomputed_scalar_reference_finite_element.h:72-78): host outputs, phi [nsf][nq], grad [nsf][2*nq]
+ * with columns (2k, 2k+1) = (d/dx0, d/dx1) at point k.  Returns nsf (or <0). cell_type 3 = tria, 4 = quad.          */
+int lfgpu_fe_tabulate(int degree, int cell_type, const lfgpu_quad* qr, double* phi, double* grad);
+/* default rule make_QuadRule(ref_el, degree) (quad/make_quad_rule.cc:21-157): returns n; points [2][n], weights [n] */
+int lfgpu_default_quad_rule(int cell_type, int degree, int capacity, double* points, double* weights);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LFGPU_H */

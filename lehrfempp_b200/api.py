@@ -1,0 +1,445 @@
+"""ctypes binding of include/lfgpu.h (host plumbing; no numerics happen in Python)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+COL_MAJOR, ROW_MAJOR = 0, 1
+ALGO_AUTO, ALGO_ATOMIC, ALGO_GATHER = 0, 1, 2
+NIL = 0xFFFFFFFF
+
+_STATUS = {-1: "INVALID", -2: "CUDA", -3: "NO_DEVICE", -4: "MISSING_RULE", -5: "DEGENERATE", -6: "OVERFLOW",
+           -7: "UNSUPPORTED", -8: "NCCL"}
+
+
+class LfgpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("lfgpu error %s (%d): %s" % (_STATUS.get(code, "?"), code, msg))
+        self.code = code
+
+
+def library_path():
+    return os.path.join(_HERE, "liblfgpu.so")
+
+
+def build_library(force=False):
+    """Compile liblfgpu.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    args = ["make", "-C", os.path.join(_HERE, "csrc"), "-s", "-j8"]
+    if force:
+        subprocess.check_call(args + ["clean"])
+    subprocess.check_call(args)
+    return library_path()
+
+
+class _CQuad(C.Structure):
+    _fields_ = [("n", C.c_int), ("points", C.c_void_p), ("weights", C.c_void_p)]
+
+
+class _CCoeff(C.Structure):
+    _fields_ = [("kind", C.c_int), ("c", C.c_double * 4), ("data", C.c_void_p), ("stride", C.c_int64)]
+
+
+def _lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise ImportError("liblfgpu.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` or "
+                          "`make -C lehrfempp_b200/csrc`. There is no CPU fallback." % path)
+    L = C.CDLL(path)
+    vp, i64, i32, dbl = C.c_void_p, C.c_int64, C.c_int, C.c_double
+    pp = C.POINTER(C.c_void_p)
+    sig = {
+        "lfgpu_ctx_create": (i32, [i32, pp]),
+        "lfgpu_ctx_destroy": (None, [vp]),
+        "lfgpu_last_error": (C.c_char_p, [vp]),
+        "lfgpu_ctx_synchronize": (i32, [vp]),
+        "lfgpu_ctx_stream": (vp, [vp]),
+        "lfgpu_ctx_kernel_launches": (i64, [vp]),
+        "lfgpu_version": (C.c_char_p, []),
+        "lfgpu_malloc": (i32, [vp, i64, pp]),
+        "lfgpu_free": (i32, [vp, vp]),
+        "lfgpu_memset": (i32, [vp, vp, i32, i64]),
+        "lfgpu_memcpy_h2d": (i32, [vp, vp, vp, i64]),
+        "lfgpu_memcpy_d2h": (i32, [vp, vp, vp, i64]),
+        "lfgpu_host_alloc_pinned": (i32, [vp, i64, pp]),
+        "lfgpu_host_free_pinned": (i32, [vp, vp]),
+        "lfgpu_mesh_upload": (i32, [vp, i64, vp, i64, vp, vp, pp]),
+        "lfgpu_mesh_tp_tria": (i32, [vp, C.c_uint32, C.c_uint32, dbl, dbl, dbl, dbl, pp]),
+        "lfgpu_mesh_tp_quad": (i32, [vp, C.c_uint32, C.c_uint32, dbl, dbl, dbl, dbl, pp]),
+        "lfgpu_mesh_hybrid": (i32, [vp, C.c_uint32, dbl, C.c_uint64, pp]),
+        "lfgpu_mesh_build_topology": (i32, [vp, vp, i64, vp, vp]),
+        "lfgpu_mesh_counts": (i32, [vp] + [C.POINTER(i64)] * 5),
+        "lfgpu_mesh_download": (i32, [vp] * 9),
+        "lfgpu_mesh_update_node_coords": (i32, [vp, vp, vp]),
+        "lfgpu_mesh_destroy": (None, [vp]),
+        "lfgpu_dofmap_upload": (i32, [vp, vp, i64, i32, vp, vp, pp]),
+        "lfgpu_dofmap_uniform": (i32, [vp, vp, i32, i32, i32, i32, pp]),
+        "lfgpu_dofmap_lagrange": (i32, [vp, vp, i32, pp]),
+        "lfgpu_dofmap_num_dofs": (i64, [vp]),
+        "lfgpu_dofmap_stride": (i32, [vp]),
+        "lfgpu_dofmap_download": (i32, [vp, vp, vp, vp]),
+        "lfgpu_dofmap_destroy": (None, [vp]),
+        "lfgpu_symbolic": (i32, [vp, vp, vp, vp, i32, pp]),
+        "lfgpu_pattern_nnz": (i64, [vp]),
+        "lfgpu_pattern_rows": (i64, [vp]),
+        "lfgpu_pattern_cols": (i64, [vp]),
+        "lfgpu_pattern_download": (i32, [vp, vp, vp, vp]),
+        "lfgpu_pattern_outer_device": (vp, [vp]),
+        "lfgpu_pattern_inner_device": (vp, [vp]),
+        "lfgpu_pattern_destroy": (None, [vp]),
+        "lfgpu_assemble_reaction_diffusion": (i32, [vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), C.POINTER(_CCoeff),
+                                                    C.POINTER(_CCoeff), vp, dbl, vp, i32]),
+        "lfgpu_assemble_load": (i32, [vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), C.POINTER(_CCoeff), vp, dbl, vp, i32]),
+        "lfgpu_qp_coords": (i32, [vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), i32, vp]),
+        "lfgpu_fe_tabulate": (i32, [i32, i32, C.POINTER(_CQuad), vp, vp]),
+        "lfgpu_default_quad_rule": (i32, [i32, i32, i32, vp, vp]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    L._exported = sorted(sig)
+    _LIB = L
+    return L
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class QuadRule:
+    """lf::quad::QuadRule: points [2][n], weights [n] (host)."""
+
+    def __init__(self, points, weights):
+        self.points = np.ascontiguousarray(points, dtype=np.float64)
+        self.weights = np.ascontiguousarray(weights, dtype=np.float64)
+        assert self.points.shape == (2, self.weights.size)
+        self._c = _CQuad(self.weights.size, self.points.ctypes.data, self.weights.ctypes.data)
+
+    def ref(self):
+        return C.byref(self._c)
+
+
+def _qref(q):
+    return None if q is None else q.ref()
+
+
+def default_quad_rule(cell_type, degree):
+    """make_QuadRule(ref_el, degree) as tabulated inside liblfgpu (host data)."""
+    L = _lib()
+    n = L.lfgpu_default_quad_rule(cell_type, degree, 0, None, None)
+    if n < 0:
+        raise LfgpuError(n, "no such rule")
+    pts = np.zeros((2, n))
+    w = np.zeros(n)
+    L.lfgpu_default_quad_rule(cell_type, degree, n, _p(pts), _p(w))
+    return QuadRule(pts, w)
+
+
+def fe_tabulate(degree, cell_type, qr=None):
+    L = _lib()
+    nsf = {3: (3, 6, 10), 4: (4, 9, 16)}[cell_type][degree - 1]
+    nq = qr.weights.size if qr is not None else default_quad_rule(cell_type, 2 * degree).weights.size
+    phi = np.zeros((nsf, nq))
+    grad = np.zeros((nsf, 2 * nq))
+    rc = L.lfgpu_fe_tabulate(degree, cell_type, _qref(qr), _p(phi), _p(grad))
+    if rc < 0:
+        raise LfgpuError(rc, L.lfgpu_last_error(None).decode())
+    return phi, grad
+
+
+class Coeff:
+    """Coefficient descriptor (a MeshFunction evaluated at the quadrature points)."""
+
+    def __init__(self, kind, c=(0, 0, 0, 0), data=None, stride=0):
+        self._c = _CCoeff(kind=kind)
+        for i in range(4):
+            self._c.c[i] = float(c[i])
+        self._data = data  # keeps the DeviceArray alive
+        self._c.data = data.ptr if data is not None else None
+        self._c.stride = stride
+
+    @staticmethod
+    def const(v):
+        return Coeff(0, (v, 0, 0, 0))
+
+    @staticmethod
+    def const2x2(m):
+        return Coeff(1, tuple(np.asarray(m, dtype=np.float64).reshape(4)))
+
+    @staticmethod
+    def per_cell(dev):
+        return Coeff(2, data=dev, stride=1)
+
+    @staticmethod
+    def per_qp(dev, stride):
+        return Coeff(3, data=dev, stride=stride)
+
+    @staticmethod
+    def per_qp_2x2(dev, stride):
+        return Coeff(4, data=dev, stride=stride)
+
+    def ref(self):
+        return C.byref(self._c)
+
+
+class Context:
+    """One lfgpu_ctx: a GPU, a stream, error state."""
+
+    def __init__(self, device=0):
+        L = _lib()
+        h = C.c_void_p()
+        rc = L.lfgpu_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise LfgpuError(rc, L.lfgpu_last_error(None).decode())
+        self.h = h
+        self.L = L
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.lfgpu_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def check(self, rc):
+        if rc != 0:
+            raise LfgpuError(rc, self.L.lfgpu_last_error(self.h).decode())
+
+    def synchronize(self):
+        self.check(self.L.lfgpu_ctx_synchronize(self.h))
+
+    @property
+    def stream(self):
+        return self.L.lfgpu_ctx_stream(self.h)
+
+    @property
+    def kernel_launches(self):
+        return self.L.lfgpu_ctx_kernel_launches(self.h)
+
+    # ---- memory -----------------------------------------------------------------------------------------------------
+    def empty(self, n, dtype=np.float64):
+        return DeviceArray(self, n, dtype)
+
+    def zeros(self, n, dtype=np.float64):
+        a = DeviceArray(self, n, dtype)
+        self.check(self.L.lfgpu_memset(self.h, a.ptr, 0, a.nbytes))
+        return a
+
+    def to_device(self, arr):
+        arr = np.ascontiguousarray(arr)
+        a = DeviceArray(self, arr.size, arr.dtype)
+        self.check(self.L.lfgpu_memcpy_h2d(self.h, a.ptr, _p(arr), arr.nbytes))
+        self.synchronize()
+        return a
+
+    # ---- meshes -------------------------------------------------------------------------------------------------------
+    def mesh_upload(self, node_coords, cell_nodes, cell_coords=None):
+        node_coords = np.ascontiguousarray(node_coords, dtype=np.float64)
+        cell_nodes = np.ascontiguousarray(cell_nodes, dtype=np.uint32)
+        assert cell_nodes.ndim == 2 and cell_nodes.shape[1] == 4
+        if cell_coords is not None:
+            cell_coords = np.ascontiguousarray(cell_coords, dtype=np.float64)
+        h = C.c_void_p()
+        self.check(self.L.lfgpu_mesh_upload(self.h, node_coords.shape[0], _p(node_coords), cell_nodes.shape[0], _p(cell_nodes),
+                                            _p(cell_coords), C.byref(h)))
+        return Mesh(self, h)
+
+    def mesh_tp_tria(self, nx, ny, x0=0.0, y0=0.0, x1=1.0, y1=1.0):
+        h = C.c_void_p()
+        self.check(self.L.lfgpu_mesh_tp_tria(self.h, nx, ny, x0, y0, x1, y1, C.byref(h)))
+        return Mesh(self, h)
+
+    def mesh_tp_quad(self, nx, ny, x0=0.0, y0=0.0, x1=1.0, y1=1.0):
+        h = C.c_void_p()
+        self.check(self.L.lfgpu_mesh_tp_quad(self.h, nx, ny, x0, y0, x1, y1, C.byref(h)))
+        return Mesh(self, h)
+
+    def mesh_hybrid(self, n, jitter=0.2, seed=12345):
+        h = C.c_void_p()
+        self.check(self.L.lfgpu_mesh_hybrid(self.h, n, jitter, seed, C.byref(h)))
+        return Mesh(self, h)
+
+
+class DeviceArray:
+    def __init__(self, ctx, n, dtype=np.float64):
+        self.ctx = ctx
+        self.n = int(n)
+        self.dtype = np.dtype(dtype)
+        self.nbytes = self.n * self.dtype.itemsize
+        p = C.c_void_p()
+        ctx.check(ctx.L.lfgpu_malloc(ctx.h, self.nbytes, C.byref(p)))
+        self.ptr = p
+
+    def __del__(self):
+        if getattr(self, "ptr", None) and getattr(self.ctx, "h", None):
+            self.ctx.L.lfgpu_free(self.ctx.h, self.ptr)
+            self.ptr = None
+
+    def to_host(self, out=None):
+        if out is None:
+            out = np.empty(self.n, self.dtype)
+        self.ctx.check(self.ctx.L.lfgpu_memcpy_d2h(self.ctx.h, _p(out), self.ptr, self.nbytes))
+        self.ctx.synchronize()
+        return out
+
+    def copy_from_host(self, arr):
+        arr = np.ascontiguousarray(arr, dtype=self.dtype)
+        assert arr.size == self.n
+        self.ctx.check(self.ctx.L.lfgpu_memcpy_h2d(self.ctx.h, self.ptr, _p(arr), self.nbytes))
+        self.ctx.synchronize()
+
+
+class Mesh:
+    def __init__(self, ctx, handle):
+        self.ctx = ctx
+        self.h = handle
+        self._refresh()
+
+    def _refresh(self):
+        v = [C.c_int64() for _ in range(5)]
+        self.ctx.check(self.ctx.L.lfgpu_mesh_counts(self.h, *[C.byref(x) for x in v]))
+        self.n_nodes, self.n_edges, self.n_cells, self.n_tria, self.n_quad = [x.value for x in v]
+
+    def __del__(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.L.lfgpu_mesh_destroy(self.h)
+            self.h = None
+
+    def build_topology(self, edge_nodes=None, cell_has_geometry=None):
+        n = 0
+        if edge_nodes is not None:
+            edge_nodes = np.ascontiguousarray(edge_nodes, dtype=np.uint32)
+            n = edge_nodes.shape[0]
+        if cell_has_geometry is not None:
+            cell_has_geometry = np.ascontiguousarray(cell_has_geometry, dtype=np.uint8)
+            assert cell_has_geometry.size == self.n_cells
+        self.ctx.check(self.ctx.L.lfgpu_mesh_build_topology(self.ctx.h, self.h, n, _p(edge_nodes), _p(cell_has_geometry)))
+        self._refresh()
+
+    def download(self, topology=False):
+        nc, nn = self.n_cells, self.n_nodes
+        out = dict(cell_type=np.zeros(nc, np.uint8), cell_nodes=np.zeros((nc, 4), np.uint32), cell_coords=np.zeros((nc, 4, 2)),
+                   node_coords=np.zeros((nn, 2)))
+        ce = co = en = None
+        if topology:
+            # edge count is known only after numbering: two-step download
+            self.ctx.check(self.ctx.L.lfgpu_mesh_download(self.ctx.h, self.h, None, None, None, _p(np.zeros((nc, 4), np.uint32)),
+                                                          None, None, None))
+            self._refresh()
+            ce = np.zeros((nc, 4), np.uint32)
+            co = np.zeros((nc, 4), np.int8)
+            en = np.zeros((self.n_edges, 2), np.uint32)
+            out.update(cell_edges=ce, cell_edge_ori=co, edge_nodes=en)
+        self.ctx.check(self.ctx.L.lfgpu_mesh_download(self.ctx.h, self.h, _p(out["cell_type"]), _p(out["cell_nodes"]),
+                                                      _p(out["cell_coords"]), _p(ce), _p(co), _p(en), _p(out["node_coords"])))
+        return out
+
+    def update_node_coords(self, xy):
+        xy = np.ascontiguousarray(xy, dtype=np.float64)
+        assert xy.shape == (self.n_nodes, 2)
+        self.ctx.check(self.ctx.L.lfgpu_mesh_update_node_coords(self.ctx.h, self.h, _p(xy)))
+
+    # ---- dof maps ---------------------------------------------------------------------------------------------------
+    def dofmap_uniform(self, n_pt=0, n_seg=0, n_tria=0, n_quad=0):
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.L.lfgpu_dofmap_uniform(self.ctx.h, self.h, n_pt, n_seg, n_tria, n_quad, C.byref(h)))
+        self._refresh()
+        return DofMap(self, h)
+
+    def dofmap_lagrange(self, degree):
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.L.lfgpu_dofmap_lagrange(self.ctx.h, self.h, degree, C.byref(h)))
+        self._refresh()
+        return DofMap(self, h)
+
+    def dofmap_upload(self, n_dofs, cell_dofs, n_ldof=None):
+        cell_dofs = np.ascontiguousarray(cell_dofs, dtype=np.int64)
+        assert cell_dofs.shape[0] == self.n_cells
+        if n_ldof is not None:
+            n_ldof = np.ascontiguousarray(n_ldof, dtype=np.uint8)
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.L.lfgpu_dofmap_upload(self.ctx.h, self.h, n_dofs, cell_dofs.shape[1], _p(cell_dofs), _p(n_ldof),
+                                                      C.byref(h)))
+        return DofMap(self, h)
+
+    def qp_coords(self, degree, nq_stride, qr_tria=None, qr_quad=None):
+        out = self.ctx.empty(self.n_cells * nq_stride * 2)
+        self.ctx.check(self.ctx.L.lfgpu_qp_coords(self.ctx.h, self.h, degree, _qref(qr_tria), _qref(qr_quad), nq_stride, out.ptr))
+        return out
+
+
+class DofMap:
+    def __init__(self, mesh, handle):
+        self.mesh = mesh
+        self.ctx = mesh.ctx
+        self.h = handle
+        self.num_dofs = self.ctx.L.lfgpu_dofmap_num_dofs(self.h)
+        self.stride = self.ctx.L.lfgpu_dofmap_stride(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.L.lfgpu_dofmap_destroy(self.h)
+            self.h = None
+
+    def download(self):
+        d = np.zeros((self.mesh.n_cells, self.stride), np.int64)
+        nl = np.zeros(self.mesh.n_cells, np.uint8)
+        self.ctx.check(self.ctx.L.lfgpu_dofmap_download(self.ctx.h, self.h, _p(d), _p(nl)))
+        return d, nl
+
+    def symbolic(self, trial=None, major=ROW_MAJOR):
+        """Pattern for test = self, trial = `trial` (default: same space)."""
+        trial = trial or self
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.L.lfgpu_symbolic(self.ctx.h, self.mesh.h, self.h, trial.h, major, C.byref(h)))
+        return Pattern(self.mesh, h, major)
+
+    def assemble_load(self, degree, f, qr_tria=None, qr_quad=None, active=None, beta=0.0, out=None):
+        """AssembleVectorLocally(0, dofh, ScalarLoadElementVectorProvider(fe_space, f), vec)."""
+        if out is None:
+            out = self.ctx.zeros(self.num_dofs)
+        self.ctx.check(self.ctx.L.lfgpu_assemble_load(self.ctx.h, self.mesh.h, self.h, degree, _qref(qr_tria), _qref(qr_quad),
+                                                      f.ref(), active.ptr if active is not None else None, beta, out.ptr, ALGO_AUTO))
+        return out
+
+
+class Pattern:
+    def __init__(self, mesh, handle, major):
+        self.mesh = mesh
+        self.ctx = mesh.ctx
+        self.h = handle
+        self.major = major
+        L = self.ctx.L
+        self.nnz = L.lfgpu_pattern_nnz(self.h)
+        self.rows = L.lfgpu_pattern_rows(self.h)
+        self.cols = L.lfgpu_pattern_cols(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.L.lfgpu_pattern_destroy(self.h)
+            self.h = None
+
+    def download(self):
+        n_outer = self.rows if self.major == ROW_MAJOR else self.cols
+        outer = np.zeros(n_outer + 1, np.int32)
+        inner = np.zeros(self.nnz, np.int32)
+        self.ctx.check(self.ctx.L.lfgpu_pattern_download(self.ctx.h, self.h, _p(outer), _p(inner)))
+        return outer, inner
+
+    def assemble_reaction_diffusion(self, degree, alpha, gamma, qr_tria=None, qr_quad=None, active=None, beta=0.0, out=None,
+                                    algo=ALGO_AUTO):
+        """AssembleMatrixLocally(0, dofh, dofh, ReactionDiffusionElementMatrixProvider(fe_space, alpha, gamma[, rules]), M)."""
+        if out is None:
+            out = self.ctx.zeros(self.nnz)
+        self.ctx.check(self.ctx.L.lfgpu_assemble_reaction_diffusion(
+            self.ctx.h, self.mesh.h, self.h, degree, _qref(qr_tria), _qref(qr_quad), alpha.ref(), gamma.ref(),
+            active.ptr if active is not None else None, beta, out.ptr, algo))
+        return out

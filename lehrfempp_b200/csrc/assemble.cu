@@ -1,0 +1,590 @@
+// Numeric pass (product code): fused element computation + scatter into the compressed matrix / load vector.
+//
+// Stands in for (paths relative to lib/lf/):
+//   uscalfe/loc_comp_ellbvp.h:266-339   ReactionDiffusionElementMatrixProvider::Eval
+//        A_K = sum_k w_k |det J_k| [ G_k^T (alpha_k G_k) + gamma_k phi_k phi_k^T ],  G_k = J_k^{-T} grad_hat(Phi)_k^T
+//   uscalfe/loc_comp_ellbvp.h:691-746   ScalarLoadElementVectorProvider::Eval
+//   geometry/tria_o1.cc:50-74, quad_o1.cc:61-158   Jacobian, inverse transposed, |det|, Global
+//   assemble/assembler.h:125-182, 306-326          the cell loop and the local -> global scatter
+//
+// Design (DESIGN.md has the long version): the unit of work is one ROW of one element matrix, (cell, local index a).
+//   * LFGPU_ALGO_ATOMIC : one thread per (cell, a); the row is added into the values with FP64 atomics through the
+//                         scatter map of the symbolic pass.
+//   * LFGPU_ALGO_GATHER : one thread per OUTER index (matrix row for CSR) walks the (cell, a) items of that dof in
+//                         ascending cell order (the reference's summation order), accumulates in a private
+//                         shared-memory strip and writes every stored value exactly once: deterministic, no atomics,
+//                         no zero-fill, no read-modify-write of the value array.
+// Both use the same element-row routine.  Affine cells with cell-wise constant coefficients take the reference-tensor
+// route (5 FMAs per entry); everything else integrates per quadrature point (3 FMAs per entry and point).
+#include <vector>
+
+#include "lfgpu_internal.cuh"
+
+namespace lfgpu {
+namespace {
+
+struct DevCoeff {
+  int kind;
+  double c[4];
+  const double* data;
+  long long stride;
+};
+
+// compact shared-memory image of the reference tables of one cell type
+struct TabView {
+  int nsf, nq;
+  const double *w, *qx, *qy, *phi, *gx, *gy;            // per-qp tables, phi[a * nq + k]
+  const double *k00, *k01, *k10, *k11, *m, *l;          // reference tensors, [a * nsf + b]
+};
+
+struct Tables {
+  // global-memory blob: [header ints][doubles...]; built on the host per call (a few KB)
+  int nsf[2], nq[2];      // index 0 = tria, 1 = quad; nsf = 0 -> no rule / shape functions for that type
+  int off[2];             // offset (in doubles) of each type's block
+  int total;              // total doubles
+};
+
+__device__ __forceinline__ int block_doubles(int nsf, int nq) { return 3 * nq + 3 * nsf * nq + 5 * nsf * nsf + nsf; }
+
+__device__ __forceinline__ TabView make_view(const double* base, int nsf, int nq) {
+  TabView v;
+  v.nsf = nsf;
+  v.nq = nq;
+  v.w = base;
+  v.qx = v.w + nq;
+  v.qy = v.qx + nq;
+  v.phi = v.qy + nq;
+  v.gx = v.phi + nsf * nq;
+  v.gy = v.gx + nsf * nq;
+  v.k00 = v.gy + nsf * nq;
+  v.k01 = v.k00 + nsf * nsf;
+  v.k10 = v.k01 + nsf * nsf;
+  v.k11 = v.k10 + nsf * nsf;
+  v.m = v.k11 + nsf * nsf;
+  v.l = v.m + nsf * nsf;
+  return v;
+}
+
+struct MeshView {
+  const double* node_coords;
+  const uint32_t* cell_nodes;
+  const double* cell_coords;
+};
+
+struct CellGeom {
+  double x[4], y[4];
+  bool quad;
+};
+
+__device__ __forceinline__ CellGeom load_geom(const MeshView& mv, int64_t cell) {
+  CellGeom g;
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(mv.cell_nodes) + cell);
+  g.quad = (v.w != LFGPU_IDX_NIL);
+  if (mv.cell_coords != nullptr) {
+    const double2* cc = reinterpret_cast<const double2*>(mv.cell_coords) + 4 * cell;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double2 p = __ldg(cc + k);
+      g.x[k] = p.x;
+      g.y[k] = p.y;
+    }
+  } else {
+    const double2* nc = reinterpret_cast<const double2*>(mv.node_coords);
+    const double2 p0 = __ldg(nc + v.x), p1 = __ldg(nc + v.y), p2 = __ldg(nc + v.z);
+    g.x[0] = p0.x; g.y[0] = p0.y; g.x[1] = p1.x; g.y[1] = p1.y; g.x[2] = p2.x; g.y[2] = p2.y;
+    if (g.quad) {
+      const double2 p3 = __ldg(nc + v.w);
+      g.x[3] = p3.x; g.y[3] = p3.y;
+    } else {
+      g.x[3] = 0.0; g.y[3] = 0.0;
+    }
+  }
+  return g;
+}
+
+// Jacobian J = [j00 j01; j10 j11] at reference point (x0, x1): tria_o1.cc:57, quad_o1.cc:114-117
+__device__ __forceinline__ void jacobian(const CellGeom& g, double x0, double x1, double& j00, double& j01, double& j10, double& j11) {
+  if (!g.quad) {
+    j00 = g.x[1] - g.x[0]; j01 = g.x[2] - g.x[0];
+    j10 = g.y[1] - g.y[0]; j11 = g.y[2] - g.y[0];
+  } else {
+    j00 = (g.x[1] - g.x[0]) * (1.0 - x1) + (g.x[2] - g.x[3]) * x1;
+    j10 = (g.y[1] - g.y[0]) * (1.0 - x1) + (g.y[2] - g.y[3]) * x1;
+    j01 = (g.x[3] - g.x[0]) * (1.0 - x0) + (g.x[2] - g.x[1]) * x0;
+    j11 = (g.y[3] - g.y[0]) * (1.0 - x0) + (g.y[2] - g.y[1]) * x0;
+  }
+}
+
+// Geometry::Global: tria_o1.cc:70-74, quad_o1.cc:68-83
+__device__ __forceinline__ void global_point(const CellGeom& g, double x0, double x1, double& X, double& Y) {
+  if (!g.quad) {
+    const double l0 = 1.0 - x0 - x1;
+    X = g.x[0] * l0 + g.x[1] * x0 + g.x[2] * x1;
+    Y = g.y[0] * l0 + g.y[1] * x0 + g.y[2] * x1;
+  } else {
+    const double a = (1.0 - x0) * (1.0 - x1), b = x0 * (1.0 - x1), c = x0 * x1, d = (1.0 - x0) * x1;
+    X = g.x[0] * a + g.x[1] * b + g.x[2] * c + g.x[3] * d;
+    Y = g.y[0] * a + g.y[1] * b + g.y[2] * c + g.y[3] * d;
+  }
+}
+
+// 2x2 diffusion tensor at (cell, qp) as used by the row routine: transposed for row-major output (see header)
+__device__ __forceinline__ void eval_alpha(const DevCoeff& A, int64_t cell, int k, bool transpose, double& a00, double& a01, double& a10, double& a11) {
+  switch (A.kind) {
+    case LFGPU_COEFF_CONST:
+      a00 = a11 = A.c[0]; a01 = a10 = 0.0;
+      break;
+    case LFGPU_COEFF_CONST_2X2:
+      a00 = A.c[0]; a01 = A.c[1]; a10 = A.c[2]; a11 = A.c[3];
+      break;
+    case LFGPU_COEFF_PER_CELL:
+      a00 = a11 = __ldg(A.data + cell); a01 = a10 = 0.0;
+      break;
+    case LFGPU_COEFF_PER_QP:
+      a00 = a11 = __ldg(A.data + cell * A.stride + k); a01 = a10 = 0.0;
+      break;
+    default: {  // PER_QP_2X2
+      const double* p = A.data + (cell * A.stride + k) * 4;
+      a00 = __ldg(p); a01 = __ldg(p + 1); a10 = __ldg(p + 2); a11 = __ldg(p + 3);
+    }
+  }
+  if (transpose) {
+    const double t = a01;
+    a01 = a10;
+    a10 = t;
+  }
+}
+__device__ __forceinline__ double eval_scalar(const DevCoeff& G, int64_t cell, int k) {
+  switch (G.kind) {
+    case LFGPU_COEFF_CONST: return G.c[0];
+    case LFGPU_COEFF_PER_CELL: return __ldg(G.data + cell);
+    default: return __ldg(G.data + cell * G.stride + k);  // PER_QP
+  }
+}
+__device__ __forceinline__ bool cellwise_const(const DevCoeff& c) { return c.kind <= LFGPU_COEFF_PER_CELL; }
+
+// Row `a` of the element matrix of `cell` (or column a when alpha is passed untransposed, see header): acc[b], b < nsf
+template <int NSF>
+__device__ __forceinline__ void element_row(const CellGeom& g, const TabView& T, int a, const DevCoeff& alpha, const DevCoeff& gamma,
+                                            int64_t cell, bool transpose_alpha, double (&acc)[NSF]) {
+#pragma unroll
+  for (int b = 0; b < NSF; ++b) acc[b] = 0.0;
+  const int nsf = T.nsf, nq = T.nq;
+  if (!g.quad && cellwise_const(alpha) && cellwise_const(gamma)) {
+    // affine cell, cell-wise constant coefficients: A_K = sum_ij M_ij Khat^{ji} + gamma |det| Mhat
+    double j00, j01, j10, j11;
+    jacobian(g, 0.0, 0.0, j00, j01, j10, j11);
+    const double det = j00 * j11 - j01 * j10;
+    const double adet = fabs(det), idet = 1.0 / det;
+    // Jinv = idet [j11 -j01; -j10 j00]
+    const double i00 = j11 * idet, i01 = -j01 * idet, i10 = -j10 * idet, i11 = j00 * idet;
+    double a00, a01, a10, a11;
+    eval_alpha(alpha, cell, 0, transpose_alpha, a00, a01, a10, a11);
+    // M = |det| Jinv A Jinv^T
+    const double t00 = i00 * a00 + i01 * a10, t01 = i00 * a01 + i01 * a11;
+    const double t10 = i10 * a00 + i11 * a10, t11 = i10 * a01 + i11 * a11;
+    const double m00 = adet * (t00 * i00 + t01 * i01), m01 = adet * (t00 * i10 + t01 * i11);
+    const double m10 = adet * (t10 * i00 + t11 * i01), m11 = adet * (t10 * i10 + t11 * i11);
+    const double gm = adet * eval_scalar(gamma, cell, 0);
+    const int row = a * nsf;
+#pragma unroll
+    for (int b = 0; b < NSF; ++b) {
+      if (b < nsf) {
+        acc[b] = m00 * T.k00[row + b] + m01 * T.k10[row + b] + m10 * T.k01[row + b] + m11 * T.k11[row + b] + gm * T.m[row + b];
+      }
+    }
+    return;
+  }
+  double j00, j01, j10, j11;
+  if (!g.quad) jacobian(g, 0.0, 0.0, j00, j01, j10, j11);
+  for (int k = 0; k < nq; ++k) {
+    if (g.quad) jacobian(g, T.qx[k], T.qy[k], j00, j01, j10, j11);
+    const double det = j00 * j11 - j01 * j10;
+    const double wd = T.w[k] * fabs(det), idet = 1.0 / det;
+    const double i00 = j11 * idet, i01 = -j01 * idet, i10 = -j10 * idet, i11 = j00 * idet;
+    double a00, a01, a10, a11;
+    eval_alpha(alpha, cell, k, transpose_alpha, a00, a01, a10, a11);
+    const double gxa = T.gx[a * nq + k], gya = T.gy[a * nq + k];
+    // G_a = Jinv^T ghat_a ; u = A G_a ; s = wd * Jinv u
+    const double Gx = i00 * gxa + i10 * gya, Gy = i01 * gxa + i11 * gya;
+    const double ux = a00 * Gx + a01 * Gy, uy = a10 * Gx + a11 * Gy;
+    const double sx = wd * (i00 * ux + i01 * uy), sy = wd * (i10 * ux + i11 * uy);
+    const double mm = wd * eval_scalar(gamma, cell, k) * T.phi[a * nq + k];
+#pragma unroll
+    for (int b = 0; b < NSF; ++b) {
+      if (b < nsf) acc[b] += sx * T.gx[b * nq + k] + sy * T.gy[b * nq + k] + mm * T.phi[b * nq + k];
+    }
+  }
+}
+
+// cooperative copy of the table blob into shared memory; returns views
+__device__ __forceinline__ void load_tables(const Tables& hdr, const double* __restrict__ blob, double* smem, TabView& tt, TabView& tq) {
+  for (int i = threadIdx.x; i < hdr.total; i += blockDim.x) smem[i] = blob[i];
+  __syncthreads();
+  tt = make_view(smem + hdr.off[0], hdr.nsf[0], hdr.nq[0]);
+  tq = make_view(smem + hdr.off[1], hdr.nsf[1], hdr.nq[1]);
+}
+
+template <int NSF, typename P>
+__global__ void __launch_bounds__(256) k_assemble_atomic(Tables hdr, const double* __restrict__ blob, MeshView mv, int64_t n_cells,
+                                                         int o_stride, int pos_row, const int32_t* __restrict__ o_dofs,
+                                                         const uint8_t* __restrict__ o_nldof, const int32_t* __restrict__ outer,
+                                                         const P* __restrict__ pos, DevCoeff alpha, DevCoeff gamma,
+                                                         const uint8_t* __restrict__ active, bool transpose_alpha,
+                                                         double* __restrict__ values, int* __restrict__ flags) {
+  extern __shared__ double smem[];
+  TabView tt, tq;
+  load_tables(hdr, blob, smem, tt, tq);
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= n_cells * o_stride) return;
+  const int64_t cell = t / o_stride;
+  const int a = static_cast<int>(t - cell * o_stride);
+  if (a >= o_nldof[cell]) return;
+  if (active != nullptr && active[cell] == 0) return;
+  const CellGeom g = load_geom(mv, cell);
+  const TabView& T = g.quad ? tq : tt;
+  if (T.nsf == 0) {
+    flags[0] = 1;  // no rule / shape functions for this cell type (loc_comp_ellbvp.h:273-287)
+    return;
+  }
+  double acc[NSF];
+  element_row<NSF>(g, T, a, alpha, gamma, cell, transpose_alpha, acc);
+  const int32_t r = o_dofs[t];
+  double* dst = values + outer[r];
+  const P* pp = pos + t * pos_row;
+#pragma unroll
+  for (int b = 0; b < NSF; ++b) {
+    if (b < T.nsf) atomicAdd(dst + pp[b], acc[b]);
+  }
+}
+
+template <int NSF, typename P>
+__global__ void __launch_bounds__(128) k_assemble_gather(Tables hdr, const double* __restrict__ blob, MeshView mv, int64_t n_outer,
+                                                         int o_stride, int pos_row, const int32_t* __restrict__ outer,
+                                                         const int32_t* __restrict__ adj_ptr, const uint32_t* __restrict__ adj,
+                                                         const P* __restrict__ pos, DevCoeff alpha, DevCoeff gamma,
+                                                         const uint8_t* __restrict__ active, bool transpose_alpha, double beta,
+                                                         int acc_rows, double* __restrict__ values, int* __restrict__ flags) {
+  extern __shared__ double smem[];
+  TabView tt, tq;
+  load_tables(hdr, blob, smem, tt, tq);
+  double* strip = smem + ((hdr.total + 1) & ~1) + threadIdx.x;  // private accumulators strip[s * blockDim.x]
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= n_outer) return;
+  const int32_t v0 = outer[r], len = outer[r + 1] - v0;
+  for (int s = 0; s < len; ++s) strip[s * blockDim.x] = 0.0;
+  const int32_t it1 = adj_ptr[r + 1];
+  for (int32_t it = adj_ptr[r]; it < it1; ++it) {
+    const uint32_t item = __ldg(adj + it);
+    const int64_t cell = item >> 4;
+    const int a = static_cast<int>(item & 15U);
+    if (active != nullptr && active[cell] == 0) continue;
+    const CellGeom g = load_geom(mv, cell);
+    const TabView& T = g.quad ? tq : tt;
+    if (T.nsf == 0) {
+      flags[0] = 1;
+      continue;
+    }
+    double acc[NSF];
+    element_row<NSF>(g, T, a, alpha, gamma, cell, transpose_alpha, acc);
+    const P* pp = pos + (cell * o_stride + a) * pos_row;
+#pragma unroll
+    for (int b = 0; b < NSF; ++b) {
+      if (b < T.nsf) strip[static_cast<int>(pp[b]) * blockDim.x] += acc[b];
+    }
+  }
+  double* dst = values + v0;
+  if (beta == 0.0) {
+    for (int s = 0; s < len; ++s) dst[s] = strip[s * blockDim.x];
+  } else {
+    for (int s = 0; s < len; ++s) dst[s] = beta * dst[s] + strip[s * blockDim.x];
+  }
+}
+
+// load vector: one thread per cell, FP64 atomics (assembler.h:322-324)
+template <int NSF>
+__global__ void __launch_bounds__(256) k_load_atomic(Tables hdr, const double* __restrict__ blob, MeshView mv, int64_t n_cells, int stride,
+                                                     const int32_t* __restrict__ dofs, const uint8_t* __restrict__ nldof, DevCoeff f,
+                                                     const uint8_t* __restrict__ active, double* __restrict__ vec, int* __restrict__ flags) {
+  extern __shared__ double smem[];
+  TabView tt, tq;
+  load_tables(hdr, blob, smem, tt, tq);
+  const int64_t cell = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (cell >= n_cells) return;
+  if (active != nullptr && active[cell] == 0) return;
+  const CellGeom g = load_geom(mv, cell);
+  const TabView& T = g.quad ? tq : tt;
+  if (T.nsf == 0) {
+    flags[0] = 1;
+    return;
+  }
+  double acc[NSF];
+#pragma unroll
+  for (int b = 0; b < NSF; ++b) acc[b] = 0.0;
+  double j00, j01, j10, j11;
+  if (!g.quad) jacobian(g, 0.0, 0.0, j00, j01, j10, j11);
+  for (int k = 0; k < T.nq; ++k) {
+    if (g.quad) jacobian(g, T.qx[k], T.qy[k], j00, j01, j10, j11);
+    const double s = T.w[k] * fabs(j00 * j11 - j01 * j10) * eval_scalar(f, cell, k);
+#pragma unroll
+    for (int b = 0; b < NSF; ++b) {
+      if (b < T.nsf) acc[b] += s * T.phi[b * T.nq + k];
+    }
+  }
+  const int n = nldof[cell];
+#pragma unroll
+  for (int b = 0; b < NSF; ++b) {
+    if (b < n) atomicAdd(vec + dofs[cell * stride + b], acc[b]);
+  }
+}
+
+__global__ void k_qp_coords(Tables hdr, const double* __restrict__ blob, MeshView mv, int64_t n_cells, int nq_stride, double* __restrict__ out) {
+  extern __shared__ double smem[];
+  TabView tt, tq;
+  load_tables(hdr, blob, smem, tt, tq);
+  const int64_t cell = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (cell >= n_cells) return;
+  const CellGeom g = load_geom(mv, cell);
+  const TabView& T = g.quad ? tq : tt;
+  for (int k = 0; k < nq_stride; ++k) {
+    double X = 0.0, Y = 0.0;
+    if (k < T.nq) global_point(g, T.qx[k], T.qy[k], X, Y);
+    out[(cell * nq_stride + k) * 2] = X;
+    out[(cell * nq_stride + k) * 2 + 1] = Y;
+  }
+}
+
+__global__ void k_scale(int64_t n, double beta, double* v) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) v[i] *= beta;
+}
+
+// host: pack the tables of both cell types into one blob
+struct HostTables {
+  Tables hdr;
+  std::vector<double> blob;
+};
+
+void pack_type(const FeTable& t, std::vector<double>& blob) {
+  FeTensors ten;
+  build_fe_tensors(t, &ten);
+  const int nsf = t.nsf, nq = t.nq;
+  auto push = [&](const double* p, int n) { blob.insert(blob.end(), p, p + n); };
+  push(t.w, nq);
+  push(t.qx, nq);
+  push(t.qy, nq);
+  push(t.phi, nsf * nq);
+  push(t.gx, nsf * nq);
+  push(t.gy, nsf * nq);
+  push(ten.k00, nsf * nsf);
+  push(ten.k01, nsf * nsf);
+  push(ten.k10, nsf * nsf);
+  push(ten.k11, nsf * nsf);
+  push(ten.m, nsf * nsf);
+  push(ten.l, nsf);
+}
+
+// rule selection as in loc_comp_ellbvp.h:210-263: both null -> default rules for both types; otherwise a type without
+// a supplied rule has no PrecomputedScalarReferenceFiniteElement and Eval fails for such cells
+int make_tables(lfgpu_ctx* ctx, int degree, const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad, HostTables* out) {
+  const bool defaults = (qr_tria == nullptr && qr_quad == nullptr);
+  out->blob.clear();
+  for (int ty = 0; ty < 2; ++ty) {
+    const lfgpu_quad* qr = ty == 0 ? qr_tria : qr_quad;
+    out->hdr.off[ty] = static_cast<int>(out->blob.size());
+    if (!defaults && qr == nullptr) {
+      out->hdr.nsf[ty] = 0;
+      out->hdr.nq[ty] = 0;
+      continue;
+    }
+    FeTable t;
+    std::string err;
+    const int rc = build_fe_table(degree, ty == 0 ? 3 : 4, qr, &t, &err);
+    if (rc < 0) LFGPU_FAIL(ctx, rc, err);
+    out->hdr.nsf[ty] = t.nsf;
+    out->hdr.nq[ty] = t.nq;
+    pack_type(t, out->blob);
+  }
+  out->hdr.total = static_cast<int>(out->blob.size());
+  return LFGPU_OK;
+}
+
+int check_coeff(lfgpu_ctx* ctx, const lfgpu_coeff* c, bool allow_tensor, const HostTables& ht, DevCoeff* out) {
+  if (c == nullptr) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "coefficient descriptor is null");
+  const int maxq = ht.hdr.nq[0] > ht.hdr.nq[1] ? ht.hdr.nq[0] : ht.hdr.nq[1];
+  switch (c->kind) {
+    case LFGPU_COEFF_CONST: break;
+    case LFGPU_COEFF_CONST_2X2:
+      if (!allow_tensor) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "this coefficient must be scalar valued");
+      break;
+    case LFGPU_COEFF_PER_CELL:
+      if (c->data == nullptr) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "PER_CELL coefficient without data");
+      break;
+    case LFGPU_COEFF_PER_QP_2X2:
+      if (!allow_tensor) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "this coefficient must be scalar valued");
+      [[fallthrough]];
+    case LFGPU_COEFF_PER_QP:
+      if (c->data == nullptr || c->stride < maxq) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "PER_QP coefficient: data null or stride < number of quadrature points");
+      break;
+    default: LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "unknown coefficient kind");
+  }
+  out->kind = c->kind;
+  for (int i = 0; i < 4; ++i) out->c[i] = c->c[i];
+  out->data = c->data;
+  out->stride = c->stride;
+  return LFGPU_OK;
+}
+
+struct DeviceBlob {
+  double* d = nullptr;
+  ~DeviceBlob() { cudaFree(d); }
+};
+
+int upload_blob(lfgpu_ctx* ctx, const HostTables& ht, DeviceBlob* b) {
+  LFGPU_CUDA_CHECK(ctx, cudaMalloc(&b->d, sizeof(double) * ht.blob.size()));
+  LFGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d, ht.blob.data(), sizeof(double) * ht.blob.size(), cudaMemcpyHostToDevice, ctx->stream));
+  return LFGPU_OK;
+}
+
+int check_flags(lfgpu_ctx* ctx, int* d_flags) {
+  int h[2] = {0, 0};
+  LFGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(h, d_flags, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  LFGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h[0]) LFGPU_FAIL(ctx, LFGPU_ERR_MISSING_RULE, "No local shape function information or no quadrature rule for a reference element type present in the mesh");
+  return LFGPU_OK;
+}
+
+template <int NSF, typename P>
+int launch_matrix(lfgpu_ctx* ctx, const HostTables& ht, const double* d_blob, const MeshView& mv, const lfgpu_pattern* p,
+                  const DevCoeff& alpha, const DevCoeff& gamma, const uint8_t* active, double beta, double* d_values, int algo,
+                  int* d_flags) {
+  const bool transpose_alpha = (p->major == LFGPU_ROW_MAJOR);
+  const size_t tab_bytes = sizeof(double) * ((ht.hdr.total + 1) & ~1);
+  if (algo == LFGPU_ALGO_ATOMIC) {
+    if (beta == 0.0) {
+      LFGPU_CUDA_CHECK(ctx, cudaMemsetAsync(d_values, 0, sizeof(double) * p->nnz, ctx->stream));
+    } else if (beta != 1.0) {
+      k_scale<<<static_cast<unsigned>(cdiv(p->nnz, 256)), 256, 0, ctx->stream>>>(p->nnz, beta, d_values);
+      LFGPU_LAUNCH_CHECK(ctx);
+    }
+    const int64_t n_threads = p->n_cells * p->o_stride;
+    k_assemble_atomic<NSF, P><<<static_cast<unsigned>(cdiv(n_threads, 256)), 256, tab_bytes, ctx->stream>>>(
+        ht.hdr, d_blob, mv, p->n_cells, p->o_stride, p->pos_row, p->o_dofs, p->o_nldof, p->outer, static_cast<const P*>(p->pos),
+        alpha, gamma, active, transpose_alpha, d_values, d_flags);
+    LFGPU_LAUNCH_CHECK(ctx);
+  } else {
+    const int threads = 128;
+    const size_t smem = tab_bytes + sizeof(double) * static_cast<size_t>(p->max_row_len) * threads;
+    if (smem > 200 * 1024) LFGPU_FAIL(ctx, LFGPU_ERR_UNSUPPORTED, "row too long for the gather kernel; use LFGPU_ALGO_ATOMIC");
+    auto kern = k_assemble_gather<NSF, P>;
+    LFGPU_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<static_cast<unsigned>(cdiv(p->n_outer, threads)), threads, smem, ctx->stream>>>(
+        ht.hdr, d_blob, mv, p->n_outer, p->o_stride, p->pos_row, p->outer, p->adj_ptr, p->adj, static_cast<const P*>(p->pos), alpha,
+        gamma, active, transpose_alpha, beta, p->max_row_len, d_values, d_flags);
+    LFGPU_LAUNCH_CHECK(ctx);
+  }
+  return LFGPU_OK;
+}
+
+}  // namespace
+}  // namespace lfgpu
+
+using namespace lfgpu;
+
+extern "C" {
+
+int lfgpu_assemble_reaction_diffusion(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, int degree,
+                                      const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad, const lfgpu_coeff* alpha,
+                                      const lfgpu_coeff* gamma, const uint8_t* active, double beta, double* d_values, int algo) {
+  if (ctx == nullptr || mesh == nullptr || p == nullptr || d_values == nullptr) return LFGPU_ERR_INVALID;
+  if (degree < 1 || degree > 3) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "degree must be 1, 2 or 3");
+  if (p->n_cells != mesh->n_cells) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "pattern was built for another mesh");
+  LFGPU_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  HostTables ht;
+  int rc = make_tables(ctx, degree, qr_tria, qr_quad, &ht);
+  if (rc != LFGPU_OK) return rc;
+  // the provider's element matrix must cover the dof tables (assembler.h:143-148)
+  // (the table stride is max(tria, quad) even on a pure triangle mesh, dofhandler.cc:138)
+  const int need = nsf_of(degree, 4);
+  if (p->o_stride > need || p->i_stride > need) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "dof tables have more local dofs than the element matrix has rows (nrows mismatch)");
+  DevCoeff da, dg;
+  if ((rc = check_coeff(ctx, alpha, true, ht, &da)) != LFGPU_OK) return rc;
+  if ((rc = check_coeff(ctx, gamma, false, ht, &dg)) != LFGPU_OK) return rc;
+  if (algo == LFGPU_ALGO_AUTO) algo = LFGPU_ALGO_GATHER;
+  if (algo != LFGPU_ALGO_ATOMIC && algo != LFGPU_ALGO_GATHER) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "unknown algo");
+  DeviceBlob blob;
+  if ((rc = upload_blob(ctx, ht, &blob)) != LFGPU_OK) return rc;
+  int* d_flags = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 128);
+  LFGPU_CUDA_CHECK(ctx, cudaMemsetAsync(d_flags, 0, 16, ctx->stream));
+  const MeshView mv{mesh->node_coords, mesh->cell_nodes, mesh->cell_coords};
+  const bool has_quads = mesh->n_quad > 0;
+#define LFGPU_DISPATCH(NSF)                                                                                                      \
+  rc = (p->pos_bytes == 1) ? launch_matrix<NSF, uint8_t>(ctx, ht, blob.d, mv, p, da, dg, active, beta, d_values, algo, d_flags)  \
+                           : launch_matrix<NSF, uint16_t>(ctx, ht, blob.d, mv, p, da, dg, active, beta, d_values, algo, d_flags)
+  switch (degree) {
+    case 1: if (has_quads) { LFGPU_DISPATCH(4); } else { LFGPU_DISPATCH(3); } break;
+    case 2: if (has_quads) { LFGPU_DISPATCH(9); } else { LFGPU_DISPATCH(6); } break;
+    default: if (has_quads) { LFGPU_DISPATCH(16); } else { LFGPU_DISPATCH(10); } break;
+  }
+#undef LFGPU_DISPATCH
+  if (rc != LFGPU_OK) return rc;
+  return check_flags(ctx, d_flags);
+}
+
+int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* dofmap, int degree, const lfgpu_quad* qr_tria,
+                        const lfgpu_quad* qr_quad, const lfgpu_coeff* f, const uint8_t* active, double beta, double* d_vec, int algo) {
+  if (ctx == nullptr || mesh == nullptr || dofmap == nullptr || d_vec == nullptr) return LFGPU_ERR_INVALID;
+  if (degree < 1 || degree > 3) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "degree must be 1, 2 or 3");
+  if (dofmap->n_cells != mesh->n_cells) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "dofmap was built for another mesh");
+  (void)algo;
+  LFGPU_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  HostTables ht;
+  int rc = make_tables(ctx, degree, qr_tria, qr_quad, &ht);
+  if (rc != LFGPU_OK) return rc;
+  DevCoeff df;
+  if ((rc = check_coeff(ctx, f, false, ht, &df)) != LFGPU_OK) return rc;
+  DeviceBlob blob;
+  if ((rc = upload_blob(ctx, ht, &blob)) != LFGPU_OK) return rc;
+  int* d_flags = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 128);
+  LFGPU_CUDA_CHECK(ctx, cudaMemsetAsync(d_flags, 0, 16, ctx->stream));
+  if (beta == 0.0) {
+    LFGPU_CUDA_CHECK(ctx, cudaMemsetAsync(d_vec, 0, sizeof(double) * dofmap->n_dofs, ctx->stream));
+  } else if (beta != 1.0) {
+    k_scale<<<static_cast<unsigned>(cdiv(dofmap->n_dofs, 256)), 256, 0, ctx->stream>>>(dofmap->n_dofs, beta, d_vec);
+    LFGPU_LAUNCH_CHECK(ctx);
+  }
+  const MeshView mv{mesh->node_coords, mesh->cell_nodes, mesh->cell_coords};
+  const size_t tab_bytes = sizeof(double) * ((ht.hdr.total + 1) & ~1);
+  const unsigned grid = static_cast<unsigned>(cdiv(mesh->n_cells, 256));
+  const bool has_quads = mesh->n_quad > 0;
+#define LFGPU_LOAD(NSF)                                                                                                         \
+  k_load_atomic<NSF><<<grid, 256, tab_bytes, ctx->stream>>>(ht.hdr, blob.d, mv, mesh->n_cells, dofmap->stride, dofmap->cell_dofs, \
+                                                            dofmap->n_ldof, df, active, d_vec, d_flags)
+  switch (degree) {
+    case 1: if (has_quads) { LFGPU_LOAD(4); } else { LFGPU_LOAD(3); } break;
+    case 2: if (has_quads) { LFGPU_LOAD(9); } else { LFGPU_LOAD(6); } break;
+    default: if (has_quads) { LFGPU_LOAD(16); } else { LFGPU_LOAD(10); } break;
+  }
+#undef LFGPU_LOAD
+  LFGPU_LAUNCH_CHECK(ctx);
+  return check_flags(ctx, d_flags);
+}
+
+int lfgpu_qp_coords(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, int degree, const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad,
+                    int nq_stride, double* d_out) {
+  if (ctx == nullptr || mesh == nullptr || d_out == nullptr || nq_stride < 1) return LFGPU_ERR_INVALID;
+  LFGPU_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  HostTables ht;
+  int rc = make_tables(ctx, degree, qr_tria, qr_quad, &ht);
+  if (rc != LFGPU_OK) return rc;
+  DeviceBlob blob;
+  if ((rc = upload_blob(ctx, ht, &blob)) != LFGPU_OK) return rc;
+  const MeshView mv{mesh->node_coords, mesh->cell_nodes, mesh->cell_coords};
+  const size_t tab_bytes = sizeof(double) * ((ht.hdr.total + 1) & ~1);
+  k_qp_coords<<<static_cast<unsigned>(cdiv(mesh->n_cells, 256)), 256, tab_bytes, ctx->stream>>>(ht.hdr, blob.d, mv, mesh->n_cells, nq_stride, d_out);
+  LFGPU_LAUNCH_CHECK(ctx);
+  LFGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return LFGPU_OK;
+}
+
+}  // extern "C"

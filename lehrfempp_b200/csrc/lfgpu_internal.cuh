@@ -1,0 +1,134 @@
+// Internal declarations of liblfgpu.so (product code; self-contained, no test infrastructure is included).
+#ifndef LFGPU_INTERNAL_CUH
+#define LFGPU_INTERNAL_CUH
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/lfgpu.h"
+
+namespace lfgpu {
+
+constexpr int kMaxNsf = 16;  // FeLagrangeO3Quad
+constexpr int kMaxNq = 36;   // largest user quadrature rule the tables hold (6x6 Gauss / 33-point triangle rule)
+
+void set_last_error(const lfgpu_ctx* ctx, const std::string& msg);
+
+}  // namespace lfgpu
+
+struct lfgpu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  int64_t launches = 0;
+  std::string last_error;
+  void* d_scratch = nullptr;  // small device scratch (flags, counters)
+};
+
+struct lfgpu_mesh {
+  lfgpu_ctx* ctx = nullptr;
+  int64_t n_nodes = 0, n_cells = 0, n_edges = 0, n_tria = 0, n_quad = 0;
+  double* node_coords = nullptr;    // [n_nodes][2]
+  uint32_t* cell_nodes = nullptr;   // [n_cells][4], NIL padded
+  double* cell_coords = nullptr;    // [n_cells][4][2] or nullptr (corners == node positions)
+  // topology (optional, built by lfgpu_mesh_build_topology / tp generators)
+  bool has_topology = false;
+  uint32_t tp_nx = 0, tp_ny = 0;    // > 0: mesh of the triangle builder, whose explicit edge list is generated on demand
+  uint32_t* edge_nodes = nullptr;   // [n_edges][2] (first, second endpoint)
+  uint32_t* cell_edges = nullptr;   // [n_cells][4]
+  int8_t* cell_edge_ori = nullptr;  // [n_cells][4]
+  // cell-interior dof numbering helper: exclusive prefix counts of triangles / quads before each cell is not stored;
+  // interior dofs are numbered in cell order across both types (dofhandler.cc:263-281), see dofs.cu
+};
+
+struct lfgpu_dofmap {
+  lfgpu_ctx* ctx = nullptr;
+  int64_t n_cells = 0, n_dofs = 0;
+  int stride = 0;
+  int32_t* cell_dofs = nullptr;  // [n_cells][stride], -1 padded (int32: the compressed matrix uses int32 indices)
+  uint8_t* n_ldof = nullptr;     // [n_cells]
+  int max_ldof = 0;
+};
+
+struct lfgpu_pattern {
+  lfgpu_ctx* ctx = nullptr;
+  int major = LFGPU_ROW_MAJOR;
+  int64_t n_outer = 0, n_inner = 0, nnz = 0, n_cells = 0;
+  int32_t* outer = nullptr;  // [n_outer + 1]
+  int32_t* inner = nullptr;  // [nnz]
+  // gather plan: for outer index r the items adj[adj_ptr[r] .. adj_ptr[r+1]) = (cell << 4 | local outer index a),
+  // ascending in cell index (the reference's summation order)
+  int32_t* adj_ptr = nullptr;   // [n_outer + 1]
+  uint32_t* adj = nullptr;      // [n_items]
+  int64_t n_items = 0;
+  // scatter map: position of inner dof b inside the outer segment of outer dof a, for every cell:
+  // pos[(cell * o_stride + a) * pos_row + b]; uint8 when max_row_len <= 256 else uint16
+  int o_stride = 0, i_stride = 0, pos_row = 0, pos_bytes = 1;
+  void* pos = nullptr;
+  int max_row_len = 0;
+  int max_items = 0;  // max number of cells adjacent to one outer dof
+  // dof tables the plan was built from (device copies owned by the pattern)
+  int32_t* o_dofs = nullptr;  // [n_cells][o_stride]
+  int32_t* i_dofs = nullptr;  // [n_cells][i_stride]
+  uint8_t* o_nldof = nullptr;
+  uint8_t* i_nldof = nullptr;
+};
+
+namespace lfgpu {
+
+#define LFGPU_CUDA_CHECK(ctx, expr)                                                                     \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess) {                                                                            \
+      ::lfgpu::set_last_error(ctx, std::string(#expr) + ": " + cudaGetErrorString(_e));                 \
+      return LFGPU_ERR_CUDA;                                                                            \
+    }                                                                                                   \
+  } while (0)
+
+#define LFGPU_FAIL(ctx, code, msg)        \
+  do {                                    \
+    ::lfgpu::set_last_error(ctx, msg);    \
+    return code;                          \
+  } while (0)
+
+#define LFGPU_LAUNCH_CHECK(ctx)                                                         \
+  do {                                                                                  \
+    (ctx)->launches++;                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                \
+    if (_e != cudaSuccess) {                                                            \
+      ::lfgpu::set_last_error(ctx, std::string("kernel launch: ") + cudaGetErrorString(_e)); \
+      return LFGPU_ERR_CUDA;                                                            \
+    }                                                                                   \
+  } while (0)
+
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- reference-element tables (host side, fe_tables.cpp) -----------------------------------------------------------
+struct FeTable {
+  int nsf = 0, nq = 0;
+  double w[kMaxNq];
+  double qx[kMaxNq], qy[kMaxNq];
+  double phi[kMaxNsf * kMaxNq];  // phi[a * nq + k]
+  double gx[kMaxNsf * kMaxNq];   // d/dx0
+  double gy[kMaxNsf * kMaxNq];   // d/dx1
+};
+// reference tensors for affine cells with cell-wise constant coefficients:
+// khat[i][j][a * nsf + b] = sum_k w_k d_i phi_a(k) d_j phi_b(k),  mhat[a * nsf + b] = sum_k w_k phi_a phi_b,
+// lhat[a] = sum_k w_k phi_a
+struct FeTensors {
+  double k00[kMaxNsf * kMaxNsf], k01[kMaxNsf * kMaxNsf], k10[kMaxNsf * kMaxNsf], k11[kMaxNsf * kMaxNsf];
+  double m[kMaxNsf * kMaxNsf];
+  double l[kMaxNsf];
+};
+
+int nsf_of(int degree, int cell_type);
+// returns 0 or a negative status; `qr` may be null (default rule 2*degree)
+int build_fe_table(int degree, int cell_type, const lfgpu_quad* qr, FeTable* out, std::string* err);
+void build_fe_tensors(const FeTable& t, FeTensors* out);
+int default_quad_rule(int cell_type, int degree, int capacity, double* points, double* weights);
+
+}  // namespace lfgpu
+#endif

@@ -1,0 +1,328 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle on the same inputs.
+
+Bars (BASELINE.json north_star): mesh numbering, dof tables and sparsity pattern BIT-EXACT; matrix / vector values
+within 1e-12 relative in max-norm.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import lfo
+from tests.helpers import BUILTIN, per_qp_scalar, per_qp_tensor100, rel_max_err, upload_oracle_mesh
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def lf():
+    import lehrfempp_b200 as lf
+    return lf
+
+
+@pytest.fixture(scope="module")
+def ctx(lf):
+    c = lf.Context(0)
+    yield c
+    c.close()
+
+
+def oracle_mesh(kind, golden_meshes):
+    if kind.startswith("golden"):
+        return lfo.Mesh.from_golden(golden_meshes[kind[6:]])
+    name, n = kind.split(":")
+    n = int(n)
+    if name == "tp_tria":
+        return lfo.Mesh.tp_tria(n, n + 1, 0.25, -0.5, 1.75, 0.5)
+    if name == "tp_quad":
+        return lfo.Mesh.tp_quad(n + 2, n, -1.0, 0.0, 1.0, 3.0)
+    return lfo.Mesh.hybrid(n, 0.2, 12345)
+
+
+def gpu_mesh(ctx, kind, golden_meshes, om):
+    if kind.startswith("golden"):
+        gm = upload_oracle_mesh(ctx, om)[0]
+        entry = golden_meshes[kind[6:]]
+        if "cells" in entry:
+            # same optional-geometry policy as the MeshFactory calls of the fixture (test_meshes.cc)
+            gm.build_topology(cell_has_geometry=[c["coords"] is not None for c in entry["cells"]])
+        else:
+            gm.build_topology(om.export()["edge_nodes"])  # selector 4 is the triangle builder: explicit edges
+        return gm
+    name, n = kind.split(":")
+    n = int(n)
+    if name == "tp_tria":
+        return ctx.mesh_tp_tria(n, n + 1, 0.25, -0.5, 1.75, 0.5)
+    if name == "tp_quad":
+        return ctx.mesh_tp_quad(n + 2, n, -1.0, 0.0, 1.0, 3.0)
+    return ctx.mesh_hybrid(n, 0.2, 12345)
+
+
+MESHES = ["tp_tria:7", "tp_quad:5", "hybrid:9", "hybrid:10", "golden0", "golden1", "golden3", "golden4", "golden5", "golden6", "golden8"]
+
+
+# ---- mesh numbering ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", MESHES)
+def test_mesh_and_topology_bit_exact(ctx, golden_meshes, kind):
+    om = oracle_mesh(kind, golden_meshes)
+    gm = gpu_mesh(ctx, kind, golden_meshes, om)
+    ex = om.export()
+    assert (gm.n_nodes, gm.n_cells, gm.n_tria, gm.n_quad) == (om.n_nodes, om.n_cells, om.n_tria, om.n_quad)
+    d = gm.download(topology=True)
+    assert gm.n_edges == om.n_edges
+    assert np.array_equal(d["cell_nodes"], ex["cell_nodes"])
+    assert np.array_equal(d["cell_type"], ex["cell_type"])
+    assert np.array_equal(d["node_coords"].view(np.uint64), ex["node_coords"].view(np.uint64))  # bitwise
+    assert np.array_equal(d["cell_coords"].view(np.uint64), ex["cell_coords"].view(np.uint64))
+    assert np.array_equal(d["edge_nodes"], ex["edge_nodes"])
+    assert np.array_equal(d["cell_edges"], ex["cell_edges"])
+    assert np.array_equal(d["cell_edge_ori"], ex["cell_edge_ori"])
+
+
+def test_explicit_edges_keep_index_and_direction(ctx):
+    # hybrid2d/mesh.cc:240-274: supplied edges keep their position as index and their orientation
+    om = lfo.Mesh.tp_tria(3, 2)
+    ex = om.export()
+    gm = ctx.mesh_upload(ex["node_coords"], ex["cell_nodes"])
+    gm.build_topology(ex["edge_nodes"][::-1].copy()[:, ::-1].copy())  # reversed list, flipped directions
+    d = gm.download(topology=True)
+    om2 = lfo.Mesh.from_arrays(ex["node_coords"], ex["cell_nodes"], edge_nodes=ex["edge_nodes"][::-1].copy()[:, ::-1].copy())
+    e2 = om2.export()
+    assert np.array_equal(d["edge_nodes"], e2["edge_nodes"])
+    assert np.array_equal(d["cell_edges"], e2["cell_edges"])
+    assert np.array_equal(d["cell_edge_ori"], e2["cell_edge_ori"])
+
+
+def test_partial_explicit_edges(ctx, golden_meshes):
+    om0 = lfo.Mesh.from_golden(golden_meshes["0"])
+    ex = om0.export()
+    some = ex["edge_nodes"][[5, 2, 11]].copy()
+    om = lfo.Mesh.from_arrays(ex["node_coords"], ex["cell_nodes"], edge_nodes=some)
+    e2 = om.export()
+    gm = ctx.mesh_upload(ex["node_coords"], ex["cell_nodes"])
+    gm.build_topology(some)
+    d = gm.download(topology=True)
+    assert np.array_equal(d["edge_nodes"], e2["edge_nodes"])
+    assert np.array_equal(d["cell_edges"], e2["cell_edges"])
+    assert np.array_equal(d["cell_edge_ori"], e2["cell_edge_ori"])
+
+
+def test_degenerate_cell_rejected(ctx, lf):
+    xy = np.array([[0.0, 0.0], [1.0, 0.0], [2.0, 0.0]])
+    cn = np.array([[0, 1, 2, lf.api.NIL]], dtype=np.uint32)
+    with pytest.raises(lf.LfgpuError) as e:
+        ctx.mesh_upload(xy, cn)
+    assert e.value.code == -5
+
+
+# ---- dof handler ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", MESHES)
+@pytest.mark.parametrize("degree", [1, 2, 3])
+def test_lagrange_dofs_bit_exact(ctx, golden_meshes, kind, degree):
+    om = oracle_mesh(kind, golden_meshes)
+    gm = gpu_mesh(ctx, kind, golden_meshes, om)
+    dm = gm.dofmap_lagrange(degree)
+    od, onl = om.cell_dofs(degree)
+    gd, gnl = dm.download()
+    assert dm.num_dofs == om.num_dofs(degree)
+    assert np.array_equal(gnl, onl)
+    assert np.array_equal(gd, od)
+
+
+def test_uniform_two_dofs_per_edge(ctx, golden_meshes):
+    # the layout of the 36x36 golden (assembly_tests.cc:460-470)
+    om = lfo.Mesh.from_golden(golden_meshes["0"])
+    gm = upload_oracle_mesh(ctx, om)[0]
+    dm = gm.dofmap_uniform(n_seg=2)
+    od, onl = lfo.DofHandler(om, n_seg=2).cell_dofs()
+    gd, gnl = dm.download()
+    assert dm.num_dofs == 36
+    assert np.array_equal(gd, od) and np.array_equal(gnl, onl)
+
+
+def test_uploaded_dofmap_roundtrip(ctx, golden_meshes):
+    om = lfo.Mesh.from_golden(golden_meshes["0"])
+    gm = upload_oracle_mesh(ctx, om)[0]
+    od, onl = om.cell_dofs(3)
+    dm = gm.dofmap_upload(om.num_dofs(3), od, onl)
+    gd, gnl = dm.download()
+    assert np.array_equal(gd, od) and np.array_equal(gnl, onl)
+
+
+# ---- pattern + values ------------------------------------------------------------------------------------------------
+def assemble_both(ctx, lf, om, gm, degree, oalpha, ogamma, galpha, ggamma, major, algo, qr=None, active=None, repeat=1):
+    q = -1 if qr is None else qr
+    o_outer, o_inner, o_vals, shape, _ = om.assemble_rd(degree, oalpha, ogamma, qr_tria=q, qr_quad=q, csr=(major == lf.ROW_MAJOR),
+                                                        active=active, repeat=repeat)
+    dm = gm.dofmap_lagrange(degree)
+    pat = dm.symbolic(major=major)
+    qt = qq = None
+    if qr is not None:
+        qt = lf.QuadRule(*lfo.quad_rule(3, qr))
+        qq = lf.QuadRule(*lfo.quad_rule(4, qr))
+    dact = ctx.to_device(np.asarray(active, dtype=np.uint8)) if active is not None else None
+    vals = pat.assemble_reaction_diffusion(degree, galpha, ggamma, qt, qq, active=dact, algo=algo)
+    for _ in range(repeat - 1):
+        pat.assemble_reaction_diffusion(degree, galpha, ggamma, qt, qq, active=dact, beta=1.0, out=vals, algo=algo)
+    g_outer, g_inner = pat.download()
+    return (o_outer, o_inner, o_vals), (g_outer, g_inner, vals.to_host()), shape
+
+
+@pytest.mark.parametrize("kind", MESHES)
+@pytest.mark.parametrize("degree", [1, 2, 3])
+@pytest.mark.parametrize("major", [0, 1])
+def test_pattern_bit_exact_and_values_const(ctx, lf, golden_meshes, kind, degree, major):
+    om = oracle_mesh(kind, golden_meshes)
+    gm = gpu_mesh(ctx, kind, golden_meshes, om)
+    for algo in (lf.ALGO_ATOMIC, lf.ALGO_GATHER):
+        o, g, _ = assemble_both(ctx, lf, om, gm, degree, lfo.coeff.const(1.5), lfo.coeff.const(0.75), lf.Coeff.const(1.5),
+                                lf.Coeff.const(0.75), major, algo)
+        assert np.array_equal(o[0], g[0]), "outer index array differs"
+        assert np.array_equal(o[1], g[1]), "inner index array differs"
+        assert rel_max_err(g[2], o[2]) <= TOL
+
+
+@pytest.mark.parametrize("kind", ["tp_tria:6", "hybrid:8", "golden0", "golden1"])
+@pytest.mark.parametrize("degree", [1, 2, 3])
+@pytest.mark.parametrize("major", [0, 1])
+def test_values_nonsymmetric_tensor_and_variable_coefficients(ctx, lf, golden_meshes, kind, degree, major):
+    om = oracle_mesh(kind, golden_meshes)
+    gm = gpu_mesh(ctx, kind, golden_meshes, om)
+    A = [[3.0, 0.0], [1.0, 2.0]]
+    for algo in (lf.ALGO_ATOMIC, lf.ALGO_GATHER):
+        # constant non-symmetric 2x2 tensor: separates rows from columns
+        o, g, _ = assemble_both(ctx, lf, om, gm, degree, lfo.coeff.const2x2(A), lfo.coeff.const(0.0), lf.Coeff.const2x2(A),
+                                lf.Coeff.const(0.0), major, algo)
+        assert np.array_equal(o[0], g[0]) and np.array_equal(o[1], g[1])
+        assert rel_max_err(g[2], o[2]) <= TOL
+        # alpha = 1 + |x|^2, gamma = 1/(1+|x|^2) evaluated per quadrature point (config C2's coefficients)
+        ga, _ = per_qp_scalar(ctx, gm, degree, 1)
+        gg, _ = per_qp_scalar(ctx, gm, degree, 2)
+        o, g, _ = assemble_both(ctx, lf, om, gm, degree, lfo.coeff.builtin(1), lfo.coeff.builtin(2), ga, gg, major, algo)
+        assert rel_max_err(g[2], o[2]) <= TOL
+        # variable non-symmetric tensor [1 x; y xy] (lagr_fe_tests.cc:818-820)
+        gt = per_qp_tensor100(ctx, gm, degree)
+        gg4, _ = per_qp_scalar(ctx, gm, degree, 4)
+        o, g, _ = assemble_both(ctx, lf, om, gm, degree, lfo.coeff.builtin(100), lfo.coeff.builtin(4), gt, gg4, major, algo)
+        assert rel_max_err(g[2], o[2]) <= TOL
+
+
+def test_reference_bilinear_form_known_answers_on_gpu(ctx, lf, golden_meshes):
+    # lagr_fe_tests.cc:807-882 re-run with the GPU-assembled matrix: 7911/8, 81, 1996731/280
+    om = lfo.Mesh.from_golden(golden_meshes["0"])
+    gm = upload_oracle_mesh(ctx, om)[0]
+    c = lfo.coeff
+    cases = [(1, 4, "tensor", 9, 10, 7911.0 / 8.0), (2, 6, 5, 8, 7, 81.0), (3, 8, 6, 11, 12, 1996731.0 / 280.0)]
+    for degree, qr, alpha, fa, fb, expect in cases:
+        qt = lf.QuadRule(*lfo.quad_rule(3, qr))
+        qq = lf.QuadRule(*lfo.quad_rule(4, qr))
+        if alpha == "tensor":
+            ga = per_qp_tensor100(ctx, gm, degree, qt, qq)
+        else:
+            ga, _ = per_qp_scalar(ctx, gm, degree, alpha, qt, qq)
+        gg, _ = per_qp_scalar(ctx, gm, degree, 4, qt, qq)
+        dm = gm.dofmap_lagrange(degree)
+        pat = dm.symbolic(major=lf.COL_MAJOR)
+        vals = pat.assemble_reaction_diffusion(degree, ga, gg, qt, qq).to_host()
+        outer, inner = pat.download()
+        A = sp.csc_matrix((vals, inner, outer), shape=(pat.rows, pat.cols))
+        av = om.nodal_projection(degree, c.builtin(fa))
+        bv = om.nodal_projection(degree, c.builtin(fb))
+        assert abs(av @ (A @ bv) - expect) < 1e-10 * abs(expect)
+
+
+@pytest.mark.parametrize("degree", [1, 2, 3])
+def test_active_mask_and_accumulate(ctx, lf, golden_meshes, degree):
+    om = oracle_mesh("hybrid:7", golden_meshes)
+    gm = gpu_mesh(ctx, "hybrid:7", golden_meshes, om)
+    rng = np.random.default_rng(5)
+    active = (rng.random(om.n_cells) < 0.6).astype(np.uint8)
+    for algo in (lf.ALGO_ATOMIC, lf.ALGO_GATHER):
+        # isActive (assembler.h:127): inactive cells contribute nothing but the pattern is the full one on the GPU;
+        # the oracle's COO only holds triplets of active cells, so compare as matrices
+        o, g, shape = assemble_both(ctx, lf, om, gm, degree, lfo.coeff.const(1.0), lfo.coeff.const(1.0), lf.Coeff.const(1.0),
+                                    lf.Coeff.const(1.0), lf.ROW_MAJOR, algo, active=active)
+        Ao = sp.csr_matrix((o[2], o[1], o[0]), shape=shape)
+        Ag = sp.csr_matrix((g[2], g[1], g[0]), shape=shape)
+        assert abs(Ao - Ag).max() <= TOL * np.abs(o[2]).max()
+        # accumulate semantics (assembler.h:84-88): assembling twice doubles the entries
+        o, g, _ = assemble_both(ctx, lf, om, gm, degree, lfo.coeff.const(1.0), lfo.coeff.const(1.0), lf.Coeff.const(1.0),
+                                lf.Coeff.const(1.0), lf.ROW_MAJOR, algo, repeat=2)
+        assert rel_max_err(g[2], o[2]) <= TOL
+
+
+def test_missing_rule_is_an_error(ctx, lf, golden_meshes):
+    # loc_comp_test.cc:154-183: only a triangle rule on a hybrid mesh -> LfException in the reference
+    om = lfo.Mesh.from_golden(golden_meshes["0"])
+    gm = upload_oracle_mesh(ctx, om)[0]
+    pat = gm.dofmap_lagrange(1).symbolic()
+    qt = lf.QuadRule(*lfo.quad_rule(3, 2))
+    with pytest.raises(lf.LfgpuError) as e:
+        pat.assemble_reaction_diffusion(1, lf.Coeff.const(1.0), lf.Coeff.const(0.0), qt, None)
+    assert e.value.code == -4
+
+
+# ---- load vector ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["tp_tria:9", "hybrid:8", "golden0", "golden1", "golden6"])
+@pytest.mark.parametrize("degree", [1, 2, 3])
+def test_load_vector(ctx, lf, golden_meshes, kind, degree):
+    om = oracle_mesh(kind, golden_meshes)
+    gm = gpu_mesh(ctx, kind, golden_meshes, om)
+    dm = gm.dofmap_lagrange(degree)
+    gf, _ = per_qp_scalar(ctx, gm, degree, 3)
+    ov, _ = om.assemble_load(degree, lfo.coeff.builtin(3))
+    gv = dm.assemble_load(degree, gf).to_host()
+    assert rel_max_err(gv, ov) <= TOL
+    # constant source, accumulate on top (assembler.h:291-293: the vector is not zeroed)
+    out = dm.assemble_load(degree, lf.Coeff.const(2.0))
+    dm.assemble_load(degree, lf.Coeff.const(2.0), beta=1.0, out=out)
+    ov2, _ = om.assemble_load(degree, lfo.coeff.const(2.0))
+    assert rel_max_err(out.to_host(), 2 * ov2) <= TOL
+
+
+# ---- BASELINE config C1 -----------------------------------------------------------------------------------------------
+def test_config_c1_p1_laplacian_256(ctx, lf):
+    om = lfo.Mesh.tp_tria(256, 256)
+    gm = ctx.mesh_tp_tria(256, 256)
+    dm = gm.dofmap_lagrange(1)
+    for major in (lf.COL_MAJOR, lf.ROW_MAJOR):
+        pat = dm.symbolic(major=major)
+        o_outer, o_inner, o_vals, shape, _ = om.assemble_rd(1, lfo.coeff.const(1.0), lfo.coeff.const(0.0), csr=(major == lf.ROW_MAJOR))
+        outer, inner = pat.download()
+        assert pat.nnz == 460289 and dm.num_dofs == 66049
+        assert np.array_equal(outer, o_outer) and np.array_equal(inner, o_inner)
+        for algo in (lf.ALGO_ATOMIC, lf.ALGO_GATHER):
+            vals = pat.assemble_reaction_diffusion(1, lf.Coeff.const(1.0), lf.Coeff.const(0.0), algo=algo).to_host()
+            assert rel_max_err(vals, o_vals) <= TOL
+            assert (vals == 0.0).sum() >= 2 * 256 * 256  # explicit zeros on the diagonal edges stay in the pattern
+    gf, _ = per_qp_scalar(ctx, gm, 1, 3)
+    ov, _ = om.assemble_load(1, lfo.coeff.builtin(3))
+    assert rel_max_err(dm.assemble_load(1, gf).to_host(), ov) <= TOL
+
+
+# ---- size-independent properties at a larger size ----------------------------------------------------------------------
+@pytest.mark.parametrize("degree,n", [(1, 1500), (2, 600), (3, 300)])
+def test_large_mesh_properties(ctx, lf, degree, n):
+    gm = ctx.mesh_tp_tria(n, n)
+    dm = gm.dofmap_lagrange(degree)
+    pat = dm.symbolic(major=lf.ROW_MAJOR)
+    outer, inner = pat.download()
+    N = dm.num_dofs
+    assert np.all(np.diff(outer) > 0)
+    # inner indices strictly ascending inside every row
+    d = np.diff(inner.astype(np.int64))
+    row_start = np.zeros(inner.size, dtype=bool)
+    row_start[outer[1:-1]] = True
+    assert np.all(d[~row_start[1:]] > 0)
+    stiff = pat.assemble_reaction_diffusion(degree, lf.Coeff.const(1.0), lf.Coeff.const(0.0), algo=lf.ALGO_GATHER).to_host()
+    A = sp.csr_matrix((stiff, inner, outer), shape=(N, N))
+    scale = np.abs(stiff).max()
+    assert np.abs(A @ np.ones(N)).max() <= 1e-11 * scale          # constants are in the kernel (bvp_fe_tests.cc:30-60)
+    assert abs(A - A.T).max() <= 1e-12 * scale                    # symmetric form
+    mass = pat.assemble_reaction_diffusion(degree, lf.Coeff.const(0.0), lf.Coeff.const(1.0), algo=lf.ALGO_GATHER).to_host()
+    assert abs(mass.sum() - 1.0) <= 1e-11                         # sum of the mass matrix = |Omega| (loc_comp_test.cc:46-84)
+    atom = pat.assemble_reaction_diffusion(degree, lf.Coeff.const(1.0), lf.Coeff.const(0.0), algo=lf.ALGO_ATOMIC).to_host()
+    assert rel_max_err(atom, stiff) <= TOL                        # the two scatter strategies agree
+    again = pat.assemble_reaction_diffusion(degree, lf.Coeff.const(1.0), lf.Coeff.const(0.0), algo=lf.ALGO_GATHER).to_host()
+    assert np.array_equal(again, stiff)                           # gather path is deterministic (bitwise repeatable)
