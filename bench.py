@@ -1,0 +1,356 @@
+#!/usr/bin/env python3
+"""bench.py -- cells assembled per second into CSR (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A step is one numeric pass of the hot path (lf::assemble::AssembleMatrixLocally with
+ReactionDiffusionElementMatrixProvider) over the whole mesh of the workload.  Default workload = BASELINE.json
+config 5 at its largest size: P1 Laplacian on the 7071 x 7071 x 2 structured triangle mesh (1.0e8 cells), CSR.
+`value` is timed on the device with CUDA events, inputs resident in HBM; `e2e` goes through the same C-ABI calls with
+the per-step input (node coordinates) coming from pinned host memory and the CSR values returned to pinned host
+memory inside the timed region.  Rank 0 prints ONE JSON line.
+
+--impl reference times the CPU restatement of the reference path (oracle/, single thread as the reference is
+serial) on a bounded sample of the same workload family.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (description, kind, n, degree)
+    "c5_1e8": ("C5: P1 Laplacian (alpha=1, gamma=0), TP-triangle mesh n=7071 (1.0e8 cells), CSR", "tp_tria", 7071, 1),
+    "c5_1e7": ("C5: P1 Laplacian, TP-triangle mesh n=2236 (1.0e7 cells), CSR", "tp_tria", 2236, 1),
+    "c5_1e6": ("C5: P1 Laplacian, TP-triangle mesh n=707 (1.0e6 cells), CSR", "tp_tria", 707, 1),
+    "c1": ("C1: P1 Laplacian, TP-triangle mesh 256x256x2 (131072 cells), CSR", "tp_tria", 256, 1),
+    "c2": ("C2: P1 reaction-diffusion, alpha=1+|x|^2, gamma=1/(1+|x|^2) per quadrature point, hybrid tri/quad mesh n=1633 (4.0e6 cells), CSR", "hybrid", 1633, 1),
+    "c3": ("C3: P2 Laplacian, TP-triangle mesh n=2828 (1.6e7 cells), CSR", "tp_tria", 2828, 2),
+    "c4s": ("C4 (single-GPU size): P3 stiffness+mass, TP-triangle mesh n=1448 (4.2e6 cells), CSR", "tp_tria", 1448, 3),
+}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 7:
+                self.samples.append((time.time(), f))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        sel = [f for (t, f) in self.samples if t0 <= t <= t1] or [f for (_, f) in self.samples]
+        if not sel:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = [float(f[0]) for f in sel if f[0].replace(".", "").isdigit()]
+        mx = [float(f[1]) for f in sel if f[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for f in sel for i in range(4) if f[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sel)}
+
+
+def cpu_reference_sample(n, repeats=1):
+    """CPU restatement of the reference path, single thread: AssembleMatrixLocally -> COO, then makeSparse."""
+    from oracle import lfo
+    m = lfo.Mesh.tp_tria(n, n)
+    best = None
+    for _ in range(repeats):
+        _, _, _, _, t = m.assemble_rd(1, lfo.coeff.const(1.0), lfo.coeff.const(0.0), csr=True)
+        s = t["assemble_s"] + t["makesparse_s"]
+        best = s if best is None else min(best, s)
+    return m.n_cells, best
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    import numpy as np  # noqa: F401
+    from oracle import lfo
+    n = 707  # 1.0e6 triangles: the smallest size of config C5, a bounded sample of the 1e8 workload
+    t_build = time.time()
+    m = lfo.Mesh.tp_tria(n, n)
+    t_build = time.time() - t_build
+    times = []
+    for it in range(args.warmup + args.steps):
+        _, _, _, _, t = m.assemble_rd(1, lfo.coeff.const(1.0), lfo.coeff.const(0.0), csr=True)
+        if it >= args.warmup:
+            times.append(t["assemble_s"] + t["makesparse_s"])
+    sec = sum(times) / len(times)
+    value = m.n_cells / sec
+    sample = "P1 Laplacian on TP-triangle mesh n=707 (%d cells), AssembleMatrixLocally->COO + makeSparse per step" % m.n_cells
+    out = {
+        "impl": "reference", "metric": "cells assembled/sec into CSR", "value": value, "unit": "cells/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload][0], "sample": sample, "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": 1, "kind": "port", "sample": sample,
+                         "note": "CPU restatement of the reference path (oracle/); the reference is serial, so 1 thread is all it can use; "
+                                 "host has %d cores; mesh construction (%.1f s) excluded" % (os.cpu_count(), t_build)},
+        "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c5_1e8", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=0, help="override the mesh parameter n (debugging)")
+    ap.add_argument("--algo", default="gather", choices=["gather", "atomic"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+
+    import lehrfempp_b200 as lf
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    desc, kind, n, degree = WORKLOADS[args.workload]
+    if args.n:
+        n = args.n
+        desc += " [n overridden to %d]" % n
+    ctx = lf.Context(local_rank)
+    algo = lf.ALGO_GATHER if args.algo == "gather" else lf.ALGO_ATOMIC
+
+    # ---- setup (untimed, like mesh / DofHandler construction on the CPU side) ----------------------------------------------
+    t_setup = time.time()
+    if kind == "tp_tria":
+        mesh = ctx.mesh_tp_tria(n, n)
+    else:
+        mesh = ctx.mesh_hybrid(n, 0.2, 12345)
+    dm = mesh.dofmap_lagrange(degree)
+    t_sym = time.time()
+    pat = dm.symbolic(major=lf.ROW_MAJOR)
+    ctx.synchronize()
+    t_sym = time.time() - t_sym
+    if args.workload == "c2":
+        stride = 4
+        xy = mesh.qp_coords(degree, stride).to_host().reshape(mesh.n_cells, stride, 2)
+        r2 = xy[..., 0] ** 2 + xy[..., 1] ** 2
+        alpha = lf.Coeff.per_qp(ctx.to_device(1.0 + r2), stride)
+        gamma = lf.Coeff.per_qp(ctx.to_device(1.0 / (1.0 + r2)), stride)
+        coef_bytes = 2 * 8.0 * (3 * mesh.n_tria + 4 * mesh.n_quad)
+    elif args.workload == "c4s":
+        alpha, gamma, coef_bytes = lf.Coeff.const(1.0), lf.Coeff.const(1.0), 0.0
+    else:
+        alpha, gamma, coef_bytes = lf.Coeff.const(1.0), lf.Coeff.const(0.0), 0.0
+    values = ctx.empty(pat.nnz)
+    t_setup = time.time() - t_setup
+
+    # row partition for N > 1: rank r owns a contiguous block of matrix rows and computes them completely
+    # (owner-computes; every rank holds the mesh, no data-path collective is needed for this partition)
+    rows = None
+    my_rows = pat.rows
+    if world > 1:
+        r0 = (pat.rows * rank) // world
+        r1 = (pat.rows * (rank + 1)) // world
+        rows = ctx.to_device(np.arange(r0, r1, dtype=np.int32))
+        my_rows = r1 - r0
+
+    def step():
+        pat.assemble_reaction_diffusion(degree, alpha, gamma, out=values, algo=algo, rows=rows)
+
+    def barrier():
+        ctx.synchronize()
+        if dist is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ev0, ev1 = ctx.event(), ctx.event()
+    l0 = ctx.kernel_launches
+    t_timed0 = time.time()
+    ctx.record(ev0)
+    for _ in range(args.steps):
+        step()
+    ctx.record(ev1)
+    ms = ctx.elapsed_ms(ev0, ev1)
+    barrier()
+    t_timed1 = time.time()
+    launches = ctx.kernel_launches - l0
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    # keep the GPU busy a little longer so that the clock sampler sees the kernel under load (not part of any number)
+    if rank == 0 and (t_timed1 - t_timed0) < 1.0:
+        t_probe = time.time()
+        while time.time() - t_probe < 1.0:
+            for _ in range(5):
+                step()
+            ctx.synchronize()
+        t_timed1 = time.time()
+
+    # ---- end to end through the C ABI with host buffers ---------------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_xy = ctx.pinned(2 * mesh.n_nodes)
+        d = mesh.download()
+        h_xy[:] = d["node_coords"].ravel()
+        del d
+        if rows is None:
+            h_vals = ctx.pinned(pat.nnz)
+            d2h = lambda: ctx.d2h_async(h_vals, values)  # noqa: E731
+            d2h_bytes = 8 * pat.nnz
+        else:
+            outer, _ = pat.download()
+            v0, v1 = int(outer[r0]), int(outer[r1])
+            h_vals = ctx.pinned(v1 - v0)
+            d2h = lambda: ctx.check(ctx.L.lfgpu_memcpy_d2h(ctx.h, h_vals.ctypes.data, values.ptr.value + 8 * v0, 8 * (v1 - v0)))  # noqa: E731
+            d2h_bytes = 8 * (v1 - v0)
+        e2e_steps = max(3, min(args.steps, 10))
+
+        def e2e_step():
+            mesh.update_node_coords(h_xy.reshape(-1, 2))   # H2D of this step's input (16 B per node)
+            step()                                           # numeric pass
+            d2h()                                            # D2H of the CSR values
+            ctx.synchronize()
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        if dist is not None:
+            t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        h2d_b = 16 * mesh.n_nodes
+        if dist is not None:
+            t = torch.tensor([float(d2h_bytes)], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            d2h_bytes = int(t.item())
+            h2d_b *= world
+        e2e = {"value": mesh.n_cells / e2e_s, "unit": "cells/s", "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_bytes),
+               "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+               "what": "per step: H2D node coordinates (pinned) -> lfgpu_assemble_reaction_diffusion -> D2H CSR values (pinned)"}
+    t_end = time.time()
+    if rank == 0:
+        sampler.stop()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    # algorithmic bytes (SURVEY.md 8d / DESIGN.md): int32 connectivity + each vertex coordinate once + coefficients +
+    # each stored value written once
+    nldof_sum = dm.stride * mesh.n_cells if mesh.n_quad == 0 or mesh.n_tria == 0 else None
+    nsf_t, nsf_q = {1: (3, 4), 2: (6, 9), 3: (10, 16)}[degree]
+    conn = 4.0 * (nsf_t * mesh.n_tria + nsf_q * mesh.n_quad)
+    alg_bytes = conn + 16.0 * mesh.n_nodes + coef_bytes + 8.0 * pat.nnz
+    # per launch (= per rank for N > 1) the kernel covers 1/world of the rows
+    alg_bytes_launch = alg_bytes / world
+    achieved = alg_bytes_launch / (ms_per_step * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            tj = json.load(open(tp)).get(args.workload + ":" + args.algo)
+            if tj:
+                traffic = tj["dram_bytes_per_cell"] * mesh.n_cells / world
+        except Exception:
+            pass
+    out = {
+        "metric": "cells assembled/sec into CSR", "value": mesh.n_cells / (ms_per_step * 1e-3), "unit": "cells/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "cells": mesh.n_cells, "dofs": dm.num_dofs, "nnz": pat.nnz, "degree": degree,
+                   "algo": args.algo, "l2": "inputs+outputs per step (%.2f GB) exceed the 126 MB L2; no explicit flush" % (alg_bytes / 1e9),
+                   "parallelism": "1 GPU" if world == 1 else "row-block owner-computes x%d (mesh replicated, no data-path collective)" % world,
+                   "symbolic_pass_s": round(t_sym, 3), "setup_s": round(t_setup, 3)},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_cell": alg_bytes / mesh.n_cells,
+                     "kernel": "k_assemble_%s" % args.algo},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(t_timed0, max(t_timed1, t_end)),
+    }
+    if e2e is not None:
+        out["e2e"] = e2e
+    if not args.no_cpu_baseline:
+        ncpu = 1000
+        cells, sec = cpu_reference_sample(ncpu)
+        out["cpu_baseline"] = {"value": cells / sec, "unit": "cells/s", "cores": 1, "kind": "port",
+                               "sample": "same operator on TP-triangle mesh n=%d (%d cells): AssembleMatrixLocally->COO + makeSparse, "
+                                         "%.2f s; host has %d cores, the reference is serial" % (ncpu, cells, sec, os.cpu_count())}
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -62,6 +62,11 @@ int lfgpu_ctx_synchronize(lfgpu_ctx* ctx);
 void* lfgpu_ctx_stream(lfgpu_ctx* ctx);       /* the cudaStream_t all work of this ctx is issued on */
 int64_t lfgpu_ctx_kernel_launches(const lfgpu_ctx* ctx); /* number of lfgpu kernels launched so far on this ctx */
 const char* lfgpu_version(void);
+/* CUDA events recorded on the ctx stream: device-side timing of a sequence of calls */
+int lfgpu_event_create(lfgpu_ctx* ctx, void** ev);
+int lfgpu_event_record(lfgpu_ctx* ctx, void* ev);
+int lfgpu_event_elapsed_ms(lfgpu_ctx* ctx, void* start, void* stop, double* ms); /* waits for `stop` */
+int lfgpu_event_destroy(lfgpu_ctx* ctx, void* ev);
 
 /* ---- device memory (plain helpers so that hosts without a CUDA binding can hold results) -------------------------- */
 int lfgpu_malloc(lfgpu_ctx* ctx, int64_t bytes, void** d_ptr);
@@ -164,6 +169,12 @@ int lfgpu_assemble_reaction_diffusion(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, co
                                       const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad, const lfgpu_coeff* alpha,
                                       const lfgpu_coeff* gamma, const uint8_t* active, double beta, double* d_values,
                                       int algo);
+/* Same, restricted to the outer indices (matrix rows for LFGPU_ROW_MAJOR) listed in d_row_list (device int32 [n_rows]);
+ * only those rows of d_values are written.  Building block of the multi-GPU row partition.  LFGPU_ALGO_GATHER only.    */
+int lfgpu_assemble_reaction_diffusion_rows(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* pattern, int degree,
+                                           const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad, const lfgpu_coeff* alpha,
+                                           const lfgpu_coeff* gamma, const uint8_t* active, double beta, double* d_values,
+                                           int algo, const int32_t* d_row_list, int64_t n_rows);
 /* lf::uscalfe::ScalarLoadElementVectorProvider<double,F>::Eval (loc_comp_ellbvp.h:691-746) + AssembleVectorLocally's
  * scatter (assembler.h:322-324).  d_vec: device array [n_dofs].                                                      */
 int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* dofmap, int degree,

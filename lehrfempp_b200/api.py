@@ -62,6 +62,10 @@ def _lib():
         "lfgpu_ctx_stream": (vp, [vp]),
         "lfgpu_ctx_kernel_launches": (i64, [vp]),
         "lfgpu_version": (C.c_char_p, []),
+        "lfgpu_event_create": (i32, [vp, pp]),
+        "lfgpu_event_record": (i32, [vp, vp]),
+        "lfgpu_event_elapsed_ms": (i32, [vp, vp, vp, C.POINTER(dbl)]),
+        "lfgpu_event_destroy": (i32, [vp, vp]),
         "lfgpu_malloc": (i32, [vp, i64, pp]),
         "lfgpu_free": (i32, [vp, vp]),
         "lfgpu_memset": (i32, [vp, vp, i32, i64]),
@@ -95,6 +99,8 @@ def _lib():
         "lfgpu_pattern_destroy": (None, [vp]),
         "lfgpu_assemble_reaction_diffusion": (i32, [vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), C.POINTER(_CCoeff),
                                                     C.POINTER(_CCoeff), vp, dbl, vp, i32]),
+        "lfgpu_assemble_reaction_diffusion_rows": (i32, [vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), C.POINTER(_CCoeff),
+                                                         C.POINTER(_CCoeff), vp, dbl, vp, i32, vp, i64]),
         "lfgpu_assemble_load": (i32, [vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), C.POINTER(_CCoeff), vp, dbl, vp, i32]),
         "lfgpu_qp_coords": (i32, [vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), i32, vp]),
         "lfgpu_fe_tabulate": (i32, [i32, i32, C.POINTER(_CQuad), vp, vp]),
@@ -203,6 +209,9 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
+            for p in getattr(self, "_pinned", []):
+                self.L.lfgpu_host_free_pinned(self.h, p)
+            self._pinned = []
             self.L.lfgpu_ctx_destroy(self.h)
             self.h = None
 
@@ -223,6 +232,36 @@ class Context:
     @property
     def kernel_launches(self):
         return self.L.lfgpu_ctx_kernel_launches(self.h)
+
+    # ---- timing -----------------------------------------------------------------------------------------------------
+    def event(self):
+        e = C.c_void_p()
+        self.check(self.L.lfgpu_event_create(self.h, C.byref(e)))
+        return e
+
+    def record(self, ev):
+        self.check(self.L.lfgpu_event_record(self.h, ev))
+
+    def elapsed_ms(self, start, stop):
+        ms = C.c_double()
+        self.check(self.L.lfgpu_event_elapsed_ms(self.h, start, stop, C.byref(ms)))
+        return ms.value
+
+    def pinned(self, n, dtype=np.float64):
+        """numpy view of a page-locked host buffer (freed with the context)."""
+        dtype = np.dtype(dtype)
+        p = C.c_void_p()
+        self.check(self.L.lfgpu_host_alloc_pinned(self.h, int(n) * dtype.itemsize, C.byref(p)))
+        buf = (C.c_char * (int(n) * dtype.itemsize)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(n))
+        self._pinned = getattr(self, "_pinned", []) + [p]
+        return arr
+
+    def h2d_async(self, dev, host):
+        self.check(self.L.lfgpu_memcpy_h2d(self.h, dev.ptr, _p(host), host.nbytes))
+
+    def d2h_async(self, host, dev):
+        self.check(self.L.lfgpu_memcpy_d2h(self.h, _p(host), dev.ptr, host.nbytes))
 
     # ---- memory -----------------------------------------------------------------------------------------------------
     def empty(self, n, dtype=np.float64):
@@ -435,11 +474,14 @@ class Pattern:
         return outer, inner
 
     def assemble_reaction_diffusion(self, degree, alpha, gamma, qr_tria=None, qr_quad=None, active=None, beta=0.0, out=None,
-                                    algo=ALGO_AUTO):
-        """AssembleMatrixLocally(0, dofh, dofh, ReactionDiffusionElementMatrixProvider(fe_space, alpha, gamma[, rules]), M)."""
+                                    algo=ALGO_AUTO, rows=None):
+        """AssembleMatrixLocally(0, dofh, dofh, ReactionDiffusionElementMatrixProvider(fe_space, alpha, gamma[, rules]), M).
+
+        rows: optional DeviceArray(int32) of outer indices to compute (row partition of a multi-GPU run)."""
         if out is None:
             out = self.ctx.zeros(self.nnz)
-        self.ctx.check(self.ctx.L.lfgpu_assemble_reaction_diffusion(
+        self.ctx.check(self.ctx.L.lfgpu_assemble_reaction_diffusion_rows(
             self.ctx.h, self.mesh.h, self.h, degree, _qref(qr_tria), _qref(qr_quad), alpha.ref(), gamma.ref(),
-            active.ptr if active is not None else None, beta, out.ptr, algo))
+            active.ptr if active is not None else None, beta, out.ptr, algo, rows.ptr if rows is not None else None,
+            rows.n if rows is not None else 0))
         return out

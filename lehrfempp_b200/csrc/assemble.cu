@@ -264,13 +264,15 @@ __global__ void __launch_bounds__(128) k_assemble_gather(Tables hdr, const doubl
                                                          const int32_t* __restrict__ adj_ptr, const uint32_t* __restrict__ adj,
                                                          const P* __restrict__ pos, DevCoeff alpha, DevCoeff gamma,
                                                          const uint8_t* __restrict__ active, bool transpose_alpha, double beta,
-                                                         int acc_rows, double* __restrict__ values, int* __restrict__ flags) {
+                                                         const int32_t* __restrict__ row_list, double* __restrict__ values,
+                                                         int* __restrict__ flags) {
   extern __shared__ double smem[];
   TabView tt, tq;
   load_tables(hdr, blob, smem, tt, tq);
   double* strip = smem + ((hdr.total + 1) & ~1) + threadIdx.x;  // private accumulators strip[s * blockDim.x]
-  const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (r >= n_outer) return;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= n_outer) return;  // n_outer = number of rows to process
+  const int64_t r = row_list != nullptr ? row_list[t] : t;
   const int32_t v0 = outer[r], len = outer[r + 1] - v0;
   for (int s = 0; s < len; ++s) strip[s * blockDim.x] = 0.0;
   const int32_t it1 = adj_ptr[r + 1];
@@ -436,28 +438,44 @@ int check_coeff(lfgpu_ctx* ctx, const lfgpu_coeff* c, bool allow_tensor, const H
 }
 
 struct DeviceBlob {
-  double* d = nullptr;
-  ~DeviceBlob() { cudaFree(d); }
+  double* d = nullptr;  // owned by the ctx table cache
 };
 
+// The tables are a few KB and rarely change between calls: keep the last few on the device, keyed by content, so that a
+// numeric call is a single kernel launch (no allocation, no synchronisation).
 int upload_blob(lfgpu_ctx* ctx, const HostTables& ht, DeviceBlob* b) {
-  LFGPU_CUDA_CHECK(ctx, cudaMalloc(&b->d, sizeof(double) * ht.blob.size()));
-  LFGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d, ht.blob.data(), sizeof(double) * ht.blob.size(), cudaMemcpyHostToDevice, ctx->stream));
+  for (auto& e : ctx->table_cache) {
+    if (e.host == ht.blob) {
+      b->d = e.dev;
+      return LFGPU_OK;
+    }
+  }
+  if (ctx->table_cache.size() >= 8) {
+    LFGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& e : ctx->table_cache) cudaFree(e.dev);
+    ctx->table_cache.clear();
+  }
+  double* d = nullptr;
+  LFGPU_CUDA_CHECK(ctx, cudaMalloc(&d, sizeof(double) * ht.blob.size()));
+  ctx->table_cache.push_back({ht.blob, d});
+  // source = the cache's own copy, which outlives the asynchronous transfer
+  LFGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(d, ctx->table_cache.back().host.data(), sizeof(double) * ht.blob.size(), cudaMemcpyHostToDevice, ctx->stream));
+  b->d = d;
   return LFGPU_OK;
 }
 
-int check_flags(lfgpu_ctx* ctx, int* d_flags) {
-  int h[2] = {0, 0};
-  LFGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(h, d_flags, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-  LFGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-  if (h[0]) LFGPU_FAIL(ctx, LFGPU_ERR_MISSING_RULE, "No local shape function information or no quadrature rule for a reference element type present in the mesh");
+// loc_comp_ellbvp.h:273-287: a cell type that occurs in the mesh but has no rule / shape functions is an error.
+// Decided on the host from the mesh's cell-type counts, so the numeric call never has to synchronise.
+int check_rules(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const HostTables& ht) {
+  if ((mesh->n_tria > 0 && ht.hdr.nsf[0] == 0) || (mesh->n_quad > 0 && ht.hdr.nsf[1] == 0))
+    LFGPU_FAIL(ctx, LFGPU_ERR_MISSING_RULE, "No local shape function information or no quadrature rule for a reference element type present in the mesh");
   return LFGPU_OK;
 }
 
 template <int NSF, typename P>
 int launch_matrix(lfgpu_ctx* ctx, const HostTables& ht, const double* d_blob, const MeshView& mv, const lfgpu_pattern* p,
                   const DevCoeff& alpha, const DevCoeff& gamma, const uint8_t* active, double beta, double* d_values, int algo,
-                  int* d_flags) {
+                  int* d_flags, const int32_t* row_list, int64_t n_rows) {
   const bool transpose_alpha = (p->major == LFGPU_ROW_MAJOR);
   const size_t tab_bytes = sizeof(double) * ((ht.hdr.total + 1) & ~1);
   if (algo == LFGPU_ALGO_ATOMIC) {
@@ -478,9 +496,12 @@ int launch_matrix(lfgpu_ctx* ctx, const HostTables& ht, const double* d_blob, co
     if (smem > 200 * 1024) LFGPU_FAIL(ctx, LFGPU_ERR_UNSUPPORTED, "row too long for the gather kernel; use LFGPU_ALGO_ATOMIC");
     auto kern = k_assemble_gather<NSF, P>;
     LFGPU_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kern<<<static_cast<unsigned>(cdiv(p->n_outer, threads)), threads, smem, ctx->stream>>>(
-        ht.hdr, d_blob, mv, p->n_outer, p->o_stride, p->pos_row, p->outer, p->adj_ptr, p->adj, static_cast<const P*>(p->pos), alpha,
-        gamma, active, transpose_alpha, beta, p->max_row_len, d_values, d_flags);
+    const int64_t rows = row_list != nullptr ? n_rows : p->n_outer;
+    if (rows > 0) {
+      kern<<<static_cast<unsigned>(cdiv(rows, threads)), threads, smem, ctx->stream>>>(
+          ht.hdr, d_blob, mv, rows, p->o_stride, p->pos_row, p->outer, p->adj_ptr, p->adj, static_cast<const P*>(p->pos), alpha,
+          gamma, active, transpose_alpha, beta, row_list, d_values, d_flags);
+    }
     LFGPU_LAUNCH_CHECK(ctx);
   }
   return LFGPU_OK;
@@ -496,6 +517,14 @@ extern "C" {
 int lfgpu_assemble_reaction_diffusion(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, int degree,
                                       const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad, const lfgpu_coeff* alpha,
                                       const lfgpu_coeff* gamma, const uint8_t* active, double beta, double* d_values, int algo) {
+  return lfgpu_assemble_reaction_diffusion_rows(ctx, mesh, p, degree, qr_tria, qr_quad, alpha, gamma, active, beta, d_values, algo,
+                                                nullptr, 0);
+}
+
+int lfgpu_assemble_reaction_diffusion_rows(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, int degree,
+                                           const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad, const lfgpu_coeff* alpha,
+                                           const lfgpu_coeff* gamma, const uint8_t* active, double beta, double* d_values,
+                                           int algo, const int32_t* d_row_list, int64_t n_rows) {
   if (ctx == nullptr || mesh == nullptr || p == nullptr || d_values == nullptr) return LFGPU_ERR_INVALID;
   if (degree < 1 || degree > 3) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "degree must be 1, 2 or 3");
   if (p->n_cells != mesh->n_cells) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "pattern was built for another mesh");
@@ -512,23 +541,23 @@ int lfgpu_assemble_reaction_diffusion(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, co
   if ((rc = check_coeff(ctx, gamma, false, ht, &dg)) != LFGPU_OK) return rc;
   if (algo == LFGPU_ALGO_AUTO) algo = LFGPU_ALGO_GATHER;
   if (algo != LFGPU_ALGO_ATOMIC && algo != LFGPU_ALGO_GATHER) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "unknown algo");
+  if (d_row_list != nullptr && algo != LFGPU_ALGO_GATHER) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "a row list needs LFGPU_ALGO_GATHER");
+  if ((rc = check_rules(ctx, mesh, ht)) != LFGPU_OK) return rc;
   DeviceBlob blob;
   if ((rc = upload_blob(ctx, ht, &blob)) != LFGPU_OK) return rc;
   int* d_flags = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 128);
-  LFGPU_CUDA_CHECK(ctx, cudaMemsetAsync(d_flags, 0, 16, ctx->stream));
   const MeshView mv{mesh->node_coords, mesh->cell_nodes, mesh->cell_coords};
   const bool has_quads = mesh->n_quad > 0;
 #define LFGPU_DISPATCH(NSF)                                                                                                      \
-  rc = (p->pos_bytes == 1) ? launch_matrix<NSF, uint8_t>(ctx, ht, blob.d, mv, p, da, dg, active, beta, d_values, algo, d_flags)  \
-                           : launch_matrix<NSF, uint16_t>(ctx, ht, blob.d, mv, p, da, dg, active, beta, d_values, algo, d_flags)
+  rc = (p->pos_bytes == 1) ? launch_matrix<NSF, uint8_t>(ctx, ht, blob.d, mv, p, da, dg, active, beta, d_values, algo, d_flags, d_row_list, n_rows)  \
+                           : launch_matrix<NSF, uint16_t>(ctx, ht, blob.d, mv, p, da, dg, active, beta, d_values, algo, d_flags, d_row_list, n_rows)
   switch (degree) {
     case 1: if (has_quads) { LFGPU_DISPATCH(4); } else { LFGPU_DISPATCH(3); } break;
     case 2: if (has_quads) { LFGPU_DISPATCH(9); } else { LFGPU_DISPATCH(6); } break;
     default: if (has_quads) { LFGPU_DISPATCH(16); } else { LFGPU_DISPATCH(10); } break;
   }
 #undef LFGPU_DISPATCH
-  if (rc != LFGPU_OK) return rc;
-  return check_flags(ctx, d_flags);
+  return rc;
 }
 
 int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* dofmap, int degree, const lfgpu_quad* qr_tria,
@@ -543,10 +572,10 @@ int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofm
   if (rc != LFGPU_OK) return rc;
   DevCoeff df;
   if ((rc = check_coeff(ctx, f, false, ht, &df)) != LFGPU_OK) return rc;
+  if ((rc = check_rules(ctx, mesh, ht)) != LFGPU_OK) return rc;
   DeviceBlob blob;
   if ((rc = upload_blob(ctx, ht, &blob)) != LFGPU_OK) return rc;
   int* d_flags = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 128);
-  LFGPU_CUDA_CHECK(ctx, cudaMemsetAsync(d_flags, 0, 16, ctx->stream));
   if (beta == 0.0) {
     LFGPU_CUDA_CHECK(ctx, cudaMemsetAsync(d_vec, 0, sizeof(double) * dofmap->n_dofs, ctx->stream));
   } else if (beta != 1.0) {
@@ -567,7 +596,7 @@ int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofm
   }
 #undef LFGPU_LOAD
   LFGPU_LAUNCH_CHECK(ctx);
-  return check_flags(ctx, d_flags);
+  return LFGPU_OK;
 }
 
 int lfgpu_qp_coords(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, int degree, const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad,

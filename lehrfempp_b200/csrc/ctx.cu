@@ -54,6 +54,7 @@ void lfgpu_ctx_destroy(lfgpu_ctx* ctx) {
   if (ctx == nullptr) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  for (auto& e : ctx->table_cache) cudaFree(e.dev);
   cudaFree(ctx->d_scratch);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -72,6 +73,33 @@ int lfgpu_ctx_synchronize(lfgpu_ctx* ctx) {
 
 void* lfgpu_ctx_stream(lfgpu_ctx* ctx) { return ctx ? static_cast<void*>(ctx->stream) : nullptr; }
 int64_t lfgpu_ctx_kernel_launches(const lfgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- timing on the ctx stream (CUDA events) ------------------------------------------------------------------------------
+int lfgpu_event_create(lfgpu_ctx* ctx, void** ev) {
+  if (ctx == nullptr || ev == nullptr) return LFGPU_ERR_INVALID;
+  cudaEvent_t e;
+  LFGPU_CUDA_CHECK(ctx, cudaEventCreate(&e));
+  *ev = e;
+  return LFGPU_OK;
+}
+int lfgpu_event_record(lfgpu_ctx* ctx, void* ev) {
+  if (ctx == nullptr || ev == nullptr) return LFGPU_ERR_INVALID;
+  LFGPU_CUDA_CHECK(ctx, cudaEventRecord(static_cast<cudaEvent_t>(ev), ctx->stream));
+  return LFGPU_OK;
+}
+int lfgpu_event_elapsed_ms(lfgpu_ctx* ctx, void* start, void* stop, double* ms) {
+  if (ctx == nullptr || ms == nullptr) return LFGPU_ERR_INVALID;
+  LFGPU_CUDA_CHECK(ctx, cudaEventSynchronize(static_cast<cudaEvent_t>(stop)));
+  float f = 0.f;
+  LFGPU_CUDA_CHECK(ctx, cudaEventElapsedTime(&f, static_cast<cudaEvent_t>(start), static_cast<cudaEvent_t>(stop)));
+  *ms = f;
+  return LFGPU_OK;
+}
+int lfgpu_event_destroy(lfgpu_ctx* ctx, void* ev) {
+  if (ctx == nullptr) return LFGPU_ERR_INVALID;
+  LFGPU_CUDA_CHECK(ctx, cudaEventDestroy(static_cast<cudaEvent_t>(ev)));
+  return LFGPU_OK;
+}
 
 int lfgpu_malloc(lfgpu_ctx* ctx, int64_t bytes, void** d_ptr) {
   if (ctx == nullptr || d_ptr == nullptr || bytes < 0) return LFGPU_ERR_INVALID;

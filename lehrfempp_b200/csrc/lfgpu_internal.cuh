@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <vector>
 
 #include "../../include/lfgpu.h"
 
@@ -26,6 +27,11 @@ struct lfgpu_ctx {
   int64_t launches = 0;
   std::string last_error;
   void* d_scratch = nullptr;  // small device scratch (flags, counters)
+  struct TableEntry {
+    std::vector<double> host;
+    double* dev;
+  };
+  std::vector<TableEntry> table_cache;  // reference-element tables already on the device (assemble.cu)
 };
 
 struct lfgpu_mesh {
