@@ -145,7 +145,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c5_1e8", choices=sorted(WORKLOADS))
     ap.add_argument("--n", type=int, default=0, help="override the mesh parameter n (debugging)")
-    ap.add_argument("--algo", default="gather", choices=["gather", "atomic"])
+    ap.add_argument("--algo", default="auto", choices=["auto", "fan", "gather", "atomic"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -174,7 +174,9 @@ def main():
         n = args.n
         desc += " [n overridden to %d]" % n
     ctx = lf.Context(local_rank)
-    algo = lf.ALGO_GATHER if args.algo == "gather" else lf.ALGO_ATOMIC
+    algo = {"auto": lf.ALGO_AUTO, "fan": lf.ALGO_FAN, "gather": lf.ALGO_GATHER, "atomic": lf.ALGO_ATOMIC}[args.algo]
+    kernel_name = {"auto": "k_assemble_p1_fan" if (degree == 1 and kind == "tp_tria") else "k_assemble_gather", "fan": "k_assemble_p1_fan",
+                   "gather": "k_assemble_gather", "atomic": "k_assemble_atomic"}[args.algo]
 
     # ---- setup (untimed, like mesh / DofHandler construction on the CPU side) ----------------------------------------------
     t_setup = time.time()
@@ -335,7 +337,7 @@ def main():
                    "symbolic_pass_s": round(t_sym, 3), "setup_s": round(t_setup, 3)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_cell": alg_bytes / mesh.n_cells,
-                     "kernel": "k_assemble_%s" % args.algo},
+                     "kernel": kernel_name},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(t_timed0, max(t_timed1, t_end)),
     }

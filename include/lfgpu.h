@@ -53,6 +53,7 @@ typedef enum {
 #define LFGPU_ALGO_AUTO 0
 #define LFGPU_ALGO_ATOMIC 1 /* one thread per (cell, local row), FP64 atomics into the values (supports beta = 1)       */
 #define LFGPU_ALGO_GATHER 2 /* owner-computes: one thread per matrix row gathers its cells, deterministic, no atomics    */
+#define LFGPU_ALGO_FAN 3    /* P1 on triangles with constant coefficients: vertex-fan kernel (AUTO picks it when it applies) */
 
 /* ---- context ------------------------------------------------------------------------------------------------------ */
 int lfgpu_ctx_create(int device, lfgpu_ctx** out);

@@ -13,6 +13,7 @@ Reference interfaces mirrored (paths relative to the LehrFEM++ checkout):
 from .api import (  # noqa: F401
     ALGO_ATOMIC,
     ALGO_AUTO,
+    ALGO_FAN,
     ALGO_GATHER,
     COL_MAJOR,
     ROW_MAJOR,
@@ -31,6 +32,6 @@ from .api import (  # noqa: F401
 )
 
 __all__ = [
-    "ALGO_ATOMIC", "ALGO_AUTO", "ALGO_GATHER", "COL_MAJOR", "ROW_MAJOR", "Coeff", "Context", "DeviceArray", "DofMap",
+    "ALGO_ATOMIC", "ALGO_AUTO", "ALGO_FAN", "ALGO_GATHER", "COL_MAJOR", "ROW_MAJOR", "Coeff", "Context", "DeviceArray", "DofMap",
     "LfgpuError", "Mesh", "Pattern", "QuadRule", "build_library", "default_quad_rule", "fe_tabulate", "library_path",
 ]

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 COL_MAJOR, ROW_MAJOR = 0, 1
-ALGO_AUTO, ALGO_ATOMIC, ALGO_GATHER = 0, 1, 2
+ALGO_AUTO, ALGO_ATOMIC, ALGO_GATHER, ALGO_FAN = 0, 1, 2, 3
 NIL = 0xFFFFFFFF
 
 _STATUS = {-1: "INVALID", -2: "CUDA", -3: "NO_DEVICE", -4: "MISSING_RULE", -5: "DEGENERATE", -6: "OVERFLOW",

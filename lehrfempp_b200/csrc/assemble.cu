@@ -16,6 +16,8 @@
 //                         no zero-fill, no read-modify-write of the value array.
 // Both use the same element-row routine.  Affine cells with cell-wise constant coefficients take the reference-tensor
 // route (5 FMAs per entry); everything else integrates per quadrature point (3 FMAs per entry and point).
+#include <cmath>
+#include <utility>
 #include <vector>
 
 #include "lfgpu_internal.cuh"
@@ -539,7 +541,46 @@ int lfgpu_assemble_reaction_diffusion_rows(lfgpu_ctx* ctx, const lfgpu_mesh* mes
   DevCoeff da, dg;
   if ((rc = check_coeff(ctx, alpha, true, ht, &da)) != LFGPU_OK) return rc;
   if ((rc = check_coeff(ctx, gamma, false, ht, &dg)) != LFGPU_OK) return rc;
-  if (algo == LFGPU_ALGO_AUTO) algo = LFGPU_ALGO_GATHER;
+  if ((rc = check_rules(ctx, mesh, ht)) != LFGPU_OK) return rc;
+  if (algo == LFGPU_ALGO_AUTO || algo == LFGPU_ALGO_FAN) {
+    // P1 vertex-fan kernel: triangles only, constant coefficients, every cell active, square nodal dof table
+    bool ok = degree == 1 && active == nullptr && da.kind <= LFGPU_COEFF_CONST_2X2 && dg.kind == LFGPU_COEFF_CONST &&
+              mesh->n_quad == 0 && mesh->cell_coords == nullptr;
+    double wsum = 0.0, m_diag = 0.0, m_off = 0.0;
+    if (ok) {
+      // reference mass tensor of the rule must not depend on the local vertex numbering (true for every symmetric rule)
+      const int nq = ht.hdr.nq[0];
+      const double* base = ht.blob.data() + ht.hdr.off[0];
+      for (int k = 0; k < nq; ++k) wsum += base[k];
+      const double* m = base + 3 * nq + 3 * 3 * nq + 4 * 9;
+      m_diag = m[0];
+      m_off = m[1];
+      if (dg.c[0] != 0.0) {
+        for (int a = 0; a < 3; ++a)
+          for (int b = 0; b < 3; ++b)
+            if (std::fabs(m[a * 3 + b] - (a == b ? m_diag : m_off)) > 1e-15) ok = false;
+      }
+    }
+    if (ok) {
+      if ((rc = p1_fan_prepare(ctx, mesh, const_cast<lfgpu_pattern*>(p))) != LFGPU_OK) return rc;
+      ok = p->fan_state == 1 && (d_row_list == nullptr || p->n_irregular == 0);
+    }
+    if (ok) {
+      const bool tr = (p->major == LFGPU_ROW_MAJOR);
+      double a[4] = {da.c[0], da.c[1], da.c[2], da.c[3]};
+      const int tensor = da.kind == LFGPU_COEFF_CONST_2X2;
+      if (tensor && tr) std::swap(a[1], a[2]);
+      if (p->n_irregular > 0) {
+        // rows that are not a single fan: generic gather kernel on exactly those rows
+        rc = lfgpu_assemble_reaction_diffusion_rows(ctx, mesh, p, degree, qr_tria, qr_quad, alpha, gamma, nullptr, beta, d_values,
+                                                    LFGPU_ALGO_GATHER, p->fan_irregular, p->n_irregular);
+        if (rc != LFGPU_OK) return rc;
+      }
+      return p1_fan_launch(ctx, mesh, p, a, tensor, dg.c[0], wsum, m_diag, m_off, beta, d_row_list, n_rows, d_values);
+    }
+    if (algo == LFGPU_ALGO_FAN) LFGPU_FAIL(ctx, LFGPU_ERR_UNSUPPORTED, "LFGPU_ALGO_FAN needs P1 on a triangle mesh with constant coefficients and no activity mask");
+    algo = LFGPU_ALGO_GATHER;
+  }
   if (algo != LFGPU_ALGO_ATOMIC && algo != LFGPU_ALGO_GATHER) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "unknown algo");
   if (d_row_list != nullptr && algo != LFGPU_ALGO_GATHER) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "a row list needs LFGPU_ALGO_GATHER");
   if ((rc = check_rules(ctx, mesh, ht)) != LFGPU_OK) return rc;

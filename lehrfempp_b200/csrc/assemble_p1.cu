@@ -1,0 +1,422 @@
+// P1 (FeLagrangeO1Tria) fast path of the numeric pass: the "vertex fan" kernel (product code).
+//
+// Same mathematics as the generic path (uscalfe/loc_comp_ellbvp.h:266-339 with FeLagrangeO1Tria, lagr_fe.h:110-128,
+// and TriaO1, geometry/tria_o1.cc:50-74), same output (the values of the compressed matrix of the symbolic pass), but
+// organised around the only data an affine P1 row really needs: for matrix row i (= mesh node i) the ring of its
+// neighbour nodes n_0, n_1, ... in fan order.  Consecutive neighbours (n_t, n_t+1) span one adjacent triangle, so
+//   * the ring IS the connectivity (4 bytes per adjacent cell, instead of cell id + 3 vertex ids + scatter slots),
+//   * every off-diagonal entry (i, n_t) is the sum of exactly two consecutive cells -> a rolling register, no
+//     accumulator array, no atomics,
+//   * the slot of column n_t inside row i is its rank among the ring's ids (+1 if i < n_t): integer compares in
+//     registers instead of a stored scatter map.
+// HBM traffic per cell: ring 12 B + vertex coordinates 8 B + row pointer 2 B + values 28 B = 50 B (algorithmic: 48 B).
+// Each warp stages its 32 consecutive rows in shared memory and writes the values as full 128-byte lines.
+//
+// Rows whose cells do not form a single fan (non-manifold vertices) or with more cells than the ring holds are listed
+// as "irregular" and go through the generic gather kernel (assemble.cu) first; this kernel then leaves them untouched.
+#include <cub/cub.cuh>
+
+#include "lfgpu_internal.cuh"
+
+namespace lfgpu {
+namespace {
+
+constexpr int kMaxFan = 12;  // longest ring the builder considers
+constexpr uint32_t kNil = 0xFFFFFFFFu;
+constexpr uint32_t kClosed = 0x80000000u;
+
+// ---- plan construction --------------------------------------------------------------------------------------------
+// One thread per row: order the adjacent cells into a fan.  Returns the ring in `ring` (ids), its length, closed flag;
+// false if the cells do not form exactly one fan.
+__device__ bool build_ring(int32_t row, int m, const uint32_t* __restrict__ adj, int64_t it0, const uint32_t* __restrict__ cell_nodes,
+                           uint32_t* ring, int& len, bool& closed) {
+  uint32_t ja[kMaxFan], ka[kMaxFan];
+  for (int t = 0; t < m; ++t) {
+    const uint32_t item = adj[it0 + t];
+    const int64_t cell = item >> 4;
+    const int a = static_cast<int>(item & 15U);
+    const uint4 v = reinterpret_cast<const uint4*>(cell_nodes)[cell];
+    const uint32_t vv[3] = {v.x, v.y, v.z};
+    ja[t] = vv[(a + 1) % 3];
+    ka[t] = vv[(a + 2) % 3];
+  }
+  // endpoints of an open fan: ids that occur exactly once
+  int start = -1;
+  bool start_is_j = true;
+  int n_single = 0;
+  for (int t = 0; t < m; ++t) {
+    for (int e = 0; e < 2; ++e) {
+      const uint32_t id = e == 0 ? ja[t] : ka[t];
+      int cnt = 0;
+      for (int u = 0; u < m; ++u) cnt += (ja[u] == id) + (ka[u] == id);
+      if (cnt == 1) {
+        ++n_single;
+        if (start < 0) {
+          start = t;
+          start_is_j = (e == 0);
+        }
+      } else if (cnt != 2) {
+        return false;  // an edge shared by more than two cells
+      }
+    }
+  }
+  if (n_single != 0 && n_single != 2) return false;
+  closed = (n_single == 0);
+  unsigned used = 0;
+  uint32_t cur;
+  if (closed) {
+    start = 0;
+    ring[0] = ja[0];
+    cur = ka[0];
+  } else {
+    ring[0] = start_is_j ? ja[start] : ka[start];
+    cur = start_is_j ? ka[start] : ja[start];
+  }
+  used |= 1U << start;
+  len = 1;
+  for (int step = 1; step < m; ++step) {
+    ring[len++] = cur;
+    int nxt = -1;
+    for (int u = 0; u < m; ++u) {
+      if (!(used & (1U << u)) && (ja[u] == cur || ka[u] == cur)) {
+        nxt = u;
+        break;
+      }
+    }
+    if (nxt < 0) return false;  // chain broken: more than one fan
+    used |= 1U << nxt;
+    cur = (ja[nxt] == cur) ? ka[nxt] : ja[nxt];
+  }
+  if (closed) {
+    if (cur != ring[0]) return false;
+  } else {
+    ring[len++] = cur;
+  }
+  (void)row;
+  return true;
+}
+
+__global__ void k_fan_lengths(int64_t n_rows, const int32_t* __restrict__ adj_ptr, const uint32_t* __restrict__ adj,
+                              const uint32_t* __restrict__ cell_nodes, uint8_t* __restrict__ ring_len, int* __restrict__ max_len) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  int len = 0;
+  if (r < n_rows) {
+    const int32_t it0 = adj_ptr[r];
+    const int m = adj_ptr[r + 1] - it0;
+    if (m >= 1 && m <= kMaxFan - 1) {
+      uint32_t ring[kMaxFan + 1];
+      bool closed;
+      if (!build_ring(static_cast<int32_t>(r), m, adj, it0, cell_nodes, ring, len, closed)) len = 0;
+    }
+    ring_len[r] = static_cast<uint8_t>(len);  // 0 = irregular
+  }
+  len = __reduce_max_sync(0xffffffffU, len);
+  if ((threadIdx.x & 31) == 0) atomicMax(max_len, len);
+}
+
+__global__ void k_fan_fill(int64_t n_rows, int W, const int32_t* __restrict__ adj_ptr, const uint32_t* __restrict__ adj,
+                           const uint32_t* __restrict__ cell_nodes, const uint8_t* __restrict__ ring_len, uint32_t* __restrict__ nbr) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  uint32_t ring[kMaxFan + 1];
+  int len = 0;
+  bool closed = false;
+  if (ring_len[r] != 0 && ring_len[r] <= W) {
+    const int32_t it0 = adj_ptr[r];
+    build_ring(static_cast<int32_t>(r), adj_ptr[r + 1] - it0, adj, it0, cell_nodes, ring, len, closed);
+  }
+  for (int s = 0; s < W; ++s) {
+    uint32_t v = (s < len) ? ring[s] : kNil;
+    if (s == 0 && len > 0 && closed) v |= kClosed;
+    nbr[static_cast<int64_t>(s) * n_rows + r] = v;
+  }
+}
+
+__global__ void k_flag_irregular(int64_t n_rows, int W, const uint8_t* __restrict__ ring_len, const int32_t* __restrict__ adj_ptr,
+                                 uint8_t* __restrict__ flag) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const bool has_cells = adj_ptr[r + 1] > adj_ptr[r];
+  flag[r] = (has_cells && (ring_len[r] == 0 || ring_len[r] > W)) ? 1 : 0;
+}
+
+// dof table == vertex table and all cells are triangles?
+__global__ void k_check_nodal(int64_t n_cells, int stride, const int32_t* __restrict__ dofs, const uint8_t* __restrict__ nldof,
+                              const uint32_t* __restrict__ cell_nodes, int* __restrict__ bad) {
+  const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (c >= n_cells) return;
+  const uint4 v = reinterpret_cast<const uint4*>(cell_nodes)[c];
+  if (v.w != kNil || nldof[c] != 3 || dofs[c * stride] != static_cast<int32_t>(v.x) || dofs[c * stride + 1] != static_cast<int32_t>(v.y) ||
+      dofs[c * stride + 2] != static_cast<int32_t>(v.z))
+    *bad = 1;
+}
+
+struct IotaIt {};
+
+// ---- the kernel -----------------------------------------------------------------------------------------------------
+struct FanParams {
+  double a00, a01, a10, a11;  // effective diffusion tensor (already transposed for row-major output)
+  double gamma;
+  double wsum;                // sum of the rule's weights (1/2 for every rule of the reference)
+  double m_diag, m_off;       // reference mass tensor of the rule
+  int tensor;                 // 0: scalar alpha = a00
+  double beta;
+};
+
+__device__ __forceinline__ double fast_rcp(double x) {
+  // 1/x to full double accuracy: single-precision seed + three Newton steps (no slow path: |x| is a cell area, far
+  // from the double range limits; degenerate cells are rejected at mesh upload)
+  double r = static_cast<double>(__frcp_rn(static_cast<float>(x)));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
+// contributions of the triangle (i, p, q) with a = x_p - x_i, b = x_q - x_i to row i: k0 (diag), k1 (col p), k2 (col q)
+__device__ __forceinline__ void fan_cell(const FanParams& P, double ax, double ay, double bx, double by, double aa, double bb,
+                                         double& k0, double& k1, double& k2) {
+  const double det = ax * by - ay * bx;
+  const double adet = fabs(det);
+  const double ridet = fast_rcp(adet);
+  if (!P.tensor) {
+    const double ab = ax * bx + ay * by;
+    const double s = P.wsum * P.a00 * ridet;
+    k1 = s * (ab - bb);
+    k2 = s * (ab - aa);
+  } else {
+    // M = |det| Jinv A Jinv^T with Jinv = 1/det [by -bx; -ay ax];  u = -(M e0 + M e1);  k1 = wsum u.x, k2 = wsum u.y
+    // work with N = adj(J) = [by -bx; -ay ax]:  M = N A N^T / |det|
+    const double n00 = by, n01 = -bx, n10 = -ay, n11 = ax;
+    const double t00 = n00 * P.a00 + n01 * P.a10, t01 = n00 * P.a01 + n01 * P.a11;
+    const double t10 = n10 * P.a00 + n11 * P.a10, t11 = n10 * P.a01 + n11 * P.a11;
+    const double m00 = t00 * n00 + t01 * n01, m01 = t00 * n10 + t01 * n11;
+    const double m10 = t10 * n00 + t11 * n01, m11 = t10 * n10 + t11 * n11;
+    const double s = P.wsum * ridet;
+    k1 = -s * (m00 + m01);
+    k2 = -s * (m10 + m11);
+  }
+  k0 = -(k1 + k2);
+  const double gm = P.gamma * adet;
+  k0 = fma(gm, P.m_diag, k0);
+  k1 = fma(gm, P.m_off, k1);
+  k2 = fma(gm, P.m_off, k2);
+}
+
+template <int W>
+__global__ void __launch_bounds__(128) k_assemble_p1_fan(int64_t n_rows, int64_t n_total_rows, const uint32_t* __restrict__ nbr,
+                                                         const double* __restrict__ node_coords, const int32_t* __restrict__ outer,
+                                                         const int32_t* __restrict__ row_list, FanParams P,
+                                                         double* __restrict__ values) {
+  extern __shared__ double stage_all[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool in_range = t < n_rows;
+  const int64_t r = in_range ? (row_list != nullptr ? row_list[t] : t) : 0;
+  int32_t v0 = 0, v1 = 0;
+  if (in_range) {
+    v0 = __ldg(outer + r);
+    v1 = __ldg(outer + r + 1);
+  }
+  const int32_t wbase = __shfl_sync(0xffffffffU, v0, 0);
+  double* stage = stage_all + warp * (32 * (W + 2));
+  const int off = v0 - wbase;
+
+  uint32_t n[W];
+  bool regular = false, closed = false;
+  if (in_range) {
+#pragma unroll
+    for (int s = 0; s < W; ++s) n[s] = __ldg(nbr + static_cast<int64_t>(s) * n_total_rows + r);
+    regular = (n[0] != kNil);
+    closed = regular && (n[0] & kClosed);
+    n[0] &= ~kClosed;
+  } else {
+#pragma unroll
+    for (int s = 0; s < W; ++s) n[s] = kNil;
+  }
+  // staging: the rows of a warp are consecutive (no row list), so their values form one contiguous range that is
+  // written as full lines.  A warp that contains an irregular row (computed by the generic kernel) writes directly.
+  const bool staged = (row_list == nullptr) && !__any_sync(0xffffffffU, in_range && !regular && v1 > v0);
+  if (regular) {
+    const double2* nc = reinterpret_cast<const double2*>(node_coords);
+    const double2 xi = __ldg(nc + r);
+    double dx[W], dy[W], dd[W];
+    int m = 0;
+#pragma unroll
+    for (int s = 0; s < W; ++s) {
+      const bool valid = (n[s] != kNil);
+      const double2 p = valid ? __ldg(nc + n[s]) : xi;
+      dx[s] = p.x - xi.x;
+      dy[s] = p.y - xi.y;
+      dd[s] = dx[s] * dx[s] + dy[s] * dy[s];
+      m += valid ? 1 : 0;
+    }
+    // slot of column n[s] inside the row = rank among all column ids of the row (ring ids + the row itself)
+    const uint32_t ri = static_cast<uint32_t>(r);
+    int pos[W];
+    int posd = 0;
+#pragma unroll
+    for (int s = 0; s < W; ++s) {
+      int c = (ri < n[s]) ? 1 : 0;
+#pragma unroll
+      for (int u = 0; u < W; ++u) c += (n[u] < n[s]) ? 1 : 0;  // NIL is the largest id: never counted, never counts itself
+      pos[s] = c;
+      posd += (n[s] < ri) ? 1 : 0;
+    }
+    double diag = 0.0, carry = 0.0, first = 0.0;
+    double lx = dx[0], ly = dy[0], ld = dd[0];
+    int lpos = pos[0];
+    double* dst = staged ? (stage + off) : (values + v0);
+    const bool accumulate = (P.beta != 0.0);
+#pragma unroll
+    for (int s = 0; s + 1 < W; ++s) {
+      if (s + 1 < m) {  // cell (i, n_s, n_s+1)
+        double k0, k1, k2;
+        fan_cell(P, dx[s], dy[s], dx[s + 1], dy[s + 1], dd[s], dd[s + 1], k0, k1, k2);
+        diag += k0;
+        if (s == 0) {
+          first = k1;
+        } else {
+          double v = carry + k1;
+          if (accumulate) v = fma(P.beta, values[v0 + pos[s]], v);
+          dst[pos[s]] = v;
+        }
+        carry = k2;
+        lx = dx[s + 1];
+        ly = dy[s + 1];
+        ld = dd[s + 1];
+        lpos = pos[s + 1];
+      }
+    }
+    if (closed) {  // wrap-around cell (i, n_m-1, n_0)
+      double k0, k1, k2;
+      fan_cell(P, lx, ly, dx[0], dy[0], ld, dd[0], k0, k1, k2);
+      diag += k0;
+      carry += k1;
+      first += k2;
+    }
+    if (m > 1) {
+      if (accumulate) {
+        carry = fma(P.beta, values[v0 + lpos], carry);
+        first = fma(P.beta, values[v0 + pos[0]], first);
+      }
+      dst[lpos] = carry;
+      dst[pos[0]] = first;
+    }
+    if (accumulate) diag = fma(P.beta, values[v0 + posd], diag);
+    dst[posd] = diag;
+  }
+  if (staged) {
+    __syncwarp();
+    // last in-range lane of the warp knows the end of the range
+    const unsigned ballot = __ballot_sync(0xffffffffU, in_range);
+    if (ballot == 0) return;
+    const int last = 31 - __clz(ballot);
+    const int32_t wend = __shfl_sync(0xffffffffU, v1, last);
+    const int total = wend - wbase;
+    double* out = values + wbase;
+    for (int k = lane; k < total; k += 32) out[k] = stage[k];
+  }
+}
+
+}  // namespace
+
+// ---- host side ---------------------------------------------------------------------------------------------------------
+int p1_fan_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
+  if (p->fan_state != 0) return LFGPU_OK;
+  p->fan_state = -1;
+  if (mesh->n_quad != 0 || mesh->cell_coords != nullptr || p->i_dofs != p->o_dofs || p->n_outer != mesh->n_nodes || p->n_outer >= (1LL << 31)) return LFGPU_OK;
+  cudaStream_t st = ctx->stream;
+  int* d_flags = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 256);
+  LFGPU_CUDA_CHECK(ctx, cudaMemsetAsync(d_flags, 0, 16, st));
+  const unsigned gc = static_cast<unsigned>(cdiv(p->n_cells, 256)), gr = static_cast<unsigned>(cdiv(p->n_outer, 256));
+  k_check_nodal<<<gc, 256, 0, st>>>(p->n_cells, p->o_stride, p->o_dofs, p->o_nldof, mesh->cell_nodes, d_flags);
+  LFGPU_LAUNCH_CHECK(ctx);
+  uint8_t* ring_len = nullptr;
+  LFGPU_CUDA_CHECK(ctx, cudaMalloc(&ring_len, p->n_outer));
+  k_fan_lengths<<<gr, 256, 0, st>>>(p->n_outer, p->adj_ptr, p->adj, mesh->cell_nodes, ring_len, d_flags + 1);
+  LFGPU_LAUNCH_CHECK(ctx);
+  int h[2] = {0, 0};
+  cudaError_t e = cudaMemcpyAsync(h, d_flags, sizeof(h), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess || h[0] != 0 || h[1] < 2) {
+    cudaFree(ring_len);
+    LFGPU_CUDA_CHECK(ctx, e);
+    return LFGPU_OK;  // not a nodal P1 table: stay with the generic kernels
+  }
+  // ring width: the kernel is instantiated for 6, 8, 10, 12; longer rings would be irregular rows
+  int W = h[1] <= 6 ? 6 : (h[1] <= 8 ? 8 : (h[1] <= 10 ? 10 : 12));
+  uint8_t* flag = nullptr;
+  int32_t* iota = nullptr;
+  int64_t* d_num = nullptr;
+  void* tmp = nullptr;
+  auto cleanup = [&]() { cudaFree(ring_len); cudaFree(flag); cudaFree(iota); cudaFree(d_num); cudaFree(tmp); };
+#define FAN_CHECK(expr)                                                             \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      set_last_error(ctx, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+      cleanup();                                                                    \
+      return LFGPU_ERR_CUDA;                                                        \
+    }                                                                               \
+  } while (0)
+  FAN_CHECK(cudaMalloc(&p->fan_nbr, sizeof(uint32_t) * static_cast<size_t>(W) * p->n_outer));
+  k_fan_fill<<<gr, 256, 0, st>>>(p->n_outer, W, p->adj_ptr, p->adj, mesh->cell_nodes, ring_len, p->fan_nbr);
+  ctx->launches++;
+  FAN_CHECK(cudaMalloc(&flag, p->n_outer));
+  k_flag_irregular<<<gr, 256, 0, st>>>(p->n_outer, W, ring_len, p->adj_ptr, flag);
+  ctx->launches++;
+  FAN_CHECK(cudaMalloc(&iota, sizeof(int32_t) * p->n_outer));
+  FAN_CHECK(cudaMalloc(&d_num, sizeof(int64_t)));
+  cub::CountingInputIterator<int32_t> count_it(0);
+  size_t tb = 0;
+  cub::DeviceSelect::Flagged(nullptr, tb, count_it, flag, iota, d_num, p->n_outer, st);
+  FAN_CHECK(cudaMalloc(&tmp, tb));
+  FAN_CHECK(cub::DeviceSelect::Flagged(tmp, tb, count_it, flag, iota, d_num, p->n_outer, st));
+  int64_t n_irr = 0;
+  FAN_CHECK(cudaMemcpyAsync(&n_irr, d_num, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  FAN_CHECK(cudaStreamSynchronize(st));
+  if (n_irr > 0) {
+    FAN_CHECK(cudaMalloc(&p->fan_irregular, sizeof(int32_t) * n_irr));
+    FAN_CHECK(cudaMemcpyAsync(p->fan_irregular, iota, sizeof(int32_t) * n_irr, cudaMemcpyDeviceToDevice, st));
+    FAN_CHECK(cudaStreamSynchronize(st));
+  }
+#undef FAN_CHECK
+  cleanup();
+  p->n_irregular = n_irr;
+  p->fan_w = W;
+  p->fan_state = 1;
+  return LFGPU_OK;
+}
+
+// launches the fan kernel over all rows (row_list == nullptr) or over the listed rows
+int p1_fan_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, const double alpha[4], int tensor, double gamma,
+                  double wsum, double m_diag, double m_off, double beta, const int32_t* row_list, int64_t n_rows, double* d_values) {
+  FanParams P;
+  P.a00 = alpha[0]; P.a01 = alpha[1]; P.a10 = alpha[2]; P.a11 = alpha[3];
+  P.tensor = tensor;
+  P.gamma = gamma;
+  P.wsum = wsum;
+  P.m_diag = m_diag;
+  P.m_off = m_off;
+  P.beta = beta;
+  const int64_t rows = row_list != nullptr ? n_rows : p->n_outer;
+  if (rows <= 0) return LFGPU_OK;
+  const int threads = 128;
+  const unsigned grid = static_cast<unsigned>(cdiv(rows, threads));
+  const int W = p->fan_w;
+  const size_t smem = sizeof(double) * (threads / 32) * 32 * (W + 2);
+  switch (W) {
+    case 6: k_assemble_p1_fan<6><<<grid, threads, smem, ctx->stream>>>(rows, p->n_outer, p->fan_nbr, mesh->node_coords, p->outer, row_list, P, d_values); break;
+    case 8: k_assemble_p1_fan<8><<<grid, threads, smem, ctx->stream>>>(rows, p->n_outer, p->fan_nbr, mesh->node_coords, p->outer, row_list, P, d_values); break;
+    case 10: k_assemble_p1_fan<10><<<grid, threads, smem, ctx->stream>>>(rows, p->n_outer, p->fan_nbr, mesh->node_coords, p->outer, row_list, P, d_values); break;
+    default: k_assemble_p1_fan<12><<<grid, threads, smem, ctx->stream>>>(rows, p->n_outer, p->fan_nbr, mesh->node_coords, p->outer, row_list, P, d_values); break;
+  }
+  LFGPU_LAUNCH_CHECK(ctx);
+  return LFGPU_OK;
+}
+
+}  // namespace lfgpu

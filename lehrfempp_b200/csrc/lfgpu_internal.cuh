@@ -81,6 +81,12 @@ struct lfgpu_pattern {
   int32_t* i_dofs = nullptr;  // [n_cells][i_stride]
   uint8_t* o_nldof = nullptr;
   uint8_t* i_nldof = nullptr;
+  // P1 vertex-fan plan (assemble_p1.cu), built on first use: 0 = not tried, 1 = ready, -1 = not applicable
+  int fan_state = 0;
+  int fan_w = 0;                     // ring slots per row
+  uint32_t* fan_nbr = nullptr;       // [fan_w][n_outer] neighbour ring of every row, slot-major; bit 31 of slot 0 = closed fan
+  int32_t* fan_irregular = nullptr;  // rows that are not a single fan (generic kernel)
+  int64_t n_irregular = 0;
 };
 
 namespace lfgpu {
@@ -135,6 +141,11 @@ int nsf_of(int degree, int cell_type);
 int build_fe_table(int degree, int cell_type, const lfgpu_quad* qr, FeTable* out, std::string* err);
 void build_fe_tensors(const FeTable& t, FeTensors* out);
 int default_quad_rule(int cell_type, int degree, int capacity, double* points, double* weights);
+
+// P1 vertex-fan fast path (assemble_p1.cu)
+int p1_fan_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p);
+int p1_fan_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, const double alpha[4], int tensor, double gamma,
+                  double wsum, double m_diag, double m_off, double beta, const int32_t* row_list, int64_t n_rows, double* d_values);
 
 }  // namespace lfgpu
 #endif

@@ -292,7 +292,7 @@ def test_config_c1_p1_laplacian_256(ctx, lf):
         outer, inner = pat.download()
         assert pat.nnz == 460289 and dm.num_dofs == 66049
         assert np.array_equal(outer, o_outer) and np.array_equal(inner, o_inner)
-        for algo in (lf.ALGO_ATOMIC, lf.ALGO_GATHER):
+        for algo in (lf.ALGO_ATOMIC, lf.ALGO_GATHER, lf.ALGO_FAN):
             vals = pat.assemble_reaction_diffusion(1, lf.Coeff.const(1.0), lf.Coeff.const(0.0), algo=algo).to_host()
             assert rel_max_err(vals, o_vals) <= TOL
             assert (vals == 0.0).sum() >= 2 * 256 * 256  # explicit zeros on the diagonal edges stay in the pattern
@@ -326,3 +326,92 @@ def test_large_mesh_properties(ctx, lf, degree, n):
     assert rel_max_err(atom, stiff) <= TOL                        # the two scatter strategies agree
     again = pat.assemble_reaction_diffusion(degree, lf.Coeff.const(1.0), lf.Coeff.const(0.0), algo=lf.ALGO_GATHER).to_host()
     assert np.array_equal(again, stiff)                           # gather path is deterministic (bitwise repeatable)
+
+
+# ---- P1 vertex-fan fast path (LFGPU_ALGO_FAN) -------------------------------------------------------------------------
+def fan_meshes():
+    """Triangle meshes that stress the fan plan: structured, unstructured, a non-manifold 'bow-tie' vertex, a vertex of
+    valence 14 (longer than the ring) and mixed cell orientations."""
+    out = {}
+    # bow-tie: two triangles that share only vertex 0, plus a regular strip
+    xy = np.array([[0.0, 0.0], [1.0, 0.0], [1.0, 1.0], [-1.0, 0.0], [-1.0, -1.0], [2.0, 0.0], [2.0, 1.0]])
+    cn = np.array([[0, 1, 2, NIL], [0, 3, 4, NIL], [1, 5, 2, NIL], [5, 6, 2, NIL]], dtype=np.uint32)
+    out["bowtie"] = (xy, cn)
+    # wheel of 14 triangles around vertex 0, alternating orientation
+    k = 14
+    ang = 2 * np.pi * np.arange(k) / k
+    xy = np.vstack([[0.0, 0.0], np.stack([np.cos(ang), np.sin(ang)], 1) * (1.0 + 0.1 * np.cos(3 * ang))[:, None]])
+    cn = np.array([[0, 1 + t, 1 + (t + 1) % k, NIL] if t % 2 == 0 else [1 + (t + 1) % k, 1 + t, 0, NIL] for t in range(k)],
+                  dtype=np.uint32)
+    out["wheel14"] = (xy, cn)
+    # wheel of 7 (closed fan of odd length) + an open fan
+    k = 7
+    ang = 2 * np.pi * np.arange(k) / k
+    xy = np.vstack([[0.0, 0.0], np.stack([np.cos(ang), np.sin(ang)], 1)])
+    cn = np.array([[0, 1 + t, 1 + (t + 1) % k, NIL] for t in range(k)], dtype=np.uint32)
+    out["wheel7"] = (xy, cn)
+    return out
+
+
+NIL = 0xFFFFFFFF
+
+
+@pytest.mark.parametrize("kind", ["tp_tria:11", "golden3", "golden4", "bowtie", "wheel14", "wheel7"])
+@pytest.mark.parametrize("major", [0, 1])
+def test_p1_fan_kernel(ctx, lf, golden_meshes, kind, major):
+    if kind in ("bowtie", "wheel14", "wheel7"):
+        xy, cn = fan_meshes()[kind]
+        om = lfo.Mesh.from_arrays(xy, cn)
+        gm = ctx.mesh_upload(xy, cn)
+    else:
+        om = oracle_mesh(kind, golden_meshes)
+        gm = gpu_mesh(ctx, kind, golden_meshes, om)
+    dm = gm.dofmap_lagrange(1)
+    pat = dm.symbolic(major=major)
+    A = [[3.0, 0.5], [1.0, 2.0]]
+    cases = [(lfo.coeff.const(1.0), lfo.coeff.const(0.0), lf.Coeff.const(1.0), lf.Coeff.const(0.0)),
+             (lfo.coeff.const(2.5), lfo.coeff.const(0.75), lf.Coeff.const(2.5), lf.Coeff.const(0.75)),
+             (lfo.coeff.const2x2(A), lfo.coeff.const(1.25), lf.Coeff.const2x2(A), lf.Coeff.const(1.25))]
+    for oa, og, ga, gg in cases:
+        o_outer, o_inner, o_vals, _, _ = om.assemble_rd(1, oa, og, csr=(major == lf.ROW_MAJOR))
+        outer, inner = pat.download()
+        assert np.array_equal(outer, o_outer) and np.array_equal(inner, o_inner)
+        v = pat.assemble_reaction_diffusion(1, ga, gg, algo=lf.ALGO_FAN)
+        assert rel_max_err(v.to_host(), o_vals) <= TOL
+        # AUTO takes the same path; accumulate on top (beta = 1) doubles the entries
+        pat.assemble_reaction_diffusion(1, ga, gg, beta=1.0, out=v, algo=lf.ALGO_AUTO)
+        assert rel_max_err(v.to_host(), 2 * o_vals) <= TOL
+        # explicit user rule of higher degree gives the same matrix (constant coefficients are integrated exactly)
+        qt = lf.QuadRule(*lfo.quad_rule(3, 6))
+        v6 = pat.assemble_reaction_diffusion(1, ga, gg, qt, None, algo=lf.ALGO_FAN).to_host()
+        assert rel_max_err(v6, o_vals) <= TOL
+
+
+def test_p1_fan_not_applicable(ctx, lf, golden_meshes):
+    om = lfo.Mesh.from_golden(golden_meshes["0"])          # hybrid mesh
+    gm = upload_oracle_mesh(ctx, om)[0]
+    pat = gm.dofmap_lagrange(1).symbolic()
+    with pytest.raises(lf.LfgpuError) as e:
+        pat.assemble_reaction_diffusion(1, lf.Coeff.const(1.0), lf.Coeff.const(0.0), algo=lf.ALGO_FAN)
+    assert e.value.code == -7
+    # AUTO falls back to the generic kernel
+    o = om.assemble_rd(1, lfo.coeff.const(1.0), lfo.coeff.const(0.0), csr=True)
+    v = pat.assemble_reaction_diffusion(1, lf.Coeff.const(1.0), lf.Coeff.const(0.0)).to_host()
+    assert rel_max_err(v, o[2]) <= TOL
+
+
+def test_p1_fan_row_list(ctx, lf):
+    # the multi-GPU building block: only the listed rows are written
+    gm = ctx.mesh_tp_tria(40, 30)
+    om = lfo.Mesh.tp_tria(40, 30)
+    dm = gm.dofmap_lagrange(1)
+    pat = dm.symbolic(major=lf.ROW_MAJOR)
+    outer, inner = pat.download()
+    o = om.assemble_rd(1, lfo.coeff.const(1.0), lfo.coeff.const(0.0), csr=True)
+    rows = np.arange(100, 900, dtype=np.int32)
+    v = ctx.to_device(np.full(pat.nnz, -7.0))
+    pat.assemble_reaction_diffusion(1, lf.Coeff.const(1.0), lf.Coeff.const(0.0), out=v, rows=ctx.to_device(rows))
+    h = v.to_host()
+    lo, hi = outer[100], outer[900]
+    assert rel_max_err(h[lo:hi], o[2][lo:hi]) <= TOL
+    assert np.all(h[:lo] == -7.0) and np.all(h[hi:] == -7.0)
