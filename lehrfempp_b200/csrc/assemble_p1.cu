@@ -23,7 +23,6 @@ namespace {
 
 constexpr int kMaxFan = 12;  // longest ring the builder considers
 constexpr uint32_t kNil = 0xFFFFFFFFu;
-constexpr uint32_t kClosed = 0x80000000u;
 
 // ---- plan construction --------------------------------------------------------------------------------------------
 // One thread per row: order the adjacent cells into a fan.  Returns the ring in `ring` (ids), its length, closed flag;
@@ -114,8 +113,11 @@ __global__ void k_fan_lengths(int64_t n_rows, const int32_t* __restrict__ adj_pt
   if ((threadIdx.x & 31) == 0) atomicMax(max_len, len);
 }
 
+// ring slot = node id | (slot of that column inside row r) << 28; rowinfo[r] = slot of the diagonal | closed << 7.
+// The slot of column c in row r is its rank among the row's column ids = ring ids and r itself.
 __global__ void k_fan_fill(int64_t n_rows, int W, const int32_t* __restrict__ adj_ptr, const uint32_t* __restrict__ adj,
-                           const uint32_t* __restrict__ cell_nodes, const uint8_t* __restrict__ ring_len, uint32_t* __restrict__ nbr) {
+                           const uint32_t* __restrict__ cell_nodes, const uint8_t* __restrict__ ring_len, uint32_t* __restrict__ nbr,
+                           uint8_t* __restrict__ rowinfo) {
   const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (r >= n_rows) return;
   uint32_t ring[kMaxFan + 1];
@@ -125,11 +127,18 @@ __global__ void k_fan_fill(int64_t n_rows, int W, const int32_t* __restrict__ ad
     const int32_t it0 = adj_ptr[r];
     build_ring(static_cast<int32_t>(r), adj_ptr[r + 1] - it0, adj, it0, cell_nodes, ring, len, closed);
   }
+  int posd = 0;
+  for (int s = 0; s < len; ++s) posd += (ring[s] < static_cast<uint32_t>(r)) ? 1 : 0;
   for (int s = 0; s < W; ++s) {
-    uint32_t v = (s < len) ? ring[s] : kNil;
-    if (s == 0 && len > 0 && closed) v |= kClosed;
+    uint32_t v = kNil;
+    if (s < len) {
+      uint32_t rank = (static_cast<uint32_t>(r) < ring[s]) ? 1U : 0U;
+      for (int u = 0; u < len; ++u) rank += (ring[u] < ring[s]) ? 1U : 0U;
+      v = ring[s] | (rank << 28);
+    }
     nbr[static_cast<int64_t>(s) * n_rows + r] = v;
   }
+  rowinfo[r] = static_cast<uint8_t>(posd | (closed ? 0x80 : 0));
 }
 
 __global__ void k_flag_irregular(int64_t n_rows, int W, const uint8_t* __restrict__ ring_len, const int32_t* __restrict__ adj_ptr,
@@ -151,45 +160,43 @@ __global__ void k_check_nodal(int64_t n_cells, int stride, const int32_t* __rest
     *bad = 1;
 }
 
-struct IotaIt {};
-
 // ---- the kernel -----------------------------------------------------------------------------------------------------
 struct FanParams {
   double a00, a01, a10, a11;  // effective diffusion tensor (already transposed for row-major output)
   double gamma;
   double wsum;                // sum of the rule's weights (1/2 for every rule of the reference)
   double m_diag, m_off;       // reference mass tensor of the rule
-  int tensor;                 // 0: scalar alpha = a00
   double beta;
 };
 
 __device__ __forceinline__ double fast_rcp(double x) {
-  // 1/x to full double accuracy: single-precision seed + three Newton steps (no slow path: |x| is a cell area, far
-  // from the double range limits; degenerate cells are rejected at mesh upload)
-  double r = static_cast<double>(__frcp_rn(static_cast<float>(x)));
+  // 1/x for x = |det J| > 0 (cell areas: far from the double range limits, degenerate cells are rejected at upload):
+  // hardware seed (MUFU.RCP64H, ~20 bits) + two Newton steps -> relative error ~1e-16, no slow path
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
   double e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
   r = fma(r, e, r);
   e = fma(-x, r, 1.0);
   r = fma(r, e, r);
   return r;
 }
 
-// contributions of the triangle (i, p, q) with a = x_p - x_i, b = x_q - x_i to row i: k0 (diag), k1 (col p), k2 (col q)
-__device__ __forceinline__ void fan_cell(const FanParams& P, double ax, double ay, double bx, double by, double aa, double bb,
-                                         double& k0, double& k1, double& k2) {
+// contributions of the triangle (i, p, q), a = x_p - x_i, b = x_q - x_i, to row i: k1 (column p), k2 (column q);
+// the diagonal contribution of the stiffness part is -(k1 + k2).  MODE 0: scalar alpha, no mass (c = wsum * alpha).
+template <int MODE>
+__device__ __forceinline__ void fan_cell(const FanParams& P, double c, double ax, double ay, double bx, double by, double aa,
+                                         double bb, double& k1, double& k2, double& kd) {
   const double det = ax * by - ay * bx;
   const double adet = fabs(det);
   const double ridet = fast_rcp(adet);
-  if (!P.tensor) {
+  if (MODE == 0) {
     const double ab = ax * bx + ay * by;
-    const double s = P.wsum * P.a00 * ridet;
+    const double s = c * ridet;
     k1 = s * (ab - bb);
     k2 = s * (ab - aa);
+    kd = -(k1 + k2);
   } else {
-    // M = |det| Jinv A Jinv^T with Jinv = 1/det [by -bx; -ay ax];  u = -(M e0 + M e1);  k1 = wsum u.x, k2 = wsum u.y
-    // work with N = adj(J) = [by -bx; -ay ax]:  M = N A N^T / |det|
+    // M = N A N^T / |det| with N = adj(J) = [by -bx; -ay ax];  row 0 of the element matrix: wsum * ghat_b^T M ghat_0
     const double n00 = by, n01 = -bx, n10 = -ay, n11 = ax;
     const double t00 = n00 * P.a00 + n01 * P.a10, t01 = n00 * P.a01 + n01 * P.a11;
     const double t10 = n10 * P.a00 + n11 * P.a10, t11 = n10 * P.a01 + n11 * P.a11;
@@ -198,45 +205,43 @@ __device__ __forceinline__ void fan_cell(const FanParams& P, double ax, double a
     const double s = P.wsum * ridet;
     k1 = -s * (m00 + m01);
     k2 = -s * (m10 + m11);
+    kd = -(k1 + k2);
+    const double gm = P.gamma * adet;
+    kd = fma(gm, P.m_diag, kd);
+    k1 = fma(gm, P.m_off, k1);
+    k2 = fma(gm, P.m_off, k2);
   }
-  k0 = -(k1 + k2);
-  const double gm = P.gamma * adet;
-  k0 = fma(gm, P.m_diag, k0);
-  k1 = fma(gm, P.m_off, k1);
-  k2 = fma(gm, P.m_off, k2);
 }
 
-template <int W>
+// ring slot = node id | slot-in-row << 28;  rowinfo = slot of the diagonal | closed << 7
+template <int W, int MODE>
 __global__ void __launch_bounds__(128) k_assemble_p1_fan(int64_t n_rows, int64_t n_total_rows, const uint32_t* __restrict__ nbr,
-                                                         const double* __restrict__ node_coords, const int32_t* __restrict__ outer,
-                                                         const int32_t* __restrict__ row_list, FanParams P,
-                                                         double* __restrict__ values) {
+                                                         const uint8_t* __restrict__ rowinfo, const double* __restrict__ node_coords,
+                                                         const int32_t* __restrict__ outer, const int32_t* __restrict__ row_list,
+                                                         FanParams P, double* __restrict__ values) {
   extern __shared__ double stage_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool in_range = t < n_rows;
   const int64_t r = in_range ? (row_list != nullptr ? row_list[t] : t) : 0;
   int32_t v0 = 0, v1 = 0;
+  uint32_t n[W];
+  int info = 0;
   if (in_range) {
     v0 = __ldg(outer + r);
     v1 = __ldg(outer + r + 1);
-  }
-  const int32_t wbase = __shfl_sync(0xffffffffU, v0, 0);
-  double* stage = stage_all + warp * (32 * (W + 2));
-  const int off = v0 - wbase;
-
-  uint32_t n[W];
-  bool regular = false, closed = false;
-  if (in_range) {
+    info = __ldg(rowinfo + r);
 #pragma unroll
     for (int s = 0; s < W; ++s) n[s] = __ldg(nbr + static_cast<int64_t>(s) * n_total_rows + r);
-    regular = (n[0] != kNil);
-    closed = regular && (n[0] & kClosed);
-    n[0] &= ~kClosed;
   } else {
 #pragma unroll
     for (int s = 0; s < W; ++s) n[s] = kNil;
   }
+  const bool regular = in_range && (n[0] != kNil);
+  const bool closed = (info & 0x80) != 0;
+  const int posd = info & 0x7f;
+  const int32_t wbase = __shfl_sync(0xffffffffU, v0, 0);
+  double* stage = stage_all + warp * (32 * (W + 2));
   // staging: the rows of a warp are consecutive (no row list), so their values form one contiguous range that is
   // written as full lines.  A warp that contains an irregular row (computed by the generic kernel) writes directly.
   const bool staged = (row_list == nullptr) && !__any_sync(0xffffffffU, in_range && !regular && v1 > v0);
@@ -244,81 +249,94 @@ __global__ void __launch_bounds__(128) k_assemble_p1_fan(int64_t n_rows, int64_t
     const double2* nc = reinterpret_cast<const double2*>(node_coords);
     const double2 xi = __ldg(nc + r);
     double dx[W], dy[W], dd[W];
+    int pos[W];
     int m = 0;
 #pragma unroll
     for (int s = 0; s < W; ++s) {
       const bool valid = (n[s] != kNil);
-      const double2 p = valid ? __ldg(nc + n[s]) : xi;
+      const double2 p = __ldg(nc + (valid ? (n[s] & 0x0fffffffU) : static_cast<uint32_t>(r)));
       dx[s] = p.x - xi.x;
       dy[s] = p.y - xi.y;
       dd[s] = dx[s] * dx[s] + dy[s] * dy[s];
+      pos[s] = static_cast<int>(n[s] >> 28);
       m += valid ? 1 : 0;
     }
-    // slot of column n[s] inside the row = rank among all column ids of the row (ring ids + the row itself)
-    const uint32_t ri = static_cast<uint32_t>(r);
-    int pos[W];
-    int posd = 0;
+    const double c = P.wsum * P.a00;
+    double* dst = staged ? (stage + (v0 - wbase)) : (values + v0);
+    const double* old = values + v0;
+    double diag = 0.0;
+    if (m == W && closed) {
+      // full closed ring (every interior vertex of a regular mesh): static indices only
+      double k1, k2, kd, carry, first;
+      fan_cell<MODE>(P, c, dx[0], dy[0], dx[1], dy[1], dd[0], dd[1], first, carry, kd);
+      diag = kd;
 #pragma unroll
-    for (int s = 0; s < W; ++s) {
-      int c = (ri < n[s]) ? 1 : 0;
-#pragma unroll
-      for (int u = 0; u < W; ++u) c += (n[u] < n[s]) ? 1 : 0;  // NIL is the largest id: never counted, never counts itself
-      pos[s] = c;
-      posd += (n[s] < ri) ? 1 : 0;
-    }
-    double diag = 0.0, carry = 0.0, first = 0.0;
-    double lx = dx[0], ly = dy[0], ld = dd[0];
-    int lpos = pos[0];
-    double* dst = staged ? (stage + off) : (values + v0);
-    const bool accumulate = (P.beta != 0.0);
-#pragma unroll
-    for (int s = 0; s + 1 < W; ++s) {
-      if (s + 1 < m) {  // cell (i, n_s, n_s+1)
-        double k0, k1, k2;
-        fan_cell(P, dx[s], dy[s], dx[s + 1], dy[s + 1], dd[s], dd[s + 1], k0, k1, k2);
-        diag += k0;
-        if (s == 0) {
-          first = k1;
-        } else {
-          double v = carry + k1;
-          if (accumulate) v = fma(P.beta, values[v0 + pos[s]], v);
-          dst[pos[s]] = v;
-        }
+      for (int s = 1; s < W; ++s) {
+        const int u = (s + 1 < W) ? s + 1 : 0;
+        fan_cell<MODE>(P, c, dx[s], dy[s], dx[u], dy[u], dd[s], dd[u], k1, k2, kd);
+        diag += kd;
+        double v = carry + k1;
+        if (MODE != 0 && P.beta != 0.0) v = fma(P.beta, old[pos[s]], v);
+        dst[pos[s]] = v;
         carry = k2;
-        lx = dx[s + 1];
-        ly = dy[s + 1];
-        ld = dd[s + 1];
-        lpos = pos[s + 1];
       }
-    }
-    if (closed) {  // wrap-around cell (i, n_m-1, n_0)
-      double k0, k1, k2;
-      fan_cell(P, lx, ly, dx[0], dy[0], ld, dd[0], k0, k1, k2);
-      diag += k0;
-      carry += k1;
-      first += k2;
-    }
-    if (m > 1) {
-      if (accumulate) {
-        carry = fma(P.beta, values[v0 + lpos], carry);
-        first = fma(P.beta, values[v0 + pos[0]], first);
+      first += carry;
+      if (MODE != 0 && P.beta != 0.0) first = fma(P.beta, old[pos[0]], first);
+      dst[pos[0]] = first;
+    } else {
+      double carry = 0.0, first = 0.0;
+      double lx = dx[0], ly = dy[0], ld = dd[0];
+      int lpos = pos[0];
+#pragma unroll
+      for (int s = 0; s + 1 < W; ++s) {
+        if (s + 1 < m) {  // cell (i, n_s, n_s+1)
+          double k1, k2, kd;
+          fan_cell<MODE>(P, c, dx[s], dy[s], dx[s + 1], dy[s + 1], dd[s], dd[s + 1], k1, k2, kd);
+          diag += kd;
+          if (s == 0) {
+            first = k1;
+          } else {
+            double v = carry + k1;
+            if (MODE != 0 && P.beta != 0.0) v = fma(P.beta, old[pos[s]], v);
+            dst[pos[s]] = v;
+          }
+          carry = k2;
+          lx = dx[s + 1];
+          ly = dy[s + 1];
+          ld = dd[s + 1];
+          lpos = pos[s + 1];
+        }
+      }
+      if (closed) {  // wrap-around cell (i, n_m-1, n_0)
+        double k1, k2, kd;
+        fan_cell<MODE>(P, c, lx, ly, dx[0], dy[0], ld, dd[0], k1, k2, kd);
+        diag += kd;
+        carry += k1;
+        first += k2;
+      }
+      if (MODE != 0 && P.beta != 0.0) {
+        carry = fma(P.beta, old[lpos], carry);
+        first = fma(P.beta, old[pos[0]], first);
       }
       dst[lpos] = carry;
       dst[pos[0]] = first;
     }
-    if (accumulate) diag = fma(P.beta, values[v0 + posd], diag);
+    if (MODE != 0 && P.beta != 0.0) diag = fma(P.beta, old[posd], diag);
     dst[posd] = diag;
   }
   if (staged) {
     __syncwarp();
-    // last in-range lane of the warp knows the end of the range
     const unsigned ballot = __ballot_sync(0xffffffffU, in_range);
     if (ballot == 0) return;
     const int last = 31 - __clz(ballot);
     const int32_t wend = __shfl_sync(0xffffffffU, v1, last);
     const int total = wend - wbase;
     double* out = values + wbase;
-    for (int k = lane; k < total; k += 32) out[k] = stage[k];
+#pragma unroll
+    for (int k = 0; k < W + 2; ++k) {
+      const int idx = k * 32 + lane;
+      if (idx < total) out[idx] = stage[idx];
+    }
   }
 }
 
@@ -328,7 +346,7 @@ __global__ void __launch_bounds__(128) k_assemble_p1_fan(int64_t n_rows, int64_t
 int p1_fan_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
   if (p->fan_state != 0) return LFGPU_OK;
   p->fan_state = -1;
-  if (mesh->n_quad != 0 || mesh->cell_coords != nullptr || p->i_dofs != p->o_dofs || p->n_outer != mesh->n_nodes || p->n_outer >= (1LL << 31)) return LFGPU_OK;
+  if (mesh->n_quad != 0 || mesh->cell_coords != nullptr || p->i_dofs != p->o_dofs || p->n_outer != mesh->n_nodes || p->n_outer >= (1LL << 28) - 1) return LFGPU_OK;  // ids share a word with a 4-bit slot
   cudaStream_t st = ctx->stream;
   int* d_flags = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 256);
   LFGPU_CUDA_CHECK(ctx, cudaMemsetAsync(d_flags, 0, 16, st));
@@ -364,7 +382,8 @@ int p1_fan_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
     }                                                                               \
   } while (0)
   FAN_CHECK(cudaMalloc(&p->fan_nbr, sizeof(uint32_t) * static_cast<size_t>(W) * p->n_outer));
-  k_fan_fill<<<gr, 256, 0, st>>>(p->n_outer, W, p->adj_ptr, p->adj, mesh->cell_nodes, ring_len, p->fan_nbr);
+  FAN_CHECK(cudaMalloc(&p->fan_rowinfo, p->n_outer));
+  k_fan_fill<<<gr, 256, 0, st>>>(p->n_outer, W, p->adj_ptr, p->adj, mesh->cell_nodes, ring_len, p->fan_nbr, p->fan_rowinfo);
   ctx->launches++;
   FAN_CHECK(cudaMalloc(&flag, p->n_outer));
   k_flag_irregular<<<gr, 256, 0, st>>>(p->n_outer, W, ring_len, p->adj_ptr, flag);
@@ -396,8 +415,7 @@ int p1_fan_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
 int p1_fan_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, const double alpha[4], int tensor, double gamma,
                   double wsum, double m_diag, double m_off, double beta, const int32_t* row_list, int64_t n_rows, double* d_values) {
   FanParams P;
-  P.a00 = alpha[0]; P.a01 = alpha[1]; P.a10 = alpha[2]; P.a11 = alpha[3];
-  P.tensor = tensor;
+  P.a00 = alpha[0]; P.a01 = tensor ? alpha[1] : 0.0; P.a10 = tensor ? alpha[2] : 0.0; P.a11 = tensor ? alpha[3] : alpha[0];
   P.gamma = gamma;
   P.wsum = wsum;
   P.m_diag = m_diag;
@@ -409,12 +427,21 @@ int p1_fan_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p
   const unsigned grid = static_cast<unsigned>(cdiv(rows, threads));
   const int W = p->fan_w;
   const size_t smem = sizeof(double) * (threads / 32) * 32 * (W + 2);
+  const bool simple = !tensor && gamma == 0.0 && beta == 0.0;  // the plain Laplacian: leanest instantiation
+#define FAN_LAUNCH(WW)                                                                                                          \
+  if (simple)                                                                                                                   \
+    k_assemble_p1_fan<WW, 0><<<grid, threads, smem, ctx->stream>>>(rows, p->n_outer, p->fan_nbr, p->fan_rowinfo, mesh->node_coords, \
+                                                                   p->outer, row_list, P, d_values);                            \
+  else                                                                                                                          \
+    k_assemble_p1_fan<WW, 1><<<grid, threads, smem, ctx->stream>>>(rows, p->n_outer, p->fan_nbr, p->fan_rowinfo, mesh->node_coords, \
+                                                                   p->outer, row_list, P, d_values)
   switch (W) {
-    case 6: k_assemble_p1_fan<6><<<grid, threads, smem, ctx->stream>>>(rows, p->n_outer, p->fan_nbr, mesh->node_coords, p->outer, row_list, P, d_values); break;
-    case 8: k_assemble_p1_fan<8><<<grid, threads, smem, ctx->stream>>>(rows, p->n_outer, p->fan_nbr, mesh->node_coords, p->outer, row_list, P, d_values); break;
-    case 10: k_assemble_p1_fan<10><<<grid, threads, smem, ctx->stream>>>(rows, p->n_outer, p->fan_nbr, mesh->node_coords, p->outer, row_list, P, d_values); break;
-    default: k_assemble_p1_fan<12><<<grid, threads, smem, ctx->stream>>>(rows, p->n_outer, p->fan_nbr, mesh->node_coords, p->outer, row_list, P, d_values); break;
+    case 6: FAN_LAUNCH(6); break;
+    case 8: FAN_LAUNCH(8); break;
+    case 10: FAN_LAUNCH(10); break;
+    default: FAN_LAUNCH(12); break;
   }
+#undef FAN_LAUNCH
   LFGPU_LAUNCH_CHECK(ctx);
   return LFGPU_OK;
 }

@@ -84,7 +84,8 @@ struct lfgpu_pattern {
   // P1 vertex-fan plan (assemble_p1.cu), built on first use: 0 = not tried, 1 = ready, -1 = not applicable
   int fan_state = 0;
   int fan_w = 0;                     // ring slots per row
-  uint32_t* fan_nbr = nullptr;       // [fan_w][n_outer] neighbour ring of every row, slot-major; bit 31 of slot 0 = closed fan
+  uint32_t* fan_nbr = nullptr;       // [fan_w][n_outer] neighbour ring of every row, slot-major: node id | slot-in-row << 28
+  uint8_t* fan_rowinfo = nullptr;    // [n_outer] slot of the diagonal | closed-fan flag << 7
   int32_t* fan_irregular = nullptr;  // rows that are not a single fan (generic kernel)
   int64_t n_irregular = 0;
 };

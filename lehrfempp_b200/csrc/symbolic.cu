@@ -128,6 +128,7 @@ void lfgpu_pattern_destroy(lfgpu_pattern* p) {
   cudaFree(p->adj);
   cudaFree(p->pos);
   cudaFree(p->fan_nbr);
+  cudaFree(p->fan_rowinfo);
   cudaFree(p->fan_irregular);
   cudaFree(p->o_dofs);
   if (p->i_dofs != p->o_dofs) cudaFree(p->i_dofs);
