@@ -181,6 +181,22 @@ int lfgpu_assemble_reaction_diffusion_rows(lfgpu_ctx* ctx, const lfgpu_mesh* mes
 int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* dofmap, int degree,
                         const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad, const lfgpu_coeff* f, const uint8_t* active,
                         double beta, double* d_vec, int algo);
+/* ---- multi-GPU building blocks (DESIGN.md "Multi-GPU"; the reference is serial) --------------------------------------- */
+/* Row segments values[outer[r] .. outer[r+1]) of the listed rows <-> a contiguous message buffer.  d_rows device int32
+ * [n_rows], d_offsets device int64 [n_rows] = start of each row's segment inside the buffer.  unpack_add ADDS the
+ * received partial sums of interface rows into the owner's values.                                                    */
+int lfgpu_rows_pack(lfgpu_ctx* ctx, const lfgpu_pattern* pattern, const int32_t* d_rows, int64_t n_rows, const int64_t* d_offsets,
+                    const double* d_values, double* d_buf);
+int lfgpu_rows_unpack_add(lfgpu_ctx* ctx, const lfgpu_pattern* pattern, const int32_t* d_rows, int64_t n_rows,
+                          const int64_t* d_offsets, const double* d_buf, double* d_values);
+/* read-only device views used by the host-side partitioner: gather lists (items = cell << 4 | local index), mesh arrays */
+const int32_t* lfgpu_pattern_adj_ptr_device(const lfgpu_pattern* p);
+const uint32_t* lfgpu_pattern_adj_device(const lfgpu_pattern* p);
+int64_t lfgpu_pattern_num_items(const lfgpu_pattern* p);
+const double* lfgpu_mesh_node_coords_device(const lfgpu_mesh* m);
+const uint32_t* lfgpu_mesh_cell_nodes_device(const lfgpu_mesh* m);
+int lfgpu_ctx_wait_event(lfgpu_ctx* ctx, void* cuda_event); /* ctx stream waits for a cudaEvent_t recorded elsewhere */
+
 /* global coordinates of every cell's quadrature points, Geometry::Global (tria_o1.cc:70-74, quad_o1.cc:68-83):
  * d_out device [n_cells][nq_stride][2]; lets a host evaluate MeshFunctionGlobal lambdas into PER_QP tables.         */
 int lfgpu_qp_coords(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, int degree, const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad,

@@ -102,6 +102,14 @@ def _lib():
         "lfgpu_assemble_reaction_diffusion_rows": (i32, [vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), C.POINTER(_CCoeff),
                                                          C.POINTER(_CCoeff), vp, dbl, vp, i32, vp, i64]),
         "lfgpu_assemble_load": (i32, [vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), C.POINTER(_CCoeff), vp, dbl, vp, i32]),
+        "lfgpu_rows_pack": (i32, [vp, vp, vp, i64, vp, vp, vp]),
+        "lfgpu_rows_unpack_add": (i32, [vp, vp, vp, i64, vp, vp, vp]),
+        "lfgpu_pattern_adj_ptr_device": (vp, [vp]),
+        "lfgpu_pattern_adj_device": (vp, [vp]),
+        "lfgpu_pattern_num_items": (i64, [vp]),
+        "lfgpu_mesh_node_coords_device": (vp, [vp]),
+        "lfgpu_mesh_cell_nodes_device": (vp, [vp]),
+        "lfgpu_ctx_wait_event": (i32, [vp, vp]),
         "lfgpu_qp_coords": (i32, [vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), i32, vp]),
         "lfgpu_fe_tabulate": (i32, [i32, i32, C.POINTER(_CQuad), vp, vp]),
         "lfgpu_default_quad_rule": (i32, [i32, i32, i32, vp, vp]),

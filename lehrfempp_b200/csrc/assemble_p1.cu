@@ -215,7 +215,7 @@ __device__ __forceinline__ void fan_cell(const FanParams& P, double c, double ax
 
 // ring slot = node id | slot-in-row << 28;  rowinfo = slot of the diagonal | closed << 7
 template <int W, int MODE>
-__global__ void __launch_bounds__(128) k_assemble_p1_fan(int64_t n_rows, int64_t n_total_rows, const uint32_t* __restrict__ nbr,
+__global__ void __launch_bounds__(128, 8) k_assemble_p1_fan(int64_t n_rows, int64_t n_total_rows, const uint32_t* __restrict__ nbr,
                                                          const uint8_t* __restrict__ rowinfo, const double* __restrict__ node_coords,
                                                          const int32_t* __restrict__ outer, const int32_t* __restrict__ row_list,
                                                          FanParams P, double* __restrict__ values) {
@@ -242,9 +242,12 @@ __global__ void __launch_bounds__(128) k_assemble_p1_fan(int64_t n_rows, int64_t
   const int posd = info & 0x7f;
   const int32_t wbase = __shfl_sync(0xffffffffU, v0, 0);
   double* stage = stage_all + warp * (32 * (W + 2));
-  // staging: the rows of a warp are consecutive (no row list), so their values form one contiguous range that is
-  // written as full lines.  A warp that contains an irregular row (computed by the generic kernel) writes directly.
-  const bool staged = (row_list == nullptr) && !__any_sync(0xffffffffU, in_range && !regular && v1 > v0);
+  // staging: when the rows of a warp are consecutive (always without a row list, mostly with the row lists of a
+  // partition) their values form one contiguous range that is written as full lines.  A warp that contains an
+  // irregular row (computed by the generic kernel) or non-consecutive rows writes directly.
+  const int64_t r_first = __shfl_sync(0xffffffffU, r, 0);
+  const bool consecutive = (row_list == nullptr) || !__any_sync(0xffffffffU, in_range && r != r_first + lane);
+  const bool staged = consecutive && !__any_sync(0xffffffffU, in_range && !regular && v1 > v0);
   if (regular) {
     const double2* nc = reinterpret_cast<const double2*>(node_coords);
     const double2 xi = __ldg(nc + r);
