@@ -154,6 +154,15 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    # watchdog: a rank that is stuck (e.g. in a collective whose peer died) must not keep the node busy
+    def _watchdog(limit=float(os.environ.get("LFGPU_BENCH_LIMIT_S", "420"))):
+        time.sleep(limit)
+        sys.stderr.write("bench.py watchdog: rank %d exceeded %.0f s, aborting\n" % (rank, limit))
+        sys.stderr.flush()
+        os._exit(3)
+    threading.Thread(target=_watchdog, daemon=True).start()
+
     if args.impl == "reference":
         run_reference(args, rank)
         return
@@ -214,8 +223,14 @@ def main():
         asm = DistributedAssembler(ctx, mesh, pat, degree)
         t_part = time.time() - t_part
 
+    use_graph = asm is not None and os.environ.get("LFGPU_BENCH_GRAPH", "0") == "1"
+    if use_graph:
+        asm.capture(alpha, gamma, values)  # the partitioned step (4 launches + 1 collective) as one CUDA graph
+
     def step():
-        if asm is not None:
+        if use_graph:
+            asm.replay()
+        elif asm is not None:
             asm.assemble(alpha, gamma, values)
         else:
             pat.assemble_reaction_diffusion(degree, alpha, gamma, out=values, algo=algo)

@@ -197,6 +197,24 @@ class DistributedAssembler:
                                                   self.recv_buf.data_ptr(), values.ptr))
         return values
 
+    # ---- CUDA graph of one step: the partitioned step is a handful of short launches plus a collective, so at 4-8 GPUs
+    # the host launch path, not the GPUs, would set the pace.  Capturing the step once makes it one launch.
+    def capture(self, alpha, gamma, values, qr_tria=None, qr_quad=None):
+        for _ in range(2):  # warm-up outside the capture: plan building, table upload, NCCL channel setup
+            self.assemble(alpha, gamma, values, qr_tria, qr_quad)
+        self.ctx.synchronize()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=self.main, capture_error_mode="thread_local"):
+            self.assemble(alpha, gamma, values, qr_tria, qr_quad)
+        self.graph = g
+        self._graph_keep = (alpha, gamma, values, qr_tria, qr_quad)
+        return g
+
+    def replay(self):
+        with torch.cuda.stream(self.main):
+            self.graph.replay()
+
     def owned_value_mask(self, outer_host):
         """bool numpy mask over the value array: entries of rows this rank owns (for checks / gathers)."""
         owned = self.plan.owned_rows.cpu().numpy()

@@ -14,6 +14,13 @@ sys.path.insert(0, ROOT)
 
 
 def main():
+    import threading
+    import time
+
+    def _watchdog():
+        time.sleep(240)
+        os._exit(3)
+    threading.Thread(target=_watchdog, daemon=True).start()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -33,8 +40,14 @@ def main():
         pat = dm.symbolic(major=lf.ROW_MAJOR)
         asm = DistributedAssembler(ctx, gm, pat, degree)
         values = ctx.zeros(pat.nnz)
+        a, g = lf.Coeff.const(1.5), lf.Coeff.const(0.5)
         for _ in range(2):  # twice: buffers and events are reused
-            asm.assemble(lf.Coeff.const(1.5), lf.Coeff.const(0.5), values)
+            asm.assemble(a, g, values)
+        if kind == "tria_big" and os.environ.get("LFGPU_TEST_GRAPH", "0") == "1":  # opt-in: captured CUDA graph of the step
+            asm.capture(a, g, values)
+            ctx.check(ctx.L.lfgpu_memset(ctx.h, values.ptr, 0, values.nbytes))
+            asm.replay()
+            asm.replay()
         ctx.synchronize()
         torch.cuda.synchronize()
         o_outer, o_inner, o_vals, _, _ = om.assemble_rd(degree, lfo.coeff.const(1.5), lfo.coeff.const(0.5), csr=True)
