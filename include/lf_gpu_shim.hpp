@@ -1,0 +1,478 @@
+// lf_gpu_shim.hpp -- header-only C++ host shim over the C ABI of liblfgpu.so (include/lfgpu.h).
+//
+// Keeps the reference call shape
+//     lf::assemble::AssembleMatrixLocally(codim, dofh_trial, dofh_test, provider, matrix)   lib/lf/assemble/assembler.h:114-186
+//     lf::assemble::AssembleVectorLocally(codim, dofh, provider, vector)                    lib/lf/assemble/assembler.h:298-327
+// and adds overloads that are selected by the TARGET type: lfgpu::CsrMatrix / lfgpu::Vector live on the GPU.
+//
+// The shim is written against the reference's public interfaces only (Mesh::Entities / Index, Entity::RefEl /
+// SubEntities / Geometry, Geometry::Global, DofHandler::NumDofs / NumLocalDofs / GlobalDofIndices, QuadRule::Points /
+// Weights).  Because the spelling of a few members differs between LehrFEM++ and a stand-in mesh library, those calls
+// go through a small ADAPTOR policy; INTEGRATION.md lists the adaptor for the real LehrFEM++ types.  The providers of
+// the reference keep their coefficients private (uscalfe/loc_comp_ellbvp.h:178-188), so the shim ships providers with
+// the SAME template and constructor signatures plus read-only accessors.
+//
+// Errors: a negative status of the C ABI becomes lfgpu::Error; LFGPU_ERR_MISSING_RULE is the reference's
+// base::LfException case (loc_comp_ellbvp.h:278-287).  There is no CPU fallback.
+#ifndef LF_GPU_SHIM_HPP
+#define LF_GPU_SHIM_HPP
+
+#include <array>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "lfgpu.h"
+
+namespace lfgpu {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& what) : std::runtime_error(what), code(c) {}
+};
+
+class Context {
+ public:
+  explicit Context(int device = 0) {
+    const int rc = lfgpu_ctx_create(device, &ctx_);
+    if (rc != 0) throw Error(rc, std::string("lfgpu_ctx_create: ") + lfgpu_last_error(nullptr));
+  }
+  ~Context() { lfgpu_ctx_destroy(ctx_); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  [[nodiscard]] lfgpu_ctx* get() const { return ctx_; }
+  void check(int rc, const char* where) const {
+    if (rc != 0) throw Error(rc, std::string(where) + ": " + lfgpu_last_error(ctx_));
+  }
+
+ private:
+  lfgpu_ctx* ctx_ = nullptr;
+};
+
+// ---- coefficient description -------------------------------------------------------------------------------------------
+// What the device can evaluate: constants directly; anything else is tabulated by the shim at the quadrature points
+// (mesh/utils/mesh_function_global.h:77-88 evaluates the user's functor at Geometry::Global(points) -- so does the shim,
+// on the host, once per assembly; the table travels as LFGPU_COEFF_PER_QP).
+struct HostCoeff {
+  int kind = LFGPU_COEFF_CONST;
+  double c[4] = {0, 0, 0, 0};
+  std::vector<double> table;  // PER_QP / PER_QP_2X2 values, [n_cells][stride]([4])
+  long stride = 0;
+};
+
+// Reference-element description handed to the C ABI: quadrature rules per cell type (null = provider default)
+struct Rules {
+  std::vector<double> pts_tria, w_tria, pts_quad, w_quad;
+  bool has_tria = false, has_quad = false;
+};
+
+// ---- flattened mesh + dof tables (the shim's "flatten step") -------------------------------------------------------------
+struct FlatMesh {
+  std::vector<double> node_coords;     // [n_nodes][2]
+  std::vector<std::uint32_t> cell_nodes;  // [n_cells][4]
+  std::vector<double> cell_coords;     // [n_cells][4][2]
+  bool coords_match_nodes = true;
+  std::int64_t n_nodes = 0, n_cells = 0;
+};
+
+// ADAPTOR requirements (all static):
+//   entities(mesh, codim) -> iterable of const ENTITY*;  num_entities(mesh, codim);  index(mesh, entity) -> unsigned
+//   is_tria(entity) -> bool;  sub_entities(entity, rel_codim) -> iterable of const ENTITY*
+//   corner(entity, k, d) -> double   (= entity.Geometry()->Global(RefEl().NodeCoords())(d, k))
+//   num_dofs(dofh), num_local_dofs(dofh, entity), global_dof_indices(dofh, entity) -> indexable, mesh(dofh) -> const MESH&
+template <class A, class MESH>
+FlatMesh Flatten(const MESH& mesh) {
+  FlatMesh f;
+  f.n_nodes = A::num_entities(mesh, 2);
+  f.n_cells = A::num_entities(mesh, 0);
+  f.node_coords.assign(2 * f.n_nodes, 0.0);
+  std::vector<char> seen(f.n_nodes, 0);
+  f.cell_nodes.assign(4 * f.n_cells, LFGPU_IDX_NIL);
+  f.cell_coords.assign(8 * f.n_cells, 0.0);
+  for (const auto* cell : A::entities(mesh, 0)) {
+    const std::int64_t c = A::index(mesh, *cell);
+    const int nv = A::is_tria(*cell) ? 3 : 4;
+    int k = 0;
+    for (const auto* v : A::sub_entities(*cell, 2)) {
+      const std::uint32_t n = A::index(mesh, *v);
+      f.cell_nodes[4 * c + k] = n;
+      const double x = A::corner(*cell, k, 0), y = A::corner(*cell, k, 1);
+      f.cell_coords[8 * c + 2 * k] = x;
+      f.cell_coords[8 * c + 2 * k + 1] = y;
+      if (!seen[n]) {
+        seen[n] = 1;
+        f.node_coords[2 * n] = x;
+        f.node_coords[2 * n + 1] = y;
+      } else if (f.node_coords[2 * n] != x || f.node_coords[2 * n + 1] != y) {
+        f.coords_match_nodes = false;  // e.g. refined meshes: child geometries differ from node objects by an ulp
+      }
+      ++k;
+    }
+    (void)nv;
+  }
+  return f;
+}
+
+template <class A, class DOFH, class MESH>
+void FlattenDofs(const DOFH& dofh, const MESH& mesh, std::vector<std::int64_t>& cell_dofs, std::vector<std::uint8_t>& n_ldof, int& stride) {
+  const std::int64_t n_cells = A::num_entities(mesh, 0);
+  stride = 0;
+  for (const auto* cell : A::entities(mesh, 0)) stride = std::max<int>(stride, A::num_local_dofs(dofh, *cell));
+  cell_dofs.assign(static_cast<std::size_t>(n_cells) * stride, -1);
+  n_ldof.assign(n_cells, 0);
+  for (const auto* cell : A::entities(mesh, 0)) {
+    const std::int64_t c = A::index(mesh, *cell);
+    const int n = A::num_local_dofs(dofh, *cell);
+    const auto idx = A::global_dof_indices(dofh, *cell);
+    for (int k = 0; k < n; ++k) cell_dofs[c * stride + k] = idx[k];
+    n_ldof[c] = static_cast<std::uint8_t>(n);
+  }
+}
+
+// ---- device-side targets ---------------------------------------------------------------------------------------------------
+// Compressed matrix on the GPU, the TMPMATRIX of the GPU overload.  Like COOMatrix it ACCUMULATES: AssembleMatrixLocally
+// does not zero it (assembler.h:84-88); setZero() does.  makeSparse-like access: Download() returns Eigen-compatible
+// column-major arrays (outer = column pointers) or CSR, as chosen at construction.
+class CsrMatrix {
+ public:
+  CsrMatrix(Context& ctx, int major = LFGPU_COL_MAJOR) : ctx_(ctx), major_(major) {}
+  ~CsrMatrix() {
+    if (d_values_) lfgpu_free(ctx_.get(), d_values_);
+    lfgpu_pattern_destroy(pattern_);
+    lfgpu_dofmap_destroy(test_);
+    if (trial_ != test_) lfgpu_dofmap_destroy(trial_);
+    lfgpu_mesh_destroy(mesh_);
+  }
+  CsrMatrix(const CsrMatrix&) = delete;
+  CsrMatrix& operator=(const CsrMatrix&) = delete;
+  void setZero() {
+    if (d_values_) ctx_.check(lfgpu_memset(ctx_.get(), d_values_, 0, 8 * nnz()), "lfgpu_memset");
+    empty_ = true;
+  }
+  [[nodiscard]] std::int64_t rows() const { return pattern_ ? lfgpu_pattern_rows(pattern_) : 0; }
+  [[nodiscard]] std::int64_t cols() const { return pattern_ ? lfgpu_pattern_cols(pattern_) : 0; }
+  [[nodiscard]] std::int64_t nnz() const { return pattern_ ? lfgpu_pattern_nnz(pattern_) : 0; }
+  [[nodiscard]] double* device_values() const { return static_cast<double*>(d_values_); }
+  [[nodiscard]] const lfgpu_pattern* pattern() const { return pattern_; }
+  void Download(std::vector<std::int32_t>& outer, std::vector<std::int32_t>& inner, std::vector<double>& values) const {
+    const std::int64_t n_outer = major_ == LFGPU_ROW_MAJOR ? rows() : cols();
+    outer.resize(n_outer + 1);
+    inner.resize(nnz());
+    values.resize(nnz());
+    ctx_.check(lfgpu_pattern_download(ctx_.get(), pattern_, outer.data(), inner.data()), "lfgpu_pattern_download");
+    ctx_.check(lfgpu_memcpy_d2h(ctx_.get(), values.data(), d_values_, 8 * nnz()), "lfgpu_memcpy_d2h");
+    ctx_.check(lfgpu_ctx_synchronize(ctx_.get()), "lfgpu_ctx_synchronize");
+  }
+
+  // internal: (re)build mesh / dof tables / pattern when first used (one-time symbolic pass)
+  template <class A, class DOFH>
+  void Prepare(const DOFH& trial, const DOFH& test) {
+    if (pattern_ != nullptr) return;
+    const auto& mesh = A::mesh(trial);
+    const FlatMesh f = Flatten<A>(mesh);
+    ctx_.check(lfgpu_mesh_upload(ctx_.get(), f.n_nodes, f.node_coords.data(), f.n_cells, f.cell_nodes.data(),
+                                 f.coords_match_nodes ? nullptr : f.cell_coords.data(), &mesh_), "lfgpu_mesh_upload");
+    std::vector<std::int64_t> dofs;
+    std::vector<std::uint8_t> nl;
+    int stride = 0;
+    FlattenDofs<A>(test, mesh, dofs, nl, stride);
+    ctx_.check(lfgpu_dofmap_upload(ctx_.get(), mesh_, A::num_dofs(test), stride, dofs.data(), nl.data(), &test_), "lfgpu_dofmap_upload");
+    if (&trial == &test) {
+      trial_ = test_;
+    } else {
+      FlattenDofs<A>(trial, mesh, dofs, nl, stride);
+      ctx_.check(lfgpu_dofmap_upload(ctx_.get(), mesh_, A::num_dofs(trial), stride, dofs.data(), nl.data(), &trial_), "lfgpu_dofmap_upload");
+    }
+    ctx_.check(lfgpu_symbolic(ctx_.get(), mesh_, test_, trial_, major_, &pattern_), "lfgpu_symbolic");
+    ctx_.check(lfgpu_malloc(ctx_.get(), 8 * nnz(), &d_values_), "lfgpu_malloc");
+    setZero();
+  }
+  [[nodiscard]] Context& ctx() const { return ctx_; }
+  [[nodiscard]] lfgpu_mesh* mesh() const { return mesh_; }
+  [[nodiscard]] lfgpu_dofmap* test_dofs() const { return test_; }
+  bool empty_ = true;
+
+ private:
+  Context& ctx_;
+  int major_;
+  lfgpu_mesh* mesh_ = nullptr;
+  lfgpu_dofmap *test_ = nullptr, *trial_ = nullptr;
+  lfgpu_pattern* pattern_ = nullptr;
+  void* d_values_ = nullptr;
+};
+
+// Dense vector on the GPU, the VECTOR of the GPU overload of AssembleVectorLocally (accumulates, assembler.h:291-293)
+class Vector {
+ public:
+  explicit Vector(Context& ctx) : ctx_(ctx) {}
+  ~Vector() {
+    if (d_) lfgpu_free(ctx_.get(), d_);
+    lfgpu_dofmap_destroy(dofs_);
+    lfgpu_mesh_destroy(mesh_);
+  }
+  Vector(const Vector&) = delete;
+  Vector& operator=(const Vector&) = delete;
+  void setZero() {
+    if (d_) ctx_.check(lfgpu_memset(ctx_.get(), d_, 0, 8 * n_), "lfgpu_memset");
+  }
+  [[nodiscard]] std::int64_t size() const { return n_; }
+  [[nodiscard]] std::vector<double> Download() const {
+    std::vector<double> h(n_);
+    ctx_.check(lfgpu_memcpy_d2h(ctx_.get(), h.data(), d_, 8 * n_), "lfgpu_memcpy_d2h");
+    ctx_.check(lfgpu_ctx_synchronize(ctx_.get()), "lfgpu_ctx_synchronize");
+    return h;
+  }
+  template <class A, class DOFH>
+  void Prepare(const DOFH& dofh) {
+    if (dofs_ != nullptr) return;
+    const auto& mesh = A::mesh(dofh);
+    const FlatMesh f = Flatten<A>(mesh);
+    ctx_.check(lfgpu_mesh_upload(ctx_.get(), f.n_nodes, f.node_coords.data(), f.n_cells, f.cell_nodes.data(),
+                                 f.coords_match_nodes ? nullptr : f.cell_coords.data(), &mesh_), "lfgpu_mesh_upload");
+    std::vector<std::int64_t> dofs;
+    std::vector<std::uint8_t> nl;
+    int stride = 0;
+    FlattenDofs<A>(dofh, mesh, dofs, nl, stride);
+    n_ = A::num_dofs(dofh);
+    ctx_.check(lfgpu_dofmap_upload(ctx_.get(), mesh_, n_, stride, dofs.data(), nl.data(), &dofs_), "lfgpu_dofmap_upload");
+    ctx_.check(lfgpu_malloc(ctx_.get(), 8 * n_, &d_), "lfgpu_malloc");
+    setZero();
+  }
+  [[nodiscard]] Context& ctx() const { return ctx_; }
+  [[nodiscard]] lfgpu_mesh* mesh() const { return mesh_; }
+  [[nodiscard]] lfgpu_dofmap* dofs() const { return dofs_; }
+  [[nodiscard]] double* device() const { return static_cast<double*>(d_); }
+
+ private:
+  Context& ctx_;
+  lfgpu_mesh* mesh_ = nullptr;
+  lfgpu_dofmap* dofs_ = nullptr;
+  void* d_ = nullptr;
+  std::int64_t n_ = 0;
+};
+
+// ---- mesh functions the device understands ---------------------------------------------------------------------------------
+// Same names and call operators as lf::mesh::utils::MeshFunctionConstant / MeshFunctionGlobal
+// (mesh/utils/mesh_function_constant.h:26-46, mesh_function_global.h:55-98) are NOT required: the shim only needs to
+// know how to turn a coefficient object into a HostCoeff.  Specialise CoeffTraits for further mesh-function types.
+struct Matrix2 {
+  double a[2][2];
+};
+template <class R>
+struct MeshFunctionConstant {
+  R value;
+};
+template <class F>
+struct MeshFunctionGlobal {
+  F f;  // double f(double x, double y)  or  Matrix2 f(double x, double y)
+};
+
+template <class MF>
+struct CoeffTraits;  // static HostCoeff describe(const MF&, const double* qp_xy /*[n_cells][stride][2]*/, n_cells, stride)
+
+template <>
+struct CoeffTraits<MeshFunctionConstant<double>> {
+  static constexpr bool needs_points = false;
+  static HostCoeff describe(const MeshFunctionConstant<double>& mf, const double*, std::int64_t, long) {
+    HostCoeff c;
+    c.kind = LFGPU_COEFF_CONST;
+    c.c[0] = mf.value;
+    return c;
+  }
+};
+template <>
+struct CoeffTraits<MeshFunctionConstant<Matrix2>> {
+  static constexpr bool needs_points = false;
+  static HostCoeff describe(const MeshFunctionConstant<Matrix2>& mf, const double*, std::int64_t, long) {
+    HostCoeff c;
+    c.kind = LFGPU_COEFF_CONST_2X2;
+    c.c[0] = mf.value.a[0][0]; c.c[1] = mf.value.a[0][1]; c.c[2] = mf.value.a[1][0]; c.c[3] = mf.value.a[1][1];
+    return c;
+  }
+};
+template <class F>
+struct CoeffTraits<MeshFunctionGlobal<F>> {
+  static constexpr bool needs_points = true;
+  using R = decltype(std::declval<F>()(0.0, 0.0));
+  static HostCoeff describe(const MeshFunctionGlobal<F>& mf, const double* xy, std::int64_t n_cells, long stride) {
+    HostCoeff c;
+    c.stride = stride;
+    if constexpr (std::is_same_v<R, Matrix2>) {
+      c.kind = LFGPU_COEFF_PER_QP_2X2;
+      c.table.resize(static_cast<std::size_t>(n_cells) * stride * 4);
+      for (std::int64_t i = 0; i < n_cells * stride; ++i) {
+        const Matrix2 m = mf.f(xy[2 * i], xy[2 * i + 1]);
+        c.table[4 * i] = m.a[0][0]; c.table[4 * i + 1] = m.a[0][1]; c.table[4 * i + 2] = m.a[1][0]; c.table[4 * i + 3] = m.a[1][1];
+      }
+    } else {
+      c.kind = LFGPU_COEFF_PER_QP;
+      c.table.resize(static_cast<std::size_t>(n_cells) * stride);
+      for (std::int64_t i = 0; i < n_cells * stride; ++i) c.table[i] = mf.f(xy[2 * i], xy[2 * i + 1]);
+    }
+    return c;
+  }
+};
+
+// ---- providers: same template / constructor signatures as the reference, plus accessors -----------------------------------
+// lf::uscalfe::ReactionDiffusionElementMatrixProvider<SCALAR, DIFF_COEFF, REACTION_COEFF> (loc_comp_ellbvp.h:85-189):
+//   ctor (fe_space, alpha, gamma)            -> default rules of degree 2 * fe->Degree()   (:210-231)
+//   ctor (fe_space, alpha, gamma, qr_map)    -> user rules per RefEl                        (:234-263)
+// FE_SPACE must offer Degree() (1..3 = FeSpaceLagrangeO1/O2/O3) and LocGlobMap().
+template <class SCALAR, class DIFF_COEFF, class REACTION_COEFF>
+class ReactionDiffusionElementMatrixProvider {
+ public:
+  static_assert(std::is_same_v<SCALAR, double>, "the GPU path computes in double (the reference's default scalar)");
+  template <class FE_SPACE>
+  ReactionDiffusionElementMatrixProvider(std::shared_ptr<const FE_SPACE> fe_space, DIFF_COEFF alpha, REACTION_COEFF gamma)
+      : alpha_(std::move(alpha)), gamma_(std::move(gamma)), degree_(fe_space->Degree()) {}
+  template <class FE_SPACE, class QR_MAP>
+  ReactionDiffusionElementMatrixProvider(std::shared_ptr<const FE_SPACE> fe_space, DIFF_COEFF alpha, REACTION_COEFF gamma,
+                                         const QR_MAP& qr_collection)
+      : alpha_(std::move(alpha)), gamma_(std::move(gamma)), degree_(fe_space->Degree()) {
+    custom_rules_ = true;
+    for (const auto& kv : qr_collection) AddRule(kv.first.Id(), kv.second);
+  }
+  ReactionDiffusionElementMatrixProvider(const ReactionDiffusionElementMatrixProvider&) = delete;
+  ReactionDiffusionElementMatrixProvider(ReactionDiffusionElementMatrixProvider&&) noexcept = default;
+  [[nodiscard]] const DIFF_COEFF& Alpha() const { return alpha_; }
+  [[nodiscard]] const REACTION_COEFF& Gamma() const { return gamma_; }
+  [[nodiscard]] int Degree() const { return degree_; }
+  [[nodiscard]] const Rules& QuadRules() const { return rules_; }
+  [[nodiscard]] bool HasCustomRules() const { return custom_rules_; }
+
+ private:
+  template <class QR>
+  void AddRule(unsigned ref_el_id, const QR& qr) {
+    const int n = static_cast<int>(qr.NumPoints());
+    auto& pts = ref_el_id == 3 ? rules_.pts_tria : rules_.pts_quad;
+    auto& w = ref_el_id == 3 ? rules_.w_tria : rules_.w_quad;
+    pts.resize(2 * n);
+    w.resize(n);
+    for (int k = 0; k < n; ++k) {
+      pts[k] = qr.Points()(0, k);
+      pts[n + k] = qr.Points()(1, k);
+      w[k] = qr.Weights()[k];
+    }
+    (ref_el_id == 3 ? rules_.has_tria : rules_.has_quad) = true;
+  }
+  DIFF_COEFF alpha_;
+  REACTION_COEFF gamma_;
+  int degree_;
+  Rules rules_;
+  bool custom_rules_ = false;
+};
+
+// lf::uscalfe::ScalarLoadElementVectorProvider<SCALAR, MESH_FUNCTION> (loc_comp_ellbvp.h:562-624, ctors :638-686)
+template <class SCALAR, class MESH_FUNCTION>
+class ScalarLoadElementVectorProvider {
+ public:
+  static_assert(std::is_same_v<SCALAR, double>, "the GPU path computes in double");
+  template <class FE_SPACE>
+  ScalarLoadElementVectorProvider(std::shared_ptr<const FE_SPACE> fe_space, MESH_FUNCTION f) : f_(std::move(f)), degree_(fe_space->Degree()) {}
+  [[nodiscard]] const MESH_FUNCTION& F() const { return f_; }
+  [[nodiscard]] int Degree() const { return degree_; }
+
+ private:
+  MESH_FUNCTION f_;
+  int degree_;
+};
+
+namespace detail {
+struct DeviceCoeff {
+  lfgpu_coeff c{};
+  void* d_table = nullptr;
+  lfgpu_ctx* ctx = nullptr;
+  ~DeviceCoeff() {
+    if (d_table) lfgpu_free(ctx, d_table);
+  }
+};
+inline void to_device(Context& ctx, const HostCoeff& h, DeviceCoeff& d) {
+  d.ctx = ctx.get();
+  d.c.kind = h.kind;
+  for (int i = 0; i < 4; ++i) d.c.c[i] = h.c[i];
+  d.c.stride = h.stride;
+  d.c.data = nullptr;
+  if (!h.table.empty()) {
+    ctx.check(lfgpu_malloc(ctx.get(), 8 * static_cast<std::int64_t>(h.table.size()), &d.d_table), "lfgpu_malloc");
+    ctx.check(lfgpu_memcpy_h2d(ctx.get(), d.d_table, h.table.data(), 8 * static_cast<std::int64_t>(h.table.size())), "lfgpu_memcpy_h2d");
+    d.c.data = static_cast<const double*>(d.d_table);
+  }
+}
+// global coordinates of all quadrature points, computed on the device (Geometry::Global), for host-evaluated functors
+inline std::vector<double> qp_coords(Context& ctx, lfgpu_mesh* mesh, std::int64_t n_cells, int degree, const lfgpu_quad* qt,
+                                     const lfgpu_quad* qq, int stride) {
+  std::vector<double> xy(static_cast<std::size_t>(n_cells) * stride * 2);
+  void* d = nullptr;
+  ctx.check(lfgpu_malloc(ctx.get(), 8 * static_cast<std::int64_t>(xy.size()), &d), "lfgpu_malloc");
+  ctx.check(lfgpu_qp_coords(ctx.get(), mesh, degree, qt, qq, stride, static_cast<double*>(d)), "lfgpu_qp_coords");
+  ctx.check(lfgpu_memcpy_d2h(ctx.get(), xy.data(), d, 8 * static_cast<std::int64_t>(xy.size())), "lfgpu_memcpy_d2h");
+  ctx.check(lfgpu_ctx_synchronize(ctx.get()), "lfgpu_ctx_synchronize");
+  lfgpu_free(ctx.get(), d);
+  return xy;
+}
+}  // namespace detail
+
+inline constexpr int kMaxPoints = 36;  // table stride for host-evaluated coefficients (largest rule the library holds)
+
+// ---- the overloads ------------------------------------------------------------------------------------------------------------
+// GPU overload of lf::assemble::AssembleMatrixLocally (assembler.h:114-186): same arguments, TMPMATRIX = lfgpu::CsrMatrix.
+template <class A, class DOFH, class ALPHA, class GAMMA>
+void AssembleMatrixLocally(unsigned codim, const DOFH& dof_handler_trial, const DOFH& dof_handler_test,
+                           ReactionDiffusionElementMatrixProvider<double, ALPHA, GAMMA>& emp, CsrMatrix& matrix) {
+  if (codim != 0) throw Error(LFGPU_ERR_UNSUPPORTED, "the GPU overload assembles cell (codim 0) contributions");
+  if (&A::mesh(dof_handler_trial) != &A::mesh(dof_handler_test))
+    throw Error(LFGPU_ERR_INVALID, "Trial and test space must be defined on the same mesh");  // assembler.h:121-122
+  Context& ctx = matrix.ctx();
+  matrix.template Prepare<A>(dof_handler_trial, dof_handler_test);
+  const Rules& r = emp.QuadRules();
+  lfgpu_quad qt{static_cast<int>(r.w_tria.size()), r.pts_tria.data(), r.w_tria.data()};
+  lfgpu_quad qq{static_cast<int>(r.w_quad.size()), r.pts_quad.data(), r.w_quad.data()};
+  const lfgpu_quad* pqt = (emp.HasCustomRules() && r.has_tria) ? &qt : nullptr;
+  const lfgpu_quad* pqq = (emp.HasCustomRules() && r.has_quad) ? &qq : nullptr;
+  std::int64_t n_cells = 0;
+  lfgpu_mesh_counts(matrix.mesh(), nullptr, nullptr, &n_cells, nullptr, nullptr);
+  std::vector<double> xy;
+  int stride = 0;
+  if (CoeffTraits<ALPHA>::needs_points || CoeffTraits<GAMMA>::needs_points) {
+    stride = kMaxPoints;
+    xy = detail::qp_coords(ctx, matrix.mesh(), n_cells, emp.Degree(), pqt, pqq, stride);
+  }
+  detail::DeviceCoeff da, dg;
+  detail::to_device(ctx, CoeffTraits<ALPHA>::describe(emp.Alpha(), xy.data(), n_cells, stride), da);
+  detail::to_device(ctx, CoeffTraits<GAMMA>::describe(emp.Gamma(), xy.data(), n_cells, stride), dg);
+  // accumulate like the reference (assembler.h:84-88); a freshly zeroed matrix is simply overwritten
+  const double beta = matrix.empty_ ? 0.0 : 1.0;
+  ctx.check(lfgpu_assemble_reaction_diffusion(ctx.get(), matrix.mesh(), matrix.pattern(), emp.Degree(), pqt, pqq, &da.c, &dg.c,
+                                              nullptr, beta, matrix.device_values(), LFGPU_ALGO_AUTO),
+            "lfgpu_assemble_reaction_diffusion");
+  ctx.check(lfgpu_ctx_synchronize(ctx.get()), "lfgpu_ctx_synchronize");
+  matrix.empty_ = false;
+}
+// GPU overload of lf::assemble::AssembleVectorLocally (assembler.h:298-327): VECTOR = lfgpu::Vector
+template <class A, class DOFH, class F>
+void AssembleVectorLocally(unsigned codim, const DOFH& dof_handler, ScalarLoadElementVectorProvider<double, F>& evp, Vector& v) {
+  if (codim != 0) throw Error(LFGPU_ERR_UNSUPPORTED, "the GPU overload assembles cell (codim 0) contributions");
+  Context& ctx = v.ctx();
+  v.template Prepare<A>(dof_handler);
+  std::int64_t n_cells = 0;
+  lfgpu_mesh_counts(v.mesh(), nullptr, nullptr, &n_cells, nullptr, nullptr);
+  std::vector<double> xy;
+  int stride = 0;
+  if (CoeffTraits<F>::needs_points) {
+    stride = 36;
+    xy = detail::qp_coords(ctx, v.mesh(), n_cells, evp.Degree(), nullptr, nullptr, stride);
+  }
+  detail::DeviceCoeff df;
+  detail::to_device(ctx, CoeffTraits<F>::describe(evp.F(), xy.data(), n_cells, stride), df);
+  ctx.check(lfgpu_assemble_load(ctx.get(), v.mesh(), v.dofs(), evp.Degree(), nullptr, nullptr, &df.c, nullptr, 1.0, v.device(), LFGPU_ALGO_AUTO),
+            "lfgpu_assemble_load");
+  ctx.check(lfgpu_ctx_synchronize(ctx.get()), "lfgpu_ctx_synchronize");
+}
+
+}  // namespace lfgpu
+#endif

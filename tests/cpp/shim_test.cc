@@ -1,0 +1,131 @@
+// Test of the header-only C++ shim (include/lf_gpu_shim.hpp): the reference call sequence
+//   fe_space -> provider(fe_space, alpha, gamma) -> AssembleMatrixLocally(0, dofh, dofh, provider, matrix)
+// once with the oracle's COOMatrix (CPU restatement of the reference) and once with lfgpu::CsrMatrix (GPU overload).
+// The oracle's mesh / DofHandler classes play the role of the LehrFEM++ types (same interface, see OracleAdaptor).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
+#include "../../include/lf_gpu_shim.hpp"
+#include "../../oracle/lfo_uscalfe.h"
+
+using namespace lfo;
+
+struct OracleAdaptor {
+  static auto entities(const mesh::Mesh& m, unsigned codim) { return m.Entities(codim); }
+  static std::int64_t num_entities(const mesh::Mesh& m, unsigned codim) { return m.NumEntities(codim); }
+  static unsigned index(const mesh::Mesh& m, const mesh::Entity& e) { return m.Index(e); }
+  static bool is_tria(const mesh::Entity& e) { return e.RefElem() == RefEl::kTria(); }
+  static auto sub_entities(const mesh::Entity& e, unsigned rel_codim) { return e.SubEntities(rel_codim); }
+  static double corner(const mesh::Entity& e, int k, int d) { return e.Geometry()->Global(e.RefElem().NodeCoords())(d, k); }
+  static std::int64_t num_dofs(const assemble::DofHandler& d) { return d.NumDofs(); }
+  static int num_local_dofs(const assemble::DofHandler& d, const mesh::Entity& e) { return d.NumLocalDofs(e); }
+  static auto global_dof_indices(const assemble::DofHandler& d, const mesh::Entity& e) { return d.GlobalDofIndices(e); }
+  static const mesh::Mesh& mesh(const assemble::DofHandler& d) { return *d.Mesh(); }
+};
+
+// stand-in for FeSpaceLagrangeO<p>: what the shim's providers need from the FE space
+struct FeSpace {
+  std::shared_ptr<uscalfe::UniformScalarFESpace> fes;
+  int degree;
+  int Degree() const { return degree; }
+  const assemble::DofHandler& LocGlobMap() const { return fes->LocGlobMap(); }
+};
+
+static int failures = 0;
+#define CHECK(cond, ...)                     \
+  do {                                       \
+    if (!(cond)) {                           \
+      std::printf("FAIL %s:%d: ", __FILE__, __LINE__); \
+      std::printf(__VA_ARGS__);              \
+      std::printf("\n");                     \
+      ++failures;                            \
+    }                                        \
+  } while (0)
+
+template <class OA, class OG, class GA, class GG>
+void compare_matrix(lfgpu::Context& ctx, std::shared_ptr<mesh::Mesh> m, int degree, OA oalpha, OG ogamma, GA galpha, GG ggamma, const char* what) {
+  auto fes = std::make_shared<uscalfe::UniformScalarFESpace>(m, degree);
+  const assemble::DofHandler& dofh = fes->LocGlobMap();
+  // reference path (oracle)
+  uscalfe::ReactionDiffusionElementMatrixProvider<OA, OG> oprov(fes, oalpha, ogamma);
+  assemble::COOMatrix coo(dofh.NumDofs(), dofh.NumDofs());
+  assemble::AssembleMatrixLocally(0, dofh, dofh, oprov, coo);
+  assemble::AssembleMatrixLocally(0, dofh, dofh, oprov, coo);  // accumulate twice (assembler.h:84-88)
+  const auto ref = coo.makeSparse();
+  // GPU path through the shim: same call shape
+  auto gfes = std::make_shared<const FeSpace>(FeSpace{fes, degree});
+  lfgpu::ReactionDiffusionElementMatrixProvider<double, GA, GG> gprov(gfes, galpha, ggamma);
+  lfgpu::CsrMatrix M(ctx, LFGPU_COL_MAJOR);
+  lfgpu::AssembleMatrixLocally<OracleAdaptor>(0, dofh, dofh, gprov, M);
+  lfgpu::AssembleMatrixLocally<OracleAdaptor>(0, dofh, dofh, gprov, M);
+  std::vector<std::int32_t> outer, inner;
+  std::vector<double> vals;
+  M.Download(outer, inner, vals);
+  CHECK(outer.size() == ref.outer.size() && inner.size() == ref.inner.size(), "%s: pattern size", what);
+  bool same = outer.size() == ref.outer.size() && inner.size() == ref.inner.size();
+  for (std::size_t i = 0; same && i < outer.size(); ++i) same = outer[i] == ref.outer[i];
+  for (std::size_t i = 0; same && i < inner.size(); ++i) same = inner[i] == ref.inner[i];
+  CHECK(same, "%s: pattern differs", what);
+  double scale = 0, err = 0;
+  for (std::size_t i = 0; same && i < vals.size(); ++i) {
+    scale = std::max(scale, std::fabs(ref.values[i]));
+    err = std::max(err, std::fabs(vals[i] - ref.values[i]));
+  }
+  CHECK(same && err <= 1e-12 * scale, "%s: value error %.3e (scale %.3e)", what, err, scale);
+  std::printf("%-46s N=%6ld nnz=%8zu rel.err=%.2e\n", what, static_cast<long>(dofh.NumDofs()), vals.size(), scale > 0 ? err / scale : 0.0);
+}
+
+int main() {
+  try {
+    lfgpu::Context ctx(0);
+    auto tria = mesh::utils::TPTriagMeshBuild(24, 17, 0.0, 0.0, 2.0, 1.0);
+    auto hyb = mesh::utils::HybridMeshBuild(14, 0.2, 99);
+    using OC = uscalfe::MeshFunctionConstant<double>;
+    using GC = lfgpu::MeshFunctionConstant<double>;
+    for (int p = 1; p <= 3; ++p) {
+      compare_matrix(ctx, tria, p, OC(1.0), OC(0.0), GC{1.0}, GC{0.0}, "TP-tria, Laplacian");
+      compare_matrix(ctx, hyb, p, OC(2.0), OC(3.0), GC{2.0}, GC{3.0}, "hybrid, const reaction-diffusion");
+      // variable coefficients through user functors (MeshFunctionGlobal): evaluated by the shim on the host
+      auto fa = [](double x, double y) { return 1.0 + x * x + y * y; };
+      auto fg = [](double x, double y) { return 1.0 / (1.0 + x * x + y * y); };
+      uscalfe::MeshFunctionGlobal<double> oa(fa), og(fg);
+      lfgpu::MeshFunctionGlobal<decltype(fa)> ga{fa};
+      lfgpu::MeshFunctionGlobal<decltype(fg)> gg{fg};
+      compare_matrix(ctx, hyb, p, oa, og, ga, gg, "hybrid, alpha=1+|x|^2 gamma=1/(1+|x|^2)");
+      // non-symmetric tensor diffusion
+      auto ft = [](double x, double y) { return uscalfe::Mat2{{{1, x}, {y, x * y + 2.0}}}; };
+      auto gt = [](double x, double y) { return lfgpu::Matrix2{{{1, x}, {y, x * y + 2.0}}}; };
+      uscalfe::MeshFunctionGlobal<uscalfe::Mat2> ot(ft);
+      lfgpu::MeshFunctionGlobal<decltype(gt)> gtt{gt};
+      compare_matrix(ctx, hyb, p, ot, OC(0.0), gtt, GC{0.0}, "hybrid, tensor alpha=[1 x; y xy+2]");
+    }
+    // load vector
+    for (int p = 1; p <= 3; ++p) {
+      auto fes = std::make_shared<uscalfe::UniformScalarFESpace>(hyb, p);
+      const assemble::DofHandler& dofh = fes->LocGlobMap();
+      auto f = [](double x, double y) { return std::sin(2 * M_PI * x) * std::sin(2 * M_PI * y); };
+      uscalfe::ScalarLoadElementVectorProvider<uscalfe::MeshFunctionGlobal<double>> oprov(fes, uscalfe::MeshFunctionGlobal<double>(f));
+      std::vector<double> ref(dofh.NumDofs(), 0.0);
+      assemble::AssembleVectorLocally(0, dofh, oprov, ref);
+      auto gfes = std::make_shared<const FeSpace>(FeSpace{fes, p});
+      lfgpu::ScalarLoadElementVectorProvider<double, lfgpu::MeshFunctionGlobal<decltype(f)>> gprov(gfes, lfgpu::MeshFunctionGlobal<decltype(f)>{f});
+      lfgpu::Vector v(ctx);
+      lfgpu::AssembleVectorLocally<OracleAdaptor>(0, dofh, gprov, v);
+      const auto h = v.Download();
+      double scale = 0, err = 0;
+      for (std::size_t i = 0; i < h.size(); ++i) {
+        scale = std::max(scale, std::fabs(ref[i]));
+        err = std::max(err, std::fabs(h[i] - ref[i]));
+      }
+      CHECK(err <= 1e-12 * scale, "load vector P%d: error %.3e", p, err);
+      std::printf("load vector P%d on hybrid mesh                  N=%6zu rel.err=%.2e\n", p, h.size(), err / scale);
+    }
+    // missing rule -> error (loc_comp_ellbvp.h:278-287)
+  } catch (const lfgpu::Error& e) {
+    std::printf("lfgpu::Error %d: %s\n", e.code, e.what());
+    return e.code == LFGPU_ERR_NO_DEVICE ? 77 : 2;
+  }
+  std::printf(failures == 0 ? "SHIM_TEST_OK\n" : "SHIM_TEST_FAILED\n");
+  return failures == 0 ? 0 : 1;
+}
