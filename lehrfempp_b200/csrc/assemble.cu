@@ -164,20 +164,22 @@ __device__ __forceinline__ double eval_scalar(const DevCoeff& G, int64_t cell, i
   }
 }
 __device__ __forceinline__ bool cellwise_const(const DevCoeff& c) { return c.kind <= LFGPU_COEFF_PER_CELL; }
+__device__ __forceinline__ double fast_rcp(double x);
 
 // Row `a` of the element matrix of `cell` (or column a when alpha is passed untransposed, see header): acc[b], b < nsf
-template <int NSF>
+// TENSOR_ONLY: the caller guarantees affine cells with cell-wise constant coefficients (no quadrature loop is compiled)
+template <int NSF, bool TENSOR_ONLY = false>
 __device__ __forceinline__ void element_row(const CellGeom& g, const TabView& T, int a, const DevCoeff& alpha, const DevCoeff& gamma,
                                             int64_t cell, bool transpose_alpha, double (&acc)[NSF]) {
 #pragma unroll
   for (int b = 0; b < NSF; ++b) acc[b] = 0.0;
   const int nsf = T.nsf, nq = T.nq;
-  if (!g.quad && cellwise_const(alpha) && cellwise_const(gamma)) {
+  if (TENSOR_ONLY || (!g.quad && cellwise_const(alpha) && cellwise_const(gamma))) {
     // affine cell, cell-wise constant coefficients: A_K = sum_ij M_ij Khat^{ji} + gamma |det| Mhat
     double j00, j01, j10, j11;
     jacobian(g, 0.0, 0.0, j00, j01, j10, j11);
     const double det = j00 * j11 - j01 * j10;
-    const double adet = fabs(det), idet = 1.0 / det;
+    const double adet = fabs(det), idet = fast_rcp(det);
     // Jinv = idet [j11 -j01; -j10 j00]
     const double i00 = j11 * idet, i01 = -j01 * idet, i10 = -j10 * idet, i11 = j00 * idet;
     double a00, a01, a10, a11;
@@ -197,12 +199,13 @@ __device__ __forceinline__ void element_row(const CellGeom& g, const TabView& T,
     }
     return;
   }
+  if (TENSOR_ONLY) return;
   double j00, j01, j10, j11;
   if (!g.quad) jacobian(g, 0.0, 0.0, j00, j01, j10, j11);
   for (int k = 0; k < nq; ++k) {
     if (g.quad) jacobian(g, T.qx[k], T.qy[k], j00, j01, j10, j11);
     const double det = j00 * j11 - j01 * j10;
-    const double wd = T.w[k] * fabs(det), idet = 1.0 / det;
+    const double wd = T.w[k] * fabs(det), idet = fast_rcp(det);
     const double i00 = j11 * idet, i01 = -j01 * idet, i10 = -j10 * idet, i11 = j00 * idet;
     double a00, a01, a10, a11;
     eval_alpha(alpha, cell, k, transpose_alpha, a00, a01, a10, a11);
@@ -219,12 +222,34 @@ __device__ __forceinline__ void element_row(const CellGeom& g, const TabView& T,
   }
 }
 
-// cooperative copy of the table blob into shared memory; returns views
-__device__ __forceinline__ void load_tables(const Tables& hdr, const double* __restrict__ blob, double* smem, TabView& tt, TabView& tq) {
-  for (int i = threadIdx.x; i < hdr.total; i += blockDim.x) smem[i] = blob[i];
+// cooperative copy of the table blob into shared memory; returns views.
+// what: bit 0 = triangle tables, bit 1 = quadrilateral tables, bit 2 = the per-quadrature-point part is needed too
+// (a kernel that only meets affine cells with cell-wise constant coefficients reads the reference tensors only)
+__device__ __forceinline__ void load_tables(const Tables& hdr, const double* __restrict__ blob, double* smem, TabView& tt, TabView& tq,
+                                            int what = 7) {
+  for (int ty = 0; ty < 2; ++ty) {
+    if (!(what & (1 << ty)) || hdr.nsf[ty] == 0) continue;
+    const int nsf = hdr.nsf[ty], nq = hdr.nq[ty];
+    const int qp_len = 3 * nq + 3 * nsf * nq;
+    const int begin = hdr.off[ty] + ((what & 4) ? 0 : qp_len);
+    const int end = hdr.off[ty] + block_doubles(nsf, nq);
+    for (int i = begin + threadIdx.x; i < end; i += blockDim.x) smem[i] = blob[i];
+  }
   __syncthreads();
   tt = make_view(smem + hdr.off[0], hdr.nsf[0], hdr.nq[0]);
   tq = make_view(smem + hdr.off[1], hdr.nsf[1], hdr.nq[1]);
+}
+
+// 1/x for x != 0 of moderate magnitude (Jacobian determinants; degenerate cells are rejected at upload): hardware seed
+// (MUFU.RCP64H) + two Newton steps, relative error ~1e-16, no slow path
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
 }
 
 template <int NSF, typename P>
@@ -260,49 +285,98 @@ __global__ void __launch_bounds__(256) k_assemble_atomic(Tables hdr, const doubl
   }
 }
 
-template <int NSF, typename P>
-__global__ void __launch_bounds__(128) k_assemble_gather(Tables hdr, const double* __restrict__ blob, MeshView mv, int64_t n_outer,
-                                                         int o_stride, int pos_row, const int32_t* __restrict__ outer,
-                                                         const int32_t* __restrict__ adj_ptr, const uint32_t* __restrict__ adj,
-                                                         const P* __restrict__ pos, DevCoeff alpha, DevCoeff gamma,
-                                                         const uint8_t* __restrict__ active, bool transpose_alpha, double beta,
-                                                         const int32_t* __restrict__ row_list, double* __restrict__ values,
-                                                         int* __restrict__ flags) {
+// Owner-computes kernel: one thread per outer index (matrix row for CSR).  The thread walks the (cell, a) items of its
+// dof in ascending cell order and accumulates into ITS segment of a block-wide shared-memory image of the value range
+// the block owns (segment offsets = block scan of the row lengths, i.e. the image is laid out exactly like the output).
+// The block then streams the image to HBM as one contiguous, fully coalesced copy.  Every value is written exactly
+// once: no atomics, no zero-fill, no read-modify-write of the value array.
+template <int NSF, typename P, int THREADS, bool TENSOR_ONLY>
+__global__ void __launch_bounds__(THREADS, 6) k_assemble_gather(Tables hdr, const double* __restrict__ blob, int table_mask, MeshView mv,
+                                                                int64_t n_rows, int o_stride, int pos_row,
+                                                                const int32_t* __restrict__ outer, const int32_t* __restrict__ adj_ptr,
+                                                                const uint32_t* __restrict__ adj, const P* __restrict__ pos,
+                                                                DevCoeff alpha, DevCoeff gamma, const uint8_t* __restrict__ active,
+                                                                bool transpose_alpha, double beta, const int32_t* __restrict__ row_list,
+                                                                double* __restrict__ values, int* __restrict__ flags) {
   extern __shared__ double smem[];
+  __shared__ int32_t s_warp[THREADS / 32 + 1];
+  __shared__ int32_t s_first_v0;
   TabView tt, tq;
-  load_tables(hdr, blob, smem, tt, tq);
-  double* strip = smem + ((hdr.total + 1) & ~1) + threadIdx.x;  // private accumulators strip[s * blockDim.x]
-  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (t >= n_outer) return;  // n_outer = number of rows to process
-  const int64_t r = row_list != nullptr ? row_list[t] : t;
-  const int32_t v0 = outer[r], len = outer[r + 1] - v0;
-  for (int s = 0; s < len; ++s) strip[s * blockDim.x] = 0.0;
-  const int32_t it1 = adj_ptr[r + 1];
-  for (int32_t it = adj_ptr[r]; it < it1; ++it) {
-    const uint32_t item = __ldg(adj + it);
-    const int64_t cell = item >> 4;
-    const int a = static_cast<int>(item & 15U);
-    if (active != nullptr && active[cell] == 0) continue;
-    const CellGeom g = load_geom(mv, cell);
-    const TabView& T = g.quad ? tq : tt;
-    if (T.nsf == 0) {
-      flags[0] = 1;
-      continue;
-    }
-    double acc[NSF];
-    element_row<NSF>(g, T, a, alpha, gamma, cell, transpose_alpha, acc);
-    const P* pp = pos + (cell * o_stride + a) * pos_row;
+  load_tables(hdr, blob, smem, tt, tq, table_mask);
+  double* image = smem + ((hdr.total + 1) & ~1);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * THREADS + threadIdx.x;
+  const bool in_range = t < n_rows;
+  const int64_t r = in_range ? (row_list != nullptr ? row_list[t] : t) : 0;
+  int32_t v0 = 0, len = 0;
+  if (in_range) {
+    v0 = __ldg(outer + r);
+    len = __ldg(outer + r + 1) - v0;
+  }
+  // exclusive block scan of the row lengths
+  int32_t inc = len;
 #pragma unroll
-    for (int b = 0; b < NSF; ++b) {
-      if (b < T.nsf) strip[static_cast<int>(pp[b]) * blockDim.x] += acc[b];
+  for (int d = 1; d < 32; d <<= 1) {
+    const int32_t up = __shfl_up_sync(0xffffffffU, inc, d);
+    if (lane >= d) inc += up;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  if (threadIdx.x == 0) s_first_v0 = v0;
+  __syncthreads();
+  int32_t base = 0;
+#pragma unroll
+  for (int w = 0; w < THREADS / 32; ++w) base += (w < warp) ? s_warp[w] : 0;
+  const int32_t off = base + inc - len;
+  double* mine = image + off;
+  if (in_range) {
+    for (int s = 0; s < len; ++s) mine[s] = 0.0;
+    const int32_t it1 = __ldg(adj_ptr + r + 1);
+    for (int32_t it = __ldg(adj_ptr + r); it < it1; ++it) {
+      const uint32_t item = __ldg(adj + it);
+      const int64_t cell = item >> 4;
+      const int a = static_cast<int>(item & 15U);
+      if (active != nullptr && active[cell] == 0) continue;
+      const CellGeom g = load_geom(mv, cell);
+      const TabView& T = g.quad ? tq : tt;
+      // slots of the row's entries: pos_row bytes (or shorts), fetched as 32-bit words
+      constexpr int kWords = (NSF * static_cast<int>(sizeof(P)) + 3) / 4;
+      uint32_t pw[kWords];
+      const uint32_t* pp = reinterpret_cast<const uint32_t*>(pos + (cell * o_stride + a) * pos_row);
+#pragma unroll
+      for (int w = 0; w < kWords; ++w) pw[w] = __ldg(pp + w);
+      double acc[NSF];
+      element_row<NSF, TENSOR_ONLY>(g, T, a, alpha, gamma, cell, transpose_alpha, acc);
+#pragma unroll
+      for (int b = 0; b < NSF; ++b) {
+        if (b < T.nsf) {
+          const int slot = sizeof(P) == 1 ? static_cast<int>((pw[b >> 2] >> (8 * (b & 3))) & 0xffU)
+                                          : static_cast<int>((pw[b >> 1] >> (16 * (b & 1))) & 0xffffU);
+          mine[slot] += acc[b];
+        }
+      }
     }
   }
-  double* dst = values + v0;
-  if (beta == 0.0) {
-    for (int s = 0; s < len; ++s) dst[s] = strip[s * blockDim.x];
-  } else {
-    for (int s = 0; s < len; ++s) dst[s] = beta * dst[s] + strip[s * blockDim.x];
+  // do the block's rows form one contiguous value range?  (always without a row list; mostly with a partition's list)
+  const int contiguous = __syncthreads_and(!in_range || v0 == s_first_v0 + off);
+  if (contiguous) {
+    int32_t total = 0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) total += s_warp[w];
+    double* dst = values + s_first_v0;
+    if (beta == 0.0) {
+      for (int k = threadIdx.x; k < total; k += THREADS) dst[k] = image[k];
+    } else {
+      for (int k = threadIdx.x; k < total; k += THREADS) dst[k] = fma(beta, dst[k], image[k]);
+    }
+  } else if (in_range) {
+    double* dst = values + v0;
+    if (beta == 0.0) {
+      for (int s = 0; s < len; ++s) dst[s] = mine[s];
+    } else {
+      for (int s = 0; s < len; ++s) dst[s] = fma(beta, dst[s], mine[s]);
+    }
   }
+  (void)flags;
 }
 
 // load vector: one thread per cell, FP64 atomics (assembler.h:322-324)
@@ -477,7 +551,7 @@ int check_rules(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const HostTables& ht) {
 template <int NSF, typename P>
 int launch_matrix(lfgpu_ctx* ctx, const HostTables& ht, const double* d_blob, const MeshView& mv, const lfgpu_pattern* p,
                   const DevCoeff& alpha, const DevCoeff& gamma, const uint8_t* active, double beta, double* d_values, int algo,
-                  int* d_flags, const int32_t* row_list, int64_t n_rows) {
+                  int* d_flags, const int32_t* row_list, int64_t n_rows, bool has_tria, bool has_quad) {
   const bool transpose_alpha = (p->major == LFGPU_ROW_MAJOR);
   const size_t tab_bytes = sizeof(double) * ((ht.hdr.total + 1) & ~1);
   if (algo == LFGPU_ALGO_ATOMIC) {
@@ -493,16 +567,24 @@ int launch_matrix(lfgpu_ctx* ctx, const HostTables& ht, const double* d_blob, co
         alpha, gamma, active, transpose_alpha, d_values, d_flags);
     LFGPU_LAUNCH_CHECK(ctx);
   } else {
-    const int threads = 128;
-    const size_t smem = tab_bytes + sizeof(double) * static_cast<size_t>(p->max_row_len) * threads;
-    if (smem > 200 * 1024) LFGPU_FAIL(ctx, LFGPU_ERR_UNSUPPORTED, "row too long for the gather kernel; use LFGPU_ALGO_ATOMIC");
-    auto kern = k_assemble_gather<NSF, P>;
+    constexpr int threads = 128;
+    // shared-memory image of the block's value range: exact maximum over the blocks of consecutive rows (symbolic pass)
+    // or, with a row list, the safe bound threads * longest row
+    const int64_t image_len = row_list != nullptr ? static_cast<int64_t>(threads) * p->max_row_len : p->max_block_nnz;
+    const size_t smem = tab_bytes + sizeof(double) * static_cast<size_t>(image_len);
+    if (smem > 200 * 1024) LFGPU_FAIL(ctx, LFGPU_ERR_UNSUPPORTED, "rows too long for the gather kernel; use LFGPU_ALGO_ATOMIC");
+    // which tables the kernel will touch: cell types present in the mesh; the per-point part only if quadrature is needed
+    int table_mask = (has_tria ? 1 : 0) | (has_quad ? 2 : 0);
+    const bool cellwise = alpha.kind <= LFGPU_COEFF_PER_CELL && gamma.kind <= LFGPU_COEFF_PER_CELL;
+    const bool tensor_only = cellwise && !has_quad;
+    if (!tensor_only) table_mask |= 4;
+    auto kern = tensor_only ? k_assemble_gather<NSF, P, threads, true> : k_assemble_gather<NSF, P, threads, false>;
     LFGPU_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     const int64_t rows = row_list != nullptr ? n_rows : p->n_outer;
     if (rows > 0) {
       kern<<<static_cast<unsigned>(cdiv(rows, threads)), threads, smem, ctx->stream>>>(
-          ht.hdr, d_blob, mv, rows, p->o_stride, p->pos_row, p->outer, p->adj_ptr, p->adj, static_cast<const P*>(p->pos), alpha,
-          gamma, active, transpose_alpha, beta, row_list, d_values, d_flags);
+          ht.hdr, d_blob, table_mask, mv, rows, p->o_stride, p->pos_row, p->outer, p->adj_ptr, p->adj,
+          static_cast<const P*>(p->pos), alpha, gamma, active, transpose_alpha, beta, row_list, d_values, d_flags);
     }
     LFGPU_LAUNCH_CHECK(ctx);
   }
@@ -590,8 +672,8 @@ int lfgpu_assemble_reaction_diffusion_rows(lfgpu_ctx* ctx, const lfgpu_mesh* mes
   const MeshView mv{mesh->node_coords, mesh->cell_nodes, mesh->cell_coords};
   const bool has_quads = mesh->n_quad > 0;
 #define LFGPU_DISPATCH(NSF)                                                                                                      \
-  rc = (p->pos_bytes == 1) ? launch_matrix<NSF, uint8_t>(ctx, ht, blob.d, mv, p, da, dg, active, beta, d_values, algo, d_flags, d_row_list, n_rows)  \
-                           : launch_matrix<NSF, uint16_t>(ctx, ht, blob.d, mv, p, da, dg, active, beta, d_values, algo, d_flags, d_row_list, n_rows)
+  rc = (p->pos_bytes == 1) ? launch_matrix<NSF, uint8_t>(ctx, ht, blob.d, mv, p, da, dg, active, beta, d_values, algo, d_flags, d_row_list, n_rows, mesh->n_tria > 0, mesh->n_quad > 0)  \
+                           : launch_matrix<NSF, uint16_t>(ctx, ht, blob.d, mv, p, da, dg, active, beta, d_values, algo, d_flags, d_row_list, n_rows, mesh->n_tria > 0, mesh->n_quad > 0)
   switch (degree) {
     case 1: if (has_quads) { LFGPU_DISPATCH(4); } else { LFGPU_DISPATCH(3); } break;
     case 2: if (has_quads) { LFGPU_DISPATCH(9); } else { LFGPU_DISPATCH(6); } break;

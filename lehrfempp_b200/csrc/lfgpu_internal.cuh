@@ -75,6 +75,7 @@ struct lfgpu_pattern {
   int o_stride = 0, i_stride = 0, pos_row = 0, pos_bytes = 1;
   void* pos = nullptr;
   int max_row_len = 0;
+  int max_block_nnz = 0;  // max over blocks of 128 consecutive outer indices of their number of stored values
   int max_items = 0;  // max number of cells adjacent to one outer dof
   // dof tables the plan was built from (device copies owned by the pattern)
   int32_t* o_dofs = nullptr;  // [n_cells][o_stride]

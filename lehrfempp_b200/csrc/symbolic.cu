@@ -52,6 +52,18 @@ __global__ void k_max_diff(int64_t n, const int32_t* __restrict__ ptr, int* __re
   if ((threadIdx.x & 31) == 0) atomicMax(max_len, len);
 }
 
+// longest value range owned by a block of `block` consecutive outer indices
+__global__ void k_max_block_nnz(int64_t n, int block, const int32_t* __restrict__ ptr, int* __restrict__ out) {
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  int len = 0;
+  if (b * block < n) {
+    const int64_t e = (b + 1) * block < n ? (b + 1) * block : n;
+    len = ptr[e] - ptr[b * block];
+  }
+  len = __reduce_max_sync(0xffffffffU, len);
+  if ((threadIdx.x & 31) == 0) atomicMax(out, len);
+}
+
 __global__ void k_item_counts(int64_t n_items, const uint32_t* __restrict__ adj, const uint8_t* __restrict__ i_nldof,
                               int64_t* __restrict__ counts) {
   const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -292,12 +304,14 @@ int lfgpu_symbolic(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* t
   k_low32<<<static_cast<unsigned>(cdiv(nnz, kThreads)), kThreads, 0, st>>>(nnz, ck_in, p->inner);
   k_lower_bounds<uint64_t><<<static_cast<unsigned>(cdiv(p->n_outer + 1, kThreads)), kThreads, 0, st>>>(p->n_outer + 1, nnz, ck_in, 32, p->outer, nullptr);
   k_max_diff<<<static_cast<unsigned>(cdiv(p->n_outer, kThreads)), kThreads, 0, st>>>(p->n_outer, p->outer, d_flags + 5);
-  ctx->launches += 3;
+  k_max_block_nnz<<<static_cast<unsigned>(cdiv(cdiv(p->n_outer, 128), kThreads)), kThreads, 0, st>>>(p->n_outer, 128, p->outer, d_flags + 6);
+  ctx->launches += 4;
   int h_flags[8] = {0};
   SYM_CHECK(cudaMemcpyAsync(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
   SYM_CHECK(cudaStreamSynchronize(st));
   p->max_items = h_flags[4];
   p->max_row_len = h_flags[5];
+  p->max_block_nnz = h_flags[6];
   cudaFree(ck_in); ck_in = nullptr;
 
   // ---- 3. scatter map -------------------------------------------------------------------------------------------
