@@ -191,10 +191,26 @@ __device__ __forceinline__ void element_row(const CellGeom& g, const TabView& T,
     const double m10 = adet * (t10 * i00 + t11 * i01), m11 = adet * (t10 * i10 + t11 * i11);
     const double gm = adet * eval_scalar(gamma, cell, 0);
     const int row = a * nsf;
+    // fewer table reads where the coefficients allow it (warp-uniform branches): no mass term, symmetric M
+    const bool sym = alpha.kind != LFGPU_COEFF_CONST_2X2;
+    if (sym) {
+      if (gm == 0.0) {
 #pragma unroll
-    for (int b = 0; b < NSF; ++b) {
-      if (b < nsf) {
-        acc[b] = m00 * T.k00[row + b] + m01 * T.k10[row + b] + m10 * T.k01[row + b] + m11 * T.k11[row + b] + gm * T.m[row + b];
+        for (int b = 0; b < NSF; ++b) {
+          if (b < nsf) acc[b] = m00 * T.k00[row + b] + m01 * (T.k10[row + b] + T.k01[row + b]) + m11 * T.k11[row + b];
+        }
+      } else {
+#pragma unroll
+        for (int b = 0; b < NSF; ++b) {
+          if (b < nsf) acc[b] = m00 * T.k00[row + b] + m01 * (T.k10[row + b] + T.k01[row + b]) + m11 * T.k11[row + b] + gm * T.m[row + b];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int b = 0; b < NSF; ++b) {
+        if (b < nsf) {
+          acc[b] = m00 * T.k00[row + b] + m01 * T.k10[row + b] + m10 * T.k01[row + b] + m11 * T.k11[row + b] + gm * T.m[row + b];
+        }
       }
     }
     return;
@@ -239,6 +255,11 @@ __device__ __forceinline__ void load_tables(const Tables& hdr, const double* __r
   tt = make_view(smem + hdr.off[0], hdr.nsf[0], hdr.nq[0]);
   tq = make_view(smem + hdr.off[1], hdr.nsf[1], hdr.nq[1]);
 }
+
+// Bank swizzle of the shared-memory image of a block's value range: rows of equal length L start L doubles apart, and
+// L = 16 (e.g. the edge dofs of cubic triangles) would put the same slot of 16 rows into ONE bank.  XOR-ing the low four
+// index bits with the next four is a bijection inside every aligned group of 16 and spreads such columns over all banks.
+__device__ __forceinline__ int swz(int k) { return k ^ ((k >> 4) & 15); }
 
 // 1/x for x != 0 of moderate magnitude (Jacobian determinants; degenerate cells are rejected at upload): hardware seed
 // (MUFU.RCP64H) + two Newton steps, relative error ~1e-16, no slow path
@@ -327,9 +348,8 @@ __global__ void __launch_bounds__(THREADS, 6) k_assemble_gather(Tables hdr, cons
 #pragma unroll
   for (int w = 0; w < THREADS / 32; ++w) base += (w < warp) ? s_warp[w] : 0;
   const int32_t off = base + inc - len;
-  double* mine = image + off;
   if (in_range) {
-    for (int s = 0; s < len; ++s) mine[s] = 0.0;
+    for (int s = 0; s < len; ++s) image[swz(off + s)] = 0.0;
     const int32_t it1 = __ldg(adj_ptr + r + 1);
     for (int32_t it = __ldg(adj_ptr + r); it < it1; ++it) {
       const uint32_t item = __ldg(adj + it);
@@ -351,7 +371,7 @@ __global__ void __launch_bounds__(THREADS, 6) k_assemble_gather(Tables hdr, cons
         if (b < T.nsf) {
           const int slot = sizeof(P) == 1 ? static_cast<int>((pw[b >> 2] >> (8 * (b & 3))) & 0xffU)
                                           : static_cast<int>((pw[b >> 1] >> (16 * (b & 1))) & 0xffffU);
-          mine[slot] += acc[b];
+          image[swz(off + slot)] += acc[b];
         }
       }
     }
@@ -364,19 +384,93 @@ __global__ void __launch_bounds__(THREADS, 6) k_assemble_gather(Tables hdr, cons
     for (int w = 0; w < THREADS / 32; ++w) total += s_warp[w];
     double* dst = values + s_first_v0;
     if (beta == 0.0) {
-      for (int k = threadIdx.x; k < total; k += THREADS) dst[k] = image[k];
+      for (int k = threadIdx.x; k < total; k += THREADS) dst[k] = image[swz(k)];
     } else {
-      for (int k = threadIdx.x; k < total; k += THREADS) dst[k] = fma(beta, dst[k], image[k]);
+      for (int k = threadIdx.x; k < total; k += THREADS) dst[k] = fma(beta, dst[k], image[swz(k)]);
     }
   } else if (in_range) {
     double* dst = values + v0;
     if (beta == 0.0) {
-      for (int s = 0; s < len; ++s) dst[s] = mine[s];
+      for (int s = 0; s < len; ++s) dst[s] = image[swz(off + s)];
     } else {
-      for (int s = 0; s < len; ++s) dst[s] = fma(beta, dst[s], mine[s]);
+      for (int s = 0; s < len; ++s) dst[s] = fma(beta, dst[s], image[swz(off + s)]);
     }
   }
   (void)flags;
+}
+
+// Item-parallel owner-computes kernel (the default without a row list): one thread per ITEM (cell, a) of the block's
+// outer indices, so the element rows of all items are computed concurrently and the work is balanced whatever the
+// valence of a dof.  The items of one dof are then folded into the block's shared-memory image of its value range in
+// rounds: round k adds the k-th item of every dof (at most one item per dof and round -> plain read-modify-write, no
+// atomics; ascending cell order per entry = the reference's summation order, bitwise repeatable).  The image is laid
+// out exactly like the output and leaves as one coalesced copy.
+template <int NSF, typename P, bool TENSOR_ONLY>
+__global__ void __launch_bounds__(256, TENSOR_ONLY ? 4 : 2) k_assemble_items(Tables hdr, const double* __restrict__ blob, int table_mask, MeshView mv,
+                                                           const int32_t* __restrict__ blk_rows, int pos_row,
+                                                           const int32_t* __restrict__ outer, const int32_t* __restrict__ adj_ptr,
+                                                           const uint32_t* __restrict__ adj, const P* __restrict__ pos_item,
+                                                           const uint32_t* __restrict__ item_perm, DevCoeff alpha, DevCoeff gamma,
+                                                           const uint8_t* __restrict__ active, bool transpose_alpha, double beta,
+                                                           double* __restrict__ values) {
+  extern __shared__ double smem[];
+  __shared__ int32_t s_out[257];
+  const int tid = threadIdx.x;
+  const int32_t R0 = __ldg(blk_rows + blockIdx.x), R1 = __ldg(blk_rows + blockIdx.x + 1);
+  const int nrows = R1 - R0;
+  const int32_t adj0 = __ldg(adj_ptr + R0), out0 = __ldg(outer + R0);
+  const int n_items = __ldg(adj_ptr + R1) - adj0;
+  for (int j = tid; j <= nrows; j += 256) s_out[j] = __ldg(outer + R0 + j) - out0;
+  TabView tt, tq;
+  load_tables(hdr, blob, smem, tt, tq, table_mask);  // contains a __syncthreads()
+  double* image = smem + ((hdr.total + 1) & ~1);
+  const int total = s_out[nrows];
+  for (int k = tid; k < ((total + 15) & ~15); k += 256) image[k] = 0.0;
+  // my item (threads are ordered by rank-in-dof, then dof: see k_item_perm)
+  bool valid = tid < n_items;
+  int rank = 0, off = 0, nsf = 0;
+  double acc[NSF];
+  constexpr int kWords = (NSF * static_cast<int>(sizeof(P)) + 3) / 4;
+  uint32_t pw[kWords];
+  if (valid) {
+    const uint32_t w = __ldg(item_perm + adj0 + tid);
+    const int li = static_cast<int>(w & 255U);
+    rank = static_cast<int>(w >> 16);
+    off = s_out[(w >> 8) & 255U];
+    const uint32_t item = __ldg(adj + adj0 + li);
+    const int64_t cell = item >> 4;
+    const int a = static_cast<int>(item & 15U);
+    if (active != nullptr && active[cell] == 0) {
+      valid = false;
+    } else {
+      const uint32_t* pp = reinterpret_cast<const uint32_t*>(pos_item + (static_cast<int64_t>(adj0) + li) * pos_row);
+#pragma unroll
+      for (int w = 0; w < kWords; ++w) pw[w] = __ldg(pp + w);
+      const CellGeom g = load_geom(mv, cell);
+      const TabView& T = g.quad ? tq : tt;
+      nsf = T.nsf;
+      element_row<NSF, TENSOR_ONLY>(g, T, a, alpha, gamma, cell, transpose_alpha, acc);
+    }
+  }
+  __syncthreads();  // image zeroed
+  for (int k = 0; __syncthreads_or(valid && rank >= k); ++k) {
+    if (valid && rank == k) {
+#pragma unroll
+      for (int b = 0; b < NSF; ++b) {
+        if (b < nsf) {
+          const int slot = sizeof(P) == 1 ? static_cast<int>((pw[b >> 2] >> (8 * (b & 3))) & 0xffU)
+                                          : static_cast<int>((pw[b >> 1] >> (16 * (b & 1))) & 0xffffU);
+          image[swz(off + slot)] += acc[b];
+        }
+      }
+    }
+  }
+  double* dst = values + out0;
+  if (beta == 0.0) {
+    for (int k = tid; k < total; k += 256) dst[k] = image[swz(k)];
+  } else {
+    for (int k = tid; k < total; k += 256) dst[k] = fma(beta, dst[k], image[swz(k)]);
+  }
 }
 
 // load vector: one thread per cell, FP64 atomics (assembler.h:322-324)
@@ -567,17 +661,29 @@ int launch_matrix(lfgpu_ctx* ctx, const HostTables& ht, const double* d_blob, co
         alpha, gamma, active, transpose_alpha, d_values, d_flags);
     LFGPU_LAUNCH_CHECK(ctx);
   } else {
-    constexpr int threads = 128;
-    // shared-memory image of the block's value range: exact maximum over the blocks of consecutive rows (symbolic pass)
-    // or, with a row list, the safe bound threads * longest row
-    const int64_t image_len = row_list != nullptr ? static_cast<int64_t>(threads) * p->max_row_len : p->max_block_nnz;
-    const size_t smem = tab_bytes + sizeof(double) * static_cast<size_t>(image_len);
-    if (smem > 200 * 1024) LFGPU_FAIL(ctx, LFGPU_ERR_UNSUPPORTED, "rows too long for the gather kernel; use LFGPU_ALGO_ATOMIC");
     // which tables the kernel will touch: cell types present in the mesh; the per-point part only if quadrature is needed
     int table_mask = (has_tria ? 1 : 0) | (has_quad ? 2 : 0);
     const bool cellwise = alpha.kind <= LFGPU_COEFF_PER_CELL && gamma.kind <= LFGPU_COEFF_PER_CELL;
     const bool tensor_only = cellwise && !has_quad;
     if (!tensor_only) table_mask |= 4;
+    if (row_list == nullptr && p->blk_rows != nullptr) {
+      const size_t smem_i = tab_bytes + sizeof(double) * static_cast<size_t>((p->max_item_block_nnz + 15) & ~15);
+      if (smem_i <= 200 * 1024) {
+        auto ki = tensor_only ? k_assemble_items<NSF, P, true> : k_assemble_items<NSF, P, false>;
+        LFGPU_CUDA_CHECK(ctx, cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_i)));
+        ki<<<static_cast<unsigned>(p->n_item_blocks), 256, smem_i, ctx->stream>>>(
+            ht.hdr, d_blob, table_mask, mv, p->blk_rows, p->pos_row, p->outer, p->adj_ptr, p->adj, static_cast<const P*>(p->pos_item),
+            p->item_perm, alpha, gamma, active, transpose_alpha, beta, d_values);
+        LFGPU_LAUNCH_CHECK(ctx);
+        return LFGPU_OK;
+      }
+    }
+    constexpr int threads = 128;
+    // shared-memory image of the block's value range: exact maximum over the blocks of consecutive rows (symbolic pass)
+    // or, with a row list, the safe bound threads * longest row
+    const int64_t image_len = row_list != nullptr ? static_cast<int64_t>(threads) * p->max_row_len : p->max_block_nnz;
+    const size_t smem = tab_bytes + sizeof(double) * static_cast<size_t>((image_len + 15) & ~15);
+    if (smem > 200 * 1024) LFGPU_FAIL(ctx, LFGPU_ERR_UNSUPPORTED, "rows too long for the gather kernel; use LFGPU_ALGO_ATOMIC");
     auto kern = tensor_only ? k_assemble_gather<NSF, P, threads, true> : k_assemble_gather<NSF, P, threads, false>;
     LFGPU_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     const int64_t rows = row_list != nullptr ? n_rows : p->n_outer;

@@ -76,6 +76,13 @@ struct lfgpu_pattern {
   void* pos = nullptr;
   int max_row_len = 0;
   int max_block_nnz = 0;  // max over blocks of 128 consecutive outer indices of their number of stored values
+  // item-parallel gather plan: block b of the item kernel owns the outer indices [blk_rows[b], blk_rows[b+1]), chosen so
+  // that it has at most 256 items; pos_item = scatter slots re-ordered to item order (streamed, not gathered)
+  int64_t n_item_blocks = 0;
+  int32_t* blk_rows = nullptr;   // [n_item_blocks + 1]
+  void* pos_item = nullptr;      // [n_items][pos_row], same element type as pos
+  uint32_t* item_perm = nullptr; // [n_items] per block: thread t -> local item | local row << 8 | rank-in-row << 16, sorted by (rank, row)
+  int max_item_block_nnz = 0;
   int max_items = 0;  // max number of cells adjacent to one outer dof
   // dof tables the plan was built from (device copies owned by the pattern)
   int32_t* o_dofs = nullptr;  // [n_cells][o_stride]

@@ -64,6 +64,84 @@ __global__ void k_max_block_nnz(int64_t n, int block, const int32_t* __restrict_
   if ((threadIdx.x & 31) == 0) atomicMax(out, len);
 }
 
+// item-parallel plan: first outer index of block b = first row whose first item is >= b * items_per_block
+__global__ void k_block_rows(int64_t n_blocks, int64_t n_rows, int items_per_block, const int32_t* __restrict__ adj_ptr,
+                             int32_t* __restrict__ blk_rows) {
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (b > n_blocks) return;
+  if (b == n_blocks) {
+    blk_rows[b] = static_cast<int32_t>(n_rows);
+    return;
+  }
+  const int64_t target = b * items_per_block;
+  int64_t lo = 0, hi = n_rows;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (adj_ptr[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  blk_rows[b] = static_cast<int32_t>(lo);
+}
+__global__ void k_block_nnz(int64_t n_blocks, const int32_t* __restrict__ blk_rows, const int32_t* __restrict__ outer,
+                            const int32_t* __restrict__ adj_ptr, int* __restrict__ out /*[0] max nnz, [1] max items, [2] max rows*/) {
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  int nnz = 0, items = 0, rows = 0;
+  if (b < n_blocks) {
+    nnz = outer[blk_rows[b + 1]] - outer[blk_rows[b]];
+    items = adj_ptr[blk_rows[b + 1]] - adj_ptr[blk_rows[b]];
+    rows = blk_rows[b + 1] - blk_rows[b];
+  }
+  nnz = __reduce_max_sync(0xffffffffU, nnz);
+  items = __reduce_max_sync(0xffffffffU, items);
+  rows = __reduce_max_sync(0xffffffffU, rows);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(out, nnz);
+    atomicMax(out + 1, items);
+    atomicMax(out + 2, rows);
+  }
+}
+// thread order of the item kernel inside a block: items sorted by (rank within their dof, local index, dof), so that in
+// the k-th accumulation round the active threads are a contiguous range (whole warps work or idle)
+__global__ void __launch_bounds__(256) k_item_perm(const int32_t* __restrict__ blk_rows, const int32_t* __restrict__ adj_ptr,
+                                                   const uint32_t* __restrict__ adj, uint32_t* __restrict__ item_perm) {
+  using Sort = cub::BlockRadixSort<uint32_t, 256, 1, uint32_t>;
+  __shared__ typename Sort::TempStorage tmp;
+  __shared__ int32_t s_adj[257];
+  const int tid = threadIdx.x;
+  const int32_t R0 = blk_rows[blockIdx.x], R1 = blk_rows[blockIdx.x + 1];
+  const int nrows = R1 - R0;
+  const int32_t adj0 = adj_ptr[R0];
+  for (int j = tid; j <= nrows; j += 256) s_adj[j] = adj_ptr[R0 + j] - adj0;
+  __syncthreads();
+  const int n_items = s_adj[nrows];
+  uint32_t key[1] = {0xffffffffU}, val[1] = {0};
+  if (tid < n_items) {
+    int lo = 0, hi = nrows;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s_adj[mid] <= tid) lo = mid; else hi = mid;
+    }
+    const uint32_t rank = static_cast<uint32_t>(tid - s_adj[lo]);
+    // (rank, local index a, dof): same-rank items belong to different dofs, so their order is free -- grouping them by
+    // the local index makes the reference-tensor reads of a warp hit one table row (shared-memory broadcast)
+    const uint32_t a = adj[adj0 + tid] & 15U;
+    key[0] = (rank << 12) | (a << 8) | static_cast<uint32_t>(lo);
+    val[0] = static_cast<uint32_t>(tid) | (static_cast<uint32_t>(lo) << 8) | (rank << 16);
+  }
+  Sort(tmp).Sort(key, val, 0, 20);
+  if (tid < n_items) item_perm[adj0 + tid] = val[0];
+}
+
+template <typename P>
+__global__ void k_pos_by_item(int64_t n_items, int o_stride, int pos_row, const uint32_t* __restrict__ adj, const P* __restrict__ pos,
+                              P* __restrict__ pos_item) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= n_items * pos_row) return;
+  const int64_t it = t / pos_row;
+  const int b = static_cast<int>(t - it * pos_row);
+  const uint32_t item = adj[it];
+  pos_item[t] = pos[(static_cast<int64_t>(item >> 4) * o_stride + (item & 15U)) * pos_row + b];
+}
+
 __global__ void k_item_counts(int64_t n_items, const uint32_t* __restrict__ adj, const uint8_t* __restrict__ i_nldof,
                               int64_t* __restrict__ counts) {
   const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -139,6 +217,9 @@ void lfgpu_pattern_destroy(lfgpu_pattern* p) {
   cudaFree(p->adj_ptr);
   cudaFree(p->adj);
   cudaFree(p->pos);
+  cudaFree(p->blk_rows);
+  cudaFree(p->pos_item);
+  cudaFree(p->item_perm);
   cudaFree(p->fan_nbr);
   cudaFree(p->fan_rowinfo);
   cudaFree(p->fan_irregular);
@@ -331,6 +412,45 @@ int lfgpu_symbolic(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* t
   ctx->launches++;
   SYM_CHECK(cudaMemcpyAsync(h_flags, d_flags, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
   SYM_CHECK(cudaStreamSynchronize(st));
+  // ---- 4. item-parallel plan -----------------------------------------------------------------------------------
+  if (p->max_items >= 1 && p->max_items <= 32 && p->n_items > 0) {
+    const int items_per_block = 256 - p->max_items;
+    p->n_item_blocks = cdiv(p->n_items, items_per_block);
+    SYM_CHECK(cudaMalloc(&p->blk_rows, sizeof(int32_t) * (p->n_item_blocks + 1)));
+    k_block_rows<<<static_cast<unsigned>(cdiv(p->n_item_blocks + 1, kThreads)), kThreads, 0, st>>>(p->n_item_blocks, p->n_outer, items_per_block,
+                                                                                                 p->adj_ptr, p->blk_rows);
+    int* d_blk = d_flags + 8;
+    SYM_CHECK(cudaMemsetAsync(d_blk, 0, 16, st));
+    k_block_nnz<<<static_cast<unsigned>(cdiv(p->n_item_blocks, kThreads)), kThreads, 0, st>>>(p->n_item_blocks, p->blk_rows, p->outer, p->adj_ptr, d_blk);
+    const int64_t n_pos = p->n_items * p->pos_row;
+    SYM_CHECK(cudaMalloc(&p->pos_item, static_cast<size_t>(p->pos_bytes) * n_pos));
+    if (p->pos_bytes == 1) {
+      k_pos_by_item<uint8_t><<<static_cast<unsigned>(cdiv(n_pos, kThreads)), kThreads, 0, st>>>(p->n_items, O->stride, p->pos_row, p->adj,
+                                                                                               static_cast<const uint8_t*>(p->pos), static_cast<uint8_t*>(p->pos_item));
+    } else {
+      k_pos_by_item<uint16_t><<<static_cast<unsigned>(cdiv(n_pos, kThreads)), kThreads, 0, st>>>(p->n_items, O->stride, p->pos_row, p->adj,
+                                                                                                static_cast<const uint16_t*>(p->pos), static_cast<uint16_t*>(p->pos_item));
+    }
+    SYM_CHECK(cudaMalloc(&p->item_perm, sizeof(uint32_t) * p->n_items));
+    ctx->launches += 3;
+    int h_blk[4] = {0, 0, 0, 0};
+    SYM_CHECK(cudaMemcpyAsync(h_blk, d_blk, sizeof(h_blk), cudaMemcpyDeviceToHost, st));
+    SYM_CHECK(cudaStreamSynchronize(st));
+    p->max_item_block_nnz = h_blk[0];
+    if (h_blk[1] > 256 || h_blk[2] > 256) {  // rows without items would break the bound: keep the row-parallel kernel
+      cudaFree(p->blk_rows);
+      cudaFree(p->pos_item);
+      cudaFree(p->item_perm);
+      p->blk_rows = nullptr;
+      p->pos_item = nullptr;
+      p->item_perm = nullptr;
+      p->n_item_blocks = 0;
+    } else {
+      k_item_perm<<<static_cast<unsigned>(p->n_item_blocks), 256, 0, st>>>(p->blk_rows, p->adj_ptr, p->adj, p->item_perm);
+      ctx->launches++;
+      SYM_CHECK(cudaStreamSynchronize(st));
+    }
+  }
   cleanup();
 #undef SYM_CHECK
   if (h_flags[0]) {
