@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(256, TENSOR_ONLY ? 4 : 2) k_assemble_items(Tab
                                                            const int32_t* __restrict__ blk_rows, int pos_row,
                                                            const int32_t* __restrict__ outer, const int32_t* __restrict__ adj_ptr,
                                                            const uint32_t* __restrict__ adj, const P* __restrict__ pos_item,
-                                                           const uint32_t* __restrict__ item_perm, DevCoeff alpha, DevCoeff gamma,
+                                                           const uint2* __restrict__ item_sorted, DevCoeff alpha, DevCoeff gamma,
                                                            const uint8_t* __restrict__ active, bool transpose_alpha, double beta,
                                                            double* __restrict__ values) {
   extern __shared__ double smem[];
@@ -433,17 +433,16 @@ __global__ void __launch_bounds__(256, TENSOR_ONLY ? 4 : 2) k_assemble_items(Tab
   constexpr int kWords = (NSF * static_cast<int>(sizeof(P)) + 3) / 4;
   uint32_t pw[kWords];
   if (valid) {
-    const uint32_t w = __ldg(item_perm + adj0 + tid);
-    const int li = static_cast<int>(w & 255U);
-    rank = static_cast<int>(w >> 16);
-    off = s_out[(w >> 8) & 255U];
-    const uint32_t item = __ldg(adj + adj0 + li);
+    const uint2 w = __ldg(item_sorted + adj0 + tid);
+    rank = static_cast<int>(w.y >> 8);
+    off = s_out[w.y & 255U];
+    const uint32_t item = w.x;
     const int64_t cell = item >> 4;
     const int a = static_cast<int>(item & 15U);
     if (active != nullptr && active[cell] == 0) {
       valid = false;
     } else {
-      const uint32_t* pp = reinterpret_cast<const uint32_t*>(pos_item + (static_cast<int64_t>(adj0) + li) * pos_row);
+      const uint32_t* pp = reinterpret_cast<const uint32_t*>(pos_item + (static_cast<int64_t>(adj0) + tid) * pos_row);
 #pragma unroll
       for (int w = 0; w < kWords; ++w) pw[w] = __ldg(pp + w);
       const CellGeom g = load_geom(mv, cell);
@@ -673,7 +672,7 @@ int launch_matrix(lfgpu_ctx* ctx, const HostTables& ht, const double* d_blob, co
         LFGPU_CUDA_CHECK(ctx, cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_i)));
         ki<<<static_cast<unsigned>(p->n_item_blocks), 256, smem_i, ctx->stream>>>(
             ht.hdr, d_blob, table_mask, mv, p->blk_rows, p->pos_row, p->outer, p->adj_ptr, p->adj, static_cast<const P*>(p->pos_item),
-            p->item_perm, alpha, gamma, active, transpose_alpha, beta, d_values);
+            static_cast<const uint2*>(p->item_sorted), alpha, gamma, active, transpose_alpha, beta, d_values);
         LFGPU_LAUNCH_CHECK(ctx);
         return LFGPU_OK;
       }

@@ -81,6 +81,7 @@ struct lfgpu_pattern {
   int64_t n_item_blocks = 0;
   int32_t* blk_rows = nullptr;   // [n_item_blocks + 1]
   void* pos_item = nullptr;      // [n_items][pos_row], same element type as pos
+  void* item_sorted = nullptr;   // uint2 [n_items] in thread order: (cell << 4 | a, local row | rank << 8)
   uint32_t* item_perm = nullptr; // [n_items] per block: thread t -> local item | local row << 8 | rank-in-row << 16, sorted by (rank, row)
   int max_item_block_nnz = 0;
   int max_items = 0;  // max number of cells adjacent to one outer dof

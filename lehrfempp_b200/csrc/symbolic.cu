@@ -102,7 +102,8 @@ __global__ void k_block_nnz(int64_t n_blocks, const int32_t* __restrict__ blk_ro
 // thread order of the item kernel inside a block: items sorted by (rank within their dof, local index, dof), so that in
 // the k-th accumulation round the active threads are a contiguous range (whole warps work or idle)
 __global__ void __launch_bounds__(256) k_item_perm(const int32_t* __restrict__ blk_rows, const int32_t* __restrict__ adj_ptr,
-                                                   const uint32_t* __restrict__ adj, uint32_t* __restrict__ item_perm) {
+                                                   const uint32_t* __restrict__ adj, uint32_t* __restrict__ item_perm,
+                                                   uint2* __restrict__ item_sorted) {
   using Sort = cub::BlockRadixSort<uint32_t, 256, 1, uint32_t>;
   __shared__ typename Sort::TempStorage tmp;
   __shared__ int32_t s_adj[257];
@@ -128,17 +129,21 @@ __global__ void __launch_bounds__(256) k_item_perm(const int32_t* __restrict__ b
     val[0] = static_cast<uint32_t>(tid) | (static_cast<uint32_t>(lo) << 8) | (rank << 16);
   }
   Sort(tmp).Sort(key, val, 0, 20);
-  if (tid < n_items) item_perm[adj0 + tid] = val[0];
+  if (tid < n_items) {
+    item_perm[adj0 + tid] = val[0];
+    // thread-ordered copy of the items: (cell << 4 | a, local dof | rank << 8) -- one coalesced 8-byte load per thread
+    item_sorted[adj0 + tid] = make_uint2(adj[adj0 + (val[0] & 255U)], (val[0] >> 8) & 0xffffffU);
+  }
 }
 
 template <typename P>
-__global__ void k_pos_by_item(int64_t n_items, int o_stride, int pos_row, const uint32_t* __restrict__ adj, const P* __restrict__ pos,
+__global__ void k_pos_by_item(int64_t n_items, int o_stride, int pos_row, const uint2* __restrict__ item_sorted, const P* __restrict__ pos,
                               P* __restrict__ pos_item) {
   const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= n_items * pos_row) return;
   const int64_t it = t / pos_row;
   const int b = static_cast<int>(t - it * pos_row);
-  const uint32_t item = adj[it];
+  const uint32_t item = item_sorted[it].x;
   pos_item[t] = pos[(static_cast<int64_t>(item >> 4) * o_stride + (item & 15U)) * pos_row + b];
 }
 
@@ -220,6 +225,7 @@ void lfgpu_pattern_destroy(lfgpu_pattern* p) {
   cudaFree(p->blk_rows);
   cudaFree(p->pos_item);
   cudaFree(p->item_perm);
+  cudaFree(p->item_sorted);
   cudaFree(p->fan_nbr);
   cudaFree(p->fan_rowinfo);
   cudaFree(p->fan_irregular);
@@ -422,31 +428,32 @@ int lfgpu_symbolic(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* t
     int* d_blk = d_flags + 8;
     SYM_CHECK(cudaMemsetAsync(d_blk, 0, 16, st));
     k_block_nnz<<<static_cast<unsigned>(cdiv(p->n_item_blocks, kThreads)), kThreads, 0, st>>>(p->n_item_blocks, p->blk_rows, p->outer, p->adj_ptr, d_blk);
-    const int64_t n_pos = p->n_items * p->pos_row;
-    SYM_CHECK(cudaMalloc(&p->pos_item, static_cast<size_t>(p->pos_bytes) * n_pos));
-    if (p->pos_bytes == 1) {
-      k_pos_by_item<uint8_t><<<static_cast<unsigned>(cdiv(n_pos, kThreads)), kThreads, 0, st>>>(p->n_items, O->stride, p->pos_row, p->adj,
-                                                                                               static_cast<const uint8_t*>(p->pos), static_cast<uint8_t*>(p->pos_item));
-    } else {
-      k_pos_by_item<uint16_t><<<static_cast<unsigned>(cdiv(n_pos, kThreads)), kThreads, 0, st>>>(p->n_items, O->stride, p->pos_row, p->adj,
-                                                                                                static_cast<const uint16_t*>(p->pos), static_cast<uint16_t*>(p->pos_item));
-    }
     SYM_CHECK(cudaMalloc(&p->item_perm, sizeof(uint32_t) * p->n_items));
-    ctx->launches += 3;
+    ctx->launches += 2;
     int h_blk[4] = {0, 0, 0, 0};
     SYM_CHECK(cudaMemcpyAsync(h_blk, d_blk, sizeof(h_blk), cudaMemcpyDeviceToHost, st));
     SYM_CHECK(cudaStreamSynchronize(st));
     p->max_item_block_nnz = h_blk[0];
     if (h_blk[1] > 256 || h_blk[2] > 256) {  // rows without items would break the bound: keep the row-parallel kernel
       cudaFree(p->blk_rows);
-      cudaFree(p->pos_item);
       cudaFree(p->item_perm);
       p->blk_rows = nullptr;
-      p->pos_item = nullptr;
       p->item_perm = nullptr;
       p->n_item_blocks = 0;
     } else {
-      k_item_perm<<<static_cast<unsigned>(p->n_item_blocks), 256, 0, st>>>(p->blk_rows, p->adj_ptr, p->adj, p->item_perm);
+      SYM_CHECK(cudaMalloc(&p->item_sorted, sizeof(uint2) * p->n_items));
+      k_item_perm<<<static_cast<unsigned>(p->n_item_blocks), 256, 0, st>>>(p->blk_rows, p->adj_ptr, p->adj, p->item_perm,
+                                                                           static_cast<uint2*>(p->item_sorted));
+      ctx->launches++;
+    const int64_t n_pos = p->n_items * p->pos_row;
+      SYM_CHECK(cudaMalloc(&p->pos_item, static_cast<size_t>(p->pos_bytes) * n_pos));
+      if (p->pos_bytes == 1) {
+        k_pos_by_item<uint8_t><<<static_cast<unsigned>(cdiv(n_pos, kThreads)), kThreads, 0, st>>>(p->n_items, O->stride, p->pos_row, static_cast<const uint2*>(p->item_sorted),
+                                                                                                 static_cast<const uint8_t*>(p->pos), static_cast<uint8_t*>(p->pos_item));
+      } else {
+        k_pos_by_item<uint16_t><<<static_cast<unsigned>(cdiv(n_pos, kThreads)), kThreads, 0, st>>>(p->n_items, O->stride, p->pos_row, static_cast<const uint2*>(p->item_sorted),
+                                                                                                  static_cast<const uint16_t*>(p->pos), static_cast<uint16_t*>(p->pos_item));
+      }
       ctx->launches++;
       SYM_CHECK(cudaStreamSynchronize(st));
     }
