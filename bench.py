@@ -185,8 +185,8 @@ def main():
         desc += " [n overridden to %d]" % n
     ctx = lf.Context(local_rank)
     algo = {"auto": lf.ALGO_AUTO, "fan": lf.ALGO_FAN, "gather": lf.ALGO_GATHER, "atomic": lf.ALGO_ATOMIC}[args.algo]
-    kernel_name = {"auto": "k_assemble_p1_fan" if (degree == 1 and kind == "tp_tria") else "k_assemble_gather", "fan": "k_assemble_p1_fan",
-                   "gather": "k_assemble_gather", "atomic": "k_assemble_atomic"}[args.algo]
+    kernel_name = {"auto": "k_assemble_p1_fan" if (degree == 1 and kind == "tp_tria") else "k_assemble_items", "fan": "k_assemble_p1_fan",
+                   "gather": "k_assemble_items", "atomic": "k_assemble_atomic"}[args.algo]
 
     # ---- setup (untimed, like mesh / DofHandler construction on the CPU side) ----------------------------------------------
     t_setup = time.time()
