@@ -129,8 +129,14 @@ def device_view(ptr, n, dtype, device):
 class DistributedAssembler:
     """Partitioned AssembleMatrixLocally over the GPUs of one node (one process per GPU, torch.distributed / NCCL)."""
 
-    def __init__(self, ctx, mesh, pattern, degree, group=None):
+    def __init__(self, ctx, mesh, pattern, degree, group=None, mode="exchange"):
+        """mode = "exchange": every rank assembles the contributions of its cells, interface rows are summed at their
+        owner (one all-to-all-v per step).  mode = "owner": the owner of a row assembles it completely, re-computing the
+        few halo cells of its neighbours (the mesh is replicated at setup) -- no data-path collective at all."""
         import lehrfempp_b200 as lf
+        assert mode in ("exchange", "owner")
+        self.mode = mode
+        self.graph = None
         self.lf, self.ctx, self.mesh, self.pattern, self.degree, self.group = lf, ctx, mesh, pattern, degree, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         L = ctx.L
@@ -153,7 +159,7 @@ class DistributedAssembler:
         self.send_buf = torch.zeros(max(p.n_send, 1), dtype=torch.float64, device=dev)
         self.recv_buf = torch.zeros(max(p.n_recv, 1), dtype=torch.float64, device=dev)
         self.main = torch.cuda.ExternalStream(ctx.stream, device=dev)
-        self.comm = torch.cuda.Stream(device=dev)
+        self.comm = torch.cuda.Stream(device=dev, priority=-1)  # high priority: the collective must not queue behind the interior kernel
         self.ev_packed = torch.cuda.Event()
         self.ev_received = torch.cuda.Event()
         torch.cuda.synchronize()
@@ -170,6 +176,11 @@ class DistributedAssembler:
         """One partitioned numeric pass; afterwards this rank's OWNED rows of `values` are final."""
         lf, ctx, p, L = self.lf, self.ctx, self.plan, self.ctx.L
         pat = self.pattern
+        if self.mode == "owner" and self.world > 1:
+            # owner-computes: one launch over the rows I own, all adjacent cells (mine or halo) contribute
+            pat.assemble_reaction_diffusion(self.degree, alpha, gamma, qr_tria, qr_quad, out=values, algo=lf.ALGO_AUTO,
+                                            rows=self._Rows(p.owned_rows))
+            return values
         if self.world > 1 and p.iface_rows.numel() > 0:
             # 1. interface rows: only my cells contribute (activity mask), generic owner-computes kernel
             pat.assemble_reaction_diffusion(self.degree, alpha, gamma, qr_tria, qr_quad, active=self._Mask(p.active), out=values,

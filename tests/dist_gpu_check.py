@@ -38,7 +38,7 @@ def main():
             gm, om = ctx.mesh_hybrid(24, 0.2, 12345), lfo.Mesh.hybrid(24, 0.2, 12345)
         dm = gm.dofmap_lagrange(degree)
         pat = dm.symbolic(major=lf.ROW_MAJOR)
-        asm = DistributedAssembler(ctx, gm, pat, degree)
+        asm = DistributedAssembler(ctx, gm, pat, degree, mode=os.environ.get("LFGPU_DIST_MODE", "exchange"))
         values = ctx.zeros(pat.nnz)
         a, g = lf.Coeff.const(1.5), lf.Coeff.const(0.5)
         for _ in range(2):  # twice: buffers and events are reused
