@@ -220,7 +220,9 @@ def main():
     if world > 1:
         from lehrfempp_b200.distributed import DistributedAssembler
         t_part = time.time()
-        dist_mode = os.environ.get("LFGPU_DIST_MODE", "exchange")
+        # default: owner-computes (faster: one launch per rank, no collective); LFGPU_DIST_MODE=exchange selects the
+        # contributions-to-owner variant with the NCCL all-to-all-v (both are parity-tested by tests/dist_gpu_check.py)
+        dist_mode = os.environ.get("LFGPU_DIST_MODE", "owner")
         asm = DistributedAssembler(ctx, mesh, pat, degree, mode=dist_mode)
         t_part = time.time() - t_part
 

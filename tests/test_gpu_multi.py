@@ -1,4 +1,4 @@
-"""Multi-GPU parity (needs >= 2 GPUs; skipped on a 1-GPU box)."""
+"""Multi-GPU parity (needs >= 2 GPUs; skipped on a 1-GPU box): both partitioned modes against the oracle."""
 import os
 import subprocess
 import sys
@@ -9,12 +9,13 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_distributed_assembly_two_gpus():
+@pytest.mark.parametrize("mode,port", [("owner", 29541), ("exchange", 29542)])
+def test_distributed_assembly_two_gpus(mode, port):
     import torch
-    n = torch.cuda.device_count()
-    if n < 2:
+    if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29541", os.path.join(ROOT, "tests", "dist_gpu_check.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+           "--master-port", str(port), os.path.join(ROOT, "tests", "dist_gpu_check.py")]
+    env = dict(os.environ, LFGPU_DIST_MODE=mode)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=400, env=env)
     assert "DIST_CHECK_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
