@@ -167,6 +167,33 @@ __device__ __forceinline__ bool cellwise_const(const DevCoeff& c) { return c.kin
 __device__ __forceinline__ double fast_rcp(double x);
 
 // Row `a` of the element matrix of `cell` (or column a when alpha is passed untransposed, see header): acc[b], b < nsf
+// Row `a` of the element matrix from the cell metric and the reference tensors of the rule:
+//   acc[b] = sum_ij M_ij Khat^{ji}[a][b] + gm Mhat[a][b]        (5 FMA per entry; 3 when M is symmetric and gm = 0)
+template <int NSF>
+__device__ __forceinline__ void tensor_row(const TabView& T, int a, double m00, double m01, double m10, double m11, double gm, bool sym,
+                                           double (&acc)[NSF]) {
+  const int nsf = T.nsf;
+  const int row = a * nsf;
+  if (sym) {  // warp-uniform branches
+    if (gm == 0.0) {
+#pragma unroll
+      for (int b = 0; b < NSF; ++b) {
+        if (b < nsf) acc[b] = m00 * T.k00[row + b] + m01 * (T.k10[row + b] + T.k01[row + b]) + m11 * T.k11[row + b];
+      }
+    } else {
+#pragma unroll
+      for (int b = 0; b < NSF; ++b) {
+        if (b < nsf) acc[b] = m00 * T.k00[row + b] + m01 * (T.k10[row + b] + T.k01[row + b]) + m11 * T.k11[row + b] + gm * T.m[row + b];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int b = 0; b < NSF; ++b) {
+      if (b < nsf) acc[b] = m00 * T.k00[row + b] + m01 * T.k10[row + b] + m10 * T.k01[row + b] + m11 * T.k11[row + b] + gm * T.m[row + b];
+    }
+  }
+}
+
 // TENSOR_ONLY: the caller guarantees affine cells with cell-wise constant coefficients (no quadrature loop is compiled)
 template <int NSF, bool TENSOR_ONLY = false>
 __device__ __forceinline__ void element_row(const CellGeom& g, const TabView& T, int a, const DevCoeff& alpha, const DevCoeff& gamma,
@@ -190,29 +217,7 @@ __device__ __forceinline__ void element_row(const CellGeom& g, const TabView& T,
     const double m00 = adet * (t00 * i00 + t01 * i01), m01 = adet * (t00 * i10 + t01 * i11);
     const double m10 = adet * (t10 * i00 + t11 * i01), m11 = adet * (t10 * i10 + t11 * i11);
     const double gm = adet * eval_scalar(gamma, cell, 0);
-    const int row = a * nsf;
-    // fewer table reads where the coefficients allow it (warp-uniform branches): no mass term, symmetric M
-    const bool sym = alpha.kind != LFGPU_COEFF_CONST_2X2;
-    if (sym) {
-      if (gm == 0.0) {
-#pragma unroll
-        for (int b = 0; b < NSF; ++b) {
-          if (b < nsf) acc[b] = m00 * T.k00[row + b] + m01 * (T.k10[row + b] + T.k01[row + b]) + m11 * T.k11[row + b];
-        }
-      } else {
-#pragma unroll
-        for (int b = 0; b < NSF; ++b) {
-          if (b < nsf) acc[b] = m00 * T.k00[row + b] + m01 * (T.k10[row + b] + T.k01[row + b]) + m11 * T.k11[row + b] + gm * T.m[row + b];
-        }
-      }
-    } else {
-#pragma unroll
-      for (int b = 0; b < NSF; ++b) {
-        if (b < nsf) {
-          acc[b] = m00 * T.k00[row + b] + m01 * T.k10[row + b] + m10 * T.k01[row + b] + m11 * T.k11[row + b] + gm * T.m[row + b];
-        }
-      }
-    }
+    tensor_row<NSF>(T, a, m00, m01, m10, m11, gm, alpha.kind != LFGPU_COEFF_CONST_2X2, acc);
     return;
   }
   if (TENSOR_ONLY) return;
@@ -236,6 +241,25 @@ __device__ __forceinline__ void element_row(const CellGeom& g, const TabView& T,
       if (b < nsf) acc[b] += sx * T.gx[b * nq + k] + sy * T.gy[b * nq + k] + mm * T.phi[b * nq + k];
     }
   }
+}
+
+// per-cell metric of an affine cell with cell-wise constant coefficients: M = |det| Jinv A Jinv^T and gamma |det|
+__device__ __forceinline__ void cell_metric(const CellGeom& g, const DevCoeff& alpha, const DevCoeff& gamma, int64_t cell,
+                                            bool transpose_alpha, double& m00, double& m01, double& m10, double& m11, double& gm) {
+  double j00, j01, j10, j11;
+  jacobian(g, 0.0, 0.0, j00, j01, j10, j11);
+  const double det = j00 * j11 - j01 * j10;
+  const double adet = fabs(det), idet = fast_rcp(det);
+  const double i00 = j11 * idet, i01 = -j01 * idet, i10 = -j10 * idet, i11 = j00 * idet;
+  double a00, a01, a10, a11;
+  eval_alpha(alpha, cell, 0, transpose_alpha, a00, a01, a10, a11);
+  const double t00 = i00 * a00 + i01 * a10, t01 = i00 * a01 + i01 * a11;
+  const double t10 = i10 * a00 + i11 * a10, t11 = i10 * a01 + i11 * a11;
+  m00 = adet * (t00 * i00 + t01 * i01);
+  m01 = adet * (t00 * i10 + t01 * i11);
+  m10 = adet * (t10 * i00 + t11 * i01);
+  m11 = adet * (t10 * i10 + t11 * i11);
+  gm = adet * eval_scalar(gamma, cell, 0);
 }
 
 // cooperative copy of the table blob into shared memory; returns views.
@@ -399,6 +423,22 @@ __global__ void __launch_bounds__(THREADS, 6) k_assemble_gather(Tables hdr, cons
   (void)flags;
 }
 
+// Per-cell metric table for meshes of affine cells with cell-wise constant coefficients: (M00, M01, M10, M11, gamma |det|, 0)
+// with M = |det J| J^-1 A J^-T.  Computed once per numeric pass so that the 6..10 items of a cell neither repeat the
+// geometry nor chase cell -> vertices -> coordinates: an item then needs one 48-byte read.
+__global__ void __launch_bounds__(256) k_cell_metric(MeshView mv, int64_t n_cells, DevCoeff alpha, DevCoeff gamma, bool transpose_alpha,
+                                                     double* __restrict__ out) {
+  const int64_t cell = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (cell >= n_cells) return;
+  const CellGeom g = load_geom(mv, cell);
+  double m00, m01, m10, m11, gm;
+  cell_metric(g, alpha, gamma, cell, transpose_alpha, m00, m01, m10, m11, gm);
+  double2* o = reinterpret_cast<double2*>(out) + 3 * cell;
+  o[0] = make_double2(m00, m01);
+  o[1] = make_double2(m10, m11);
+  o[2] = make_double2(gm, 0.0);
+}
+
 // Item-parallel owner-computes kernel (the default without a row list): one thread per ITEM (cell, a) of the block's
 // outer indices, so the element rows of all items are computed concurrently and the work is balanced whatever the
 // valence of a dof.  The items of one dof are then folded into the block's shared-memory image of its value range in
@@ -412,7 +452,7 @@ __global__ void __launch_bounds__(256, TENSOR_ONLY ? 4 : 2) k_assemble_items(Tab
                                                            const uint32_t* __restrict__ adj, const P* __restrict__ pos_item,
                                                            const uint2* __restrict__ item_sorted, DevCoeff alpha, DevCoeff gamma,
                                                            const uint8_t* __restrict__ active, bool transpose_alpha, double beta,
-                                                           double* __restrict__ values) {
+                                                           const double* __restrict__ cell_metric_tab, double* __restrict__ values) {
   extern __shared__ double smem[];
   __shared__ int32_t s_out[257];
   const int tid = threadIdx.x;
@@ -445,10 +485,18 @@ __global__ void __launch_bounds__(256, TENSOR_ONLY ? 4 : 2) k_assemble_items(Tab
       const uint32_t* pp = reinterpret_cast<const uint32_t*>(pos_item + (static_cast<int64_t>(adj0) + tid) * pos_row);
 #pragma unroll
       for (int w = 0; w < kWords; ++w) pw[w] = __ldg(pp + w);
-      const CellGeom g = load_geom(mv, cell);
-      const TabView& T = g.quad ? tq : tt;
-      nsf = T.nsf;
-      element_row<NSF, TENSOR_ONLY>(g, T, a, alpha, gamma, cell, transpose_alpha, acc);
+      if (TENSOR_ONLY && cell_metric_tab != nullptr) {
+        // affine cells, cell-wise constant coefficients: the metric of every cell was computed once by k_cell_metric
+        const double2* mp = reinterpret_cast<const double2*>(cell_metric_tab) + 3 * cell;
+        const double2 ma = __ldg(mp), mb = __ldg(mp + 1), mc = __ldg(mp + 2);
+        nsf = tt.nsf;
+        tensor_row<NSF>(tt, a, ma.x, ma.y, mb.x, mb.y, mc.x, alpha.kind != LFGPU_COEFF_CONST_2X2, acc);
+      } else {
+        const CellGeom g = load_geom(mv, cell);
+        const TabView& T = g.quad ? tq : tt;
+        nsf = T.nsf;
+        element_row<NSF, TENSOR_ONLY>(g, T, a, alpha, gamma, cell, transpose_alpha, acc);
+      }
     }
   }
   __syncthreads();  // image zeroed
@@ -670,9 +718,19 @@ int launch_matrix(lfgpu_ctx* ctx, const HostTables& ht, const double* d_blob, co
       if (smem_i <= 200 * 1024) {
         auto ki = tensor_only ? k_assemble_items<NSF, P, true> : k_assemble_items<NSF, P, false>;
         LFGPU_CUDA_CHECK(ctx, cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_i)));
+        const double* metric = nullptr;
+        if (tensor_only && NSF > 3) {
+          // P2 / P3: each cell has 6 / 10 items -- compute its metric once (scratch owned by the pattern, 48 B per cell)
+          lfgpu_pattern* pm = const_cast<lfgpu_pattern*>(p);
+          if (pm->cell_metric == nullptr) LFGPU_CUDA_CHECK(ctx, cudaMalloc(&pm->cell_metric, sizeof(double) * 6 * p->n_cells));
+          k_cell_metric<<<static_cast<unsigned>(cdiv(p->n_cells, 256)), 256, 0, ctx->stream>>>(mv, p->n_cells, alpha, gamma, transpose_alpha,
+                                                                                              pm->cell_metric);
+          LFGPU_LAUNCH_CHECK(ctx);
+          metric = pm->cell_metric;
+        }
         ki<<<static_cast<unsigned>(p->n_item_blocks), 256, smem_i, ctx->stream>>>(
             ht.hdr, d_blob, table_mask, mv, p->blk_rows, p->pos_row, p->outer, p->adj_ptr, p->adj, static_cast<const P*>(p->pos_item),
-            static_cast<const uint2*>(p->item_sorted), alpha, gamma, active, transpose_alpha, beta, d_values);
+            static_cast<const uint2*>(p->item_sorted), alpha, gamma, active, transpose_alpha, beta, metric, d_values);
         LFGPU_LAUNCH_CHECK(ctx);
         return LFGPU_OK;
       }

@@ -84,6 +84,7 @@ struct lfgpu_pattern {
   void* item_sorted = nullptr;   // uint2 [n_items] in thread order: (cell << 4 | a, local row | rank << 8)
   uint32_t* item_perm = nullptr; // [n_items] per block: thread t -> local item | local row << 8 | rank-in-row << 16, sorted by (rank, row)
   int max_item_block_nnz = 0;
+  double* cell_metric = nullptr; // [n_cells][6] scratch of the numeric pass (assemble.cu: k_cell_metric)
   int max_items = 0;  // max number of cells adjacent to one outer dof
   // dof tables the plan was built from (device copies owned by the pattern)
   int32_t* o_dofs = nullptr;  // [n_cells][o_stride]

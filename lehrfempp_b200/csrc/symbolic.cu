@@ -226,6 +226,7 @@ void lfgpu_pattern_destroy(lfgpu_pattern* p) {
   cudaFree(p->pos_item);
   cudaFree(p->item_perm);
   cudaFree(p->item_sorted);
+  cudaFree(p->cell_metric);
   cudaFree(p->fan_nbr);
   cudaFree(p->fan_rowinfo);
   cudaFree(p->fan_irregular);
