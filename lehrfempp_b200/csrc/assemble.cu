@@ -446,26 +446,20 @@ __global__ void __launch_bounds__(256) k_cell_metric(MeshView mv, int64_t n_cell
 // atomics; ascending cell order per entry = the reference's summation order, bitwise repeatable).  The image is laid
 // out exactly like the output and leaves as one coalesced copy.
 template <int NSF, typename P, bool TENSOR_ONLY>
-__global__ void __launch_bounds__(256, TENSOR_ONLY ? 4 : 2) k_assemble_items(Tables hdr, const double* __restrict__ blob, int table_mask, MeshView mv,
-                                                           const int32_t* __restrict__ blk_rows, int pos_row,
-                                                           const int32_t* __restrict__ outer, const int32_t* __restrict__ adj_ptr,
-                                                           const uint32_t* __restrict__ adj, const P* __restrict__ pos_item,
+__global__ void __launch_bounds__(kItemThreads, TENSOR_ONLY ? (NSF <= 6 ? 6 : 5) : 4) k_assemble_items(Tables hdr, const double* __restrict__ blob, int table_mask, MeshView mv,
+                                                           const int4* __restrict__ blk_hdr, int pos_row, const P* __restrict__ pos_item,
                                                            const uint2* __restrict__ item_sorted, DevCoeff alpha, DevCoeff gamma,
                                                            const uint8_t* __restrict__ active, bool transpose_alpha, double beta,
                                                            const double* __restrict__ cell_metric_tab, double* __restrict__ values) {
   extern __shared__ double smem[];
-  __shared__ int32_t s_out[257];
   const int tid = threadIdx.x;
-  const int32_t R0 = __ldg(blk_rows + blockIdx.x), R1 = __ldg(blk_rows + blockIdx.x + 1);
-  const int nrows = R1 - R0;
-  const int32_t adj0 = __ldg(adj_ptr + R0), out0 = __ldg(outer + R0);
-  const int n_items = __ldg(adj_ptr + R1) - adj0;
-  for (int j = tid; j <= nrows; j += 256) s_out[j] = __ldg(outer + R0 + j) - out0;
+  const int4 bh = __ldg(blk_hdr + blockIdx.x);
+  const int32_t adj0 = bh.x, out0 = bh.y;
+  const int n_items = bh.z & 0xffff, max_rank = bh.z >> 16, total = bh.w;
   TabView tt, tq;
   load_tables(hdr, blob, smem, tt, tq, table_mask);  // contains a __syncthreads()
   double* image = smem + ((hdr.total + 1) & ~1);
-  const int total = s_out[nrows];
-  for (int k = tid; k < ((total + 15) & ~15); k += 256) image[k] = 0.0;
+  for (int k = tid; k < ((total + 15) & ~15); k += kItemThreads) image[k] = 0.0;
   // my item (threads are ordered by rank-in-dof, then dof: see k_item_perm)
   bool valid = tid < n_items;
   int rank = 0, off = 0, nsf = 0;
@@ -474,8 +468,8 @@ __global__ void __launch_bounds__(256, TENSOR_ONLY ? 4 : 2) k_assemble_items(Tab
   uint32_t pw[kWords];
   if (valid) {
     const uint2 w = __ldg(item_sorted + adj0 + tid);
-    rank = static_cast<int>(w.y >> 8);
-    off = s_out[w.y & 255U];
+    rank = static_cast<int>(w.y >> 16);
+    off = static_cast<int>(w.y & 0xffffU);
     const uint32_t item = w.x;
     const int64_t cell = item >> 4;
     const int a = static_cast<int>(item & 15U);
@@ -500,7 +494,8 @@ __global__ void __launch_bounds__(256, TENSOR_ONLY ? 4 : 2) k_assemble_items(Tab
     }
   }
   __syncthreads();  // image zeroed
-  for (int k = 0; __syncthreads_or(valid && rank >= k); ++k) {
+  for (int k = 0; k <= max_rank; ++k) {
+    if (k > 0) __syncthreads();
     if (valid && rank == k) {
 #pragma unroll
       for (int b = 0; b < NSF; ++b) {
@@ -512,11 +507,12 @@ __global__ void __launch_bounds__(256, TENSOR_ONLY ? 4 : 2) k_assemble_items(Tab
       }
     }
   }
+  __syncthreads();
   double* dst = values + out0;
   if (beta == 0.0) {
-    for (int k = tid; k < total; k += 256) dst[k] = image[swz(k)];
+    for (int k = tid; k < total; k += kItemThreads) dst[k] = image[swz(k)];
   } else {
-    for (int k = tid; k < total; k += 256) dst[k] = fma(beta, dst[k], image[swz(k)]);
+    for (int k = tid; k < total; k += kItemThreads) dst[k] = fma(beta, dst[k], image[swz(k)]);
   }
 }
 
@@ -728,8 +724,8 @@ int launch_matrix(lfgpu_ctx* ctx, const HostTables& ht, const double* d_blob, co
           LFGPU_LAUNCH_CHECK(ctx);
           metric = pm->cell_metric;
         }
-        ki<<<static_cast<unsigned>(p->n_item_blocks), 256, smem_i, ctx->stream>>>(
-            ht.hdr, d_blob, table_mask, mv, p->blk_rows, p->pos_row, p->outer, p->adj_ptr, p->adj, static_cast<const P*>(p->pos_item),
+        ki<<<static_cast<unsigned>(p->n_item_blocks), kItemThreads, smem_i, ctx->stream>>>(
+            ht.hdr, d_blob, table_mask, mv, static_cast<const int4*>(p->blk_hdr), p->pos_row, static_cast<const P*>(p->pos_item),
             static_cast<const uint2*>(p->item_sorted), alpha, gamma, active, transpose_alpha, beta, metric, d_values);
         LFGPU_LAUNCH_CHECK(ctx);
         return LFGPU_OK;

@@ -14,7 +14,8 @@
 namespace lfgpu {
 
 constexpr int kMaxNsf = 16;  // FeLagrangeO3Quad
-constexpr int kMaxNq = 36;   // largest user quadrature rule the tables hold (6x6 Gauss / 33-point triangle rule)
+constexpr int kMaxNq = 36;
+constexpr int kItemThreads = 256;  // block size of the item-parallel kernel = max items of one block of the plan   // largest user quadrature rule the tables hold (6x6 Gauss / 33-point triangle rule)
 
 void set_last_error(const lfgpu_ctx* ctx, const std::string& msg);
 
@@ -81,7 +82,8 @@ struct lfgpu_pattern {
   int64_t n_item_blocks = 0;
   int32_t* blk_rows = nullptr;   // [n_item_blocks + 1]
   void* pos_item = nullptr;      // [n_items][pos_row], same element type as pos
-  void* item_sorted = nullptr;   // uint2 [n_items] in thread order: (cell << 4 | a, local row | rank << 8)
+  void* blk_hdr = nullptr;       // int4 [n_item_blocks]: first item, first value, n_items | max rank << 16, number of values
+  void* item_sorted = nullptr;   // uint2 [n_items] in thread order: (cell << 4 | a, image offset of the dof | rank << 16)
   uint32_t* item_perm = nullptr; // [n_items] per block: thread t -> local item | local row << 8 | rank-in-row << 16, sorted by (rank, row)
   int max_item_block_nnz = 0;
   double* cell_metric = nullptr; // [n_cells][6] scratch of the numeric pass (assemble.cu: k_cell_metric)

@@ -101,17 +101,20 @@ __global__ void k_block_nnz(int64_t n_blocks, const int32_t* __restrict__ blk_ro
 }
 // thread order of the item kernel inside a block: items sorted by (rank within their dof, local index, dof), so that in
 // the k-th accumulation round the active threads are a contiguous range (whole warps work or idle)
-__global__ void __launch_bounds__(256) k_item_perm(const int32_t* __restrict__ blk_rows, const int32_t* __restrict__ adj_ptr,
-                                                   const uint32_t* __restrict__ adj, uint32_t* __restrict__ item_perm,
-                                                   uint2* __restrict__ item_sorted) {
-  using Sort = cub::BlockRadixSort<uint32_t, 256, 1, uint32_t>;
+__global__ void __launch_bounds__(kItemThreads) k_item_perm(const int32_t* __restrict__ blk_rows, const int32_t* __restrict__ adj_ptr,
+                                                   const int32_t* __restrict__ outer, const uint32_t* __restrict__ adj,
+                                                   uint32_t* __restrict__ item_perm, uint2* __restrict__ item_sorted,
+                                                   int4* __restrict__ blk_hdr) {
+  using Sort = cub::BlockRadixSort<uint32_t, kItemThreads, 1, uint32_t>;
   __shared__ typename Sort::TempStorage tmp;
-  __shared__ int32_t s_adj[257];
+  __shared__ int32_t s_adj[kItemThreads + 1];
+  __shared__ int s_max_rank;
   const int tid = threadIdx.x;
+  if (tid == 0) s_max_rank = 0;
   const int32_t R0 = blk_rows[blockIdx.x], R1 = blk_rows[blockIdx.x + 1];
   const int nrows = R1 - R0;
   const int32_t adj0 = adj_ptr[R0];
-  for (int j = tid; j <= nrows; j += 256) s_adj[j] = adj_ptr[R0 + j] - adj0;
+  for (int j = tid; j <= nrows; j += kItemThreads) s_adj[j] = adj_ptr[R0 + j] - adj0;
   __syncthreads();
   const int n_items = s_adj[nrows];
   uint32_t key[1] = {0xffffffffU}, val[1] = {0};
@@ -127,13 +130,21 @@ __global__ void __launch_bounds__(256) k_item_perm(const int32_t* __restrict__ b
     const uint32_t a = adj[adj0 + tid] & 15U;
     key[0] = (rank << 12) | (a << 8) | static_cast<uint32_t>(lo);
     val[0] = static_cast<uint32_t>(tid) | (static_cast<uint32_t>(lo) << 8) | (rank << 16);
+    atomicMax(&s_max_rank, static_cast<int>(rank));
   }
   Sort(tmp).Sort(key, val, 0, 20);
+  const int32_t out0 = outer[R0];
   if (tid < n_items) {
     item_perm[adj0 + tid] = val[0];
-    // thread-ordered copy of the items: (cell << 4 | a, local dof | rank << 8) -- one coalesced 8-byte load per thread
-    item_sorted[adj0 + tid] = make_uint2(adj[adj0 + (val[0] & 255U)], (val[0] >> 8) & 0xffffffU);
+    // thread-ordered copy of the items: (cell << 4 | a, offset of the dof's segment in the block image | rank << 16)
+    // -- one coalesced 8-byte load per thread, nothing else to look up
+    const uint32_t lo = (val[0] >> 8) & 255U;
+    const uint32_t off = static_cast<uint32_t>(outer[R0 + lo] - out0);
+    item_sorted[adj0 + tid] = make_uint2(adj[adj0 + (val[0] & 255U)], off | ((val[0] >> 16) << 16));
   }
+  __syncthreads();
+  // block header: everything the item kernel needs to start, in one 16-byte load
+  if (tid == 0) blk_hdr[blockIdx.x] = make_int4(adj0, out0, n_items | (s_max_rank << 16), outer[R1] - out0);
 }
 
 template <typename P>
@@ -226,6 +237,7 @@ void lfgpu_pattern_destroy(lfgpu_pattern* p) {
   cudaFree(p->pos_item);
   cudaFree(p->item_perm);
   cudaFree(p->item_sorted);
+  cudaFree(p->blk_hdr);
   cudaFree(p->cell_metric);
   cudaFree(p->fan_nbr);
   cudaFree(p->fan_rowinfo);
@@ -421,7 +433,7 @@ int lfgpu_symbolic(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* t
   SYM_CHECK(cudaStreamSynchronize(st));
   // ---- 4. item-parallel plan -----------------------------------------------------------------------------------
   if (p->max_items >= 1 && p->max_items <= 32 && p->n_items > 0) {
-    const int items_per_block = 256 - p->max_items;
+    const int items_per_block = kItemThreads - p->max_items;
     p->n_item_blocks = cdiv(p->n_items, items_per_block);
     SYM_CHECK(cudaMalloc(&p->blk_rows, sizeof(int32_t) * (p->n_item_blocks + 1)));
     k_block_rows<<<static_cast<unsigned>(cdiv(p->n_item_blocks + 1, kThreads)), kThreads, 0, st>>>(p->n_item_blocks, p->n_outer, items_per_block,
@@ -435,7 +447,7 @@ int lfgpu_symbolic(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* t
     SYM_CHECK(cudaMemcpyAsync(h_blk, d_blk, sizeof(h_blk), cudaMemcpyDeviceToHost, st));
     SYM_CHECK(cudaStreamSynchronize(st));
     p->max_item_block_nnz = h_blk[0];
-    if (h_blk[1] > 256 || h_blk[2] > 256) {  // rows without items would break the bound: keep the row-parallel kernel
+    if (h_blk[1] > kItemThreads || h_blk[2] > kItemThreads || h_blk[0] >= 65536) {  // rows without items would break the bound: keep the row-parallel kernel
       cudaFree(p->blk_rows);
       cudaFree(p->item_perm);
       p->blk_rows = nullptr;
@@ -443,8 +455,9 @@ int lfgpu_symbolic(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* t
       p->n_item_blocks = 0;
     } else {
       SYM_CHECK(cudaMalloc(&p->item_sorted, sizeof(uint2) * p->n_items));
-      k_item_perm<<<static_cast<unsigned>(p->n_item_blocks), 256, 0, st>>>(p->blk_rows, p->adj_ptr, p->adj, p->item_perm,
-                                                                           static_cast<uint2*>(p->item_sorted));
+      SYM_CHECK(cudaMalloc(&p->blk_hdr, sizeof(int4) * p->n_item_blocks));
+      k_item_perm<<<static_cast<unsigned>(p->n_item_blocks), kItemThreads, 0, st>>>(p->blk_rows, p->adj_ptr, p->outer, p->adj, p->item_perm,
+                                                                           static_cast<uint2*>(p->item_sorted), static_cast<int4*>(p->blk_hdr));
       ctx->launches++;
     const int64_t n_pos = p->n_items * p->pos_row;
       SYM_CHECK(cudaMalloc(&p->pos_item, static_cast<size_t>(p->pos_bytes) * n_pos));
