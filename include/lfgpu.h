@@ -181,6 +181,18 @@ int lfgpu_assemble_reaction_diffusion_rows(lfgpu_ctx* ctx, const lfgpu_mesh* mes
 int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* dofmap, int degree,
                         const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad, const lfgpu_coeff* f, const uint8_t* active,
                         double beta, double* d_vec, int algo);
+/* ---- essential boundary conditions (first "next" row) ------------------------------------------- */
+/* lf::assemble::FixFlaggedSolutionComponents (assemble/fix_dof.h:86-138) on the compressed matrix: with xhat = the
+ * prescribed values on the fixed dofs and 0 elsewhere,  rhs -= A * xhat;  rhs[fixed] = xhat;  every entry in a fixed row
+ * or column is erased (COOMatrix::setZero, assemble/coomatrix.h:108-115) and the diagonal of a fixed dof becomes 1.
+ * d_values / d_rhs are edited in place (erased entries stay as explicit zeros in the pattern of the symbolic pass).
+ * If d_outer_out [n+1], d_inner_out [>= nnz], d_values_out [>= nnz] are all non-null the erased entries are also
+ * removed, which yields exactly makeSparse() of the reference's edited triplet list; *nnz_out = entries kept.
+ * d_fixed: device uint8 [n_dofs] (non-zero = fixed), d_fixed_values: device double [n_dofs] (read where fixed).
+ * Errors: non-square matrix (fix_dof.h:90 "Matrix must be square!"), fixed dof without a diagonal entry.            */
+int lfgpu_fix_flagged_solution_components(lfgpu_ctx* ctx, const lfgpu_pattern* pattern, double* d_values, double* d_rhs,
+                                          const uint8_t* d_fixed, const double* d_fixed_values, int32_t* d_outer_out,
+                                          int32_t* d_inner_out, double* d_values_out, int64_t* nnz_out);
 /* ---- multi-GPU building blocks (DESIGN.md "Multi-GPU"; the reference is serial) --------------------------------------- */
 /* Row segments values[outer[r] .. outer[r+1]) of the listed rows <-> a contiguous message buffer.  d_rows device int32
  * [n_rows], d_offsets device int64 [n_rows] = start of each row's segment inside the buffer.  unpack_add ADDS the

@@ -62,6 +62,9 @@ def lib():
         L.lfo_assemble_rd.restype = C.c_void_p
         L.lfo_assemble_rd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Coeff), C.POINTER(Coeff),
                                       C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.lfo_assemble_fixed.restype = C.c_void_p
+        L.lfo_assemble_fixed.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_void_p]
         L.lfo_cm_sizes.argtypes = [C.c_void_p] + [C.POINTER(C.c_int64)] * 3
         L.lfo_cm_export.argtypes = [C.c_void_p] * 4
         L.lfo_cm_free.argtypes = [C.c_void_p]
@@ -251,6 +254,24 @@ class Mesh:
         lib().lfo_cm_export(h, _p(outer), _p(inner), _p(vals))
         lib().lfo_cm_free(h)
         return outer, inner, vals, (r.value, c.value), dict(assemble_s=ta.value, makesparse_s=tm.value)
+
+    def assemble_fixed(self, degree, alpha, gamma, f, fixed, fixed_vals, csr=False):
+        """Matrix + load vector with constant coefficients, then FixFlaggedSolutionComponents, then makeSparse.
+        Returns (outer, inner, values, rhs)."""
+        fixed = np.ascontiguousarray(fixed, dtype=np.uint8)
+        fixed_vals = np.ascontiguousarray(fixed_vals, dtype=np.float64)
+        n = self.num_dofs(degree)
+        rhs = np.zeros(n)
+        h = lib().lfo_assemble_fixed(self.h, degree, alpha, gamma, f, _p(fixed), _p(fixed_vals), 1 if csr else 0, _p(rhs))
+        _check(h)
+        r, c, nnz = C.c_int64(), C.c_int64(), C.c_int64()
+        lib().lfo_cm_sizes(h, C.byref(r), C.byref(c), C.byref(nnz))
+        outer = np.zeros(c.value + 1, np.int32)
+        inner = np.zeros(nnz.value, np.int32)
+        vals = np.zeros(nnz.value)
+        lib().lfo_cm_export(h, _p(outer), _p(inner), _p(vals))
+        lib().lfo_cm_free(h)
+        return outer, inner, vals, rhs
 
     def assemble_load(self, degree, f, qr_tria=-1, qr_quad=-1, active=None, out=None):
         n = self.num_dofs(degree)

@@ -194,6 +194,17 @@ class COOMatrix {
     triplets_.push_back(Triplet{static_cast<int>(i), static_cast<int>(j), increment});
   }
   void setZero() { triplets_.clear(); }
+  // coomatrix.h:108-115: remove every triplet for which pred(row, col) holds
+  template <typename PREDICATE>
+  void setZero(PREDICATE&& pred) {
+    auto new_last = std::remove_if(triplets_.begin(), triplets_.end(), [&pred](Triplet& t) { return pred(t.row, t.col); });
+    triplets_.erase(new_last, triplets_.end());
+  }
+  // coomatrix.h:250-262: resvec += alpha * A * vec, triplet by triplet
+  template <typename VECTOR, typename RESULTVECTOR>
+  void MatVecMult(double alpha, const VECTOR& vec, RESULTVECTOR& resvec) const {
+    for (const Triplet& t : triplets_) resvec[t.row] += t.value * (alpha * vec[t.col]);
+  }
   [[nodiscard]] const std::vector<Triplet>& triplets() const { return triplets_; }
 
   // coomatrix.h:172-180 -> Eigen 3.4.0 SparseMatrix::setFromTriplets (set_from_triplets in SparseMatrix.h):
@@ -261,6 +272,30 @@ class COOMatrix {
   gdof_idx_t rows_, cols_;
   std::vector<Triplet> triplets_;
 };
+
+// lib/lf/assemble/fix_dof.h:86-138: enforce prescribed solution components on the COO matrix and the right-hand side.
+// SELECTOR: idx -> std::pair<bool, double>
+template <typename SELECTOR, typename RHSVECTOR>
+void FixFlaggedSolutionComponents(SELECTOR&& selectvals, COOMatrix& A, RHSVECTOR& b) {
+  const gdof_idx_t N = A.cols();
+  LFO_VERIFY(A.rows() == N, "Matrix must be square!");
+  {
+    std::vector<double> tmp_vec(N);
+    for (gdof_idx_t k = 0; k < N; ++k) {
+      const auto selval{selectvals(k)};
+      tmp_vec[k] = selval.first ? selval.second : 0.0;
+    }
+    A.MatVecMult(-1.0, tmp_vec, b);
+  }
+  for (gdof_idx_t k = 0; k < N; ++k) {
+    const auto selval{selectvals(k)};
+    if (selval.first) b[k] = selval.second;
+  }
+  A.setZero([&selectvals](gdof_idx_t i, gdof_idx_t j) { return selectvals(i).first || selectvals(j).first; });
+  for (gdof_idx_t dofnum = 0; dofnum < N; ++dofnum) {
+    if (selectvals(dofnum).first) A.AddToEntry(dofnum, dofnum, 1.0);
+  }
+}
 
 // lib/lf/assemble/assembler.h:114-186
 template <typename TMPMATRIX, typename ENTITY_MATRIX_PROVIDER>

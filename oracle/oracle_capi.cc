@@ -442,6 +442,34 @@ void* lfo_assemble_rd(void* mesh_h, int degree, int qr_tria, int qr_quad, const 
   return run_matrix(*fes, prov, transpose, t_assemble, t_makesparse, repeat_accumulate);
   LFO_CATCH(nullptr)
 }
+// Assemble the P<degree> reaction-diffusion matrix and load vector (constant coefficients alpha, gamma, source f), then
+// FixFlaggedSolutionComponents (assemble/fix_dof.h:86-138) with flags/values per dof, then makeSparse.
+// rhs (length N) receives the modified right-hand side.  transpose as in lfo_assemble_rd.
+void* lfo_assemble_fixed(void* mesh_h, int degree, double alpha, double gamma, double f, const std::uint8_t* fixed,
+                         const double* fixed_vals, int transpose, double* rhs) {
+  LFO_TRY
+  auto* mh = static_cast<MeshH*>(mesh_h);
+  auto fes = std::make_shared<uscalfe::UniformScalarFESpace>(mh->mesh, degree);
+  const auto& dofh = fes->LocGlobMap();
+  using MF = uscalfe::MeshFunctionConstant<double>;
+  uscalfe::ReactionDiffusionElementMatrixProvider<MF, MF> prov(fes, MF(alpha), MF(gamma));
+  assemble::COOMatrix coo(dofh.NumDofs(), dofh.NumDofs());
+  assemble::AssembleMatrixLocally(0, dofh, dofh, prov, coo);
+  uscalfe::ScalarLoadElementVectorProvider<MF> lprov(fes, MF(f));
+  std::vector<double> b(dofh.NumDofs(), 0.0);
+  assemble::AssembleVectorLocally(0, dofh, lprov, b);
+  assemble::FixFlaggedSolutionComponents(
+      [&](gdof_idx_t i) { return std::make_pair(fixed[i] != 0, fixed_vals[i]); }, coo, b);
+  std::copy(b.begin(), b.end(), rhs);
+  if (transpose) {
+    assemble::COOMatrix t(coo.rows(), coo.cols());
+    for (const auto& tr : coo.triplets()) t.AddToEntry(tr.col, tr.row, tr.value);
+    return new assemble::CompressedMatrix(t.makeSparse());
+  }
+  return new assemble::CompressedMatrix(coo.makeSparse());
+  LFO_CATCH(nullptr)
+}
+
 void lfo_cm_sizes(void* h, std::int64_t* rows, std::int64_t* cols, std::int64_t* nnz) {
   auto* cm = static_cast<assemble::CompressedMatrix*>(h);
   *rows = cm->rows;
