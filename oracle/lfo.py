@@ -65,6 +65,8 @@ def lib():
         L.lfo_assemble_fixed.restype = C.c_void_p
         L.lfo_assemble_fixed.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int,
                                          C.c_void_p]
+        L.lfo_fix_coo.restype = C.c_void_p
+        L.lfo_fix_coo.argtypes = [C.c_int64, C.c_int64] + [C.c_void_p] * 6
         L.lfo_cm_sizes.argtypes = [C.c_void_p] + [C.POINTER(C.c_int64)] * 3
         L.lfo_cm_export.argtypes = [C.c_void_p] * 4
         L.lfo_cm_free.argtypes = [C.c_void_p]
@@ -365,3 +367,24 @@ def eval_fe(degree, ref_el_id, pts):
 
 def builtin_scalar(fid, x, y):
     return lib().lfo_builtin_scalar(fid, x, y)
+
+
+def fix_coo(n, rows, cols, vals, fixed, fixed_vals, rhs):
+    """FixFlaggedSolutionComponents on an n x n triplet list; returns (outer, inner, values) of makeSparse() (column-major)
+    and the modified right-hand side."""
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    cols = np.ascontiguousarray(cols, dtype=np.int32)
+    vals = np.ascontiguousarray(vals, dtype=np.float64)
+    fixed = np.ascontiguousarray(fixed, dtype=np.uint8)
+    fixed_vals = np.ascontiguousarray(fixed_vals, dtype=np.float64)
+    rhs = np.array(rhs, dtype=np.float64)
+    h = lib().lfo_fix_coo(n, len(vals), _p(rows), _p(cols), _p(vals), _p(fixed), _p(fixed_vals), _p(rhs))
+    _check(h)
+    r, c, nnz = C.c_int64(), C.c_int64(), C.c_int64()
+    lib().lfo_cm_sizes(h, C.byref(r), C.byref(c), C.byref(nnz))
+    outer = np.zeros(c.value + 1, np.int32)
+    inner = np.zeros(nnz.value, np.int32)
+    out = np.zeros(nnz.value)
+    lib().lfo_cm_export(h, _p(outer), _p(inner), _p(out))
+    lib().lfo_cm_free(h)
+    return outer, inner, out, rhs

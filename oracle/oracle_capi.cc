@@ -470,6 +470,21 @@ void* lfo_assemble_fixed(void* mesh_h, int degree, double alpha, double gamma, d
   LFO_CATCH(nullptr)
 }
 
+// FixFlaggedSolutionComponents on a caller-supplied triplet list (the shape of the reference's own test,
+// assemble/test/coomatrix_tests.cc:181-237): n x n COO matrix from AddToEntry(rows[k], cols[k], vals[k]), rhs in/out.
+void* lfo_fix_coo(std::int64_t n, std::int64_t n_trip, const std::int32_t* rows, const std::int32_t* cols, const double* vals,
+                  const std::uint8_t* fixed, const double* fixed_vals, double* rhs) {
+  LFO_TRY
+  assemble::COOMatrix coo(static_cast<size_type>(n), static_cast<size_type>(n));
+  for (std::int64_t k = 0; k < n_trip; ++k) coo.AddToEntry(rows[k], cols[k], vals[k]);
+  std::vector<double> b(rhs, rhs + n);
+  assemble::FixFlaggedSolutionComponents(
+      [&](gdof_idx_t i) { return std::make_pair(fixed[i] != 0, fixed_vals[i]); }, coo, b);
+  std::copy(b.begin(), b.end(), rhs);
+  return new assemble::CompressedMatrix(coo.makeSparse());
+  LFO_CATCH(nullptr)
+}
+
 void lfo_cm_sizes(void* h, std::int64_t* rows, std::int64_t* cols, std::int64_t* nnz) {
   auto* cm = static_cast<assemble::CompressedMatrix*>(h);
   *rows = cm->rows;
