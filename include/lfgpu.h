@@ -193,6 +193,11 @@ int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofm
 int lfgpu_fix_flagged_solution_components(lfgpu_ctx* ctx, const lfgpu_pattern* pattern, double* d_values, double* d_rhs,
                                           const uint8_t* d_fixed, const double* d_fixed_values, int32_t* d_outer_out,
                                           int32_t* d_inner_out, double* d_values_out, int64_t* nnz_out);
+/* lf::assemble::FixFlaggedSolutionCompAlt (assemble/fix_dof.h:181-218), the non-symmetric variant: only the ROWS of the
+ * fixed dofs become unit rows, rhs[fixed] = xhat, everything else untouched.  Same arguments as above.              */
+int lfgpu_fix_flagged_solution_comp_alt(lfgpu_ctx* ctx, const lfgpu_pattern* pattern, double* d_values, double* d_rhs,
+                                        const uint8_t* d_fixed, const double* d_fixed_values, int32_t* d_outer_out,
+                                        int32_t* d_inner_out, double* d_values_out, int64_t* nnz_out);
 /* ---- multi-GPU building blocks (DESIGN.md "Multi-GPU"; the reference is serial) --------------------------------------- */
 /* Row segments values[outer[r] .. outer[r+1]) of the listed rows <-> a contiguous message buffer.  d_rows device int32
  * [n_rows], d_offsets device int64 [n_rows] = start of each row's segment inside the buffer.  unpack_add ADDS the

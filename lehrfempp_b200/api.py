@@ -103,6 +103,7 @@ def _lib():
                                                          C.POINTER(_CCoeff), vp, dbl, vp, i32, vp, i64]),
         "lfgpu_assemble_load": (i32, [vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), C.POINTER(_CCoeff), vp, dbl, vp, i32]),
         "lfgpu_fix_flagged_solution_components": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "lfgpu_fix_flagged_solution_comp_alt": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "lfgpu_rows_pack": (i32, [vp, vp, vp, i64, vp, vp, vp]),
         "lfgpu_rows_unpack_add": (i32, [vp, vp, vp, i64, vp, vp, vp]),
         "lfgpu_pattern_adj_ptr_device": (vp, [vp]),
@@ -495,22 +496,22 @@ class Pattern:
             rows.n if rows is not None else 0))
         return out
 
-    def fix_flagged_solution_components(self, values, rhs, fixed, fixed_values, compact=False):
-        """FixFlaggedSolutionComponents(selectvals, A, b) (assemble/fix_dof.h:86-138) on the device.
+    def fix_flagged_solution_components(self, values, rhs, fixed, fixed_values, compact=False, alt=False):
+        """FixFlaggedSolutionComponents(selectvals, A, b) (assemble/fix_dof.h:86-138) on the device;
+        alt=True: FixFlaggedSolutionCompAlt (fix_dof.h:181-218), unit rows only.
 
         values [nnz] / rhs [n] are edited in place; fixed: DeviceArray(uint8) [n]; fixed_values: DeviceArray(float64) [n].
         compact=True additionally returns (outer, inner, values) DeviceArrays + nnz of the matrix with the erased
         entries removed -- makeSparse() of the reference's edited triplet list."""
-        L = self.ctx.L
+        fn = self.ctx.L.lfgpu_fix_flagged_solution_comp_alt if alt else self.ctx.L.lfgpu_fix_flagged_solution_components
         if not compact:
-            self.ctx.check(L.lfgpu_fix_flagged_solution_components(self.ctx.h, self.h, values.ptr, rhs.ptr, fixed.ptr,
-                                                                   fixed_values.ptr, None, None, None, None))
+            self.ctx.check(fn(self.ctx.h, self.h, values.ptr, rhs.ptr, fixed.ptr, fixed_values.ptr, None, None, None, None))
             return None
         n_outer = self.rows if self.major == ROW_MAJOR else self.cols
         outer = self.ctx.empty(n_outer + 1, np.int32)
         inner = self.ctx.empty(max(self.nnz, 1), np.int32)
         vals = self.ctx.empty(max(self.nnz, 1), np.float64)
         kept = C.c_int64(0)
-        self.ctx.check(L.lfgpu_fix_flagged_solution_components(self.ctx.h, self.h, values.ptr, rhs.ptr, fixed.ptr, fixed_values.ptr,
-                                                               outer.ptr, inner.ptr, vals.ptr, C.byref(kept)))
+        self.ctx.check(fn(self.ctx.h, self.h, values.ptr, rhs.ptr, fixed.ptr, fixed_values.ptr, outer.ptr, inner.ptr, vals.ptr,
+                          C.byref(kept)))
         return outer, inner, vals, kept.value

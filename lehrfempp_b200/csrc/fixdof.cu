@@ -46,14 +46,15 @@ __global__ void k_rhs_set(int64_t n, const uint8_t* __restrict__ fixed, const do
 }
 // one thread per outer index: rewrite values, flag survivors; missing diagonal of a fixed dof is an error
 __global__ void k_mark(int64_t n, const int32_t* __restrict__ outer, const int32_t* __restrict__ inner, double* __restrict__ values,
-                       const uint8_t* __restrict__ fixed, uint8_t* __restrict__ keep, int* __restrict__ flags) {
+                       const uint8_t* __restrict__ fixed, uint8_t* __restrict__ keep, int* __restrict__ flags, bool by_outer,
+                       bool by_inner) {
   const int64_t o = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (o >= n) return;
   const bool fo = fixed[o] != 0;
   bool diag_seen = false;
   for (int32_t k = outer[o]; k < outer[o + 1]; ++k) {
     const int32_t i = inner[k];
-    const bool erased = fo || fixed[i];
+    const bool erased = (by_outer && fo) || (by_inner && fixed[i]);
     if (erased) {
       const bool diag = (i == o);
       values[k] = diag ? 1.0 : 0.0;
@@ -76,14 +77,12 @@ __global__ void k_widen(int64_t n, const uint8_t* __restrict__ in, int32_t* __re
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) out[i] = in[i];
 }
-}  // namespace
-}  // namespace lfgpu
 
-using namespace lfgpu;
-
-extern "C" int lfgpu_fix_flagged_solution_components(lfgpu_ctx* ctx, const lfgpu_pattern* p, double* d_values, double* d_rhs,
-                                                      const uint8_t* d_fixed, const double* d_fixed_values, int32_t* d_outer_out,
-                                                      int32_t* d_inner_out, double* d_values_out, int64_t* nnz_out) {
+// rows_only = FixFlaggedSolutionCompAlt (fix_dof.h:181-218): unit ROWS for the fixed dofs, columns and the other
+// right-hand-side entries untouched.
+int fix_impl(lfgpu_ctx* ctx, const lfgpu_pattern* p, double* d_values, double* d_rhs, const uint8_t* d_fixed,
+             const double* d_fixed_values, int32_t* d_outer_out, int32_t* d_inner_out, double* d_values_out, int64_t* nnz_out,
+             bool rows_only) {
   if (ctx == nullptr || p == nullptr || d_values == nullptr || d_rhs == nullptr || d_fixed == nullptr || d_fixed_values == nullptr)
     return LFGPU_ERR_INVALID;
   if (p->n_outer != p->n_inner) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "Matrix must be square!");  // fix_dof.h:90
@@ -95,12 +94,14 @@ extern "C" int lfgpu_fix_flagged_solution_components(lfgpu_ctx* ctx, const lfgpu
   const int64_t N = p->n_outer, nnz = p->nnz;
   const unsigned gn = static_cast<unsigned>(cdiv(N, kThreads));
   // 1. right-hand side
-  if (p->major == LFGPU_ROW_MAJOR) {
-    k_rhs_rows<<<gn, kThreads, 0, st>>>(N, p->outer, p->inner, d_values, d_fixed, d_fixed_values, d_rhs);
-  } else {
-    k_rhs_cols<<<gn, kThreads, 0, st>>>(N, p->outer, p->inner, d_values, d_fixed, d_fixed_values, d_rhs);
+  if (!rows_only) {
+    if (p->major == LFGPU_ROW_MAJOR) {
+      k_rhs_rows<<<gn, kThreads, 0, st>>>(N, p->outer, p->inner, d_values, d_fixed, d_fixed_values, d_rhs);
+    } else {
+      k_rhs_cols<<<gn, kThreads, 0, st>>>(N, p->outer, p->inner, d_values, d_fixed, d_fixed_values, d_rhs);
+    }
+    LFGPU_LAUNCH_CHECK(ctx);
   }
-  LFGPU_LAUNCH_CHECK(ctx);
   k_rhs_set<<<gn, kThreads, 0, st>>>(N, d_fixed, d_fixed_values, d_rhs);
   LFGPU_LAUNCH_CHECK(ctx);
   // 2. matrix
@@ -116,7 +117,9 @@ extern "C" int lfgpu_fix_flagged_solution_components(lfgpu_ctx* ctx, const lfgpu
     cleanup();
     LFGPU_CUDA_CHECK(ctx, e);
   }
-  k_mark<<<gn, kThreads, 0, st>>>(N, p->outer, p->inner, d_values, d_fixed, keep, d_flags);
+  const bool by_outer = !rows_only || p->major == LFGPU_ROW_MAJOR;  // outer index is a row
+  const bool by_inner = !rows_only || p->major != LFGPU_ROW_MAJOR;  // inner index is a row
+  k_mark<<<gn, kThreads, 0, st>>>(N, p->outer, p->inner, d_values, d_fixed, keep, d_flags, by_outer, by_inner);
   ctx->launches++;
   int h_flags[2] = {0, 0};
   if (compact) {
@@ -152,4 +155,17 @@ extern "C" int lfgpu_fix_flagged_solution_components(lfgpu_ctx* ctx, const lfgpu
   LFGPU_CUDA_CHECK(ctx, e);
   if (h_flags[0]) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "a fixed dof has no diagonal entry in the pattern");
   return LFGPU_OK;
+}
+}  // namespace
+}  // namespace lfgpu
+
+extern "C" int lfgpu_fix_flagged_solution_components(lfgpu_ctx* ctx, const lfgpu_pattern* p, double* d_values, double* d_rhs,
+                                                      const uint8_t* d_fixed, const double* d_fixed_values, int32_t* d_outer_out,
+                                                      int32_t* d_inner_out, double* d_values_out, int64_t* nnz_out) {
+  return lfgpu::fix_impl(ctx, p, d_values, d_rhs, d_fixed, d_fixed_values, d_outer_out, d_inner_out, d_values_out, nnz_out, false);
+}
+extern "C" int lfgpu_fix_flagged_solution_comp_alt(lfgpu_ctx* ctx, const lfgpu_pattern* p, double* d_values, double* d_rhs,
+                                                    const uint8_t* d_fixed, const double* d_fixed_values, int32_t* d_outer_out,
+                                                    int32_t* d_inner_out, double* d_values_out, int64_t* nnz_out) {
+  return lfgpu::fix_impl(ctx, p, d_values, d_rhs, d_fixed, d_fixed_values, d_outer_out, d_inner_out, d_values_out, nnz_out, true);
 }

@@ -64,9 +64,9 @@ def lib():
                                       C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.lfo_assemble_fixed.restype = C.c_void_p
         L.lfo_assemble_fixed.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int,
-                                         C.c_void_p]
+                                         C.c_int, C.c_void_p]
         L.lfo_fix_coo.restype = C.c_void_p
-        L.lfo_fix_coo.argtypes = [C.c_int64, C.c_int64] + [C.c_void_p] * 6
+        L.lfo_fix_coo.argtypes = [C.c_int64, C.c_int64] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
         L.lfo_cm_sizes.argtypes = [C.c_void_p] + [C.POINTER(C.c_int64)] * 3
         L.lfo_cm_export.argtypes = [C.c_void_p] * 4
         L.lfo_cm_free.argtypes = [C.c_void_p]
@@ -257,14 +257,14 @@ class Mesh:
         lib().lfo_cm_free(h)
         return outer, inner, vals, (r.value, c.value), dict(assemble_s=ta.value, makesparse_s=tm.value)
 
-    def assemble_fixed(self, degree, alpha, gamma, f, fixed, fixed_vals, csr=False):
+    def assemble_fixed(self, degree, alpha, gamma, f, fixed, fixed_vals, csr=False, alt=False):
         """Matrix + load vector with constant coefficients, then FixFlaggedSolutionComponents, then makeSparse.
         Returns (outer, inner, values, rhs)."""
         fixed = np.ascontiguousarray(fixed, dtype=np.uint8)
         fixed_vals = np.ascontiguousarray(fixed_vals, dtype=np.float64)
         n = self.num_dofs(degree)
         rhs = np.zeros(n)
-        h = lib().lfo_assemble_fixed(self.h, degree, alpha, gamma, f, _p(fixed), _p(fixed_vals), 1 if csr else 0, _p(rhs))
+        h = lib().lfo_assemble_fixed(self.h, degree, alpha, gamma, f, _p(fixed), _p(fixed_vals), 1 if csr else 0, 1 if alt else 0, _p(rhs))
         _check(h)
         r, c, nnz = C.c_int64(), C.c_int64(), C.c_int64()
         lib().lfo_cm_sizes(h, C.byref(r), C.byref(c), C.byref(nnz))
@@ -369,7 +369,7 @@ def builtin_scalar(fid, x, y):
     return lib().lfo_builtin_scalar(fid, x, y)
 
 
-def fix_coo(n, rows, cols, vals, fixed, fixed_vals, rhs):
+def fix_coo(n, rows, cols, vals, fixed, fixed_vals, rhs, alt=False):
     """FixFlaggedSolutionComponents on an n x n triplet list; returns (outer, inner, values) of makeSparse() (column-major)
     and the modified right-hand side."""
     rows = np.ascontiguousarray(rows, dtype=np.int32)
@@ -378,7 +378,7 @@ def fix_coo(n, rows, cols, vals, fixed, fixed_vals, rhs):
     fixed = np.ascontiguousarray(fixed, dtype=np.uint8)
     fixed_vals = np.ascontiguousarray(fixed_vals, dtype=np.float64)
     rhs = np.array(rhs, dtype=np.float64)
-    h = lib().lfo_fix_coo(n, len(vals), _p(rows), _p(cols), _p(vals), _p(fixed), _p(fixed_vals), _p(rhs))
+    h = lib().lfo_fix_coo(n, len(vals), _p(rows), _p(cols), _p(vals), _p(fixed), _p(fixed_vals), 1 if alt else 0, _p(rhs))
     _check(h)
     r, c, nnz = C.c_int64(), C.c_int64(), C.c_int64()
     lib().lfo_cm_sizes(h, C.byref(r), C.byref(c), C.byref(nnz))

@@ -297,6 +297,22 @@ void FixFlaggedSolutionComponents(SELECTOR&& selectvals, COOMatrix& A, RHSVECTOR
   }
 }
 
+// lib/lf/assemble/fix_dof.h:181-218: the non-symmetric variant -- only the ROWS of fixed components are replaced by
+// unit rows, the right-hand side just receives the prescribed values.
+template <typename SELECTOR, typename RHSVECTOR>
+void FixFlaggedSolutionCompAlt(SELECTOR&& selectvals, COOMatrix& A, RHSVECTOR& b) {
+  const gdof_idx_t N = A.cols();
+  LFO_VERIFY(A.rows() == N, "Matrix must be square!");
+  for (gdof_idx_t k = 0; k < N; ++k) {
+    const auto selval{selectvals(k)};
+    if (selval.first) b[k] = selval.second;
+  }
+  A.setZero([&selectvals](gdof_idx_t i, gdof_idx_t /*j*/) { return selectvals(i).first; });
+  for (gdof_idx_t dofnum = 0; dofnum < N; ++dofnum) {
+    if (selectvals(dofnum).first) A.AddToEntry(dofnum, dofnum, 1.0);
+  }
+}
+
 // lib/lf/assemble/assembler.h:114-186
 template <typename TMPMATRIX, typename ENTITY_MATRIX_PROVIDER>
 void AssembleMatrixLocally(dim_t codim, const DofHandler& dof_handler_trial, const DofHandler& dof_handler_test,

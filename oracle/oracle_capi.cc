@@ -446,7 +446,7 @@ void* lfo_assemble_rd(void* mesh_h, int degree, int qr_tria, int qr_quad, const 
 // FixFlaggedSolutionComponents (assemble/fix_dof.h:86-138) with flags/values per dof, then makeSparse.
 // rhs (length N) receives the modified right-hand side.  transpose as in lfo_assemble_rd.
 void* lfo_assemble_fixed(void* mesh_h, int degree, double alpha, double gamma, double f, const std::uint8_t* fixed,
-                         const double* fixed_vals, int transpose, double* rhs) {
+                         const double* fixed_vals, int transpose, int alt, double* rhs) {
   LFO_TRY
   auto* mh = static_cast<MeshH*>(mesh_h);
   auto fes = std::make_shared<uscalfe::UniformScalarFESpace>(mh->mesh, degree);
@@ -458,8 +458,12 @@ void* lfo_assemble_fixed(void* mesh_h, int degree, double alpha, double gamma, d
   uscalfe::ScalarLoadElementVectorProvider<MF> lprov(fes, MF(f));
   std::vector<double> b(dofh.NumDofs(), 0.0);
   assemble::AssembleVectorLocally(0, dofh, lprov, b);
-  assemble::FixFlaggedSolutionComponents(
-      [&](gdof_idx_t i) { return std::make_pair(fixed[i] != 0, fixed_vals[i]); }, coo, b);
+  auto sel = [&](gdof_idx_t i) { return std::make_pair(fixed[i] != 0, fixed_vals[i]); };
+  if (alt) {
+    assemble::FixFlaggedSolutionCompAlt(sel, coo, b);
+  } else {
+    assemble::FixFlaggedSolutionComponents(sel, coo, b);
+  }
   std::copy(b.begin(), b.end(), rhs);
   if (transpose) {
     assemble::COOMatrix t(coo.rows(), coo.cols());
@@ -473,13 +477,17 @@ void* lfo_assemble_fixed(void* mesh_h, int degree, double alpha, double gamma, d
 // FixFlaggedSolutionComponents on a caller-supplied triplet list (the shape of the reference's own test,
 // assemble/test/coomatrix_tests.cc:181-237): n x n COO matrix from AddToEntry(rows[k], cols[k], vals[k]), rhs in/out.
 void* lfo_fix_coo(std::int64_t n, std::int64_t n_trip, const std::int32_t* rows, const std::int32_t* cols, const double* vals,
-                  const std::uint8_t* fixed, const double* fixed_vals, double* rhs) {
+                  const std::uint8_t* fixed, const double* fixed_vals, int alt, double* rhs) {
   LFO_TRY
   assemble::COOMatrix coo(static_cast<size_type>(n), static_cast<size_type>(n));
   for (std::int64_t k = 0; k < n_trip; ++k) coo.AddToEntry(rows[k], cols[k], vals[k]);
   std::vector<double> b(rhs, rhs + n);
-  assemble::FixFlaggedSolutionComponents(
-      [&](gdof_idx_t i) { return std::make_pair(fixed[i] != 0, fixed_vals[i]); }, coo, b);
+  auto sel = [&](gdof_idx_t i) { return std::make_pair(fixed[i] != 0, fixed_vals[i]); };
+  if (alt) {
+    assemble::FixFlaggedSolutionCompAlt(sel, coo, b);
+  } else {
+    assemble::FixFlaggedSolutionComponents(sel, coo, b);
+  }
   std::copy(b.begin(), b.end(), rhs);
   return new assemble::CompressedMatrix(coo.makeSparse());
   LFO_CATCH(nullptr)

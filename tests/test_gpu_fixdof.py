@@ -68,6 +68,26 @@ def test_fix_compact_matches_oracle(ctx, lf, kind, degree, csr):
     assert abs(A_inplace - A_oracle).max() <= TOL * np.abs(o_vals).max()
 
 
+@pytest.mark.parametrize("degree", [1, 3])
+@pytest.mark.parametrize("csr", [False, True])
+def test_fix_alt_matches_oracle(ctx, lf, degree, csr):
+    # FixFlaggedSolutionCompAlt (fix_dof.h:181-218): unit rows only
+    om, gm = meshes(ctx, "hybrid")
+    n = om.num_dofs(degree)
+    rng = np.random.default_rng(17 + degree)
+    fixed = (rng.random(n) < 0.3).astype(np.uint8)
+    xhat = rng.standard_normal(n)
+    o_outer, o_inner, o_vals, o_rhs = om.assemble_fixed(degree, 1.5, 0.5, 2.0, fixed, xhat, csr=csr, alt=True)
+    dm, pat, vals, rhs = gpu_system(ctx, lf, gm, degree, lf.ROW_MAJOR if csr else lf.COL_MAJOR, 1.5, 0.5, 2.0)
+    outer, inner, cvals, kept = pat.fix_flagged_solution_components(vals, rhs, ctx.to_device(fixed), ctx.to_device(xhat), compact=True,
+                                                                    alt=True)
+    assert kept == len(o_vals)
+    assert np.array_equal(outer.to_host(), o_outer)
+    assert np.array_equal(inner.to_host()[:kept], o_inner)
+    assert rel_max_err(cvals.to_host()[:kept], o_vals) <= TOL
+    assert rel_max_err(rhs.to_host(), o_rhs) <= TOL
+
+
 def test_fix_in_place_only(ctx, lf):
     om, gm = meshes(ctx, "hybrid")
     n = om.num_dofs(2)

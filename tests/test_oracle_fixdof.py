@@ -90,6 +90,32 @@ def test_reference_known_answer():
     assert len(v) == 28 - 4 * 3  # 28 entries; each fixed dof loses its 2 row and 2 column off-diagonals, keeps a unit diagonal
 
 
+def test_reference_known_answer_alt():
+    # coomatrix_tests.cc:123-179: the row-only variant has the same solution
+    n, rows, cols, vals, b, fixed, xhat, exact = tridiag_case()
+    outer, inner, v, rhs = lfo.fix_coo(n, rows, cols, vals, fixed, xhat, b, alt=True)
+    x = spla.spsolve(sp.csc_matrix((v, inner, outer), shape=(n, n)), rhs)
+    assert np.linalg.norm(x - exact) <= 1e-12
+    assert len(v) == 28 - 2 * 3  # only the two off-diagonals of each fixed ROW go
+    assert np.array_equal(rhs[fixed == 0], b[fixed == 0])
+
+
+def test_alt_matches_dense_definition():
+    om = lfo.Mesh.hybrid(5, 0.2, 12345)
+    n = om.num_dofs(2)
+    fixed, xhat = random_fixed(n, 3)
+    outer, inner, vals, rhs = om.assemble_fixed(2, 1.5, 0.5, 2.0, fixed, xhat, alt=True)
+    o0, i0, v0, shape, _ = om.assemble_rd(2, lfo.coeff.const(1.5), lfo.coeff.const(0.5))
+    A0 = sp.csc_matrix((v0, i0, o0), shape=shape).toarray()
+    b0, _ = om.assemble_load(2, lfo.coeff.const(2.0))
+    f = fixed.astype(bool)
+    A0[f, :] = 0.0
+    A0[f, f] = 1.0
+    b0[f] = xhat[f]
+    assert np.abs(sp.csc_matrix((vals, inner, outer), shape=(n, n)).toarray() - A0).max() <= 1e-13 * np.abs(v0).max()
+    assert np.array_equal(rhs, b0)
+
+
 def test_nothing_fixed_is_identity():
     om = lfo.Mesh.tp_quad(4, 3)
     n = om.num_dofs(2)
