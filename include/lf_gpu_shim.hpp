@@ -474,5 +474,47 @@ void AssembleVectorLocally(unsigned codim, const DOFH& dof_handler, ScalarLoadEl
   ctx.check(lfgpu_ctx_synchronize(ctx.get()), "lfgpu_ctx_synchronize");
 }
 
+// GPU overloads of lf::assemble::FixFlaggedSolutionComponents / FixFlaggedSolutionCompAlt (fix_dof.h:86-138,181-218):
+// same SELECTOR contract (gdof index -> std::pair<bool, double>), evaluated once per dof on the host; the matrix keeps
+// the pattern of the symbolic pass (erased entries become explicit zeros), the vector is edited in place.
+namespace detail {
+template <class SELECTOR>
+void fix_components(SELECTOR&& selectvals, CsrMatrix& A, Vector& b, bool rows_only) {
+  Context& ctx = A.ctx();
+  const std::int64_t n = A.cols();
+  if (A.rows() != n) throw Error(LFGPU_ERR_INVALID, "Matrix must be square!");
+  if (b.size() != n) throw Error(LFGPU_ERR_INVALID, "Mismatch of matrix and right-hand-side size");
+  std::vector<std::uint8_t> flags(n);
+  std::vector<double> vals(n, 0.0);
+  for (std::int64_t k = 0; k < n; ++k) {
+    const auto selval{selectvals(k)};
+    flags[k] = selval.first ? 1 : 0;
+    if (selval.first) vals[k] = selval.second;
+  }
+  void *d_flags = nullptr, *d_vals = nullptr;
+  ctx.check(lfgpu_malloc(ctx.get(), n, &d_flags), "lfgpu_malloc");
+  ctx.check(lfgpu_malloc(ctx.get(), 8 * n, &d_vals), "lfgpu_malloc");
+  int rc = lfgpu_memcpy_h2d(ctx.get(), d_flags, flags.data(), n);
+  if (rc == LFGPU_OK) rc = lfgpu_memcpy_h2d(ctx.get(), d_vals, vals.data(), 8 * n);
+  if (rc == LFGPU_OK) {
+    auto* fn = rows_only ? lfgpu_fix_flagged_solution_comp_alt : lfgpu_fix_flagged_solution_components;
+    rc = fn(ctx.get(), A.pattern(), A.device_values(), b.device(), static_cast<const std::uint8_t*>(d_flags),
+            static_cast<const double*>(d_vals), nullptr, nullptr, nullptr, nullptr);
+  }
+  if (rc == LFGPU_OK) rc = lfgpu_ctx_synchronize(ctx.get());
+  lfgpu_free(ctx.get(), d_flags);
+  lfgpu_free(ctx.get(), d_vals);
+  ctx.check(rc, "lfgpu_fix_flagged_solution_components");
+}
+}  // namespace detail
+template <class SCALAR = double, class SELECTOR>
+void FixFlaggedSolutionComponents(SELECTOR&& selectvals, CsrMatrix& A, Vector& b) {
+  detail::fix_components(selectvals, A, b, false);
+}
+template <class SCALAR = double, class SELECTOR>
+void FixFlaggedSolutionCompAlt(SELECTOR&& selectvals, CsrMatrix& A, Vector& b) {
+  detail::fix_components(selectvals, A, b, true);
+}
+
 }  // namespace lfgpu
 #endif
