@@ -305,7 +305,14 @@ def main():
             d2h_bytes = 8 * n_own
         e2e_steps = max(3, min(args.steps, 10))
 
+        e2e_blocks = int(os.environ.get("LFGPU_E2E_BLOCKS", "16"))
+
         def e2e_step():
+            if asm is None:
+                # the host-buffer C-ABI call: pinned coordinates in, pinned CSR values out; upload, kernel and download
+                # are pipelined over row blocks inside the call (csrc/hostpipe.cu); returns when h_vals is complete
+                pat.assemble_reaction_diffusion_host(degree, alpha, gamma, h_xy, h_vals, out=values, algo=algo, n_blocks=e2e_blocks)
+                return
             mesh.update_node_coords(h_xy.reshape(-1, 2))   # H2D of this step's input (16 B per node)
             step()                                           # numeric pass
             d2h()                                            # D2H of the CSR values
@@ -330,7 +337,9 @@ def main():
             h2d_b *= world
         e2e = {"value": mesh.n_cells / e2e_s, "unit": "cells/s", "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_bytes),
                "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-               "what": "per step: H2D node coordinates (pinned) -> lfgpu_assemble_reaction_diffusion -> D2H CSR values (pinned)"}
+               "what": ("per step: one lfgpu_assemble_reaction_diffusion_host call = H2D node coordinates (pinned) -> kernel -> D2H CSR "
+                        "values (pinned), pipelined over %d row blocks" % e2e_blocks) if asm is None else
+                       "per step: H2D node coordinates (pinned) -> partitioned assembly -> D2H of the owned CSR rows (pinned)"}
     t_end = time.time()
     if rank == 0:
         sampler.stop()

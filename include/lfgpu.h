@@ -181,6 +181,18 @@ int lfgpu_assemble_reaction_diffusion_rows(lfgpu_ctx* ctx, const lfgpu_mesh* mes
 int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* dofmap, int degree,
                         const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad, const lfgpu_coeff* f, const uint8_t* active,
                         double beta, double* d_vec, int algo);
+/* Host-buffer form of the matrix assembly -- the call a CPU-side user of AssembleMatrixLocally (assembler.h:114-186)
+ * makes: this step's node coordinates come from host memory (h_node_coords [n_nodes][2], NULL = keep the device copy),
+ * every cell is active, the values are overwritten in d_values (device, [nnz]) and copied to h_values (host [nnz],
+ * NULL = no download).  Returns when h_values is complete.  Page-locked host buffers (lfgpu_host_alloc_pinned) let
+ * upload, kernel and download overlap: the outer indices are processed in n_blocks (<= 0: default 16) contiguous
+ * blocks, each computed as soon as the leading part of the coordinate array it refers to is on the device and
+ * downloaded while later blocks are still uploading.  Results are identical to
+ * lfgpu_mesh_update_node_coords + lfgpu_assemble_reaction_diffusion + lfgpu_memcpy_d2h.                             */
+int lfgpu_assemble_reaction_diffusion_host(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const lfgpu_pattern* pattern, int degree,
+                                           const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad, const lfgpu_coeff* alpha,
+                                           const lfgpu_coeff* gamma, const double* h_node_coords, double* d_values,
+                                           double* h_values, int algo, int n_blocks);
 /* ---- essential boundary conditions (first "next" row) ------------------------------------------- */
 /* lf::assemble::FixFlaggedSolutionComponents (assemble/fix_dof.h:86-138) on the compressed matrix: with xhat = the
  * prescribed values on the fixed dofs and 0 elsewhere,  rhs -= A * xhat;  rhs[fixed] = xhat;  every entry in a fixed row

@@ -104,6 +104,8 @@ def _lib():
         "lfgpu_assemble_load": (i32, [vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), C.POINTER(_CCoeff), vp, dbl, vp, i32]),
         "lfgpu_fix_flagged_solution_components": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "lfgpu_fix_flagged_solution_comp_alt": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "lfgpu_assemble_reaction_diffusion_host": (i32, [vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), C.POINTER(_CCoeff),
+                                                         C.POINTER(_CCoeff), vp, vp, vp, i32, i32]),
         "lfgpu_rows_pack": (i32, [vp, vp, vp, i64, vp, vp, vp]),
         "lfgpu_rows_unpack_add": (i32, [vp, vp, vp, i64, vp, vp, vp]),
         "lfgpu_pattern_adj_ptr_device": (vp, [vp]),
@@ -494,6 +496,22 @@ class Pattern:
             self.ctx.h, self.mesh.h, self.h, degree, _qref(qr_tria), _qref(qr_quad), alpha.ref(), gamma.ref(),
             active.ptr if active is not None else None, beta, out.ptr, algo, rows.ptr if rows is not None else None,
             rows.n if rows is not None else 0))
+        return out
+
+    def assemble_reaction_diffusion_host(self, degree, alpha, gamma, h_node_coords, h_values, out=None, qr_tria=None, qr_quad=None,
+                                         algo=ALGO_AUTO, n_blocks=0):
+        """Host-buffer form: node coordinates from the numpy array h_node_coords (None = keep), values into the numpy array
+        h_values (None = no download); pinned arrays (Context.pinned) make upload, kernel and download overlap.
+        Returns the device values; synchronous."""
+        if out is None:
+            out = self.ctx.empty(self.nnz)
+        if h_node_coords is not None:
+            assert h_node_coords.dtype == np.float64 and h_node_coords.size == 2 * self.mesh.n_nodes and h_node_coords.flags.c_contiguous
+        if h_values is not None:
+            assert h_values.dtype == np.float64 and h_values.size == self.nnz and h_values.flags.c_contiguous
+        self.ctx.check(self.ctx.L.lfgpu_assemble_reaction_diffusion_host(
+            self.ctx.h, self.mesh.h, self.h, degree, _qref(qr_tria), _qref(qr_quad), alpha.ref(), gamma.ref(), _p(h_node_coords), out.ptr,
+            _p(h_values), algo, n_blocks))
         return out
 
     def fix_flagged_solution_components(self, values, rhs, fixed, fixed_values, compact=False, alt=False):

@@ -768,6 +768,18 @@ int lfgpu_assemble_reaction_diffusion_rows(lfgpu_ctx* ctx, const lfgpu_mesh* mes
                                            const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad, const lfgpu_coeff* alpha,
                                            const lfgpu_coeff* gamma, const uint8_t* active, double beta, double* d_values,
                                            int algo, const int32_t* d_row_list, int64_t n_rows) {
+  return lfgpu::assemble_rd_impl(ctx, mesh, p, degree, qr_tria, qr_quad, alpha, gamma, active, beta, d_values, algo, d_row_list, n_rows,
+                                 -1, nullptr);
+}
+}  // extern "C"
+
+// row0 >= 0 (with d_row_list == nullptr): only the contiguous outer range [row0, row0 + n_rows) -- fan path only.
+// fan_query != nullptr: nothing is launched; *fan_query tells whether this call would run entirely in the fan kernel.
+int lfgpu::assemble_rd_impl(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, int degree, const lfgpu_quad* qr_tria,
+                            const lfgpu_quad* qr_quad, const lfgpu_coeff* alpha, const lfgpu_coeff* gamma, const uint8_t* active,
+                            double beta, double* d_values, int algo, const int32_t* d_row_list, int64_t n_rows, int64_t row0,
+                            int* fan_query) {
+  if (fan_query != nullptr) *fan_query = 0;
   if (ctx == nullptr || mesh == nullptr || p == nullptr || d_values == nullptr) return LFGPU_ERR_INVALID;
   if (degree < 1 || degree > 3) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "degree must be 1, 2 or 3");
   if (p->n_cells != mesh->n_cells) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "pattern was built for another mesh");
@@ -804,7 +816,11 @@ int lfgpu_assemble_reaction_diffusion_rows(lfgpu_ctx* ctx, const lfgpu_mesh* mes
     }
     if (ok) {
       if ((rc = p1_fan_prepare(ctx, mesh, const_cast<lfgpu_pattern*>(p))) != LFGPU_OK) return rc;
-      ok = p->fan_state == 1 && (d_row_list == nullptr || p->n_irregular == 0);
+      ok = p->fan_state == 1 && ((d_row_list == nullptr && row0 < 0) || p->n_irregular == 0);
+    }
+    if (fan_query != nullptr) {
+      *fan_query = (ok && p->n_irregular == 0) ? 1 : 0;
+      return LFGPU_OK;
     }
     if (ok) {
       const bool tr = (p->major == LFGPU_ROW_MAJOR);
@@ -817,11 +833,13 @@ int lfgpu_assemble_reaction_diffusion_rows(lfgpu_ctx* ctx, const lfgpu_mesh* mes
                                                     LFGPU_ALGO_GATHER, p->fan_irregular, p->n_irregular);
         if (rc != LFGPU_OK) return rc;
       }
-      return p1_fan_launch(ctx, mesh, p, a, tensor, dg.c[0], wsum, m_diag, m_off, beta, d_row_list, n_rows, d_values);
+      return p1_fan_launch(ctx, mesh, p, a, tensor, dg.c[0], wsum, m_diag, m_off, beta, d_row_list, n_rows, d_values, row0);
     }
     if (algo == LFGPU_ALGO_FAN) LFGPU_FAIL(ctx, LFGPU_ERR_UNSUPPORTED, "LFGPU_ALGO_FAN needs P1 on a triangle mesh with constant coefficients and no activity mask");
     algo = LFGPU_ALGO_GATHER;
   }
+  if (fan_query != nullptr) return LFGPU_OK;
+  if (row0 >= 0) LFGPU_FAIL(ctx, LFGPU_ERR_UNSUPPORTED, "contiguous row ranges are a fan-kernel feature");
   if (algo != LFGPU_ALGO_ATOMIC && algo != LFGPU_ALGO_GATHER) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "unknown algo");
   if (d_row_list != nullptr && algo != LFGPU_ALGO_GATHER) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "a row list needs LFGPU_ALGO_GATHER");
   if ((rc = check_rules(ctx, mesh, ht)) != LFGPU_OK) return rc;
@@ -841,6 +859,8 @@ int lfgpu_assemble_reaction_diffusion_rows(lfgpu_ctx* ctx, const lfgpu_mesh* mes
 #undef LFGPU_DISPATCH
   return rc;
 }
+
+extern "C" {
 
 int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* dofmap, int degree, const lfgpu_quad* qr_tria,
                         const lfgpu_quad* qr_quad, const lfgpu_coeff* f, const uint8_t* active, double beta, double* d_vec, int algo) {

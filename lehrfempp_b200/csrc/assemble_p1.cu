@@ -218,12 +218,12 @@ template <int W, int MODE>
 __global__ void __launch_bounds__(128, 8) k_assemble_p1_fan(int64_t n_rows, int64_t n_total_rows, const uint32_t* __restrict__ nbr,
                                                          const uint8_t* __restrict__ rowinfo, const double* __restrict__ node_coords,
                                                          const int32_t* __restrict__ outer, const int32_t* __restrict__ row_list,
-                                                         FanParams P, double* __restrict__ values) {
+                                                         int64_t row0, FanParams P, double* __restrict__ values) {
   extern __shared__ double stage_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool in_range = t < n_rows;
-  const int64_t r = in_range ? (row_list != nullptr ? row_list[t] : t) : 0;
+  const int64_t r = in_range ? (row_list != nullptr ? row_list[t] : t + row0) : 0;
   int32_t v0 = 0, v1 = 0;
   uint32_t n[W];
   int info = 0;
@@ -414,9 +414,11 @@ int p1_fan_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
   return LFGPU_OK;
 }
 
-// launches the fan kernel over all rows (row_list == nullptr) or over the listed rows
+// launches the fan kernel over all rows (row_list == nullptr, row0 < 0), over the listed rows, or over the contiguous
+// range [row0, row0 + n_rows) (row_list == nullptr, row0 >= 0)
 int p1_fan_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, const double alpha[4], int tensor, double gamma,
-                  double wsum, double m_diag, double m_off, double beta, const int32_t* row_list, int64_t n_rows, double* d_values) {
+                  double wsum, double m_diag, double m_off, double beta, const int32_t* row_list, int64_t n_rows, double* d_values,
+                  int64_t row0) {
   FanParams P;
   P.a00 = alpha[0]; P.a01 = tensor ? alpha[1] : 0.0; P.a10 = tensor ? alpha[2] : 0.0; P.a11 = tensor ? alpha[3] : alpha[0];
   P.gamma = gamma;
@@ -424,8 +426,9 @@ int p1_fan_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p
   P.m_diag = m_diag;
   P.m_off = m_off;
   P.beta = beta;
-  const int64_t rows = row_list != nullptr ? n_rows : p->n_outer;
+  const int64_t rows = (row_list != nullptr || row0 >= 0) ? n_rows : p->n_outer;
   if (rows <= 0) return LFGPU_OK;
+  const int64_t first_row = (row_list == nullptr && row0 >= 0) ? row0 : 0;
   const int threads = 128;
   const unsigned grid = static_cast<unsigned>(cdiv(rows, threads));
   const int W = p->fan_w;
@@ -434,10 +437,10 @@ int p1_fan_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p
 #define FAN_LAUNCH(WW)                                                                                                          \
   if (simple)                                                                                                                   \
     k_assemble_p1_fan<WW, 0><<<grid, threads, smem, ctx->stream>>>(rows, p->n_outer, p->fan_nbr, p->fan_rowinfo, mesh->node_coords, \
-                                                                   p->outer, row_list, P, d_values);                            \
+                                                                   p->outer, row_list, first_row, P, d_values);                 \
   else                                                                                                                          \
     k_assemble_p1_fan<WW, 1><<<grid, threads, smem, ctx->stream>>>(rows, p->n_outer, p->fan_nbr, p->fan_rowinfo, mesh->node_coords, \
-                                                                   p->outer, row_list, P, d_values)
+                                                                   p->outer, row_list, first_row, P, d_values)
   switch (W) {
     case 6: FAN_LAUNCH(6); break;
     case 8: FAN_LAUNCH(8); break;

@@ -55,6 +55,9 @@ void lfgpu_ctx_destroy(lfgpu_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto& e : ctx->table_cache) cudaFree(e.dev);
+  for (cudaEvent_t ev : ctx->pipe_events) cudaEventDestroy(ev);
+  if (ctx->s_h2d != nullptr) cudaStreamDestroy(ctx->s_h2d);
+  if (ctx->s_d2h != nullptr) cudaStreamDestroy(ctx->s_d2h);
   cudaFree(ctx->d_scratch);
   cudaStreamDestroy(ctx->stream);
   delete ctx;

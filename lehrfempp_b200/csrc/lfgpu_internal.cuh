@@ -33,6 +33,9 @@ struct lfgpu_ctx {
     double* dev;
   };
   std::vector<TableEntry> table_cache;  // reference-element tables already on the device (assemble.cu)
+  // copy streams + events of the host pipeline (hostpipe.cu), created on first use
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  std::vector<cudaEvent_t> pipe_events;
 };
 
 struct lfgpu_mesh {
@@ -100,6 +103,11 @@ struct lfgpu_pattern {
   uint8_t* fan_rowinfo = nullptr;    // [n_outer] slot of the diagonal | closed-fan flag << 7
   int32_t* fan_irregular = nullptr;  // rows that are not a single fan (generic kernel)
   int64_t n_irregular = 0;
+  // host pipeline plan (hostpipe.cu): for hp_blocks equal blocks of outer indices, the number of leading node coordinates
+  // that must be on the device before block b can be computed (running maximum, so monotone)
+  int hp_blocks = 0;
+  std::vector<int64_t> hp_need;
+  std::vector<int64_t> hp_val;  // [hp_blocks + 1] first stored value of every block
 };
 
 namespace lfgpu {
@@ -158,7 +166,12 @@ int default_quad_rule(int cell_type, int degree, int capacity, double* points, d
 // P1 vertex-fan fast path (assemble_p1.cu)
 int p1_fan_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p);
 int p1_fan_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, const double alpha[4], int tensor, double gamma,
-                  double wsum, double m_diag, double m_off, double beta, const int32_t* row_list, int64_t n_rows, double* d_values);
+                  double wsum, double m_diag, double m_off, double beta, const int32_t* row_list, int64_t n_rows, double* d_values,
+                  int64_t row0 = -1);
+// body of lfgpu_assemble_reaction_diffusion_rows (assemble.cu) with two extras used by the host pipeline (hostpipe.cu)
+int assemble_rd_impl(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, int degree, const lfgpu_quad* qr_tria,
+                     const lfgpu_quad* qr_quad, const lfgpu_coeff* alpha, const lfgpu_coeff* gamma, const uint8_t* active, double beta,
+                     double* d_values, int algo, const int32_t* d_row_list, int64_t n_rows, int64_t row0, int* fan_query);
 
 }  // namespace lfgpu
 #endif
