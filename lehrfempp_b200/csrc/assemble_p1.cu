@@ -14,6 +14,9 @@
 //
 // Rows whose cells do not form a single fan (non-manifold vertices) or with more cells than the ring holds are listed
 // as "irregular" and go through the generic gather kernel (assemble.cu) first; this kernel then leaves them untouched.
+#include <algorithm>
+#include <cstdlib>
+
 #include <cub/cub.cuh>
 
 #include "lfgpu_internal.cuh"
@@ -214,39 +217,20 @@ __device__ __forceinline__ void fan_cell(const FanParams& P, double c, double ax
 }
 
 // ring slot = node id | slot-in-row << 28;  rowinfo = slot of the diagonal | closed << 7
+// One row per lane: ring n[] (kNil padded), value range [v0, v1), rowinfo; the warp's 32 rows are staged in `stage`.
 template <int W, int MODE>
-__global__ void __launch_bounds__(128, 8) k_assemble_p1_fan(int64_t n_rows, int64_t n_total_rows, const uint32_t* __restrict__ nbr,
-                                                         const uint8_t* __restrict__ rowinfo, const double* __restrict__ node_coords,
-                                                         const int32_t* __restrict__ outer, const int32_t* __restrict__ row_list,
-                                                         int64_t row0, FanParams P, double* __restrict__ values) {
-  extern __shared__ double stage_all[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const bool in_range = t < n_rows;
-  const int64_t r = in_range ? (row_list != nullptr ? row_list[t] : t + row0) : 0;
-  int32_t v0 = 0, v1 = 0;
-  uint32_t n[W];
-  int info = 0;
-  if (in_range) {
-    v0 = __ldg(outer + r);
-    v1 = __ldg(outer + r + 1);
-    info = __ldg(rowinfo + r);
-#pragma unroll
-    for (int s = 0; s < W; ++s) n[s] = __ldg(nbr + static_cast<int64_t>(s) * n_total_rows + r);
-  } else {
-#pragma unroll
-    for (int s = 0; s < W; ++s) n[s] = kNil;
-  }
+__device__ __forceinline__ void fan_row(const uint32_t (&n)[W], int32_t v0, int32_t v1, int info, int64_t r, bool in_range, int lane,
+                                        bool listed, double* __restrict__ stage, const double* __restrict__ node_coords,
+                                        const FanParams& P, double* __restrict__ values) {
   const bool regular = in_range && (n[0] != kNil);
   const bool closed = (info & 0x80) != 0;
   const int posd = info & 0x7f;
   const int32_t wbase = __shfl_sync(0xffffffffU, v0, 0);
-  double* stage = stage_all + warp * (32 * (W + 2));
   // staging: when the rows of a warp are consecutive (always without a row list, mostly with the row lists of a
   // partition) their values form one contiguous range that is written as full lines.  A warp that contains an
   // irregular row (computed by the generic kernel) or non-consecutive rows writes directly.
   const int64_t r_first = __shfl_sync(0xffffffffU, r, 0);
-  const bool consecutive = (row_list == nullptr) || !__any_sync(0xffffffffU, in_range && r != r_first + lane);
+  const bool consecutive = !listed || !__any_sync(0xffffffffU, in_range && r != r_first + lane);
   const bool staged = consecutive && !__any_sync(0xffffffffU, in_range && !regular && v1 > v0);
   if (regular) {
     const double2* nc = reinterpret_cast<const double2*>(node_coords);
@@ -330,10 +314,9 @@ __global__ void __launch_bounds__(128, 8) k_assemble_p1_fan(int64_t n_rows, int6
   if (staged) {
     __syncwarp();
     const unsigned ballot = __ballot_sync(0xffffffffU, in_range);
-    if (ballot == 0) return;
-    const int last = 31 - __clz(ballot);
+    const int last = ballot != 0 ? 31 - __clz(ballot) : 0;
     const int32_t wend = __shfl_sync(0xffffffffU, v1, last);
-    const int total = wend - wbase;
+    const int total = ballot != 0 ? wend - wbase : 0;
     double* out = values + wbase;
 #pragma unroll
     for (int k = 0; k < W + 2; ++k) {
@@ -341,6 +324,131 @@ __global__ void __launch_bounds__(128, 8) k_assemble_p1_fan(int64_t n_rows, int6
       if (idx < total) out[idx] = stage[idx];
     }
   }
+}
+
+// one thread per row, one pass
+template <int W, int MODE>
+__global__ void __launch_bounds__(128, 8) k_assemble_p1_fan(int64_t n_rows, int64_t n_total_rows, const uint32_t* __restrict__ nbr,
+                                                         const uint8_t* __restrict__ rowinfo, const double* __restrict__ node_coords,
+                                                         const int32_t* __restrict__ outer, const int32_t* __restrict__ row_list,
+                                                         int64_t row0, int64_t pf_dist, FanParams P, double* __restrict__ values) {
+  extern __shared__ double stage_all[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool in_range = t < n_rows;
+  const int64_t r = in_range ? (row_list != nullptr ? row_list[t] : t + row0) : 0;
+  // L2 prefetch for the warp pf_dist rows ahead (see k_assemble_p1_fan_compact): W ring slots, row info, row pointers,
+  // 4 lines of coordinates
+  if (pf_dist > 0 && row_list == nullptr) {
+    const int64_t tp = (t - lane) + pf_dist;
+    if (tp + 32 <= n_rows && lane <W + 6) {
+      const int64_t rp = tp + row0;
+      const void* a;
+      if (lane < W) {
+        a = nbr + lane * n_total_rows + rp;
+      } else if (lane == W) {
+        a = rowinfo + rp;
+      } else if (lane == W + 1) {
+        a = outer + rp;
+      } else {
+        a = node_coords + 2 * rp + 16 * (lane - (W + 2));
+      }
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+    }
+  }
+  int32_t v0 = 0, v1 = 0;
+  uint32_t n[W];
+  int info = 0;
+  if (in_range) {
+    v0 = __ldg(outer + r);
+    v1 = __ldg(outer + r + 1);
+    info = __ldg(rowinfo + r);
+#pragma unroll
+    for (int s = 0; s < W; ++s) n[s] = __ldg(nbr + static_cast<int64_t>(s) * n_total_rows + r);
+  } else {
+#pragma unroll
+    for (int s = 0; s < W; ++s) n[s] = kNil;
+  }
+  fan_row<W, MODE>(n, v0, v1, info, r, in_range, lane, row_list != nullptr, stage_all + warp * (32 * (W + 2)), node_coords, P, values);
+}
+
+// Same kernel on the compact plan (W = 6): ring ids as 16-bit offsets from the row id, the 4-bit slots of the ring
+// positions, the diagonal slot and the closed flag packed into one word per row: 16 B of plan per row instead of 25 B.
+template <int MODE>
+__global__ void __launch_bounds__(128, 8) k_assemble_p1_fan_compact(int64_t n_rows, int64_t n_total_rows, const int16_t* __restrict__ nbr16,
+                                                                 const uint32_t* __restrict__ info32, const double* __restrict__ node_coords,
+                                                                 const int32_t* __restrict__ outer, const int32_t* __restrict__ row_list,
+                                                                 int64_t row0, int64_t pf_dist, FanParams P,
+                                                                 double* __restrict__ values) {
+  constexpr int W = 6;
+  extern __shared__ double stage_all[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool in_range = t < n_rows;
+  const int64_t r = in_range ? (row_list != nullptr ? row_list[t] : t + row0) : 0;
+  // The warps of an SM run in phase (all wait for the plan, all wait for the coordinates, all compute), so DRAM latency
+  // is not hidden by occupancy.  Pull the lines of the warp that runs pf_dist rows later (about one grid wave) into
+  // L2 now: 6 ring slots x 64 B, row info, row pointers, 4 lines of coordinates -- 12 lanes, one instruction each.
+  if (pf_dist > 0 && row_list == nullptr) {
+    const int64_t tp = (t - lane) + pf_dist;
+    if (tp + 32 <= n_rows && lane <12) {
+      const int64_t rp = tp + row0;
+      const void* a;
+      if (lane < 6) {
+        a = nbr16 + lane * n_total_rows + rp;
+      } else if (lane == 6) {
+        a = info32 + rp;
+      } else if (lane == 7) {
+        a = outer + rp;
+      } else {
+        a = node_coords + 2 * rp + 16 * (lane - 8);
+      }
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+    }
+  }
+  int32_t v0 = 0, v1 = 0;
+  uint32_t n[W];
+  int info = 0;
+  if (in_range) {
+    v0 = __ldg(outer + r);
+    v1 = __ldg(outer + r + 1);
+    const uint32_t w = __ldg(info32 + r);
+    int d[W];
+#pragma unroll
+    for (int s = 0; s < W; ++s) d[s] = __ldg(nbr16 + static_cast<int64_t>(s) * n_total_rows + r);
+#pragma unroll
+    for (int s = 0; s < W; ++s)
+      n[s] = d[s] == 0 ? kNil : (static_cast<uint32_t>(static_cast<int32_t>(r) + d[s]) | (((w >> (4 * s)) & 15U) << 28));
+    info = static_cast<int>(((w >> 24) & 15U) | (((w >> 28) & 1U) << 7));
+  } else {
+#pragma unroll
+    for (int s = 0; s < W; ++s) n[s] = kNil;
+  }
+  fan_row<W, MODE>(n, v0, v1, info, r, in_range, lane, row_list != nullptr, stage_all + warp * (32 * (W + 2)), node_coords, P, values);
+}
+
+// plan compaction: one thread per row; *bad is raised if a ring id is further than 32767 from its row
+__global__ void k_fan_compact(int64_t n_rows, const uint32_t* __restrict__ nbr, const uint8_t* __restrict__ rowinfo,
+                              int16_t* __restrict__ nbr16, uint32_t* __restrict__ info32, int* __restrict__ bad) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const int info = rowinfo[r];
+  uint32_t w = (static_cast<uint32_t>(info & 0x7f) << 24) | (static_cast<uint32_t>((info >> 7) & 1) << 28);
+  for (int s = 0; s < 6; ++s) {
+    const uint32_t v = nbr[static_cast<int64_t>(s) * n_rows + r];
+    int16_t d = 0;
+    if (v != kNil) {
+      const int64_t delta = static_cast<int64_t>(v & 0x0fffffffU) - r;
+      if (delta < -32767 || delta > 32767 || delta == 0) {
+        *bad = 1;
+      } else {
+        d = static_cast<int16_t>(delta);
+      }
+      w |= (v >> 28) << (4 * s);
+    }
+    nbr16[static_cast<int64_t>(s) * n_rows + r] = d;
+  }
+  info32[r] = w;
 }
 
 }  // namespace
@@ -385,7 +493,7 @@ int p1_fan_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
     }                                                                               \
   } while (0)
   FAN_CHECK(cudaMalloc(&p->fan_nbr, sizeof(uint32_t) * static_cast<size_t>(W) * p->n_outer));
-  FAN_CHECK(cudaMalloc(&p->fan_rowinfo, p->n_outer));
+  FAN_CHECK(cudaMalloc(&p->fan_rowinfo, p->n_outer + 4));  // the prefetching kernel reads whole words
   k_fan_fill<<<gr, 256, 0, st>>>(p->n_outer, W, p->adj_ptr, p->adj, mesh->cell_nodes, ring_len, p->fan_nbr, p->fan_rowinfo);
   ctx->launches++;
   FAN_CHECK(cudaMalloc(&flag, p->n_outer));
@@ -411,6 +519,34 @@ int p1_fan_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
   p->n_irregular = n_irr;
   p->fan_w = W;
   p->fan_state = 1;
+  // compact plan where it applies (LFGPU_FAN_COMPACT=0 keeps the wide one, for A/B measurements)
+  const char* env = std::getenv("LFGPU_FAN_COMPACT");
+  if (W == 6 && (env == nullptr || env[0] != '0')) {
+    int16_t* n16 = nullptr;
+    uint32_t* i32 = nullptr;
+    cudaError_t ce = cudaMalloc(&n16, sizeof(int16_t) * 6 * static_cast<size_t>(p->n_outer));
+    if (ce == cudaSuccess) ce = cudaMalloc(&i32, sizeof(uint32_t) * static_cast<size_t>(p->n_outer));
+    int bad = 1;
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(d_flags, 0, sizeof(int), st);
+    if (ce == cudaSuccess) {
+      k_fan_compact<<<gr, 256, 0, st>>>(p->n_outer, p->fan_nbr, p->fan_rowinfo, n16, i32, d_flags);
+      ctx->launches++;
+      ce = cudaMemcpyAsync(&bad, d_flags, sizeof(int), cudaMemcpyDeviceToHost, st);
+    }
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    if (ce == cudaSuccess && bad == 0) {
+      p->fan_nbr16 = n16;
+      p->fan_info32 = i32;
+      cudaFree(p->fan_nbr);
+      cudaFree(p->fan_rowinfo);
+      p->fan_nbr = nullptr;
+      p->fan_rowinfo = nullptr;
+    } else {
+      cudaFree(n16);
+      cudaFree(i32);
+      (void)cudaGetLastError();  // an allocation failure here only means: stay with the wide plan
+    }
+  }
   return LFGPU_OK;
 }
 
@@ -432,15 +568,29 @@ int p1_fan_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p
   const int threads = 128;
   const unsigned grid = static_cast<unsigned>(cdiv(rows, threads));
   const int W = p->fan_w;
-  const size_t smem = sizeof(double) * (threads / 32) * 32 * (W + 2);
   const bool simple = !tensor && gamma == 0.0 && beta == 0.0;  // the plain Laplacian: leanest instantiation
+  const size_t smem = sizeof(double) * (threads / 32) * 32 * (W + 2);
+  // L2 prefetch distance in rows: 3/4 of a wave of resident CTAs (measured best of 1/8 .. 4 waves on B200;
+  // LFGPU_FAN_PFD = percent of a wave, 0 = off)
+  static const int pfd_env = [] { const char* e = std::getenv("LFGPU_FAN_PFD"); return e != nullptr ? std::atoi(e) : 75; }();
+  const int64_t pf_dist = (static_cast<int64_t>(ctx->sm_count) * 8 * threads * pfd_env / 100) & ~static_cast<int64_t>(31);
+  if (p->fan_nbr16 != nullptr) {
+    if (simple)
+      k_assemble_p1_fan_compact<0><<<grid, threads, smem, ctx->stream>>>(rows, p->n_outer, p->fan_nbr16, p->fan_info32, mesh->node_coords,
+                                                                          p->outer, row_list, first_row, pf_dist, P, d_values);
+    else
+      k_assemble_p1_fan_compact<1><<<grid, threads, smem, ctx->stream>>>(rows, p->n_outer, p->fan_nbr16, p->fan_info32, mesh->node_coords,
+                                                                          p->outer, row_list, first_row, pf_dist, P, d_values);
+    LFGPU_LAUNCH_CHECK(ctx);
+    return LFGPU_OK;
+  }
 #define FAN_LAUNCH(WW)                                                                                                          \
   if (simple)                                                                                                                   \
     k_assemble_p1_fan<WW, 0><<<grid, threads, smem, ctx->stream>>>(rows, p->n_outer, p->fan_nbr, p->fan_rowinfo, mesh->node_coords, \
-                                                                   p->outer, row_list, first_row, P, d_values);                 \
+                                                                   p->outer, row_list, first_row, pf_dist, P, d_values);        \
   else                                                                                                                          \
     k_assemble_p1_fan<WW, 1><<<grid, threads, smem, ctx->stream>>>(rows, p->n_outer, p->fan_nbr, p->fan_rowinfo, mesh->node_coords, \
-                                                                   p->outer, row_list, first_row, P, d_values)
+                                                                   p->outer, row_list, first_row, pf_dist, P, d_values)
   switch (W) {
     case 6: FAN_LAUNCH(6); break;
     case 8: FAN_LAUNCH(8); break;

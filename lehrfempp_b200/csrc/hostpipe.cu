@@ -16,18 +16,15 @@
 namespace lfgpu {
 namespace {
 constexpr int kThreads = 256;
-constexpr uint32_t kNilNode = 0xFFFFFFFFu;
 
-// need[b] = 1 + largest node index the fan kernel reads for the rows of block b (the row's own node and its ring)
-__global__ void k_block_need(int64_t n_rows, int W, const uint32_t* __restrict__ nbr, int64_t rows_per_block,
-                             unsigned long long* __restrict__ need) {
+// need[b] = 1 + largest node index the fan kernel reads for the rows of block b.  The fan kernel runs on nodal P1
+// tables only, where the stored columns of row r are exactly node r and its ring (and the pattern is symmetric).
+__global__ void k_block_need(int64_t n_rows, const int32_t* __restrict__ outer, const int32_t* __restrict__ inner,
+                             int64_t rows_per_block, unsigned long long* __restrict__ need) {
   const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (r >= n_rows) return;
   unsigned long long m = static_cast<unsigned long long>(r);
-  for (int s = 0; s < W; ++s) {
-    const uint32_t v = nbr[static_cast<int64_t>(s) * n_rows + r];
-    if (v != kNilNode) m = max(m, static_cast<unsigned long long>(v & 0x0fffffffU));
-  }
+  for (int32_t k = outer[r]; k < outer[r + 1]; ++k) m = max(m, static_cast<unsigned long long>(inner[k]));
   atomicMax(need + r / rows_per_block, m + 1);
 }
 
@@ -50,7 +47,7 @@ int build_plan(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p, int nb)
   LFGPU_CUDA_CHECK(ctx, cudaMalloc(&d_need, sizeof(unsigned long long) * nb));
   cudaError_t e = cudaMemsetAsync(d_need, 0, sizeof(unsigned long long) * nb, ctx->stream);
   if (e == cudaSuccess) {
-    k_block_need<<<static_cast<unsigned>(cdiv(N, kThreads)), kThreads, 0, ctx->stream>>>(N, p->fan_w, p->fan_nbr, rpb, d_need);
+    k_block_need<<<static_cast<unsigned>(cdiv(N, kThreads)), kThreads, 0, ctx->stream>>>(N, p->outer, p->inner, rpb, d_need);
     ctx->launches++;
     e = cudaGetLastError();
   }

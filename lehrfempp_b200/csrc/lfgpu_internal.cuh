@@ -101,6 +101,9 @@ struct lfgpu_pattern {
   int fan_w = 0;                     // ring slots per row
   uint32_t* fan_nbr = nullptr;       // [fan_w][n_outer] neighbour ring of every row, slot-major: node id | slot-in-row << 28
   uint8_t* fan_rowinfo = nullptr;    // [n_outer] slot of the diagonal | closed-fan flag << 7
+  // compact form of the same plan (rings of <= 6 neighbours whose ids are within +-32767 of the row): fan_nbr is freed
+  int16_t* fan_nbr16 = nullptr;      // [6][n_outer] neighbour id - row id, 0 = empty slot
+  uint32_t* fan_info32 = nullptr;    // [n_outer] 4 bits slot-in-row per ring position | diagonal slot << 24 | closed << 28
   int32_t* fan_irregular = nullptr;  // rows that are not a single fan (generic kernel)
   int64_t n_irregular = 0;
   // host pipeline plan (hostpipe.cu): for hp_blocks equal blocks of outer indices, the number of leading node coordinates

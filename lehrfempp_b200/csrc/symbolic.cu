@@ -241,6 +241,8 @@ void lfgpu_pattern_destroy(lfgpu_pattern* p) {
   cudaFree(p->cell_metric);
   cudaFree(p->fan_nbr);
   cudaFree(p->fan_rowinfo);
+  cudaFree(p->fan_nbr16);
+  cudaFree(p->fan_info32);
   cudaFree(p->fan_irregular);
   cudaFree(p->o_dofs);
   if (p->i_dofs != p->o_dofs) cudaFree(p->i_dofs);
