@@ -216,40 +216,40 @@ __device__ __forceinline__ void fan_cell(const FanParams& P, double c, double ax
   }
 }
 
-// ring slot = node id | slot-in-row << 28;  rowinfo = slot of the diagonal | closed << 7
-// One row per lane: ring n[] (kNil padded), value range [v0, v1), rowinfo; the warp's 32 rows are staged in `stage`.
+__device__ __forceinline__ void prefetch_l2(const void* a) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a)); }
+
+// One row per lane.  nid[]: node ids of the ring in fan order (< 0 = empty slot; a row that is not a single fan has
+// nid[0] < 0 and is left alone), pos[]: slot of every ring column inside the row, [v0, v1): the row's value range, posd:
+// slot of the diagonal, closed: the fan closes around the node.
+// The values of the warp's rows are collected in the warp's shared-memory stage: at offset v0 - wbase when the 32
+// rows are consecutive (always without a row list, mostly with the row lists of a partition) -- then the stage is the
+// image of one contiguous range of the output and leaves as full 128-byte lines -- else at lane * (W + 1), and every
+// lane copies its own row.  A warp that contains a non-fan row (computed by the generic kernel) takes the second way.
 template <int W, int MODE>
-__device__ __forceinline__ void fan_row(const uint32_t (&n)[W], int32_t v0, int32_t v1, int info, int64_t r, bool in_range, int lane,
-                                        bool listed, double* __restrict__ stage, const double* __restrict__ node_coords,
-                                        const FanParams& P, double* __restrict__ values) {
-  const bool regular = in_range && (n[0] != kNil);
-  const bool closed = (info & 0x80) != 0;
-  const int posd = info & 0x7f;
+__device__ __forceinline__ void fan_row(const int32_t (&nid)[W], const int (&pos)[W], int32_t v0, int32_t v1, int posd, bool closed,
+                                        int32_t r, bool in_range, int lane, bool listed, double* __restrict__ stage,
+                                        const double* __restrict__ node_coords, const FanParams& P, double* __restrict__ values) {
+  const bool regular = in_range && nid[0] >= 0;
   const int32_t wbase = __shfl_sync(0xffffffffU, v0, 0);
-  // staging: when the rows of a warp are consecutive (always without a row list, mostly with the row lists of a
-  // partition) their values form one contiguous range that is written as full lines.  A warp that contains an
-  // irregular row (computed by the generic kernel) or non-consecutive rows writes directly.
-  const int64_t r_first = __shfl_sync(0xffffffffU, r, 0);
+  const int32_t r_first = __shfl_sync(0xffffffffU, r, 0);
   const bool consecutive = !listed || !__any_sync(0xffffffffU, in_range && r != r_first + lane);
   const bool staged = consecutive && !__any_sync(0xffffffffU, in_range && !regular && v1 > v0);
+  double* dst = stage + (staged ? v0 - wbase : lane * (W + 1));
   if (regular) {
     const double2* nc = reinterpret_cast<const double2*>(node_coords);
     const double2 xi = __ldg(nc + r);
     double dx[W], dy[W], dd[W];
-    int pos[W];
     int m = 0;
 #pragma unroll
     for (int s = 0; s < W; ++s) {
-      const bool valid = (n[s] != kNil);
-      const double2 p = __ldg(nc + (valid ? (n[s] & 0x0fffffffU) : static_cast<uint32_t>(r)));
+      const bool valid = nid[s] >= 0;
+      const double2 p = __ldg(nc + (valid ? nid[s] : r));
       dx[s] = p.x - xi.x;
       dy[s] = p.y - xi.y;
       dd[s] = dx[s] * dx[s] + dy[s] * dy[s];
-      pos[s] = static_cast<int>(n[s] >> 28);
       m += valid ? 1 : 0;
     }
     const double c = P.wsum * P.a00;
-    double* dst = staged ? (stage + (v0 - wbase)) : (values + v0);
     const double* old = values + v0;
     double diag = 0.0;
     if (m == W && closed) {
@@ -311,120 +311,139 @@ __device__ __forceinline__ void fan_row(const uint32_t (&n)[W], int32_t v0, int3
     if (MODE != 0 && P.beta != 0.0) diag = fma(P.beta, old[posd], diag);
     dst[posd] = diag;
   }
+  __syncwarp();
   if (staged) {
-    __syncwarp();
     const unsigned ballot = __ballot_sync(0xffffffffU, in_range);
-    const int last = ballot != 0 ? 31 - __clz(ballot) : 0;
-    const int32_t wend = __shfl_sync(0xffffffffU, v1, last);
-    const int total = ballot != 0 ? wend - wbase : 0;
+    if (ballot == 0) return;
+    const int total = __shfl_sync(0xffffffffU, v1, 31 - __clz(ballot)) - wbase;
     double* out = values + wbase;
 #pragma unroll
-    for (int k = 0; k < W + 2; ++k) {
+    for (int k = 0; k < W + 1; ++k) {  // a row has at most W + 1 stored values
       const int idx = k * 32 + lane;
       if (idx < total) out[idx] = stage[idx];
     }
+  } else if (regular) {
+    const int len = v1 - v0;
+    for (int k = 0; k < len; ++k) values[v0 + k] = dst[k];
   }
 }
 
-// one thread per row, one pass
+// The warps of an SM run in phase (all wait for the plan words, all wait for the coordinates, all compute), so the
+// DRAM latency of the kernel's two dependent load levels is not hidden by occupancy (ncu: half of all stall samples on
+// the first use of either).  Warp 0 of every CTA therefore pulls the lines of the CTA that runs pf_dist rows later
+// (about 3/4 of a wave of resident CTAs) into L2 -- plan, row pointers, and the CTA's own coordinates; the ring
+// neighbours' coordinates are some other row's own coordinates inside the same window.  Both load levels then hit L2.
+
+// one thread per row: wide plan (ring slot = node id | slot-in-row << 28; rowinfo = slot of the diagonal | closed << 7)
 template <int W, int MODE>
-__global__ void __launch_bounds__(128, 8) k_assemble_p1_fan(int64_t n_rows, int64_t n_total_rows, const uint32_t* __restrict__ nbr,
+__global__ void __launch_bounds__(128, 8) k_assemble_p1_fan(int n_rows, int n_total_rows, const uint32_t* __restrict__ nbr,
                                                          const uint8_t* __restrict__ rowinfo, const double* __restrict__ node_coords,
-                                                         const int32_t* __restrict__ outer, const int32_t* __restrict__ row_list,
-                                                         int64_t row0, int64_t pf_dist, FanParams P, double* __restrict__ values) {
+                                                         const int32_t* __restrict__ outer, const int32_t* __restrict__ row_list, int row0,
+                                                         int pf_dist, FanParams P, double* __restrict__ values) {
   extern __shared__ double stage_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = t < n_rows;
-  const int64_t r = in_range ? (row_list != nullptr ? row_list[t] : t + row0) : 0;
-  // L2 prefetch for the warp pf_dist rows ahead (see k_assemble_p1_fan_compact): W ring slots, row info, row pointers,
-  // 4 lines of coordinates
-  if (pf_dist > 0 && row_list == nullptr) {
-    const int64_t tp = (t - lane) + pf_dist;
-    if (tp + 32 <= n_rows && lane <W + 6) {
-      const int64_t rp = tp + row0;
-      const void* a;
-      if (lane < W) {
-        a = nbr + lane * n_total_rows + rp;
-      } else if (lane == W) {
-        a = rowinfo + rp;
-      } else if (lane == W + 1) {
-        a = outer + rp;
-      } else {
-        a = node_coords + 2 * rp + 16 * (lane - (W + 2));
+  const int32_t r = in_range ? (row_list != nullptr ? row_list[t] : t + row0) : 0;
+  if (pf_dist > 0 && row_list == nullptr && warp == 0) {
+    const int tp = blockIdx.x * blockDim.x + pf_dist;
+    if (tp + 128 <= n_rows) {
+      const size_t rp = static_cast<size_t>(tp) + row0;
+      for (int L = lane; L < 4 * W + 21; L += 32) {  // 128-byte lines: 4 per ring slot, 1 row info, 4 row pointers, 16 coordinates
+        const char* a;
+        if (L < 4 * W) {
+          a = reinterpret_cast<const char*>(nbr + static_cast<size_t>(L >> 2) * n_total_rows + rp) + (L & 3) * 128;
+        } else if (L == 4 * W) {
+          a = reinterpret_cast<const char*>(rowinfo + rp);
+        } else if (L < 4 * W + 5) {
+          a = reinterpret_cast<const char*>(outer + rp) + (L - 4 * W - 1) * 128;
+        } else {
+          a = reinterpret_cast<const char*>(node_coords + 2 * rp) + (L - 4 * W - 5) * 128;
+        }
+        prefetch_l2(a);
       }
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
     }
   }
   int32_t v0 = 0, v1 = 0;
-  uint32_t n[W];
+  int32_t nid[W];
+  int pos[W];
   int info = 0;
   if (in_range) {
     v0 = __ldg(outer + r);
     v1 = __ldg(outer + r + 1);
     info = __ldg(rowinfo + r);
 #pragma unroll
-    for (int s = 0; s < W; ++s) n[s] = __ldg(nbr + static_cast<int64_t>(s) * n_total_rows + r);
+    for (int s = 0; s < W; ++s) {
+      const uint32_t u = __ldg(nbr + static_cast<size_t>(s) * n_total_rows + r);
+      nid[s] = u == kNil ? -1 : static_cast<int32_t>(u & 0x0fffffffU);
+      pos[s] = static_cast<int>(u >> 28);
+    }
   } else {
 #pragma unroll
-    for (int s = 0; s < W; ++s) n[s] = kNil;
+    for (int s = 0; s < W; ++s) {
+      nid[s] = -1;
+      pos[s] = 0;
+    }
   }
-  fan_row<W, MODE>(n, v0, v1, info, r, in_range, lane, row_list != nullptr, stage_all + warp * (32 * (W + 2)), node_coords, P, values);
+  fan_row<W, MODE>(nid, pos, v0, v1, info & 0x7f, (info & 0x80) != 0, r, in_range, lane, row_list != nullptr,
+                   stage_all + warp * (32 * (W + 2)), node_coords, P, values);
 }
 
-// Same kernel on the compact plan (W = 6): ring ids as 16-bit offsets from the row id, the 4-bit slots of the ring
+// Same kernel on the compact plan (W = 6): ring ids as 16-bit offsets from the row id; the 4-bit slots of the ring
 // positions, the diagonal slot and the closed flag packed into one word per row: 16 B of plan per row instead of 25 B.
 template <int MODE>
-__global__ void __launch_bounds__(128, 8) k_assemble_p1_fan_compact(int64_t n_rows, int64_t n_total_rows, const int16_t* __restrict__ nbr16,
+__global__ void __launch_bounds__(128, 8) k_assemble_p1_fan_compact(int n_rows, int n_total_rows, const int16_t* __restrict__ nbr16,
                                                                  const uint32_t* __restrict__ info32, const double* __restrict__ node_coords,
                                                                  const int32_t* __restrict__ outer, const int32_t* __restrict__ row_list,
-                                                                 int64_t row0, int64_t pf_dist, FanParams P,
-                                                                 double* __restrict__ values) {
+                                                                 int row0, int pf_dist, FanParams P, double* __restrict__ values) {
   constexpr int W = 6;
   extern __shared__ double stage_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = t < n_rows;
-  const int64_t r = in_range ? (row_list != nullptr ? row_list[t] : t + row0) : 0;
-  // The warps of an SM run in phase (all wait for the plan, all wait for the coordinates, all compute), so DRAM latency
-  // is not hidden by occupancy.  Pull the lines of the warp that runs pf_dist rows later (about one grid wave) into
-  // L2 now: 6 ring slots x 64 B, row info, row pointers, 4 lines of coordinates -- 12 lanes, one instruction each.
-  if (pf_dist > 0 && row_list == nullptr) {
-    const int64_t tp = (t - lane) + pf_dist;
-    if (tp + 32 <= n_rows && lane <12) {
-      const int64_t rp = tp + row0;
-      const void* a;
-      if (lane < 6) {
-        a = nbr16 + lane * n_total_rows + rp;
-      } else if (lane == 6) {
-        a = info32 + rp;
-      } else if (lane == 7) {
-        a = outer + rp;
+  const int32_t r = in_range ? (row_list != nullptr ? row_list[t] : t + row0) : 0;
+  if (pf_dist > 0 && row_list == nullptr && warp == 0) {
+    const int tp = blockIdx.x * blockDim.x + pf_dist;
+    if (tp + 128 <= n_rows) {
+      // 36 lines of 128 B: 2 per ring slot, 4 row info, 4 row pointers, 16 coordinates
+      const size_t rp = static_cast<size_t>(tp) + row0;
+      const char* a;
+      if (lane < 12) {
+        a = reinterpret_cast<const char*>(nbr16 + static_cast<size_t>(lane >> 1) * n_total_rows + rp) + (lane & 1) * 128;
+      } else if (lane < 16) {
+        a = reinterpret_cast<const char*>(info32 + rp) + (lane - 12) * 128;
+      } else if (lane < 20) {
+        a = reinterpret_cast<const char*>(outer + rp) + (lane - 16) * 128;
       } else {
-        a = node_coords + 2 * rp + 16 * (lane - 8);
+        a = reinterpret_cast<const char*>(node_coords + 2 * rp) + (lane - 20) * 128;
       }
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+      prefetch_l2(a);
+      if (lane < 4) prefetch_l2(reinterpret_cast<const char*>(node_coords + 2 * rp) + (12 + lane) * 128);
     }
   }
   int32_t v0 = 0, v1 = 0;
-  uint32_t n[W];
-  int info = 0;
+  int32_t nid[W];
+  int pos[W];
+  uint32_t w = 0;
   if (in_range) {
     v0 = __ldg(outer + r);
     v1 = __ldg(outer + r + 1);
-    const uint32_t w = __ldg(info32 + r);
-    int d[W];
+    w = __ldg(info32 + r);
 #pragma unroll
-    for (int s = 0; s < W; ++s) d[s] = __ldg(nbr16 + static_cast<int64_t>(s) * n_total_rows + r);
-#pragma unroll
-    for (int s = 0; s < W; ++s)
-      n[s] = d[s] == 0 ? kNil : (static_cast<uint32_t>(static_cast<int32_t>(r) + d[s]) | (((w >> (4 * s)) & 15U) << 28));
-    info = static_cast<int>(((w >> 24) & 15U) | (((w >> 28) & 1U) << 7));
+    for (int s = 0; s < W; ++s) {
+      const int d = __ldg(nbr16 + static_cast<size_t>(s) * n_total_rows + r);
+      nid[s] = d == 0 ? -1 : r + d;
+      pos[s] = static_cast<int>((w >> (4 * s)) & 15U);
+    }
   } else {
 #pragma unroll
-    for (int s = 0; s < W; ++s) n[s] = kNil;
+    for (int s = 0; s < W; ++s) {
+      nid[s] = -1;
+      pos[s] = 0;
+    }
   }
-  fan_row<W, MODE>(n, v0, v1, info, r, in_range, lane, row_list != nullptr, stage_all + warp * (32 * (W + 2)), node_coords, P, values);
+  fan_row<W, MODE>(nid, pos, v0, v1, static_cast<int>((w >> 24) & 15U), ((w >> 28) & 1U) != 0, r, in_range, lane, row_list != nullptr,
+                   stage_all + warp * (32 * (W + 2)), node_coords, P, values);
 }
 
 // plan compaction: one thread per row; *bad is raised if a ring id is further than 32767 from its row
@@ -573,24 +592,25 @@ int p1_fan_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p
   // L2 prefetch distance in rows: 3/4 of a wave of resident CTAs (measured best of 1/8 .. 4 waves on B200;
   // LFGPU_FAN_PFD = percent of a wave, 0 = off)
   static const int pfd_env = [] { const char* e = std::getenv("LFGPU_FAN_PFD"); return e != nullptr ? std::atoi(e) : 75; }();
-  const int64_t pf_dist = (static_cast<int64_t>(ctx->sm_count) * 8 * threads * pfd_env / 100) & ~static_cast<int64_t>(31);
+  const int ipf = static_cast<int>((static_cast<int64_t>(ctx->sm_count) * 8 * threads * pfd_env / 100) & ~static_cast<int64_t>(127));
+  const int irows = static_cast<int>(rows), itotal = static_cast<int>(p->n_outer), ifirst = static_cast<int>(first_row);  // < 2^28 (p1_fan_prepare)
   if (p->fan_nbr16 != nullptr) {
     if (simple)
-      k_assemble_p1_fan_compact<0><<<grid, threads, smem, ctx->stream>>>(rows, p->n_outer, p->fan_nbr16, p->fan_info32, mesh->node_coords,
-                                                                          p->outer, row_list, first_row, pf_dist, P, d_values);
+      k_assemble_p1_fan_compact<0><<<grid, threads, smem, ctx->stream>>>(irows, itotal, p->fan_nbr16, p->fan_info32, mesh->node_coords,
+                                                                          p->outer, row_list, ifirst, ipf, P, d_values);
     else
-      k_assemble_p1_fan_compact<1><<<grid, threads, smem, ctx->stream>>>(rows, p->n_outer, p->fan_nbr16, p->fan_info32, mesh->node_coords,
-                                                                          p->outer, row_list, first_row, pf_dist, P, d_values);
+      k_assemble_p1_fan_compact<1><<<grid, threads, smem, ctx->stream>>>(irows, itotal, p->fan_nbr16, p->fan_info32, mesh->node_coords,
+                                                                          p->outer, row_list, ifirst, ipf, P, d_values);
     LFGPU_LAUNCH_CHECK(ctx);
     return LFGPU_OK;
   }
 #define FAN_LAUNCH(WW)                                                                                                          \
   if (simple)                                                                                                                   \
-    k_assemble_p1_fan<WW, 0><<<grid, threads, smem, ctx->stream>>>(rows, p->n_outer, p->fan_nbr, p->fan_rowinfo, mesh->node_coords, \
-                                                                   p->outer, row_list, first_row, pf_dist, P, d_values);        \
+    k_assemble_p1_fan<WW, 0><<<grid, threads, smem, ctx->stream>>>(irows, itotal, p->fan_nbr, p->fan_rowinfo, mesh->node_coords, \
+                                                                   p->outer, row_list, ifirst, ipf, P, d_values);        \
   else                                                                                                                          \
-    k_assemble_p1_fan<WW, 1><<<grid, threads, smem, ctx->stream>>>(rows, p->n_outer, p->fan_nbr, p->fan_rowinfo, mesh->node_coords, \
-                                                                   p->outer, row_list, first_row, pf_dist, P, d_values)
+    k_assemble_p1_fan<WW, 1><<<grid, threads, smem, ctx->stream>>>(irows, itotal, p->fan_nbr, p->fan_rowinfo, mesh->node_coords, \
+                                                                   p->outer, row_list, ifirst, ipf, P, d_values)
   switch (W) {
     case 6: FAN_LAUNCH(6); break;
     case 8: FAN_LAUNCH(8); break;
