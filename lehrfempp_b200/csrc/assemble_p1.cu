@@ -589,9 +589,9 @@ int p1_fan_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p
   const int W = p->fan_w;
   const bool simple = !tensor && gamma == 0.0 && beta == 0.0;  // the plain Laplacian: leanest instantiation
   const size_t smem = sizeof(double) * (threads / 32) * 32 * (W + 2);
-  // L2 prefetch distance in rows: 3/4 of a wave of resident CTAs (measured best of 1/8 .. 4 waves on B200;
-  // LFGPU_FAN_PFD = percent of a wave, 0 = off)
-  static const int pfd_env = [] { const char* e = std::getenv("LFGPU_FAN_PFD"); return e != nullptr ? std::atoi(e) : 75; }();
+  // L2 prefetch distance in rows: one wave of resident CTAs (flat optimum between 1/2 and 2 waves on B200, slower
+  // below 1/4 and above 4; LFGPU_FAN_PFD = percent of a wave, 0 = off)
+  static const int pfd_env = [] { const char* e = std::getenv("LFGPU_FAN_PFD"); return e != nullptr ? std::atoi(e) : 100; }();
   const int ipf = static_cast<int>((static_cast<int64_t>(ctx->sm_count) * 8 * threads * pfd_env / 100) & ~static_cast<int64_t>(127));
   const int irows = static_cast<int>(rows), itotal = static_cast<int>(p->n_outer), ifirst = static_cast<int>(first_row);  // < 2^28 (p1_fan_prepare)
   if (p->fan_nbr16 != nullptr) {
