@@ -222,7 +222,8 @@ def main():
         t_part = time.time()
         # default: owner-computes (faster: one launch per rank, no collective); LFGPU_DIST_MODE=exchange selects the
         # contributions-to-owner variant with the NCCL all-to-all-v (both are parity-tested by tests/dist_gpu_check.py)
-        dist_mode = os.environ.get("LFGPU_DIST_MODE", "owner")
+        # owner_rows (default): the same owner-computes scheme over contiguous row blocks -- one range launch per rank
+        dist_mode = os.environ.get("LFGPU_DIST_MODE", "owner_rows")
         asm = DistributedAssembler(ctx, mesh, pat, degree, mode=dist_mode)
         t_part = time.time() - t_part
 
@@ -385,7 +386,10 @@ def main():
                    "algo": args.algo, "l2": "inputs+outputs per step (%.2f GB) exceed the 126 MB L2; no explicit flush" % (alg_bytes / 1e9),
                    "parallelism": "1 GPU" if world == 1 else (
                        "Morton cell partition x%d, interface rows to owner by one NCCL all-to-all-v overlapped with interior rows%s" % (world, ", step replayed as a CUDA graph" if use_graph else "")
-                       if asm.mode == "exchange" else "Morton cell partition x%d, owner-computes rows (halo cells recomputed, no data-path collective)" % world),
+                       if asm.mode == "exchange" else
+                       "Morton cell partition x%d, owner-computes rows (halo cells recomputed, no data-path collective)" % world
+                       if asm.mode == "owner" else
+                       "%d contiguous row blocks of equal nnz, owner-computes (halo cells recomputed, no data-path collective)" % world),
                    "symbolic_pass_s": round(t_sym, 3), "setup_s": round(t_setup, 3), "partition_s": round(t_part, 3)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_cell": alg_bytes / mesh.n_cells,

@@ -181,6 +181,13 @@ int lfgpu_assemble_reaction_diffusion_rows(lfgpu_ctx* ctx, const lfgpu_mesh* mes
 int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* dofmap, int degree,
                         const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad, const lfgpu_coeff* f, const uint8_t* active,
                         double beta, double* d_vec, int algo);
+/* Same, restricted to the contiguous outer range [row0, row0 + n_rows): the row partition of a multi-GPU run by row
+ * blocks (every cell is active).  Runs in the P1 vertex-fan kernel only; LFGPU_ERR_UNSUPPORTED otherwise -- pass the
+ * rows as a list to lfgpu_assemble_reaction_diffusion_rows then.                                                    */
+int lfgpu_assemble_reaction_diffusion_range(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* pattern, int degree,
+                                            const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad, const lfgpu_coeff* alpha,
+                                            const lfgpu_coeff* gamma, double beta, double* d_values, int algo, int64_t row0,
+                                            int64_t n_rows);
 /* Host-buffer form of the matrix assembly -- the call a CPU-side user of AssembleMatrixLocally (assembler.h:114-186)
  * makes: this step's node coordinates come from host memory (h_node_coords [n_nodes][2], NULL = keep the device copy),
  * every cell is active, the values are overwritten in d_values (device, [nnz]) and copied to h_values (host [nnz],

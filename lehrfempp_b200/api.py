@@ -101,6 +101,8 @@ def _lib():
                                                     C.POINTER(_CCoeff), vp, dbl, vp, i32]),
         "lfgpu_assemble_reaction_diffusion_rows": (i32, [vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), C.POINTER(_CCoeff),
                                                          C.POINTER(_CCoeff), vp, dbl, vp, i32, vp, i64]),
+        "lfgpu_assemble_reaction_diffusion_range": (i32, [vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), C.POINTER(_CCoeff),
+                                                          C.POINTER(_CCoeff), dbl, vp, i32, i64, i64]),
         "lfgpu_assemble_load": (i32, [vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), C.POINTER(_CCoeff), vp, dbl, vp, i32]),
         "lfgpu_fix_flagged_solution_components": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "lfgpu_fix_flagged_solution_comp_alt": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
@@ -496,6 +498,16 @@ class Pattern:
             self.ctx.h, self.mesh.h, self.h, degree, _qref(qr_tria), _qref(qr_quad), alpha.ref(), gamma.ref(),
             active.ptr if active is not None else None, beta, out.ptr, algo, rows.ptr if rows is not None else None,
             rows.n if rows is not None else 0))
+        return out
+
+    def assemble_reaction_diffusion_range(self, degree, alpha, gamma, row0, n_rows, qr_tria=None, qr_quad=None, beta=0.0, out=None,
+                                          algo=ALGO_AUTO):
+        """Only the contiguous outer range [row0, row0 + n_rows) (fan kernel only: LfgpuError UNSUPPORTED otherwise)."""
+        if out is None:
+            out = self.ctx.zeros(self.nnz)
+        self.ctx.check(self.ctx.L.lfgpu_assemble_reaction_diffusion_range(
+            self.ctx.h, self.mesh.h, self.h, degree, _qref(qr_tria), _qref(qr_quad), alpha.ref(), gamma.ref(), beta, out.ptr, algo,
+            int(row0), int(n_rows)))
         return out
 
     def assemble_reaction_diffusion_host(self, degree, alpha, gamma, h_node_coords, h_values, out=None, qr_tria=None, qr_quad=None,

@@ -771,6 +771,16 @@ int lfgpu_assemble_reaction_diffusion_rows(lfgpu_ctx* ctx, const lfgpu_mesh* mes
   return lfgpu::assemble_rd_impl(ctx, mesh, p, degree, qr_tria, qr_quad, alpha, gamma, active, beta, d_values, algo, d_row_list, n_rows,
                                  -1, nullptr);
 }
+
+int lfgpu_assemble_reaction_diffusion_range(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, int degree,
+                                            const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad, const lfgpu_coeff* alpha,
+                                            const lfgpu_coeff* gamma, double beta, double* d_values, int algo, int64_t row0,
+                                            int64_t n_rows) {
+  if (p == nullptr || row0 < 0 || n_rows < 0 || row0 + n_rows > p->n_outer) return LFGPU_ERR_INVALID;
+  if (n_rows == 0) return LFGPU_OK;
+  return lfgpu::assemble_rd_impl(ctx, mesh, p, degree, qr_tria, qr_quad, alpha, gamma, nullptr, beta, d_values, algo, nullptr, n_rows, row0,
+                                 nullptr);
+}
 }  // extern "C"
 
 // row0 >= 0 (with d_row_list == nullptr): only the contiguous outer range [row0, row0 + n_rows) -- fan path only.

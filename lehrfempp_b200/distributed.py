@@ -52,6 +52,19 @@ def morton_partition(node_xy, cell_nodes, world):
     return part
 
 
+def row_ranges(outer, world):
+    """Contiguous row blocks with (nearly) equal numbers of stored values: boundaries [world + 1] as a python list.
+    Block k = rows [b[k], b[k+1]).  `outer` is the row-pointer array of the pattern (any device)."""
+    n_rows = outer.numel() - 1
+    nnz = int(outer[-1].item())
+    targets = torch.tensor([nnz * k // world for k in range(1, world)], dtype=outer.dtype, device=outer.device)
+    cuts = torch.searchsorted(outer[:-1].contiguous(), targets, right=False).tolist() if world > 1 else []
+    bounds = [0] + [min(max(int(c), 0), n_rows) for c in cuts] + [n_rows]
+    for k in range(1, len(bounds)):  # monotone even for degenerate inputs
+        bounds[k] = max(bounds[k], bounds[k - 1])
+    return bounds
+
+
 class PartitionPlan:
     """Row classification and message layout of one rank (device-agnostic torch tensors)."""
 
@@ -134,8 +147,32 @@ class DistributedAssembler:
         owner (one all-to-all-v per step).  mode = "owner": the owner of a row assembles it completely, re-computing the
         few halo cells of its neighbours (the mesh is replicated at setup) -- no data-path collective at all."""
         import lehrfempp_b200 as lf
-        assert mode in ("exchange", "owner")
+        assert mode in ("exchange", "owner", "owner_rows")
         self.mode = mode
+        if mode == "owner_rows":
+            # owner-computes over contiguous ROW BLOCKS with equal numbers of stored values: no Morton plan, no lists --
+            # the rank's share is one range launch of the fastest kernel (the fan kernel with its L2 prefetch needs
+            # contiguous rows); halo cells are re-computed from the replicated geometry as in "owner"
+            self.graph = None
+            self.lf, self.ctx, self.mesh, self.pattern, self.degree, self.group = lf, ctx, mesh, pattern, degree, group
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+            dev = torch.device("cuda", torch.cuda.current_device())
+            self.dev = dev
+            ctx.synchronize()
+            n_rows = pattern.rows if pattern.major == lf.ROW_MAJOR else pattern.cols
+            outer = device_view(ctx.L.lfgpu_pattern_outer_device(pattern.h), n_rows + 1, torch.int32, dev)
+            self.bounds = row_ranges(outer, self.world)
+            self.row0, self.n_rows = self.bounds[self.rank], self.bounds[self.rank + 1] - self.bounds[self.rank]
+
+            class _P:  # the part of PartitionPlan the callers look at
+                pass
+            self.plan = _P()
+            self.plan.owned_rows = torch.arange(self.row0, self.row0 + self.n_rows, dtype=torch.int32, device=dev)
+            self.plan.interior_rows = self.plan.iface_rows = torch.zeros(0, dtype=torch.int32, device=dev)
+            self.plan.n_send = self.plan.n_recv = 0
+            self._range_ok = True
+            self.main = torch.cuda.ExternalStream(ctx.stream, device=dev)
+            return
         self.graph = None
         self.lf, self.ctx, self.mesh, self.pattern, self.degree, self.group = lf, ctx, mesh, pattern, degree, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
@@ -176,6 +213,18 @@ class DistributedAssembler:
         """One partitioned numeric pass; afterwards this rank's OWNED rows of `values` are final."""
         lf, ctx, p, L = self.lf, self.ctx, self.plan, self.ctx.L
         pat = self.pattern
+        if self.mode == "owner_rows":
+            if self._range_ok:
+                try:
+                    pat.assemble_reaction_diffusion_range(self.degree, alpha, gamma, self.row0, self.n_rows, qr_tria, qr_quad, out=values)
+                    return values
+                except lf.LfgpuError as e:
+                    if e.code != -7:  # LFGPU_ERR_UNSUPPORTED: not a fan-kernel call -> generic kernel over the same rows as a list
+                        raise
+                    self._range_ok = False
+            pat.assemble_reaction_diffusion(self.degree, alpha, gamma, qr_tria, qr_quad, out=values, algo=lf.ALGO_AUTO,
+                                            rows=self._Rows(p.owned_rows))
+            return values
         if self.mode == "owner" and self.world > 1:
             # owner-computes: one launch over the rows I own, all adjacent cells (mine or halo) contribute
             pat.assemble_reaction_diffusion(self.degree, alpha, gamma, qr_tria, qr_quad, out=values, algo=lf.ALGO_AUTO,

@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("mode,port", [("owner", 29541), ("exchange", 29542)])
+@pytest.mark.parametrize("mode,port", [("owner", 29541), ("exchange", 29542), ("owner_rows", 29543)])
 def test_distributed_assembly_two_gpus(mode, port):
     import torch
     if torch.cuda.device_count() < 2:

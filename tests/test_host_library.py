@@ -76,3 +76,22 @@ def test_default_rules_match_oracle(lib, cell_type, degree):
     else:
         # Gauss-Legendre from two independent Newton iterations: equal up to the last bit
         assert np.abs(q.points - p).max() <= 2.3e-16 and np.abs(q.weights - w).max() <= 2.3e-16
+
+
+def test_row_ranges_cover_and_balance():
+    """Row-block partition of the owner_rows multi-GPU mode: blocks cover all rows exactly once with ~equal nnz."""
+    import torch
+    from lehrfempp_b200.distributed import row_ranges
+    rng = np.random.default_rng(3)
+    lens = rng.integers(0, 12, size=10007)
+    outer = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32)
+    for world in (1, 2, 3, 8):
+        b = row_ranges(outer, world)
+        assert len(b) == world + 1 and b[0] == 0 and b[-1] == len(lens)
+        assert all(b[k] <= b[k + 1] for k in range(world))
+        nnz = [int(outer[b[k + 1]] - outer[b[k]]) for k in range(world)]
+        assert sum(nnz) == int(outer[-1])
+        assert max(nnz) - min(nnz) <= 2 * 12
+    # degenerate: fewer rows than ranks
+    b = row_ranges(torch.tensor([0, 3, 5], dtype=torch.int32), 4)
+    assert b[0] == 0 and b[-1] == 2 and all(b[k] <= b[k + 1] for k in range(4))
