@@ -134,7 +134,11 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out))
+    print_result(out)
+
+
+def print_result(obj):  # replaced in main() by a writer to the real stdout
+    print(json.dumps(obj))
 
 
 def main():
@@ -154,6 +158,18 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    # stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 (NCCL prints its version banner
+    # there) are sent to stderr for the duration of the run; emit() writes the result to the real stdout
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+    global print_result
+    print_result = emit
 
     # watchdog: a rank that is stuck (e.g. in a collective whose peer died) must not keep the node busy
     def _watchdog(limit=float(os.environ.get("LFGPU_BENCH_LIMIT_S", "420"))):
@@ -405,7 +421,7 @@ def main():
         out["cpu_baseline"] = {"value": cells / sec, "unit": "cells/s", "cores": 1, "kind": "port",
                                "sample": "same operator on TP-triangle mesh n=%d (%d cells): AssembleMatrixLocally->COO + makeSparse, "
                                          "%.2f s; host has %d cores, the reference is serial" % (ncpu, cells, sec, os.cpu_count())}
-    print(json.dumps(out))
+    print_result(out)
     teardown()
 
 
