@@ -65,6 +65,14 @@ def lib():
         L.lfo_assemble_fixed.restype = C.c_void_p
         L.lfo_assemble_fixed.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int,
                                          C.c_int, C.c_void_p]
+        L.lfo_boundary_edges.argtypes = [C.c_void_p, C.c_void_p]
+        L.lfo_assemble_boundary_test_matrix.argtypes = [C.c_void_p, C.c_void_p]
+        L.lfo_edge_matrices.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(Coeff), C.c_void_p, C.c_int]
+        L.lfo_edge_vectors.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(Coeff), C.c_void_p, C.c_int]
+        L.lfo_assemble_rd_edge.restype = C.c_void_p
+        L.lfo_assemble_rd_edge.argtypes = [C.c_void_p, C.c_int, C.POINTER(Coeff), C.POINTER(Coeff), C.POINTER(Coeff), C.c_int, C.c_void_p,
+                                           C.c_int]
+        L.lfo_assemble_edge_load.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(Coeff), C.c_void_p, C.c_void_p]
         L.lfo_fix_coo.restype = C.c_void_p
         L.lfo_fix_coo.argtypes = [C.c_int64, C.c_int64] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
         L.lfo_cm_sizes.argtypes = [C.c_void_p] + [C.POINTER(C.c_int64)] * 3
@@ -275,6 +283,49 @@ class Mesh:
         lib().lfo_cm_free(h)
         return outer, inner, vals, rhs
 
+    # ---- edge (codim-1) contributions ---------------------------------------------------------------------------
+    def boundary_edges(self):
+        f = np.zeros(self.n_edges, np.uint8)
+        _check(lib().lfo_boundary_edges(self.h, _p(f)) == 0)
+        return f
+
+    def edge_matrices(self, degree, eta, qr_degree=-1):
+        """MassEdgeMatrixProvider::Eval of every edge -> [edge][row][col]"""
+        s = degree + 1
+        out = np.zeros((self.n_edges, s, s))
+        _check(lib().lfo_edge_matrices(self.h, degree, qr_degree, C.byref(eta), _p(out), s) == 0)
+        return out.transpose(0, 2, 1).copy()
+
+    def edge_vectors(self, degree, g, qr_degree=-1):
+        s = degree + 1
+        out = np.zeros((self.n_edges, s))
+        _check(lib().lfo_edge_vectors(self.h, degree, qr_degree, C.byref(g), _p(out), s) == 0)
+        return out
+
+    def assemble_rd_edge(self, degree, alpha, gamma, eta, edge_mask=None, qr_degree=-1, csr=False):
+        """cell reaction-diffusion matrix + edge mass matrix of the flagged edges in one COO, makeSparse -> (outer, inner, values)"""
+        if edge_mask is not None:
+            edge_mask = np.ascontiguousarray(edge_mask, dtype=np.uint8)
+        h = lib().lfo_assemble_rd_edge(self.h, degree, C.byref(alpha), C.byref(gamma), C.byref(eta), qr_degree, _p(edge_mask),
+                                       1 if csr else 0)
+        _check(h)
+        r, c, nnz = C.c_int64(), C.c_int64(), C.c_int64()
+        lib().lfo_cm_sizes(h, C.byref(r), C.byref(c), C.byref(nnz))
+        outer = np.zeros(c.value + 1, np.int32)
+        inner = np.zeros(nnz.value, np.int32)
+        vals = np.zeros(nnz.value)
+        lib().lfo_cm_export(h, _p(outer), _p(inner), _p(vals))
+        lib().lfo_cm_free(h)
+        return outer, inner, vals
+
+    def assemble_edge_load(self, degree, g, edge_mask=None, qr_degree=-1, out=None):
+        if out is None:
+            out = np.zeros(self.num_dofs(degree))
+        if edge_mask is not None:
+            edge_mask = np.ascontiguousarray(edge_mask, dtype=np.uint8)
+        _check(lib().lfo_assemble_edge_load(self.h, degree, qr_degree, C.byref(g), _p(edge_mask), _p(out)) == 0)
+        return out
+
     def assemble_load(self, degree, f, qr_tria=-1, qr_quad=-1, active=None, out=None):
         n = self.num_dofs(degree)
         if out is None:
@@ -340,6 +391,12 @@ class DofHandler:
     def test_vector(self):
         out = np.zeros(self.num_dofs)
         _check(lib().lfo_assemble_test_vector(self.h, _p(out)) == 0)
+        return out
+
+    def boundary_test_matrix(self):
+        """AssembleMatrixLocally(1, dofh, BoundaryAssembler) of assemble/test/assembly_tests.cc:491-590 (dense)"""
+        out = np.zeros((self.num_dofs, self.num_dofs))
+        _check(lib().lfo_assemble_boundary_test_matrix(self.h, _p(out)) == 0)
         return out
 
 

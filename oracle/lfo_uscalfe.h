@@ -670,6 +670,101 @@ class ScalarLoadElementVectorProvider {
   std::array<PrecomputedScalarReferenceFiniteElement, 5> fe_precomp_;
 };
 
+// lib/lf/uscalfe/loc_comp_ellbvp.h:367-529 -- edge (codim-1) mass matrix, for impedance / Robin boundary terms.
+// EDGESELECTOR: const mesh::Entity& -> bool
+template <class COEFF, class EDGESELECTOR>
+class MassEdgeMatrixProvider {
+ public:
+  using ElemMat = Mat;
+  MassEdgeMatrixProvider(std::shared_ptr<const UniformScalarFESpace> fe_space, COEFF gamma, EDGESELECTOR edge_selector)
+      : gamma_(std::move(gamma)), edge_sel_(std::move(edge_selector)) {
+    auto fe = fe_space->ShapeFunctionLayout(RefEl::kSegment());
+    LFO_VERIFY(fe != nullptr, "No shape functions specified for edges");
+    fe_precomp_ = PrecomputedScalarReferenceFiniteElement(fe, quad::make_QuadRule(RefEl::kSegment(), 2 * fe->Degree()));
+  }
+  MassEdgeMatrixProvider(std::shared_ptr<const UniformScalarFESpace> fe_space, COEFF gamma, quad::QuadRule quadrule,
+                         EDGESELECTOR edge_selector)
+      : gamma_(std::move(gamma)), edge_sel_(std::move(edge_selector)) {
+    auto fe = fe_space->ShapeFunctionLayout(RefEl::kSegment());
+    LFO_VERIFY(fe != nullptr, "No shape functions specified for edges");
+    LFO_VERIFY(quadrule.RefElem() == RefEl::kSegment(), "Quadrature rule not meant for EDGE entities!");
+    fe_precomp_ = PrecomputedScalarReferenceFiniteElement(fe, std::move(quadrule));
+  }
+  virtual ~MassEdgeMatrixProvider() = default;
+  bool isActive(const mesh::Entity& edge) {
+    LFO_VERIFY(edge.RefElem() == RefEl::kSegment(), "Wrong type for an edge");
+    return edge_sel_(edge);
+  }
+  // :491-529
+  ElemMat Eval(const mesh::Entity& edge) {
+    LFO_VERIFY(edge.RefElem() == RefEl::kSegment(), "Edge must be of segment type");
+    const geometry::Geometry* geo_ptr = edge.Geometry();
+    LFO_VERIFY(geo_ptr != nullptr, "Invalid geometry!");
+    const Mat determinants(geo_ptr->IntegrationElement(fe_precomp_.Qr().Points()));
+    const long nsf = fe_precomp_.NumRefShapeFunctions();
+    ElemMat mat(nsf, nsf);
+    mat.setZero();
+    auto gammaval = gamma_(edge, fe_precomp_.Qr().Points());
+    const Mat& phi = fe_precomp_.PrecompReferenceShapeFunctions();
+    for (long k = 0; k < determinants.size(); ++k) {
+      const double w = (fe_precomp_.Qr().Weights()[k] * determinants[k]) * gammaval[k];
+      for (long b = 0; b < nsf; ++b)
+        for (long a = 0; a < nsf; ++a) mat(a, b) += (phi(a, k) * phi(b, k)) * w;
+    }
+    return mat;
+  }
+
+ private:
+  COEFF gamma_;
+  EDGESELECTOR edge_sel_;
+  PrecomputedScalarReferenceFiniteElement fe_precomp_;
+};
+
+// lib/lf/uscalfe/loc_comp_ellbvp.h:784-921 -- edge load vector (Neumann / impedance data)
+template <class FUNCTOR, class EDGESELECTOR>
+class ScalarLoadEdgeVectorProvider {
+ public:
+  using ElemVec = Mat;
+  ScalarLoadEdgeVectorProvider(std::shared_ptr<const UniformScalarFESpace> fe_space, FUNCTOR g, EDGESELECTOR edge_sel)
+      : g_(std::move(g)), edge_sel_(std::move(edge_sel)) {
+    auto fe = fe_space->ShapeFunctionLayout(RefEl::kSegment());
+    LFO_VERIFY(fe != nullptr, "No shape functions specified for edges");
+    pfe_ = PrecomputedScalarReferenceFiniteElement(fe, quad::make_QuadRule(RefEl::kSegment(), 2 * fe->Degree()));
+  }
+  ScalarLoadEdgeVectorProvider(std::shared_ptr<const UniformScalarFESpace> fe_space, FUNCTOR g, quad::QuadRule quadrule,
+                               EDGESELECTOR edge_sel)
+      : g_(std::move(g)), edge_sel_(std::move(edge_sel)) {
+    auto fe = fe_space->ShapeFunctionLayout(RefEl::kSegment());
+    LFO_VERIFY(fe != nullptr, "No shape functions specified for edges");
+    LFO_VERIFY(quadrule.RefElem() == RefEl::kSegment(), "Quadrature rule not meant for EDGE entities!");
+    pfe_ = PrecomputedScalarReferenceFiniteElement(fe, std::move(quadrule));
+  }
+  virtual ~ScalarLoadEdgeVectorProvider() = default;
+  virtual bool isActive(const mesh::Entity& edge) { return edge_sel_(edge); }
+  // :886-921
+  ElemVec Eval(const mesh::Entity& edge) {
+    LFO_VERIFY(edge.RefElem() == RefEl::kSegment(), "Edge must be of segment type");
+    const geometry::Geometry* geo_ptr = edge.Geometry();
+    LFO_VERIFY(geo_ptr != nullptr, "Invalid geometry!");
+    const Mat determinants(geo_ptr->IntegrationElement(pfe_.Qr().Points()));
+    const long nsf = pfe_.NumRefShapeFunctions();
+    ElemVec vec(nsf, 1);
+    vec.setZero();
+    auto g_vals = g_(edge, pfe_.Qr().Points());
+    const Mat& phi = pfe_.PrecompReferenceShapeFunctions();
+    for (long k = 0; k < determinants.size(); ++k) {
+      const double w = (pfe_.Qr().Weights()[k] * determinants[k]) * g_vals[k];
+      for (long a = 0; a < nsf; ++a) vec[a] += phi(a, k) * w;
+    }
+    return vec;
+  }
+
+ private:
+  FUNCTOR g_;
+  EDGESELECTOR edge_sel_;
+  PrecomputedScalarReferenceFiniteElement pfe_;
+};
+
 // lib/lf/fe/fe_tools.h:198-258 (NodalValuesToDofs is the identity for the Lagrange elements here)
 template <class MF>
 std::vector<double> NodalProjection(const UniformScalarFESpace& fe_space, const MF& u) {

@@ -493,6 +493,148 @@ void* lfo_fix_coo(std::int64_t n, std::int64_t n_trip, const std::int32_t* rows,
   LFO_CATCH(nullptr)
 }
 
+// ---- edge (codim-1) contributions: SURVEY section 8f row 2 -----------------------------------------------------------
+namespace {
+// edges with exactly one adjacent cell (mesh/utils: flagEntitiesOnBoundary(mesh, 1) / CountNumSuperEntities(mesh, 1, 1))
+std::vector<std::uint8_t> boundary_edge_flags(const mesh::Mesh& m) {
+  std::vector<unsigned> cnt(m.NumEntities(1), 0);
+  for (const mesh::Entity* cell : m.Entities(0))
+    for (const mesh::Entity* e : cell->SubEntities(1)) cnt[m.Index(*e)]++;
+  std::vector<std::uint8_t> f(cnt.size());
+  for (std::size_t i = 0; i < cnt.size(); ++i) f[i] = cnt[i] == 1 ? 1 : 0;
+  return f;
+}
+struct EdgeMask {
+  const std::uint8_t* mask;
+  const mesh::Mesh* mesh;
+  bool operator()(const mesh::Entity& e) const { return mask == nullptr || mask[mesh->Index(e)] != 0; }
+};
+quad::QuadRule segment_rule(int degree, int qr_degree) {
+  return quad::make_QuadRule(RefEl::kSegment(), qr_degree >= 0 ? static_cast<unsigned>(qr_degree) : 2U * degree);
+}
+// assemble/test/assembly_tests.cc:491-523 (BoundaryAssembler): boundary edges get idx * [[1, -1], [-1, 1]]
+struct BoundaryAssembler {
+  const mesh::Mesh& mesh_;
+  std::vector<std::uint8_t> bd_;
+  explicit BoundaryAssembler(const mesh::Mesh& m) : mesh_(m), bd_(boundary_edge_flags(m)) {}
+  bool isActive(const mesh::Entity& edge) { return bd_[mesh_.Index(edge)] != 0; }
+  Mat Eval(const mesh::Entity& edge) {
+    const double idx = mesh_.Index(edge);
+    Mat m(2, 2);
+    m(0, 0) = idx;
+    m(1, 1) = idx;
+    m(0, 1) = -idx;
+    m(1, 0) = -idx;
+    return m;
+  }
+};
+}  // namespace
+
+int lfo_boundary_edges(void* mesh_h, std::uint8_t* flags) {
+  LFO_TRY
+  const auto f = boundary_edge_flags(*static_cast<MeshH*>(mesh_h)->mesh);
+  std::copy(f.begin(), f.end(), flags);
+  return 0;
+  LFO_CATCH(-1)
+}
+// assembly_tests.cc:525-590: AssembleMatrixLocally(1, dofh, BoundaryAssembler) -> dense N x N (row-major)
+int lfo_assemble_boundary_test_matrix(void* dofh_h, double* dense_out) {
+  LFO_TRY
+  auto* d = static_cast<DofH*>(dofh_h);
+  const long N = d->dofh->NumDofs();
+  assemble::COOMatrix coo(N, N);
+  BoundaryAssembler a(*d->mesh);
+  assemble::AssembleMatrixLocally(1, *d->dofh, *d->dofh, a, coo);
+  const auto cm = coo.makeSparse();
+  for (long i = 0; i < N * N; ++i) dense_out[i] = 0.0;
+  for (long c = 0; c < cm.cols; ++c)
+    for (int k = cm.outer[c]; k < cm.outer[c + 1]; ++k) dense_out[cm.inner[k] * N + c] = cm.values[k];
+  return 0;
+  LFO_CATCH(-1)
+}
+// MassEdgeMatrixProvider::Eval / ScalarLoadEdgeVectorProvider::Eval for every edge: out[edge][b * stride + a] (column-major
+// blocks) resp. out[edge][a]; qr_degree < 0 = default rule of degree 2p
+int lfo_edge_matrices(void* mesh_h, int degree, int qr_degree, const lfo_coeff* eta, double* out, int stride) {
+  LFO_TRY
+  auto* mh = static_cast<MeshH*>(mesh_h);
+  auto fes = std::make_shared<uscalfe::UniformScalarFESpace>(mh->mesh, degree);
+  uscalfe::MassEdgeMatrixProvider<ScalarMF, EdgeMask> prov(fes, make_scalar_mf(eta, mh->mesh.get()), segment_rule(degree, qr_degree),
+                                                          EdgeMask{nullptr, mh->mesh.get()});
+  std::size_t e = 0;
+  for (const mesh::Entity* edge : mh->mesh->Entities(1)) {
+    const Mat m = prov.Eval(*edge);
+    for (long j = 0; j < m.cols(); ++j)
+      for (long i = 0; i < m.rows(); ++i) out[e * stride * stride + j * stride + i] = m(i, j);
+    ++e;
+  }
+  return 0;
+  LFO_CATCH(-1)
+}
+int lfo_edge_vectors(void* mesh_h, int degree, int qr_degree, const lfo_coeff* g, double* out, int stride) {
+  LFO_TRY
+  auto* mh = static_cast<MeshH*>(mesh_h);
+  auto fes = std::make_shared<uscalfe::UniformScalarFESpace>(mh->mesh, degree);
+  uscalfe::ScalarLoadEdgeVectorProvider<ScalarMF, EdgeMask> prov(fes, make_scalar_mf(g, mh->mesh.get()), segment_rule(degree, qr_degree),
+                                                                EdgeMask{nullptr, mh->mesh.get()});
+  std::size_t e = 0;
+  for (const mesh::Entity* edge : mh->mesh->Entities(1)) {
+    const Mat v = prov.Eval(*edge);
+    for (long i = 0; i < v.size(); ++i) out[e * stride + i] = v[i];
+    ++e;
+  }
+  return 0;
+  LFO_CATCH(-1)
+}
+// The Galerkin matrix of a second-order BVP with impedance part (uscalfe/test/sec_ord_ell_bvp.h:147-215):
+//   AssembleMatrixLocally(0, ..., ReactionDiffusionElementMatrixProvider(alpha, gamma), A);
+//   AssembleMatrixLocally(1, ..., MassEdgeMatrixProvider(eta, edge_sel), A);   -> A.makeSparse()
+// edge_mask: uint8 per edge (NULL = all edges), transpose as in lfo_assemble_rd.
+void* lfo_assemble_rd_edge(void* mesh_h, int degree, const lfo_coeff* alpha, const lfo_coeff* gamma, const lfo_coeff* eta,
+                           int qr_degree, const std::uint8_t* edge_mask, int transpose) {
+  LFO_TRY
+  auto* mh = static_cast<MeshH*>(mesh_h);
+  auto fes = std::make_shared<uscalfe::UniformScalarFESpace>(mh->mesh, degree);
+  const auto& dofh = fes->LocGlobMap();
+  assemble::COOMatrix coo(dofh.NumDofs(), dofh.NumDofs());
+  TransposedCOO tcoo{coo};
+  ScalarMF g = make_scalar_mf(gamma, mh->mesh.get());
+  auto cells = [&](auto& prov) {
+    if (transpose) {
+      assemble::AssembleMatrixLocally(0, dofh, dofh, prov, tcoo);
+    } else {
+      assemble::AssembleMatrixLocally(0, dofh, dofh, prov, coo);
+    }
+  };
+  if (is_tensor(alpha)) {
+    uscalfe::ReactionDiffusionElementMatrixProvider<TensorMF, ScalarMF> prov(fes, make_tensor_mf(alpha), g);
+    cells(prov);
+  } else {
+    uscalfe::ReactionDiffusionElementMatrixProvider<ScalarMF, ScalarMF> prov(fes, make_scalar_mf(alpha, mh->mesh.get()), g);
+    cells(prov);
+  }
+  uscalfe::MassEdgeMatrixProvider<ScalarMF, EdgeMask> eprov(fes, make_scalar_mf(eta, mh->mesh.get()), segment_rule(degree, qr_degree),
+                                                           EdgeMask{edge_mask, mh->mesh.get()});
+  if (transpose) {
+    assemble::AssembleMatrixLocally(1, dofh, dofh, eprov, tcoo);
+  } else {
+    assemble::AssembleMatrixLocally(1, dofh, dofh, eprov, coo);
+  }
+  return new assemble::CompressedMatrix(coo.makeSparse());
+  LFO_CATCH(nullptr)
+}
+// AssembleVectorLocally(1, dofh, ScalarLoadEdgeVectorProvider(g, edge_sel), out): accumulates into out (length N)
+int lfo_assemble_edge_load(void* mesh_h, int degree, int qr_degree, const lfo_coeff* g, const std::uint8_t* edge_mask, double* out) {
+  LFO_TRY
+  auto* mh = static_cast<MeshH*>(mesh_h);
+  auto fes = std::make_shared<uscalfe::UniformScalarFESpace>(mh->mesh, degree);
+  uscalfe::ScalarLoadEdgeVectorProvider<ScalarMF, EdgeMask> prov(fes, make_scalar_mf(g, mh->mesh.get()), segment_rule(degree, qr_degree),
+                                                                EdgeMask{edge_mask, mh->mesh.get()});
+  std::span<double> v(out, fes->LocGlobMap().NumDofs());
+  assemble::AssembleVectorLocally(1, fes->LocGlobMap(), prov, v);
+  return 0;
+  LFO_CATCH(-1)
+}
+
 void lfo_cm_sizes(void* h, std::int64_t* rows, std::int64_t* cols, std::int64_t* nnz) {
   auto* cm = static_cast<assemble::CompressedMatrix*>(h);
   *rows = cm->rows;
