@@ -200,6 +200,25 @@ int lfgpu_assemble_reaction_diffusion_host(lfgpu_ctx* ctx, lfgpu_mesh* mesh, con
                                            const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad, const lfgpu_coeff* alpha,
                                            const lfgpu_coeff* gamma, const double* h_node_coords, double* d_values,
                                            double* h_values, int algo, int n_blocks);
+/* ---- edge (codim-1) contributions (second "next" row) ------------------------------------------- */
+/* AssembleMatrixLocally(1, dofh, dofh, MassEdgeMatrixProvider(fe_space, gamma[, rule], edge_selector), A)
+ * (uscalfe/loc_comp_ellbvp.h:367-529, assembler.h:114-186 with codim 1): for every active edge the mass matrix
+ * sum_k w_k |e| gamma(x_k) phi_a phi_b of FeLagrangeO<degree>Segment is ADDED to d_values (the reference accumulates
+ * into the COO matrix that already holds the cell terms; the entries are part of the pattern of the symbolic pass).
+ * dofmap: from lfgpu_dofmap_lagrange(degree) (edge dofs must be known).  qr_segment: points[n] on [0,1], NULL = the
+ * provider's default make_QuadRule(kSegment, 2*degree).  gamma: CONST, PER_CELL (one value per EDGE) or PER_QP (per
+ * edge and point).  active_edges: device uint8 [n_edges] = the EDGESELECTOR, NULL = all edges.                      */
+int lfgpu_assemble_edge_mass(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const lfgpu_dofmap* dofmap, const lfgpu_pattern* pattern, int degree,
+                             const lfgpu_quad* qr_segment, const lfgpu_coeff* gamma, const uint8_t* active_edges, double* d_values);
+/* AssembleVectorLocally(1, dofh, ScalarLoadEdgeVectorProvider(fe_space, g[, rule], edge_selector), vec)
+ * (uscalfe/loc_comp_ellbvp.h:784-921): accumulates into d_vec [n_dofs].                                             */
+int lfgpu_assemble_edge_load(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const lfgpu_dofmap* dofmap, int degree, const lfgpu_quad* qr_segment,
+                             const lfgpu_coeff* g, const uint8_t* active_edges, double* d_vec);
+/* global coordinates of every edge's quadrature points, SegmentO1::Global (geometry/segment_o1.cc:9-11):
+ * d_out device [n_edges][nq_stride][2] -- lets a host tabulate MeshFunctionGlobal lambdas into PER_QP edge tables    */
+int lfgpu_edge_qp_coords(lfgpu_ctx* ctx, lfgpu_mesh* mesh, int degree, const lfgpu_quad* qr_segment, int nq_stride, double* d_out);
+/* edges with exactly one adjacent cell (mesh/utils flagEntitiesOnBoundary(mesh, 1)): d_flags device uint8 [n_edges]  */
+int lfgpu_mesh_boundary_edges(lfgpu_ctx* ctx, lfgpu_mesh* mesh, uint8_t* d_flags);
 /* ---- essential boundary conditions (first "next" row) ------------------------------------------- */
 /* lf::assemble::FixFlaggedSolutionComponents (assemble/fix_dof.h:86-138) on the compressed matrix: with xhat = the
  * prescribed values on the fixed dofs and 0 elsewhere,  rhs -= A * xhat;  rhs[fixed] = xhat;  every entry in a fixed row

@@ -104,6 +104,10 @@ def _lib():
         "lfgpu_assemble_reaction_diffusion_range": (i32, [vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), C.POINTER(_CCoeff),
                                                           C.POINTER(_CCoeff), dbl, vp, i32, i64, i64]),
         "lfgpu_assemble_load": (i32, [vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), C.POINTER(_CCoeff), vp, dbl, vp, i32]),
+        "lfgpu_assemble_edge_mass": (i32, [vp, vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CCoeff), vp, vp]),
+        "lfgpu_assemble_edge_load": (i32, [vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CCoeff), vp, vp]),
+        "lfgpu_edge_qp_coords": (i32, [vp, vp, i32, C.POINTER(_CQuad), i32, vp]),
+        "lfgpu_mesh_boundary_edges": (i32, [vp, vp, vp]),
         "lfgpu_fix_flagged_solution_components": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "lfgpu_fix_flagged_solution_comp_alt": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "lfgpu_assemble_reaction_diffusion_host": (i32, [vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), C.POINTER(_CCoeff),
@@ -139,7 +143,8 @@ class QuadRule:
     def __init__(self, points, weights):
         self.points = np.ascontiguousarray(points, dtype=np.float64)
         self.weights = np.ascontiguousarray(weights, dtype=np.float64)
-        assert self.points.shape == (2, self.weights.size)
+        n = self.weights.size
+        assert self.points.shape in ((2, n), (1, n), (n,))  # cells: [2][n]; segment rules: [n]
         self._c = _CQuad(self.weights.size, self.points.ctypes.data, self.weights.ctypes.data)
 
     def ref(self):
@@ -156,7 +161,7 @@ def default_quad_rule(cell_type, degree):
     n = L.lfgpu_default_quad_rule(cell_type, degree, 0, None, None)
     if n < 0:
         raise LfgpuError(n, "no such rule")
-    pts = np.zeros((2, n))
+    pts = np.zeros(n) if cell_type == 2 else np.zeros((2, n))  # 2 = segment (RefEl::Id)
     w = np.zeros(n)
     L.lfgpu_default_quad_rule(cell_type, degree, n, _p(pts), _p(w))
     return QuadRule(pts, w)
@@ -395,6 +400,24 @@ class Mesh:
                                                       _p(out["cell_coords"]), _p(ce), _p(co), _p(en), _p(out["node_coords"])))
         return out
 
+    def boundary_edges(self):
+        """DeviceArray(uint8)[n_edges]: edges with exactly one adjacent cell (flagEntitiesOnBoundary(mesh, 1))."""
+        if self.n_edges == 0:
+            self.build_topology()  # edges discovered from the cells (hybrid2d/mesh.cc:378-404)
+        out = self.ctx.empty(max(self.n_edges, 1), np.uint8)
+        self.ctx.check(self.ctx.L.lfgpu_mesh_boundary_edges(self.ctx.h, self.h, out.ptr))
+        return out
+
+    def edge_qp_coords(self, degree, qr_segment=None, nq_stride=None):
+        """[n_edges][nq_stride][2] global coordinates of the edge quadrature points (host array)."""
+        nq = qr_segment.weights.size if qr_segment is not None else degree + 1
+        nq_stride = nq_stride or nq
+        if self.n_edges == 0:
+            self.build_topology()
+        out = self.ctx.empty(max(self.n_edges, 1) * nq_stride * 2)
+        self.ctx.check(self.ctx.L.lfgpu_edge_qp_coords(self.ctx.h, self.h, degree, _qref(qr_segment), nq_stride, out.ptr))
+        return out.to_host()[: self.n_edges * nq_stride * 2].reshape(self.n_edges, nq_stride, 2)
+
     def update_node_coords(self, xy):
         xy = np.ascontiguousarray(xy, dtype=np.float64)
         assert xy.shape == (self.n_nodes, 2)
@@ -455,6 +478,14 @@ class DofMap:
         self.ctx.check(self.ctx.L.lfgpu_symbolic(self.ctx.h, self.mesh.h, self.h, trial.h, major, C.byref(h)))
         return Pattern(self.mesh, h, major)
 
+    def assemble_edge_load(self, degree, g, qr_segment=None, active_edges=None, out=None):
+        """AssembleVectorLocally(1, dofh, ScalarLoadEdgeVectorProvider(fe_space, g, edge_sel), vec): accumulates into out."""
+        if out is None:
+            out = self.ctx.zeros(self.num_dofs)
+        self.ctx.check(self.ctx.L.lfgpu_assemble_edge_load(self.ctx.h, self.mesh.h, self.h, degree, _qref(qr_segment), g.ref(),
+                                                           active_edges.ptr if active_edges is not None else None, out.ptr))
+        return out
+
     def assemble_load(self, degree, f, qr_tria=None, qr_quad=None, active=None, beta=0.0, out=None):
         """AssembleVectorLocally(0, dofh, ScalarLoadElementVectorProvider(fe_space, f), vec)."""
         if out is None:
@@ -499,6 +530,12 @@ class Pattern:
             active.ptr if active is not None else None, beta, out.ptr, algo, rows.ptr if rows is not None else None,
             rows.n if rows is not None else 0))
         return out
+
+    def assemble_edge_mass(self, dofmap, degree, gamma, values, qr_segment=None, active_edges=None):
+        """AssembleMatrixLocally(1, dofh, dofh, MassEdgeMatrixProvider(fe_space, gamma, edge_sel), A): ADDS to `values`."""
+        self.ctx.check(self.ctx.L.lfgpu_assemble_edge_mass(self.ctx.h, self.mesh.h, dofmap.h, self.h, degree, _qref(qr_segment), gamma.ref(),
+                                                           active_edges.ptr if active_edges is not None else None, values.ptr))
+        return values
 
     def assemble_reaction_diffusion_range(self, degree, alpha, gamma, row0, n_rows, qr_tria=None, qr_quad=None, beta=0.0, out=None,
                                           algo=ALGO_AUTO):

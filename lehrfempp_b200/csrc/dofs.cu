@@ -169,6 +169,9 @@ int lfgpu_dofmap_uniform(lfgpu_ctx* ctx, lfgpu_mesh* mesh, int n_pt, int n_seg, 
   d->n_dofs = n_dofs;
   d->stride = stride;
   d->max_ldof = stride;
+  d->n_pt = n_pt;
+  d->n_seg = n_seg;
+  d->n_nodes = mesh->n_nodes;
   int64_t *counts = nullptr, *offsets = nullptr;
   void* tmp = nullptr;
   cudaError_t e = cudaMalloc(&d->cell_dofs, sizeof(int32_t) * n * stride);

@@ -149,6 +149,14 @@ int default_quad_rule(int cell_type, int degree, int capacity, double* points, d
     }
     return n * n;
   }
+  if (cell_type == 2) {  // segment: make_quad_rule.cc:22-27
+    const int n = degree / 2 + 1;
+    if (points != nullptr && weights != nullptr) {
+      if (n > capacity || n > 64) return LFGPU_ERR_INVALID;
+      gauss_legendre_01(n, points, weights);
+    }
+    return n;
+  }
   return LFGPU_ERR_INVALID;
 }
 
@@ -210,6 +218,40 @@ int build_fe_table(int degree, int cell_type, const lfgpu_quad* qr, FeTable* out
     }
   }
   return 0;
+}
+
+// FeLagrangeO{1,2,3}Segment (uscalfe/lagr_fe.h:243-305, 451-528, 839-931) tabulated at a rule on [0,1]: local shape
+// functions 0, 1 belong to the endpoints, 2.. to the interior nodes in ascending position.  qr: points[n] (only row 0 is
+// read), NULL = make_QuadRule(kSegment, 2 * degree) = Gauss-Legendre with degree + 1 points (make_quad_rule.cc:22-27)
+int build_segment_table(int degree, const lfgpu_quad* qr, SegTable* out, std::string* err) {
+  if (degree < 1 || degree > 3) {
+    if (err) *err = "degree must be 1, 2 or 3";
+    return LFGPU_ERR_INVALID;
+  }
+  std::memset(out, 0, sizeof(SegTable));
+  const int p = degree;
+  out->nsf = p + 1;
+  if (qr != nullptr) {
+    if (qr->n < 1 || qr->n > kMaxSegNq || qr->points == nullptr || qr->weights == nullptr) {
+      if (err) *err = "segment quadrature rule must have 1.." + std::to_string(kMaxSegNq) + " points";
+      return LFGPU_ERR_INVALID;
+    }
+    out->nq = qr->n;
+    std::memcpy(out->x, qr->points, sizeof(double) * qr->n);
+    std::memcpy(out->w, qr->weights, sizeof(double) * qr->n);
+  } else {
+    out->nq = (2 * p) / 2 + 1;
+    gauss_legendre_01(out->nq, out->x, out->w);
+  }
+  for (int a = 0; a <= p; ++a) {
+    const int m = a == 0 ? 0 : (a == 1 ? p : a - 1);  // lattice node of local shape function a
+    for (int k = 0; k < out->nq; ++k) {
+      double f, df;
+      lagrange_1d(p, m, out->x[k], &f, &df);
+      out->phi[a * kMaxSegNq + k] = f;
+    }
+  }
+  return LFGPU_OK;
 }
 
 void build_fe_tensors(const FeTable& t, FeTensors* out) {

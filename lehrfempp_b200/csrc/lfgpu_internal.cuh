@@ -61,6 +61,10 @@ struct lfgpu_dofmap {
   int32_t* cell_dofs = nullptr;  // [n_cells][stride], -1 padded (int32: the compressed matrix uses int32 indices)
   uint8_t* n_ldof = nullptr;     // [n_cells]
   int max_ldof = 0;
+  // uniform layouts built on the device remember their per-entity counts (dofs of node v: v * n_pt + j; interior dofs of
+  // edge e: n_nodes * n_pt + e * n_seg + j); -1 for uploaded tables, whose edge dofs are unknown
+  int n_pt = -1, n_seg = -1;
+  int64_t n_nodes = 0;
 };
 
 struct lfgpu_pattern {
@@ -160,11 +164,24 @@ struct FeTensors {
   double l[kMaxNsf];
 };
 
+// FeLagrangeO{1,2,3}Segment at the points of a rule on [0,1] (edges.cu); small enough to travel as a kernel argument
+constexpr int kMaxSegNq = 16;
+struct SegTable {
+  int nsf = 0, nq = 0;
+  double w[kMaxSegNq];
+  double x[kMaxSegNq];
+  double phi[4 * kMaxSegNq];  // phi[a * kMaxSegNq + k]
+};
+int build_segment_table(int degree, const lfgpu_quad* qr, SegTable* out, std::string* err);
+
 int nsf_of(int degree, int cell_type);
 // returns 0 or a negative status; `qr` may be null (default rule 2*degree)
 int build_fe_table(int degree, int cell_type, const lfgpu_quad* qr, FeTable* out, std::string* err);
 void build_fe_tensors(const FeTable& t, FeTensors* out);
 int default_quad_rule(int cell_type, int degree, int capacity, double* points, double* weights);
+
+// edges numbered? (mesh.cu; lazy for the structured generators)
+int ensure_topology(lfgpu_ctx* ctx, lfgpu_mesh* m);
 
 // P1 vertex-fan fast path (assemble_p1.cu)
 int p1_fan_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p);
