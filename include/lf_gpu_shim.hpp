@@ -474,6 +474,130 @@ void AssembleVectorLocally(unsigned codim, const DOFH& dof_handler, ScalarLoadEl
   ctx.check(lfgpu_ctx_synchronize(ctx.get()), "lfgpu_ctx_synchronize");
 }
 
+// ---- edge (codim-1) providers ------------------------------------------------------------------------------------------------
+// lf::uscalfe::MassEdgeMatrixProvider<SCALAR, COEFF, EDGESELECTOR> (loc_comp_ellbvp.h:367-447) and
+// lf::uscalfe::ScalarLoadEdgeVectorProvider<SCALAR, FUNCTOR, EDGESELECTOR> (:784-850): same constructor shape
+// (fe_space, coefficient, edge_selector); the selector is called on the host for every edge, exactly like isActive().
+struct PredicateTrue {
+  template <class... T>
+  bool operator()(T&&...) const { return true; }
+};
+template <class SCALAR, class COEFF, class EDGESELECTOR = PredicateTrue>
+class MassEdgeMatrixProvider {
+ public:
+  static_assert(std::is_same_v<SCALAR, double>, "the GPU path computes in double");
+  template <class FE_SPACE>
+  MassEdgeMatrixProvider(std::shared_ptr<const FE_SPACE> fe_space, COEFF gamma, EDGESELECTOR edge_selector = EDGESELECTOR{})
+      : gamma_(std::move(gamma)), edge_sel_(std::move(edge_selector)), degree_(fe_space->Degree()) {}
+  template <class EDGE>
+  bool isActive(const EDGE& edge) { return edge_sel_(edge); }
+  [[nodiscard]] const COEFF& Coeff() const { return gamma_; }
+  [[nodiscard]] int Degree() const { return degree_; }
+
+ private:
+  COEFF gamma_;
+  EDGESELECTOR edge_sel_;
+  int degree_;
+};
+template <class SCALAR, class FUNCTOR, class EDGESELECTOR = PredicateTrue>
+class ScalarLoadEdgeVectorProvider {
+ public:
+  static_assert(std::is_same_v<SCALAR, double>, "the GPU path computes in double");
+  template <class FE_SPACE>
+  ScalarLoadEdgeVectorProvider(std::shared_ptr<const FE_SPACE> fe_space, FUNCTOR g, EDGESELECTOR edge_sel = EDGESELECTOR{})
+      : g_(std::move(g)), edge_sel_(std::move(edge_sel)), degree_(fe_space->Degree()) {}
+  template <class EDGE>
+  bool isActive(const EDGE& edge) { return edge_sel_(edge); }
+  [[nodiscard]] const FUNCTOR& Coeff() const { return g_; }
+  [[nodiscard]] int Degree() const { return degree_; }
+
+ private:
+  FUNCTOR g_;
+  EDGESELECTOR edge_sel_;
+  int degree_;
+};
+
+namespace detail {
+// the active edges of a provider as flat arrays + the coefficient tabulated at their quadrature points
+struct SegmentList {
+  std::vector<double> xy;          // [n][4]
+  std::vector<std::int32_t> dofs;  // [n][degree + 1]
+  std::int64_t n = 0;
+  void *d_xy = nullptr, *d_dofs = nullptr;
+  lfgpu_ctx* ctx = nullptr;
+  ~SegmentList() {
+    if (d_xy) lfgpu_free(ctx, d_xy);
+    if (d_dofs) lfgpu_free(ctx, d_dofs);
+  }
+};
+template <class A, class DOFH, class PROVIDER>
+void collect_segments(Context& ctx, const DOFH& dofh, PROVIDER& prov, SegmentList& s, DeviceCoeff& dc) {
+  const auto& mesh = A::mesh(dofh);
+  const int nsf = prov.Degree() + 1;
+  for (const auto* edge : A::entities(mesh, 1)) {
+    if (!prov.isActive(*edge)) continue;
+    if (A::num_local_dofs(dofh, *edge) != nsf) throw Error(LFGPU_ERR_INVALID, "edge dofs do not match the Lagrange degree of the provider");
+    for (int k = 0; k < 2; ++k)
+      for (int d = 0; d < 2; ++d) s.xy.push_back(A::corner(*edge, k, d));
+    for (const auto g : A::global_dof_indices(dofh, *edge)) s.dofs.push_back(static_cast<std::int32_t>(g));
+    ++s.n;
+  }
+  s.ctx = ctx.get();
+  if (s.n == 0) return;
+  ctx.check(lfgpu_malloc(ctx.get(), 8 * static_cast<std::int64_t>(s.xy.size()), &s.d_xy), "lfgpu_malloc");
+  ctx.check(lfgpu_malloc(ctx.get(), 4 * static_cast<std::int64_t>(s.dofs.size()), &s.d_dofs), "lfgpu_malloc");
+  ctx.check(lfgpu_memcpy_h2d(ctx.get(), s.d_xy, s.xy.data(), 8 * static_cast<std::int64_t>(s.xy.size())), "lfgpu_memcpy_h2d");
+  ctx.check(lfgpu_memcpy_h2d(ctx.get(), s.d_dofs, s.dofs.data(), 4 * static_cast<std::int64_t>(s.dofs.size())), "lfgpu_memcpy_h2d");
+  // coefficient at the quadrature points of the default rule make_QuadRule(kSegment, 2p): SegmentO1::Global
+  using MF = std::decay_t<decltype(prov.Coeff())>;
+  std::vector<double> qxy;
+  int stride = 0;
+  if (CoeffTraits<MF>::needs_points) {
+    double pts[16], w[16];
+    const int nq = lfgpu_default_quad_rule(2, 2 * prov.Degree(), 16, pts, w);
+    if (nq < 0) throw Error(nq, "no default segment rule");
+    stride = nq;
+    qxy.resize(static_cast<std::size_t>(s.n) * nq * 2);
+    for (std::int64_t e = 0; e < s.n; ++e)
+      for (int k = 0; k < nq; ++k)
+        for (int d = 0; d < 2; ++d) qxy[(e * nq + k) * 2 + d] = s.xy[4 * e + 2 + d] * pts[k] + s.xy[4 * e + d] * (1 - pts[k]);
+  }
+  to_device(ctx, CoeffTraits<MF>::describe(prov.Coeff(), qxy.data(), s.n, stride), dc);
+}
+}  // namespace detail
+
+// AssembleMatrixLocally(1, dofh, dofh, MassEdgeMatrixProvider, A): adds to the matrix that holds the cell terms
+template <class A, class DOFH, class COEFF, class SEL>
+void AssembleMatrixLocally(unsigned codim, const DOFH& dof_handler_trial, const DOFH& dof_handler_test,
+                           MassEdgeMatrixProvider<double, COEFF, SEL>& emp, CsrMatrix& matrix) {
+  if (codim != 1) throw Error(LFGPU_ERR_UNSUPPORTED, "MassEdgeMatrixProvider assembles edge (codim 1) contributions");
+  if (&dof_handler_trial != &dof_handler_test) throw Error(LFGPU_ERR_UNSUPPORTED, "edge mass terms need trial space == test space");
+  Context& ctx = matrix.ctx();
+  matrix.template Prepare<A>(dof_handler_trial, dof_handler_test);
+  detail::SegmentList s;
+  detail::DeviceCoeff dc;
+  detail::collect_segments<A>(ctx, dof_handler_test, emp, s, dc);
+  if (s.n == 0) return;
+  ctx.check(lfgpu_assemble_segment_mass(ctx.get(), matrix.pattern(), emp.Degree(), nullptr, s.n, static_cast<const double*>(s.d_xy),
+                                        static_cast<const std::int32_t*>(s.d_dofs), &dc.c, matrix.device_values()),
+            "lfgpu_assemble_segment_mass");
+  matrix.empty_ = false;
+}
+// AssembleVectorLocally(1, dofh, ScalarLoadEdgeVectorProvider, vec)
+template <class A, class DOFH, class F, class SEL>
+void AssembleVectorLocally(unsigned codim, const DOFH& dof_handler, ScalarLoadEdgeVectorProvider<double, F, SEL>& evp, Vector& v) {
+  if (codim != 1) throw Error(LFGPU_ERR_UNSUPPORTED, "ScalarLoadEdgeVectorProvider assembles edge (codim 1) contributions");
+  Context& ctx = v.ctx();
+  v.template Prepare<A>(dof_handler);
+  detail::SegmentList s;
+  detail::DeviceCoeff dc;
+  detail::collect_segments<A>(ctx, dof_handler, evp, s, dc);
+  if (s.n == 0) return;
+  ctx.check(lfgpu_assemble_segment_load(ctx.get(), evp.Degree(), nullptr, s.n, static_cast<const double*>(s.d_xy),
+                                        static_cast<const std::int32_t*>(s.d_dofs), &dc.c, v.size(), v.device()),
+            "lfgpu_assemble_segment_load");
+}
+
 // GPU overloads of lf::assemble::FixFlaggedSolutionComponents / FixFlaggedSolutionCompAlt (fix_dof.h:86-138,181-218):
 // same SELECTOR contract (gdof index -> std::pair<bool, double>), evaluated once per dof on the host; the matrix keeps
 // the pattern of the symbolic pass (erased entries become explicit zeros), the vector is edited in place.

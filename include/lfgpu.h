@@ -214,6 +214,14 @@ int lfgpu_assemble_edge_mass(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const lfgpu_dofma
  * (uscalfe/loc_comp_ellbvp.h:784-921): accumulates into d_vec [n_dofs].                                             */
 int lfgpu_assemble_edge_load(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const lfgpu_dofmap* dofmap, int degree, const lfgpu_quad* qr_segment,
                              const lfgpu_coeff* g, const uint8_t* active_edges, double* d_vec);
+/* The same two operations for an explicit list of straight segments -- the form a host caller that owns the
+ * DofHandler uses: it passes only the ACTIVE edges (d_seg_xy device [n][4] = x0 y0 x1 y1 of the edge geometry,
+ * d_seg_dofs device int32 [n][degree + 1] = DofHandler::GlobalDofIndices(edge)); coefficient tables are per segment.  */
+int lfgpu_assemble_segment_mass(lfgpu_ctx* ctx, const lfgpu_pattern* pattern, int degree, const lfgpu_quad* qr_segment,
+                                int64_t n_segments, const double* d_seg_xy, const int32_t* d_seg_dofs, const lfgpu_coeff* gamma,
+                                double* d_values);
+int lfgpu_assemble_segment_load(lfgpu_ctx* ctx, int degree, const lfgpu_quad* qr_segment, int64_t n_segments, const double* d_seg_xy,
+                                const int32_t* d_seg_dofs, const lfgpu_coeff* g, int64_t n_dofs, double* d_vec);
 /* global coordinates of every edge's quadrature points, SegmentO1::Global (geometry/segment_o1.cc:9-11):
  * d_out device [n_edges][nq_stride][2] -- lets a host tabulate MeshFunctionGlobal lambdas into PER_QP edge tables    */
 int lfgpu_edge_qp_coords(lfgpu_ctx* ctx, lfgpu_mesh* mesh, int degree, const lfgpu_quad* qr_segment, int nq_stride, double* d_out);

@@ -106,6 +106,8 @@ def _lib():
         "lfgpu_assemble_load": (i32, [vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), C.POINTER(_CCoeff), vp, dbl, vp, i32]),
         "lfgpu_assemble_edge_mass": (i32, [vp, vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CCoeff), vp, vp]),
         "lfgpu_assemble_edge_load": (i32, [vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CCoeff), vp, vp]),
+        "lfgpu_assemble_segment_mass": (i32, [vp, vp, i32, C.POINTER(_CQuad), i64, vp, vp, C.POINTER(_CCoeff), vp]),
+        "lfgpu_assemble_segment_load": (i32, [vp, i32, C.POINTER(_CQuad), i64, vp, vp, C.POINTER(_CCoeff), i64, vp]),
         "lfgpu_edge_qp_coords": (i32, [vp, vp, i32, C.POINTER(_CQuad), i32, vp]),
         "lfgpu_mesh_boundary_edges": (i32, [vp, vp, vp]),
         "lfgpu_fix_flagged_solution_components": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),

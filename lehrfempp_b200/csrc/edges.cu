@@ -120,6 +120,51 @@ __global__ void k_edge_load(int64_t n_edges, const uint32_t* __restrict__ edge_n
     if (a < T.nsf) atomicAdd(vec + edge_dof(a, n0, n1, e, n_seg, edge_base), v[a]);
 }
 
+// The same two operations for an explicit list of straight segments with their dofs -- the form a host caller that
+// owns the DofHandler uses (it passes the ACTIVE edges only, typically a boundary part): seg_xy [n][4] = x0 y0 x1 y1,
+// seg_dofs [n][nsf] = GlobalDofIndices(edge).
+__global__ void k_segment_mass(int64_t n, const double* __restrict__ seg_xy, const int32_t* __restrict__ seg_dofs, SegTable T, EdgeCoeff G,
+                               bool row_major, const int32_t* __restrict__ outer, const int32_t* __restrict__ inner,
+                               double* __restrict__ values, int* __restrict__ flags) {
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const double dx = seg_xy[4 * e + 2] - seg_xy[4 * e], dy = seg_xy[4 * e + 3] - seg_xy[4 * e + 1];
+  const double len = sqrt(dx * dx + dy * dy);
+  const int nsf = T.nsf;
+  for (int a = 0; a < nsf; ++a) {
+    const int32_t da = seg_dofs[e * nsf + a];
+    for (int b = 0; b < nsf; ++b) {
+      const int32_t db = seg_dofs[e * nsf + b];
+      double m = 0.0;
+      for (int k = 0; k < T.nq; ++k) m += (T.phi[a * kMaxSegNq + k] * T.phi[b * kMaxSegNq + k]) * ((T.w[k] * len) * eval_edge_coeff(G, e, k));
+      const int32_t o = row_major ? da : db, i = row_major ? db : da;
+      const int slot = find_slot(inner, outer[o], outer[o + 1], i);
+      if (slot < 0) {
+        flags[0] = 1;
+      } else {
+        atomicAdd(values + slot, m);
+      }
+    }
+  }
+}
+__global__ void k_segment_load(int64_t n, const double* __restrict__ seg_xy, const int32_t* __restrict__ seg_dofs, SegTable T, EdgeCoeff G,
+                               int64_t n_dofs, double* __restrict__ vec, int* __restrict__ flags) {
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const double dx = seg_xy[4 * e + 2] - seg_xy[4 * e], dy = seg_xy[4 * e + 3] - seg_xy[4 * e + 1];
+  const double len = sqrt(dx * dx + dy * dy);
+  for (int a = 0; a < T.nsf; ++a) {
+    double v = 0.0;
+    for (int k = 0; k < T.nq; ++k) v += T.phi[a * kMaxSegNq + k] * ((T.w[k] * len) * eval_edge_coeff(G, e, k));
+    const int32_t d = seg_dofs[e * T.nsf + a];
+    if (d < 0 || d >= n_dofs) {
+      flags[0] = 1;
+    } else {
+      atomicAdd(vec + d, v);
+    }
+  }
+}
+
 // SegmentO1::Global (segment_o1.cc:9-11): x = p1 * t + p0 * (1 - t)
 __global__ void k_edge_qp_coords(int64_t n_edges, const uint32_t* __restrict__ edge_nodes, const double* __restrict__ xy, SegTable T,
                                  int nq_stride, double* __restrict__ out) {
@@ -229,6 +274,65 @@ int lfgpu_edge_qp_coords(lfgpu_ctx* ctx, lfgpu_mesh* mesh, int degree, const lfg
   k_edge_qp_coords<<<static_cast<unsigned>(cdiv(mesh->n_edges, kThreads)), kThreads, 0, ctx->stream>>>(mesh->n_edges, mesh->edge_nodes,
                                                                                                       mesh->node_coords, T, nq_stride, d_out);
   LFGPU_LAUNCH_CHECK(ctx);
+  return LFGPU_OK;
+}
+
+static int prepare_segments(lfgpu_ctx* ctx, int degree, const lfgpu_quad* qr, const lfgpu_coeff* coeff, SegTable* T, EdgeCoeff* G) {
+  std::string err;
+  const int rc = build_segment_table(degree, qr, T, &err);
+  if (rc != LFGPU_OK) LFGPU_FAIL(ctx, rc, err);
+  if (coeff->kind != LFGPU_COEFF_CONST && coeff->kind != LFGPU_COEFF_PER_CELL && coeff->kind != LFGPU_COEFF_PER_QP)
+    LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "segment coefficient must be CONST, PER_CELL (per segment) or PER_QP");
+  if (coeff->kind != LFGPU_COEFF_CONST && coeff->data == nullptr) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "coefficient table missing");
+  if (coeff->kind == LFGPU_COEFF_PER_QP && coeff->stride < T->nq) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "coefficient stride smaller than the number of quadrature points");
+  G->kind = coeff->kind;
+  G->c = coeff->c[0];
+  G->data = coeff->data;
+  G->stride = coeff->stride;
+  return LFGPU_OK;
+}
+
+int lfgpu_assemble_segment_mass(lfgpu_ctx* ctx, const lfgpu_pattern* p, int degree, const lfgpu_quad* qr_segment, int64_t n_segments,
+                                const double* d_seg_xy, const int32_t* d_seg_dofs, const lfgpu_coeff* gamma, double* d_values) {
+  if (ctx == nullptr || p == nullptr || gamma == nullptr || d_values == nullptr || n_segments < 0) return LFGPU_ERR_INVALID;
+  if (n_segments == 0) return LFGPU_OK;
+  if (d_seg_xy == nullptr || d_seg_dofs == nullptr) return LFGPU_ERR_INVALID;
+  LFGPU_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  SegTable T;
+  EdgeCoeff G{};
+  const int rc = prepare_segments(ctx, degree, qr_segment, gamma, &T, &G);
+  if (rc != LFGPU_OK) return rc;
+  int* d_flags = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 768);
+  LFGPU_CUDA_CHECK(ctx, cudaMemsetAsync(d_flags, 0, sizeof(int), ctx->stream));
+  k_segment_mass<<<static_cast<unsigned>(cdiv(n_segments, kThreads)), kThreads, 0, ctx->stream>>>(
+      n_segments, d_seg_xy, d_seg_dofs, T, G, p->major == LFGPU_ROW_MAJOR, p->outer, p->inner, d_values, d_flags);
+  LFGPU_LAUNCH_CHECK(ctx);
+  int h = 0;
+  LFGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(&h, d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  LFGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h != 0) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "a segment entry is missing from the pattern");
+  return LFGPU_OK;
+}
+
+int lfgpu_assemble_segment_load(lfgpu_ctx* ctx, int degree, const lfgpu_quad* qr_segment, int64_t n_segments, const double* d_seg_xy,
+                                const int32_t* d_seg_dofs, const lfgpu_coeff* g, int64_t n_dofs, double* d_vec) {
+  if (ctx == nullptr || g == nullptr || d_vec == nullptr || n_segments < 0) return LFGPU_ERR_INVALID;
+  if (n_segments == 0) return LFGPU_OK;
+  if (d_seg_xy == nullptr || d_seg_dofs == nullptr) return LFGPU_ERR_INVALID;
+  LFGPU_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  SegTable T;
+  EdgeCoeff G{};
+  const int rc = prepare_segments(ctx, degree, qr_segment, g, &T, &G);
+  if (rc != LFGPU_OK) return rc;
+  int* d_flags = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 768);
+  LFGPU_CUDA_CHECK(ctx, cudaMemsetAsync(d_flags, 0, sizeof(int), ctx->stream));
+  k_segment_load<<<static_cast<unsigned>(cdiv(n_segments, kThreads)), kThreads, 0, ctx->stream>>>(n_segments, d_seg_xy, d_seg_dofs, T, G, n_dofs,
+                                                                                                 d_vec, d_flags);
+  LFGPU_LAUNCH_CHECK(ctx);
+  int h = 0;
+  LFGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(&h, d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  LFGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h != 0) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "a segment dof is outside the vector");
   return LFGPU_OK;
 }
 

@@ -179,6 +179,62 @@ int main() {
       std::printf("%-46s N=%6zu nnz=%8zu rel.err=%.2e rhs=%.2e\n", variant == 0 ? "FixFlaggedSolutionComponents P2 hybrid" : "FixFlaggedSolutionCompAlt P2 hybrid", n,
                   kept, err / scale, berr / bscale);
     }
+    // impedance boundary terms (sec_ord_ell_bvp.h:147-215): cell matrix + edge mass on the part {x = 0} u {y = 0} of the
+    // boundary, load vector + edge load; same call sequence on both sides, same pattern (edge entries live in cell entries)
+    for (int p = 1; p <= 3; ++p) {
+      auto fes = std::make_shared<uscalfe::UniformScalarFESpace>(hyb, p);
+      const assemble::DofHandler& dofh = fes->LocGlobMap();
+      const std::size_t n = dofh.NumDofs();
+      auto sel = [](const mesh::Entity& e) {
+        const Mat c = e.Geometry()->Global(e.RefElem().NodeCoords());
+        return (c(0, 0) < 1e-12 && c(0, 1) < 1e-12) || (c(1, 0) < 1e-12 && c(1, 1) < 1e-12);
+      };
+      auto feta = [](double x, double y) { return 1.0 + x * x + y * y; };
+      auto fg = [](double x, double y) { return std::cos(3.0 * x) + y; };
+      // reference side
+      uscalfe::ReactionDiffusionElementMatrixProvider<OC, OC> oprov(fes, OC(1.0), OC(0.5));
+      uscalfe::MassEdgeMatrixProvider<uscalfe::MeshFunctionGlobal<double>, decltype(sel)> oeprov(fes, uscalfe::MeshFunctionGlobal<double>(feta), sel);
+      assemble::COOMatrix coo(n, n);
+      assemble::AssembleMatrixLocally(0, dofh, dofh, oprov, coo);
+      assemble::AssembleMatrixLocally(1, dofh, dofh, oeprov, coo);
+      const auto ref = coo.makeSparse();
+      uscalfe::ScalarLoadElementVectorProvider<OC> olprov(fes, OC(1.0));
+      uscalfe::ScalarLoadEdgeVectorProvider<uscalfe::MeshFunctionGlobal<double>, decltype(sel)> oelprov(fes, uscalfe::MeshFunctionGlobal<double>(fg), sel);
+      std::vector<double> ref_b(n, 0.0);
+      assemble::AssembleVectorLocally(0, dofh, olprov, ref_b);
+      assemble::AssembleVectorLocally(1, dofh, oelprov, ref_b);
+      // GPU side
+      auto gfes = std::make_shared<const FeSpace>(FeSpace{fes, p});
+      lfgpu::ReactionDiffusionElementMatrixProvider<double, GC, GC> gprov(gfes, GC{1.0}, GC{0.5});
+      lfgpu::MassEdgeMatrixProvider<double, lfgpu::MeshFunctionGlobal<decltype(feta)>, decltype(sel)> geprov(gfes, lfgpu::MeshFunctionGlobal<decltype(feta)>{feta}, sel);
+      lfgpu::ScalarLoadElementVectorProvider<double, GC> glprov(gfes, GC{1.0});
+      lfgpu::ScalarLoadEdgeVectorProvider<double, lfgpu::MeshFunctionGlobal<decltype(fg)>, decltype(sel)> gelprov(gfes, lfgpu::MeshFunctionGlobal<decltype(fg)>{fg}, sel);
+      lfgpu::CsrMatrix M(ctx, LFGPU_COL_MAJOR);
+      lfgpu::Vector v(ctx);
+      lfgpu::AssembleMatrixLocally<OracleAdaptor>(0, dofh, dofh, gprov, M);
+      lfgpu::AssembleMatrixLocally<OracleAdaptor>(1, dofh, dofh, geprov, M);
+      lfgpu::AssembleVectorLocally<OracleAdaptor>(0, dofh, glprov, v);
+      lfgpu::AssembleVectorLocally<OracleAdaptor>(1, dofh, gelprov, v);
+      std::vector<std::int32_t> outer, inner;
+      std::vector<double> vals;
+      M.Download(outer, inner, vals);
+      bool same = outer.size() == ref.outer.size() && inner.size() == ref.inner.size();
+      for (std::size_t i = 0; same && i < outer.size(); ++i) same = outer[i] == ref.outer[i];
+      for (std::size_t i = 0; same && i < inner.size(); ++i) same = inner[i] == ref.inner[i];
+      double scale = 0, err = 0;
+      for (std::size_t i = 0; same && i < vals.size(); ++i) {
+        scale = std::max(scale, std::fabs(ref.values[i]));
+        err = std::max(err, std::fabs(vals[i] - ref.values[i]));
+      }
+      const auto hb = v.Download();
+      double bscale = 0, berr = 0;
+      for (std::size_t i = 0; i < n; ++i) {
+        bscale = std::max(bscale, std::fabs(ref_b[i]));
+        berr = std::max(berr, std::fabs(hb[i] - ref_b[i]));
+      }
+      CHECK(same && err <= 1e-12 * scale && berr <= 1e-12 * bscale, "impedance terms P%d: same=%d matrix err %.3e rhs err %.3e", p, static_cast<int>(same), err, berr);
+      std::printf("cell + edge (impedance) terms P%d on hybrid mesh     N=%6zu nnz=%8zu rel.err=%.2e rhs=%.2e\n", p, n, vals.size(), err / scale, berr / bscale);
+    }
     // missing rule -> error (loc_comp_ellbvp.h:278-287)
   } catch (const lfgpu::Error& e) {
     std::printf("lfgpu::Error %d: %s\n", e.code, e.what());
