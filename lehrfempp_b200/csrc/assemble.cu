@@ -17,6 +17,7 @@
 // Both use the same element-row routine.  Affine cells with cell-wise constant coefficients take the reference-tensor
 // route (5 FMAs per entry); everything else integrates per quadrature point (3 FMAs per entry and point).
 #include <cmath>
+#include <cstdlib>
 #include <utility>
 #include <vector>
 
@@ -190,6 +191,43 @@ __device__ __forceinline__ void tensor_row(const TabView& T, int a, double m00, 
 #pragma unroll
     for (int b = 0; b < NSF; ++b) {
       if (b < nsf) acc[b] = m00 * T.k00[row + b] + m01 * T.k10[row + b] + m10 * T.k01[row + b] + m11 * T.k11[row + b] + gm * T.m[row + b];
+    }
+  }
+}
+
+// The same with the reference tensors in CONSTANT memory (the table blob of the current call, uploaded by the host
+// before the launch).  ncu on the P2 workload showed the item kernel limited by the L1/shared-memory pipe (84 % busy):
+// 24-40 table loads per item came from shared memory plus a per-block copy of the tables; threads of a warp share `a`
+// (items are ordered by rank, local index, dof), so the constant cache serves them as broadcasts and the LSU pipe is
+// left to the accumulation rounds.
+constexpr int kConstTableDoubles = 4096;
+__constant__ double c_tables[kConstTableDoubles];
+
+template <int NSF>
+__device__ __forceinline__ void tensor_row_const(int kbase, int nsf, int a, double m00, double m01, double m10, double m11, double gm,
+                                                 bool sym, double (&acc)[NSF]) {
+  const int nn = nsf * nsf;
+  const int r0 = kbase + a * nsf;  // k00; then k01, k10, k11, m at multiples of nn (make_view)
+  if (sym) {
+    if (gm == 0.0) {
+#pragma unroll
+      for (int b = 0; b < NSF; ++b) {
+        if (b < nsf) acc[b] = m00 * c_tables[r0 + b] + m01 * (c_tables[r0 + 2 * nn + b] + c_tables[r0 + nn + b]) + m11 * c_tables[r0 + 3 * nn + b];
+      }
+    } else {
+#pragma unroll
+      for (int b = 0; b < NSF; ++b) {
+        if (b < nsf)
+          acc[b] = m00 * c_tables[r0 + b] + m01 * (c_tables[r0 + 2 * nn + b] + c_tables[r0 + nn + b]) + m11 * c_tables[r0 + 3 * nn + b] +
+                   gm * c_tables[r0 + 4 * nn + b];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int b = 0; b < NSF; ++b) {
+      if (b < nsf)
+        acc[b] = m00 * c_tables[r0 + b] + m01 * c_tables[r0 + 2 * nn + b] + m10 * c_tables[r0 + nn + b] + m11 * c_tables[r0 + 3 * nn + b] +
+                 gm * c_tables[r0 + 4 * nn + b];
     }
   }
 }
@@ -450,15 +488,18 @@ __global__ void __launch_bounds__(kItemThreads, TENSOR_ONLY ? (NSF <= 6 ? 6 : 5)
                                                            const int4* __restrict__ blk_hdr, int pos_row, const P* __restrict__ pos_item,
                                                            const uint2* __restrict__ item_sorted, DevCoeff alpha, DevCoeff gamma,
                                                            const uint8_t* __restrict__ active, bool transpose_alpha, double beta,
-                                                           const double* __restrict__ cell_metric_tab, double* __restrict__ values) {
+                                                           const double* __restrict__ cell_metric_tab, double* __restrict__ values,
+                                                           bool const_tables) {
   extern __shared__ double smem[];
   const int tid = threadIdx.x;
   const int4 bh = __ldg(blk_hdr + blockIdx.x);
   const int32_t adj0 = bh.x, out0 = bh.y;
   const int n_items = bh.z & 0xffff, max_rank = bh.z >> 16, total = bh.w;
+  // metric route with the reference tensors in constant memory: no shared-memory tables at all
+  const bool ctab = TENSOR_ONLY && const_tables && cell_metric_tab != nullptr;
   TabView tt, tq;
-  load_tables(hdr, blob, smem, tt, tq, table_mask);  // contains a __syncthreads()
-  double* image = smem + ((hdr.total + 1) & ~1);
+  if (!ctab) load_tables(hdr, blob, smem, tt, tq, table_mask);  // contains a __syncthreads()
+  double* image = ctab ? smem : smem + ((hdr.total + 1) & ~1);
   for (int k = tid; k < ((total + 15) & ~15); k += kItemThreads) image[k] = 0.0;
   // my item (threads are ordered by rank-in-dof, then dof: see k_item_perm)
   bool valid = tid < n_items;
@@ -483,8 +524,13 @@ __global__ void __launch_bounds__(kItemThreads, TENSOR_ONLY ? (NSF <= 6 ? 6 : 5)
         // affine cells, cell-wise constant coefficients: the metric of every cell was computed once by k_cell_metric
         const double2* mp = reinterpret_cast<const double2*>(cell_metric_tab) + 3 * cell;
         const double2 ma = __ldg(mp), mb = __ldg(mp + 1), mc = __ldg(mp + 2);
-        nsf = tt.nsf;
-        tensor_row<NSF>(tt, a, ma.x, ma.y, mb.x, mb.y, mc.x, alpha.kind != LFGPU_COEFF_CONST_2X2, acc);
+        nsf = hdr.nsf[0];
+        if (ctab) {
+          const int kbase = hdr.off[0] + 3 * hdr.nq[0] + 3 * nsf * hdr.nq[0];
+          tensor_row_const<NSF>(kbase, nsf, a, ma.x, ma.y, mb.x, mb.y, mc.x, alpha.kind != LFGPU_COEFF_CONST_2X2, acc);
+        } else {
+          tensor_row<NSF>(tt, a, ma.x, ma.y, mb.x, mb.y, mc.x, alpha.kind != LFGPU_COEFF_CONST_2X2, acc);
+        }
       } else {
         const CellGeom g = load_geom(mv, cell);
         const TabView& T = g.quad ? tq : tt;
@@ -724,9 +770,15 @@ int launch_matrix(lfgpu_ctx* ctx, const HostTables& ht, const double* d_blob, co
           LFGPU_LAUNCH_CHECK(ctx);
           metric = pm->cell_metric;
         }
+        // metric route: reference tensors through the constant cache (LFGPU_CONST_TABLES=0 keeps them in shared memory)
+        static const bool ctab_env = [] { const char* e = std::getenv("LFGPU_CONST_TABLES"); return e == nullptr || e[0] != '0'; }();
+        const bool const_tables = ctab_env && metric != nullptr && ht.hdr.total <= kConstTableDoubles;
+        if (const_tables)
+          LFGPU_CUDA_CHECK(ctx, cudaMemcpyToSymbolAsync(c_tables, ht.blob.data(), sizeof(double) * ht.hdr.total, 0, cudaMemcpyHostToDevice,
+                                                        ctx->stream));
         ki<<<static_cast<unsigned>(p->n_item_blocks), kItemThreads, smem_i, ctx->stream>>>(
             ht.hdr, d_blob, table_mask, mv, static_cast<const int4*>(p->blk_hdr), p->pos_row, static_cast<const P*>(p->pos_item),
-            static_cast<const uint2*>(p->item_sorted), alpha, gamma, active, transpose_alpha, beta, metric, d_values);
+            static_cast<const uint2*>(p->item_sorted), alpha, gamma, active, transpose_alpha, beta, metric, d_values, const_tables);
         LFGPU_LAUNCH_CHECK(ctx);
         return LFGPU_OK;
       }
