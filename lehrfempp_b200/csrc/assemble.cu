@@ -461,20 +461,28 @@ __global__ void __launch_bounds__(THREADS, 6) k_assemble_gather(Tables hdr, cons
   (void)flags;
 }
 
-// Per-cell metric table for meshes of affine cells with cell-wise constant coefficients: (M00, M01, M10, M11, gamma |det|, 0)
-// with M = |det J| J^-1 A J^-T.  Computed once per numeric pass so that the 6..10 items of a cell neither repeat the
-// geometry nor chase cell -> vertices -> coordinates: an item then needs one 48-byte read.
+// Per-cell metric table for meshes of affine cells with cell-wise constant coefficients, M = |det J| J^-1 A J^-T:
+// (M00, M01, M11, gamma |det|) = 32 B when A is a scalar (M symmetric; the row routine never reads M10 then), else
+// (M00, M01, M10, M11, gamma |det|, 0) = 48 B.  Computed once per numeric pass so that the 6..10 items of a cell neither
+// repeat the geometry nor chase cell -> vertices -> coordinates.  The records are GATHERED by the items (one line per
+// lane in the worst case), so their size is what the L1 pipe of the item kernel pays for.
 __global__ void __launch_bounds__(256) k_cell_metric(MeshView mv, int64_t n_cells, DevCoeff alpha, DevCoeff gamma, bool transpose_alpha,
-                                                     double* __restrict__ out) {
+                                                     bool sym, double* __restrict__ out) {
   const int64_t cell = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (cell >= n_cells) return;
   const CellGeom g = load_geom(mv, cell);
   double m00, m01, m10, m11, gm;
   cell_metric(g, alpha, gamma, cell, transpose_alpha, m00, m01, m10, m11, gm);
-  double2* o = reinterpret_cast<double2*>(out) + 3 * cell;
-  o[0] = make_double2(m00, m01);
-  o[1] = make_double2(m10, m11);
-  o[2] = make_double2(gm, 0.0);
+  if (sym) {
+    double2* o = reinterpret_cast<double2*>(out) + 2 * cell;
+    o[0] = make_double2(m00, m01);
+    o[1] = make_double2(m11, gm);
+  } else {
+    double2* o = reinterpret_cast<double2*>(out) + 3 * cell;
+    o[0] = make_double2(m00, m01);
+    o[1] = make_double2(m10, m11);
+    o[2] = make_double2(gm, 0.0);
+  }
 }
 
 // Item-parallel owner-computes kernel (the default without a row list): one thread per ITEM (cell, a) of the block's
@@ -522,14 +530,23 @@ __global__ void __launch_bounds__(kItemThreads, TENSOR_ONLY ? (NSF <= 6 ? 6 : 5)
       for (int w = 0; w < kWords; ++w) pw[w] = __ldg(pp + w);
       if (TENSOR_ONLY && cell_metric_tab != nullptr) {
         // affine cells, cell-wise constant coefficients: the metric of every cell was computed once by k_cell_metric
-        const double2* mp = reinterpret_cast<const double2*>(cell_metric_tab) + 3 * cell;
-        const double2 ma = __ldg(mp), mb = __ldg(mp + 1), mc = __ldg(mp + 2);
+        const bool sym = alpha.kind != LFGPU_COEFF_CONST_2X2;
+        double m00, m01, m10, m11, gm;
+        if (sym) {
+          const double2* mp = reinterpret_cast<const double2*>(cell_metric_tab) + 2 * cell;
+          const double2 ma = __ldg(mp), mb = __ldg(mp + 1);
+          m00 = ma.x; m01 = ma.y; m10 = ma.y; m11 = mb.x; gm = mb.y;
+        } else {
+          const double2* mp = reinterpret_cast<const double2*>(cell_metric_tab) + 3 * cell;
+          const double2 ma = __ldg(mp), mb = __ldg(mp + 1), mc = __ldg(mp + 2);
+          m00 = ma.x; m01 = ma.y; m10 = mb.x; m11 = mb.y; gm = mc.x;
+        }
         nsf = hdr.nsf[0];
         if (ctab) {
           const int kbase = hdr.off[0] + 3 * hdr.nq[0] + 3 * nsf * hdr.nq[0];
-          tensor_row_const<NSF>(kbase, nsf, a, ma.x, ma.y, mb.x, mb.y, mc.x, alpha.kind != LFGPU_COEFF_CONST_2X2, acc);
+          tensor_row_const<NSF>(kbase, nsf, a, m00, m01, m10, m11, gm, sym, acc);
         } else {
-          tensor_row<NSF>(tt, a, ma.x, ma.y, mb.x, mb.y, mc.x, alpha.kind != LFGPU_COEFF_CONST_2X2, acc);
+          tensor_row<NSF>(tt, a, m00, m01, m10, m11, gm, sym, acc);
         }
       } else {
         const CellGeom g = load_geom(mv, cell);
@@ -766,7 +783,7 @@ int launch_matrix(lfgpu_ctx* ctx, const HostTables& ht, const double* d_blob, co
           lfgpu_pattern* pm = const_cast<lfgpu_pattern*>(p);
           if (pm->cell_metric == nullptr) LFGPU_CUDA_CHECK(ctx, cudaMalloc(&pm->cell_metric, sizeof(double) * 6 * p->n_cells));
           k_cell_metric<<<static_cast<unsigned>(cdiv(p->n_cells, 256)), 256, 0, ctx->stream>>>(mv, p->n_cells, alpha, gamma, transpose_alpha,
-                                                                                              pm->cell_metric);
+                                                                                              alpha.kind != LFGPU_COEFF_CONST_2X2, pm->cell_metric);
           LFGPU_LAUNCH_CHECK(ctx);
           metric = pm->cell_metric;
         }
