@@ -244,6 +244,15 @@ int lfgpu_fix_flagged_solution_components(lfgpu_ctx* ctx, const lfgpu_pattern* p
 int lfgpu_fix_flagged_solution_comp_alt(lfgpu_ctx* ctx, const lfgpu_pattern* pattern, double* d_values, double* d_rhs,
                                         const uint8_t* d_fixed, const double* d_fixed_values, int32_t* d_outer_out,
                                         int32_t* d_inner_out, double* d_values_out, int64_t* nnz_out);
+/* ---- consumer side: the assembled matrix used in place ------------------------------------ */
+/* y = A x on the compressed arrays (either storage order); d_x [cols], d_y [rows] device                             */
+int lfgpu_spmv(lfgpu_ctx* ctx, const lfgpu_pattern* pattern, const double* d_values, const double* d_x, double* d_y);
+/* Conjugate gradients for the symmetric positive definite systems the path produces (what the reference hands to an
+ * Eigen solver after makeSparse(), examples/ellbvp_linfe/homDir_linfe_demo.cc:166-175).  d_x: initial guess in, solution
+ * out.  Stops when ||r||_2 <= rel_tol * ||b||_2 or after max_iter iterations; jacobi != 0 = diagonal preconditioner.
+ * iters_out / rel_res_out (nullable): iterations done, final relative residual.                                      */
+int lfgpu_cg_solve(lfgpu_ctx* ctx, const lfgpu_pattern* pattern, const double* d_values, const double* d_rhs, double* d_x,
+                   double rel_tol, int max_iter, int jacobi, int* iters_out, double* rel_res_out);
 /* ---- multi-GPU building blocks (DESIGN.md "Multi-GPU"; the reference is serial) --------------------------------------- */
 /* Row segments values[outer[r] .. outer[r+1]) of the listed rows <-> a contiguous message buffer.  d_rows device int32
  * [n_rows], d_offsets device int64 [n_rows] = start of each row's segment inside the buffer.  unpack_add ADDS the

@@ -114,6 +114,8 @@ def _lib():
         "lfgpu_fix_flagged_solution_comp_alt": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "lfgpu_assemble_reaction_diffusion_host": (i32, [vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), C.POINTER(_CCoeff),
                                                          C.POINTER(_CCoeff), vp, vp, vp, i32, i32]),
+        "lfgpu_spmv": (i32, [vp, vp, vp, vp, vp]),
+        "lfgpu_cg_solve": (i32, [vp, vp, vp, vp, vp, dbl, i32, i32, vp, vp]),
         "lfgpu_rows_pack": (i32, [vp, vp, vp, i64, vp, vp, vp]),
         "lfgpu_rows_unpack_add": (i32, [vp, vp, vp, i64, vp, vp, vp]),
         "lfgpu_pattern_adj_ptr_device": (vp, [vp]),
@@ -564,6 +566,22 @@ class Pattern:
             self.ctx.h, self.mesh.h, self.h, degree, _qref(qr_tria), _qref(qr_quad), alpha.ref(), gamma.ref(), _p(h_node_coords), out.ptr,
             _p(h_values), algo, n_blocks))
         return out
+
+    def spmv(self, values, x, out=None):
+        """y = A x on the device."""
+        if out is None:
+            out = self.ctx.empty(self.rows)
+        self.ctx.check(self.ctx.L.lfgpu_spmv(self.ctx.h, self.h, values.ptr, x.ptr, out.ptr))
+        return out
+
+    def cg_solve(self, values, rhs, x=None, rel_tol=1e-10, max_iter=10000, jacobi=True):
+        """Conjugate gradients on the assembled matrix; returns (x, iterations, relative residual)."""
+        if x is None:
+            x = self.ctx.zeros(self.rows)
+        it, res = C.c_int(0), C.c_double(0.0)
+        self.ctx.check(self.ctx.L.lfgpu_cg_solve(self.ctx.h, self.h, values.ptr, rhs.ptr, x.ptr, rel_tol, max_iter, 1 if jacobi else 0,
+                                                 C.byref(it), C.byref(res)))
+        return x, it.value, res.value
 
     def fix_flagged_solution_components(self, values, rhs, fixed, fixed_values, compact=False, alt=False):
         """FixFlaggedSolutionComponents(selectvals, A, b) (assemble/fix_dof.h:86-138) on the device;
