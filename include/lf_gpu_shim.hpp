@@ -640,5 +640,26 @@ void FixFlaggedSolutionCompAlt(SELECTOR&& selectvals, CsrMatrix& A, Vector& b) {
   detail::fix_components(selectvals, A, b, true);
 }
 
+// Conjugate gradients on the device for the (symmetric positive definite) system held by A and b -- the step the
+// reference does with an Eigen solver on makeSparse() (homDir_linfe_demo.cc:166-175).  Returns the solution on the host.
+inline std::vector<double> SolveCG(CsrMatrix& A, Vector& b, double rel_tol = 1e-10, int max_iter = 10000, int* iterations = nullptr,
+                                   double* rel_residual = nullptr) {
+  Context& ctx = A.ctx();
+  const std::int64_t n = A.rows();
+  if (b.size() != n) throw Error(LFGPU_ERR_INVALID, "Mismatch of matrix and right-hand-side size");
+  void* d_x = nullptr;
+  ctx.check(lfgpu_malloc(ctx.get(), 8 * n, &d_x), "lfgpu_malloc");
+  int rc = lfgpu_memset(ctx.get(), d_x, 0, 8 * n);
+  if (rc == LFGPU_OK)
+    rc = lfgpu_cg_solve(ctx.get(), A.pattern(), A.device_values(), b.device(), static_cast<double*>(d_x), rel_tol, max_iter, 1, iterations,
+                        rel_residual);
+  std::vector<double> x(n);
+  if (rc == LFGPU_OK) rc = lfgpu_memcpy_d2h(ctx.get(), x.data(), d_x, 8 * n);
+  if (rc == LFGPU_OK) rc = lfgpu_ctx_synchronize(ctx.get());
+  lfgpu_free(ctx.get(), d_x);
+  ctx.check(rc, "lfgpu_cg_solve");
+  return x;
+}
+
 }  // namespace lfgpu
 #endif

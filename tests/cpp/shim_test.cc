@@ -176,6 +176,16 @@ int main() {
         berr = std::max(berr, std::fabs(hb[i] - ref_b[i]));
       }
       CHECK(err <= 1e-12 * scale && berr <= 1e-12 * bscale, "fix variant %d: matrix err %.3e rhs err %.3e", variant, err, berr);
+      if (variant == 0) {  // the symmetric variant keeps the system SPD: solve on the device, fixed components must come out
+        int iters = 0;
+        double res = 1.0;
+        const auto x = lfgpu::SolveCG(M, v, 1e-12, 5000, &iters, &res);
+        double fix_err = 0;
+        for (std::size_t i = 0; i < n; ++i)
+          if (sel(static_cast<std::int64_t>(i)).first) fix_err = std::max(fix_err, std::fabs(x[i] - sel(static_cast<std::int64_t>(i)).second));
+        CHECK(res <= 1e-12 && fix_err <= 1e-11, "device CG: residual %.3e after %d iterations, fixed components off by %.3e", res, iters, fix_err);
+        std::printf("%-46s iterations=%d rel.residual=%.2e fixed-dof error=%.2e\n", "SolveCG after FixFlaggedSolutionComponents", iters, res, fix_err);
+      }
       std::printf("%-46s N=%6zu nnz=%8zu rel.err=%.2e rhs=%.2e\n", variant == 0 ? "FixFlaggedSolutionComponents P2 hybrid" : "FixFlaggedSolutionCompAlt P2 hybrid", n,
                   kept, err / scale, berr / bscale);
     }
