@@ -323,8 +323,21 @@ def main():
         e2e_steps = max(3, min(args.steps, 10))
 
         e2e_blocks = int(os.environ.get("LFGPU_E2E_BLOCKS", "16"))
+        # owner_rows on the fan kernel: every rank runs the host-buffer call for ITS row block -- uploads only the coordinate
+        # window its rows refer to and downloads only its rows (lfgpu_assemble_reaction_diffusion_host_range)
+        range_mode = asm is not None and asm.mode == "owner_rows" and getattr(asm, "_range_ok", False) and args.algo in ("auto", "fan")
+        h2d_rank = 16 * mesh.n_nodes
+        if range_mode:
+            inner_t = torch.as_tensor(pat.download()[1], device="cuda")
+            seg = inner_t[int(outer_t[asm.row0].item()):int(outer_t[asm.row0 + asm.n_rows].item())]
+            h2d_rank = 16 * (int(seg.max().item()) + 1 - int(seg.min().item())) if seg.numel() > 0 else 0
+            del inner_t, seg
 
         def e2e_step():
+            if range_mode:
+                pat.assemble_reaction_diffusion_host_range(degree, alpha, gamma, h_xy, h_vals, asm.row0, asm.n_rows, out=values, algo=algo,
+                                                           n_blocks=max(2, e2e_blocks // world))
+                return
             if asm is None:
                 # the host-buffer C-ABI call: pinned coordinates in, pinned CSR values out; upload, kernel and download
                 # are pipelined over row blocks inside the call (csrc/hostpipe.cu); returns when h_vals is complete
@@ -346,16 +359,18 @@ def main():
             t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
-        h2d_b = 16 * mesh.n_nodes
+        h2d_b = h2d_rank
         if dist is not None:
-            t = torch.tensor([float(d2h_bytes)], device="cuda", dtype=torch.float64)
+            t = torch.tensor([float(d2h_bytes), float(h2d_rank)], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            d2h_bytes = int(t.item())
-            h2d_b *= world
+            d2h_bytes = int(t[0].item())
+            h2d_b = int(t[1].item())
         e2e = {"value": mesh.n_cells / e2e_s, "unit": "cells/s", "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_bytes),
                "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                "what": ("per step: one lfgpu_assemble_reaction_diffusion_host call = H2D node coordinates (pinned) -> kernel -> D2H CSR "
                         "values (pinned), pipelined over %d row blocks" % e2e_blocks) if asm is None else
+                       ("per step and rank: one lfgpu_assemble_reaction_diffusion_host_range call = H2D of the coordinate window of the "
+                        "rank's row block (pinned) -> kernel -> D2H of its CSR rows (pinned), pipelined") if range_mode else
                        "per step: H2D node coordinates (pinned) -> partitioned assembly -> D2H of the owned CSR rows (pinned)"}
     t_end = time.time()
     if rank == 0:

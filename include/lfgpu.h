@@ -200,6 +200,14 @@ int lfgpu_assemble_reaction_diffusion_host(lfgpu_ctx* ctx, lfgpu_mesh* mesh, con
                                            const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad, const lfgpu_coeff* alpha,
                                            const lfgpu_coeff* gamma, const double* h_node_coords, double* d_values,
                                            double* h_values, int algo, int n_blocks);
+/* The same for the contiguous outer range [row0, row0 + n_rows) -- the share of one GPU when the rows are split into
+ * blocks (lehrfempp_b200/distributed.py, mode "owner_rows"): h_node_coords is still the FULL coordinate array, of
+ * which only the window the range refers to is uploaded; h_values_range receives the values of the range only (its
+ * element 0 is the first value of row row0).  Fan kernel only (LFGPU_ERR_UNSUPPORTED otherwise).                     */
+int lfgpu_assemble_reaction_diffusion_host_range(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const lfgpu_pattern* pattern, int degree,
+                                                 const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad, const lfgpu_coeff* alpha,
+                                                 const lfgpu_coeff* gamma, const double* h_node_coords, double* d_values,
+                                                 double* h_values_range, int algo, int n_blocks, int64_t row0, int64_t n_rows);
 /* ---- edge (codim-1) contributions (second "next" row) ------------------------------------------- */
 /* AssembleMatrixLocally(1, dofh, dofh, MassEdgeMatrixProvider(fe_space, gamma[, rule], edge_selector), A)
  * (uscalfe/loc_comp_ellbvp.h:367-529, assembler.h:114-186 with codim 1): for every active edge the mass matrix

@@ -114,6 +114,8 @@ def _lib():
         "lfgpu_fix_flagged_solution_comp_alt": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "lfgpu_assemble_reaction_diffusion_host": (i32, [vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), C.POINTER(_CCoeff),
                                                          C.POINTER(_CCoeff), vp, vp, vp, i32, i32]),
+        "lfgpu_assemble_reaction_diffusion_host_range": (i32, [vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), C.POINTER(_CCoeff),
+                                                               C.POINTER(_CCoeff), vp, vp, vp, i32, i32, i64, i64]),
         "lfgpu_spmv": (i32, [vp, vp, vp, vp, vp]),
         "lfgpu_cg_solve": (i32, [vp, vp, vp, vp, vp, dbl, i32, i32, vp, vp]),
         "lfgpu_rows_pack": (i32, [vp, vp, vp, i64, vp, vp, vp]),
@@ -565,6 +567,21 @@ class Pattern:
         self.ctx.check(self.ctx.L.lfgpu_assemble_reaction_diffusion_host(
             self.ctx.h, self.mesh.h, self.h, degree, _qref(qr_tria), _qref(qr_quad), alpha.ref(), gamma.ref(), _p(h_node_coords), out.ptr,
             _p(h_values), algo, n_blocks))
+        return out
+
+    def assemble_reaction_diffusion_host_range(self, degree, alpha, gamma, h_node_coords, h_values_range, row0, n_rows, out=None,
+                                               qr_tria=None, qr_quad=None, algo=ALGO_AUTO, n_blocks=0):
+        """Host-buffer form for the outer range [row0, row0 + n_rows): uploads only the coordinate window the range refers to
+        (h_node_coords is the full array), downloads only the range's values into h_values_range."""
+        if out is None:
+            out = self.ctx.empty(self.nnz)
+        if h_node_coords is not None:
+            assert h_node_coords.dtype == np.float64 and h_node_coords.size == 2 * self.mesh.n_nodes and h_node_coords.flags.c_contiguous
+        if h_values_range is not None:
+            assert h_values_range.dtype == np.float64 and h_values_range.flags.c_contiguous
+        self.ctx.check(self.ctx.L.lfgpu_assemble_reaction_diffusion_host_range(
+            self.ctx.h, self.mesh.h, self.h, degree, _qref(qr_tria), _qref(qr_quad), alpha.ref(), gamma.ref(), _p(h_node_coords), out.ptr,
+            _p(h_values_range), algo, n_blocks, int(row0), int(n_rows)))
         return out
 
     def spmv(self, values, x, out=None):

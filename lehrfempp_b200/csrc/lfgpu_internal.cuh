@@ -113,6 +113,8 @@ struct lfgpu_pattern {
   // host pipeline plan (hostpipe.cu): for hp_blocks equal blocks of outer indices, the number of leading node coordinates
   // that must be on the device before block b can be computed (running maximum, so monotone)
   int hp_blocks = 0;
+  int64_t hp_row0 = -1, hp_rows = -1;  // the row range the cached plan was built for
+  int64_t hp_lo = 0;                   // smallest node index the range refers to
   std::vector<int64_t> hp_need;
   std::vector<int64_t> hp_val;  // [hp_blocks + 1] first stored value of every block
 };

@@ -123,6 +123,40 @@ def test_host_entry_generic_path(ctx, lf, degree):
     assert np.array_equal(h_vals, ref)
 
 
+@pytest.mark.parametrize("parts", [2, 3])
+def test_host_entry_row_ranges_tile_the_matrix(ctx, lf, parts):
+    """The _range form (one GPU's share in the owner_rows mode): ranges that tile the rows reproduce the full result; each
+    call uploads only the coordinate window its rows refer to."""
+    from lehrfempp_b200.distributed import row_ranges
+    import torch
+    gm = ctx.mesh_tp_tria(260, 190)
+    dm = gm.dofmap_lagrange(1)
+    pat = dm.symbolic(major=lf.ROW_MAJOR)
+    xy0 = gm.download()["node_coords"]
+    xy = moved(xy0, 21)
+    alpha, gamma = lf.Coeff.const(1.5), lf.Coeff.const(0.25)
+    ref = separate_calls(ctx, lf, gm, pat, 1, alpha, gamma, xy)
+    outer, _ = pat.download()
+    bounds = row_ranges(torch.as_tensor(outer), parts)
+    h_xy = ctx.pinned(xy.size)
+    h_xy[:] = xy.ravel()
+    got = np.full(pat.nnz, np.nan)
+    for k in range(parts):
+        r0, r1 = bounds[k], bounds[k + 1]
+        # poison the device coordinates so that every range must bring its own window
+        gm.update_node_coords(np.full_like(xy0, 1e30))
+        ctx.synchronize()
+        h_part = ctx.pinned(int(outer[r1] - outer[r0]))
+        h_part[:] = np.nan
+        pat.assemble_reaction_diffusion_host_range(1, alpha, gamma, h_xy, h_part, r0, r1 - r0, n_blocks=3)
+        got[outer[r0]:outer[r1]] = h_part
+        dev_xy = gm.download()["node_coords"]
+        touched = np.flatnonzero(dev_xy[:, 0] < 1e29)
+        assert touched.size < (0.75 if parts == 2 else 0.6) * len(xy)  # a window, not the whole array
+        assert np.array_equal(dev_xy[touched], xy[touched])
+    assert np.array_equal(got, ref)
+
+
 def test_host_entry_optional_buffers(ctx, lf):
     gm = ctx.mesh_tp_tria(150, 150)
     dm = gm.dofmap_lagrange(1)
