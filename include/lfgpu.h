@@ -92,6 +92,10 @@ int lfgpu_mesh_upload(lfgpu_ctx* ctx, int64_t n_nodes, const double* node_coords
 int lfgpu_mesh_tp_tria(lfgpu_ctx* ctx, uint32_t nx, uint32_t ny, double x0, double y0, double x1, double y1, lfgpu_mesh** out);
 int lfgpu_mesh_tp_quad(lfgpu_ctx* ctx, uint32_t nx, uint32_t ny, double x0, double y0, double x1, double y1, lfgpu_mesh** out);
 int lfgpu_mesh_hybrid(lfgpu_ctx* ctx, uint32_t n, double jitter, uint64_t seed, lfgpu_mesh** out);
+/* refine : lf::refinement::MeshHierarchy::RefineRegular (refinement/mesh_hierarchy.cc:72-114, 368-1262) -- one step of
+ *          regular refinement of `parent` with the reference's node / edge / cell numbering (SURVEY.md section 8f row
+ *          3): the mesh of benchmark config C4.  Needs a parent whose cell corners are its node positions.            */
+int lfgpu_mesh_refine_regular(lfgpu_ctx* ctx, lfgpu_mesh* parent, lfgpu_mesh** out);
 /* Edge numbering and orientations exactly as the lf::mesh::hybrid2d::Mesh constructor assigns them
  * (mesh/hybrid2d/mesh.cc:178-810): the n_explicit edges (edge_nodes [n][2], nullable) keep their position as index and
  * their direction; the remaining edges are numbered in ascending (min,max) endpoint order and point along the local

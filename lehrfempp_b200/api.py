@@ -78,6 +78,7 @@ def _lib():
         "lfgpu_mesh_tp_quad": (i32, [vp, C.c_uint32, C.c_uint32, dbl, dbl, dbl, dbl, pp]),
         "lfgpu_mesh_hybrid": (i32, [vp, C.c_uint32, dbl, C.c_uint64, pp]),
         "lfgpu_mesh_build_topology": (i32, [vp, vp, i64, vp, vp]),
+        "lfgpu_mesh_refine_regular": (i32, [vp, vp, pp]),
         "lfgpu_mesh_counts": (i32, [vp] + [C.POINTER(i64)] * 5),
         "lfgpu_mesh_download": (i32, [vp] * 9),
         "lfgpu_mesh_update_node_coords": (i32, [vp, vp, vp]),
@@ -405,6 +406,13 @@ class Mesh:
         self.ctx.check(self.ctx.L.lfgpu_mesh_download(self.ctx.h, self.h, _p(out["cell_type"]), _p(out["cell_nodes"]),
                                                       _p(out["cell_coords"]), _p(ce), _p(co), _p(en), _p(out["node_coords"])))
         return out
+
+    def refine_regular(self):
+        """MeshHierarchy::RefineRegular(): the regularly refined mesh with the reference's numbering, built on the device."""
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.L.lfgpu_mesh_refine_regular(self.ctx.h, self.h, C.byref(h)))
+        self._refresh()  # the parent's edges are numbered now
+        return Mesh(self.ctx, h)
 
     def boundary_edges(self):
         """DeviceArray(uint8)[n_edges]: edges with exactly one adjacent cell (flagEntitiesOnBoundary(mesh, 1))."""

@@ -454,7 +454,7 @@ int lfgpu_mesh_hybrid(lfgpu_ctx* ctx, uint32_t n, double jitter, uint64_t seed, 
 namespace lfgpu {
 // d_explicit_in: device array [n_explicit][2] or nullptr; if tp_recipe the explicit list of the triangle builder is generated
 static int build_topology_impl(lfgpu_ctx* ctx, lfgpu_mesh* m, int64_t n_explicit, const uint32_t* edge_nodes_host, bool tp_recipe,
-                               const uint8_t* cell_geo_host) {
+                               const uint8_t* cell_geo_host, const uint32_t* d_explicit_given = nullptr) {
   LFGPU_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const int64_t total = n_explicit + 4 * m->n_cells;
@@ -485,6 +485,8 @@ static int build_topology_impl(lfgpu_ctx* ctx, lfgpu_mesh* m, int64_t n_explicit
     if (tp_recipe) {
       k_tp_tria_edges<<<static_cast<unsigned>(cdiv(n_explicit, kThreads)), kThreads, 0, st>>>(m->tp_nx, m->tp_ny, d_explicit);
       ctx->launches++;
+    } else if (d_explicit_given != nullptr) {
+      TOPO_CHECK(cudaMemcpyAsync(d_explicit, d_explicit_given, sizeof(uint32_t) * 2 * n_explicit, cudaMemcpyDeviceToDevice, st));
     } else {
       TOPO_CHECK(cudaMemcpyAsync(d_explicit, edge_nodes_host, sizeof(uint32_t) * 2 * n_explicit, cudaMemcpyHostToDevice, st));
     }
@@ -627,5 +629,131 @@ extern "C" int lfgpu_mesh_download(lfgpu_ctx* ctx, const lfgpu_mesh* m, uint8_t*
     cudaFree(d_ct);
   }
   LFGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+  return LFGPU_OK;
+}
+
+// ---- regular refinement with the reference's numbering -----------------------------------------------------------------
+// MeshHierarchy::RefineRegular (refinement/mesh_hierarchy.cc:72-114) -> PerformRefinement (:368-1262) for the all-regular
+// case, as a device-side mesh generator (the input of BASELINE config 4 at scale).  Numbering = order of the reference's
+// MeshFactory calls: nodes = copies, then edge midpoints in edge order, then quad centres in cell order; ALL edges
+// explicit: (p0, mid), (mid, p1) per parent edge, then per parent cell its interior edges; four children per cell.
+// Child corners are the parent map at lattice points / 6 (hybrid2d_refinement_pattern.cc, tria_o1.cc:99-151): for
+// straight-sided parents whose corners are node positions these are bitwise the new node positions, so the refined mesh
+// needs no separate cell corner array.  Products and sums are rounded separately like the host code (no FMA).
+namespace lfgpu {
+namespace {
+__global__ void k_ref_is_quad(int64_t n_cells, const uint32_t* __restrict__ cell_nodes, int32_t* __restrict__ is_quad) {
+  const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (c < n_cells) is_quad[c] = cell_nodes[4 * c + 3] != LFGPU_IDX_NIL ? 1 : 0;
+}
+__global__ void k_ref_nodes_edges(int64_t nn, int64_t ne, const double* __restrict__ xy, const uint32_t* __restrict__ edge_nodes,
+                                  double* __restrict__ xy_f, uint32_t* __restrict__ edges_f) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t < nn) {
+    xy_f[2 * t] = xy[2 * t];
+    xy_f[2 * t + 1] = xy[2 * t + 1];
+  } else if (t < nn + ne) {
+    const int64_t e = t - nn;
+    const uint32_t p0 = edge_nodes[2 * e], p1 = edge_nodes[2 * e + 1];
+    const double h = 1.0 / 6.0, s = h * 3.0;  // lattice constant 6, midpoint = lattice point 3
+    // SegmentO1::Global (segment_o1.cc:9-11): col(1) * t + col(0) * (1 - t)
+    xy_f[2 * t] = __dadd_rn(__dmul_rn(xy[2 * p1], s), __dmul_rn(xy[2 * p0], 1.0 - s));
+    xy_f[2 * t + 1] = __dadd_rn(__dmul_rn(xy[2 * p1 + 1], s), __dmul_rn(xy[2 * p0 + 1], 1.0 - s));
+    const uint32_t mid = static_cast<uint32_t>(t);
+    edges_f[4 * e] = p0;
+    edges_f[4 * e + 1] = mid;
+    edges_f[4 * e + 2] = mid;
+    edges_f[4 * e + 3] = p1;
+  }
+}
+__global__ void k_ref_cells(int64_t nc, int64_t nn, int64_t ne, const uint32_t* __restrict__ cell_nodes, const uint32_t* __restrict__ cell_edges,
+                            const int32_t* __restrict__ quads_before, const double* __restrict__ xy, double* __restrict__ xy_f,
+                            uint32_t* __restrict__ edges_f, uint32_t* __restrict__ cells_f) {
+  const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const uint32_t v[4] = {cell_nodes[4 * c], cell_nodes[4 * c + 1], cell_nodes[4 * c + 2], cell_nodes[4 * c + 3]};
+  const bool quad = v[3] != LFGPU_IDX_NIL;
+  const int64_t qb = quads_before[c], tb = c - qb;
+  uint32_t m[4];
+  for (int j = 0; j < (quad ? 4 : 3); ++j) m[j] = static_cast<uint32_t>(nn + cell_edges[4 * c + j]);
+  uint32_t* ed = edges_f + 2 * (2 * ne + 3 * tb + 4 * qb);  // interior edges of this cell
+  uint32_t* ch = cells_f + 16 * c;
+  if (!quad) {
+    // interior edges (m0,m2), (m0,m1), (m2,m1); children (v0,m0,m2), (v1,m0,m1), (v2,m2,m1), (m0,m1,m2)
+    ed[0] = m[0]; ed[1] = m[2]; ed[2] = m[0]; ed[3] = m[1]; ed[4] = m[2]; ed[5] = m[1];
+    const uint32_t t4[4][4] = {{v[0], m[0], m[2], LFGPU_IDX_NIL}, {v[1], m[0], m[1], LFGPU_IDX_NIL}, {v[2], m[2], m[1], LFGPU_IDX_NIL},
+                               {m[0], m[1], m[2], LFGPU_IDX_NIL}};
+    for (int k = 0; k < 4; ++k)
+      for (int l = 0; l < 4; ++l) ch[4 * k + l] = t4[k][l];
+  } else {
+    const uint32_t ctr = static_cast<uint32_t>(nn + ne + qb);
+    // QuadO1::Global at (1/2, 1/2) (quad_o1.cc:68-83): c0 (1-x0)(1-x1) + c1 x0 (1-x1) + c2 x0 x1 + c3 (1-x0) x1
+    const double h = 1.0 / 6.0, x0 = h * 3.0, x1 = h * 3.0;
+    const double w0 = __dmul_rn(1.0 - x0, 1.0 - x1), w1 = __dmul_rn(x0, 1.0 - x1), w2 = __dmul_rn(x0, x1), w3 = __dmul_rn(1.0 - x0, x1);
+    for (int d = 0; d < 2; ++d) {
+      double s = __dmul_rn(xy[2 * v[0] + d], w0);
+      s = __dadd_rn(s, __dmul_rn(xy[2 * v[1] + d], w1));
+      s = __dadd_rn(s, __dmul_rn(xy[2 * v[2] + d], w2));
+      s = __dadd_rn(s, __dmul_rn(xy[2 * v[3] + d], w3));
+      xy_f[2 * static_cast<int64_t>(ctr) + d] = s;
+    }
+    for (int k = 0; k < 4; ++k) {
+      ed[2 * k] = m[k];
+      ed[2 * k + 1] = ctr;
+    }
+    const uint32_t q4[4][4] = {{v[0], m[0], ctr, m[3]}, {v[1], m[1], ctr, m[0]}, {v[2], m[1], ctr, m[2]}, {v[3], m[2], ctr, m[3]}};
+    for (int k = 0; k < 4; ++k)
+      for (int l = 0; l < 4; ++l) ch[4 * k + l] = q4[k][l];
+  }
+}
+}  // namespace
+}  // namespace lfgpu
+
+extern "C" int lfgpu_mesh_refine_regular(lfgpu_ctx* ctx, lfgpu_mesh* parent, lfgpu_mesh** out) {
+  if (ctx == nullptr || parent == nullptr || out == nullptr) return LFGPU_ERR_INVALID;
+  *out = nullptr;
+  if (parent->cell_coords != nullptr) LFGPU_FAIL(ctx, LFGPU_ERR_UNSUPPORTED, "parent carries explicit cell corner coordinates: refine on the host and upload");
+  int rc = ensure_topology(ctx, parent);
+  if (rc != LFGPU_OK) return rc;
+  cudaStream_t st = ctx->stream;
+  const int64_t nn = parent->n_nodes, ne = parent->n_edges, nc = parent->n_cells, nt = parent->n_tria, nq = parent->n_quad;
+  const int64_t nn_f = nn + ne + nq, ne_f = 2 * ne + 3 * nt + 4 * nq, nc_f = 4 * nc;
+  lfgpu_mesh* m = nullptr;
+  if ((rc = alloc_mesh(ctx, nn_f, nc_f, false, &m)) != LFGPU_OK) return rc;
+  int32_t *is_quad = nullptr, *quads_before = nullptr;
+  uint32_t* edges_f = nullptr;
+  void* tmp = nullptr;
+  auto cleanup = [&]() { cudaFree(is_quad); cudaFree(quads_before); cudaFree(edges_f); cudaFree(tmp); };
+  cudaError_t e = cudaMalloc(&is_quad, sizeof(int32_t) * nc);
+  if (e == cudaSuccess) e = cudaMalloc(&quads_before, sizeof(int32_t) * nc);
+  if (e == cudaSuccess) e = cudaMalloc(&edges_f, sizeof(uint32_t) * 2 * ne_f);
+  if (e == cudaSuccess) {
+    k_ref_is_quad<<<static_cast<unsigned>(cdiv(nc, kThreads)), kThreads, 0, st>>>(nc, parent->cell_nodes, is_quad);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, is_quad, quads_before, static_cast<int>(nc), st);
+    e = cudaMalloc(&tmp, tb);
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tb, is_quad, quads_before, static_cast<int>(nc), st);
+  }
+  if (e == cudaSuccess) {
+    k_ref_nodes_edges<<<static_cast<unsigned>(cdiv(nn + ne, kThreads)), kThreads, 0, st>>>(nn, ne, parent->node_coords, parent->edge_nodes,
+                                                                                          m->node_coords, edges_f);
+    k_ref_cells<<<static_cast<unsigned>(cdiv(nc, kThreads)), kThreads, 0, st>>>(nc, nn, ne, parent->cell_nodes, parent->cell_edges, quads_before,
+                                                                               parent->node_coords, m->node_coords, edges_f, m->cell_nodes);
+    ctx->launches += 3;
+    e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) {
+    cleanup();
+    lfgpu_mesh_destroy(m);
+    LFGPU_FAIL(ctx, LFGPU_ERR_CUDA, std::string("mesh_refine_regular: ") + cudaGetErrorString(e));
+  }
+  rc = finish_mesh(ctx, m);
+  if (rc == LFGPU_OK) rc = build_topology_impl(ctx, m, ne_f, nullptr, false, nullptr, edges_f);
+  cleanup();
+  if (rc != LFGPU_OK) {
+    lfgpu_mesh_destroy(m);
+    return rc;
+  }
+  *out = m;
   return LFGPU_OK;
 }

@@ -46,6 +46,8 @@ def lib():
         L.lfo_mesh_from_arrays.restype = C.c_void_p
         L.lfo_mesh_from_arrays.argtypes = [C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_int64, C.c_void_p]
+        L.lfo_mesh_refine_regular.restype = C.c_void_p
+        L.lfo_mesh_refine_regular.argtypes = [C.c_void_p]
         L.lfo_mesh_free.argtypes = [C.c_void_p]
         L.lfo_mesh_counts.argtypes = [C.c_void_p] + [C.POINTER(C.c_int64)] * 5
         L.lfo_mesh_export.argtypes = [C.c_void_p] * 8
@@ -187,6 +189,10 @@ class Mesh:
     @staticmethod
     def hybrid(n, jitter=0.2, seed=12345):
         return Mesh(lib().lfo_mesh_hybrid(n, jitter, seed))
+
+    def refine_regular(self):
+        """MeshHierarchy::RefineRegular(): the regularly refined mesh with the reference's numbering."""
+        return Mesh(lib().lfo_mesh_refine_regular(self.h))
 
     @staticmethod
     def from_arrays(node_xy, cell_nodes, cell_coords=None, cell_geo=None, edge_nodes=None):

@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <string>
 
+#include "lfo_refinement.h"
 #include "lfo_uscalfe.h"
 
 using namespace lfo;
@@ -150,6 +151,14 @@ void* lfo_mesh_from_arrays(std::int64_t n_nodes, const double* xy, std::int64_t 
     }
   }
   return new MeshH{f.Build()};
+  LFO_CATCH(nullptr)
+}
+// MeshHierarchy::RefineRegular() + getMesh(finest): one regular refinement step with the reference's numbering
+void* lfo_mesh_refine_regular(void* h) {
+  LFO_TRY
+  auto m = refinement::RefineRegular(*static_cast<MeshH*>(h)->mesh);
+  if (!m) throw LfException("empty mesh");
+  return new MeshH{m};
   LFO_CATCH(nullptr)
 }
 void lfo_mesh_free(void* h) { delete static_cast<MeshH*>(h); }
