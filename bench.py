@@ -34,6 +34,10 @@ WORKLOADS = {
     "c2": ("C2: P1 reaction-diffusion, alpha=1+|x|^2, gamma=1/(1+|x|^2) per quadrature point, hybrid tri/quad mesh n=1633 (4.0e6 cells), CSR", "hybrid", 1633, 1),
     "c3": ("C3: P2 Laplacian, TP-triangle mesh n=2828 (1.6e7 cells), CSR", "tp_tria", 2828, 2),
     "c4s": ("C4 (single-GPU size): P3 stiffness+mass, TP-triangle mesh n=1448 (4.2e6 cells), CSR", "tp_tria", 1448, 3),
+    "c4": ("C4 (single-GPU size): P3 stiffness+mass on a MeshHierarchy-refined mesh: TP-triangle mesh n=181, 3 x RefineRegular "
+           "(4.2e6 cells), CSR", "refined:3", 181, 3),
+    "c4_32m": ("C4: P3 stiffness+mass on a MeshHierarchy-refined mesh: TP-triangle mesh n=250, 4 x RefineRegular (3.2e7 cells), CSR",
+               "refined:4", 250, 3),
 }
 
 
@@ -208,6 +212,11 @@ def main():
     t_setup = time.time()
     if kind == "tp_tria":
         mesh = ctx.mesh_tp_tria(n, n)
+    elif kind.startswith("refined:"):
+        # MeshHierarchy-refined mesh (BASELINE config 4): builder mesh + regular refinement steps with the reference's numbering
+        mesh = ctx.mesh_tp_tria(n, n)
+        for _ in range(int(kind.split(":")[1])):
+            mesh = mesh.refine_regular()
     else:
         mesh = ctx.mesh_hybrid(n, 0.2, 12345)
     dm = mesh.dofmap_lagrange(degree)
@@ -222,7 +231,7 @@ def main():
         alpha = lf.Coeff.per_qp(ctx.to_device(1.0 + r2), stride)
         gamma = lf.Coeff.per_qp(ctx.to_device(1.0 / (1.0 + r2)), stride)
         coef_bytes = 2 * 8.0 * (3 * mesh.n_tria + 4 * mesh.n_quad)
-    elif args.workload == "c4s":
+    elif args.workload in ("c4s", "c4", "c4_32m"):
         alpha, gamma, coef_bytes = lf.Coeff.const(1.0), lf.Coeff.const(1.0), 0.0
     else:
         alpha, gamma, coef_bytes = lf.Coeff.const(1.0), lf.Coeff.const(0.0), 0.0
