@@ -6,6 +6,8 @@
 // SpMV: a group of LANES threads per outer index (LANES = 1..32, chosen from the mean segment length) walks the
 // segment with coalesced loads and reduces with shuffles; the compressed-column layout (Eigen's default) scatters with
 // FP64 atomics instead.  Dot products are two-stage with a fixed grid, hence bitwise repeatable.
+#include <cstdlib>
+
 #include "lfgpu_internal.cuh"
 
 namespace lfgpu {
@@ -117,9 +119,13 @@ int spmv(lfgpu_ctx* ctx, const lfgpu_pattern* p, const double* d_values, const d
   const int64_t n = p->n_outer;
   if (p->major == LFGPU_ROW_MAJOR || treat_outer_as_rows) {
     const double mean = n > 0 ? static_cast<double>(p->nnz) / static_cast<double>(n) : 0.0;
-    const int lanes = mean <= 6 ? 2 : (mean <= 12 ? 4 : (mean <= 24 ? 8 : (mean <= 48 ? 16 : 32)));
+    static const int lanes_env = [] { const char* e = std::getenv("LFGPU_SPMV_LANES"); return e != nullptr ? std::atoi(e) : 0; }();
+    // measured at 7 entries per row (3.5e8 entries): 2 lanes 0.97 ms, 4 lanes 1.55 ms, 8 lanes 2.53 ms -> few lanes, long segments
+    int lanes = mean <= 4 ? 1 : (mean <= 10 ? 2 : (mean <= 20 ? 4 : (mean <= 40 ? 8 : (mean <= 80 ? 16 : 32))));
+    if (lanes_env == 1 || lanes_env == 2 || lanes_env == 4 || lanes_env == 8 || lanes_env == 16 || lanes_env == 32) lanes = lanes_env;
     const unsigned grid = static_cast<unsigned>(cdiv(n * lanes, kThreads));
     switch (lanes) {
+      case 1: k_spmv_rows<1><<<grid, kThreads, 0, st>>>(n, p->outer, p->inner, d_values, d_x, d_y); break;
       case 2: k_spmv_rows<2><<<grid, kThreads, 0, st>>>(n, p->outer, p->inner, d_values, d_x, d_y); break;
       case 4: k_spmv_rows<4><<<grid, kThreads, 0, st>>>(n, p->outer, p->inner, d_values, d_x, d_y); break;
       case 8: k_spmv_rows<8><<<grid, kThreads, 0, st>>>(n, p->outer, p->inner, d_values, d_x, d_y); break;
