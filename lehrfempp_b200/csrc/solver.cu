@@ -120,8 +120,8 @@ int spmv(lfgpu_ctx* ctx, const lfgpu_pattern* p, const double* d_values, const d
   if (p->major == LFGPU_ROW_MAJOR || treat_outer_as_rows) {
     const double mean = n > 0 ? static_cast<double>(p->nnz) / static_cast<double>(n) : 0.0;
     static const int lanes_env = [] { const char* e = std::getenv("LFGPU_SPMV_LANES"); return e != nullptr ? std::atoi(e) : 0; }();
-    // measured at 7 entries per row (3.5e8 entries): 2 lanes 0.97 ms, 4 lanes 1.55 ms, 8 lanes 2.53 ms -> few lanes, long segments
-    int lanes = mean <= 4 ? 1 : (mean <= 10 ? 2 : (mean <= 20 ? 4 : (mean <= 40 ? 8 : (mean <= 80 ? 16 : 32))));
+    // measured at 7 entries per row (3.5e8 entries): 1 lane 0.85 ms, 2 lanes 0.97 ms, 4 lanes 1.55 ms, 8 lanes 2.53 ms
+    int lanes = mean <= 10 ? 1 : (mean <= 20 ? 2 : (mean <= 40 ? 4 : (mean <= 80 ? 8 : (mean <= 160 ? 16 : 32))));
     if (lanes_env == 1 || lanes_env == 2 || lanes_env == 4 || lanes_env == 8 || lanes_env == 16 || lanes_env == 32) lanes = lanes_env;
     const unsigned grid = static_cast<unsigned>(cdiv(n * lanes, kThreads));
     switch (lanes) {
