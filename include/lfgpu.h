@@ -124,6 +124,12 @@ int lfgpu_dofmap_upload(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, int64_t n_dofs, 
 int lfgpu_dofmap_uniform(lfgpu_ctx* ctx, lfgpu_mesh* mesh, int n_pt, int n_seg, int n_tria, int n_quad, lfgpu_dofmap** out);
 /* dof layout of lf::uscalfe::FeSpaceLagrangeO{1,2,3} (uscalfe/uniform_scalar_fe_space.h:241-342) */
 int lfgpu_dofmap_lagrange(lfgpu_ctx* ctx, lfgpu_mesh* mesh, int degree, lfgpu_dofmap** out);
+/* lf::assemble::DynamicFEDofHandler(mesh, locdof) (assemble/dofhandler.h:514-789): variable numbers of interior dofs,
+ * numbered on the device.  The LOCALDOFINFO functor is passed tabulated: n_int_node [n_nodes], n_int_edge [n_edges],
+ * n_int_cell [n_cells] host arrays = locdof(entity) in entity-index order; NULL = 0 for that codimension.  A cell may
+ * carry at most 16 local dofs (LFGPU_ERR_UNSUPPORTED otherwise).  The table stride is the longest cell list.           */
+int lfgpu_dofmap_dynamic(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const uint32_t* n_int_node, const uint32_t* n_int_edge,
+                         const uint32_t* n_int_cell, lfgpu_dofmap** out);
 int64_t lfgpu_dofmap_num_dofs(const lfgpu_dofmap* d);
 int lfgpu_dofmap_stride(const lfgpu_dofmap* d);
 int lfgpu_dofmap_download(lfgpu_ctx* ctx, const lfgpu_dofmap* d, int64_t* cell_dofs, uint8_t* n_ldof);
@@ -181,7 +187,9 @@ int lfgpu_assemble_reaction_diffusion_rows(lfgpu_ctx* ctx, const lfgpu_mesh* mes
                                            const lfgpu_coeff* gamma, const uint8_t* active, double beta, double* d_values,
                                            int algo, const int32_t* d_row_list, int64_t n_rows);
 /* lf::uscalfe::ScalarLoadElementVectorProvider<double,F>::Eval (loc_comp_ellbvp.h:691-746) + AssembleVectorLocally's
- * scatter (assembler.h:322-324).  d_vec: device array [n_dofs].                                                      */
+ * scatter (assembler.h:322-324).  d_vec: device array [n_dofs].  algo: LFGPU_ALGO_ATOMIC (= AUTO) one thread per cell
+ * and FP64 atomics; LFGPU_ALGO_GATHER one thread per dof adding its cells' entries in ascending cell order, i.e. the
+ * reference's order of additions (deterministic; the per-dof lists are built on first use and cached in the dofmap). */
 int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* dofmap, int degree,
                         const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad, const lfgpu_coeff* f, const uint8_t* active,
                         double beta, double* d_vec, int algo);

@@ -86,6 +86,7 @@ def _lib():
         "lfgpu_dofmap_upload": (i32, [vp, vp, i64, i32, vp, vp, pp]),
         "lfgpu_dofmap_uniform": (i32, [vp, vp, i32, i32, i32, i32, pp]),
         "lfgpu_dofmap_lagrange": (i32, [vp, vp, i32, pp]),
+        "lfgpu_dofmap_dynamic": (i32, [vp, vp, vp, vp, vp, pp]),
         "lfgpu_dofmap_num_dofs": (i64, [vp]),
         "lfgpu_dofmap_stride": (i32, [vp]),
         "lfgpu_dofmap_download": (i32, [vp, vp, vp, vp]),
@@ -450,6 +451,18 @@ class Mesh:
         self._refresh()
         return DofMap(self, h)
 
+    def dofmap_dynamic(self, n_int_node=None, n_int_edge=None, n_int_cell=None):
+        """DynamicFEDofHandler(mesh, locdof), locdof tabulated per node / edge / cell (uint32 host arrays, None = 0)."""
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.uint32) for a in (n_int_node, n_int_edge, n_int_cell)]
+        if arrs[1] is not None and self.n_edges == 0:
+            self.build_topology()
+        for a, n in zip(arrs, (self.n_nodes, self.n_edges, self.n_cells)):
+            assert a is None or a.shape == (n,), "one count per entity"
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.L.lfgpu_dofmap_dynamic(self.ctx.h, self.h, _p(arrs[0]), _p(arrs[1]), _p(arrs[2]), C.byref(h)))
+        self._refresh()
+        return DofMap(self, h)
+
     def dofmap_upload(self, n_dofs, cell_dofs, n_ldof=None):
         cell_dofs = np.ascontiguousarray(cell_dofs, dtype=np.int64)
         assert cell_dofs.shape[0] == self.n_cells
@@ -500,12 +513,12 @@ class DofMap:
                                                            active_edges.ptr if active_edges is not None else None, out.ptr))
         return out
 
-    def assemble_load(self, degree, f, qr_tria=None, qr_quad=None, active=None, beta=0.0, out=None):
+    def assemble_load(self, degree, f, qr_tria=None, qr_quad=None, active=None, beta=0.0, out=None, algo=ALGO_AUTO):
         """AssembleVectorLocally(0, dofh, ScalarLoadElementVectorProvider(fe_space, f), vec)."""
         if out is None:
             out = self.ctx.zeros(self.num_dofs)
         self.ctx.check(self.ctx.L.lfgpu_assemble_load(self.ctx.h, self.mesh.h, self.h, degree, _qref(qr_tria), _qref(qr_quad),
-                                                      f.ref(), active.ptr if active is not None else None, beta, out.ptr, ALGO_AUTO))
+                                                      f.ref(), active.ptr if active is not None else None, beta, out.ptr, algo))
         return out
 
 

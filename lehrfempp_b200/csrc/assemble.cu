@@ -616,6 +616,45 @@ __global__ void __launch_bounds__(256) k_load_atomic(Tables hdr, const double* _
   }
 }
 
+// load vector, owner-computes: one thread per dof walks its (cell, local index) items in ascending cell order and adds
+// the entries phi_K[a] = sum_k w_k |det J_k| f(x_k) phi_a(x_k) in that order -- result[dof] += elem_vec[a] of
+// assembler.h:322-324 with the additions in the reference's order: no atomics, no zero-fill, bitwise repeatable.
+// Every cell is visited once per local dof; the load vector is a small part of the traffic of the path.
+__global__ void __launch_bounds__(256) k_load_gather(Tables hdr, const double* __restrict__ blob, MeshView mv, int64_t n_dofs,
+                                                     const int32_t* __restrict__ ptr, const uint32_t* __restrict__ items, DevCoeff f,
+                                                     const uint8_t* __restrict__ active, double beta, double* __restrict__ vec,
+                                                     int* __restrict__ flags) {
+  extern __shared__ double smem[];
+  TabView tt, tq;
+  load_tables(hdr, blob, smem, tt, tq);
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= n_dofs) return;
+  double sum = (beta == 0.0) ? 0.0 : beta * vec[r];
+  const int32_t t1 = ptr[r + 1];
+  for (int32_t t = ptr[r]; t < t1; ++t) {
+    const uint32_t item = __ldg(items + t);
+    const int64_t cell = item >> 4;
+    const int a = static_cast<int>(item & 15U);
+    if (active != nullptr && active[cell] == 0) continue;
+    const CellGeom g = load_geom(mv, cell);
+    const TabView& T = g.quad ? tq : tt;
+    if (T.nsf == 0) {
+      flags[0] = 1;
+      continue;
+    }
+    double j00, j01, j10, j11;
+    if (!g.quad) jacobian(g, 0.0, 0.0, j00, j01, j10, j11);
+    double e = 0.0;
+    for (int k = 0; k < T.nq; ++k) {
+      if (g.quad) jacobian(g, T.qx[k], T.qy[k], j00, j01, j10, j11);
+      const double s = T.w[k] * fabs(j00 * j11 - j01 * j10) * eval_scalar(f, cell, k);
+      e += s * T.phi[a * T.nq + k];
+    }
+    sum += e;
+  }
+  vec[r] = sum;
+}
+
 __global__ void k_qp_coords(Tables hdr, const double* __restrict__ blob, MeshView mv, int64_t n_cells, int nq_stride, double* __restrict__ out) {
   extern __shared__ double smem[];
   TabView tt, tq;
@@ -946,7 +985,8 @@ int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofm
   if (ctx == nullptr || mesh == nullptr || dofmap == nullptr || d_vec == nullptr) return LFGPU_ERR_INVALID;
   if (degree < 1 || degree > 3) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "degree must be 1, 2 or 3");
   if (dofmap->n_cells != mesh->n_cells) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "dofmap was built for another mesh");
-  (void)algo;
+  if (algo != LFGPU_ALGO_AUTO && algo != LFGPU_ALGO_ATOMIC && algo != LFGPU_ALGO_GATHER)
+    LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "load vector: algo must be AUTO, ATOMIC or GATHER");
   LFGPU_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
   HostTables ht;
   int rc = make_tables(ctx, degree, qr_tria, qr_quad, &ht);
@@ -957,6 +997,16 @@ int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofm
   DeviceBlob blob;
   if ((rc = upload_blob(ctx, ht, &blob)) != LFGPU_OK) return rc;
   int* d_flags = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 128);
+  if (algo == LFGPU_ALGO_GATHER) {
+    // deterministic owner-computes variant (AUTO stays on the atomic kernel until the two are measured side by side)
+    if ((rc = dofmap_gather_plan(ctx, dofmap)) != LFGPU_OK) return rc;
+    const MeshView mvg{mesh->node_coords, mesh->cell_nodes, mesh->cell_coords};
+    const size_t tbg = sizeof(double) * ((ht.hdr.total + 1) & ~1);
+    k_load_gather<<<static_cast<unsigned>(cdiv(dofmap->n_dofs, 256)), 256, tbg, ctx->stream>>>(
+        ht.hdr, blob.d, mvg, dofmap->n_dofs, dofmap->g_ptr, dofmap->g_items, df, active, beta, d_vec, d_flags);
+    LFGPU_LAUNCH_CHECK(ctx);
+    return LFGPU_OK;
+  }
   if (beta == 0.0) {
     LFGPU_CUDA_CHECK(ctx, cudaMemsetAsync(d_vec, 0, sizeof(double) * dofmap->n_dofs, ctx->stream));
   } else if (beta != 1.0) {

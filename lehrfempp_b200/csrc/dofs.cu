@@ -75,6 +75,98 @@ __global__ void k_convert_dofs(int64_t n, int stride, const int64_t* __restrict_
   nl_out[c] = static_cast<uint8_t>(cnt);
 }
 
+// ---- DynamicFEDofHandler (dofhandler.h:514-789): per-entity numbers of interior dofs ---------------------------------
+// counts widened to int64 with a trailing 0, so that an exclusive scan over n + 1 entries also yields the total
+__global__ void k_widen_counts(int64_t n, const uint32_t* __restrict__ in, int64_t* __restrict__ out, int* __restrict__ flags) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  const uint32_t v = (i < n && in != nullptr) ? in[i] : 0U;
+  if (v > static_cast<uint32_t>(kMaxNsf)) flags[0] = 1;
+  out[i] = v;
+}
+
+// length of every cell's dof list and its maximum (= row length of the table)
+__global__ void k_dynamic_lengths(int64_t n_cells, const uint32_t* __restrict__ cell_nodes, const uint32_t* __restrict__ cell_edges,
+                                  const int64_t* __restrict__ node_off, const int64_t* __restrict__ edge_off,
+                                  const int64_t* __restrict__ cell_off, int* __restrict__ max_len) {
+  const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  int len = 0;
+  if (c < n_cells) {
+    const uint4 v = reinterpret_cast<const uint4*>(cell_nodes)[c];
+    const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+    const int nv = (v.w == LFGPU_IDX_NIL) ? 3 : 4;
+    for (int l = 0; l < nv; ++l) {
+      len += static_cast<int>(node_off[vv[l] + 1] - node_off[vv[l]]);
+      if (edge_off != nullptr) {
+        const uint32_t e = cell_edges[4 * c + l];
+        len += static_cast<int>(edge_off[e + 1] - edge_off[e]);
+      }
+    }
+    len += static_cast<int>(cell_off[c + 1] - cell_off[c]);
+  }
+  len = __reduce_max_sync(0xffffffffU, len);
+  if ((threadIdx.x & 31) == 0) atomicMax(max_len, len);
+}
+
+// one thread per cell writes its list: vertex dofs | edge-interior dofs per local edge, reversed for a negative relative
+// orientation (dofhandler.h:669-688) | own interior dofs
+__global__ void k_dynamic_dofs(int64_t n_cells, const uint32_t* __restrict__ cell_nodes, const uint32_t* __restrict__ cell_edges,
+                               const int8_t* __restrict__ cell_edge_ori, const int64_t* __restrict__ node_off,
+                               const int64_t* __restrict__ edge_off, const int64_t* __restrict__ cell_off, int64_t edge_dof_base,
+                               int64_t cell_dof_base, int stride, int32_t* __restrict__ cell_dofs, uint8_t* __restrict__ n_ldof) {
+  const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (c >= n_cells) return;
+  const uint4 v = reinterpret_cast<const uint4*>(cell_nodes)[c];
+  const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+  const int nv = (v.w == LFGPU_IDX_NIL) ? 3 : 4;
+  int32_t* out = cell_dofs + c * stride;
+  int k = 0;
+  for (int l = 0; l < nv; ++l) {
+    const int64_t b = node_off[vv[l]], e = node_off[vv[l] + 1];
+    for (int64_t d = b; d < e && k < stride; ++d) out[k++] = static_cast<int32_t>(d);
+  }
+  if (edge_off != nullptr) {
+    for (int l = 0; l < nv; ++l) {
+      const uint32_t ed = cell_edges[4 * c + l];
+      const int64_t b = edge_dof_base + edge_off[ed], e = edge_dof_base + edge_off[ed + 1];
+      if (cell_edge_ori[4 * c + l] > 0) {
+        for (int64_t d = b; d < e && k < stride; ++d) out[k++] = static_cast<int32_t>(d);
+      } else {
+        for (int64_t d = e - 1; d >= b && k < stride; --d) out[k++] = static_cast<int32_t>(d);
+      }
+    }
+  }
+  {
+    const int64_t b = cell_dof_base + cell_off[c], e = cell_dof_base + cell_off[c + 1];
+    for (int64_t d = b; d < e && k < stride; ++d) out[k++] = static_cast<int32_t>(d);
+  }
+  n_ldof[c] = static_cast<uint8_t>(k);
+  for (; k < stride; ++k) out[k] = -1;
+}
+
+// ---- gather plan of the load vector ------------------------------------------------------------------------------------
+__global__ void k_plan_items(int64_t n_cells, int stride, const int32_t* __restrict__ dofs, const uint8_t* __restrict__ nldof,
+                             int32_t invalid_key, int32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= n_cells * stride) return;
+  const int64_t c = t / stride;
+  const int a = static_cast<int>(t - c * stride);
+  keys[t] = (a < nldof[c]) ? dofs[t] : invalid_key;  // unused slots sort behind every dof
+  vals[t] = (static_cast<uint32_t>(c) << 4) | static_cast<uint32_t>(a);
+}
+
+// ptr[r] = number of sorted keys < r, r = 0 .. n_dofs
+__global__ void k_plan_ptr(int64_t n_dofs, int64_t n_keys, const int32_t* __restrict__ keys, int32_t* __restrict__ ptr) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r > n_dofs) return;
+  int64_t lo = 0, hi = n_keys;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (keys[mid] < r) lo = mid + 1; else hi = mid;
+  }
+  ptr[r] = static_cast<int32_t>(lo);
+}
+
 __global__ void k_dofs_to_i64(int64_t n, const int32_t* __restrict__ in, int64_t* __restrict__ out) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) out[i] = in[i];
@@ -82,6 +174,57 @@ __global__ void k_dofs_to_i64(int64_t n, const int32_t* __restrict__ in, int64_t
 
 }  // namespace
 }  // namespace lfgpu
+
+// Items (dof, cell << 4 | a) sorted stably by dof: the slots are generated in (cell, a) order, so the items of a dof end
+// up in ascending cell order -- the order of the reference's cell loop.
+int lfgpu::dofmap_gather_plan(lfgpu_ctx* ctx, const lfgpu_dofmap* dc) {
+  lfgpu_dofmap* d = const_cast<lfgpu_dofmap*>(dc);
+  if (d->g_state == 1) return LFGPU_OK;
+  if (d->n_cells >= (1LL << 28)) LFGPU_FAIL(ctx, LFGPU_ERR_OVERFLOW, "gather plan: more than 2^28 cells");
+  cudaStream_t st = ctx->stream;
+  const int64_t n_slots = d->n_cells * d->stride;
+  int32_t *keys_in = nullptr, *keys_out = nullptr;
+  uint32_t *vals_in = nullptr, *vals_out = nullptr;
+  int32_t* ptr = nullptr;
+  void* tmp = nullptr;
+  cudaError_t e = cudaMalloc(&keys_in, sizeof(int32_t) * n_slots);
+  if (e == cudaSuccess) e = cudaMalloc(&keys_out, sizeof(int32_t) * n_slots);
+  if (e == cudaSuccess) e = cudaMalloc(&vals_in, sizeof(uint32_t) * n_slots);
+  if (e == cudaSuccess) e = cudaMalloc(&vals_out, sizeof(uint32_t) * n_slots);
+  if (e == cudaSuccess) e = cudaMalloc(&ptr, sizeof(int32_t) * (d->n_dofs + 1));
+  if (e == cudaSuccess) {
+    k_plan_items<<<static_cast<unsigned>(cdiv(n_slots, kThreads)), kThreads, 0, st>>>(d->n_cells, d->stride, d->cell_dofs, d->n_ldof,
+                                                                                     static_cast<int32_t>(d->n_dofs), keys_in, vals_in);
+    ctx->launches++;
+    int key_bits = 1;
+    while ((1LL << key_bits) <= d->n_dofs) ++key_bits;
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, keys_in, keys_out, vals_in, vals_out, n_slots, 0, key_bits, st);
+    e = cudaMalloc(&tmp, tb);
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tb, keys_in, keys_out, vals_in, vals_out, n_slots, 0, key_bits, st);
+  }
+  int32_t n_items = 0;
+  if (e == cudaSuccess) {
+    k_plan_ptr<<<static_cast<unsigned>(cdiv(d->n_dofs + 1, kThreads)), kThreads, 0, st>>>(d->n_dofs, n_slots, keys_out, ptr);
+    ctx->launches++;
+    e = cudaMemcpyAsync(&n_items, ptr + d->n_dofs, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(keys_in);
+  cudaFree(keys_out);
+  cudaFree(vals_in);
+  cudaFree(tmp);
+  if (e != cudaSuccess) {
+    cudaFree(vals_out);
+    cudaFree(ptr);
+    LFGPU_FAIL(ctx, LFGPU_ERR_CUDA, std::string("dofmap gather plan: ") + cudaGetErrorString(e));
+  }
+  d->g_ptr = ptr;
+  d->g_items = vals_out;  // the first n_items entries are the used slots
+  d->g_n_items = n_items;
+  d->g_state = 1;
+  return LFGPU_OK;
+}
 
 using namespace lfgpu;
 
@@ -95,6 +238,8 @@ void lfgpu_dofmap_destroy(lfgpu_dofmap* d) {
   }
   cudaFree(d->cell_dofs);
   cudaFree(d->n_ldof);
+  cudaFree(d->g_ptr);
+  cudaFree(d->g_items);
   delete d;
 }
 
@@ -203,6 +348,108 @@ int lfgpu_dofmap_uniform(lfgpu_ctx* ctx, lfgpu_mesh* mesh, int n_pt, int n_seg, 
     lfgpu_dofmap_destroy(d);
     LFGPU_FAIL(ctx, LFGPU_ERR_CUDA, std::string("dofmap_uniform: ") + cudaGetErrorString(e));
   }
+  *out = d;
+  return LFGPU_OK;
+}
+
+int lfgpu_dofmap_dynamic(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const uint32_t* n_int_node, const uint32_t* n_int_edge,
+                         const uint32_t* n_int_cell, lfgpu_dofmap** out) {
+  if (ctx == nullptr || mesh == nullptr || out == nullptr) return LFGPU_ERR_INVALID;
+  *out = nullptr;
+  LFGPU_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  if (n_int_edge != nullptr) {
+    const int rc = ensure_topology(ctx, mesh);
+    if (rc != LFGPU_OK) return rc;
+  }
+  cudaStream_t st = ctx->stream;
+  const int64_t n_ent[3] = {mesh->n_nodes, n_int_edge != nullptr ? mesh->n_edges : 0, mesh->n_cells};
+  const uint32_t* h_cnt[3] = {n_int_node, n_int_edge, n_int_cell};
+  uint32_t* d_cnt[3] = {nullptr, nullptr, nullptr};
+  int64_t* d_wide[3] = {nullptr, nullptr, nullptr};
+  int64_t* d_off[3] = {nullptr, nullptr, nullptr};
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0;
+  lfgpu_dofmap* d = nullptr;
+  auto cleanup = [&]() {
+    for (int k = 0; k < 3; ++k) {
+      cudaFree(d_cnt[k]);
+      cudaFree(d_wide[k]);
+      cudaFree(d_off[k]);
+    }
+    cudaFree(tmp);
+  };
+#define DYN_CHECK(expr)                                                                  \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      set_last_error(ctx, std::string("dofmap_dynamic: ") + cudaGetErrorString(_e));     \
+      cleanup();                                                                         \
+      lfgpu_dofmap_destroy(d);                                                           \
+      return LFGPU_ERR_CUDA;                                                             \
+    }                                                                                    \
+  } while (0)
+  int* d_flags = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 64);
+  DYN_CHECK(cudaMemsetAsync(d_flags, 0, 64, st));
+  int64_t totals[3] = {0, 0, 0};
+  for (int k = 0; k < 3; ++k) {
+    const int64_t n = n_ent[k];
+    if (h_cnt[k] != nullptr && n > 0) {
+      DYN_CHECK(cudaMalloc(&d_cnt[k], sizeof(uint32_t) * n));
+      DYN_CHECK(cudaMemcpyAsync(d_cnt[k], h_cnt[k], sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+    }
+    DYN_CHECK(cudaMalloc(&d_wide[k], sizeof(int64_t) * (n + 1)));
+    DYN_CHECK(cudaMalloc(&d_off[k], sizeof(int64_t) * (n + 1)));
+    k_widen_counts<<<static_cast<unsigned>(cdiv(n + 1, kThreads)), kThreads, 0, st>>>(n, d_cnt[k], d_wide[k], d_flags);
+    ctx->launches++;
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, d_wide[k], d_off[k], n + 1, st);
+    if (tb > tmp_bytes) {
+      DYN_CHECK(cudaStreamSynchronize(st));
+      cudaFree(tmp);
+      tmp = nullptr;
+      DYN_CHECK(cudaMalloc(&tmp, tb));
+      tmp_bytes = tb;
+    }
+    DYN_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_wide[k], d_off[k], n + 1, st));
+    DYN_CHECK(cudaMemcpyAsync(&totals[k], d_off[k] + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  }
+  k_dynamic_lengths<<<static_cast<unsigned>(cdiv(mesh->n_cells, kThreads)), kThreads, 0, st>>>(
+      mesh->n_cells, mesh->cell_nodes, mesh->cell_edges, d_off[0], n_int_edge != nullptr ? d_off[1] : nullptr, d_off[2], d_flags + 1);
+  ctx->launches++;
+  int h_flags[2] = {0, 0};
+  DYN_CHECK(cudaMemcpyAsync(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+  DYN_CHECK(cudaStreamSynchronize(st));
+  const int stride = h_flags[1];
+  if (h_flags[0] != 0 || stride > kMaxNsf) {
+    cleanup();
+    LFGPU_FAIL(ctx, LFGPU_ERR_UNSUPPORTED, "a cell may carry at most 16 local dofs");
+  }
+  const int64_t n_dofs = totals[0] + totals[1] + totals[2];
+  if (n_dofs < 1 || stride < 1) {
+    cleanup();
+    LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "the layout assigns no dofs");
+  }
+  if (n_dofs >= (1LL << 31)) {
+    cleanup();
+    LFGPU_FAIL(ctx, LFGPU_ERR_OVERFLOW, "n_dofs does not fit the int32 storage index");
+  }
+  d = new lfgpu_dofmap;
+  d->ctx = ctx;
+  d->n_cells = mesh->n_cells;
+  d->n_dofs = n_dofs;
+  d->stride = stride;
+  d->max_ldof = stride;
+  d->n_nodes = mesh->n_nodes;
+  DYN_CHECK(cudaMalloc(&d->cell_dofs, sizeof(int32_t) * mesh->n_cells * stride));
+  DYN_CHECK(cudaMalloc(&d->n_ldof, mesh->n_cells));
+  k_dynamic_dofs<<<static_cast<unsigned>(cdiv(mesh->n_cells, kThreads)), kThreads, 0, st>>>(
+      mesh->n_cells, mesh->cell_nodes, mesh->cell_edges, mesh->cell_edge_ori, d_off[0], n_int_edge != nullptr ? d_off[1] : nullptr,
+      d_off[2], totals[0], totals[0] + totals[1], stride, d->cell_dofs, d->n_ldof);
+  ctx->launches++;
+  DYN_CHECK(cudaGetLastError());
+  DYN_CHECK(cudaStreamSynchronize(st));
+#undef DYN_CHECK
+  cleanup();
   *out = d;
   return LFGPU_OK;
 }

@@ -65,6 +65,13 @@ struct lfgpu_dofmap {
   // edge e: n_nodes * n_pt + e * n_seg + j); -1 for uploaded tables, whose edge dofs are unknown
   int n_pt = -1, n_seg = -1;
   int64_t n_nodes = 0;
+  // gather plan of the load vector (dofs.cu: dofmap_gather_plan), built on first use: for dof r the items
+  // g_items[g_ptr[r] .. g_ptr[r+1]) = (cell << 4 | local index), ascending in cell index = the order in which
+  // AssembleVectorLocally adds to result[r] (assembler.h:322-324)
+  int g_state = 0;  // 0 = not built, 1 = ready
+  int32_t* g_ptr = nullptr;
+  uint32_t* g_items = nullptr;
+  int64_t g_n_items = 0;
 };
 
 struct lfgpu_pattern {
@@ -181,6 +188,9 @@ int nsf_of(int degree, int cell_type);
 int build_fe_table(int degree, int cell_type, const lfgpu_quad* qr, FeTable* out, std::string* err);
 void build_fe_tensors(const FeTable& t, FeTensors* out);
 int default_quad_rule(int cell_type, int degree, int capacity, double* points, double* weights);
+
+// per-dof gather lists of a dofmap (dofs.cu), cached in the handle
+int dofmap_gather_plan(lfgpu_ctx* ctx, const lfgpu_dofmap* d);
 
 // edges numbered? (mesh.cu; lazy for the structured generators)
 int ensure_topology(lfgpu_ctx* ctx, lfgpu_mesh* m);

@@ -53,6 +53,8 @@ def lib():
         L.lfo_mesh_export.argtypes = [C.c_void_p] * 8
         L.lfo_dofh_create.restype = C.c_void_p
         L.lfo_dofh_create.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_uint]
+        L.lfo_dofh_create_dynamic.restype = C.c_void_p
+        L.lfo_dofh_create_dynamic.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.lfo_dofh_free.argtypes = [C.c_void_p]
         L.lfo_dofh_num_dofs.restype = C.c_int64
         L.lfo_dofh_num_dofs.argtypes = [C.c_void_p]
@@ -365,9 +367,9 @@ class Mesh:
 class DofHandler:
     """UniformFEDofHandler(mesh, {Point: n_pt, Segment: n_seg, Tria: n_tria, Quad: n_quad})."""
 
-    def __init__(self, mesh, n_pt=0, n_seg=0, n_tria=0, n_quad=0):
+    def __init__(self, mesh, n_pt=0, n_seg=0, n_tria=0, n_quad=0, _handle=None):
         self.mesh = mesh
-        self.h = lib().lfo_dofh_create(mesh.h, n_pt, n_seg, n_tria, n_quad)
+        self.h = _handle if _handle is not None else lib().lfo_dofh_create(mesh.h, n_pt, n_seg, n_tria, n_quad)
         _check(self.h)
         self.num_dofs = lib().lfo_dofh_num_dofs(self.h)
         self.stride = lib().lfo_dofh_stride(self.h)
@@ -376,6 +378,15 @@ class DofHandler:
         if getattr(self, "h", None):
             lib().lfo_dofh_free(self.h)
             self.h = None
+
+    @staticmethod
+    def dynamic(mesh, n_int_node=None, n_int_edge=None, n_int_cell=None):
+        """DynamicFEDofHandler(mesh, locdof) with locdof tabulated per node / edge / cell (None = 0 everywhere)."""
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.uint32) for a in (n_int_node, n_int_edge, n_int_cell)]
+        for a, n in zip(arrs, (mesh.n_nodes, mesh.n_edges, mesh.n_cells)):
+            assert a is None or a.shape == (n,)
+        h = lib().lfo_dofh_create_dynamic(mesh.h, *[_p(a) for a in arrs])
+        return DofHandler(mesh, _handle=h)
 
     def cell_dofs(self):
         d = np.zeros((self.mesh.n_cells, self.stride), np.int64)

@@ -167,6 +167,120 @@ class UniformFEDofHandler final : public DofHandler {
   std::vector<const mesh::Entity*> dof_entities_;
 };
 
+// lib/lf/assemble/dofhandler.h:514-789 (constructor :566-718), dofhandler.cc:340-404 (accessors).
+// Variable number of interior dofs per entity (hp-FEM).  LOCALDOFINFO: const mesh::Entity& -> size_type.
+// Numbering: nodes by index, then edges by index, then cells by index, each entity taking as many consecutive
+// indices as it has interior dofs.  The list of an edge = dofs of endpoint 0, endpoint 1, own; the list of a cell =
+// vertex dofs in local vertex order, then per local edge its interior dofs (reversed for a negative relative
+// orientation, :669-688), then own.  Lists are stored back to back with an offset array per codimension.
+class DynamicFEDofHandler final : public DofHandler {
+ public:
+  template <typename LOCALDOFINFO>
+  DynamicFEDofHandler(std::shared_ptr<const mesh::Mesh> mesh, LOCALDOFINFO&& locdof) : mesh_(std::move(mesh)) {
+    LFO_VERIFY(mesh_->DimMesh() == 2, "Can handle 2D meshes only");
+    gdof_idx_t next = 0;
+    // nodes (:577-601)
+    const size_type nn = mesh_->NumEntities(2);
+    n_int_[2].assign(nn, 0);
+    off_[2].assign(nn + 1, 0);
+    for (glb_idx_t i = 0; i < nn; ++i) {
+      const mesh::Entity* node = mesh_->EntityByIndex(2, i);
+      off_[2][i] = static_cast<size_type>(next);
+      const size_type k = locdof(*node);
+      n_int_[2][i] = k;
+      for (size_type j = 0; j < k; ++j) {
+        list_[2].push_back(next++);
+        owner_.push_back(node);
+      }
+    }
+    off_[2][nn] = static_cast<size_type>(next);
+    // edges (:603-639)
+    const size_type ne = mesh_->NumEntities(1);
+    n_int_[1].assign(ne, 0);
+    off_[1].assign(ne + 1, 0);
+    for (glb_idx_t i = 0; i < ne; ++i) {
+      const mesh::Entity* edge = mesh_->EntityByIndex(1, i);
+      off_[1][i] = static_cast<size_type>(list_[1].size());
+      const size_type k = locdof(*edge);
+      n_int_[1][i] = k;
+      for (const mesh::Entity* ep : edge->SubEntities(1)) append_node_dofs(mesh_->Index(*ep), list_[1]);
+      for (size_type j = 0; j < k; ++j) {
+        list_[1].push_back(next++);
+        owner_.push_back(edge);
+      }
+    }
+    off_[1][ne] = static_cast<size_type>(list_[1].size());
+    // cells (:641-713)
+    const size_type nc = mesh_->NumEntities(0);
+    n_int_[0].assign(nc, 0);
+    off_[0].assign(nc + 1, 0);
+    for (glb_idx_t i = 0; i < nc; ++i) {
+      const mesh::Entity* cell = mesh_->EntityByIndex(0, i);
+      off_[0][i] = static_cast<size_type>(list_[0].size());
+      const size_type k = locdof(*cell);
+      n_int_[0][i] = k;
+      for (const mesh::Entity* v : cell->SubEntities(2)) append_node_dofs(mesh_->Index(*v), list_[0]);
+      const auto ori = cell->RelativeOrientations();
+      const auto edges = cell->SubEntities(1);
+      const size_type n_loc_edges = cell->RefElem().NumSubEntities(1);
+      for (size_type l = 0; l < n_loc_edges; ++l) {
+        const glb_idx_t e = mesh_->Index(*edges[l]);
+        const size_type ke = n_int_[1][e];
+        const size_type first = off_[1][e + 1] - ke;  // interior dofs sit at the end of the edge's list
+        if (ori[l] == mesh::Orientation::positive) {
+          for (size_type j = 0; j < ke; ++j) list_[0].push_back(list_[1][first + j]);
+        } else {
+          for (size_type j = ke; j-- > 0;) list_[0].push_back(list_[1][first + j]);
+        }
+      }
+      for (size_type j = 0; j < k; ++j) {
+        list_[0].push_back(next++);
+        owner_.push_back(cell);
+      }
+    }
+    off_[0][nc] = static_cast<size_type>(list_[0].size());
+    num_dof_ = static_cast<size_type>(next);
+  }
+
+  [[nodiscard]] size_type NumDofs() const override { return num_dof_; }
+  // dofhandler.cc:340-359
+  [[nodiscard]] size_type NumLocalDofs(const mesh::Entity& e) const override {
+    const dim_t cd = e.Codim();
+    const glb_idx_t i = mesh_->Index(e);
+    return off_[cd][i + 1] - off_[cd][i];
+  }
+  [[nodiscard]] size_type NumInteriorDofs(const mesh::Entity& e) const override { return n_int_[e.Codim()][mesh_->Index(e)]; }
+  // dofhandler.cc:361-384
+  [[nodiscard]] std::span<const gdof_idx_t> GlobalDofIndices(const mesh::Entity& e) const override {
+    const dim_t cd = e.Codim();
+    const glb_idx_t i = mesh_->Index(e);
+    const gdof_idx_t* b = list_[cd].data();
+    return {b + off_[cd][i], b + off_[cd][i + 1]};
+  }
+  // dofhandler.cc:386-404
+  [[nodiscard]] std::span<const gdof_idx_t> InteriorGlobalDofIndices(const mesh::Entity& e) const override {
+    const dim_t cd = e.Codim();
+    const glb_idx_t i = mesh_->Index(e);
+    const gdof_idx_t* b = list_[cd].data();
+    return {b + (off_[cd][i + 1] - n_int_[cd][i]), b + off_[cd][i + 1]};
+  }
+  [[nodiscard]] const mesh::Entity& Entity(gdof_idx_t dofnum) const override {
+    LFO_VERIFY(dofnum >= 0 && static_cast<std::size_t>(dofnum) < owner_.size(), "Illegal dof index");
+    return *owner_[dofnum];
+  }
+  [[nodiscard]] std::shared_ptr<const mesh::Mesh> Mesh() const override { return mesh_; }
+
+ private:
+  void append_node_dofs(glb_idx_t node, std::vector<gdof_idx_t>& dst) const {
+    for (size_type j = 0; j < n_int_[2][node]; ++j) dst.push_back(list_[2][off_[2][node] + j]);
+  }
+  std::shared_ptr<const mesh::Mesh> mesh_;
+  size_type num_dof_ = 0;
+  std::vector<const mesh::Entity*> owner_;
+  std::array<std::vector<size_type>, 3> n_int_, off_;  // index = codimension
+  std::array<std::vector<gdof_idx_t>, 3> list_;
+};
+
 // Eigen::Triplet<double> : int row, int col, double value (16 bytes)
 struct Triplet {
   int row, col;

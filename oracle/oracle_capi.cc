@@ -18,7 +18,12 @@ struct MeshH {
 };
 struct DofH {
   std::shared_ptr<mesh::Mesh> mesh;
-  std::unique_ptr<assemble::UniformFEDofHandler> dofh;
+  std::unique_ptr<assemble::DofHandler> dofh;  // UniformFEDofHandler or DynamicFEDofHandler
+  size_type stride = 0;                        // longest cell list (the row length of the exported table)
+  void set_stride() {
+    stride = 0;
+    for (const mesh::Entity* cell : mesh->Entities(0)) stride = std::max(stride, dofh->NumLocalDofs(*cell));
+  }
 };
 
 double now() {
@@ -223,24 +228,43 @@ int lfo_mesh_export(void* h, std::uint8_t* cell_type, std::uint32_t* cell_nodes,
 void* lfo_dofh_create(void* mesh_h, unsigned n_pt, unsigned n_seg, unsigned n_tria, unsigned n_quad) {
   LFO_TRY
   auto* mh = static_cast<MeshH*>(mesh_h);
-  auto d = new DofH{mh->mesh, nullptr};
+  auto d = new DofH{mh->mesh, nullptr, 0};
   assemble::UniformFEDofHandler::dof_map_t layout;
   if (n_pt) layout[RefEl::kPoint()] = n_pt;
   if (n_seg) layout[RefEl::kSegment()] = n_seg;
   if (n_tria) layout[RefEl::kTria()] = n_tria;
   if (n_quad) layout[RefEl::kQuad()] = n_quad;
-  d->dofh = std::make_unique<assemble::UniformFEDofHandler>(mh->mesh, layout);
+  auto u = std::make_unique<assemble::UniformFEDofHandler>(mh->mesh, layout);
+  d->stride = u->CellStride();
+  d->dofh = std::move(u);
+  return d;
+  LFO_CATCH(nullptr)
+}
+// DynamicFEDofHandler(mesh, locdof) with locdof tabulated per entity: n_int_node [n_nodes], n_int_edge [n_edges],
+// n_int_cell [n_cells] (any may be null = 0 for that codimension)
+void* lfo_dofh_create_dynamic(void* mesh_h, const std::uint32_t* n_int_node, const std::uint32_t* n_int_edge,
+                              const std::uint32_t* n_int_cell) {
+  LFO_TRY
+  auto* mh = static_cast<MeshH*>(mesh_h);
+  auto d = new DofH{mh->mesh, nullptr, 0};
+  const mesh::Mesh& m = *mh->mesh;
+  const std::uint32_t* tab[3] = {n_int_cell, n_int_edge, n_int_node};
+  d->dofh = std::make_unique<assemble::DynamicFEDofHandler>(mh->mesh, [&](const mesh::Entity& e) -> size_type {
+    const std::uint32_t* t = tab[e.Codim()];
+    return t ? t[m.Index(e)] : 0U;
+  });
+  d->set_stride();
   return d;
   LFO_CATCH(nullptr)
 }
 void lfo_dofh_free(void* h) { delete static_cast<DofH*>(h); }
 std::int64_t lfo_dofh_num_dofs(void* h) { return static_cast<DofH*>(h)->dofh->NumDofs(); }
-int lfo_dofh_stride(void* h) { return static_cast<int>(static_cast<DofH*>(h)->dofh->CellStride()); }
+int lfo_dofh_stride(void* h) { return static_cast<int>(static_cast<DofH*>(h)->stride); }
 // cell_dofs [n_cells][stride] (unused slots = -1), n_ldof [n_cells]
 int lfo_dofh_export(void* h, std::int64_t* cell_dofs, std::uint8_t* n_ldof) {
   LFO_TRY
   auto* d = static_cast<DofH*>(h);
-  const std::size_t stride = d->dofh->CellStride();
+  const std::size_t stride = d->stride;
   std::size_t c = 0;
   for (const mesh::Entity* cell : d->mesh->Entities(0)) {
     const auto idx = d->dofh->GlobalDofIndices(*cell);
