@@ -114,6 +114,39 @@ int lfgpu_mesh_download(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, uint8_t* cell_ty
 int lfgpu_mesh_update_node_coords(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const double* node_coords);
 void lfgpu_mesh_destroy(lfgpu_mesh* mesh);
 
+/* ---- Gmsh input: stands in for lf::io::GmshReader (io/gmsh_reader.h:55-200, io/gmsh_reader.cc) ----------------------- */
+/* Host-side reader of MSH 2.2 and 4.1 files, text or binary (ReadGmshFile, gmsh_reader.cc:629-697), flattened the way
+ * GmshReader::InitGmshFile (gmsh_reader.cc:121-340, 343-627) feeds its hybrid2d::MeshFactory -- which fixes the entity
+ * numbering every dof number depends on: mesh nodes = the vertices of elements in FILE order (auxiliary nodes of
+ * second-order elements are not mesh nodes), explicitly listed edges in file order ahead of all other edges, cells in
+ * file order, consecutive repetitions of one element merged.  dim_world must be 2.  Errors (unreadable file,
+ * unsupported version or element type, z != 0) return LFGPU_ERR_INVALID with the text in lfgpu_last_error(NULL).       */
+typedef struct lfgpu_gmsh lfgpu_gmsh;
+int lfgpu_gmsh_read_file(const char* filename, int dim_world, lfgpu_gmsh** out);
+int lfgpu_gmsh_read_memory(const void* data, int64_t n_bytes, int dim_world, lfgpu_gmsh** out);
+void lfgpu_gmsh_destroy(lfgpu_gmsh* g);
+/* geometry_order: 1, or 2 when the file holds second-order elements (every output nullable) */
+int lfgpu_gmsh_counts(const lfgpu_gmsh* g, int64_t* n_nodes, int64_t* n_explicit_edges, int64_t* n_cells, int* geometry_order,
+                      int* n_physical_names);
+/* node_coords [n_nodes][2], edge_nodes [n_explicit_edges][2], cell_nodes [n_cells][4] (LFGPU_IDX_NIL in slot 3 of a
+ * triangle): the arguments of AddPoint / AddEntity in call order (every output nullable)                            */
+int lfgpu_gmsh_arrays(const lfgpu_gmsh* g, double* node_coords, uint32_t* edge_nodes, uint32_t* cell_nodes);
+/* GmshReader::PhysicalEntityNr(entity) (gmsh_reader.cc:115-118): returns the number of physical entity numbers of the
+ * entity (codim 0 = cell, 1 = edge, 2 = node; edges beyond the explicit ones have none) and writes min(count, capacity) */
+int lfgpu_gmsh_physical_entity_nr(const lfgpu_gmsh* g, int codim, int64_t index, int capacity, uint32_t* out);
+/* flags[i] = GmshReader::IsPhysicalEntity(entity i, nr) for the first n entities of the codimension: the selectors
+ * the examples build for boundary conditions, ready for active_edges / d_fixed style arguments after upload         */
+int lfgpu_gmsh_physical_flags(const lfgpu_gmsh* g, int codim, uint32_t nr, int64_t n, uint8_t* flags);
+/* $PhysicalNames entry i: number, codimension (= 2 - dimension), name; returns the name's length */
+int lfgpu_gmsh_physical_name(const lfgpu_gmsh* g, int i, uint32_t* nr, int* codim, char* buf, int capacity);
+/* GmshReader::PhysicalEntityName2Nr / PhysicalEntityNr2Name (gmsh_reader.cc:30-99); codim < 0 = not specified, which is
+ * an error when the name / number exists for several codimensions (as in the reference)                             */
+int lfgpu_gmsh_physical_name2nr(const lfgpu_gmsh* g, const char* name, int codim, uint32_t* nr);
+int lfgpu_gmsh_physical_nr2name(const lfgpu_gmsh* g, uint32_t nr, int codim, char* buf, int capacity);
+/* reader.mesh() on the device: upload + edge numbering with the explicit edges first (lfgpu_mesh_build_topology).
+ * LFGPU_ERR_UNSUPPORTED for second-order files (TriaO2 / QuadO2 geometries are outside the device path).            */
+int lfgpu_gmsh_mesh(lfgpu_ctx* ctx, const lfgpu_gmsh* g, lfgpu_mesh** out);
+
 /* ---- dof maps: stand in for lf::assemble::DofHandler (assemble/dofhandler.h:112-228) ------------------------------- */
 /* From any DofHandler: cell_dofs [n_cells][stride] = GlobalDofIndices(cell), n_ldof [n_cells] = NumLocalDofs(cell)
  * (nullable: then 3/4 * ... is derived as the count of non-negative entries).                                         */

@@ -9,6 +9,8 @@ Reference interfaces mirrored (paths relative to the LehrFEM++ checkout):
   lf::assemble::UniformFEDofHandler                              lib/lf/assemble/dofhandler.h:260-503
   lf::uscalfe::ReactionDiffusionElementMatrixProvider            lib/lf/uscalfe/loc_comp_ellbvp.h:85-339
   lf::uscalfe::ScalarLoadElementVectorProvider                   lib/lf/uscalfe/loc_comp_ellbvp.h:562-746
+  lf::assemble::DynamicFEDofHandler                              lib/lf/assemble/dofhandler.h:514-789
+  lf::io::GmshReader                                             lib/lf/io/gmsh_reader.h:55-200, gmsh_reader.cc
 """
 from .api import (  # noqa: F401
     ALGO_ATOMIC,
@@ -21,6 +23,7 @@ from .api import (  # noqa: F401
     Context,
     DeviceArray,
     DofMap,
+    GmshReader,
     LfgpuError,
     Mesh,
     Pattern,
@@ -33,5 +36,5 @@ from .api import (  # noqa: F401
 
 __all__ = [
     "ALGO_ATOMIC", "ALGO_AUTO", "ALGO_FAN", "ALGO_GATHER", "COL_MAJOR", "ROW_MAJOR", "Coeff", "Context", "DeviceArray", "DofMap",
-    "LfgpuError", "Mesh", "Pattern", "QuadRule", "build_library", "default_quad_rule", "fe_tabulate", "library_path",
+    "GmshReader",    "LfgpuError", "Mesh", "Pattern", "QuadRule", "build_library", "default_quad_rule", "fe_tabulate", "library_path",
 ]

@@ -83,6 +83,17 @@ def _lib():
         "lfgpu_mesh_download": (i32, [vp] * 9),
         "lfgpu_mesh_update_node_coords": (i32, [vp, vp, vp]),
         "lfgpu_mesh_destroy": (None, [vp]),
+        "lfgpu_gmsh_read_file": (i32, [C.c_char_p, i32, pp]),
+        "lfgpu_gmsh_read_memory": (i32, [vp, i64, i32, pp]),
+        "lfgpu_gmsh_destroy": (None, [vp]),
+        "lfgpu_gmsh_counts": (i32, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]),
+        "lfgpu_gmsh_arrays": (i32, [vp, vp, vp, vp]),
+        "lfgpu_gmsh_physical_entity_nr": (i32, [vp, i32, i64, i32, vp]),
+        "lfgpu_gmsh_physical_flags": (i32, [vp, i32, C.c_uint32, i64, vp]),
+        "lfgpu_gmsh_physical_name": (i32, [vp, i32, C.POINTER(C.c_uint32), C.POINTER(i32), C.c_char_p, i32]),
+        "lfgpu_gmsh_physical_name2nr": (i32, [vp, C.c_char_p, i32, C.POINTER(C.c_uint32)]),
+        "lfgpu_gmsh_physical_nr2name": (i32, [vp, C.c_uint32, i32, C.c_char_p, i32]),
+        "lfgpu_gmsh_mesh": (i32, [vp, vp, pp]),
         "lfgpu_dofmap_upload": (i32, [vp, vp, i64, i32, vp, vp, pp]),
         "lfgpu_dofmap_uniform": (i32, [vp, vp, i32, i32, i32, i32, pp]),
         "lfgpu_dofmap_lagrange": (i32, [vp, vp, i32, pp]),
@@ -332,6 +343,85 @@ class Context:
         h = C.c_void_p()
         self.check(self.L.lfgpu_mesh_hybrid(self.h, n, jitter, seed, C.byref(h)))
         return Mesh(self, h)
+
+
+class GmshReader:
+    """lf::io::GmshReader over the C ABI (host side; `mesh(ctx)` gives reader.mesh() on the device)."""
+
+    def __init__(self, source, dim_world=2):
+        L = _lib()
+        self.L = L
+        h = C.c_void_p()
+        if isinstance(source, (bytes, bytearray)):
+            buf = bytes(source)
+            rc = L.lfgpu_gmsh_read_memory(buf, len(buf), dim_world, C.byref(h))
+        else:
+            rc = L.lfgpu_gmsh_read_file(os.fsencode(source), dim_world, C.byref(h))
+        self.h = h if rc == 0 else None
+        self._check(rc)
+        v = [C.c_int64() for _ in range(3)]
+        order, nnames = C.c_int(), C.c_int()
+        self._check(L.lfgpu_gmsh_counts(self.h, *[C.byref(x) for x in v], C.byref(order), C.byref(nnames)))
+        self.n_nodes, self.n_explicit_edges, self.n_cells = [x.value for x in v]
+        self.geometry_order = order.value
+        self.n_physical_names = nnames.value
+
+    def _check(self, rc):
+        if rc < 0:
+            raise LfgpuError(rc, (self.L.lfgpu_last_error(None) or b"").decode())
+        return rc
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.lfgpu_gmsh_destroy(self.h)
+            self.h = None
+
+    def arrays(self):
+        """(node_coords [n][2], edge_nodes uint32 [n_explicit][2], cell_nodes uint32 [n_cells][4]) in AddPoint / AddEntity order."""
+        xy = np.zeros((self.n_nodes, 2))
+        en = np.zeros((self.n_explicit_edges, 2), np.uint32)
+        cn = np.zeros((self.n_cells, 4), np.uint32)
+        self._check(self.L.lfgpu_gmsh_arrays(self.h, _p(xy), _p(en), _p(cn)))
+        return xy, en, cn
+
+    def physical_entity_nr(self, codim, index):
+        out = np.zeros(16, np.uint32)
+        n = self._check(self.L.lfgpu_gmsh_physical_entity_nr(self.h, codim, index, out.size, _p(out)))
+        if n > out.size:
+            out = np.zeros(n, np.uint32)
+            self._check(self.L.lfgpu_gmsh_physical_entity_nr(self.h, codim, index, n, _p(out)))
+        return [int(x) for x in out[:n]]
+
+    def physical_flags(self, codim, nr, n):
+        """uint8 [n]: IsPhysicalEntity(entity i of the codimension, nr)."""
+        out = np.zeros(n, np.uint8)
+        self._check(self.L.lfgpu_gmsh_physical_flags(self.h, codim, nr, n, _p(out)))
+        return out
+
+    def physical_entities(self, codim):
+        res = []
+        for i in range(self.n_physical_names):
+            nr, cd = C.c_uint32(), C.c_int()
+            buf = C.create_string_buffer(256)
+            self._check(self.L.lfgpu_gmsh_physical_name(self.h, i, C.byref(nr), C.byref(cd), buf, 256))
+            if cd.value == codim:
+                res.append((nr.value, buf.value.decode()))
+        return sorted(res)
+
+    def name2nr(self, name, codim=-1):
+        nr = C.c_uint32()
+        self._check(self.L.lfgpu_gmsh_physical_name2nr(self.h, name.encode(), codim, C.byref(nr)))
+        return nr.value
+
+    def nr2name(self, nr, codim=-1):
+        buf = C.create_string_buffer(256)
+        self._check(self.L.lfgpu_gmsh_physical_nr2name(self.h, nr, codim, buf, 256))
+        return buf.value.decode()
+
+    def mesh(self, ctx):
+        h = C.c_void_p()
+        ctx.check(self.L.lfgpu_gmsh_mesh(ctx.h, self.h, C.byref(h)))
+        return Mesh(ctx, h)
 
 
 class DeviceArray:

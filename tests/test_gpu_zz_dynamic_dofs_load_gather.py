@@ -1,13 +1,17 @@
-"""GPU parity of the two round-1 late additions (file name sorts last on purpose: both were written after the round's
+"""GPU parity of the three round-1 late additions (file name sorts last on purpose: they were written after the round's
 GPU minutes were spent, so their first run on a B200 is the driver's round-end run).
 
   * lfgpu_dofmap_dynamic      = lf::assemble::DynamicFEDofHandler (assemble/dofhandler.h:514-789), bit-exact dof tables
   * lfgpu_assemble_load(GATHER) = AssembleVectorLocally with the additions in the reference's order (assembler.h:322-324)
+  * lfgpu_gmsh_mesh           = lf::io::GmshReader::mesh() on the device (io/gmsh_reader.cc), numbering bit-exact
 """
+import os
+
 import numpy as np
 import pytest
 
 from oracle import lfo
+from oracle.lfo_gmsh import GmshReader as OracleReader
 from tests.helpers import per_qp_scalar, rel_max_err, upload_oracle_mesh
 
 pytestmark = pytest.mark.gpu
@@ -149,3 +153,47 @@ def test_load_vector_gather_larger_mesh_properties(ctx, lf):
         assert abs(v.sum() - 2.0) <= 1e-11
         a = dm.assemble_load(degree, lf.Coeff.const(1.0), algo=lf.ALGO_ATOMIC).to_host()
         assert rel_max_err(v, a) <= 1e-13
+
+
+# ---- Gmsh input -> device mesh (lfgpu_gmsh_mesh = reader.mesh()) ------------------------------------------------------------
+MSH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "msh")
+
+
+@pytest.mark.parametrize("name", ["two_element_hybrid_2d.msh", "two_element_hybrid_2d_v4_binary.msh", "lecturedemomesh.msh",
+                                  "circle_first_order.msh", "circle_first_order_v4.msh", "piece_of_cake.msh"])
+def test_gmsh_mesh_numbering_and_assembly(ctx, lf, name):
+    path = os.path.join(MSH, name)
+    o = OracleReader(path)
+    xy, en, cn, _ = o.arrays()
+    om = lfo.Mesh.from_arrays(xy, cn, edge_nodes=en)
+    g = lf.GmshReader(path)
+    gm = g.mesh(ctx)
+    assert (gm.n_nodes, gm.n_edges, gm.n_cells) == (om.n_nodes, om.n_edges, om.n_cells)
+    d, e = gm.download(topology=True), om.export()
+    for key in ("cell_nodes", "edge_nodes", "cell_edges", "cell_edge_ori"):
+        assert np.array_equal(d[key], e[key]), key
+    assert np.array_equal(d["node_coords"], e["node_coords"])
+    # P2 reaction-diffusion on the mesh: dof numbers depend on the explicit-edge numbering of the reader
+    dm = gm.dofmap_lagrange(2)
+    od, onl = om.cell_dofs(2)
+    gd, gnl = dm.download()
+    assert np.array_equal(gd, od) and np.array_equal(gnl, onl)
+    pat = dm.symbolic(major=lf.COL_MAJOR)
+    oo = om.assemble_rd(2, lfo.coeff.const(1.5), lfo.coeff.const(0.5))
+    outer, inner = pat.download()
+    assert np.array_equal(outer, oo[0]) and np.array_equal(inner, oo[1])
+    vals = pat.assemble_reaction_diffusion(2, lf.Coeff.const(1.5), lf.Coeff.const(0.5)).to_host()
+    assert rel_max_err(vals, oo[2]) <= TOL
+    # Dirichlet-type selector from a physical group: flags on the edges of the device mesh
+    for nr, _name in g.physical_entities(1):
+        flags = g.physical_flags(1, nr, gm.n_edges)
+        want = [o.is_physical_entity(1, i, nr) for i in range(gm.n_edges)]
+        assert list(flags) == [int(w) for w in want]
+
+
+def test_gmsh_second_order_mesh_is_rejected_on_the_device(ctx, lf):
+    g = lf.GmshReader(os.path.join(MSH, "circle_second_order.msh"))
+    assert g.geometry_order == 2
+    with pytest.raises(lf.LfgpuError) as e:
+        g.mesh(ctx)
+    assert e.value.code == -7
