@@ -1,5 +1,4 @@
-"""GPU parity of the three round-1 late additions (file name sorts last on purpose: they were written after the round's
-GPU minutes were spent, so their first run on a B200 is the driver's round-end run).
+"""GPU parity of the three late round-1 additions (30 tests green on B200, profiles/r01_gpu_tests_late_additions.log).
 
   * lfgpu_dofmap_dynamic      = lf::assemble::DynamicFEDofHandler (assemble/dofhandler.h:514-789), bit-exact dof tables
   * lfgpu_assemble_load(GATHER) = AssembleVectorLocally with the additions in the reference's order (assembler.h:322-324)
@@ -90,9 +89,10 @@ def test_dynamic_structured_mesh_lagrange_layouts(ctx):
     om = lfo.Mesh.tp_tria(7, 5)
     for degree, (n_seg, n_tri) in ((2, (1, 0)), (3, (2, 1))):
         dm = gm.dofmap_dynamic(np.ones(gm.n_nodes), np.full(gm.n_edges, n_seg), np.full(gm.n_cells, n_tri))
-        od, onl = om.cell_dofs(degree)
+        od, onl = om.cell_dofs(degree)  # row length max(tria, quad) (dofhandler.cc:138); the dynamic table is as long as needed
         gd, gnl = dm.download()
-        assert np.array_equal(gd, od) and np.array_equal(gnl, onl)
+        assert dm.stride == onl.max() and np.all(od[:, dm.stride:] == -1)
+        assert np.array_equal(gd, od[:, :dm.stride]) and np.array_equal(gnl, onl)
         o1, i1 = dm.symbolic().download()
         o2, i2 = gm.dofmap_lagrange(degree).symbolic().download()
         assert np.array_equal(o1, o2) and np.array_equal(i1, i2)
