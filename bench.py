@@ -205,7 +205,10 @@ def main():
         desc += " [n overridden to %d]" % n
     ctx = lf.Context(local_rank)
     algo = {"auto": lf.ALGO_AUTO, "fan": lf.ALGO_FAN, "gather": lf.ALGO_GATHER, "atomic": lf.ALGO_ATOMIC}[args.algo]
-    kernel_name = {"auto": "k_assemble_p1_fan" if (degree == 1 and kind == "tp_tria") else "k_assemble_items", "fan": "k_assemble_p1_fan",
+    structured = kind == "tp_tria" or kind.startswith("refined:")
+    row_kernels = {1: "k_assemble_p1_fan", 2: "k_p2_vertex_rows + k_p2_edge_rows"}
+    kernel_name = {"auto": row_kernels[degree] if (degree in row_kernels and structured) else "k_assemble_items",
+                   "fan": row_kernels.get(degree, "k_assemble_items"),
                    "gather": "k_assemble_items", "atomic": "k_assemble_atomic"}[args.algo]
 
     # ---- setup (untimed, like mesh / DofHandler construction on the CPU side) ----------------------------------------------

@@ -953,7 +953,30 @@ int lfgpu::assemble_rd_impl(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_
       }
       return p1_fan_launch(ctx, mesh, p, a, tensor, dg.c[0], wsum, m_diag, m_off, beta, d_row_list, n_rows, d_values, row0);
     }
-    if (algo == LFGPU_ALGO_FAN) LFGPU_FAIL(ctx, LFGPU_ERR_UNSUPPORTED, "LFGPU_ALGO_FAN needs P1 on a triangle mesh with constant coefficients and no activity mask");
+    // P2 row kernels (assemble_p2.cu): triangles, constant coefficients, the provider's default rule (exact for P2, hence
+    // independent of the local vertex numbering), every cell active, all rows, overwrite.  LFGPU_ALGO_FAN asks for them
+    // explicitly; LFGPU_ALGO_AUTO takes them unless LFGPU_P2_ROWS=0.
+    static const bool p2_env = [] { const char* e = std::getenv("LFGPU_P2_ROWS"); return e == nullptr || e[0] != '0'; }();
+    if (degree == 2 && fan_query == nullptr && (algo == LFGPU_ALGO_FAN || p2_env) && active == nullptr && beta == 0.0 &&
+        d_row_list == nullptr && row0 < 0 && qr_tria == nullptr && qr_quad == nullptr && da.kind <= LFGPU_COEFF_CONST_2X2 &&
+        dg.kind == LFGPU_COEFF_CONST && mesh->n_quad == 0 && mesh->cell_coords == nullptr && ht.hdr.nsf[0] == 6) {
+      if ((rc = p2_rows_prepare(ctx, mesh, const_cast<lfgpu_pattern*>(p))) != LFGPU_OK) return rc;
+      if (p->p2_state == 1) {
+        const bool tr = (p->major == LFGPU_ROW_MAJOR);
+        double a[4] = {da.c[0], da.c[1], da.c[2], da.c[3]};
+        const int tensor = da.kind == LFGPU_COEFF_CONST_2X2;
+        if (tensor && tr) std::swap(a[1], a[2]);
+        if (p->n_p2_irregular > 0) {
+          rc = lfgpu_assemble_reaction_diffusion_rows(ctx, mesh, p, degree, qr_tria, qr_quad, alpha, gamma, nullptr, beta, d_values,
+                                                      LFGPU_ALGO_GATHER, p->p2_irregular, p->n_p2_irregular);
+          if (rc != LFGPU_OK) return rc;
+        }
+        const int nq = ht.hdr.nq[0];
+        const double* k00 = ht.blob.data() + ht.hdr.off[0] + 3 * nq + 3 * 6 * nq;  // pack_type: w qx qy | phi gx gy | k00 k01 k10 k11 m
+        return p2_rows_launch(ctx, mesh, p, a, tensor, dg.c[0], k00, k00 + 36, k00 + 72, k00 + 108, k00 + 144, d_values);
+      }
+    }
+    if (algo == LFGPU_ALGO_FAN) LFGPU_FAIL(ctx, LFGPU_ERR_UNSUPPORTED, "LFGPU_ALGO_FAN needs P1 or P2 on a triangle mesh with constant coefficients and no activity mask");
     algo = LFGPU_ALGO_GATHER;
   }
   if (fan_query != nullptr) return LFGPU_OK;

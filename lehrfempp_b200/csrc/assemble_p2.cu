@@ -1,0 +1,528 @@
+// P2 (FeLagrangeO2Tria) fast path of the numeric pass: "row kernels" that own matrix rows in registers (product code).
+//
+// Same mathematics as the generic path (uscalfe/loc_comp_ellbvp.h:266-339 with FeLagrangeO2Tria, lagr_fe.h:399-546, and
+// TriaO1, geometry/tria_o1.cc:50-74; affine cells with constant coefficients, i.e. A_K = sum_ij M_ij Khat^{ji} + gamma
+// |det| Mhat with the reference tensors of the provider's default rule), same output (the values of the compressed matrix
+// of the symbolic pass).  What changes is the decomposition: ncu showed the item kernel bound by
+// shared-memory work and barriers per item, so -- as the vertex-fan kernel does for P1 -- one thread owns one ROW:
+//   * a VERTEX row (dof = mesh node i, interior vertex of valence 6): ring n_0..n_5 of neighbour nodes in fan order; cell
+//     k is the triangle (i, n_k, n_k+1) taken with i as local vertex 0, so only row 0 of the reference tensors is needed;
+//     its six entries go to the diagonal, the two neighbour columns, the two spoke-edge columns (each summed over the two
+//     cells sharing them: a rolling register) and the rim-edge column (one cell).  19 stored values.
+//   * an EDGE row (dof = mesh edge e with two adjacent cells): endpoints p, q, opposite vertices o_1, o_2; both cells are
+//     taken as (p, q, o) so only row 3 (local edge 0) of the reference tensors is needed.  9 stored values.
+// Taking a cell with another local numbering than the mesh's is legitimate because the P2 Lagrange basis is invariant
+// under vertex permutations and the default rule (degree 4) integrates stiffness and mass products exactly: the entries
+// are the same integrals, rounded differently (parity bar 1e-12, observed ~1e-15).  The slot of every column inside
+// the row comes from the scatter map of the symbolic pass and is stored in the plan (5 / 4 bits per entry).
+// Each warp stages its 32 consecutive rows in shared memory and writes the values as full 128-byte lines.
+// Every other row (boundary vertices and edges, valence != 6, ...) is listed as irregular and computed by the generic
+// gather kernel (assemble.cu); the row kernels leave those rows untouched.
+#include <algorithm>
+#include <cstdlib>
+
+#include <cub/cub.cuh>
+
+#include "lfgpu_internal.cuh"
+
+namespace lfgpu {
+namespace {
+
+constexpr int kRing = 6;         // valence handled by the vertex-row kernel
+constexpr int kVertexRowLen = 19;  // 1 + 6 neighbours + 6 spokes + 6 rim edges
+constexpr int kEdgeRowLen = 9;
+constexpr uint32_t kNil = 0xFFFFFFFFu;
+
+// ---- plan construction ------------------------------------------------------------------------------------------------
+// dof table == [node ids | edge dofs >= n_nodes] and all cells are triangles with six local dofs?
+__global__ void k_p2_check(int64_t n_cells, int stride, int64_t n_nodes, const int32_t* __restrict__ dofs, const uint8_t* __restrict__ nldof,
+                           const uint32_t* __restrict__ cell_nodes, int* __restrict__ bad) {
+  const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (c >= n_cells) return;
+  const uint4 v = reinterpret_cast<const uint4*>(cell_nodes)[c];
+  const int32_t* d = dofs + c * stride;
+  bool ok = v.w == kNil && nldof[c] == 6 && d[0] == static_cast<int32_t>(v.x) && d[1] == static_cast<int32_t>(v.y) &&
+            d[2] == static_cast<int32_t>(v.z);
+  if (ok) ok = d[3] >= n_nodes && d[4] >= n_nodes && d[5] >= n_nodes;
+  if (!ok) *bad = 1;
+}
+
+// vertex row r < n_nodes: ring of exactly six cells closing around the node -> nbr[k][r] = n_k, slots[0..2][r]
+// (5 bits per ring position: neighbour columns | spoke-edge columns | rim-edge columns); irregular rows get nbr[0][r] = -1
+__global__ void k_p2_vertex_plan(int64_t n_nodes, int o_stride, int pos_row, const int32_t* __restrict__ adj_ptr,
+                                 const uint32_t* __restrict__ adj, const uint32_t* __restrict__ cell_nodes,
+                                 const uint8_t* __restrict__ pos, const int32_t* __restrict__ outer, int32_t* __restrict__ nbr,
+                                 uint32_t* __restrict__ slots, uint8_t* __restrict__ irregular) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= n_nodes) return;
+  const int32_t it0 = adj_ptr[r];
+  const int m = adj_ptr[r + 1] - it0;
+  bool ok = (m == kRing) && (outer[r + 1] - outer[r] == kVertexRowLen);
+  uint32_t ja[kRing], ka[kRing], ring[kRing];
+  int cell_a[kRing];       // local index of the node in the cell
+  int64_t cell_id[kRing];
+  int ord[kRing];          // adjacent cell at ring position k
+  bool fwd[kRing];         // cell k runs n_k = next local vertex, n_k+1 = the one after (else the other way round)
+  if (ok) {
+    for (int t = 0; t < kRing; ++t) {
+      const uint32_t item = adj[it0 + t];
+      cell_id[t] = item >> 4;
+      cell_a[t] = static_cast<int>(item & 15U);
+      if (cell_a[t] > 2) {
+        ok = false;
+        cell_a[t] = 0;
+      }
+      const uint4 v = reinterpret_cast<const uint4*>(cell_nodes)[cell_id[t]];
+      const uint32_t vv[3] = {v.x, v.y, v.z};
+      ja[t] = vv[(cell_a[t] + 1) % 3];
+      ka[t] = vv[(cell_a[t] + 2) % 3];
+    }
+  }
+  if (ok) {
+    unsigned used = 1U;
+    ring[0] = ja[0];
+    ord[0] = 0;
+    fwd[0] = true;
+    uint32_t cur = ka[0];
+    for (int k = 1; k < kRing && ok; ++k) {
+      int nxt = -1;
+      for (int u = 0; u < kRing; ++u) {
+        if (!(used & (1U << u)) && (ja[u] == cur || ka[u] == cur)) {
+          nxt = u;
+          break;
+        }
+      }
+      if (nxt < 0) {
+        ok = false;
+        break;
+      }
+      used |= 1U << nxt;
+      ring[k] = cur;
+      ord[k] = nxt;
+      fwd[k] = (ja[nxt] == cur);
+      cur = fwd[k] ? ka[nxt] : ja[nxt];
+    }
+    if (ok && cur != ring[0]) ok = false;
+    // six distinct neighbours, none of them the node itself
+    for (int k = 0; k < kRing && ok; ++k) {
+      if (ring[k] == static_cast<uint32_t>(r)) ok = false;
+      for (int u = 0; u < k; ++u)
+        if (ring[u] == ring[k]) ok = false;
+    }
+  }
+  uint32_t w[3] = {0U, 0U, 0U};
+  if (ok) {
+    int sum = 0, sd = -1;
+    for (int k = 0; k < kRing; ++k) {
+      const int u = ord[k];
+      const int a = cell_a[u], vb = (a + 1) % 3, vc = (a + 2) % 3;
+      const uint8_t* prow = pos + (cell_id[u] * o_stride + a) * static_cast<int64_t>(pos_row);
+      const int s_n = prow[fwd[k] ? vb : vc];       // column n_k
+      const int s_s = prow[3 + (fwd[k] ? a : vc)];  // spoke edge (i, n_k)
+      const int s_r = prow[3 + vb];                 // rim edge (n_k, n_k+1)
+      const int s_d = prow[a];
+      if (sd >= 0 && s_d != sd) ok = false;
+      sd = s_d;
+      if (s_n >= kVertexRowLen || s_s >= kVertexRowLen || s_r >= kVertexRowLen) ok = false;
+      w[0] |= static_cast<uint32_t>(s_n & 31) << (5 * k);
+      w[1] |= static_cast<uint32_t>(s_s & 31) << (5 * k);
+      w[2] |= static_cast<uint32_t>(s_r & 31) << (5 * k);
+      sum += s_n + s_s + s_r;
+    }
+    // the 19 slots must be a permutation of 0..18 (the kernel recovers the diagonal slot as 171 - sum of the others)
+    if (ok && sd != 171 - sum) ok = false;
+    if (ok) {
+      unsigned seen = 1U << sd;
+      for (int j = 0; j < 3; ++j)
+        for (int k = 0; k < kRing; ++k) seen |= 1U << ((w[j] >> (5 * k)) & 31U);
+      if (seen != (1U << kVertexRowLen) - 1U) ok = false;
+    }
+  }
+  for (int k = 0; k < kRing; ++k) nbr[static_cast<int64_t>(k) * n_nodes + r] = ok ? static_cast<int32_t>(ring[k]) : -1;
+  for (int j = 0; j < 3; ++j) slots[static_cast<int64_t>(j) * n_nodes + r] = ok ? w[j] : 0U;
+  irregular[r] = (!ok && m > 0) ? 1 : 0;
+}
+
+// edge row r = n_nodes + e with exactly two adjacent cells: enb[0..3][e] = p, q, o_1, o_2; eslots[e] = 8 x 4 bits:
+// columns p, q, o_1, o_2, edge (q, o_1), edge (o_1, p), edge (q, o_2), edge (o_2, p); the row's own slot is 36 - sum
+__global__ void k_p2_edge_plan(int64_t n_nodes, int64_t n_edges, int o_stride, int pos_row, const int32_t* __restrict__ adj_ptr,
+                               const uint32_t* __restrict__ adj, const uint32_t* __restrict__ cell_nodes,
+                               const uint8_t* __restrict__ pos, const int32_t* __restrict__ outer, int32_t* __restrict__ enb,
+                               uint32_t* __restrict__ eslots, uint8_t* __restrict__ irregular) {
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const int64_t r = n_nodes + e;
+  const int32_t it0 = adj_ptr[r];
+  const int m = adj_ptr[r + 1] - it0;
+  bool ok = (m == 2) && (outer[r + 1] - outer[r] == kEdgeRowLen);
+  uint32_t ids[4] = {0, 0, 0, 0};
+  uint32_t w = 0;
+  if (ok) {
+    const uint32_t i1 = adj[it0], i2 = adj[it0 + 1];
+    const int64_t c1 = i1 >> 4, c2 = i2 >> 4;
+    const int a1 = static_cast<int>(i1 & 15U), a2 = static_cast<int>(i2 & 15U);
+    if (a1 < 3 || a1 > 5 || a2 < 3 || a2 > 5) ok = false;
+    if (ok) {
+      const int j1 = a1 - 3, j2 = a2 - 3;
+      const uint4 v1 = reinterpret_cast<const uint4*>(cell_nodes)[c1];
+      const uint4 v2 = reinterpret_cast<const uint4*>(cell_nodes)[c2];
+      const uint32_t n1[3] = {v1.x, v1.y, v1.z}, n2[3] = {v2.x, v2.y, v2.z};
+      const uint32_t p = n1[j1], q = n1[(j1 + 1) % 3], o1 = n1[(j1 + 2) % 3], o2 = n2[(j2 + 2) % 3];
+      const bool same = (n2[j2] == p && n2[(j2 + 1) % 3] == q);
+      const bool opposite = (n2[j2] == q && n2[(j2 + 1) % 3] == p);
+      if (!(same || opposite) || o1 == o2) ok = false;
+      const uint8_t* r1 = pos + (c1 * o_stride + a1) * static_cast<int64_t>(pos_row);
+      const uint8_t* r2 = pos + (c2 * o_stride + a2) * static_cast<int64_t>(pos_row);
+      int s[8];
+      s[0] = r1[j1];                // p
+      s[1] = r1[(j1 + 1) % 3];      // q
+      s[2] = r1[(j1 + 2) % 3];      // o_1
+      s[3] = r2[(j2 + 2) % 3];      // o_2
+      s[4] = r1[3 + (j1 + 1) % 3];  // edge (q, o_1)
+      s[5] = r1[3 + (j1 + 2) % 3];  // edge (o_1, p)
+      // in cell 2 local edge j2+1 starts at the second endpoint of the shared edge, local edge j2+2 ends at the first
+      s[6] = r2[3 + (same ? (j2 + 1) % 3 : (j2 + 2) % 3)];  // edge (q, o_2)
+      s[7] = r2[3 + (same ? (j2 + 2) % 3 : (j2 + 1) % 3)];  // edge (o_2, p)
+      const int self = r1[a1];
+      if (r2[a2] != self) ok = false;
+      int sum = 0;
+      unsigned seen = 1U << self;
+      for (int k = 0; k < 8; ++k) {
+        if (s[k] >= kEdgeRowLen) ok = false;
+        sum += s[k];
+        seen |= 1U << (s[k] & 15);
+        w |= static_cast<uint32_t>(s[k] & 15) << (4 * k);
+      }
+      if (self != 36 - sum || seen != (1U << kEdgeRowLen) - 1U) ok = false;
+      ids[0] = p; ids[1] = q; ids[2] = o1; ids[3] = o2;
+    }
+  }
+  for (int k = 0; k < 4; ++k) enb[static_cast<int64_t>(k) * n_edges + e] = ok ? static_cast<int32_t>(ids[k]) : -1;
+  eslots[e] = ok ? w : 0U;
+  irregular[r] = (!ok && m > 0) ? 1 : 0;
+}
+
+// ---- the kernels --------------------------------------------------------------------------------------------------------
+struct P2Params {
+  double a00, a01, a10, a11;  // diffusion tensor as the row routine of assemble.cu uses it (transposed for row-major output)
+  double gamma;
+  // rows 0 (vertex kernel) and 3 (edge kernel) of the reference tensors; MODE 0 reads k01 as k01 + k10
+  double vk00[6], vk01[6], vk10[6], vk11[6], vm[6];
+  double ek00[6], ek01[6], ek10[6], ek11[6], em[6];
+};
+
+__device__ __forceinline__ double rcp64(double x) {
+  // as in assemble.cu: hardware seed + two Newton steps (Jacobian determinants: no denormals, no zeros)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
+// row `a` (0 or 3, through the tables handed in) of the element matrix of the triangle (x0, x0 + A, x0 + B):
+// J = [A B], M = |det| J^-1 alpha J^-T, t[b] = sum_ij M_ij Khat^{ji}[a][b] + gamma |det| Mhat[a][b]
+// MODE 0: scalar alpha, gamma = 0 (M symmetric: three products per entry)
+template <int MODE>
+__device__ __forceinline__ void p2_row(const P2Params& P, const double (&k00)[6], const double (&k01)[6], const double (&k10)[6],
+                                       const double (&k11)[6], const double (&km)[6], double ax, double ay, double bx, double by,
+                                       double (&t)[6]) {
+  const double det = ax * by - ay * bx;
+  if (MODE == 0) {
+    const double s = P.a00 * rcp64(fabs(det));
+    const double m00 = s * (bx * bx + by * by), m01 = -s * (ax * bx + ay * by), m11 = s * (ax * ax + ay * ay);
+#pragma unroll
+    for (int b = 0; b < 6; ++b) t[b] = m00 * k00[b] + m01 * k01[b] + m11 * k11[b];
+  } else {
+    const double adet = fabs(det), idet = rcp64(det);
+    const double i00 = by * idet, i01 = -bx * idet, i10 = -ay * idet, i11 = ax * idet;
+    const double t00 = i00 * P.a00 + i01 * P.a10, t01 = i00 * P.a01 + i01 * P.a11;
+    const double t10 = i10 * P.a00 + i11 * P.a10, t11 = i10 * P.a01 + i11 * P.a11;
+    const double m00 = adet * (t00 * i00 + t01 * i01), m01 = adet * (t00 * i10 + t01 * i11);
+    const double m10 = adet * (t10 * i00 + t11 * i01), m11 = adet * (t10 * i10 + t11 * i11);
+    const double gm = adet * P.gamma;
+#pragma unroll
+    for (int b = 0; b < 6; ++b) t[b] = m00 * k00[b] + m01 * k10[b] + m10 * k01[b] + m11 * k11[b] + gm * km[b];
+  }
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* a) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a)); }
+
+// copy-out shared by both kernels: the warp's stage is the image of the contiguous value range of its 32 rows
+template <int LEN>
+__device__ __forceinline__ void write_rows(bool staged, bool regular, bool in_range, int lane, int32_t v0, int32_t v1, int32_t wbase,
+                                           const double* __restrict__ stage, const double* __restrict__ dst, double* __restrict__ values) {
+  __syncwarp();
+  if (staged) {
+    const unsigned ballot = __ballot_sync(0xffffffffU, in_range);
+    if (ballot == 0) return;
+    const int total = __shfl_sync(0xffffffffU, v1, 31 - __clz(ballot)) - wbase;
+    double* out = values + wbase;
+#pragma unroll
+    for (int k = 0; k < LEN; ++k) {
+      const int idx = k * 32 + lane;
+      if (idx < total) out[idx] = stage[idx];
+    }
+  } else if (regular) {
+    for (int k = 0; k < LEN; ++k) values[v0 + k] = dst[k];
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128, 4) k_p2_vertex_rows(int n_rows, const int32_t* __restrict__ nbr, const uint32_t* __restrict__ slots,
+                                                         const double* __restrict__ node_coords, const int32_t* __restrict__ outer,
+                                                         int pf_dist, P2Params P, double* __restrict__ values) {
+  extern __shared__ double stage_all[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = r < n_rows;
+  if (pf_dist > 0 && warp == 0) {
+    // pull the lines of the CTA that runs about one wave later into L2 (see assemble_p1.cu): 4 lines per plan array
+    // (6 ring + 3 slot arrays), 4 of row pointers, 16 of coordinates
+    const int rp = blockIdx.x * blockDim.x + pf_dist;
+    if (rp + 128 <= n_rows) {
+      for (int L = lane; L < 56; L += 32) {
+        const char* a;
+        if (L < 24) a = reinterpret_cast<const char*>(nbr + static_cast<size_t>(L >> 2) * n_rows + rp) + (L & 3) * 128;
+        else if (L < 36) a = reinterpret_cast<const char*>(slots + static_cast<size_t>((L - 24) >> 2) * n_rows + rp) + (L & 3) * 128;
+        else if (L < 40) a = reinterpret_cast<const char*>(outer + rp) + (L - 36) * 128;
+        else a = reinterpret_cast<const char*>(node_coords + 2 * static_cast<size_t>(rp)) + (L - 40) * 128;
+        prefetch_l2(a);
+      }
+    }
+  }
+  int32_t v0 = 0, v1 = 0;
+  int32_t nid[kRing];
+  uint32_t w0 = 0, w1 = 0, w2 = 0;
+#pragma unroll
+  for (int s = 0; s < kRing; ++s) nid[s] = -1;
+  if (in_range) {
+    v0 = __ldg(outer + r);
+    v1 = __ldg(outer + r + 1);
+#pragma unroll
+    for (int s = 0; s < kRing; ++s) nid[s] = __ldg(nbr + static_cast<size_t>(s) * n_rows + r);
+    w0 = __ldg(slots + r);
+    w1 = __ldg(slots + static_cast<size_t>(n_rows) + r);
+    w2 = __ldg(slots + 2 * static_cast<size_t>(n_rows) + r);
+  }
+  const bool regular = in_range && nid[0] >= 0;
+  const int32_t wbase = __shfl_sync(0xffffffffU, v0, 0);
+  const bool staged = !__any_sync(0xffffffffU, in_range && !regular && v1 > v0);
+  double* stage = stage_all + warp * (32 * (kVertexRowLen + 1));
+  double* dst = stage + (staged ? v0 - wbase : lane * (kVertexRowLen + 1));
+  if (regular) {
+    const double2* nc = reinterpret_cast<const double2*>(node_coords);
+    const double2 xi = __ldg(nc + r);
+    double dx[kRing], dy[kRing];
+#pragma unroll
+    for (int s = 0; s < kRing; ++s) {
+      const double2 p = __ldg(nc + nid[s]);
+      dx[s] = p.x - xi.x;
+      dy[s] = p.y - xi.y;
+    }
+    int ssum = 0;
+#pragma unroll
+    for (int s = 0; s < kRing; ++s) ssum += static_cast<int>((w0 >> (5 * s)) & 31U) + static_cast<int>((w1 >> (5 * s)) & 31U) +
+                                            static_cast<int>((w2 >> (5 * s)) & 31U);
+    double t[6];
+    p2_row<MODE>(P, P.vk00, P.vk01, P.vk10, P.vk11, P.vm, dx[0], dy[0], dx[1], dy[1], t);
+    double diag = t[0];
+    const double first_n = t[1], first_s = t[3];
+    double carry_n = t[2], carry_s = t[5];
+    dst[w2 & 31U] = t[4];
+#pragma unroll
+    for (int s = 1; s < kRing; ++s) {
+      const int u = (s + 1 < kRing) ? s + 1 : 0;
+      p2_row<MODE>(P, P.vk00, P.vk01, P.vk10, P.vk11, P.vm, dx[s], dy[s], dx[u], dy[u], t);
+      diag += t[0];
+      dst[(w0 >> (5 * s)) & 31U] = carry_n + t[1];
+      dst[(w1 >> (5 * s)) & 31U] = carry_s + t[3];
+      dst[(w2 >> (5 * s)) & 31U] = t[4];
+      carry_n = t[2];
+      carry_s = t[5];
+    }
+    dst[w0 & 31U] = first_n + carry_n;
+    dst[w1 & 31U] = first_s + carry_s;
+    dst[171 - ssum] = diag;
+  }
+  write_rows<kVertexRowLen>(staged, regular, in_range, lane, v0, v1, wbase, stage, dst, values);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128, 4) k_p2_edge_rows(int n_edges, int row0, const int32_t* __restrict__ enb,
+                                                       const uint32_t* __restrict__ eslots, const double* __restrict__ node_coords,
+                                                       const int32_t* __restrict__ outer, int pf_dist, P2Params P,
+                                                       double* __restrict__ values) {
+  extern __shared__ double stage_all[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = e < n_edges;
+  if (pf_dist > 0 && warp == 0) {
+    const int ep = blockIdx.x * blockDim.x + pf_dist;
+    if (ep + 128 <= n_edges && lane < 24) {  // 4 lines per id array, 4 of slots, 4 of row pointers
+      const char* a;
+      if (lane < 16) a = reinterpret_cast<const char*>(enb + static_cast<size_t>(lane >> 2) * n_edges + ep) + (lane & 3) * 128;
+      else if (lane < 20) a = reinterpret_cast<const char*>(eslots + ep) + (lane - 16) * 128;
+      else a = reinterpret_cast<const char*>(outer + row0 + ep) + (lane - 20) * 128;
+      prefetch_l2(a);
+    }
+  }
+  int32_t v0 = 0, v1 = 0;
+  int32_t ip = -1, iq = 0, io1 = 0, io2 = 0;
+  uint32_t w = 0;
+  if (in_range) {
+    v0 = __ldg(outer + row0 + e);
+    v1 = __ldg(outer + row0 + e + 1);
+    ip = __ldg(enb + e);
+    iq = __ldg(enb + static_cast<size_t>(n_edges) + e);
+    io1 = __ldg(enb + 2 * static_cast<size_t>(n_edges) + e);
+    io2 = __ldg(enb + 3 * static_cast<size_t>(n_edges) + e);
+    w = __ldg(eslots + e);
+  }
+  const bool regular = in_range && ip >= 0;
+  const int32_t wbase = __shfl_sync(0xffffffffU, v0, 0);
+  const bool staged = !__any_sync(0xffffffffU, in_range && !regular && v1 > v0);
+  double* stage = stage_all + warp * (32 * (kEdgeRowLen + 1));
+  double* dst = stage + (staged ? v0 - wbase : lane * (kEdgeRowLen + 1));
+  if (regular) {
+    const double2* nc = reinterpret_cast<const double2*>(node_coords);
+    const double2 xp = __ldg(nc + ip), xq = __ldg(nc + iq), x1 = __ldg(nc + io1), x2 = __ldg(nc + io2);
+    const double ax = xq.x - xp.x, ay = xq.y - xp.y;
+    double t1[6], t2[6];
+    p2_row<MODE>(P, P.ek00, P.ek01, P.ek10, P.ek11, P.em, ax, ay, x1.x - xp.x, x1.y - xp.y, t1);
+    p2_row<MODE>(P, P.ek00, P.ek01, P.ek10, P.ek11, P.em, ax, ay, x2.x - xp.x, x2.y - xp.y, t2);
+    int ssum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ssum += static_cast<int>((w >> (4 * k)) & 15U);
+    dst[w & 15U] = t1[0] + t2[0];
+    dst[(w >> 4) & 15U] = t1[1] + t2[1];
+    dst[(w >> 8) & 15U] = t1[2];
+    dst[(w >> 12) & 15U] = t2[2];
+    dst[(w >> 16) & 15U] = t1[4];
+    dst[(w >> 20) & 15U] = t1[5];
+    dst[(w >> 24) & 15U] = t2[4];
+    dst[(w >> 28) & 15U] = t2[5];
+    dst[36 - ssum] = t1[3] + t2[3];
+  }
+  write_rows<kEdgeRowLen>(staged, regular, in_range, lane, v0, v1, wbase, stage, dst, values);
+}
+
+}  // namespace
+
+// ---- host side -----------------------------------------------------------------------------------------------------------
+int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
+  if (p->p2_state != 0) return LFGPU_OK;
+  p->p2_state = -1;
+  const int64_t nn = mesh->n_nodes, ne = p->n_outer - mesh->n_nodes;
+  if (mesh->n_quad != 0 || mesh->cell_coords != nullptr || p->i_dofs != p->o_dofs || ne <= 0 || p->pos_bytes != 1 || p->pos == nullptr ||
+      p->n_outer >= (1LL << 31) - 256)
+    return LFGPU_OK;
+  cudaStream_t st = ctx->stream;
+  int* d_flags = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 256);
+  LFGPU_CUDA_CHECK(ctx, cudaMemsetAsync(d_flags, 0, 16, st));
+  k_p2_check<<<static_cast<unsigned>(cdiv(p->n_cells, 256)), 256, 0, st>>>(p->n_cells, p->o_stride, nn, p->o_dofs, p->o_nldof, mesh->cell_nodes,
+                                                                            d_flags);
+  LFGPU_LAUNCH_CHECK(ctx);
+  int bad = 1;
+  LFGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(&bad, d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+  LFGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+  if (bad != 0) return LFGPU_OK;  // not the dof layout of FeSpaceLagrangeO2 on triangles: stay with the generic kernels
+  uint8_t* flag = nullptr;
+  int32_t* iota = nullptr;
+  int64_t* d_num = nullptr;
+  void* tmp = nullptr;
+  auto cleanup = [&]() { cudaFree(flag); cudaFree(iota); cudaFree(d_num); cudaFree(tmp); };
+  auto drop_plan = [&]() {
+    cudaFree(p->p2v_nbr); cudaFree(p->p2v_slots); cudaFree(p->p2e_nbr); cudaFree(p->p2e_slots); cudaFree(p->p2_irregular);
+    p->p2v_nbr = nullptr; p->p2v_slots = nullptr; p->p2e_nbr = nullptr; p->p2e_slots = nullptr; p->p2_irregular = nullptr;
+  };
+#define P2_CHECK(expr)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      set_last_error(ctx, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+      cleanup();                                                                    \
+      drop_plan();                                                                  \
+      return LFGPU_ERR_CUDA;                                                        \
+    }                                                                               \
+  } while (0)
+  // + 128 entries of slack: the prefetch of the kernels reads whole lines
+  P2_CHECK(cudaMalloc(&p->p2v_nbr, sizeof(int32_t) * (kRing * static_cast<size_t>(nn) + 128)));
+  P2_CHECK(cudaMalloc(&p->p2v_slots, sizeof(uint32_t) * (3 * static_cast<size_t>(nn) + 128)));
+  P2_CHECK(cudaMalloc(&p->p2e_nbr, sizeof(int32_t) * (4 * static_cast<size_t>(ne) + 128)));
+  P2_CHECK(cudaMalloc(&p->p2e_slots, sizeof(uint32_t) * (static_cast<size_t>(ne) + 128)));
+  P2_CHECK(cudaMalloc(&flag, p->n_outer));
+  k_p2_vertex_plan<<<static_cast<unsigned>(cdiv(nn, 128)), 128, 0, st>>>(nn, p->o_stride, p->pos_row, p->adj_ptr, p->adj, mesh->cell_nodes,
+                                                                          static_cast<const uint8_t*>(p->pos), p->outer, p->p2v_nbr,
+                                                                          p->p2v_slots, flag);
+  ctx->launches++;
+  k_p2_edge_plan<<<static_cast<unsigned>(cdiv(ne, 128)), 128, 0, st>>>(nn, ne, p->o_stride, p->pos_row, p->adj_ptr, p->adj, mesh->cell_nodes,
+                                                                        static_cast<const uint8_t*>(p->pos), p->outer, p->p2e_nbr,
+                                                                        p->p2e_slots, flag);
+  ctx->launches++;
+  P2_CHECK(cudaGetLastError());
+  P2_CHECK(cudaMalloc(&iota, sizeof(int32_t) * p->n_outer));
+  P2_CHECK(cudaMalloc(&d_num, sizeof(int64_t)));
+  cub::CountingInputIterator<int32_t> count_it(0);
+  size_t tb = 0;
+  cub::DeviceSelect::Flagged(nullptr, tb, count_it, flag, iota, d_num, p->n_outer, st);
+  P2_CHECK(cudaMalloc(&tmp, tb));
+  P2_CHECK(cub::DeviceSelect::Flagged(tmp, tb, count_it, flag, iota, d_num, p->n_outer, st));
+  int64_t n_irr = 0;
+  P2_CHECK(cudaMemcpyAsync(&n_irr, d_num, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  P2_CHECK(cudaStreamSynchronize(st));
+  if (n_irr > 0) {
+    P2_CHECK(cudaMalloc(&p->p2_irregular, sizeof(int32_t) * n_irr));
+    P2_CHECK(cudaMemcpyAsync(p->p2_irregular, iota, sizeof(int32_t) * n_irr, cudaMemcpyDeviceToDevice, st));
+    P2_CHECK(cudaStreamSynchronize(st));
+  }
+#undef P2_CHECK
+  cleanup();
+  p->n_p2_irregular = n_irr;
+  p->p2_nn = nn;
+  // a mesh on which most rows are irregular gains nothing: keep the item kernel there
+  if (n_irr * 2 > p->n_outer) {
+    drop_plan();
+    return LFGPU_OK;
+  }
+  p->p2_state = 1;
+  return LFGPU_OK;
+}
+
+// tables: the reference tensors of FeLagrangeO2Tria for the rule in use, each [6 * 6] row-major (assemble.cu: pack_type)
+int p2_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, const double alpha[4], int tensor, double gamma,
+                   const double* k00, const double* k01, const double* k10, const double* k11, const double* km, double* d_values) {
+  P2Params P;
+  P.a00 = alpha[0]; P.a01 = tensor ? alpha[1] : 0.0; P.a10 = tensor ? alpha[2] : 0.0; P.a11 = tensor ? alpha[3] : alpha[0];
+  P.gamma = gamma;
+  const bool simple = !tensor && gamma == 0.0;
+  for (int b = 0; b < 6; ++b) {
+    P.vk00[b] = k00[b]; P.vk01[b] = simple ? k01[b] + k10[b] : k01[b]; P.vk10[b] = k10[b]; P.vk11[b] = k11[b]; P.vm[b] = km[b];
+    P.ek00[b] = k00[18 + b]; P.ek01[b] = simple ? k01[18 + b] + k10[18 + b] : k01[18 + b]; P.ek10[b] = k10[18 + b];
+    P.ek11[b] = k11[18 + b]; P.em[b] = km[18 + b];
+  }
+  const int threads = 128;
+  const int nn = static_cast<int>(p->p2_nn), ne = static_cast<int>(p->n_outer - p->p2_nn);
+  static const int pfd_env = [] { const char* e = std::getenv("LFGPU_P2_PFD"); return e != nullptr ? std::atoi(e) : 100; }();
+  // L2 prefetch distance: about one wave of resident CTAs (6 per SM for the vertex rows, 12 for the edge rows)
+  const int ipf_v = static_cast<int>((static_cast<int64_t>(ctx->sm_count) * 6 * threads * pfd_env / 100) & ~static_cast<int64_t>(127));
+  const int ipf_e = static_cast<int>((static_cast<int64_t>(ctx->sm_count) * 12 * threads * pfd_env / 100) & ~static_cast<int64_t>(127));
+  const size_t smem_v = sizeof(double) * (threads / 32) * 32 * (kVertexRowLen + 1);
+  const size_t smem_e = sizeof(double) * (threads / 32) * 32 * (kEdgeRowLen + 1);
+  const unsigned gv = static_cast<unsigned>(cdiv(nn, threads)), ge = static_cast<unsigned>(cdiv(ne, threads));
+  if (simple) {
+    k_p2_vertex_rows<0><<<gv, threads, smem_v, ctx->stream>>>(nn, p->p2v_nbr, p->p2v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values);
+    LFGPU_LAUNCH_CHECK(ctx);
+    k_p2_edge_rows<0><<<ge, threads, smem_e, ctx->stream>>>(ne, nn, p->p2e_nbr, p->p2e_slots, mesh->node_coords, p->outer, ipf_e, P, d_values);
+  } else {
+    k_p2_vertex_rows<1><<<gv, threads, smem_v, ctx->stream>>>(nn, p->p2v_nbr, p->p2v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values);
+    LFGPU_LAUNCH_CHECK(ctx);
+    k_p2_edge_rows<1><<<ge, threads, smem_e, ctx->stream>>>(ne, nn, p->p2e_nbr, p->p2e_slots, mesh->node_coords, p->outer, ipf_e, P, d_values);
+  }
+  LFGPU_LAUNCH_CHECK(ctx);
+  return LFGPU_OK;
+}
+
+}  // namespace lfgpu

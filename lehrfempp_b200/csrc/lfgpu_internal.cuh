@@ -117,6 +117,15 @@ struct lfgpu_pattern {
   uint32_t* fan_info32 = nullptr;    // [n_outer] 4 bits slot-in-row per ring position | diagonal slot << 24 | closed << 28
   int32_t* fan_irregular = nullptr;  // rows that are not a single fan (generic kernel)
   int64_t n_irregular = 0;
+  // P2 row-kernel plan (assemble_p2.cu), built on first use: 0 = not tried, 1 = ready, -1 = not applicable
+  int p2_state = 0;
+  int64_t p2_nn = 0;                 // number of vertex rows (= mesh nodes); the edge rows follow
+  int32_t* p2v_nbr = nullptr;        // [6][p2_nn] ring of neighbour nodes of every vertex row (-1 in slot 0: not a regular row)
+  uint32_t* p2v_slots = nullptr;     // [3][p2_nn] 6 x 5 bits each: slots of the neighbour / spoke-edge / rim-edge columns
+  int32_t* p2e_nbr = nullptr;        // [4][n_edges] endpoints p, q and opposite vertices o_1, o_2 of every edge row
+  uint32_t* p2e_slots = nullptr;     // [n_edges] 8 x 4 bits: slots of p, q, o_1, o_2, (q,o_1), (o_1,p), (q,o_2), (o_2,p)
+  int32_t* p2_irregular = nullptr;   // rows left to the generic gather kernel
+  int64_t n_p2_irregular = 0;
   // host pipeline plan (hostpipe.cu): for hp_blocks equal blocks of outer indices, the number of leading node coordinates
   // that must be on the device before block b can be computed (running maximum, so monotone)
   int hp_blocks = 0;
@@ -200,6 +209,10 @@ int p1_fan_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p);
 int p1_fan_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, const double alpha[4], int tensor, double gamma,
                   double wsum, double m_diag, double m_off, double beta, const int32_t* row_list, int64_t n_rows, double* d_values,
                   int64_t row0 = -1);
+// P2 row kernels (assemble_p2.cu): k00 .. km = reference tensors of FeLagrangeO2Tria, [6 * 6] row-major each
+int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p);
+int p2_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, const double alpha[4], int tensor, double gamma,
+                   const double* k00, const double* k01, const double* k10, const double* k11, const double* km, double* d_values);
 // body of lfgpu_assemble_reaction_diffusion_rows (assemble.cu) with two extras used by the host pipeline (hostpipe.cu)
 int assemble_rd_impl(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, int degree, const lfgpu_quad* qr_tria,
                      const lfgpu_quad* qr_quad, const lfgpu_coeff* alpha, const lfgpu_coeff* gamma, const uint8_t* active, double beta,

@@ -244,6 +244,11 @@ void lfgpu_pattern_destroy(lfgpu_pattern* p) {
   cudaFree(p->fan_nbr16);
   cudaFree(p->fan_info32);
   cudaFree(p->fan_irregular);
+  cudaFree(p->p2v_nbr);
+  cudaFree(p->p2v_slots);
+  cudaFree(p->p2e_nbr);
+  cudaFree(p->p2e_slots);
+  cudaFree(p->p2_irregular);
   cudaFree(p->o_dofs);
   if (p->i_dofs != p->o_dofs) cudaFree(p->i_dofs);
   cudaFree(p->o_nldof);
