@@ -208,7 +208,7 @@ def main():
     structured = kind == "tp_tria" or kind.startswith("refined:")
     row_kernels = {1: "k_assemble_p1_fan", 2: "k_p2_vertex_rows + k_p2_edge_rows"}
     kernel_name = {"auto": row_kernels[degree] if (degree in row_kernels and structured) else "k_assemble_items",
-                   "fan": row_kernels.get(degree, "k_assemble_items"),
+                   "fan": dict(row_kernels, **{3: "k_p3_vertex_rows + k_p3_edge_rows + k_p3_cell_rows"})[degree],
                    "gather": "k_assemble_items", "atomic": "k_assemble_atomic"}[args.algo]
 
     # ---- setup (untimed, like mesh / DofHandler construction on the CPU side) ----------------------------------------------

@@ -976,7 +976,29 @@ int lfgpu::assemble_rd_impl(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_
         return p2_rows_launch(ctx, mesh, p, a, tensor, dg.c[0], k00, k00 + 36, k00 + 72, k00 + 108, k00 + 144, d_values);
       }
     }
-    if (algo == LFGPU_ALGO_FAN) LFGPU_FAIL(ctx, LFGPU_ERR_UNSUPPORTED, "LFGPU_ALGO_FAN needs P1 or P2 on a triangle mesh with constant coefficients and no activity mask");
+    // P3 row kernels (assemble_p3.cu), same conditions.  Their host/device core is checked against the oracle on the CPU;
+    // until the CUDA wrappers have been measured on a B200 they are taken on request only (LFGPU_ALGO_FAN or LFGPU_P3_ROWS=1).
+    static const bool p3_env = [] { const char* e = std::getenv("LFGPU_P3_ROWS"); return e != nullptr && e[0] == '1'; }();
+    if (degree == 3 && fan_query == nullptr && (algo == LFGPU_ALGO_FAN || p3_env) && active == nullptr && beta == 0.0 &&
+        d_row_list == nullptr && row0 < 0 && qr_tria == nullptr && qr_quad == nullptr && da.kind <= LFGPU_COEFF_CONST_2X2 &&
+        dg.kind == LFGPU_COEFF_CONST && mesh->n_quad == 0 && mesh->cell_coords == nullptr && ht.hdr.nsf[0] == 10) {
+      if ((rc = p3_rows_prepare(ctx, mesh, const_cast<lfgpu_pattern*>(p))) != LFGPU_OK) return rc;
+      if (p->p3_state == 1) {
+        const bool tr = (p->major == LFGPU_ROW_MAJOR);
+        double a[4] = {da.c[0], da.c[1], da.c[2], da.c[3]};
+        const int tensor = da.kind == LFGPU_COEFF_CONST_2X2;
+        if (tensor && tr) std::swap(a[1], a[2]);
+        if (p->n_p3_irregular > 0) {
+          rc = lfgpu_assemble_reaction_diffusion_rows(ctx, mesh, p, degree, qr_tria, qr_quad, alpha, gamma, nullptr, beta, d_values,
+                                                      LFGPU_ALGO_GATHER, p->p3_irregular, p->n_p3_irregular);
+          if (rc != LFGPU_OK) return rc;
+        }
+        const int nq = ht.hdr.nq[0];
+        const double* k00 = ht.blob.data() + ht.hdr.off[0] + 3 * nq + 3 * 10 * nq;
+        return p3_rows_launch(ctx, mesh, p, a, tensor, dg.c[0], k00, k00 + 100, k00 + 200, k00 + 300, k00 + 400, d_values);
+      }
+    }
+    if (algo == LFGPU_ALGO_FAN) LFGPU_FAIL(ctx, LFGPU_ERR_UNSUPPORTED, "LFGPU_ALGO_FAN needs P1, P2 or P3 on a triangle mesh with constant coefficients and no activity mask");
     algo = LFGPU_ALGO_GATHER;
   }
   if (fan_query != nullptr) return LFGPU_OK;

@@ -1,0 +1,362 @@
+// P3 (FeLagrangeO3Tria) fast path of the numeric pass: row kernels (product code).  The arithmetic and the index logic live
+// in rows_p3_core.h (shared with the host emulation that checks them against the oracle on the CPU); this file holds the
+// CUDA side: plan kernels, the three row kernels (vertex rows of 37, edge-dof rows of 16, cell rows of 10 stored values)
+// and the launch code.  Layout of the work as in assemble_p2.cu: one thread per row, the 32 consecutive rows of a warp
+// staged in shared memory and written as full 128-byte lines, rows that do not fit (boundary, valence != 6) computed by
+// the generic gather kernel, L2 prefetch of the plan lines one wave ahead.
+#include <algorithm>
+#include <cstdlib>
+
+#include <cub/cub.cuh>
+
+#include "lfgpu_internal.cuh"
+#include "rows_p3_core.h"
+
+namespace lfgpu {
+namespace {
+
+using namespace p3;
+constexpr uint32_t kNil = 0xFFFFFFFFu;
+
+// ---- plan construction ------------------------------------------------------------------------------------------------
+// dof table == [node ids | 6 edge dofs in [n_nodes, base_int) | base_int + cell] and all cells triangles with ten dofs?
+__global__ void k_p3_check(int64_t n_cells, int stride, int64_t n_nodes, int64_t base_int, const int32_t* __restrict__ dofs,
+                           const uint8_t* __restrict__ nldof, const uint32_t* __restrict__ cell_nodes, int* __restrict__ bad) {
+  const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (c >= n_cells) return;
+  const uint4 v = reinterpret_cast<const uint4*>(cell_nodes)[c];
+  const int32_t* d = dofs + c * stride;
+  bool ok = v.w == kNil && nldof[c] == 10 && d[0] == static_cast<int32_t>(v.x) && d[1] == static_cast<int32_t>(v.y) &&
+            d[2] == static_cast<int32_t>(v.z) && d[9] == base_int + c;
+  if (ok) {
+    for (int b = 3; b < 9; ++b) ok = ok && d[b] >= n_nodes && d[b] < base_int;
+  }
+  if (!ok) *bad = 1;
+}
+
+__global__ void k_p3_vertex_plan(int64_t n_nodes, int o_stride, int pos_row, const int32_t* __restrict__ adj_ptr,
+                                 const uint32_t* __restrict__ adj, const uint32_t* __restrict__ cell_nodes,
+                                 const uint8_t* __restrict__ pos, const int32_t* __restrict__ outer, int32_t* __restrict__ nbr,
+                                 uint32_t* __restrict__ slots, uint8_t* __restrict__ irregular) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= n_nodes) return;
+  const int32_t it0 = adj_ptr[r];
+  const int m = adj_ptr[r + 1] - it0;
+  int32_t ring[kRing] = {-1, -1, -1, -1, -1, -1};
+  uint32_t w[kVertexSlotWords] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const bool ok = vertex_plan(r, m, adj + it0, cell_nodes, pos, o_stride, pos_row, outer[r + 1] - outer[r], ring, w);
+  for (int k = 0; k < kRing; ++k) nbr[static_cast<int64_t>(k) * n_nodes + r] = ok ? ring[k] : -1;
+  for (int j = 0; j < kVertexSlotWords; ++j) slots[static_cast<int64_t>(j) * n_nodes + r] = ok ? w[j] : 0U;
+  irregular[r] = (!ok && m > 0) ? 1 : 0;
+}
+
+__global__ void k_p3_edge_plan(int64_t n_nodes, int64_t n_erows, int o_stride, int pos_row, const int32_t* __restrict__ adj_ptr,
+                               const uint32_t* __restrict__ adj, const uint32_t* __restrict__ cell_nodes,
+                               const uint8_t* __restrict__ pos, const int32_t* __restrict__ outer, int32_t* __restrict__ enb,
+                               uint32_t* __restrict__ eslots, uint8_t* __restrict__ irregular) {
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= n_erows) return;
+  const int64_t r = n_nodes + e;
+  const int32_t it0 = adj_ptr[r];
+  const int m = adj_ptr[r + 1] - it0;
+  int32_t ids[4] = {-1, -1, -1, -1};
+  uint32_t w[kEdgeSlotWords] = {0, 0};
+  const bool ok = edge_plan(m, adj + it0, cell_nodes, pos, o_stride, pos_row, outer[r + 1] - outer[r], ids, w);
+  for (int k = 0; k < 4; ++k) enb[static_cast<int64_t>(k) * n_erows + e] = ok ? ids[k] : -1;
+  for (int j = 0; j < kEdgeSlotWords; ++j) eslots[static_cast<int64_t>(j) * n_erows + e] = ok ? w[j] : 0U;
+  irregular[r] = (!ok && m > 0) ? 1 : 0;
+}
+
+// cell rows are always regular if the row has ten stored values
+__global__ void k_p3_cell_flags(int64_t n_cells, int64_t base_int, const int32_t* __restrict__ outer, uint8_t* __restrict__ irregular,
+                                int* __restrict__ bad) {
+  const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (c >= n_cells) return;
+  const int64_t r = base_int + c;
+  irregular[r] = 0;
+  if (outer[r + 1] - outer[r] != kCellRowLen) *bad = 1;
+}
+
+// ---- the kernels --------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void prefetch_l2(const void* a) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a)); }
+
+// copy-out shared by the kernels: the warp's stage is the image of the contiguous value range of its 32 rows
+template <int LEN>
+__device__ __forceinline__ void write_rows(bool staged, bool regular, bool in_range, int lane, int32_t v0, int32_t v1, int32_t wbase,
+                                           const double* __restrict__ stage, const double* __restrict__ dst, double* __restrict__ values) {
+  __syncwarp();
+  if (staged) {
+    const unsigned ballot = __ballot_sync(0xffffffffU, in_range);
+    if (ballot == 0) return;
+    const int total = __shfl_sync(0xffffffffU, v1, 31 - __clz(ballot)) - wbase;
+    double* out = values + wbase;
+#pragma unroll
+    for (int k = 0; k < LEN; ++k) {
+      const int idx = k * 32 + lane;
+      if (idx < total) out[idx] = stage[idx];
+    }
+  } else if (regular) {
+    for (int k = 0; k < LEN; ++k) values[v0 + k] = dst[k];
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128, 3) k_p3_vertex_rows(int n_rows, const int32_t* __restrict__ nbr, const uint32_t* __restrict__ slots,
+                                                         const double* __restrict__ node_coords, const int32_t* __restrict__ outer,
+                                                         int pf_dist, Params P, double* __restrict__ values) {
+  extern __shared__ double stage_all[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = r < n_rows;
+  if (pf_dist > 0 && warp == 0) {
+    // lines of the CTA about one wave later: 4 per plan array (6 ring + 9 slot arrays), 4 of row pointers, 16 of coordinates
+    const int rp = blockIdx.x * blockDim.x + pf_dist;
+    if (rp + 128 <= n_rows) {
+      for (int L = lane; L < 80; L += 32) {
+        const char* a;
+        if (L < 24) a = reinterpret_cast<const char*>(nbr + static_cast<size_t>(L >> 2) * n_rows + rp) + (L & 3) * 128;
+        else if (L < 60) a = reinterpret_cast<const char*>(slots + static_cast<size_t>((L - 24) >> 2) * n_rows + rp) + (L & 3) * 128;
+        else if (L < 64) a = reinterpret_cast<const char*>(outer + rp) + (L - 60) * 128;
+        else a = reinterpret_cast<const char*>(node_coords + 2 * static_cast<size_t>(rp)) + (L - 64) * 128;
+        prefetch_l2(a);
+      }
+    }
+  }
+  int32_t v0 = 0, v1 = 0;
+  int32_t nid[kRing];
+  uint32_t w[kVertexSlotWords];
+#pragma unroll
+  for (int s = 0; s < kRing; ++s) nid[s] = -1;
+#pragma unroll
+  for (int j = 0; j < kVertexSlotWords; ++j) w[j] = 0U;
+  if (in_range) {
+    v0 = __ldg(outer + r);
+    v1 = __ldg(outer + r + 1);
+#pragma unroll
+    for (int s = 0; s < kRing; ++s) nid[s] = __ldg(nbr + static_cast<size_t>(s) * n_rows + r);
+#pragma unroll
+    for (int j = 0; j < kVertexSlotWords; ++j) w[j] = __ldg(slots + static_cast<size_t>(j) * n_rows + r);
+  }
+  const bool regular = in_range && nid[0] >= 0;
+  const int32_t wbase = __shfl_sync(0xffffffffU, v0, 0);
+  const bool staged = !__any_sync(0xffffffffU, in_range && !regular && v1 > v0);
+  double* stage = stage_all + warp * (32 * (kVertexRowLen + 1));
+  double* dst = stage + (staged ? v0 - wbase : lane * (kVertexRowLen + 1));
+  if (regular) {
+    const double2* nc = reinterpret_cast<const double2*>(node_coords);
+    const double2 xi = __ldg(nc + r);
+    double dx[kRing], dy[kRing];
+#pragma unroll
+    for (int s = 0; s < kRing; ++s) {
+      const double2 p = __ldg(nc + nid[s]);
+      dx[s] = p.x - xi.x;
+      dy[s] = p.y - xi.y;
+    }
+    vertex_row<MODE>(P, dx, dy, w, dst);
+  }
+  write_rows<kVertexRowLen>(staged, regular, in_range, lane, v0, v1, wbase, stage, dst, values);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128, 4) k_p3_edge_rows(int n_erows, int row0, const int32_t* __restrict__ enb,
+                                                       const uint32_t* __restrict__ eslots, const double* __restrict__ node_coords,
+                                                       const int32_t* __restrict__ outer, int pf_dist, Params P,
+                                                       double* __restrict__ values) {
+  extern __shared__ double stage_all[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = e < n_erows;
+  if (pf_dist > 0 && warp == 0) {
+    const int ep = blockIdx.x * blockDim.x + pf_dist;
+    if (ep + 128 <= n_erows && lane < 28) {  // 4 lines per id array, 4 per slot array, 4 of row pointers
+      const char* a;
+      if (lane < 16) a = reinterpret_cast<const char*>(enb + static_cast<size_t>(lane >> 2) * n_erows + ep) + (lane & 3) * 128;
+      else if (lane < 24) a = reinterpret_cast<const char*>(eslots + static_cast<size_t>((lane - 16) >> 2) * n_erows + ep) + (lane & 3) * 128;
+      else a = reinterpret_cast<const char*>(outer + row0 + ep) + (lane - 24) * 128;
+      prefetch_l2(a);
+    }
+  }
+  int32_t v0 = 0, v1 = 0;
+  int32_t ip = -1, iq = 0, io1 = 0, io2 = 0;
+  uint32_t w[kEdgeSlotWords] = {0U, 0U};
+  if (in_range) {
+    v0 = __ldg(outer + row0 + e);
+    v1 = __ldg(outer + row0 + e + 1);
+    ip = __ldg(enb + e);
+    iq = __ldg(enb + static_cast<size_t>(n_erows) + e);
+    io1 = __ldg(enb + 2 * static_cast<size_t>(n_erows) + e);
+    io2 = __ldg(enb + 3 * static_cast<size_t>(n_erows) + e);
+    w[0] = __ldg(eslots + e);
+    w[1] = __ldg(eslots + static_cast<size_t>(n_erows) + e);
+  }
+  const bool regular = in_range && ip >= 0;
+  const int32_t wbase = __shfl_sync(0xffffffffU, v0, 0);
+  const bool staged = !__any_sync(0xffffffffU, in_range && !regular && v1 > v0);
+  double* stage = stage_all + warp * (32 * (kEdgeRowLen + 1));
+  double* dst = stage + (staged ? v0 - wbase : lane * (kEdgeRowLen + 1));
+  if (regular) {
+    const double2* nc = reinterpret_cast<const double2*>(node_coords);
+    const double2 xp = __ldg(nc + ip), xq = __ldg(nc + iq), x1 = __ldg(nc + io1), x2 = __ldg(nc + io2);
+    edge_row<MODE>(P, xq.x - xp.x, xq.y - xp.y, x1.x - xp.x, x1.y - xp.y, x2.x - xp.x, x2.y - xp.y, w, dst);
+  }
+  write_rows<kEdgeRowLen>(staged, regular, in_range, lane, v0, v1, wbase, stage, dst, values);
+}
+
+// one thread per cell: row 9 of its element matrix; needs no plan (cell_nodes + the scatter-map row of list position 9)
+template <int MODE>
+__global__ void __launch_bounds__(128, 4) k_p3_cell_rows(int n_cells, int row0, int o_stride, int pos_row, const uint32_t* __restrict__ cell_nodes,
+                                                       const uint8_t* __restrict__ pos, const double* __restrict__ node_coords,
+                                                       const int32_t* __restrict__ outer, Params P, double* __restrict__ values) {
+  extern __shared__ double stage_all[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = c < n_cells;
+  int32_t v0 = 0, v1 = 0;
+  if (in_range) {
+    v0 = __ldg(outer + row0 + c);
+    v1 = __ldg(outer + row0 + c + 1);
+  }
+  const int32_t wbase = __shfl_sync(0xffffffffU, v0, 0);
+  double* stage = stage_all + warp * (32 * (kCellRowLen + 1));
+  double* dst = stage + (v0 - wbase);
+  if (in_range) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(cell_nodes) + c);
+    const uint32_t* pp = reinterpret_cast<const uint32_t*>(pos + (static_cast<size_t>(c) * o_stride + 9) * pos_row);
+    const uint32_t pw[3] = {__ldg(pp), __ldg(pp + 1), __ldg(pp + 2)};
+    const double2* nc = reinterpret_cast<const double2*>(node_coords);
+    const double2 x0 = __ldg(nc + v.x), x1 = __ldg(nc + v.y), x2 = __ldg(nc + v.z);
+    cell_row<MODE>(P, x1.x - x0.x, x1.y - x0.y, x2.x - x0.x, x2.y - x0.y, pw, dst);
+  }
+  write_rows<kCellRowLen>(true, in_range, in_range, lane, v0, v1, wbase, stage, dst, values);
+}
+
+}  // namespace
+
+// ---- host side -----------------------------------------------------------------------------------------------------------
+int p3_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
+  if (p->p3_state != 0) return LFGPU_OK;
+  p->p3_state = -1;
+  const int64_t nn = mesh->n_nodes, base_int = p->n_outer - p->n_cells, ner = base_int - nn;
+  if (mesh->n_quad != 0 || mesh->cell_coords != nullptr || p->i_dofs != p->o_dofs || ner <= 0 || p->pos_bytes != 1 || p->pos == nullptr ||
+      p->n_outer >= (1LL << 31) - 256 || p->n_cells >= (1LL << 27))
+    return LFGPU_OK;
+  cudaStream_t st = ctx->stream;
+  int* d_flags = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 256);
+  LFGPU_CUDA_CHECK(ctx, cudaMemsetAsync(d_flags, 0, 16, st));
+  k_p3_check<<<static_cast<unsigned>(cdiv(p->n_cells, 256)), 256, 0, st>>>(p->n_cells, p->o_stride, nn, base_int, p->o_dofs, p->o_nldof,
+                                                                            mesh->cell_nodes, d_flags);
+  LFGPU_LAUNCH_CHECK(ctx);
+  uint8_t* flag = nullptr;
+  LFGPU_CUDA_CHECK(ctx, cudaMalloc(&flag, p->n_outer));
+  k_p3_cell_flags<<<static_cast<unsigned>(cdiv(p->n_cells, 256)), 256, 0, st>>>(p->n_cells, base_int, p->outer, flag, d_flags);
+  ctx->launches++;
+  int bad = 1;
+  cudaError_t e0 = cudaMemcpyAsync(&bad, d_flags, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e0 == cudaSuccess) e0 = cudaStreamSynchronize(st);
+  if (e0 != cudaSuccess || bad != 0) {
+    cudaFree(flag);
+    LFGPU_CUDA_CHECK(ctx, e0);
+    return LFGPU_OK;  // not the dof layout of FeSpaceLagrangeO3 on triangles: stay with the generic kernels
+  }
+  int32_t* iota = nullptr;
+  int64_t* d_num = nullptr;
+  void* tmp = nullptr;
+  auto cleanup = [&]() { cudaFree(flag); cudaFree(iota); cudaFree(d_num); cudaFree(tmp); };
+  auto drop_plan = [&]() {
+    cudaFree(p->p3v_nbr); cudaFree(p->p3v_slots); cudaFree(p->p3e_nbr); cudaFree(p->p3e_slots); cudaFree(p->p3_irregular);
+    p->p3v_nbr = nullptr; p->p3v_slots = nullptr; p->p3e_nbr = nullptr; p->p3e_slots = nullptr; p->p3_irregular = nullptr;
+  };
+#define P3_CHECK(expr)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      set_last_error(ctx, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+      cleanup();                                                                    \
+      drop_plan();                                                                  \
+      return LFGPU_ERR_CUDA;                                                        \
+    }                                                                               \
+  } while (0)
+  // + 128 entries of slack: the prefetch of the kernels reads whole lines
+  P3_CHECK(cudaMalloc(&p->p3v_nbr, sizeof(int32_t) * (kRing * static_cast<size_t>(nn) + 128)));
+  P3_CHECK(cudaMalloc(&p->p3v_slots, sizeof(uint32_t) * (kVertexSlotWords * static_cast<size_t>(nn) + 128)));
+  P3_CHECK(cudaMalloc(&p->p3e_nbr, sizeof(int32_t) * (4 * static_cast<size_t>(ner) + 128)));
+  P3_CHECK(cudaMalloc(&p->p3e_slots, sizeof(uint32_t) * (kEdgeSlotWords * static_cast<size_t>(ner) + 128)));
+  k_p3_vertex_plan<<<static_cast<unsigned>(cdiv(nn, 128)), 128, 0, st>>>(nn, p->o_stride, p->pos_row, p->adj_ptr, p->adj, mesh->cell_nodes,
+                                                                          static_cast<const uint8_t*>(p->pos), p->outer, p->p3v_nbr,
+                                                                          p->p3v_slots, flag);
+  ctx->launches++;
+  k_p3_edge_plan<<<static_cast<unsigned>(cdiv(ner, 128)), 128, 0, st>>>(nn, ner, p->o_stride, p->pos_row, p->adj_ptr, p->adj, mesh->cell_nodes,
+                                                                         static_cast<const uint8_t*>(p->pos), p->outer, p->p3e_nbr,
+                                                                         p->p3e_slots, flag);
+  ctx->launches++;
+  P3_CHECK(cudaGetLastError());
+  P3_CHECK(cudaMalloc(&iota, sizeof(int32_t) * p->n_outer));
+  P3_CHECK(cudaMalloc(&d_num, sizeof(int64_t)));
+  cub::CountingInputIterator<int32_t> count_it(0);
+  size_t tb = 0;
+  cub::DeviceSelect::Flagged(nullptr, tb, count_it, flag, iota, d_num, p->n_outer, st);
+  P3_CHECK(cudaMalloc(&tmp, tb));
+  P3_CHECK(cub::DeviceSelect::Flagged(tmp, tb, count_it, flag, iota, d_num, p->n_outer, st));
+  int64_t n_irr = 0;
+  P3_CHECK(cudaMemcpyAsync(&n_irr, d_num, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  P3_CHECK(cudaStreamSynchronize(st));
+  if (n_irr > 0) {
+    P3_CHECK(cudaMalloc(&p->p3_irregular, sizeof(int32_t) * n_irr));
+    P3_CHECK(cudaMemcpyAsync(p->p3_irregular, iota, sizeof(int32_t) * n_irr, cudaMemcpyDeviceToDevice, st));
+    P3_CHECK(cudaStreamSynchronize(st));
+  }
+#undef P3_CHECK
+  cleanup();
+  p->n_p3_irregular = n_irr;
+  p->p3_nn = nn;
+  if (n_irr * 2 > p->n_outer) {  // mostly irregular rows: the item kernel is the better choice
+    drop_plan();
+    return LFGPU_OK;
+  }
+  p->p3_state = 1;
+  return LFGPU_OK;
+}
+
+// k00 .. km: the reference tensors of FeLagrangeO3Tria for the rule in use, each [10 * 10] row-major (assemble.cu: pack_type)
+int p3_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, const double alpha[4], int tensor, double gamma,
+                   const double* k00, const double* k01, const double* k10, const double* k11, const double* km, double* d_values) {
+  Params P;
+  P.a00 = alpha[0]; P.a01 = tensor ? alpha[1] : 0.0; P.a10 = tensor ? alpha[2] : 0.0; P.a11 = tensor ? alpha[3] : alpha[0];
+  P.gamma = gamma;
+  const bool simple = !tensor && gamma == 0.0;
+  const int rows[3] = {0, 3, 9};
+  for (int w = 0; w < 3; ++w)
+    for (int b = 0; b < 10; ++b) {
+      const int i = rows[w] * 10 + b;
+      P.k00[w][b] = k00[i]; P.k01[w][b] = simple ? k01[i] + k10[i] : k01[i]; P.k10[w][b] = k10[i]; P.k11[w][b] = k11[i]; P.km[w][b] = km[i];
+    }
+  const int threads = 128;
+  const int nn = static_cast<int>(p->p3_nn), nc = static_cast<int>(p->n_cells);
+  const int base_int = static_cast<int>(p->n_outer - p->n_cells), ner = base_int - nn;
+  static const int pfd_env = [] { const char* e = std::getenv("LFGPU_P3_PFD"); return e != nullptr ? std::atoi(e) : 100; }();
+  const int ipf_v = static_cast<int>((static_cast<int64_t>(ctx->sm_count) * 3 * threads * pfd_env / 100) & ~static_cast<int64_t>(127));
+  const int ipf_e = static_cast<int>((static_cast<int64_t>(ctx->sm_count) * 8 * threads * pfd_env / 100) & ~static_cast<int64_t>(127));
+  const size_t smem_v = sizeof(double) * (threads / 32) * 32 * (kVertexRowLen + 1);
+  const size_t smem_e = sizeof(double) * (threads / 32) * 32 * (kEdgeRowLen + 1);
+  const size_t smem_c = sizeof(double) * (threads / 32) * 32 * (kCellRowLen + 1);
+  const unsigned gv = static_cast<unsigned>(cdiv(nn, threads)), ge = static_cast<unsigned>(cdiv(ner, threads)),
+                 gc = static_cast<unsigned>(cdiv(nc, threads));
+  const uint8_t* pos = static_cast<const uint8_t*>(p->pos);
+#define P3_LAUNCH(MODE)                                                                                                                   \
+  k_p3_vertex_rows<MODE><<<gv, threads, smem_v, ctx->stream>>>(nn, p->p3v_nbr, p->p3v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values); \
+  LFGPU_LAUNCH_CHECK(ctx);                                                                                                                \
+  k_p3_edge_rows<MODE><<<ge, threads, smem_e, ctx->stream>>>(ner, nn, p->p3e_nbr, p->p3e_slots, mesh->node_coords, p->outer, ipf_e, P, d_values); \
+  LFGPU_LAUNCH_CHECK(ctx);                                                                                                                \
+  k_p3_cell_rows<MODE><<<gc, threads, smem_c, ctx->stream>>>(nc, base_int, p->o_stride, p->pos_row, mesh->cell_nodes, pos, mesh->node_coords,    \
+                                                             p->outer, P, d_values);                                                    \
+  LFGPU_LAUNCH_CHECK(ctx)
+  if (simple) {
+    P3_LAUNCH(0);
+  } else {
+    P3_LAUNCH(1);
+  }
+#undef P3_LAUNCH
+  return LFGPU_OK;
+}
+
+}  // namespace lfgpu

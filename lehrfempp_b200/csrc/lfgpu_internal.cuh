@@ -126,6 +126,15 @@ struct lfgpu_pattern {
   uint32_t* p2e_slots = nullptr;     // [n_edges] 8 x 4 bits: slots of p, q, o_1, o_2, (q,o_1), (o_1,p), (q,o_2), (o_2,p)
   int32_t* p2_irregular = nullptr;   // rows left to the generic gather kernel
   int64_t n_p2_irregular = 0;
+  // P3 row-kernel plan (assemble_p3.cu, rows_p3_core.h): vertex rows [0, p3_nn), edge-dof rows, then one row per cell
+  int p3_state = 0;
+  int64_t p3_nn = 0;
+  int32_t* p3v_nbr = nullptr;        // [6][p3_nn] ring of neighbour nodes (-1 in slot 0: not a regular row)
+  uint32_t* p3v_slots = nullptr;     // [9][p3_nn] 36 slot bytes per row
+  int32_t* p3e_nbr = nullptr;        // [4][n_edge_rows] P, Q, o_1, o_2
+  uint32_t* p3e_slots = nullptr;     // [2][n_edge_rows] 16 slot nibbles per row
+  int32_t* p3_irregular = nullptr;
+  int64_t n_p3_irregular = 0;
   // host pipeline plan (hostpipe.cu): for hp_blocks equal blocks of outer indices, the number of leading node coordinates
   // that must be on the device before block b can be computed (running maximum, so monotone)
   int hp_blocks = 0;
@@ -212,6 +221,10 @@ int p1_fan_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p
 // P2 row kernels (assemble_p2.cu): k00 .. km = reference tensors of FeLagrangeO2Tria, [6 * 6] row-major each
 int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p);
 int p2_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, const double alpha[4], int tensor, double gamma,
+                   const double* k00, const double* k01, const double* k10, const double* k11, const double* km, double* d_values);
+// P3 row kernels (assemble_p3.cu): k00 .. km = reference tensors of FeLagrangeO3Tria, [10 * 10] row-major each
+int p3_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p);
+int p3_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, const double alpha[4], int tensor, double gamma,
                    const double* k00, const double* k01, const double* k10, const double* k11, const double* km, double* d_values);
 // body of lfgpu_assemble_reaction_diffusion_rows (assemble.cu) with two extras used by the host pipeline (hostpipe.cu)
 int assemble_rd_impl(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, int degree, const lfgpu_quad* qr_tria,

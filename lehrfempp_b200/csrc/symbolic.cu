@@ -249,6 +249,11 @@ void lfgpu_pattern_destroy(lfgpu_pattern* p) {
   cudaFree(p->p2e_nbr);
   cudaFree(p->p2e_slots);
   cudaFree(p->p2_irregular);
+  cudaFree(p->p3v_nbr);
+  cudaFree(p->p3v_slots);
+  cudaFree(p->p3e_nbr);
+  cudaFree(p->p3e_slots);
+  cudaFree(p->p3_irregular);
   cudaFree(p->o_dofs);
   if (p->i_dofs != p->o_dofs) cudaFree(p->i_dofs);
   cudaFree(p->o_nldof);

@@ -1,0 +1,40 @@
+"""Times the numeric pass of degree p on a TP-triangle mesh with the row kernels (ALGO_FAN) and the item kernel (ALGO_GATHER):
+CUDA events on the ctx stream, warm-up 3, 10 steps each.  usage: rows_probe.py <degree> <n> [rows|items]
+Prints one JSON line (kept under profiles/)."""
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import lehrfempp_b200 as lf  # noqa: E402
+
+degree = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 1448
+only = sys.argv[3] if len(sys.argv) > 3 else ""
+ctx = lf.Context(0)
+mesh = ctx.mesh_tp_tria(n, n)
+pat = mesh.dofmap_lagrange(degree).symbolic(major=lf.ROW_MAJOR)
+vals = ctx.empty(pat.nnz)
+out = {"degree": degree, "cells": mesh.n_cells, "nnz": pat.nnz}
+alpha, gamma = lf.Coeff.const(1.0), lf.Coeff.const(1.0 if degree == 3 else 0.0)  # config C4: stiffness + mass
+nldof = {1: 3, 2: 6, 3: 10}[degree]
+res = {}
+for name, algo in (("rows", lf.ALGO_FAN), ("items", lf.ALGO_GATHER)):
+    if only and name != only:
+        continue
+    for _ in range(3):
+        pat.assemble_reaction_diffusion(degree, alpha, gamma, out=vals, algo=algo)
+    e0, e1 = ctx.event(), ctx.event()
+    ctx.record(e0)
+    for _ in range(10):
+        pat.assemble_reaction_diffusion(degree, alpha, gamma, out=vals, algo=algo)
+    ctx.record(e1)
+    ms = ctx.elapsed_ms(e0, e1) / 10
+    res[name] = vals.to_host()
+    alg_bytes = 4 * nldof * mesh.n_cells + 16 * mesh.n_nodes + 8 * pat.nnz
+    out[name] = {"ms": ms, "cells_per_s": mesh.n_cells / ms * 1e3, "alg_GBs": alg_bytes / ms / 1e6}
+if not only:
+    out["rel_diff"] = float(np.abs(res["rows"] - res["items"]).max() / np.abs(res["items"]).max())
+print(json.dumps(out))
