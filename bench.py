@@ -25,6 +25,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+AUTO_ROW_DEGREES = (1, 2)  # degrees for which LFGPU_ALGO_AUTO runs the row kernels (lehrfempp_b200/csrc/assemble.cu)
+
 WORKLOADS = {
     # name: (description, kind, n, degree)
     "c5_1e8": ("C5: P1 Laplacian (alpha=1, gamma=0), TP-triangle mesh n=7071 (1.0e8 cells), CSR", "tp_tria", 7071, 1),
@@ -206,10 +208,14 @@ def main():
     ctx = lf.Context(local_rank)
     algo = {"auto": lf.ALGO_AUTO, "fan": lf.ALGO_FAN, "gather": lf.ALGO_GATHER, "atomic": lf.ALGO_ATOMIC}[args.algo]
     structured = kind == "tp_tria" or kind.startswith("refined:")
-    row_kernels = {1: "k_assemble_p1_fan", 2: "k_p2_vertex_rows + k_p2_edge_rows"}
-    kernel_name = {"auto": row_kernels[degree] if (degree in row_kernels and structured) else "k_assemble_items",
-                   "fan": dict(row_kernels, **{3: "k_p3_vertex_rows + k_p3_edge_rows + k_p3_cell_rows"})[degree],
-                   "gather": "k_assemble_items", "atomic": "k_assemble_atomic"}[args.algo]
+    # kernels that own matrix rows in registers; AUTO takes them for P1 / P2 (P3: on request, --algo fan)
+    row_kernels = {1: "k_assemble_p1_fan", 2: "k_p2_vertex_rows + k_p2_edge_rows", 3: "k_p3_vertex_rows + k_p3_edge_rows + k_p3_cell_rows"}
+    if args.algo == "auto":
+        kernel_name = row_kernels[degree] if (structured and degree in AUTO_ROW_DEGREES) else "k_assemble_items"
+    elif args.algo == "fan":
+        kernel_name = row_kernels[degree]
+    else:
+        kernel_name = {"gather": "k_assemble_items", "atomic": "k_assemble_atomic"}[args.algo]
 
     # ---- setup (untimed, like mesh / DofHandler construction on the CPU side) ----------------------------------------------
     t_setup = time.time()
