@@ -25,7 +25,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-AUTO_ROW_DEGREES = (1, 2)  # degrees for which LFGPU_ALGO_AUTO runs the row kernels (lehrfempp_b200/csrc/assemble.cu)
+AUTO_ROW_DEGREES = (1, 2, 3)  # degrees for which LFGPU_ALGO_AUTO runs the row kernels (lehrfempp_b200/csrc/assemble.cu)
 
 WORKLOADS = {
     # name: (description, kind, n, degree)
@@ -208,7 +208,7 @@ def main():
     ctx = lf.Context(local_rank)
     algo = {"auto": lf.ALGO_AUTO, "fan": lf.ALGO_FAN, "gather": lf.ALGO_GATHER, "atomic": lf.ALGO_ATOMIC}[args.algo]
     structured = kind == "tp_tria" or kind.startswith("refined:")
-    # kernels that own matrix rows in registers; AUTO takes them for P1 / P2 (P3: on request, --algo fan)
+    # kernels that own matrix rows in registers (LFGPU_ALGO_AUTO takes them on triangle meshes with constant coefficients)
     row_kernels = {1: "k_assemble_p1_fan", 2: "k_p2_vertex_rows + k_p2_edge_rows", 3: "k_p3_vertex_rows + k_p3_edge_rows + k_p3_cell_rows"}
     if args.algo == "auto":
         kernel_name = row_kernels[degree] if (structured and degree in AUTO_ROW_DEGREES) else "k_assemble_items"

@@ -976,9 +976,9 @@ int lfgpu::assemble_rd_impl(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_
         return p2_rows_launch(ctx, mesh, p, a, tensor, dg.c[0], k00, k00 + 36, k00 + 72, k00 + 108, k00 + 144, d_values);
       }
     }
-    // P3 row kernels (assemble_p3.cu), same conditions.  Their host/device core is checked against the oracle on the CPU;
-    // until the CUDA wrappers have been measured on a B200 they are taken on request only (LFGPU_ALGO_FAN or LFGPU_P3_ROWS=1).
-    static const bool p3_env = [] { const char* e = std::getenv("LFGPU_P3_ROWS"); return e != nullptr && e[0] == '1'; }();
+    // P3 row kernels (assemble_p3.cu), same conditions (their host/device core is also checked against the oracle on the CPU);
+    // LFGPU_P3_ROWS=0 keeps LFGPU_ALGO_AUTO on the item kernel.
+    static const bool p3_env = [] { const char* e = std::getenv("LFGPU_P3_ROWS"); return e == nullptr || e[0] != '0'; }();
     if (degree == 3 && fan_query == nullptr && (algo == LFGPU_ALGO_FAN || p3_env) && active == nullptr && beta == 0.0 &&
         d_row_list == nullptr && row0 < 0 && qr_tria == nullptr && qr_quad == nullptr && da.kind <= LFGPU_COEFF_CONST_2X2 &&
         dg.kind == LFGPU_COEFF_CONST && mesh->n_quad == 0 && mesh->cell_coords == nullptr && ht.hdr.nsf[0] == 10) {

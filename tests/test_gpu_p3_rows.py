@@ -3,7 +3,7 @@
 The row kernels take every cell with the row's own vertex / edge as local entity 0, so values differ from the generic
 kernels by rounding only (bar of the path: 1e-12 relative in max-norm); irregular rows (boundary, valence != 6) come from
 the generic gather kernel and must fit in seamlessly.  The arithmetic and index logic are also checked without a GPU
-(tests/test_p3_rows_core.py); these tests cover the CUDA wrappers.  The kernels are taken on request (LFGPU_ALGO_FAN).
+(tests/test_p3_rows_core.py); these tests cover the CUDA wrappers.
 """
 import os
 
