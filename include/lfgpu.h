@@ -53,7 +53,8 @@ typedef enum {
 #define LFGPU_ALGO_AUTO 0
 #define LFGPU_ALGO_ATOMIC 1 /* one thread per (cell, local row), FP64 atomics into the values (supports beta = 1)       */
 #define LFGPU_ALGO_GATHER 2 /* owner-computes: one thread per matrix row gathers its cells, deterministic, no atomics    */
-#define LFGPU_ALGO_FAN 3    /* P1 on triangles with constant coefficients: vertex-fan kernel (AUTO picks it when it applies) */
+#define LFGPU_ALGO_FAN 3    /* triangles with constant coefficients: the kernels that own matrix rows in registers -- P1 vertex-fan
+                               kernel, P2 / P3 row kernels (AUTO picks them when they apply; this value insists on them)       */
 
 /* ---- context ------------------------------------------------------------------------------------------------------ */
 int lfgpu_ctx_create(int device, lfgpu_ctx** out);
@@ -227,7 +228,8 @@ int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofm
                         const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad, const lfgpu_coeff* f, const uint8_t* active,
                         double beta, double* d_vec, int algo);
 /* Same, restricted to the contiguous outer range [row0, row0 + n_rows): the row partition of a multi-GPU run by row
- * blocks (every cell is active).  Runs in the P1 vertex-fan kernel only; LFGPU_ERR_UNSUPPORTED otherwise -- pass the
+ * blocks (every cell is active).  Runs in the kernels that own rows in registers -- the P1 vertex-fan kernel, the P2 / P3
+ * row kernels (triangles, constant coefficients, default rule, beta = 0); LFGPU_ERR_UNSUPPORTED otherwise -- pass the
  * rows as a list to lfgpu_assemble_reaction_diffusion_rows then.                                                    */
 int lfgpu_assemble_reaction_diffusion_range(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* pattern, int degree,
                                             const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad, const lfgpu_coeff* alpha,

@@ -16,6 +16,7 @@
 //                         no zero-fill, no read-modify-write of the value array.
 // Both use the same element-row routine.  Affine cells with cell-wise constant coefficients take the reference-tensor
 // route (5 FMAs per entry); everything else integrates per quadrature point (3 FMAs per entry and point).
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <utility>
@@ -958,7 +959,7 @@ int lfgpu::assemble_rd_impl(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_
     // explicitly; LFGPU_ALGO_AUTO takes them unless LFGPU_P2_ROWS=0.
     static const bool p2_env = [] { const char* e = std::getenv("LFGPU_P2_ROWS"); return e == nullptr || e[0] != '0'; }();
     if (degree == 2 && fan_query == nullptr && (algo == LFGPU_ALGO_FAN || p2_env) && active == nullptr && beta == 0.0 &&
-        d_row_list == nullptr && row0 < 0 && qr_tria == nullptr && qr_quad == nullptr && da.kind <= LFGPU_COEFF_CONST_2X2 &&
+        d_row_list == nullptr && qr_tria == nullptr && qr_quad == nullptr && da.kind <= LFGPU_COEFF_CONST_2X2 &&
         dg.kind == LFGPU_COEFF_CONST && mesh->n_quad == 0 && mesh->cell_coords == nullptr && ht.hdr.nsf[0] == 6) {
       if ((rc = p2_rows_prepare(ctx, mesh, const_cast<lfgpu_pattern*>(p))) != LFGPU_OK) return rc;
       if (p->p2_state == 1) {
@@ -966,21 +967,25 @@ int lfgpu::assemble_rd_impl(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_
         double a[4] = {da.c[0], da.c[1], da.c[2], da.c[3]};
         const int tensor = da.kind == LFGPU_COEFF_CONST_2X2;
         if (tensor && tr) std::swap(a[1], a[2]);
-        if (p->n_p2_irregular > 0) {
+        // all rows, or the contiguous range [row0, row0 + n_rows) of one GPU of a row-block partition
+        const int64_t r0 = row0 >= 0 ? row0 : 0, r1 = row0 >= 0 ? row0 + n_rows : p->n_outer;
+        const auto& irr = p->p2_irregular_host;
+        const int64_t i0 = std::lower_bound(irr.begin(), irr.end(), r0) - irr.begin(), i1 = std::lower_bound(irr.begin(), irr.end(), r1) - irr.begin();
+        if (i1 > i0) {
           rc = lfgpu_assemble_reaction_diffusion_rows(ctx, mesh, p, degree, qr_tria, qr_quad, alpha, gamma, nullptr, beta, d_values,
-                                                      LFGPU_ALGO_GATHER, p->p2_irregular, p->n_p2_irregular);
+                                                      LFGPU_ALGO_GATHER, p->p2_irregular + i0, i1 - i0);
           if (rc != LFGPU_OK) return rc;
         }
         const int nq = ht.hdr.nq[0];
         const double* k00 = ht.blob.data() + ht.hdr.off[0] + 3 * nq + 3 * 6 * nq;  // pack_type: w qx qy | phi gx gy | k00 k01 k10 k11 m
-        return p2_rows_launch(ctx, mesh, p, a, tensor, dg.c[0], k00, k00 + 36, k00 + 72, k00 + 108, k00 + 144, d_values);
+        return p2_rows_launch(ctx, mesh, p, a, tensor, dg.c[0], k00, k00 + 36, k00 + 72, k00 + 108, k00 + 144, d_values, r0, r1);
       }
     }
     // P3 row kernels (assemble_p3.cu), same conditions (their host/device core is also checked against the oracle on the CPU);
     // LFGPU_P3_ROWS=0 keeps LFGPU_ALGO_AUTO on the item kernel.
     static const bool p3_env = [] { const char* e = std::getenv("LFGPU_P3_ROWS"); return e == nullptr || e[0] != '0'; }();
     if (degree == 3 && fan_query == nullptr && (algo == LFGPU_ALGO_FAN || p3_env) && active == nullptr && beta == 0.0 &&
-        d_row_list == nullptr && row0 < 0 && qr_tria == nullptr && qr_quad == nullptr && da.kind <= LFGPU_COEFF_CONST_2X2 &&
+        d_row_list == nullptr && qr_tria == nullptr && qr_quad == nullptr && da.kind <= LFGPU_COEFF_CONST_2X2 &&
         dg.kind == LFGPU_COEFF_CONST && mesh->n_quad == 0 && mesh->cell_coords == nullptr && ht.hdr.nsf[0] == 10) {
       if ((rc = p3_rows_prepare(ctx, mesh, const_cast<lfgpu_pattern*>(p))) != LFGPU_OK) return rc;
       if (p->p3_state == 1) {
@@ -988,14 +993,17 @@ int lfgpu::assemble_rd_impl(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_
         double a[4] = {da.c[0], da.c[1], da.c[2], da.c[3]};
         const int tensor = da.kind == LFGPU_COEFF_CONST_2X2;
         if (tensor && tr) std::swap(a[1], a[2]);
-        if (p->n_p3_irregular > 0) {
+        const int64_t r0 = row0 >= 0 ? row0 : 0, r1 = row0 >= 0 ? row0 + n_rows : p->n_outer;
+        const auto& irr = p->p3_irregular_host;
+        const int64_t i0 = std::lower_bound(irr.begin(), irr.end(), r0) - irr.begin(), i1 = std::lower_bound(irr.begin(), irr.end(), r1) - irr.begin();
+        if (i1 > i0) {
           rc = lfgpu_assemble_reaction_diffusion_rows(ctx, mesh, p, degree, qr_tria, qr_quad, alpha, gamma, nullptr, beta, d_values,
-                                                      LFGPU_ALGO_GATHER, p->p3_irregular, p->n_p3_irregular);
+                                                      LFGPU_ALGO_GATHER, p->p3_irregular + i0, i1 - i0);
           if (rc != LFGPU_OK) return rc;
         }
         const int nq = ht.hdr.nq[0];
         const double* k00 = ht.blob.data() + ht.hdr.off[0] + 3 * nq + 3 * 10 * nq;
-        return p3_rows_launch(ctx, mesh, p, a, tensor, dg.c[0], k00, k00 + 100, k00 + 200, k00 + 300, k00 + 400, d_values);
+        return p3_rows_launch(ctx, mesh, p, a, tensor, dg.c[0], k00, k00 + 100, k00 + 200, k00 + 300, k00 + 400, d_values, r0, r1);
       }
     }
     if (algo == LFGPU_ALGO_FAN) LFGPU_FAIL(ctx, LFGPU_ERR_UNSUPPORTED, "LFGPU_ALGO_FAN needs P1, P2 or P3 on a triangle mesh with constant coefficients and no activity mask");

@@ -271,18 +271,20 @@ __device__ __forceinline__ void write_rows(bool staged, bool regular, bool in_ra
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(128, 4) k_p2_vertex_rows(int n_rows, const int32_t* __restrict__ nbr, const uint32_t* __restrict__ slots,
-                                                         const double* __restrict__ node_coords, const int32_t* __restrict__ outer,
-                                                         int pf_dist, P2Params P, double* __restrict__ values) {
+__global__ void __launch_bounds__(128, 4) k_p2_vertex_rows(int first, int end, int n_rows, const int32_t* __restrict__ nbr,
+                                                         const uint32_t* __restrict__ slots, const double* __restrict__ node_coords,
+                                                         const int32_t* __restrict__ outer, int pf_dist, P2Params P,
+                                                         double* __restrict__ values) {
+  // rows [first, end) of the n_rows vertex rows (the whole range, or one GPU's share of it)
   extern __shared__ double stage_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in_range = r < n_rows;
+  const int r = first + blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = r < end;
   if (pf_dist > 0 && warp == 0) {
     // pull the lines of the CTA that runs about one wave later into L2 (see assemble_p1.cu): 4 lines per plan array
     // (6 ring + 3 slot arrays), 4 of row pointers, 16 of coordinates
-    const int rp = blockIdx.x * blockDim.x + pf_dist;
-    if (rp + 128 <= n_rows) {
+    const int rp = first + blockIdx.x * blockDim.x + pf_dist;
+    if (rp + 128 <= end) {
       for (int L = lane; L < 56; L += 32) {
         const char* a;
         if (L < 24) a = reinterpret_cast<const char*>(nbr + static_cast<size_t>(L >> 2) * n_rows + rp) + (L & 3) * 128;
@@ -351,17 +353,18 @@ __global__ void __launch_bounds__(128, 4) k_p2_vertex_rows(int n_rows, const int
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(128, 4) k_p2_edge_rows(int n_edges, int row0, const int32_t* __restrict__ enb,
+__global__ void __launch_bounds__(128, 4) k_p2_edge_rows(int first, int end, int n_edges, int row0, const int32_t* __restrict__ enb,
                                                        const uint32_t* __restrict__ eslots, const double* __restrict__ node_coords,
                                                        const int32_t* __restrict__ outer, int pf_dist, P2Params P,
                                                        double* __restrict__ values) {
+  // edge rows [first, end) of n_edges; edge e is matrix row row0 + e
   extern __shared__ double stage_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in_range = e < n_edges;
+  const int e = first + blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = e < end;
   if (pf_dist > 0 && warp == 0) {
-    const int ep = blockIdx.x * blockDim.x + pf_dist;
-    if (ep + 128 <= n_edges && lane < 24) {  // 4 lines per id array, 4 of slots, 4 of row pointers
+    const int ep = first + blockIdx.x * blockDim.x + pf_dist;
+    if (ep + 128 <= end && lane < 24) {  // 4 lines per id array, 4 of slots, 4 of row pointers
       const char* a;
       if (lane < 16) a = reinterpret_cast<const char*>(enb + static_cast<size_t>(lane >> 2) * n_edges + ep) + (lane & 3) * 128;
       else if (lane < 20) a = reinterpret_cast<const char*>(eslots + ep) + (lane - 16) * 128;
@@ -476,6 +479,8 @@ int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
   if (n_irr > 0) {
     P2_CHECK(cudaMalloc(&p->p2_irregular, sizeof(int32_t) * n_irr));
     P2_CHECK(cudaMemcpyAsync(p->p2_irregular, iota, sizeof(int32_t) * n_irr, cudaMemcpyDeviceToDevice, st));
+    p->p2_irregular_host.resize(static_cast<size_t>(n_irr));  // ascending; lets a row range find its share of the list
+    P2_CHECK(cudaMemcpyAsync(p->p2_irregular_host.data(), iota, sizeof(int32_t) * n_irr, cudaMemcpyDeviceToHost, st));
     P2_CHECK(cudaStreamSynchronize(st));
   }
 #undef P2_CHECK
@@ -492,8 +497,10 @@ int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
 }
 
 // tables: the reference tensors of FeLagrangeO2Tria for the rule in use, each [6 * 6] row-major (assemble.cu: pack_type)
+// rows [r0, r1) of the matrix (the caller has already sent the irregular rows of the range through the generic kernel)
 int p2_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, const double alpha[4], int tensor, double gamma,
-                   const double* k00, const double* k01, const double* k10, const double* k11, const double* km, double* d_values) {
+                   const double* k00, const double* k01, const double* k10, const double* k11, const double* km, double* d_values,
+                   int64_t r0, int64_t r1) {
   P2Params P;
   P.a00 = alpha[0]; P.a01 = tensor ? alpha[1] : 0.0; P.a10 = tensor ? alpha[2] : 0.0; P.a11 = tensor ? alpha[3] : alpha[0];
   P.gamma = gamma;
@@ -511,17 +518,25 @@ int p2_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* 
   const int ipf_e = static_cast<int>((static_cast<int64_t>(ctx->sm_count) * 12 * threads * pfd_env / 100) & ~static_cast<int64_t>(127));
   const size_t smem_v = sizeof(double) * (threads / 32) * 32 * (kVertexRowLen + 1);
   const size_t smem_e = sizeof(double) * (threads / 32) * 32 * (kEdgeRowLen + 1);
-  const unsigned gv = static_cast<unsigned>(cdiv(nn, threads)), ge = static_cast<unsigned>(cdiv(ne, threads));
-  if (simple) {
-    k_p2_vertex_rows<0><<<gv, threads, smem_v, ctx->stream>>>(nn, p->p2v_nbr, p->p2v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values);
+  // the share of the range in the vertex rows [0, nn) and in the edge rows [nn, nn + ne)
+  const int v_first = static_cast<int>(std::min<int64_t>(std::max<int64_t>(r0, 0), nn)), v_end = static_cast<int>(std::min<int64_t>(r1, nn));
+  const int e_first = static_cast<int>(std::max<int64_t>(r0 - nn, 0)), e_end = static_cast<int>(std::min<int64_t>(std::max<int64_t>(r1 - nn, 0), ne));
+  if (v_end > v_first) {
+    const unsigned gv = static_cast<unsigned>(cdiv(v_end - v_first, threads));
+    if (simple)
+      k_p2_vertex_rows<0><<<gv, threads, smem_v, ctx->stream>>>(v_first, v_end, nn, p->p2v_nbr, p->p2v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values);
+    else
+      k_p2_vertex_rows<1><<<gv, threads, smem_v, ctx->stream>>>(v_first, v_end, nn, p->p2v_nbr, p->p2v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values);
     LFGPU_LAUNCH_CHECK(ctx);
-    k_p2_edge_rows<0><<<ge, threads, smem_e, ctx->stream>>>(ne, nn, p->p2e_nbr, p->p2e_slots, mesh->node_coords, p->outer, ipf_e, P, d_values);
-  } else {
-    k_p2_vertex_rows<1><<<gv, threads, smem_v, ctx->stream>>>(nn, p->p2v_nbr, p->p2v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values);
-    LFGPU_LAUNCH_CHECK(ctx);
-    k_p2_edge_rows<1><<<ge, threads, smem_e, ctx->stream>>>(ne, nn, p->p2e_nbr, p->p2e_slots, mesh->node_coords, p->outer, ipf_e, P, d_values);
   }
-  LFGPU_LAUNCH_CHECK(ctx);
+  if (e_end > e_first) {
+    const unsigned ge = static_cast<unsigned>(cdiv(e_end - e_first, threads));
+    if (simple)
+      k_p2_edge_rows<0><<<ge, threads, smem_e, ctx->stream>>>(e_first, e_end, ne, nn, p->p2e_nbr, p->p2e_slots, mesh->node_coords, p->outer, ipf_e, P, d_values);
+    else
+      k_p2_edge_rows<1><<<ge, threads, smem_e, ctx->stream>>>(e_first, e_end, ne, nn, p->p2e_nbr, p->p2e_slots, mesh->node_coords, p->outer, ipf_e, P, d_values);
+    LFGPU_LAUNCH_CHECK(ctx);
+  }
   return LFGPU_OK;
 }
 

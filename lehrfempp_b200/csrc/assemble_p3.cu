@@ -101,17 +101,19 @@ __device__ __forceinline__ void write_rows(bool staged, bool regular, bool in_ra
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(128, 3) k_p3_vertex_rows(int n_rows, const int32_t* __restrict__ nbr, const uint32_t* __restrict__ slots,
-                                                         const double* __restrict__ node_coords, const int32_t* __restrict__ outer,
-                                                         int pf_dist, Params P, double* __restrict__ values) {
+__global__ void __launch_bounds__(128, 3) k_p3_vertex_rows(int first, int end, int n_rows, const int32_t* __restrict__ nbr,
+                                                         const uint32_t* __restrict__ slots, const double* __restrict__ node_coords,
+                                                         const int32_t* __restrict__ outer, int pf_dist, Params P,
+                                                         double* __restrict__ values) {
+  // rows [first, end) of the n_rows vertex rows (the whole range, or one GPU's share of it)
   extern __shared__ double stage_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in_range = r < n_rows;
+  const int r = first + blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = r < end;
   if (pf_dist > 0 && warp == 0) {
     // lines of the CTA about one wave later: 4 per plan array (6 ring + 9 slot arrays), 4 of row pointers, 16 of coordinates
-    const int rp = blockIdx.x * blockDim.x + pf_dist;
-    if (rp + 128 <= n_rows) {
+    const int rp = first + blockIdx.x * blockDim.x + pf_dist;
+    if (rp + 128 <= end) {
       for (int L = lane; L < 80; L += 32) {
         const char* a;
         if (L < 24) a = reinterpret_cast<const char*>(nbr + static_cast<size_t>(L >> 2) * n_rows + rp) + (L & 3) * 128;
@@ -158,17 +160,18 @@ __global__ void __launch_bounds__(128, 3) k_p3_vertex_rows(int n_rows, const int
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(128, 4) k_p3_edge_rows(int n_erows, int row0, const int32_t* __restrict__ enb,
+__global__ void __launch_bounds__(128, 4) k_p3_edge_rows(int first, int end, int n_erows, int row0, const int32_t* __restrict__ enb,
                                                        const uint32_t* __restrict__ eslots, const double* __restrict__ node_coords,
                                                        const int32_t* __restrict__ outer, int pf_dist, Params P,
                                                        double* __restrict__ values) {
+  // edge-dof rows [first, end) of n_erows; row e of them is matrix row row0 + e
   extern __shared__ double stage_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in_range = e < n_erows;
+  const int e = first + blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = e < end;
   if (pf_dist > 0 && warp == 0) {
-    const int ep = blockIdx.x * blockDim.x + pf_dist;
-    if (ep + 128 <= n_erows && lane < 28) {  // 4 lines per id array, 4 per slot array, 4 of row pointers
+    const int ep = first + blockIdx.x * blockDim.x + pf_dist;
+    if (ep + 128 <= end && lane < 28) {  // 4 lines per id array, 4 per slot array, 4 of row pointers
       const char* a;
       if (lane < 16) a = reinterpret_cast<const char*>(enb + static_cast<size_t>(lane >> 2) * n_erows + ep) + (lane & 3) * 128;
       else if (lane < 24) a = reinterpret_cast<const char*>(eslots + static_cast<size_t>((lane - 16) >> 2) * n_erows + ep) + (lane & 3) * 128;
@@ -204,13 +207,15 @@ __global__ void __launch_bounds__(128, 4) k_p3_edge_rows(int n_erows, int row0, 
 
 // one thread per cell: row 9 of its element matrix; needs no plan (cell_nodes + the scatter-map row of list position 9)
 template <int MODE>
-__global__ void __launch_bounds__(128, 4) k_p3_cell_rows(int n_cells, int row0, int o_stride, int pos_row, const uint32_t* __restrict__ cell_nodes,
-                                                       const uint8_t* __restrict__ pos, const double* __restrict__ node_coords,
-                                                       const int32_t* __restrict__ outer, Params P, double* __restrict__ values) {
+__global__ void __launch_bounds__(128, 4) k_p3_cell_rows(int first, int end, int row0, int o_stride, int pos_row,
+                                                       const uint32_t* __restrict__ cell_nodes, const uint8_t* __restrict__ pos,
+                                                       const double* __restrict__ node_coords, const int32_t* __restrict__ outer, Params P,
+                                                       double* __restrict__ values) {
+  // cells [first, end); cell c is matrix row row0 + c
   extern __shared__ double stage_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in_range = c < n_cells;
+  const int c = first + blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = c < end;
   int32_t v0 = 0, v1 = 0;
   if (in_range) {
     v0 = __ldg(outer + row0 + c);
@@ -303,6 +308,8 @@ int p3_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
   if (n_irr > 0) {
     P3_CHECK(cudaMalloc(&p->p3_irregular, sizeof(int32_t) * n_irr));
     P3_CHECK(cudaMemcpyAsync(p->p3_irregular, iota, sizeof(int32_t) * n_irr, cudaMemcpyDeviceToDevice, st));
+    p->p3_irregular_host.resize(static_cast<size_t>(n_irr));  // ascending; lets a row range find its share of the list
+    P3_CHECK(cudaMemcpyAsync(p->p3_irregular_host.data(), iota, sizeof(int32_t) * n_irr, cudaMemcpyDeviceToHost, st));
     P3_CHECK(cudaStreamSynchronize(st));
   }
 #undef P3_CHECK
@@ -318,8 +325,10 @@ int p3_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
 }
 
 // k00 .. km: the reference tensors of FeLagrangeO3Tria for the rule in use, each [10 * 10] row-major (assemble.cu: pack_type)
+// rows [r0, r1) of the matrix (the caller has already sent the irregular rows of the range through the generic kernel)
 int p3_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, const double alpha[4], int tensor, double gamma,
-                   const double* k00, const double* k01, const double* k10, const double* k11, const double* km, double* d_values) {
+                   const double* k00, const double* k01, const double* k10, const double* k11, const double* km, double* d_values,
+                   int64_t r0, int64_t r1) {
   Params P;
   P.a00 = alpha[0]; P.a01 = tensor ? alpha[1] : 0.0; P.a10 = tensor ? alpha[2] : 0.0; P.a11 = tensor ? alpha[3] : alpha[0];
   P.gamma = gamma;
@@ -339,21 +348,32 @@ int p3_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* 
   const size_t smem_v = sizeof(double) * (threads / 32) * 32 * (kVertexRowLen + 1);
   const size_t smem_e = sizeof(double) * (threads / 32) * 32 * (kEdgeRowLen + 1);
   const size_t smem_c = sizeof(double) * (threads / 32) * 32 * (kCellRowLen + 1);
-  const unsigned gv = static_cast<unsigned>(cdiv(nn, threads)), ge = static_cast<unsigned>(cdiv(ner, threads)),
-                 gc = static_cast<unsigned>(cdiv(nc, threads));
   const uint8_t* pos = static_cast<const uint8_t*>(p->pos);
+  // the share of the range in the vertex rows [0, nn), the edge-dof rows [nn, base_int) and the cell rows [base_int, N)
+  auto clip = [](int64_t v, int64_t lo, int64_t hi) { return static_cast<int>(std::min<int64_t>(std::max<int64_t>(v, lo), hi)); };
+  const int v_first = clip(r0, 0, nn), v_end = clip(r1, 0, nn);
+  const int e_first = clip(r0 - nn, 0, ner), e_end = clip(r1 - nn, 0, ner);
+  const int c_first = clip(r0 - base_int, 0, nc), c_end = clip(r1 - base_int, 0, nc);
 #define P3_LAUNCH(MODE)                                                                                                                   \
-  k_p3_vertex_rows<MODE><<<gv, threads, smem_v, ctx->stream>>>(nn, p->p3v_nbr, p->p3v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values); \
-  LFGPU_LAUNCH_CHECK(ctx);                                                                                                                \
-  k_p3_edge_rows<MODE><<<ge, threads, smem_e, ctx->stream>>>(ner, nn, p->p3e_nbr, p->p3e_slots, mesh->node_coords, p->outer, ipf_e, P, d_values); \
-  LFGPU_LAUNCH_CHECK(ctx);                                                                                                                \
-  k_p3_cell_rows<MODE><<<gc, threads, smem_c, ctx->stream>>>(nc, base_int, p->o_stride, p->pos_row, mesh->cell_nodes, pos, mesh->node_coords,    \
-                                                             p->outer, P, d_values);                                                    \
-  LFGPU_LAUNCH_CHECK(ctx)
+  if (v_end > v_first) {                                                                                                                  \
+    k_p3_vertex_rows<MODE><<<static_cast<unsigned>(cdiv(v_end - v_first, threads)), threads, smem_v, ctx->stream>>>(                      \
+        v_first, v_end, nn, p->p3v_nbr, p->p3v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values);                                   \
+    LFGPU_LAUNCH_CHECK(ctx);                                                                                                              \
+  }                                                                                                                                       \
+  if (e_end > e_first) {                                                                                                                  \
+    k_p3_edge_rows<MODE><<<static_cast<unsigned>(cdiv(e_end - e_first, threads)), threads, smem_e, ctx->stream>>>(                        \
+        e_first, e_end, ner, nn, p->p3e_nbr, p->p3e_slots, mesh->node_coords, p->outer, ipf_e, P, d_values);                              \
+    LFGPU_LAUNCH_CHECK(ctx);                                                                                                              \
+  }                                                                                                                                       \
+  if (c_end > c_first) {                                                                                                                  \
+    k_p3_cell_rows<MODE><<<static_cast<unsigned>(cdiv(c_end - c_first, threads)), threads, smem_c, ctx->stream>>>(                        \
+        c_first, c_end, base_int, p->o_stride, p->pos_row, mesh->cell_nodes, pos, mesh->node_coords, p->outer, P, d_values);              \
+    LFGPU_LAUNCH_CHECK(ctx);                                                                                                              \
+  }
   if (simple) {
-    P3_LAUNCH(0);
+    P3_LAUNCH(0)
   } else {
-    P3_LAUNCH(1);
+    P3_LAUNCH(1)
   }
 #undef P3_LAUNCH
   return LFGPU_OK;

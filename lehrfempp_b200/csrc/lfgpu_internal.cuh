@@ -124,8 +124,9 @@ struct lfgpu_pattern {
   uint32_t* p2v_slots = nullptr;     // [3][p2_nn] 6 x 5 bits each: slots of the neighbour / spoke-edge / rim-edge columns
   int32_t* p2e_nbr = nullptr;        // [4][n_edges] endpoints p, q and opposite vertices o_1, o_2 of every edge row
   uint32_t* p2e_slots = nullptr;     // [n_edges] 8 x 4 bits: slots of p, q, o_1, o_2, (q,o_1), (o_1,p), (q,o_2), (o_2,p)
-  int32_t* p2_irregular = nullptr;   // rows left to the generic gather kernel
+  int32_t* p2_irregular = nullptr;   // rows left to the generic gather kernel (ascending)
   int64_t n_p2_irregular = 0;
+  std::vector<int32_t> p2_irregular_host;  // host copy: a row range looks up its share of the list
   // P3 row-kernel plan (assemble_p3.cu, rows_p3_core.h): vertex rows [0, p3_nn), edge-dof rows, then one row per cell
   int p3_state = 0;
   int64_t p3_nn = 0;
@@ -135,6 +136,7 @@ struct lfgpu_pattern {
   uint32_t* p3e_slots = nullptr;     // [2][n_edge_rows] 16 slot nibbles per row
   int32_t* p3_irregular = nullptr;
   int64_t n_p3_irregular = 0;
+  std::vector<int32_t> p3_irregular_host;
   // host pipeline plan (hostpipe.cu): for hp_blocks equal blocks of outer indices, the number of leading node coordinates
   // that must be on the device before block b can be computed (running maximum, so monotone)
   int hp_blocks = 0;
@@ -221,11 +223,13 @@ int p1_fan_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p
 // P2 row kernels (assemble_p2.cu): k00 .. km = reference tensors of FeLagrangeO2Tria, [6 * 6] row-major each
 int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p);
 int p2_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, const double alpha[4], int tensor, double gamma,
-                   const double* k00, const double* k01, const double* k10, const double* k11, const double* km, double* d_values);
+                   const double* k00, const double* k01, const double* k10, const double* k11, const double* km, double* d_values,
+                   int64_t r0, int64_t r1);
 // P3 row kernels (assemble_p3.cu): k00 .. km = reference tensors of FeLagrangeO3Tria, [10 * 10] row-major each
 int p3_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p);
 int p3_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, const double alpha[4], int tensor, double gamma,
-                   const double* k00, const double* k01, const double* k10, const double* k11, const double* km, double* d_values);
+                   const double* k00, const double* k01, const double* k10, const double* k11, const double* km, double* d_values,
+                   int64_t r0, int64_t r1);
 // body of lfgpu_assemble_reaction_diffusion_rows (assemble.cu) with two extras used by the host pipeline (hostpipe.cu)
 int assemble_rd_impl(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, int degree, const lfgpu_quad* qr_tria,
                      const lfgpu_quad* qr_quad, const lfgpu_coeff* alpha, const lfgpu_coeff* gamma, const uint8_t* active, double beta,
