@@ -32,7 +32,7 @@ def test_ranges_tile_the_full_pass(ctx, lf, degree, gamma):
     n = outer.size - 1
     a, g = lf.Coeff.const(1.5), lf.Coeff.const(gamma)
     full = pat.assemble_reaction_diffusion(degree, a, g, algo=lf.ALGO_FAN).to_host()
-    # cuts inside the vertex rows, inside the edge rows, (P3) inside the cell rows, and one-row / empty pieces
+    # cuts inside the vertex rows, inside the edge rows, (P3) inside the cell rows, and one-row pieces
     cuts = sorted({0, 1, 17, gm.n_nodes // 2 + 3, gm.n_nodes, gm.n_nodes + 5, (gm.n_nodes + n) // 2 + 1, n - gm.n_cells // 3, n - 1, n})
     out = ctx.to_device(np.full(pat.nnz, np.nan))
     for r0, r1 in zip(cuts[:-1], cuts[1:]):
