@@ -270,3 +270,32 @@ def test_all_reference_test_meshes_build(golden_meshes, sel):
             assert en == {int(ex["cell_nodes"][c, j]), int(ex["cell_nodes"][c, (j + 1) % nv])}
     if sel == "4":
         assert (m.n_cells, m.n_edges, m.n_nodes) == (18, 33, 16)
+
+
+# ---- lagr_fe_tests.cc:497-532 (lf_fe_ellbvp): alpha = 1, gamma = 0 against the closed-form LinearFELaplaceElementMatrix -------
+def test_p1_laplace_element_matrices_closed_form(golden_meshes):
+    """uscalfe/lin_fe.cc:39-160: triangles -> |K| grad(lambda_i).grad(lambda_j) with constant barycentric gradients;
+    quadrilaterals -> 2x2 Gauss rule on the bilinear parametrisation.  The reference asks 1e-2 in the Frobenius norm; the
+    two computations are the same integrals (the default rule of degree 2 is exact / is that Gauss rule), so 1e-12 here."""
+    m = mesh0(golden_meshes)
+    ex = m.export()
+    mats = m.element_matrices(1, lfo.coeff.const(1.0), lfo.coeff.const(0.0))
+    g = 0.5 / np.sqrt(3.0)
+    gauss = [0.5 - g, 0.5 + g]
+    for c in range(m.n_cells):
+        nv = 3 if ex["cell_type"][c] == 3 else 4
+        p = ex["cell_coords"][c, :nv]
+        if nv == 3:
+            area2 = (p[1, 0] - p[0, 0]) * (p[2, 1] - p[0, 1]) - (p[2, 0] - p[0, 0]) * (p[1, 1] - p[0, 1])
+            grads = np.array([[p[(i + 1) % 3, 1] - p[(i + 2) % 3, 1], p[(i + 2) % 3, 0] - p[(i + 1) % 3, 0]] for i in range(3)]) / area2
+            ref = 0.5 * abs(area2) * grads @ grads.T
+        else:
+            ref = np.zeros((4, 4))
+            for x0 in gauss:
+                for x1 in gauss:
+                    dphi = np.array([[-(1 - x1), -(1 - x0)], [1 - x1, -x0], [x1, x0], [-x1, 1 - x0]])  # bilinear shape functions
+                    J = p.T @ dphi
+                    G = dphi @ np.linalg.inv(J)
+                    ref += 0.25 * abs(np.linalg.det(J)) * G @ G.T
+        A = mats[c][:nv, :nv]
+        assert np.linalg.norm(A - ref) <= 1e-12 * max(1.0, np.linalg.norm(ref))
