@@ -17,6 +17,7 @@
 #ifndef LF_GPU_SHIM_HPP
 #define LF_GPU_SHIM_HPP
 
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <map>
@@ -133,6 +134,103 @@ void FlattenDofs(const DOFH& dofh, const MESH& mesh, std::vector<std::int64_t>& 
     n_ldof[c] = static_cast<std::uint8_t>(n);
   }
 }
+
+// ---- Gmsh input ------------------------------------------------------------------------------------------------------------
+// lf::io::GmshReader (lib/lf/io/gmsh_reader.h:55-200) with the reference's member names.  The reference identifies an
+// entity by `const mesh::Entity&`; here an entity is (codim, index) with the indices reader.mesh() assigns -- the
+// numbering lfgpu_gmsh_mesh reproduces on the device (nodes and cells in file order, explicitly listed edges first).
+// Errors of the reference (base::LfException: unknown / ambiguous names, unreadable files) become lfgpu::Error.
+class GmshReader {
+ public:
+  using size_type = unsigned int;
+  using dim_t = int;  // the reference's default "codim not given" is static_cast<dim_t>(-1)
+  explicit GmshReader(const std::string& filename, int dim_world = 2) {
+    const int rc = lfgpu_gmsh_read_file(filename.c_str(), dim_world, &g_);
+    if (rc != 0) throw Error(rc, std::string("GmshReader: ") + lfgpu_last_error(nullptr));
+    lfgpu_gmsh_counts(g_, &n_nodes_, &n_explicit_edges_, &n_cells_, &order_, &n_names_);
+  }
+  GmshReader(const void* data, std::int64_t n_bytes, int dim_world = 2) {
+    const int rc = lfgpu_gmsh_read_memory(data, n_bytes, dim_world, &g_);
+    if (rc != 0) throw Error(rc, std::string("GmshReader: ") + lfgpu_last_error(nullptr));
+    lfgpu_gmsh_counts(g_, &n_nodes_, &n_explicit_edges_, &n_cells_, &order_, &n_names_);
+  }
+  ~GmshReader() { lfgpu_gmsh_destroy(g_); }
+  GmshReader(const GmshReader&) = delete;
+  GmshReader& operator=(const GmshReader&) = delete;
+
+  // reader.mesh(): the mesh on the device (caller owns the handle: lfgpu_mesh_destroy)
+  [[nodiscard]] lfgpu_mesh* mesh(const Context& ctx) const {
+    lfgpu_mesh* m = nullptr;
+    ctx.check(lfgpu_gmsh_mesh(ctx.get(), g_, &m), "lfgpu_gmsh_mesh");
+    return m;
+  }
+  // the arguments of the reference's AddPoint / AddEntity calls, for a caller that builds its own mesh object
+  [[nodiscard]] FlatMesh Flat(std::vector<std::uint32_t>* explicit_edges = nullptr) const {
+    FlatMesh f;
+    f.n_nodes = n_nodes_;
+    f.n_cells = n_cells_;
+    f.node_coords.assign(2 * n_nodes_, 0.0);
+    f.cell_nodes.assign(4 * n_cells_, LFGPU_IDX_NIL);
+    std::vector<std::uint32_t> en(2 * n_explicit_edges_);
+    lfgpu_gmsh_arrays(g_, f.node_coords.data(), en.data(), f.cell_nodes.data());
+    if (explicit_edges != nullptr) *explicit_edges = std::move(en);
+    return f;
+  }
+  [[nodiscard]] std::int64_t NumEntities(dim_t codim) const { return codim == 0 ? n_cells_ : (codim == 1 ? n_explicit_edges_ : n_nodes_); }
+  [[nodiscard]] int GeometryOrder() const { return order_; }
+
+  // gmsh_reader.cc:30-99
+  [[nodiscard]] size_type PhysicalEntityName2Nr(const std::string& name, dim_t codim = -1) const {
+    std::uint32_t nr = 0;
+    const int rc = lfgpu_gmsh_physical_name2nr(g_, name.c_str(), codim, &nr);
+    if (rc != 0) throw Error(rc, lfgpu_last_error(nullptr));
+    return nr;
+  }
+  [[nodiscard]] std::string PhysicalEntityNr2Name(size_type number, dim_t codim = -1) const {
+    char buf[512];
+    const int rc = lfgpu_gmsh_physical_nr2name(g_, number, codim, buf, sizeof(buf));
+    if (rc < 0) throw Error(rc, lfgpu_last_error(nullptr));
+    return buf;
+  }
+  // gmsh_reader.cc:101-113
+  [[nodiscard]] std::vector<std::pair<size_type, std::string>> PhysicalEntities(dim_t codim) const {
+    std::vector<std::pair<size_type, std::string>> result;
+    for (int i = 0; i < n_names_; ++i) {
+      std::uint32_t nr = 0;
+      int cd = 0;
+      char buf[512];
+      lfgpu_gmsh_physical_name(g_, i, &nr, &cd, buf, sizeof(buf));
+      if (cd == codim) result.emplace_back(nr, buf);
+    }
+    return result;
+  }
+  // gmsh_reader.cc:17-23, 115-118 with the entity given as (codim, index)
+  [[nodiscard]] std::vector<size_type> PhysicalEntityNr(dim_t codim, std::int64_t index) const {
+    std::uint32_t tmp[32];
+    const int n = lfgpu_gmsh_physical_entity_nr(g_, codim, index, 32, tmp);
+    if (n < 0) throw Error(n, "PhysicalEntityNr: no such entity");
+    std::vector<size_type> out(static_cast<std::size_t>(n));
+    if (n > 32) lfgpu_gmsh_physical_entity_nr(g_, codim, index, n, out.data());
+    else std::copy(tmp, tmp + n, out.begin());
+    return out;
+  }
+  [[nodiscard]] bool IsPhysicalEntity(dim_t codim, std::int64_t index, size_type physical_entity_nr) const {
+    const auto nrs = PhysicalEntityNr(codim, index);
+    return std::find(nrs.begin(), nrs.end(), physical_entity_nr) != nrs.end();
+  }
+  // the same for all n entities of a codimension at once: the selector arrays the device calls take
+  [[nodiscard]] std::vector<std::uint8_t> PhysicalEntityFlags(dim_t codim, size_type physical_entity_nr, std::int64_t n) const {
+    std::vector<std::uint8_t> flags(static_cast<std::size_t>(n), 0);
+    lfgpu_gmsh_physical_flags(g_, codim, physical_entity_nr, n, flags.data());
+    return flags;
+  }
+  [[nodiscard]] const lfgpu_gmsh* get() const { return g_; }
+
+ private:
+  lfgpu_gmsh* g_ = nullptr;
+  std::int64_t n_nodes_ = 0, n_explicit_edges_ = 0, n_cells_ = 0;
+  int order_ = 1, n_names_ = 0;
+};
 
 // ---- device-side targets ---------------------------------------------------------------------------------------------------
 // Compressed matrix on the GPU, the TMPMATRIX of the GPU overload.  Like COOMatrix it ACCUMULATES: AssembleMatrixLocally

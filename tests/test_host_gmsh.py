@@ -92,3 +92,13 @@ def test_non_consecutive_repetition_is_not_merged():
     assert g.n_explicit_edges == 2 and g.n_cells == 2
     assert g.physical_entity_nr(1, 0) == [7, 8] == o.physical_entity_nr(1, 0)
     assert g.physical_entity_nr(1, 1) == [9] and g.physical_entity_nr(0, 1) == [6]
+
+
+def test_shim_reader_passes_the_reference_reader_tests():
+    """tests/cpp/gmsh_shim_test.cc: checkTwoElementMesh / checkPieceOfCake of gmsh_reader_tests.cc against lfgpu::GmshReader
+    (the C++ shim class with the reference's member names)."""
+    import subprocess
+    cpp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp")
+    subprocess.check_call(["make", "-C", cpp, "-s", "gmsh_shim_test"])
+    out = subprocess.run([os.path.join(cpp, "gmsh_shim_test"), MSH], capture_output=True, text=True)
+    assert out.returncode == 0 and "GMSH_SHIM_TEST_OK" in out.stdout, out.stdout + out.stderr
