@@ -14,8 +14,8 @@
 namespace lfgpu {
 
 constexpr int kMaxNsf = 16;  // FeLagrangeO3Quad
-constexpr int kMaxNq = 36;
-constexpr int kItemThreads = 256;  // block size of the item-parallel kernel = max items of one block of the plan   // largest user quadrature rule the tables hold (6x6 Gauss / 33-point triangle rule)
+constexpr int kMaxNq = 36;         // largest user quadrature rule the tables hold (6x6 Gauss / 33-point triangle rule)
+constexpr int kItemThreads = 256;  // block size of the item-parallel kernel = max items of one block of the plan
 
 void set_last_error(const lfgpu_ctx* ctx, const std::string& msg);
 
