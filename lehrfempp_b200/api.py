@@ -368,7 +368,7 @@ class GmshReader:
 
     def _check(self, rc):
         if rc < 0:
-            raise LfgpuError(rc, (self.L.lfgpu_last_error(None) or b"").decode())
+            raise LfgpuError(rc, (self.L.lfgpu_last_error(None) or b"").decode(errors="replace"))
         return rc
 
     def __del__(self):
@@ -405,7 +405,7 @@ class GmshReader:
             buf = C.create_string_buffer(256)
             self._check(self.L.lfgpu_gmsh_physical_name(self.h, i, C.byref(nr), C.byref(cd), buf, 256))
             if cd.value == codim:
-                res.append((nr.value, buf.value.decode()))
+                res.append((nr.value, buf.value.decode(errors="replace")))
         return sorted(res)
 
     def name2nr(self, name, codim=-1):
@@ -416,7 +416,7 @@ class GmshReader:
     def nr2name(self, nr, codim=-1):
         buf = C.create_string_buffer(256)
         self._check(self.L.lfgpu_gmsh_physical_nr2name(self.h, nr, codim, buf, 256))
-        return buf.value.decode()
+        return buf.value.decode(errors="replace")
 
     def mesh(self, ctx):
         h = C.c_void_p()

