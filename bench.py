@@ -376,7 +376,10 @@ def main():
         e2e_blocks = int(os.environ.get("LFGPU_E2E_BLOCKS", "16"))
         # owner_rows on the fan kernel: every rank runs the host-buffer call for ITS row block -- uploads only the coordinate
         # window its rows refer to and downloads only its rows (lfgpu_assemble_reaction_diffusion_host_range)
-        range_mode = asm is not None and asm.mode == "owner_rows" and getattr(asm, "_range_ok", False) and args.algo in ("auto", "fan")
+        # (P1 only: the P2 / P3 row kernels also take row ranges, but the host-buffer range call knows the coordinate window of
+        # the fan kernel only -- they go through the generic upload / step / download sequence below)
+        range_mode = (asm is not None and asm.mode == "owner_rows" and getattr(asm, "_range_ok", False) and args.algo in ("auto", "fan")
+                      and degree == 1)
         h2d_rank = 16 * mesh.n_nodes
         if range_mode:
             inner_t = torch.as_tensor(pat.download()[1], device="cuda")
