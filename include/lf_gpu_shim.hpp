@@ -738,6 +738,26 @@ void FixFlaggedSolutionCompAlt(SELECTOR&& selectvals, CsrMatrix& A, Vector& b) {
   detail::fix_components(selectvals, A, b, true);
 }
 
+// lf::assemble::FixSolutionComponentsLse (fix_dof.h:250-280): the prescribed components come as (index, value) pairs --
+// values of a repeated index ADD UP (:268) -- and are imposed through the row-only variant (:272-279).
+template <class SCALAR = double>
+using fixed_components_t = std::vector<std::pair<std::int64_t, SCALAR>>;  // fix_dof.h:222-223
+template <class SCALAR = double>
+void FixSolutionComponentsLse(const fixed_components_t<SCALAR>& fixed_components, CsrMatrix& A, Vector& b) {
+  const std::int64_t N = A.cols();
+  if (A.rows() != N) throw Error(LFGPU_ERR_INVALID, "Matrix must be square!");
+  if (b.size() != N) throw Error(LFGPU_ERR_INVALID, "Mismatch of matrix and right-hand-side size");
+  std::vector<double> fixed_vec(static_cast<std::size_t>(N), 0.0);
+  std::vector<char> fixed_comp_flags(static_cast<std::size_t>(N), 0);
+  for (const auto& idx_val_pair : fixed_components) {
+    if (idx_val_pair.first < 0 || idx_val_pair.first >= N) throw Error(LFGPU_ERR_INVALID, "Index " + std::to_string(idx_val_pair.first) + " >= N");
+    fixed_vec[static_cast<std::size_t>(idx_val_pair.first)] += idx_val_pair.second;
+    fixed_comp_flags[static_cast<std::size_t>(idx_val_pair.first)] = 1;
+  }
+  FixFlaggedSolutionCompAlt<SCALAR>(
+      [&](std::int64_t i) { return std::make_pair(fixed_comp_flags[static_cast<std::size_t>(i)] != 0, fixed_vec[static_cast<std::size_t>(i)]); }, A, b);
+}
+
 // Conjugate gradients on the device for the (symmetric positive definite) system held by A and b -- the step the
 // reference does with an Eigen solver on makeSparse() (homDir_linfe_demo.cc:166-175).  Returns the solution on the host.
 inline std::vector<double> SolveCG(CsrMatrix& A, Vector& b, double rel_tol = 1e-10, int max_iter = 10000, int* iterations = nullptr,

@@ -79,6 +79,8 @@ def lib():
         L.lfo_assemble_edge_load.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(Coeff), C.c_void_p, C.c_void_p]
         L.lfo_fix_coo.restype = C.c_void_p
         L.lfo_fix_coo.argtypes = [C.c_int64, C.c_int64] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
+        L.lfo_fix_coo_lse.restype = C.c_void_p
+        L.lfo_fix_coo_lse.argtypes = [C.c_int64, C.c_int64] + [C.c_void_p] * 3 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.lfo_cm_sizes.argtypes = [C.c_void_p] + [C.POINTER(C.c_int64)] * 3
         L.lfo_cm_export.argtypes = [C.c_void_p] * 4
         L.lfo_cm_free.argtypes = [C.c_void_p]
@@ -453,6 +455,27 @@ def fix_coo(n, rows, cols, vals, fixed, fixed_vals, rhs, alt=False):
     fixed_vals = np.ascontiguousarray(fixed_vals, dtype=np.float64)
     rhs = np.array(rhs, dtype=np.float64)
     h = lib().lfo_fix_coo(n, len(vals), _p(rows), _p(cols), _p(vals), _p(fixed), _p(fixed_vals), 1 if alt else 0, _p(rhs))
+    _check(h)
+    r, c, nnz = C.c_int64(), C.c_int64(), C.c_int64()
+    lib().lfo_cm_sizes(h, C.byref(r), C.byref(c), C.byref(nnz))
+    outer = np.zeros(c.value + 1, np.int32)
+    inner = np.zeros(nnz.value, np.int32)
+    out = np.zeros(nnz.value)
+    lib().lfo_cm_export(h, _p(outer), _p(inner), _p(out))
+    lib().lfo_cm_free(h)
+    return outer, inner, out, rhs
+
+
+def fix_coo_lse(n, rows, cols, vals, pairs, rhs):
+    """FixSolutionComponentsLse on an n x n triplet list with prescribed components [(index, value), ...]; returns
+    (outer, inner, values) of makeSparse() (column-major) and the modified right-hand side."""
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    cols = np.ascontiguousarray(cols, dtype=np.int32)
+    vals = np.ascontiguousarray(vals, dtype=np.float64)
+    idx = np.ascontiguousarray([p[0] for p in pairs], dtype=np.int64)
+    val = np.ascontiguousarray([p[1] for p in pairs], dtype=np.float64)
+    rhs = np.array(rhs, dtype=np.float64)
+    h = lib().lfo_fix_coo_lse(n, len(vals), _p(rows), _p(cols), _p(vals), len(idx), _p(idx), _p(val), _p(rhs))
     _check(h)
     r, c, nnz = C.c_int64(), C.c_int64(), C.c_int64()
     lib().lfo_cm_sizes(h, C.byref(r), C.byref(c), C.byref(nnz))

@@ -427,6 +427,25 @@ void FixFlaggedSolutionCompAlt(SELECTOR&& selectvals, COOMatrix& A, RHSVECTOR& b
   }
 }
 
+// lib/lf/assemble/fix_dof.h:250-280: prescribed components as (index, value) pairs; values of a repeated index add up
+// (:268); imposed through the row-only variant (:272-279).
+using fixed_components_t = std::vector<std::pair<gdof_idx_t, double>>;
+template <typename RHSVECTOR>
+void FixSolutionComponentsLse(const fixed_components_t& fixed_components, COOMatrix& A, RHSVECTOR& b) {
+  const gdof_idx_t N = A.cols();
+  LFO_VERIFY(A.rows() == N, "Matrix must be square!");
+  std::vector<double> fixed_vec(N, 0.0);
+  std::vector<bool> fixed_comp_flags(N, false);
+  for (const auto& idx_val_pair : fixed_components) {
+    LFO_VERIFY(idx_val_pair.first < N, "Index >= N");
+    fixed_vec[idx_val_pair.first] += idx_val_pair.second;
+    fixed_comp_flags[idx_val_pair.first] = true;
+  }
+  FixFlaggedSolutionCompAlt(
+      [&fixed_comp_flags, &fixed_vec](gdof_idx_t i) -> std::pair<bool, double> { return std::make_pair(fixed_comp_flags[i], fixed_vec[i]); }, A,
+      b);
+}
+
 // lib/lf/assemble/assembler.h:114-186
 template <typename TMPMATRIX, typename ENTITY_MATRIX_PROVIDER>
 void AssembleMatrixLocally(dim_t codim, const DofHandler& dof_handler_trial, const DofHandler& dof_handler_test,

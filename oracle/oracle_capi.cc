@@ -526,6 +526,21 @@ void* lfo_fix_coo(std::int64_t n, std::int64_t n_trip, const std::int32_t* rows,
   LFO_CATCH(nullptr)
 }
 
+// FixSolutionComponentsLse (fix_dof.h:250-280) on a triplet list: prescribed components as (index, value) pairs
+void* lfo_fix_coo_lse(std::int64_t n, std::int64_t n_trip, const std::int32_t* rows, const std::int32_t* cols, const double* vals,
+                      std::int64_t n_pairs, const std::int64_t* pair_idx, const double* pair_val, double* rhs) {
+  LFO_TRY
+  assemble::COOMatrix coo(static_cast<size_type>(n), static_cast<size_type>(n));
+  for (std::int64_t k = 0; k < n_trip; ++k) coo.AddToEntry(rows[k], cols[k], vals[k]);
+  std::vector<double> b(rhs, rhs + n);
+  assemble::fixed_components_t fixed;
+  for (std::int64_t k = 0; k < n_pairs; ++k) fixed.emplace_back(pair_idx[k], pair_val[k]);
+  assemble::FixSolutionComponentsLse(fixed, coo, b);
+  std::copy(b.begin(), b.end(), rhs);
+  return new assemble::CompressedMatrix(coo.makeSparse());
+  LFO_CATCH(nullptr)
+}
+
 // ---- edge (codim-1) contributions: SURVEY section 8f row 2 -----------------------------------------------------------
 namespace {
 // edges with exactly one adjacent cell (mesh/utils: flagEntitiesOnBoundary(mesh, 1) / CountNumSuperEntities(mesh, 1, 1))

@@ -122,7 +122,7 @@ int main() {
       std::printf("load vector P%d on hybrid mesh                  N=%6zu rel.err=%.2e\n", p, h.size(), err / scale);
     }
     // Dirichlet elimination (fix_dof.h:86-138,181-218): assemble A, b, fix every third dof, compare operator and rhs
-    for (int variant = 0; variant < 2; ++variant) {
+    for (int variant = 0; variant < 3; ++variant) {  // 2 = FixSolutionComponentsLse: (index, value) pairs, repeated indices add up
       const int p = 2;
       auto fes = std::make_shared<uscalfe::UniformScalarFESpace>(hyb, p);
       const assemble::DofHandler& dofh = fes->LocGlobMap();
@@ -134,10 +134,16 @@ int main() {
       uscalfe::ScalarLoadElementVectorProvider<OC> olprov(fes, OC(3.0));
       std::vector<double> ref_b(n, 0.0);
       assemble::AssembleVectorLocally(0, dofh, olprov, ref_b);
+      std::vector<std::pair<std::int64_t, double>> pairs;
+      for (std::size_t i = 0; i < n; ++i)
+        if (sel(static_cast<std::int64_t>(i)).first) pairs.emplace_back(static_cast<std::int64_t>(i), sel(static_cast<std::int64_t>(i)).second);
+      pairs.emplace_back(1, 0.125);  // dof 1 is fixed already: its value becomes the sum (fix_dof.h:268)
       if (variant == 0) {
         assemble::FixFlaggedSolutionComponents(sel, coo, ref_b);
-      } else {
+      } else if (variant == 1) {
         assemble::FixFlaggedSolutionCompAlt(sel, coo, ref_b);
+      } else {
+        assemble::FixSolutionComponentsLse(pairs, coo, ref_b);
       }
       const auto ref = coo.makeSparse();
       auto gfes = std::make_shared<const FeSpace>(FeSpace{fes, p});
@@ -149,8 +155,10 @@ int main() {
       lfgpu::AssembleVectorLocally<OracleAdaptor>(0, dofh, glprov, v);
       if (variant == 0) {
         lfgpu::FixFlaggedSolutionComponents<double>(sel, M, v);
-      } else {
+      } else if (variant == 1) {
         lfgpu::FixFlaggedSolutionCompAlt<double>(sel, M, v);
+      } else {
+        lfgpu::FixSolutionComponentsLse<double>(pairs, M, v);
       }
       std::vector<std::int32_t> outer, inner;
       std::vector<double> vals;
@@ -186,7 +194,7 @@ int main() {
         CHECK(res <= 1e-12 && fix_err <= 1e-11, "device CG: residual %.3e after %d iterations, fixed components off by %.3e", res, iters, fix_err);
         std::printf("%-46s iterations=%d rel.residual=%.2e fixed-dof error=%.2e\n", "SolveCG after FixFlaggedSolutionComponents", iters, res, fix_err);
       }
-      std::printf("%-46s N=%6zu nnz=%8zu rel.err=%.2e rhs=%.2e\n", variant == 0 ? "FixFlaggedSolutionComponents P2 hybrid" : "FixFlaggedSolutionCompAlt P2 hybrid", n,
+      std::printf("%-46s N=%6zu nnz=%8zu rel.err=%.2e rhs=%.2e\n", variant == 0 ? "FixFlaggedSolutionComponents P2 hybrid" : (variant == 1 ? "FixFlaggedSolutionCompAlt P2 hybrid" : "FixSolutionComponentsLse P2 hybrid"), n,
                   kept, err / scale, berr / bscale);
     }
     // impedance boundary terms (sec_ord_ell_bvp.h:147-215): cell matrix + edge mass on the part {x = 0} u {y = 0} of the

@@ -123,3 +123,17 @@ def test_nothing_fixed_is_identity():
     o0, i0, v0, _, _ = om.assemble_rd(2, lfo.coeff.const(1.0), lfo.coeff.const(1.0))
     b0, _ = om.assemble_load(2, lfo.coeff.const(1.0))
     assert np.array_equal(outer, o0) and np.array_equal(inner, i0) and np.array_equal(vals, v0) and np.array_equal(rhs, b0)
+
+
+def test_reference_known_answer_lse():
+    """coomatrix_tests.cc:78-122 (fix_dof_test): FixSolutionComponentsLse with {2: -1, 4: -2, 8: -3} on tridiag(-1, 2, -1),
+    b = 1..10 -> x = (1, 1, -1, 0.5, -2, 7.75, 11.5, 8.25, -3, 3.5) to 1e-12; values of a repeated index add up
+    (fix_dof.h:268)."""
+    n, rows, cols, vals, b, fixed, xhat, exact = tridiag_case()
+    outer, inner, v, rhs = lfo.fix_coo_lse(n, rows, cols, vals, [(2, -1.0), (4, -2.0), (8, -3.0)], b)
+    x = spla.spsolve(sp.csc_matrix((v, inner, outer), shape=(n, n)), rhs)
+    assert np.linalg.norm(x - exact) <= 1e-12
+    o2, i2, v2, rhs2 = lfo.fix_coo(n, rows, cols, vals, fixed, xhat, b, alt=True)  # same as the row-only variant with flags
+    assert np.array_equal(outer, o2) and np.array_equal(inner, i2) and np.array_equal(v, v2) and np.array_equal(rhs, rhs2)
+    _, _, _, rhs3 = lfo.fix_coo_lse(n, rows, cols, vals, [(2, -0.25), (4, -2.0), (2, -0.75), (8, -3.0)], b)
+    assert np.array_equal(rhs3, rhs)
