@@ -248,6 +248,15 @@ class CsrMatrix {
   }
   CsrMatrix(const CsrMatrix&) = delete;
   CsrMatrix& operator=(const CsrMatrix&) = delete;
+  // movable, so that the returning forms of AssembleMatrixLocally (assembler.h:209-220, 243-249) can hand it out
+  CsrMatrix(CsrMatrix&& o) noexcept
+      : empty_(o.empty_), ctx_(o.ctx_), major_(o.major_), mesh_(o.mesh_), test_(o.test_), trial_(o.trial_), pattern_(o.pattern_),
+        d_values_(o.d_values_) {
+    o.mesh_ = nullptr;
+    o.test_ = o.trial_ = nullptr;
+    o.pattern_ = nullptr;
+    o.d_values_ = nullptr;
+  }
   void setZero() {
     if (d_values_) ctx_.check(lfgpu_memset(ctx_.get(), d_values_, 0, 8 * nnz()), "lfgpu_memset");
     empty_ = true;
@@ -315,6 +324,12 @@ class Vector {
   }
   Vector(const Vector&) = delete;
   Vector& operator=(const Vector&) = delete;
+  Vector(Vector&& o) noexcept : ctx_(o.ctx_), mesh_(o.mesh_), dofs_(o.dofs_), d_(o.d_), n_(o.n_) {  // assembler.h:354-365 returns the vector
+    o.mesh_ = nullptr;
+    o.dofs_ = nullptr;
+    o.d_ = nullptr;
+    o.n_ = 0;
+  }
   void setZero() {
     if (d_) ctx_.check(lfgpu_memset(ctx_.get(), d_, 0, 8 * n_), "lfgpu_memset");
   }
@@ -570,6 +585,27 @@ void AssembleVectorLocally(unsigned codim, const DOFH& dof_handler, ScalarLoadEl
   ctx.check(lfgpu_assemble_load(ctx.get(), v.mesh(), v.dofs(), evp.Degree(), nullptr, nullptr, &df.c, nullptr, 1.0, v.device(), LFGPU_ALGO_AUTO),
             "lfgpu_assemble_load");
   ctx.check(lfgpu_ctx_synchronize(ctx.get()), "lfgpu_ctx_synchronize");
+}
+
+// The returning forms of the reference (assembler.h:209-220 two handlers, :243-249 one handler, :354-365 vector): the
+// reference builds TMPMATRIX{rows, cols} / VECTOR(size) itself; a device target needs its context, the one extra argument.
+template <class A, class DOFH, class PROVIDER>
+CsrMatrix AssembleMatrixLocally(Context& ctx, unsigned codim, const DOFH& dof_handler_trial, const DOFH& dof_handler_test,
+                                PROVIDER& entity_matrix_provider, int major = LFGPU_COL_MAJOR) {
+  CsrMatrix matrix(ctx, major);
+  AssembleMatrixLocally<A>(codim, dof_handler_trial, dof_handler_test, entity_matrix_provider, matrix);
+  return matrix;
+}
+template <class A, class DOFH, class PROVIDER>
+CsrMatrix AssembleMatrixLocally(Context& ctx, unsigned codim, const DOFH& dof_handler, PROVIDER& entity_matrix_provider,
+                                int major = LFGPU_COL_MAJOR) {
+  return AssembleMatrixLocally<A>(ctx, codim, dof_handler, dof_handler, entity_matrix_provider, major);
+}
+template <class A, class DOFH, class PROVIDER>
+Vector AssembleVectorLocally(Context& ctx, unsigned codim, const DOFH& dof_handler, PROVIDER& entity_vector_provider) {
+  Vector v(ctx);
+  AssembleVectorLocally<A>(codim, dof_handler, entity_vector_provider, v);
+  return v;
 }
 
 // ---- edge (codim-1) providers ------------------------------------------------------------------------------------------------

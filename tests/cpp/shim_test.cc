@@ -120,6 +120,21 @@ int main() {
       }
       CHECK(err <= 1e-12 * scale, "load vector P%d: error %.3e", p, err);
       std::printf("load vector P%d on hybrid mesh                  N=%6zu rel.err=%.2e\n", p, h.size(), err / scale);
+      // the returning forms (assembler.h:243-249, 354-365): same numbers as the accumulating forms on fresh targets
+      lfgpu::Vector v2 = lfgpu::AssembleVectorLocally<OracleAdaptor>(ctx, 0, dofh, gprov);
+      const auto h2 = v2.Download();
+      bool same_vec = h2.size() == h.size();
+      for (std::size_t i = 0; same_vec && i < h.size(); ++i) same_vec = std::fabs(h2[i] - h[i]) <= 1e-13 * scale;
+      CHECK(same_vec, "returning AssembleVectorLocally P%d differs", p);
+      lfgpu::ReactionDiffusionElementMatrixProvider<double, GC, GC> mprov(gfes, GC{1.0}, GC{1.0});
+      lfgpu::CsrMatrix M1(ctx, LFGPU_COL_MAJOR);
+      lfgpu::AssembleMatrixLocally<OracleAdaptor>(0, dofh, dofh, mprov, M1);
+      lfgpu::CsrMatrix M2 = lfgpu::AssembleMatrixLocally<OracleAdaptor>(ctx, 0, dofh, mprov);
+      std::vector<std::int32_t> o1, i1, o2, i2;
+      std::vector<double> a1, a2;
+      M1.Download(o1, i1, a1);
+      M2.Download(o2, i2, a2);
+      CHECK(o1 == o2 && i1 == i2 && a1 == a2, "returning AssembleMatrixLocally P%d differs", p);
     }
     // Dirichlet elimination (fix_dof.h:86-138,181-218): assemble A, b, fix every third dof, compare operator and rhs
     for (int variant = 0; variant < 3; ++variant) {  // 2 = FixSolutionComponentsLse: (index, value) pairs, repeated indices add up
