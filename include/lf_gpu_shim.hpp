@@ -587,6 +587,33 @@ void AssembleVectorLocally(unsigned codim, const DOFH& dof_handler, ScalarLoadEl
   ctx.check(lfgpu_ctx_synchronize(ctx.get()), "lfgpu_ctx_synchronize");
 }
 
+// lf::fe::DiffusionElementMatrixProvider / MassElementMatrixProvider (lib/lf/fe/loc_comp_ellbvp.h:76-226, 256-384), the
+// providers of the generic lf::fe module, for the Lagrange spaces the device path knows: same constructor shape
+// (fe_space, coefficient), rule of degree 2 * Degree() (:186, :365) = the uscalfe provider's default.  They are the
+// reaction-diffusion provider with the other coefficient identically zero -- bitwise so in the reference's arithmetic
+// (w * (x + 0) = w * x; checked on the oracle, tests/test_oracle_fe_providers.py) -- hence take every overload above.
+namespace fe {
+template <class SCALAR, class DIFF_COEFF>
+class DiffusionElementMatrixProvider : public ReactionDiffusionElementMatrixProvider<SCALAR, DIFF_COEFF, MeshFunctionConstant<double>> {
+ public:
+  template <class FE_SPACE>
+  DiffusionElementMatrixProvider(std::shared_ptr<const FE_SPACE> fe_space, DIFF_COEFF alpha)
+      : ReactionDiffusionElementMatrixProvider<SCALAR, DIFF_COEFF, MeshFunctionConstant<double>>(std::move(fe_space), std::move(alpha),
+                                                                                                   MeshFunctionConstant<double>{0.0}) {}
+};
+template <class SCALAR, class REACTION_COEFF>
+class MassElementMatrixProvider : public ReactionDiffusionElementMatrixProvider<SCALAR, MeshFunctionConstant<double>, REACTION_COEFF> {
+ public:
+  template <class FE_SPACE>
+  MassElementMatrixProvider(std::shared_ptr<const FE_SPACE> fe_space, REACTION_COEFF gamma)
+      : ReactionDiffusionElementMatrixProvider<SCALAR, MeshFunctionConstant<double>, REACTION_COEFF>(
+            std::move(fe_space), MeshFunctionConstant<double>{0.0}, std::move(gamma)) {}
+};
+// lf::fe::ScalarLoadElementVectorProvider (:569-700) has the uscalfe provider's form and rule
+template <class SCALAR, class MESH_FUNCTION>
+using ScalarLoadElementVectorProvider = ::lfgpu::ScalarLoadElementVectorProvider<SCALAR, MESH_FUNCTION>;
+}  // namespace fe
+
 // The returning forms of the reference (assembler.h:209-220 two handlers, :243-249 one handler, :354-365 vector): the
 // reference builds TMPMATRIX{rows, cols} / VECTOR(size) itself; a device target needs its context, the one extra argument.
 template <class A, class DOFH, class PROVIDER>

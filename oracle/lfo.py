@@ -88,6 +88,7 @@ def lib():
                                         C.POINTER(C.c_double)]
         L.lfo_element_matrices.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Coeff), C.POINTER(Coeff),
                                            C.c_void_p, C.c_int]
+        L.lfo_fe_element_matrices.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(Coeff), C.c_void_p, C.c_int]
         L.lfo_fespace_num_dofs.restype = C.c_int64
         L.lfo_fespace_num_dofs.argtypes = [C.c_void_p, C.c_int]
         L.lfo_fespace_cell_dofs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -352,6 +353,13 @@ class Mesh:
         _check(lib().lfo_element_matrices(self.h, degree, qr_tria, qr_quad, C.byref(alpha), C.byref(gamma), _p(out),
                                           stride) == 0)
         return out.transpose(0, 2, 1).copy()  # -> [cell][row][col]
+
+    def fe_element_matrices(self, degree, which, coeff_):
+        """lf::fe::DiffusionElementMatrixProvider (which="diffusion") / MassElementMatrixProvider (which="mass") per cell."""
+        stride = {1: 4, 2: 9, 3: 16}[degree]
+        out = np.zeros((self.n_cells, stride, stride))
+        _check(lib().lfo_fe_element_matrices(self.h, degree, 1 if which == "mass" else 0, C.byref(coeff_), _p(out), stride) == 0)
+        return out.transpose(0, 2, 1).copy()
 
     def nodal_projection(self, degree, u):
         out = np.zeros(self.num_dofs(degree))

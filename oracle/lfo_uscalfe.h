@@ -783,4 +783,86 @@ std::vector<double> NodalProjection(const UniformScalarFESpace& fe_space, const 
 }
 
 }  // namespace lfo::uscalfe
+
+// lib/lf/fe/loc_comp_ellbvp.h: the providers of the generic lf::fe module, restated for the spaces this oracle has (the
+// Lagrange spaces; in the reference FeSpaceLagrangeO<p> IS-A lf::fe::ScalarFESpace).  They differ from the uscalfe provider
+// in form only: one term each, shape functions evaluated per call instead of precomputed, rule of degree 2 * Degree() from a
+// QuadRuleCache -- the same rule the uscalfe provider uses by default.
+namespace lfo::fe {
+using uscalfe::UniformScalarFESpace;
+
+// fe/loc_comp_ellbvp.h:76-226
+template <class DIFF_COEFF>
+class DiffusionElementMatrixProvider {
+ public:
+  using ElemMat = Mat;
+  DiffusionElementMatrixProvider(std::shared_ptr<const UniformScalarFESpace> fe_space, DIFF_COEFF alpha)
+      : alpha_(std::move(alpha)), fe_space_(std::move(fe_space)) {}
+  bool isActive(const mesh::Entity& /*cell*/) const { return true; }
+  // :170-226
+  ElemMat Eval(const mesh::Entity& cell) {
+    const geometry::Geometry* geo_ptr = cell.Geometry();
+    const auto sfl = fe_space_->ShapeFunctionLayout(cell.RefElem());
+    const quad::QuadRule qr = quad::make_QuadRule(cell.RefElem(), 2 * sfl->Degree());
+    const Mat determinants(geo_ptr->IntegrationElement(qr.Points()));
+    const Mat JinvT(geo_ptr->JacobianInverseGramian(qr.Points()));
+    auto alphaval = alpha_(cell, qr.Points());
+    const long nsf = sfl->NumRefShapeFunctions();
+    ElemMat mat(nsf, nsf);
+    mat.setZero();
+    const Mat grsf = sfl->GradientsReferenceShapeFunctions(qr.Points());
+    for (size_type k = 0; k < qr.NumPoints(); ++k) {
+      const double w = qr.Weights()[k] * determinants[k];
+      Mat trf_grad(2, nsf);
+      for (long a = 0; a < nsf; ++a) {
+        trf_grad(0, a) = JinvT(0, 2 * k) * grsf(a, 2 * k) + JinvT(0, 2 * k + 1) * grsf(a, 2 * k + 1);
+        trf_grad(1, a) = JinvT(1, 2 * k) * grsf(a, 2 * k) + JinvT(1, 2 * k + 1) * grsf(a, 2 * k + 1);
+      }
+      Mat alpha_trf_grad(2, nsf);
+      uscalfe::detail::ApplyCoeff(alphaval[k], trf_grad, alpha_trf_grad);
+      // mat += w * trf_grad^H * (alpha * trf_grad)
+      for (long b = 0; b < nsf; ++b)
+        for (long a = 0; a < nsf; ++a) mat(a, b) += w * (trf_grad(0, a) * alpha_trf_grad(0, b) + trf_grad(1, a) * alpha_trf_grad(1, b));
+    }
+    return mat;
+  }
+
+ private:
+  DIFF_COEFF alpha_;
+  std::shared_ptr<const UniformScalarFESpace> fe_space_;
+};
+
+// fe/loc_comp_ellbvp.h:256-384
+template <class REACTION_COEFF>
+class MassElementMatrixProvider {
+ public:
+  using ElemMat = Mat;
+  MassElementMatrixProvider(std::shared_ptr<const UniformScalarFESpace> fe_space, REACTION_COEFF gamma)
+      : gamma_(std::move(gamma)), fe_space_(std::move(fe_space)) {}
+  bool isActive(const mesh::Entity& /*cell*/) const { return true; }
+  // :351-384
+  ElemMat Eval(const mesh::Entity& cell) {
+    const geometry::Geometry* geo_ptr = cell.Geometry();
+    const auto sfl = fe_space_->ShapeFunctionLayout(cell.RefElem());
+    const quad::QuadRule qr = quad::make_QuadRule(cell.RefElem(), 2 * sfl->Degree());
+    const Mat determinants(geo_ptr->IntegrationElement(qr.Points()));
+    auto gammaval = gamma_(cell, qr.Points());
+    const long nsf = sfl->NumRefShapeFunctions();
+    ElemMat mat(nsf, nsf);
+    mat.setZero();
+    const Mat rsf = sfl->EvalReferenceShapeFunctions(qr.Points());
+    for (size_type k = 0; k < qr.NumPoints(); ++k) {
+      const double w = qr.Weights()[k] * determinants[k];
+      for (long b = 0; b < nsf; ++b)
+        for (long a = 0; a < nsf; ++a) mat(a, b) += w * ((gammaval[k] * rsf(a, k)) * rsf(b, k));
+    }
+    return mat;
+  }
+
+ private:
+  REACTION_COEFF gamma_;
+  std::shared_ptr<const UniformScalarFESpace> fe_space_;
+};
+
+}  // namespace lfo::fe
 #endif

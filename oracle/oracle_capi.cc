@@ -750,6 +750,35 @@ int lfo_element_matrices(void* mesh_h, int degree, int qr_tria, int qr_quad, con
   LFO_CATCH(-1)
 }
 
+// element matrices of lf::fe::DiffusionElementMatrixProvider (which = 0, coefficient alpha) or MassElementMatrixProvider
+// (which = 1, scalar coefficient): out as in lfo_element_matrices
+int lfo_fe_element_matrices(void* mesh_h, int degree, int which, const lfo_coeff* coeff, double* out, int stride) {
+  LFO_TRY
+  auto* mh = static_cast<MeshH*>(mesh_h);
+  auto fes = std::make_shared<uscalfe::UniformScalarFESpace>(mh->mesh, degree);
+  std::size_t c = 0;
+  auto run = [&](auto& prov) {
+    for (const mesh::Entity* cell : mh->mesh->Entities(0)) {
+      const Mat m = prov.Eval(*cell);
+      for (long j = 0; j < m.cols(); ++j)
+        for (long i = 0; i < m.rows(); ++i) out[c * stride * stride + j * stride + i] = m(i, j);
+      ++c;
+    }
+  };
+  if (which == 1) {
+    fe::MassElementMatrixProvider<ScalarMF> prov(fes, make_scalar_mf(coeff, mh->mesh.get()));
+    run(prov);
+  } else if (is_tensor(coeff)) {
+    fe::DiffusionElementMatrixProvider<TensorMF> prov(fes, make_tensor_mf(coeff));
+    run(prov);
+  } else {
+    fe::DiffusionElementMatrixProvider<ScalarMF> prov(fes, make_scalar_mf(coeff, mh->mesh.get()));
+    run(prov);
+  }
+  return 0;
+  LFO_CATCH(-1)
+}
+
 std::int64_t lfo_fespace_num_dofs(void* mesh_h, int degree) {
   LFO_TRY
   auto* mh = static_cast<MeshH*>(mesh_h);

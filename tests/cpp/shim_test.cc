@@ -135,6 +135,21 @@ int main() {
       M1.Download(o1, i1, a1);
       M2.Download(o2, i2, a2);
       CHECK(o1 == o2 && i1 == i2 && a1 == a2, "returning AssembleMatrixLocally P%d differs", p);
+      // lf::fe providers (fe/loc_comp_ellbvp.h): diffusion + mass accumulated into one matrix = the reaction-diffusion matrix
+      lfgpu::fe::DiffusionElementMatrixProvider<double, GC> dprov(gfes, GC{1.0});
+      lfgpu::fe::MassElementMatrixProvider<double, GC> maprov(gfes, GC{1.0});
+      lfgpu::CsrMatrix M3(ctx, LFGPU_COL_MAJOR);
+      lfgpu::AssembleMatrixLocally<OracleAdaptor>(0, dofh, dofh, dprov, M3);
+      lfgpu::AssembleMatrixLocally<OracleAdaptor>(0, dofh, dofh, maprov, M3);  // accumulates (assembler.h:84-88)
+      std::vector<std::int32_t> o3, i3;
+      std::vector<double> a3;
+      M3.Download(o3, i3, a3);
+      double s3 = 0, e3 = 0;
+      for (std::size_t k = 0; k < a1.size() && k < a3.size(); ++k) {
+        s3 = std::max(s3, std::fabs(a1[k]));
+        e3 = std::max(e3, std::fabs(a1[k] - a3[k]));
+      }
+      CHECK(o1 == o3 && i1 == i3 && e3 <= 1e-13 * s3, "lf::fe diffusion + mass P%d: error %.3e", p, e3);
     }
     // Dirichlet elimination (fix_dof.h:86-138,181-218): assemble A, b, fix every third dof, compare operator and rhs
     for (int variant = 0; variant < 3; ++variant) {  // 2 = FixSolutionComponentsLse: (index, value) pairs, repeated indices add up
