@@ -282,6 +282,13 @@ int lfgpu_assemble_segment_load(lfgpu_ctx* ctx, int degree, const lfgpu_quad* qr
 int lfgpu_edge_qp_coords(lfgpu_ctx* ctx, lfgpu_mesh* mesh, int degree, const lfgpu_quad* qr_segment, int nq_stride, double* d_out);
 /* edges with exactly one adjacent cell (mesh/utils flagEntitiesOnBoundary(mesh, 1)): d_flags device uint8 [n_edges]  */
 int lfgpu_mesh_boundary_edges(lfgpu_ctx* ctx, lfgpu_mesh* mesh, uint8_t* d_flags);
+/* nodes on the boundary (flagEntitiesOnBoundary(mesh, 2)): d_node_flags device uint8 [n_nodes]                         */
+int lfgpu_mesh_boundary_nodes(lfgpu_ctx* ctx, lfgpu_mesh* mesh, uint8_t* d_node_flags);
+/* dofs on the boundary -- the selector of the examples, `boundary(dofh.Entity(dof))` with flagEntitiesOnBoundary(mesh)
+ * (examples/ellbvp_linfe/homDir_linfe_demo.cc:158-165, fe/test/loc_comp_tests.cc:86-91): d_dof_flags device uint8
+ * [n_dofs], ready as d_fixed of lfgpu_fix_flagged_solution_components.  Needs a dof map numbered on the device
+ * (lfgpu_dofmap_uniform / _lagrange), where dof -> entity is arithmetic; LFGPU_ERR_UNSUPPORTED for uploaded tables. */
+int lfgpu_dofmap_boundary_dofs(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const lfgpu_dofmap* dofmap, uint8_t* d_dof_flags);
 /* ---- essential boundary conditions (first "next" row) ------------------------------------------- */
 /* lf::assemble::FixFlaggedSolutionComponents (assemble/fix_dof.h:86-138) on the compressed matrix: with xhat = the
  * prescribed values on the fixed dofs and 0 elsewhere,  rhs -= A * xhat;  rhs[fixed] = xhat;  every entry in a fixed row

@@ -123,6 +123,8 @@ def _lib():
         "lfgpu_assemble_segment_load": (i32, [vp, i32, C.POINTER(_CQuad), i64, vp, vp, C.POINTER(_CCoeff), i64, vp]),
         "lfgpu_edge_qp_coords": (i32, [vp, vp, i32, C.POINTER(_CQuad), i32, vp]),
         "lfgpu_mesh_boundary_edges": (i32, [vp, vp, vp]),
+        "lfgpu_mesh_boundary_nodes": (i32, [vp, vp, vp]),
+        "lfgpu_dofmap_boundary_dofs": (i32, [vp, vp, vp, vp]),
         "lfgpu_fix_flagged_solution_components": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "lfgpu_fix_flagged_solution_comp_alt": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "lfgpu_assemble_reaction_diffusion_host": (i32, [vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), C.POINTER(_CCoeff),
@@ -513,6 +515,14 @@ class Mesh:
         self.ctx.check(self.ctx.L.lfgpu_mesh_boundary_edges(self.ctx.h, self.h, out.ptr))
         return out
 
+    def boundary_nodes(self):
+        """DeviceArray(uint8)[n_nodes]: endpoints of boundary edges (flagEntitiesOnBoundary(mesh, 2))."""
+        if self.n_edges == 0:
+            self.build_topology()
+        out = self.ctx.empty(max(self.n_nodes, 1), np.uint8)
+        self.ctx.check(self.ctx.L.lfgpu_mesh_boundary_nodes(self.ctx.h, self.h, out.ptr))
+        return out
+
     def edge_qp_coords(self, degree, qr_segment=None, nq_stride=None):
         """[n_edges][nq_stride][2] global coordinates of the edge quadrature points (host array)."""
         nq = qr_segment.weights.size if qr_segment is not None else degree + 1
@@ -594,6 +604,14 @@ class DofMap:
         h = C.c_void_p()
         self.ctx.check(self.ctx.L.lfgpu_symbolic(self.ctx.h, self.mesh.h, self.h, trial.h, major, C.byref(h)))
         return Pattern(self.mesh, h, major)
+
+    def boundary_dofs(self):
+        """DeviceArray(uint8)[n_dofs]: dofs whose entity lies on the boundary (for device-numbered uniform layouts)."""
+        if self.mesh.n_edges == 0:
+            self.mesh.build_topology()
+        out = self.ctx.empty(self.num_dofs, np.uint8)
+        self.ctx.check(self.ctx.L.lfgpu_dofmap_boundary_dofs(self.ctx.h, self.mesh.h, self.h, out.ptr))
+        return out
 
     def assemble_edge_load(self, degree, g, qr_segment=None, active_edges=None, out=None):
         """AssembleVectorLocally(1, dofh, ScalarLoadEdgeVectorProvider(fe_space, g, edge_sel), vec): accumulates into out."""

@@ -14,6 +14,8 @@
 // When two active edges share a dof the order of their two additions is not fixed (last-bit differences only).
 #include <cmath>
 
+#include <algorithm>
+
 #include "lfgpu_internal.cuh"
 
 namespace lfgpu {
@@ -195,6 +197,26 @@ __global__ void k_flag_boundary(int64_t n_edges, const unsigned* __restrict__ co
   if (e < n_edges) flags[e] = count[e] == 1U ? 1 : 0;
 }
 
+// boundary flags of nodes (endpoints of boundary edges) and of the dofs of a uniform layout (dofhandler.cc:141-284: node
+// dofs first, n_pt per node; then edge-interior dofs, n_seg per edge; cell-interior dofs are never on the boundary)
+__global__ void k_boundary_nodes(int64_t n_edges, const uint32_t* __restrict__ edge_nodes, const uint8_t* __restrict__ edge_flags,
+                                 uint8_t* __restrict__ node_flags) {
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= n_edges || edge_flags[e] == 0) return;
+  node_flags[edge_nodes[2 * e]] = 1;  // several edges may write the same 1: benign
+  node_flags[edge_nodes[2 * e + 1]] = 1;
+}
+__global__ void k_boundary_dofs(int64_t n_dofs, int64_t n_nodes, int64_t n_edges, int n_pt, int n_seg, const uint8_t* __restrict__ node_flags,
+                                const uint8_t* __restrict__ edge_flags, uint8_t* __restrict__ dof_flags) {
+  const int64_t d = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (d >= n_dofs) return;
+  const int64_t node_dofs = n_nodes * n_pt, edge_dofs = n_edges * n_seg;
+  uint8_t f = 0;
+  if (d < node_dofs) f = node_flags[d / n_pt];
+  else if (d < node_dofs + edge_dofs) f = edge_flags[(d - node_dofs) / n_seg];
+  dof_flags[d] = f;
+}
+
 int prepare(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const lfgpu_dofmap* dofmap, int degree, const lfgpu_quad* qr, const lfgpu_coeff* coeff,
             SegTable* T, EdgeCoeff* G) {
   if (degree < 1 || degree > 3) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "degree must be 1, 2 or 3");
@@ -354,6 +376,67 @@ int lfgpu_mesh_boundary_edges(lfgpu_ctx* ctx, lfgpu_mesh* mesh, uint8_t* d_flags
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   cudaFree(count);
+  LFGPU_CUDA_CHECK(ctx, e);
+  return LFGPU_OK;
+}
+
+// d_node_flags [n_nodes]: nodes on the boundary = endpoints of boundary edges (flagEntitiesOnBoundary(mesh, 2))
+int lfgpu_mesh_boundary_nodes(lfgpu_ctx* ctx, lfgpu_mesh* mesh, uint8_t* d_node_flags) {
+  if (ctx == nullptr || mesh == nullptr || d_node_flags == nullptr) return LFGPU_ERR_INVALID;
+  LFGPU_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  int rc = ensure_topology(ctx, mesh);
+  if (rc != LFGPU_OK) return rc;
+  LFGPU_CUDA_CHECK(ctx, cudaMemsetAsync(d_node_flags, 0, mesh->n_nodes, ctx->stream));
+  if (mesh->n_edges == 0) return LFGPU_OK;
+  uint8_t* d_edge = nullptr;
+  LFGPU_CUDA_CHECK(ctx, cudaMalloc(&d_edge, mesh->n_edges));
+  rc = lfgpu_mesh_boundary_edges(ctx, mesh, d_edge);
+  if (rc == LFGPU_OK) {
+    k_boundary_nodes<<<static_cast<unsigned>(cdiv(mesh->n_edges, kThreads)), kThreads, 0, ctx->stream>>>(mesh->n_edges, mesh->edge_nodes, d_edge,
+                                                                                                        d_node_flags);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      set_last_error(ctx, std::string("boundary nodes: ") + cudaGetErrorString(e));
+      rc = LFGPU_ERR_CUDA;
+    }
+  }
+  cudaFree(d_edge);
+  return rc;
+}
+
+int lfgpu_dofmap_boundary_dofs(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const lfgpu_dofmap* dofmap, uint8_t* d_dof_flags) {
+  if (ctx == nullptr || mesh == nullptr || dofmap == nullptr || d_dof_flags == nullptr) return LFGPU_ERR_INVALID;
+  if (dofmap->n_pt < 0 || dofmap->n_seg < 0 || dofmap->n_nodes != mesh->n_nodes)
+    LFGPU_FAIL(ctx, LFGPU_ERR_UNSUPPORTED, "boundary dofs need a dof map built by lfgpu_dofmap_uniform / _lagrange on this mesh");
+  LFGPU_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  int rc = ensure_topology(ctx, mesh);
+  if (rc != LFGPU_OK) return rc;
+  uint8_t *d_edge = nullptr, *d_node = nullptr;
+  LFGPU_CUDA_CHECK(ctx, cudaMalloc(&d_edge, std::max<int64_t>(mesh->n_edges, 1)));
+  cudaError_t e = cudaMalloc(&d_node, std::max<int64_t>(mesh->n_nodes, 1));
+  if (e != cudaSuccess) {
+    cudaFree(d_edge);
+    LFGPU_CUDA_CHECK(ctx, e);
+  }
+  rc = lfgpu_mesh_boundary_edges(ctx, mesh, d_edge);
+  if (rc == LFGPU_OK) e = cudaMemsetAsync(d_node, 0, std::max<int64_t>(mesh->n_nodes, 1), ctx->stream);
+  if (rc == LFGPU_OK && e == cudaSuccess && mesh->n_edges > 0) {
+    k_boundary_nodes<<<static_cast<unsigned>(cdiv(mesh->n_edges, kThreads)), kThreads, 0, ctx->stream>>>(mesh->n_edges, mesh->edge_nodes, d_edge, d_node);
+    ctx->launches++;
+  }
+  if (rc == LFGPU_OK && e == cudaSuccess) {
+    const int64_t n_edges_with_dofs = dofmap->n_seg > 0 ? mesh->n_edges : 0;
+    k_boundary_dofs<<<static_cast<unsigned>(cdiv(dofmap->n_dofs, kThreads)), kThreads, 0, ctx->stream>>>(
+        dofmap->n_dofs, mesh->n_nodes, n_edges_with_dofs, dofmap->n_pt, dofmap->n_seg > 0 ? dofmap->n_seg : 1, d_node, d_edge, d_dof_flags);
+    ctx->launches++;
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  }
+  cudaFree(d_edge);
+  cudaFree(d_node);
+  if (rc != LFGPU_OK) return rc;
   LFGPU_CUDA_CHECK(ctx, e);
   return LFGPU_OK;
 }
