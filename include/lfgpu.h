@@ -289,6 +289,15 @@ int lfgpu_mesh_boundary_nodes(lfgpu_ctx* ctx, lfgpu_mesh* mesh, uint8_t* d_node_
  * [n_dofs], ready as d_fixed of lfgpu_fix_flagged_solution_components.  Needs a dof map numbered on the device
  * (lfgpu_dofmap_uniform / _lagrange), where dof -> entity is arithmetic; LFGPU_ERR_UNSUPPORTED for uploaded tables. */
 int lfgpu_dofmap_boundary_dofs(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const lfgpu_dofmap* dofmap, uint8_t* d_dof_flags);
+/* lf::fe::InitEssentialConditionFromFunction (fe/fe_tools.h:301-356) in two device steps.  (1) the dofs of the selected edges
+ * -- their interior dofs and those of their end points, GlobalDofIndices(edge) -- as flags: d_edge_sel device uint8 [n_edges]
+ * (e.g. lfgpu_mesh_boundary_edges or a physical group), d_flags device uint8 [n_dofs].  (2) the position of every dof
+ * (the interpolation node of its Lagrange shape function: vertices; points at 1/2 resp. 1/3, 2/3 of an edge in the edge's
+ * own direction; cell interior nodes), d_xy device [n_dofs][2]: the prescribed value of a flagged dof is g at that point
+ * (NodalValuesToDofs of the Lagrange elements is the identity).  n_tria / n_quad: interior dofs per cell of the layout
+ * (0/0, 0/1, 1/4 for degree 1, 2, 3).  Device-numbered uniform layouts only.                                          */
+int lfgpu_dofmap_edge_dof_flags(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const lfgpu_dofmap* dofmap, const uint8_t* d_edge_sel, uint8_t* d_flags);
+int lfgpu_dofmap_dof_coords(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const lfgpu_dofmap* dofmap, int n_tria, int n_quad, double* d_xy);
 /* ---- essential boundary conditions (first "next" row) ------------------------------------------- */
 /* lf::assemble::FixFlaggedSolutionComponents (assemble/fix_dof.h:86-138) on the compressed matrix: with xhat = the
  * prescribed values on the fixed dofs and 0 elsewhere,  rhs -= A * xhat;  rhs[fixed] = xhat;  every entry in a fixed row

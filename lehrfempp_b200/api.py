@@ -125,6 +125,8 @@ def _lib():
         "lfgpu_mesh_boundary_edges": (i32, [vp, vp, vp]),
         "lfgpu_mesh_boundary_nodes": (i32, [vp, vp, vp]),
         "lfgpu_dofmap_boundary_dofs": (i32, [vp, vp, vp, vp]),
+        "lfgpu_dofmap_edge_dof_flags": (i32, [vp, vp, vp, vp, vp]),
+        "lfgpu_dofmap_dof_coords": (i32, [vp, vp, vp, i32, i32, vp]),
         "lfgpu_fix_flagged_solution_components": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "lfgpu_fix_flagged_solution_comp_alt": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "lfgpu_assemble_reaction_diffusion_host": (i32, [vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), C.POINTER(_CCoeff),
@@ -612,6 +614,19 @@ class DofMap:
         out = self.ctx.empty(self.num_dofs, np.uint8)
         self.ctx.check(self.ctx.L.lfgpu_dofmap_boundary_dofs(self.ctx.h, self.mesh.h, self.h, out.ptr))
         return out
+
+    def edge_dof_flags(self, edge_sel):
+        """DeviceArray(uint8)[n_dofs]: dofs of the selected edges incl. their end points (InitEssentialConditionFromFunction, step 1)."""
+        out = self.ctx.empty(self.num_dofs, np.uint8)
+        self.ctx.check(self.ctx.L.lfgpu_dofmap_edge_dof_flags(self.ctx.h, self.mesh.h, self.h, edge_sel.ptr, out.ptr))
+        return out
+
+    def dof_coords(self, degree):
+        """[n_dofs][2] host array: interpolation node of every dof of the degree-`degree` Lagrange layout."""
+        n_tria, n_quad = {1: (0, 0), 2: (0, 1), 3: (1, 4)}[degree]
+        out = self.ctx.empty(2 * self.num_dofs)
+        self.ctx.check(self.ctx.L.lfgpu_dofmap_dof_coords(self.ctx.h, self.mesh.h, self.h, n_tria, n_quad, out.ptr))
+        return out.to_host().reshape(-1, 2)
 
     def assemble_edge_load(self, degree, g, qr_segment=None, active_edges=None, out=None):
         """AssembleVectorLocally(1, dofh, ScalarLoadEdgeVectorProvider(fe_space, g, edge_sel), vec): accumulates into out."""

@@ -167,6 +167,75 @@ __global__ void k_plan_ptr(int64_t n_dofs, int64_t n_keys, const int32_t* __rest
   ptr[r] = static_cast<int32_t>(lo);
 }
 
+// ---- positions of the dofs of a Lagrange layout (interpolation nodes: lagr_fe.h EvaluationNodes of O1 / O2 / O3) ----------
+__global__ void k_dof_xy_nodes(int64_t n_nodes, int n_pt, const double* __restrict__ node_coords, double* __restrict__ out) {
+  const int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (v >= n_nodes) return;
+  for (int j = 0; j < n_pt; ++j) {
+    out[2 * (v * n_pt + j)] = node_coords[2 * v];
+    out[2 * (v * n_pt + j) + 1] = node_coords[2 * v + 1];
+  }
+}
+// interior dof j of an edge sits at t = (j + 1) / (n_seg + 1) along the edge's own direction (FeLagrangeO{2,3}Segment)
+__global__ void k_dof_xy_edges(int64_t n_edges, int n_seg, int64_t base, const uint32_t* __restrict__ edge_nodes,
+                               const double* __restrict__ node_coords, double* __restrict__ out) {
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const uint32_t a = edge_nodes[2 * e], b = edge_nodes[2 * e + 1];
+  const double ax = node_coords[2 * a], ay = node_coords[2 * a + 1], bx = node_coords[2 * b], by = node_coords[2 * b + 1];
+  for (int j = 0; j < n_seg; ++j) {
+    const double t = static_cast<double>(j + 1) / static_cast<double>(n_seg + 1);
+    out[2 * (base + e * n_seg + j)] = ax * (1.0 - t) + bx * t;  // SegmentO1::Global (geometry/segment_o1.cc:9-11)
+    out[2 * (base + e * n_seg + j) + 1] = ay * (1.0 - t) + by * t;
+  }
+}
+// cell-interior dofs: triangle centroid (O3), quadrilateral centre (O2) or the 2 x 2 interior lattice (O3) -- read off the table
+__global__ void k_dof_xy_cells(int64_t n_cells, int stride, int n_pt, int n_seg, int n_tria, int n_quad,
+                               const uint32_t* __restrict__ cell_nodes, const double* __restrict__ node_coords,
+                               const double* __restrict__ cell_coords, const int32_t* __restrict__ cell_dofs, double* __restrict__ out) {
+  const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (c >= n_cells) return;
+  const uint4 v = reinterpret_cast<const uint4*>(cell_nodes)[c];
+  const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+  const int nv = (v.w == LFGPU_IDX_NIL) ? 3 : 4;
+  double x[4], y[4];
+  for (int k = 0; k < nv; ++k) {
+    x[k] = cell_coords ? cell_coords[8 * c + 2 * k] : node_coords[2 * vv[k]];
+    y[k] = cell_coords ? cell_coords[8 * c + 2 * k + 1] : node_coords[2 * vv[k] + 1];
+  }
+  const int n_int = nv == 3 ? n_tria : n_quad;
+  const int first = nv * n_pt + nv * n_seg;
+  for (int j = 0; j < n_int; ++j) {
+    double X, Y;
+    if (nv == 3) {  // TriaO1::Global at (1/3, 1/3) (tria_o1.cc:70-74)
+      const double t = 1.0 / 3.0, l0 = 1.0 - t - t;
+      X = x[0] * l0 + x[1] * t + x[2] * t;
+      Y = y[0] * l0 + y[1] * t + y[2] * t;
+    } else {  // QuadO1::Global (quad_o1.cc:68-83)
+      const double third = 1.0 / 3.0;
+      const double rx[4] = {third, 2 * third, 2 * third, third}, ry[4] = {third, third, 2 * third, 2 * third};
+      const double x0 = n_int == 1 ? 0.5 : rx[j], x1 = n_int == 1 ? 0.5 : ry[j];
+      const double a = (1.0 - x0) * (1.0 - x1), b = x0 * (1.0 - x1), cc = x0 * x1, d = (1.0 - x0) * x1;
+      X = x[0] * a + x[1] * b + x[2] * cc + x[3] * d;
+      Y = y[0] * a + y[1] * b + y[2] * cc + y[3] * d;
+    }
+    const int32_t dof = cell_dofs[c * stride + first + j];
+    out[2 * static_cast<int64_t>(dof)] = X;
+    out[2 * static_cast<int64_t>(dof) + 1] = Y;
+  }
+}
+
+// dofs of the selected edges: their interior dofs and the dofs of their end points (fe/fe_tools.h:320-353 visits the
+// selected edges and flags GlobalDofIndices(edge))
+__global__ void k_edge_dof_flags(int64_t n_edges, int n_pt, int n_seg, int64_t edge_base, const uint32_t* __restrict__ edge_nodes,
+                                 const uint8_t* __restrict__ edge_sel, uint8_t* __restrict__ flags) {
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= n_edges || edge_sel[e] == 0) return;
+  for (int k = 0; k < 2; ++k)
+    for (int j = 0; j < n_pt; ++j) flags[static_cast<int64_t>(edge_nodes[2 * e + k]) * n_pt + j] = 1;  // benign: every writer stores 1
+  for (int j = 0; j < n_seg; ++j) flags[edge_base + e * n_seg + j] = 1;
+}
+
 __global__ void k_dofs_to_i64(int64_t n, const int32_t* __restrict__ in, int64_t* __restrict__ out) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) out[i] = in[i];
@@ -464,6 +533,57 @@ int lfgpu_dofmap_lagrange(lfgpu_ctx* ctx, lfgpu_mesh* mesh, int degree, lfgpu_do
       if (ctx) set_last_error(ctx, "degree must be 1, 2 or 3");
       return LFGPU_ERR_INVALID;
   }
+}
+
+int lfgpu_dofmap_dof_coords(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const lfgpu_dofmap* d, int n_tria, int n_quad, double* d_xy) {
+  if (ctx == nullptr || mesh == nullptr || d == nullptr || d_xy == nullptr) return LFGPU_ERR_INVALID;
+  if (d->n_pt < 0 || d->n_seg < 0 || d->n_nodes != mesh->n_nodes || d->n_cells != mesh->n_cells)
+    LFGPU_FAIL(ctx, LFGPU_ERR_UNSUPPORTED, "dof positions need a dof map built by lfgpu_dofmap_uniform / _lagrange on this mesh");
+  if (d->n_pt > 1 || d->n_seg > 2 || n_tria < 0 || n_tria > 1 || (n_quad != 0 && n_quad != 1 && n_quad != 4))
+    LFGPU_FAIL(ctx, LFGPU_ERR_UNSUPPORTED, "dof positions are defined for the Lagrange layouts of degree 1..3");
+  LFGPU_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  if (d->n_seg > 0) {
+    const int rc = ensure_topology(ctx, mesh);
+    if (rc != LFGPU_OK) return rc;
+  }
+  cudaStream_t st = ctx->stream;
+  if (d->n_pt > 0) {
+    k_dof_xy_nodes<<<static_cast<unsigned>(cdiv(mesh->n_nodes, kThreads)), kThreads, 0, st>>>(mesh->n_nodes, d->n_pt, mesh->node_coords, d_xy);
+    ctx->launches++;
+  }
+  const int64_t edge_base = mesh->n_nodes * d->n_pt;
+  if (d->n_seg > 0 && mesh->n_edges > 0) {
+    k_dof_xy_edges<<<static_cast<unsigned>(cdiv(mesh->n_edges, kThreads)), kThreads, 0, st>>>(mesh->n_edges, d->n_seg, edge_base, mesh->edge_nodes,
+                                                                                             mesh->node_coords, d_xy);
+    ctx->launches++;
+  }
+  if (n_tria > 0 || n_quad > 0) {
+    k_dof_xy_cells<<<static_cast<unsigned>(cdiv(mesh->n_cells, kThreads)), kThreads, 0, st>>>(mesh->n_cells, d->stride, d->n_pt, d->n_seg, n_tria, n_quad,
+                                                                                             mesh->cell_nodes, mesh->node_coords, mesh->cell_coords,
+                                                                                             d->cell_dofs, d_xy);
+    ctx->launches++;
+  }
+  LFGPU_CUDA_CHECK(ctx, cudaGetLastError());
+  LFGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+  return LFGPU_OK;
+}
+
+int lfgpu_dofmap_edge_dof_flags(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const lfgpu_dofmap* d, const uint8_t* d_edge_sel, uint8_t* d_flags) {
+  if (ctx == nullptr || mesh == nullptr || d == nullptr || d_edge_sel == nullptr || d_flags == nullptr) return LFGPU_ERR_INVALID;
+  if (d->n_pt < 0 || d->n_seg < 0 || d->n_nodes != mesh->n_nodes)
+    LFGPU_FAIL(ctx, LFGPU_ERR_UNSUPPORTED, "edge dof flags need a dof map built by lfgpu_dofmap_uniform / _lagrange on this mesh");
+  LFGPU_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  const int rc = ensure_topology(ctx, mesh);
+  if (rc != LFGPU_OK) return rc;
+  LFGPU_CUDA_CHECK(ctx, cudaMemsetAsync(d_flags, 0, d->n_dofs, ctx->stream));
+  if (mesh->n_edges > 0) {
+    k_edge_dof_flags<<<static_cast<unsigned>(cdiv(mesh->n_edges, kThreads)), kThreads, 0, ctx->stream>>>(
+        mesh->n_edges, d->n_pt, d->n_seg, mesh->n_nodes * d->n_pt, mesh->edge_nodes, d_edge_sel, d_flags);
+    ctx->launches++;
+  }
+  LFGPU_CUDA_CHECK(ctx, cudaGetLastError());
+  LFGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return LFGPU_OK;
 }
 
 int lfgpu_dofmap_download(lfgpu_ctx* ctx, const lfgpu_dofmap* d, int64_t* cell_dofs, uint8_t* n_ldof) {

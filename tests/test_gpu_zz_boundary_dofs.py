@@ -87,3 +87,48 @@ def test_device_resident_poisson_pipeline(ctx, lf, degree):
     assert np.abs(xh - ref).max() <= 1e-9 * np.abs(ref).max()
     assert np.all(xh[flags == 1] == 0.0)
     assert abs(xh.max() - 0.0736713) < 2e-3  # max of the torsion function of the unit square
+
+
+# ---- lf::fe::InitEssentialConditionFromFunction on the device (fe/fe_tools.h:301-356) ------------------------------------------
+def oracle_dof_coords(om, degree):
+    """Global(EvaluationNodes) of every cell, scattered through the cell's dof list (position b carries shape function b)."""
+    ex = om.export()
+    dofs, nl = om.cell_dofs(degree)
+    xy = np.full((om.num_dofs(degree), 2), np.nan)
+    nodes = {3: lfo.eval_fe(degree, 3, np.zeros((2, 1)))[2], 4: lfo.eval_fe(degree, 4, np.zeros((2, 1)))[2]}
+    for c in range(om.n_cells):
+        t = int(ex["cell_type"][c])
+        p = ex["cell_coords"][c, :t]
+        x0, x1 = nodes[t]
+        if t == 3:
+            w = np.stack([1 - x0 - x1, x0, x1])
+        else:
+            w = np.stack([(1 - x0) * (1 - x1), x0 * (1 - x1), x0 * x1, (1 - x0) * x1])
+        xy[dofs[c, : nl[c]]] = (w.T @ p)
+    return xy
+
+
+@pytest.mark.parametrize("kind", ["tp_tria", "hybrid"])
+@pytest.mark.parametrize("degree", [1, 2, 3])
+def test_dof_positions_and_essential_condition(ctx, lf, kind, degree):
+    if kind == "tp_tria":
+        om, gm = lfo.Mesh.tp_tria(5, 4, 0.0, 0.0, 2.0, 1.0), ctx.mesh_tp_tria(5, 4, 0.0, 0.0, 2.0, 1.0)
+    else:
+        om, gm = lfo.Mesh.hybrid(5, 0.2, 9), ctx.mesh_hybrid(5, 0.2, 9)
+    dm = gm.dofmap_lagrange(degree)
+    want = oracle_dof_coords(om, degree)
+    got = dm.dof_coords(degree)
+    assert not np.isnan(want).any()
+    assert np.abs(got - want).max() <= 1e-14
+    # step 1 of InitEssentialConditionFromFunction with the boundary edges as selector = the boundary dofs
+    flags = dm.edge_dof_flags(gm.boundary_edges()).to_host()
+    assert np.array_equal(flags, dm.boundary_dofs().to_host())
+    assert np.array_equal(flags, expected_flags(om, degree)[1])
+    # a partial selector: only the edges on {y = 0}
+    ex = om.export()
+    mid_y = ex["node_coords"][ex["edge_nodes"]][:, :, 1]
+    sel = (np.abs(mid_y).max(axis=1) < 1e-12).astype(np.uint8)
+    part = dm.edge_dof_flags(ctx.to_device(sel)).to_host()
+    assert part.sum() > 0 and np.all(np.abs(want[part == 1][:, 1]) < 1e-12) and np.all(part <= flags)
+    on_line = np.abs(want[:, 1]) < 1e-12
+    assert np.array_equal(part.astype(bool), on_line)
