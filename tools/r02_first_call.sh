@@ -1,0 +1,30 @@
+#!/bin/bash
+# First GPU call of the next round (run under gpurun from the repo root):  gpurun --timeout 600 -- 'bash tools/r02_first_call.sh'
+# Everything the end of round 1 could not measure any more, outputs under gpurun_out/.
+set -u
+out=gpurun_out
+mkdir -p $out
+# 1. the whole GPU suite, including the files added after the round-1 GPU minutes were spent (test_gpu_zz_*.py)
+timeout 180 python -m pytest tests -m gpu -q 2>&1 | tail -25 > $out/r02_gpu_tests.log
+tail -5 $out/r02_gpu_tests.log
+# 2. bench lines of the configurations that changed kernels (P2 / P3 row kernels on AUTO) and of the weakest one (C2)
+for w in c3 c4 c4s c2; do
+  timeout 120 python bench.py --workload $w --steps 30 --warmup 5 > $out/r02_bench_$w.json 2> $out/bench_$w.err
+  tail -c 600 $out/r02_bench_$w.json; echo
+done
+# 3. full ncu capture of the three P3 row kernels (none exists yet) and of the C2 item kernel
+timeout 150 ncu --set full --clock-control none --import-source on -k "regex:k_p3_(vertex|edge|cell)_rows" -c 3 -f -o $out/r02_p3_rows \
+  python tools/rows_probe.py 3 1448 rows > $out/ncu_p3.log 2>&1
+tail -2 $out/ncu_p3.log
+timeout 150 ncu --set full --clock-control none --import-source on -k "regex:k_assemble_items" -c 1 -f -o $out/r02_c2_items \
+  python bench.py --workload c2 --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > $out/ncu_c2.log 2>&1
+tail -2 $out/ncu_c2.log
+# 4. launch lists (kernel shares of a step) for C3 and C4
+for w in c3 c4; do
+  timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:k_p[23]_|k_assemble" -c 40 --csv --log-file $out/r02_launches_$w.csv \
+    python bench.py --workload $w --steps 3 --warmup 1 --no-cpu-baseline --no-e2e > /dev/null 2>&1
+done
+# 5. probes: both P3 / P2 kernels in one process, load vector
+timeout 60 python tools/rows_probe.py 3 1448 > $out/r02_p3_rows_vs_items.json 2>/dev/null; cat $out/r02_p3_rows_vs_items.json
+timeout 60 python tools/rows_probe.py 2 2828 > $out/r02_p2_rows_vs_items.json 2>/dev/null; cat $out/r02_p2_rows_vs_items.json
+timeout 60 python tools/load_probe.py > $out/r02_load_probe.json 2>/dev/null; cat $out/r02_load_probe.json
