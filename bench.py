@@ -223,12 +223,14 @@ def main():
         return
 
     import numpy as np
-    import torch
 
     import lehrfempp_b200 as lf
 
+    # torch is plumbing for N > 1 only (process group, NCCL); a single-GPU run does not pay its import
+    torch = None
     dist = None
     if world > 1:
+        import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         import datetime
