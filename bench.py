@@ -446,6 +446,26 @@ def main():
         teardown()
         return
 
+    # size-independent witness that the matrix left in `values` at the FULL size is the right operator (not part of any timing):
+    # one device SpMV with the constant vector -- constants are in the kernel of the stiffness part, 1^T M 1 = |Omega| = 1
+    check = None
+    if asm is None:
+        try:
+            y = pat.spmv(values, ctx.to_device(np.ones(dm.num_dofs))).to_host()
+            if args.workload in ("c4s", "c4", "c4_27m"):
+                check = {"what": "1^T A 1 for stiffness + mass with alpha = gamma = 1 on the unit square", "value": float(y.sum()), "expected": 1.0}
+            elif args.workload == "c2":
+                from scipy.integrate import dblquad
+                expected = dblquad(lambda yy, xx: 1.0 / (1.0 + xx * xx + yy * yy), 0.0, 1.0, 0.0, 1.0)[0]
+                check = {"what": "1^T A 1 = integral of gamma = 1 / (1 + |x|^2) over the unit square (quadrature error O(h^2))",
+                         "value": float(y.sum()), "expected": expected}
+            else:
+                check = {"what": "max |A 1| for the Laplacian (constants are in its kernel; entries are O(1))", "value": float(np.abs(y).max()),
+                         "expected": 0.0}
+            del y
+        except Exception as e:  # a witness must never cost the bench line
+            check = {"error": str(e)[:200]}
+
     peak, peak_src = measured_peak()
     # algorithmic bytes (SURVEY.md 8d / DESIGN.md): int32 connectivity + each vertex coordinate once + coefficients +
     # each stored value written once
@@ -484,6 +504,8 @@ def main():
         "gpu_launches": int(launches),
         "clocks": sampler.summary(t_timed0, max(t_timed1, t_end)),
     }
+    if check is not None:
+        out["check"] = check
     if e2e is not None:
         out["e2e"] = e2e
     if not args.no_cpu_baseline:

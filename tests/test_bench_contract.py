@@ -43,6 +43,7 @@ def check_line(out, steps):
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
     assert out["gpu_launches"] >= steps
     assert "workload" in out["config"]
+    assert "error" not in out["check"] and {"what", "value", "expected"} <= set(out["check"])
 
 
 @pytest.mark.parametrize("workload", sorted(KERNEL))
