@@ -24,6 +24,7 @@
 #include <cub/cub.cuh>
 
 #include "lfgpu_internal.cuh"
+#include "rows_p2_core.h"
 
 namespace lfgpu {
 namespace {
@@ -140,6 +141,24 @@ __global__ void k_p2_vertex_plan(int64_t n_nodes, int o_stride, int pos_row, con
   }
   for (int k = 0; k < kRing; ++k) nbr[static_cast<int64_t>(k) * n_nodes + r] = ok ? static_cast<int32_t>(ring[k]) : -1;
   for (int j = 0; j < 3; ++j) slots[static_cast<int64_t>(j) * n_nodes + r] = ok ? w[j] : 0U;
+  irregular[r] = (!ok && m > 0) ? 1 : 0;
+}
+
+// the same for any closed ring of 3..8 cells (rows_p2_core.h): gnbr[k][r] = n_k (-1 beyond the ring / for an irregular row),
+// gslots[0..5][r]; replaces the valence-6 plan on meshes with other valences (unstructured input)
+__global__ void k_p2_vertex_plan_general(int64_t n_nodes, int o_stride, int pos_row, const int32_t* __restrict__ adj_ptr,
+                                         const uint32_t* __restrict__ adj, const uint32_t* __restrict__ cell_nodes,
+                                         const uint8_t* __restrict__ pos, const int32_t* __restrict__ outer, int32_t* __restrict__ gnbr,
+                                         uint32_t* __restrict__ gslots, uint8_t* __restrict__ irregular) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= n_nodes) return;
+  const int32_t it0 = adj_ptr[r];
+  const int m = adj_ptr[r + 1] - it0;
+  int32_t ring[p2::kMaxRing];
+  uint32_t w[p2::kSlotWords];
+  const bool ok = p2::vertex_plan_general(r, m, adj + it0, cell_nodes, pos, o_stride, pos_row, outer[r + 1] - outer[r], ring, w);
+  for (int k = 0; k < p2::kMaxRing; ++k) gnbr[static_cast<int64_t>(k) * n_nodes + r] = ok ? ring[k] : -1;
+  for (int j = 0; j < p2::kSlotWords; ++j) gslots[static_cast<int64_t>(j) * n_nodes + r] = ok ? w[j] : 0U;
   irregular[r] = (!ok && m > 0) ? 1 : 0;
 }
 
@@ -352,6 +371,65 @@ __global__ void __launch_bounds__(128, 4) k_p2_vertex_rows(int first, int end, i
   write_rows<kVertexRowLen>(staged, regular, in_range, lane, v0, v1, wbase, stage, dst, values);
 }
 
+// vertex rows with closed rings of 3..8 cells (rows_p2_core.h); rows of different lengths (1 + 3m) share a warp, the staged
+// copy-out only needs their value ranges to be consecutive
+template <int MODE>
+__global__ void __launch_bounds__(128, 4) k_p2_vertex_rows_general(int first, int end, int n_rows, const int32_t* __restrict__ gnbr,
+                                                                 const uint32_t* __restrict__ gslots, const double* __restrict__ node_coords,
+                                                                 const int32_t* __restrict__ outer, p2::VertexParams P,
+                                                                 double* __restrict__ values) {
+  extern __shared__ double stage_all[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = first + blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = r < end;
+  int32_t v0 = 0, v1 = 0;
+  int32_t nid[p2::kMaxRing];
+  uint32_t w[p2::kSlotWords];
+#pragma unroll
+  for (int s = 0; s < p2::kMaxRing; ++s) nid[s] = -1;
+#pragma unroll
+  for (int j = 0; j < p2::kSlotWords; ++j) w[j] = 0U;
+  if (in_range) {
+    v0 = __ldg(outer + r);
+    v1 = __ldg(outer + r + 1);
+#pragma unroll
+    for (int s = 0; s < p2::kMaxRing; ++s) nid[s] = __ldg(gnbr + static_cast<size_t>(s) * n_rows + r);
+#pragma unroll
+    for (int j = 0; j < p2::kSlotWords; ++j) w[j] = __ldg(gslots + static_cast<size_t>(j) * n_rows + r);
+  }
+  const bool regular = in_range && nid[0] >= 0;
+  const int32_t wbase = __shfl_sync(0xffffffffU, v0, 0);
+  const bool staged = !__any_sync(0xffffffffU, in_range && !regular && v1 > v0);
+  double* stage = stage_all + warp * (32 * (p2::kMaxVertexRowLen + 1));
+  double* dst = stage + (staged ? v0 - wbase : lane * (p2::kMaxVertexRowLen + 1));
+  if (regular) {
+    const double2* nc = reinterpret_cast<const double2*>(node_coords);
+    const double2 xi = __ldg(nc + r);
+    double dx[p2::kMaxRing], dy[p2::kMaxRing];
+#pragma unroll
+    for (int s = 0; s < p2::kMaxRing; ++s) {
+      const double2 q = __ldg(nc + (nid[s] >= 0 ? nid[s] : r));
+      dx[s] = q.x - xi.x;
+      dy[s] = q.y - xi.y;
+    }
+    p2::vertex_row_general<MODE>(P, dx, dy, w, dst);
+  }
+  __syncwarp();
+  if (staged) {
+    const unsigned ballot = __ballot_sync(0xffffffffU, in_range);
+    if (ballot == 0) return;
+    const int total = __shfl_sync(0xffffffffU, v1, 31 - __clz(ballot)) - wbase;
+    double* out = values + wbase;
+#pragma unroll
+    for (int k = 0; k < p2::kMaxVertexRowLen; ++k) {
+      const int idx = k * 32 + lane;
+      if (idx < total) out[idx] = stage[idx];
+    }
+  } else if (regular) {
+    for (int k = 0; k < v1 - v0; ++k) values[v0 + k] = dst[k];
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(128, 4) k_p2_edge_rows(int first, int end, int n_edges, int row0, const int32_t* __restrict__ enb,
                                                        const uint32_t* __restrict__ eslots, const double* __restrict__ node_coords,
@@ -439,7 +517,9 @@ int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
   auto cleanup = [&]() { cudaFree(flag); cudaFree(iota); cudaFree(d_num); cudaFree(tmp); };
   auto drop_plan = [&]() {
     cudaFree(p->p2v_nbr); cudaFree(p->p2v_slots); cudaFree(p->p2e_nbr); cudaFree(p->p2e_slots); cudaFree(p->p2_irregular);
+    cudaFree(p->p2g_nbr); cudaFree(p->p2g_slots);
     p->p2v_nbr = nullptr; p->p2v_slots = nullptr; p->p2e_nbr = nullptr; p->p2e_slots = nullptr; p->p2_irregular = nullptr;
+    p->p2g_nbr = nullptr; p->p2g_slots = nullptr; p->p2_general = false;
   };
 #define P2_CHECK(expr)                                                              \
   do {                                                                              \
@@ -466,6 +546,20 @@ int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
                                                                         p->p2e_slots, flag);
   ctx->launches++;
   P2_CHECK(cudaGetLastError());
+  // Unstructured meshes: vertex rows whose ring is not exactly six cells would all go to the generic kernel.  On request
+  // (LFGPU_P2_GENERAL=1; the kernel's host/device core is checked on the CPU, its CUDA wrapper has not been on a B200 yet)
+  // the plan for closed rings of 3..8 cells replaces the valence-6 plan of the vertex rows.
+  static const bool general_env = [] { const char* e = std::getenv("LFGPU_P2_GENERAL"); return e != nullptr && e[0] == '1'; }();
+  if (general_env) {
+    P2_CHECK(cudaMalloc(&p->p2g_nbr, sizeof(int32_t) * (p2::kMaxRing * static_cast<size_t>(nn) + 128)));
+    P2_CHECK(cudaMalloc(&p->p2g_slots, sizeof(uint32_t) * (p2::kSlotWords * static_cast<size_t>(nn) + 128)));
+    k_p2_vertex_plan_general<<<static_cast<unsigned>(cdiv(nn, 128)), 128, 0, st>>>(nn, p->o_stride, p->pos_row, p->adj_ptr, p->adj,
+                                                                                    mesh->cell_nodes, static_cast<const uint8_t*>(p->pos),
+                                                                                    p->outer, p->p2g_nbr, p->p2g_slots, flag);
+    ctx->launches++;
+    P2_CHECK(cudaGetLastError());
+    p->p2_general = true;
+  }
   P2_CHECK(cudaMalloc(&iota, sizeof(int32_t) * p->n_outer));
   P2_CHECK(cudaMalloc(&d_num, sizeof(int64_t)));
   cub::CountingInputIterator<int32_t> count_it(0);
@@ -521,7 +615,20 @@ int p2_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* 
   // the share of the range in the vertex rows [0, nn) and in the edge rows [nn, nn + ne)
   const int v_first = static_cast<int>(std::min<int64_t>(std::max<int64_t>(r0, 0), nn)), v_end = static_cast<int>(std::min<int64_t>(r1, nn));
   const int e_first = static_cast<int>(std::max<int64_t>(r0 - nn, 0)), e_end = static_cast<int>(std::min<int64_t>(std::max<int64_t>(r1 - nn, 0), ne));
-  if (v_end > v_first) {
+  if (v_end > v_first && p->p2_general) {
+    p2::VertexParams G;
+    G.a00 = P.a00; G.a01 = P.a01; G.a10 = P.a10; G.a11 = P.a11; G.gamma = P.gamma;
+    for (int b = 0; b < 6; ++b) {
+      G.k00[b] = P.vk00[b]; G.k01[b] = P.vk01[b]; G.k10[b] = P.vk10[b]; G.k11[b] = P.vk11[b]; G.km[b] = P.vm[b];
+    }
+    const size_t smem_g = sizeof(double) * (threads / 32) * 32 * (p2::kMaxVertexRowLen + 1);
+    const unsigned gg = static_cast<unsigned>(cdiv(v_end - v_first, threads));
+    if (simple)
+      k_p2_vertex_rows_general<0><<<gg, threads, smem_g, ctx->stream>>>(v_first, v_end, nn, p->p2g_nbr, p->p2g_slots, mesh->node_coords, p->outer, G, d_values);
+    else
+      k_p2_vertex_rows_general<1><<<gg, threads, smem_g, ctx->stream>>>(v_first, v_end, nn, p->p2g_nbr, p->p2g_slots, mesh->node_coords, p->outer, G, d_values);
+    LFGPU_LAUNCH_CHECK(ctx);
+  } else if (v_end > v_first) {
     const unsigned gv = static_cast<unsigned>(cdiv(v_end - v_first, threads));
     if (simple)
       k_p2_vertex_rows<0><<<gv, threads, smem_v, ctx->stream>>>(v_first, v_end, nn, p->p2v_nbr, p->p2v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values);

@@ -124,6 +124,9 @@ struct lfgpu_pattern {
   uint32_t* p2v_slots = nullptr;     // [3][p2_nn] 6 x 5 bits each: slots of the neighbour / spoke-edge / rim-edge columns
   int32_t* p2e_nbr = nullptr;        // [4][n_edges] endpoints p, q and opposite vertices o_1, o_2 of every edge row
   uint32_t* p2e_slots = nullptr;     // [n_edges] 8 x 4 bits: slots of p, q, o_1, o_2, (q,o_1), (o_1,p), (q,o_2), (o_2,p)
+  bool p2_general = false;           // vertex rows planned for closed rings of 3..8 cells (rows_p2_core.h) instead of exactly 6
+  int32_t* p2g_nbr = nullptr;        // [8][p2_nn]
+  uint32_t* p2g_slots = nullptr;     // [6][p2_nn]
   int32_t* p2_irregular = nullptr;   // rows left to the generic gather kernel (ascending)
   int64_t n_p2_irregular = 0;
   std::vector<int32_t> p2_irregular_host;  // host copy: a row range looks up its share of the list

@@ -249,6 +249,8 @@ void lfgpu_pattern_destroy(lfgpu_pattern* p) {
   cudaFree(p->p2e_nbr);
   cudaFree(p->p2e_slots);
   cudaFree(p->p2_irregular);
+  cudaFree(p->p2g_nbr);
+  cudaFree(p->p2g_slots);
   cudaFree(p->p3v_nbr);
   cudaFree(p->p3v_slots);
   cudaFree(p->p3e_nbr);

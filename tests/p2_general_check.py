@@ -1,0 +1,55 @@
+"""Run with LFGPU_P2_GENERAL=1 (tests/test_gpu_zz_p2_general.py does): P2 assembly on unstructured triangle meshes through the
+row kernels with the general-valence vertex plan, against the oracle.  Prints P2_GENERAL_OK."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import lehrfempp_b200 as lf  # noqa: E402
+from oracle import lfo  # noqa: E402
+from oracle.lfo_gmsh import GmshReader as OracleReader  # noqa: E402
+
+assert os.environ.get("LFGPU_P2_GENERAL") == "1"
+ctx = lf.Context(0)
+NIL = 0xFFFFFFFF
+
+
+def meshes():
+    path = os.path.join(ROOT, "tests", "golden", "msh", "circle_first_order.msh")
+    xy, en, cn, _ = OracleReader(path).arrays()
+    yield "gmsh circle", xy, cn, en
+    from scipy.spatial import Delaunay
+    for seed, n in ((11, 150), (12, 4000)):
+        pts = np.random.default_rng(seed).random((n, 2))
+        tri = Delaunay(pts).simplices.astype(np.uint32)
+        yield "delaunay %d" % n, pts, np.hstack([tri, np.full((len(tri), 1), NIL, np.uint32)]), None
+    om = lfo.Mesh.tp_tria(9, 7)
+    ex = om.export()
+    yield "tp_tria uploaded", ex["node_coords"], ex["cell_nodes"], ex["edge_nodes"]
+
+
+for name, xy, cn, en in meshes():
+    om = lfo.Mesh.from_arrays(xy, cn, edge_nodes=en)
+    gm = ctx.mesh_upload(xy, cn)
+    gm.build_topology(en)
+    for major, csr in ((lf.ROW_MAJOR, True), (lf.COL_MAJOR, False)):
+        pat = gm.dofmap_lagrange(2).symbolic(major=major)
+        for ga, gg, oa, og in ((lf.Coeff.const(1.0), lf.Coeff.const(0.0), lfo.coeff.const(1.0), lfo.coeff.const(0.0)),
+                               (lf.Coeff.const2x2([[2.0, 0.5], [-0.25, 1.5]]), lf.Coeff.const(1.25),
+                                lfo.coeff.const2x2([[2.0, 0.5], [-0.25, 1.5]]), lfo.coeff.const(1.25))):
+            o = om.assemble_rd(2, oa, og, csr=csr)
+            outer, inner = pat.download()
+            assert np.array_equal(outer, o[0]) and np.array_equal(inner, o[1]), name
+            try:
+                v = pat.assemble_reaction_diffusion(2, ga, gg, algo=lf.ALGO_FAN).to_host()
+            except lf.LfgpuError as e:
+                assert e.code == -7, e  # too few regular rows on this mesh
+                print(name, "row kernels declined")
+                continue
+            err = np.abs(v - o[2]).max() / np.abs(o[2]).max()
+            ref = pat.assemble_reaction_diffusion(2, ga, gg, algo=lf.ALGO_GATHER).to_host()
+            assert err <= 1e-12 and np.abs(v - ref).max() <= 1e-13 * np.abs(ref).max(), (name, err)
+            print(name, "major", major, "err %.2e" % err)
+print("P2_GENERAL_OK")
