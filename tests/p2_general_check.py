@@ -23,8 +23,16 @@ def meshes():
     from scipy.spatial import Delaunay
     for seed, n in ((11, 150), (12, 4000)):
         pts = np.random.default_rng(seed).random((n, 2))
-        tri = Delaunay(pts).simplices.astype(np.uint32)
-        yield "delaunay %d" % n, pts, np.hstack([tri, np.full((len(tri), 1), NIL, np.uint32)]), None
+        tri = Delaunay(pts).simplices
+        # drop the slivers of the convex hull (the device rejects degenerate cells like the reference's geometry classes)
+        a, b, c = pts[tri[:, 0]], pts[tri[:, 1]], pts[tri[:, 2]]
+        area2 = np.abs((b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (c[:, 0] - a[:, 0]) * (b[:, 1] - a[:, 1]))
+        longest2 = np.maximum.reduce([((b - a) ** 2).sum(1), ((c - b) ** 2).sum(1), ((a - c) ** 2).sum(1)])
+        tri = tri[area2 > 0.05 * longest2].astype(np.uint32)
+        used = np.unique(tri)
+        remap = np.full(len(pts), -1)
+        remap[used] = np.arange(len(used))
+        yield "delaunay %d" % n, pts[used], np.hstack([remap[tri].astype(np.uint32), np.full((len(tri), 1), NIL, np.uint32)]), None
     om = lfo.Mesh.tp_tria(9, 7)
     ex = om.export()
     yield "tp_tria uploaded", ex["node_coords"], ex["cell_nodes"], ex["edge_nodes"]
