@@ -43,6 +43,22 @@ def meshes():
     yield "tp_tria 3x3 refined twice", lfo.Mesh.tp_tria(3, 3).refine_regular().refine_regular()
     xy, en, cn, _ = OracleReader(os.path.join(HERE, "golden", "msh", "circle_first_order.msh")).arrays()
     yield "gmsh circle", lfo.Mesh.from_arrays(xy, cn, edge_nodes=en)
+    # wheels with the hub as local vertex 0, 1 or 2 and every third cell listed clockwise: edge directions disagree with the
+    # cells' local edge directions in every combination (the reversal of the two edge dofs, dofhandler.cc:245-260)
+    for m in (5, 6, 7):
+        ang = 2 * np.pi * (np.arange(m) + 0.1 * np.sin(np.arange(m))) / m
+        wxy = np.vstack([[0.05, -0.03], np.stack([np.cos(ang), 0.8 * np.sin(ang)], axis=1)])
+        rows = []
+        for k in range(m):
+            a, b = 1 + k, 1 + (k + 1) % m
+            rows.append([[0, a, b], [b, 0, a], [b, a, 0]][k % 3] + [0xFFFFFFFF])
+        yield "wheel %d" % m, lfo.Mesh.from_arrays(wxy, np.array(rows, dtype=np.uint32))
+    from scipy.spatial import Delaunay
+    pts = np.random.default_rng(11).random((150, 2))
+    tri = Delaunay(pts).simplices.astype(np.uint32)
+    flip = np.arange(len(tri)) % 4 == 1  # a quarter of the cells clockwise
+    tri[flip] = tri[flip][:, [0, 2, 1]]
+    yield "delaunay 150, mixed orientation", lfo.Mesh.from_arrays(pts, np.hstack([tri, np.full((len(tri), 1), 0xFFFFFFFF, np.uint32)]))
 
 
 COEFFS = [
