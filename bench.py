@@ -120,6 +120,11 @@ def cpu_all_cores_sample(n, max_threads=32):
     and one matrix per thread; the reference itself cannot use more than one core).  One pass per copy."""
     from oracle import lfo
     threads = max(1, min(os.cpu_count() or 1, max_threads))
+    try:  # one copy holds about 1.2 GB at n = 707 (mesh objects, triplets, compressed matrix): stay well inside the free memory
+        import psutil
+        threads = max(1, min(threads, int(psutil.virtual_memory().available / 2.5e9)))
+    except Exception:
+        threads = min(threads, 8)
     meshes = [None] * threads
     start = [0.0] * threads
     done = [0.0] * threads
