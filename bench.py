@@ -41,6 +41,10 @@ WORKLOADS = {
     # BASELINE config 4 names 3.2e7 triangles; P3 on them has 2.45e9 stored values, more than the int32 storage index of the
     # reference's Eigen::SparseMatrix (and of the replicated pattern here) can address -> LFGPU_ERR_OVERFLOW.  This is the
     # largest mesh of the family that fits (nnz 2.11e9); the full size needs the per-GPU row-block pattern.
+    # not a BASELINE configuration: an unstructured mesh (Delaunay triangulation of seeded random points, hull slivers removed,
+    # valences 3..10) for the row kernels on Gmsh-like input; LFGPU_P2_GENERAL=1 selects the general-valence P2 vertex kernel
+    "u2": ("U2: P2 Laplacian on an unstructured mesh (Delaunay triangulation of 5.0e5 random points, about 1.0e6 triangles), CSR",
+           "delaunay", 500000, 2),
     "c4_27m": ("C4: P3 stiffness+mass on a MeshHierarchy-refined mesh: TP-triangle mesh n=232, 4 x RefineRegular (2.76e7 cells, the "
                "largest of the family whose nnz fits the reference's int32 storage index), CSR", "refined:4", 232, 3),
 }
@@ -247,7 +251,7 @@ def main():
         desc += " [n overridden to %d]" % n
     ctx = lf.Context(local_rank)
     algo = {"auto": lf.ALGO_AUTO, "fan": lf.ALGO_FAN, "gather": lf.ALGO_GATHER, "atomic": lf.ALGO_ATOMIC}[args.algo]
-    structured = kind == "tp_tria" or kind.startswith("refined:")
+    structured = kind == "tp_tria" or kind.startswith("refined:") or kind == "delaunay"  # triangle meshes: the row kernels apply
     # kernels that own matrix rows in registers (LFGPU_ALGO_AUTO takes them on triangle meshes with constant coefficients)
     row_kernels = {1: "k_assemble_p1_fan", 2: "k_p2_vertex_rows + k_p2_edge_rows", 3: "k_p3_vertex_rows + k_p3_edge_rows + k_p3_cell_rows"}
     if args.algo == "auto":
@@ -266,6 +270,21 @@ def main():
         mesh = ctx.mesh_tp_tria(n, n)
         for _ in range(int(kind.split(":")[1])):
             mesh = mesh.refine_regular()
+    elif kind == "delaunay":
+        from scipy.spatial import Delaunay
+        pts = np.random.default_rng(12345).random((n, 2))
+        tri = Delaunay(pts).simplices
+        a, b, c = pts[tri[:, 0]], pts[tri[:, 1]], pts[tri[:, 2]]
+        area2 = np.abs((b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (c[:, 0] - a[:, 0]) * (b[:, 1] - a[:, 1]))
+        longest2 = np.maximum.reduce([((b - a) ** 2).sum(1), ((c - b) ** 2).sum(1), ((a - c) ** 2).sum(1)])
+        tri = tri[area2 > 0.05 * longest2]  # slivers along the convex hull
+        used = np.unique(tri)
+        remap = np.full(n, -1, dtype=np.int64)
+        remap[used] = np.arange(used.size)
+        cn = np.full((tri.shape[0], 4), 0xFFFFFFFF, dtype=np.uint32)
+        cn[:, :3] = remap[tri]
+        mesh = ctx.mesh_upload(pts[used], cn)
+        del pts, tri, a, b, c, area2, longest2, cn
     else:
         mesh = ctx.mesh_hybrid(n, 0.2, 12345)
     dm = mesh.dofmap_lagrange(degree)

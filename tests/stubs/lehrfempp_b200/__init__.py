@@ -105,6 +105,9 @@ class Context:
         n = min(nx, 64)  # the stub keeps arrays small whatever the workload asks for
         return _Mesh(self, 2 * n * n, 0, (n + 1) * (n + 1))
 
+    def mesh_upload(self, node_coords, cell_nodes, cell_coords=None):
+        return _Mesh(self, int(cell_nodes.shape[0]), 0, int(node_coords.shape[0]))
+
     def mesh_hybrid(self, n, jitter, seed):
         n = min(n, 64)
         return _Mesh(self, n * n, n * n // 2, (n + 1) * (n + 1))

@@ -34,6 +34,12 @@ KERNEL = {"c5_1e8": "k_assemble_p1_fan", "c1": "k_assemble_p1_fan", "c2": "k_ass
           "c4_27m": "k_p3_vertex_rows + k_p3_edge_rows + k_p3_cell_rows"}
 
 
+def test_unstructured_workload():
+    out = run_bench("--workload", "u2", "--n", "3000", "--steps", "3", "--no-cpu-baseline", "--no-e2e")
+    check_line(out, 3)
+    assert out["roofline"]["kernel"] == "k_p2_vertex_rows + k_p2_edge_rows" and 5000 < out["config"]["cells"] < 6100
+
+
 def check_line(out, steps):
     for key in REQUIRED:
         assert key in out, key

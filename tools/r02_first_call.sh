@@ -14,6 +14,10 @@ for w in c3 c4 c4s c2; do
   timeout 120 python bench.py --workload $w --steps 30 --warmup 5 > $out/r02_bench_$w.json 2> $out/bench_$w.err
   tail -c 600 $out/r02_bench_$w.json; echo
 done
+# 2b. unstructured mesh: valence-6 plan + generic kernel for the other vertex rows vs the general-valence vertex kernel
+timeout 120 python bench.py --workload u2 --steps 30 --warmup 5 --no-cpu-baseline --no-e2e > $out/r02_bench_u2_default.json 2> $out/bench_u2.err
+LFGPU_P2_GENERAL=1 timeout 120 python bench.py --workload u2 --steps 30 --warmup 5 --no-cpu-baseline --no-e2e > $out/r02_bench_u2_general.json 2>> $out/bench_u2.err
+tail -c 400 $out/r02_bench_u2_default.json; echo; tail -c 400 $out/r02_bench_u2_general.json; echo
 # 3. full ncu capture of the three P3 row kernels (none exists yet) and of the C2 item kernel
 timeout 150 ncu --set full --clock-control none --import-source on -k "regex:k_p3_(vertex|edge|cell)_rows" -c 3 -f -o $out/r02_p3_rows \
   python tools/rows_probe.py 3 1448 rows > $out/ncu_p3.log 2>&1
