@@ -184,6 +184,96 @@ LFGPU_HD bool vertex_plan(int64_t r, int m, const uint32_t* items, const uint32_
   return true;
 }
 
+// ---- vertex rows for ANY closed ring of 3..8 cells (unstructured meshes) ------------------------------------------------
+// Same decomposition; the loop runs over eight ring positions under `k < m` predicates so that register indices stay
+// static.  Plan: ring[8] (-1 beyond the ring), 48 slot bytes [k][n_k, spokeA_k, spokeB_k, rim1_k, rim2_k, interior_k] in 12
+// words and the ring length m in a 13th.
+constexpr int kMaxRing = 8;
+constexpr int kMaxVertexRowLen = 1 + 6 * kMaxRing;  // 49
+constexpr int kGeneralSlotWords = 13;               // 48 slot bytes + the ring length
+
+LFGPU_HD bool vertex_plan_general(int64_t r, int m, const uint32_t* items, const uint32_t* cell_nodes, const uint8_t* pos, int o_stride,
+                                  int pos_row, int row_len, int32_t (&ring)[kMaxRing], uint32_t (&words)[kGeneralSlotWords]) {
+  if (m < 3 || m > kMaxRing || row_len != 1 + 6 * m) return false;
+  uint32_t ja[kMaxRing], ka[kMaxRing], rg[kMaxRing];
+  int la[kMaxRing], ord[kMaxRing];
+  int64_t cid[kMaxRing];
+  bool fwd[kMaxRing];
+  for (int t = 0; t < m; ++t) {
+    cid[t] = items[t] >> 4;
+    la[t] = static_cast<int>(items[t] & 15U);
+    if (la[t] > 2) return false;
+    const uint32_t* v = cell_nodes + 4 * cid[t];
+    if (v[3] != 0xFFFFFFFFu) return false;  // a quadrilateral
+    ja[t] = v[(la[t] + 1) % 3];
+    ka[t] = v[(la[t] + 2) % 3];
+  }
+  unsigned used = 1U;
+  rg[0] = ja[0];
+  ord[0] = 0;
+  fwd[0] = true;
+  uint32_t cur = ka[0];
+  for (int k = 1; k < m; ++k) {
+    int nxt = -1;
+    for (int u = 0; u < m; ++u) {
+      if (!(used & (1U << u)) && (ja[u] == cur || ka[u] == cur)) {
+        nxt = u;
+        break;
+      }
+    }
+    if (nxt < 0) return false;
+    used |= 1U << nxt;
+    rg[k] = cur;
+    ord[k] = nxt;
+    fwd[k] = (ja[nxt] == cur);
+    cur = fwd[k] ? ka[nxt] : ja[nxt];
+  }
+  if (cur != rg[0]) return false;
+  for (int k = 0; k < m; ++k) {
+    if (rg[k] == static_cast<uint32_t>(r)) return false;
+    for (int u = 0; u < k; ++u)
+      if (rg[u] == rg[k]) return false;
+  }
+  uint8_t s[48];
+  for (int j = 0; j < 48; ++j) s[j] = 0;
+  int sd = -1;
+  for (int k = 0; k < m; ++k) {
+    const int u = ord[k];
+    const int a = la[u], vb = (a + 1) % 3, vc = (a + 2) % 3;
+    const uint8_t* prow = pos + (cid[u] * o_stride + a) * static_cast<int64_t>(pos_row);
+    if (sd >= 0 && prow[a] != sd) return false;
+    sd = prow[a];
+    if (fwd[k]) {
+      s[6 * k + 0] = prow[vb];
+      s[6 * k + 1] = prow[3 + 2 * a];
+      s[6 * k + 2] = prow[3 + 2 * a + 1];
+      s[6 * k + 3] = prow[3 + 2 * vb];
+      s[6 * k + 4] = prow[3 + 2 * vb + 1];
+    } else {
+      s[6 * k + 0] = prow[vc];
+      s[6 * k + 1] = prow[3 + 2 * vc + 1];
+      s[6 * k + 2] = prow[3 + 2 * vc];
+      s[6 * k + 3] = prow[3 + 2 * vb + 1];
+      s[6 * k + 4] = prow[3 + 2 * vb];
+    }
+    s[6 * k + 5] = prow[9];
+  }
+  uint64_t seen = 1ULL << sd;
+  int sum = 0;
+  for (int j = 0; j < 6 * m; ++j) {
+    if (s[j] >= row_len) return false;
+    seen |= 1ULL << s[j];
+    sum += s[j];
+  }
+  if (seen != (1ULL << row_len) - 1ULL || sd != row_len * (row_len - 1) / 2 - sum) return false;
+  for (int k = 0; k < kMaxRing; ++k) ring[k] = k < m ? static_cast<int32_t>(rg[k]) : -1;
+  for (int j = 0; j < 12; ++j)
+    words[j] = static_cast<uint32_t>(s[4 * j]) | (static_cast<uint32_t>(s[4 * j + 1]) << 8) | (static_cast<uint32_t>(s[4 * j + 2]) << 16) |
+               (static_cast<uint32_t>(s[4 * j + 3]) << 24);
+  words[12] = static_cast<uint32_t>(m);
+  return true;
+}
+
 // Edge-dof row: false unless exactly two cells share the edge and the 16 slots are a permutation of 0..15.
 // ids = P (endpoint nearer to the dof), Q, o_1, o_2.
 LFGPU_HD bool edge_plan(int m, const uint32_t* items, const uint32_t* cell_nodes, const uint8_t* pos, int o_stride, int pos_row, int row_len,
@@ -286,6 +376,50 @@ LFGPU_HD void vertex_row(const Params& P, const double (&dx)[kRing], const doubl
   dst[byte_at(w, 1)] = first_a + carry_a;
   dst[byte_at(w, 2)] = first_b + carry_b;
   dst[666 - ssum] = diag;
+}
+
+// general ring: dx, dy entries k >= m unused; dst: the row's 1 + 6m values
+template <int MODE>
+LFGPU_HD void vertex_row_general(const Params& P, const double (&dx)[kMaxRing], const double (&dy)[kMaxRing],
+                                 const uint32_t (&w)[kGeneralSlotWords], double* dst) {
+  const int m = static_cast<int>(w[12]);
+  const int len = 1 + 6 * m;
+  int ssum = 0;
+  double t[10];
+  row<MODE, 0>(P, dx[0], dy[0], dx[1], dy[1], t);  // m >= 3: cell 0 is (i, n_0, n_1)
+  double diag = t[0];
+  const double first_n = t[1], first_a = t[3], first_b = t[4];
+  double carry_n = t[2], carry_b = t[7], carry_a = t[8];
+  dst[byte_at(w, 3)] = t[5];
+  dst[byte_at(w, 4)] = t[6];
+  dst[byte_at(w, 5)] = t[9];
+  ssum += byte_at(w, 0) + byte_at(w, 1) + byte_at(w, 2) + byte_at(w, 3) + byte_at(w, 4) + byte_at(w, 5);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int s = 1; s < kMaxRing; ++s) {
+    if (s < m) {
+      const bool last = (s + 1 == m);  // the last cell closes the ring with n_0
+      const double nx = last ? dx[0] : dx[(s + 1) & (kMaxRing - 1)], ny = last ? dy[0] : dy[(s + 1) & (kMaxRing - 1)];
+      row<MODE, 0>(P, dx[s], dy[s], nx, ny, t);
+      diag += t[0];
+      dst[byte_at(w, 6 * s + 0)] = carry_n + t[1];
+      dst[byte_at(w, 6 * s + 1)] = carry_a + t[3];
+      dst[byte_at(w, 6 * s + 2)] = carry_b + t[4];
+      dst[byte_at(w, 6 * s + 3)] = t[5];
+      dst[byte_at(w, 6 * s + 4)] = t[6];
+      dst[byte_at(w, 6 * s + 5)] = t[9];
+      ssum += byte_at(w, 6 * s) + byte_at(w, 6 * s + 1) + byte_at(w, 6 * s + 2) + byte_at(w, 6 * s + 3) + byte_at(w, 6 * s + 4) +
+              byte_at(w, 6 * s + 5);
+      carry_n = t[2];
+      carry_b = t[7];
+      carry_a = t[8];
+    }
+  }
+  dst[byte_at(w, 0)] = first_n + carry_n;
+  dst[byte_at(w, 1)] = first_a + carry_a;
+  dst[byte_at(w, 2)] = first_b + carry_b;
+  dst[len * (len - 1) / 2 - ssum] = diag;
 }
 
 // (ax, ay) = Q - P, (b1x, b1y) = o_1 - P, (b2x, b2y) = o_2 - P

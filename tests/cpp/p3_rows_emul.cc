@@ -11,6 +11,7 @@
 using namespace lfgpu::p3;
 
 namespace {
+bool g_general = false;  // vertex rows through the general-valence functions
 template <int MODE>
 void run(const Params& P, int64_t n_nodes, int64_t n_cells, const uint32_t* cell_nodes, const double* xy, int stride, int pos_row,
          const std::vector<int64_t>& adj_ptr, const std::vector<uint32_t>& adj, const std::vector<uint8_t>& pos, int64_t n_dofs,
@@ -23,15 +24,28 @@ void run(const Params& P, int64_t n_nodes, int64_t n_cells, const uint32_t* cell
     double* dst = values + outer[r];
     regular[r] = 0;
     if (r < n_nodes) {
-      int32_t ring[kRing];
-      uint32_t w[kVertexSlotWords];
-      if (!vertex_plan(r, m, items, cell_nodes, pos.data(), stride, pos_row, len, ring, w)) continue;
-      double dx[kRing], dy[kRing];
-      for (int k = 0; k < kRing; ++k) {
-        dx[k] = xy[2 * ring[k]] - xy[2 * r];
-        dy[k] = xy[2 * ring[k] + 1] - xy[2 * r + 1];
+      if (g_general) {  // closed rings of 3..8 cells
+        int32_t ring[kMaxRing];
+        uint32_t w[kGeneralSlotWords];
+        if (!vertex_plan_general(r, m, items, cell_nodes, pos.data(), stride, pos_row, len, ring, w)) continue;
+        double dx[kMaxRing], dy[kMaxRing];
+        for (int k = 0; k < kMaxRing; ++k) {
+          const int64_t n = ring[k] >= 0 ? ring[k] : r;
+          dx[k] = xy[2 * n] - xy[2 * r];
+          dy[k] = xy[2 * n + 1] - xy[2 * r + 1];
+        }
+        vertex_row_general<MODE>(P, dx, dy, w, dst);
+      } else {
+        int32_t ring[kRing];
+        uint32_t w[kVertexSlotWords];
+        if (!vertex_plan(r, m, items, cell_nodes, pos.data(), stride, pos_row, len, ring, w)) continue;
+        double dx[kRing], dy[kRing];
+        for (int k = 0; k < kRing; ++k) {
+          dx[k] = xy[2 * ring[k]] - xy[2 * r];
+          dy[k] = xy[2 * ring[k] + 1] - xy[2 * r + 1];
+        }
+        vertex_row<MODE>(P, dx, dy, w, dst);
       }
-      vertex_row<MODE>(P, dx, dy, w, dst);
       regular[r] = 1;
       counts[0]++;
     } else if (r < base_int) {
@@ -60,6 +74,8 @@ void run(const Params& P, int64_t n_nodes, int64_t n_cells, const uint32_t* cell
   }
 }
 }  // namespace
+
+extern "C" void p3_rows_emulate_general(int on) { g_general = on != 0; }
 
 extern "C" int p3_rows_emulate(int64_t n_nodes, int64_t n_cells, const uint32_t* cell_nodes, const double* node_xy, int stride,
                                const int32_t* dofs, int64_t n_dofs, const int32_t* outer, const int32_t* inner, const double* alpha4,

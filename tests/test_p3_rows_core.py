@@ -45,7 +45,7 @@ def meshes():
     yield "gmsh circle", lfo.Mesh.from_arrays(xy, cn, edge_nodes=en)
     # wheels with the hub as local vertex 0, 1 or 2 and every third cell listed clockwise: edge directions disagree with the
     # cells' local edge directions in every combination (the reversal of the two edge dofs, dofhandler.cc:245-260)
-    for m in (5, 6, 7):
+    for m in range(3, 9):
         ang = 2 * np.pi * (np.arange(m) + 0.1 * np.sin(np.arange(m))) / m
         wxy = np.vstack([[0.05, -0.03], np.stack([np.cos(ang), 0.8 * np.sin(ang)], axis=1)])
         rows = []
@@ -68,11 +68,16 @@ COEFFS = [
 ]
 
 
+@pytest.mark.parametrize("general", [False, True], ids=["ring6", "ring3to8"])
 @pytest.mark.parametrize("csr", [True, False], ids=["csr", "csc"])
 @pytest.mark.parametrize("coeff", COEFFS, ids=[c[0] for c in COEFFS])
-def test_rows_match_oracle(emul, coeff, csr):
+def test_rows_match_oracle(emul, coeff, csr, general):
+    """general = vertex rows through vertex_plan_general / vertex_row_general (closed rings of 3..8 cells, the opt-in kernel for
+    unstructured meshes) instead of the valence-6 functions"""
     _, a_scalar, a_tensor, gamma = coeff
     K = reference_tensors()
+    emul.p3_rows_emulate_general(1 if general else 0)
+    seen = set()
     for name, om in meshes():
         ex = om.export()
         assert om.n_quad == 0
@@ -105,7 +110,11 @@ def test_rows_match_oracle(emul, coeff, csr):
         valence = np.bincount(ex["cell_nodes"][:, :3].ravel(), minlength=om.n_nodes)
         bd_nodes = np.zeros(om.n_nodes, bool)
         bd_nodes[ex["edge_nodes"][bd].ravel()] = True
-        assert counts[0] == int(((valence == 6) & ~bd_nodes).sum()), name
+        if general:
+            assert counts[0] == int(((valence >= 3) & (valence <= 8) & ~bd_nodes).sum()), name
+            seen |= set(valence[(valence >= 3) & (valence <= 8) & ~bd_nodes])
+        else:
+            assert counts[0] == int(((valence == 6) & ~bd_nodes).sum()), name
         if name.startswith("tp_tria"):
             assert counts[0] > 0
         # values of the rows taken: the oracle's, within the bar of the path
@@ -114,3 +123,6 @@ def test_rows_match_oracle(emul, coeff, csr):
         assert not np.isnan(out[sel]).any() and np.isnan(out[~sel]).all()
         err = np.abs(out[sel] - vals[sel]).max() / np.abs(vals).max()
         assert err <= TOL, (name, err)
+    emul.p3_rows_emulate_general(0)
+    if general:
+        assert seen >= {3, 4, 5, 6, 7, 8}
