@@ -50,6 +50,23 @@ __global__ void k_p3_vertex_plan(int64_t n_nodes, int o_stride, int pos_row, con
   irregular[r] = (!ok && m > 0) ? 1 : 0;
 }
 
+// closed rings of 3..8 cells (unstructured meshes): gnbr[k][r] = n_k (-1 beyond the ring / irregular row), gslots[0..12][r]
+__global__ void k_p3_vertex_plan_general(int64_t n_nodes, int o_stride, int pos_row, const int32_t* __restrict__ adj_ptr,
+                                         const uint32_t* __restrict__ adj, const uint32_t* __restrict__ cell_nodes,
+                                         const uint8_t* __restrict__ pos, const int32_t* __restrict__ outer, int32_t* __restrict__ gnbr,
+                                         uint32_t* __restrict__ gslots, uint8_t* __restrict__ irregular) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= n_nodes) return;
+  const int32_t it0 = adj_ptr[r];
+  const int m = adj_ptr[r + 1] - it0;
+  int32_t ring[kMaxRing];
+  uint32_t w[kGeneralSlotWords];
+  const bool ok = vertex_plan_general(r, m, adj + it0, cell_nodes, pos, o_stride, pos_row, outer[r + 1] - outer[r], ring, w);
+  for (int k = 0; k < kMaxRing; ++k) gnbr[static_cast<int64_t>(k) * n_nodes + r] = ok ? ring[k] : -1;
+  for (int j = 0; j < kGeneralSlotWords; ++j) gslots[static_cast<int64_t>(j) * n_nodes + r] = ok ? w[j] : 0U;
+  irregular[r] = (!ok && m > 0) ? 1 : 0;
+}
+
 __global__ void k_p3_edge_plan(int64_t n_nodes, int64_t n_erows, int o_stride, int pos_row, const int32_t* __restrict__ adj_ptr,
                                const uint32_t* __restrict__ adj, const uint32_t* __restrict__ cell_nodes,
                                const uint8_t* __restrict__ pos, const int32_t* __restrict__ outer, int32_t* __restrict__ enb,
@@ -157,6 +174,64 @@ __global__ void __launch_bounds__(128, 3) k_p3_vertex_rows(int first, int end, i
     vertex_row<MODE>(P, dx, dy, w, dst);
   }
   write_rows<kVertexRowLen>(staged, regular, in_range, lane, v0, v1, wbase, stage, dst, values);
+}
+
+// vertex rows with closed rings of 3..8 cells (rows_p3_core.h: vertex_row_general); rows of different lengths (1 + 6m) share a
+// warp, the staged copy-out only needs their value ranges to be consecutive
+template <int MODE>
+__global__ void __launch_bounds__(128, 2) k_p3_vertex_rows_general(int first, int end, int n_rows, const int32_t* __restrict__ gnbr,
+                                                                 const uint32_t* __restrict__ gslots, const double* __restrict__ node_coords,
+                                                                 const int32_t* __restrict__ outer, Params P, double* __restrict__ values) {
+  extern __shared__ double stage_all[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = first + blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = r < end;
+  int32_t v0 = 0, v1 = 0;
+  int32_t nid[kMaxRing];
+  uint32_t w[kGeneralSlotWords];
+#pragma unroll
+  for (int s = 0; s < kMaxRing; ++s) nid[s] = -1;
+#pragma unroll
+  for (int j = 0; j < kGeneralSlotWords; ++j) w[j] = 0U;
+  if (in_range) {
+    v0 = __ldg(outer + r);
+    v1 = __ldg(outer + r + 1);
+#pragma unroll
+    for (int s = 0; s < kMaxRing; ++s) nid[s] = __ldg(gnbr + static_cast<size_t>(s) * n_rows + r);
+#pragma unroll
+    for (int j = 0; j < kGeneralSlotWords; ++j) w[j] = __ldg(gslots + static_cast<size_t>(j) * n_rows + r);
+  }
+  const bool regular = in_range && nid[0] >= 0;
+  const int32_t wbase = __shfl_sync(0xffffffffU, v0, 0);
+  const bool staged = !__any_sync(0xffffffffU, in_range && !regular && v1 > v0);
+  double* stage = stage_all + warp * (32 * (kMaxVertexRowLen + 1));
+  double* dst = stage + (staged ? v0 - wbase : lane * (kMaxVertexRowLen + 1));
+  if (regular) {
+    const double2* nc = reinterpret_cast<const double2*>(node_coords);
+    const double2 xi = __ldg(nc + r);
+    double dx[kMaxRing], dy[kMaxRing];
+#pragma unroll
+    for (int s = 0; s < kMaxRing; ++s) {
+      const double2 q = __ldg(nc + (nid[s] >= 0 ? nid[s] : r));
+      dx[s] = q.x - xi.x;
+      dy[s] = q.y - xi.y;
+    }
+    vertex_row_general<MODE>(P, dx, dy, w, dst);
+  }
+  __syncwarp();
+  if (staged) {
+    const unsigned ballot = __ballot_sync(0xffffffffU, in_range);
+    if (ballot == 0) return;
+    const int total = __shfl_sync(0xffffffffU, v1, 31 - __clz(ballot)) - wbase;
+    double* out = values + wbase;
+#pragma unroll
+    for (int k = 0; k < kMaxVertexRowLen; ++k) {
+      const int idx = k * 32 + lane;
+      if (idx < total) out[idx] = stage[idx];
+    }
+  } else if (regular) {
+    for (int k = 0; k < v1 - v0; ++k) values[v0 + k] = dst[k];
+  }
 }
 
 template <int MODE>
@@ -269,7 +344,9 @@ int p3_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
   auto cleanup = [&]() { cudaFree(flag); cudaFree(iota); cudaFree(d_num); cudaFree(tmp); };
   auto drop_plan = [&]() {
     cudaFree(p->p3v_nbr); cudaFree(p->p3v_slots); cudaFree(p->p3e_nbr); cudaFree(p->p3e_slots); cudaFree(p->p3_irregular);
+    cudaFree(p->p3g_nbr); cudaFree(p->p3g_slots);
     p->p3v_nbr = nullptr; p->p3v_slots = nullptr; p->p3e_nbr = nullptr; p->p3e_slots = nullptr; p->p3_irregular = nullptr;
+    p->p3g_nbr = nullptr; p->p3g_slots = nullptr; p->p3_general = false;
   };
 #define P3_CHECK(expr)                                                              \
   do {                                                                              \
@@ -295,6 +372,19 @@ int p3_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
                                                                          p->p3e_slots, flag);
   ctx->launches++;
   P3_CHECK(cudaGetLastError());
+  // unstructured meshes, on request (LFGPU_P3_GENERAL=1; core checked on the CPU, wrapper not yet run on a B200): the plan
+  // for closed rings of 3..8 cells replaces the valence-6 plan of the vertex rows
+  static const bool general_env = [] { const char* e = std::getenv("LFGPU_P3_GENERAL"); return e != nullptr && e[0] == '1'; }();
+  if (general_env) {
+    P3_CHECK(cudaMalloc(&p->p3g_nbr, sizeof(int32_t) * (kMaxRing * static_cast<size_t>(nn) + 128)));
+    P3_CHECK(cudaMalloc(&p->p3g_slots, sizeof(uint32_t) * (kGeneralSlotWords * static_cast<size_t>(nn) + 128)));
+    k_p3_vertex_plan_general<<<static_cast<unsigned>(cdiv(nn, 128)), 128, 0, st>>>(nn, p->o_stride, p->pos_row, p->adj_ptr, p->adj,
+                                                                                    mesh->cell_nodes, static_cast<const uint8_t*>(p->pos),
+                                                                                    p->outer, p->p3g_nbr, p->p3g_slots, flag);
+    ctx->launches++;
+    P3_CHECK(cudaGetLastError());
+    p->p3_general = true;
+  }
   P3_CHECK(cudaMalloc(&iota, sizeof(int32_t) * p->n_outer));
   P3_CHECK(cudaMalloc(&d_num, sizeof(int64_t)));
   cub::CountingInputIterator<int32_t> count_it(0);
@@ -354,8 +444,16 @@ int p3_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* 
   const int v_first = clip(r0, 0, nn), v_end = clip(r1, 0, nn);
   const int e_first = clip(r0 - nn, 0, ner), e_end = clip(r1 - nn, 0, ner);
   const int c_first = clip(r0 - base_int, 0, nc), c_end = clip(r1 - base_int, 0, nc);
+  const size_t smem_g = sizeof(double) * (threads / 32) * 32 * (kMaxVertexRowLen + 1);
 #define P3_LAUNCH(MODE)                                                                                                                   \
-  if (v_end > v_first) {                                                                                                                  \
+  if (v_end > v_first && p->p3_general) {                                                                                                 \
+    /* 51 200 bytes of stage: above the 48 KB a kernel gets without asking */                                                             \
+    LFGPU_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_p3_vertex_rows_general<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,               \
+                                               static_cast<int>(smem_g)));                                                                \
+    k_p3_vertex_rows_general<MODE><<<static_cast<unsigned>(cdiv(v_end - v_first, threads)), threads, smem_g, ctx->stream>>>(              \
+        v_first, v_end, nn, p->p3g_nbr, p->p3g_slots, mesh->node_coords, p->outer, P, d_values);                                          \
+    LFGPU_LAUNCH_CHECK(ctx);                                                                                                              \
+  } else if (v_end > v_first) {                                                                                                           \
     k_p3_vertex_rows<MODE><<<static_cast<unsigned>(cdiv(v_end - v_first, threads)), threads, smem_v, ctx->stream>>>(                      \
         v_first, v_end, nn, p->p3v_nbr, p->p3v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values);                                   \
     LFGPU_LAUNCH_CHECK(ctx);                                                                                                              \

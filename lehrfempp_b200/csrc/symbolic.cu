@@ -256,6 +256,8 @@ void lfgpu_pattern_destroy(lfgpu_pattern* p) {
   cudaFree(p->p3e_nbr);
   cudaFree(p->p3e_slots);
   cudaFree(p->p3_irregular);
+  cudaFree(p->p3g_nbr);
+  cudaFree(p->p3g_slots);
   cudaFree(p->o_dofs);
   if (p->i_dofs != p->o_dofs) cudaFree(p->i_dofs);
   cudaFree(p->o_nldof);

@@ -8,7 +8,7 @@ mkdir -p $out
 timeout 180 python -m pytest tests -m gpu -q 2>&1 | tail -25 > $out/r02_gpu_tests.log
 tail -5 $out/r02_gpu_tests.log
 # 1b. the opt-in general-valence P2 vertex kernel (unstructured meshes), never run on a B200 yet
-LFGPU_P2_GENERAL=1 timeout 120 python tests/p2_general_check.py > $out/r02_p2_general.log 2>&1; tail -3 $out/r02_p2_general.log
+LFGPU_P2_GENERAL=1 LFGPU_P3_GENERAL=1 timeout 180 python tests/p2_general_check.py > $out/r02_p2_general.log 2>&1; tail -3 $out/r02_p2_general.log
 # 2. bench lines of the configurations that changed kernels (P2 / P3 row kernels on AUTO) and of the weakest one (C2)
 for w in c3 c4 c4s c2; do
   timeout 120 python bench.py --workload $w --steps 30 --warmup 5 > $out/r02_bench_$w.json 2> $out/bench_$w.err
