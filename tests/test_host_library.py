@@ -95,3 +95,11 @@ def test_row_ranges_cover_and_balance():
     # degenerate: fewer rows than ranks
     b = row_ranges(torch.tensor([0, 3, 5], dtype=torch.int32), 4)
     assert b[0] == 0 and b[-1] == 2 and all(b[k] <= b[k + 1] for k in range(4))
+
+
+def test_c_abi_header_is_plain_c():
+    """include/lfgpu.h is the FFI boundary: it must compile as C99 (no C++ in the signatures) and stand alone."""
+    import subprocess
+    hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "lfgpu.h")
+    out = subprocess.run(["gcc", "-x", "c", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", hdr], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
