@@ -430,8 +430,9 @@ __global__ void __launch_bounds__(128, 4) k_p2_vertex_rows_general(int first, in
   }
 }
 
+// 12 CTAs per SM = the occupancy of the measured kernel (40 registers; the row-range arguments had pushed ptxas to 46 -> 10 CTAs)
 template <int MODE>
-__global__ void __launch_bounds__(128, 4) k_p2_edge_rows(int first, int end, int n_edges, int row0, const int32_t* __restrict__ enb,
+__global__ void __launch_bounds__(128, 12) k_p2_edge_rows(int first, int end, int n_edges, int row0, const int32_t* __restrict__ enb,
                                                        const uint32_t* __restrict__ eslots, const double* __restrict__ node_coords,
                                                        const int32_t* __restrict__ outer, int pf_dist, P2Params P,
                                                        double* __restrict__ values) {
