@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(128, 4) k_p2_vertex_rows_general(int first, in
 template <int MODE>
 __global__ void __launch_bounds__(128, 12) k_p2_edge_rows(int first, int end, int n_edges, int row0, const int32_t* __restrict__ enb,
                                                        const uint32_t* __restrict__ eslots, const double* __restrict__ node_coords,
-                                                       const int32_t* __restrict__ outer, int pf_dist, P2Params P,
+                                                       const int32_t* __restrict__ outer, int pf_dist, int pfc_dist, P2Params P,
                                                        double* __restrict__ values) {
   // edge rows [first, end) of n_edges; edge e is matrix row row0 + e
   extern __shared__ double stage_all[];
@@ -449,6 +449,19 @@ __global__ void __launch_bounds__(128, 12) k_p2_edge_rows(int first, int end, in
       else if (lane < 20) a = reinterpret_cast<const char*>(eslots + ep) + (lane - 16) * 128;
       else a = reinterpret_cast<const char*>(outer + row0 + ep) + (lane - 20) * 128;
       prefetch_l2(a);
+    }
+    // opt-in (LFGPU_EDGE_PFC): the coordinates the CTA pfc_dist rows ahead will gather.  Its id lines were pulled into L2
+    // pf_dist - pfc_dist rows ago; lane l reads the four ids of every 4th edge of that CTA (neighbouring edges of a family
+    // share their coordinate lines) and pulls the lines they point to.
+    if (pfc_dist > 0) {
+      const int ec = first + blockIdx.x * blockDim.x + pfc_dist + 4 * lane;
+      if (ec < end) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int32_t id = __ldg(enb + static_cast<size_t>(k) * n_edges + ec);
+          if (id >= 0) prefetch_l2(node_coords + 2 * static_cast<size_t>(id));
+        }
+      }
     }
   }
   int32_t v0 = 0, v1 = 0;
@@ -611,6 +624,9 @@ int p2_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* 
   // L2 prefetch distance: about one wave of resident CTAs (6 per SM for the vertex rows, 12 for the edge rows)
   const int ipf_v = static_cast<int>((static_cast<int64_t>(ctx->sm_count) * 6 * threads * pfd_env / 100) & ~static_cast<int64_t>(127));
   const int ipf_e = static_cast<int>((static_cast<int64_t>(ctx->sm_count) * 12 * threads * pfd_env / 100) & ~static_cast<int64_t>(127));
+  // LFGPU_EDGE_PFC (percent of the plan distance, default 0 = off): coordinate prefetch of the edge rows through the plan
+  static const int pfc_env = [] { const char* e = std::getenv("LFGPU_EDGE_PFC"); return e != nullptr ? std::atoi(e) : 0; }();
+  const int ipc_e = pfc_env > 0 && ipf_e > 0 ? std::max(128, static_cast<int>((static_cast<int64_t>(ipf_e) * pfc_env / 100) & ~static_cast<int64_t>(127))) : 0;
   const size_t smem_v = sizeof(double) * (threads / 32) * 32 * (kVertexRowLen + 1);
   const size_t smem_e = sizeof(double) * (threads / 32) * 32 * (kEdgeRowLen + 1);
   // the share of the range in the vertex rows [0, nn) and in the edge rows [nn, nn + ne)
@@ -640,9 +656,9 @@ int p2_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* 
   if (e_end > e_first) {
     const unsigned ge = static_cast<unsigned>(cdiv(e_end - e_first, threads));
     if (simple)
-      k_p2_edge_rows<0><<<ge, threads, smem_e, ctx->stream>>>(e_first, e_end, ne, nn, p->p2e_nbr, p->p2e_slots, mesh->node_coords, p->outer, ipf_e, P, d_values);
+      k_p2_edge_rows<0><<<ge, threads, smem_e, ctx->stream>>>(e_first, e_end, ne, nn, p->p2e_nbr, p->p2e_slots, mesh->node_coords, p->outer, ipf_e, ipc_e, P, d_values);
     else
-      k_p2_edge_rows<1><<<ge, threads, smem_e, ctx->stream>>>(e_first, e_end, ne, nn, p->p2e_nbr, p->p2e_slots, mesh->node_coords, p->outer, ipf_e, P, d_values);
+      k_p2_edge_rows<1><<<ge, threads, smem_e, ctx->stream>>>(e_first, e_end, ne, nn, p->p2e_nbr, p->p2e_slots, mesh->node_coords, p->outer, ipf_e, ipc_e, P, d_values);
     LFGPU_LAUNCH_CHECK(ctx);
   }
   return LFGPU_OK;

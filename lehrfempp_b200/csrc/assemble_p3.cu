@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(128, 2) k_p3_vertex_rows_general(int first, in
 template <int MODE>
 __global__ void __launch_bounds__(128, 4) k_p3_edge_rows(int first, int end, int n_erows, int row0, const int32_t* __restrict__ enb,
                                                        const uint32_t* __restrict__ eslots, const double* __restrict__ node_coords,
-                                                       const int32_t* __restrict__ outer, int pf_dist, Params P,
+                                                       const int32_t* __restrict__ outer, int pf_dist, int pfc_dist, Params P,
                                                        double* __restrict__ values) {
   // edge-dof rows [first, end) of n_erows; row e of them is matrix row row0 + e
   extern __shared__ double stage_all[];
@@ -252,6 +252,17 @@ __global__ void __launch_bounds__(128, 4) k_p3_edge_rows(int first, int end, int
       else if (lane < 24) a = reinterpret_cast<const char*>(eslots + static_cast<size_t>((lane - 16) >> 2) * n_erows + ep) + (lane & 3) * 128;
       else a = reinterpret_cast<const char*>(outer + row0 + ep) + (lane - 24) * 128;
       prefetch_l2(a);
+    }
+    // opt-in (LFGPU_EDGE_PFC, see assemble_p2.cu): the coordinate lines the CTA pfc_dist rows ahead will gather, through its ids
+    if (pfc_dist > 0) {
+      const int ec = first + blockIdx.x * blockDim.x + pfc_dist + 4 * lane;
+      if (ec < end) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int32_t id = __ldg(enb + static_cast<size_t>(k) * n_erows + ec);
+          if (id >= 0) prefetch_l2(node_coords + 2 * static_cast<size_t>(id));
+        }
+      }
     }
   }
   int32_t v0 = 0, v1 = 0;
@@ -435,6 +446,8 @@ int p3_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* 
   static const int pfd_env = [] { const char* e = std::getenv("LFGPU_P3_PFD"); return e != nullptr ? std::atoi(e) : 100; }();
   const int ipf_v = static_cast<int>((static_cast<int64_t>(ctx->sm_count) * 3 * threads * pfd_env / 100) & ~static_cast<int64_t>(127));
   const int ipf_e = static_cast<int>((static_cast<int64_t>(ctx->sm_count) * 8 * threads * pfd_env / 100) & ~static_cast<int64_t>(127));
+  static const int pfc_env = [] { const char* e = std::getenv("LFGPU_EDGE_PFC"); return e != nullptr ? std::atoi(e) : 0; }();
+  const int ipc_e = pfc_env > 0 && ipf_e > 0 ? std::max(128, static_cast<int>((static_cast<int64_t>(ipf_e) * pfc_env / 100) & ~static_cast<int64_t>(127))) : 0;
   const size_t smem_v = sizeof(double) * (threads / 32) * 32 * (kVertexRowLen + 1);
   const size_t smem_e = sizeof(double) * (threads / 32) * 32 * (kEdgeRowLen + 1);
   const size_t smem_c = sizeof(double) * (threads / 32) * 32 * (kCellRowLen + 1);
@@ -460,7 +473,7 @@ int p3_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* 
   }                                                                                                                                       \
   if (e_end > e_first) {                                                                                                                  \
     k_p3_edge_rows<MODE><<<static_cast<unsigned>(cdiv(e_end - e_first, threads)), threads, smem_e, ctx->stream>>>(                        \
-        e_first, e_end, ner, nn, p->p3e_nbr, p->p3e_slots, mesh->node_coords, p->outer, ipf_e, P, d_values);                              \
+        e_first, e_end, ner, nn, p->p3e_nbr, p->p3e_slots, mesh->node_coords, p->outer, ipf_e, ipc_e, P, d_values);                       \
     LFGPU_LAUNCH_CHECK(ctx);                                                                                                              \
   }                                                                                                                                       \
   if (c_end > c_first) {                                                                                                                  \

@@ -34,3 +34,9 @@ done
 timeout 60 python tools/rows_probe.py 3 1448 > $out/r02_p3_rows_vs_items.json 2>/dev/null; cat $out/r02_p3_rows_vs_items.json
 timeout 60 python tools/rows_probe.py 2 2828 > $out/r02_p2_rows_vs_items.json 2>/dev/null; cat $out/r02_p2_rows_vs_items.json
 timeout 60 python tools/load_probe.py > $out/r02_load_probe.json 2>/dev/null; cat $out/r02_load_probe.json
+# 6. opt-in experiment: coordinate prefetch of the edge rows through the plan (LFGPU_EDGE_PFC = percent of the plan distance);
+#    rows_probe prints the row classes one by one ("parts"), so the effect on the edge kernels is visible directly
+for pfc in 0 25 50 100; do
+  LFGPU_EDGE_PFC=$pfc timeout 60 python tools/rows_probe.py 2 2828 rows > $out/r02_p2_rows_pfc$pfc.json 2>/dev/null; cat $out/r02_p2_rows_pfc$pfc.json
+  LFGPU_EDGE_PFC=$pfc timeout 60 python tools/rows_probe.py 3 1448 rows > $out/r02_p3_rows_pfc$pfc.json 2>/dev/null; cat $out/r02_p3_rows_pfc$pfc.json
+done

@@ -35,6 +35,24 @@ for name, algo in (("rows", lf.ALGO_FAN), ("items", lf.ALGO_GATHER)):
     res[name] = vals.to_host()
     alg_bytes = 4 * nldof * mesh.n_cells + 16 * mesh.n_nodes + 8 * pat.nnz
     out[name] = {"ms": ms, "cells_per_s": mesh.n_cells / ms * 1e3, "alg_GBs": alg_bytes / ms / 1e6}
+if only != "items" and degree >= 2:
+    # the row classes one by one through the row-range call: vertex rows, edge-dof rows, (P3) cell rows -- each range also
+    # runs the generic kernel on its irregular rows (boundary), so the parts add up to a little more than the full pass
+    n_rows = pat.download()[0].size - 1
+    nn = mesh.n_nodes
+    cuts = [0, nn, n_rows - mesh.n_cells, n_rows] if degree == 3 else [0, nn, n_rows]
+    parts = {}
+    for name, r0, r1 in zip(("vertex_rows", "edge_rows", "cell_rows"), cuts[:-1], cuts[1:]):
+        for _ in range(3):
+            pat.assemble_reaction_diffusion_range(degree, alpha, gamma, r0, r1 - r0, out=vals, algo=lf.ALGO_FAN)
+        e0, e1 = ctx.event(), ctx.event()
+        ctx.record(e0)
+        for _ in range(10):
+            pat.assemble_reaction_diffusion_range(degree, alpha, gamma, r0, r1 - r0, out=vals, algo=lf.ALGO_FAN)
+        ctx.record(e1)
+        parts[name] = {"rows": int(r1 - r0), "ms": ctx.elapsed_ms(e0, e1) / 10}
+    out["parts"] = parts
+    out["env"] = {k: v for k, v in os.environ.items() if k.startswith("LFGPU_")}
 if not only:
     out["rel_diff"] = float(np.abs(res["rows"] - res["items"]).max() / np.abs(res["items"]).max())
 print(json.dumps(out))
