@@ -117,8 +117,9 @@ __device__ __forceinline__ void write_rows(bool staged, bool regular, bool in_ra
   }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(128, 3) k_p3_vertex_rows(int first, int end, int n_rows, const int32_t* __restrict__ nbr,
+// MINB = 4 (opt-in, LFGPU_P3_VOCC=4; MODE 1 only): 128 registers instead of 168 -- a fourth CTA per SM for 328 bytes of spills
+template <int MODE, int MINB = 3>
+__global__ void __launch_bounds__(128, MINB) k_p3_vertex_rows(int first, int end, int n_rows, const int32_t* __restrict__ nbr,
                                                          const uint32_t* __restrict__ slots, const double* __restrict__ node_coords,
                                                          const int32_t* __restrict__ outer, int pf_dist, Params P,
                                                          double* __restrict__ values) {
@@ -446,6 +447,7 @@ int p3_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* 
   static const int pfd_env = [] { const char* e = std::getenv("LFGPU_P3_PFD"); return e != nullptr ? std::atoi(e) : 100; }();
   const int ipf_v = static_cast<int>((static_cast<int64_t>(ctx->sm_count) * 3 * threads * pfd_env / 100) & ~static_cast<int64_t>(127));
   const int ipf_e = static_cast<int>((static_cast<int64_t>(ctx->sm_count) * 8 * threads * pfd_env / 100) & ~static_cast<int64_t>(127));
+  static const int vocc_env = [] { const char* e = std::getenv("LFGPU_P3_VOCC"); return e != nullptr ? std::atoi(e) : 3; }();
   static const int pfc_env = [] { const char* e = std::getenv("LFGPU_EDGE_PFC"); return e != nullptr ? std::atoi(e) : 0; }();
   const int ipc_e = pfc_env > 0 && ipf_e > 0 ? std::max(128, static_cast<int>((static_cast<int64_t>(ipf_e) * pfc_env / 100) & ~static_cast<int64_t>(127))) : 0;
   const size_t smem_v = sizeof(double) * (threads / 32) * 32 * (kVertexRowLen + 1);
@@ -467,8 +469,12 @@ int p3_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* 
         v_first, v_end, nn, p->p3g_nbr, p->p3g_slots, mesh->node_coords, p->outer, P, d_values);                                          \
     LFGPU_LAUNCH_CHECK(ctx);                                                                                                              \
   } else if (v_end > v_first) {                                                                                                           \
-    k_p3_vertex_rows<MODE><<<static_cast<unsigned>(cdiv(v_end - v_first, threads)), threads, smem_v, ctx->stream>>>(                      \
-        v_first, v_end, nn, p->p3v_nbr, p->p3v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values);                                   \
+    if (MODE == 1 && vocc_env == 4)                                                                                                       \
+      k_p3_vertex_rows<1, 4><<<static_cast<unsigned>(cdiv(v_end - v_first, threads)), threads, smem_v, ctx->stream>>>(                    \
+          v_first, v_end, nn, p->p3v_nbr, p->p3v_slots, mesh->node_coords, p->outer, ipf_v * 4 / 3, P, d_values);                         \
+    else                                                                                                                                  \
+      k_p3_vertex_rows<MODE><<<static_cast<unsigned>(cdiv(v_end - v_first, threads)), threads, smem_v, ctx->stream>>>(                    \
+          v_first, v_end, nn, p->p3v_nbr, p->p3v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values);                                 \
     LFGPU_LAUNCH_CHECK(ctx);                                                                                                              \
   }                                                                                                                                       \
   if (e_end > e_first) {                                                                                                                  \

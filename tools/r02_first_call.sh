@@ -40,3 +40,6 @@ for pfc in 0 25 50 100; do
   LFGPU_EDGE_PFC=$pfc timeout 60 python tools/rows_probe.py 2 2828 rows > $out/r02_p2_rows_pfc$pfc.json 2>/dev/null; cat $out/r02_p2_rows_pfc$pfc.json
   LFGPU_EDGE_PFC=$pfc timeout 60 python tools/rows_probe.py 3 1448 rows > $out/r02_p3_rows_pfc$pfc.json 2>/dev/null; cat $out/r02_p3_rows_pfc$pfc.json
 done
+# 7. opt-in experiment: P3 vertex rows with stiffness + mass (MODE 1, config C4) at 128 registers / 4 CTAs per SM instead of 168 / 3
+#    (rel_diff against the item kernel in the same line: the variant is a different ptxas schedule of the same source)
+LFGPU_P3_VOCC=4 timeout 60 python tools/rows_probe.py 3 1448 > $out/r02_p3_rows_vocc4.json 2>/dev/null; cat $out/r02_p3_rows_vocc4.json
