@@ -43,3 +43,6 @@ done
 # 7. opt-in experiment: P3 vertex rows with stiffness + mass (MODE 1, config C4) at 128 registers / 4 CTAs per SM instead of 168 / 3
 #    (rel_diff against the item kernel in the same line: the variant is a different ptxas schedule of the same source)
 LFGPU_P3_VOCC=4 timeout 60 python tools/rows_probe.py 3 1448 > $out/r02_p3_rows_vocc4.json 2>/dev/null; cat $out/r02_p3_rows_vocc4.json
+# 8. config C2 (7.6 % of the roofline in round 1): P1 pass on triangle / quadrilateral / hybrid meshes x constant / per-cell /
+#    per-point coefficients x every algorithm -- separates the cost of the quadrature loop, the non-affine geometry and the mixed warps
+timeout 150 python tools/c2_probe.py > $out/r02_c2_probe.json 2>$out/c2_probe.err; cat $out/r02_c2_probe.json
