@@ -166,7 +166,7 @@ int build_fe_table(int degree, int cell_type, const lfgpu_quad* qr, FeTable* out
     if (err) *err = "degree must be 1..3 and cell_type 3 (tria) or 4 (quad)";
     return LFGPU_ERR_INVALID;
   }
-  std::memset(out, 0, sizeof(FeTable));
+  *out = FeTable{};
   out->nsf = nsf;
   double pts[2 * kMaxNq], wts[kMaxNq];
   int nq;
@@ -228,7 +228,7 @@ int build_segment_table(int degree, const lfgpu_quad* qr, SegTable* out, std::st
     if (err) *err = "degree must be 1, 2 or 3";
     return LFGPU_ERR_INVALID;
   }
-  std::memset(out, 0, sizeof(SegTable));
+  *out = SegTable{};
   const int p = degree;
   out->nsf = p + 1;
   if (qr != nullptr) {
