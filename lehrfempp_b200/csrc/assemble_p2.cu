@@ -290,10 +290,10 @@ __device__ __forceinline__ void write_rows(bool staged, bool regular, bool in_ra
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(128, 4) k_p2_vertex_rows(int first, int end, int n_rows, const int32_t* __restrict__ nbr,
+__global__ void __launch_bounds__(128, 4) k_p2_vertex_rows(int n_rows, const int32_t* __restrict__ nbr,
                                                          const uint32_t* __restrict__ slots, const double* __restrict__ node_coords,
                                                          const int32_t* __restrict__ outer, int pf_dist, P2Params P,
-                                                         double* __restrict__ values) {
+                                                         double* __restrict__ values, int first, int end) {
   // rows [first, end) of the n_rows vertex rows (the whole range, or one GPU's share of it)
   extern __shared__ double stage_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -432,10 +432,10 @@ __global__ void __launch_bounds__(128, 4) k_p2_vertex_rows_general(int first, in
 
 // 12 CTAs per SM = the occupancy of the measured kernel (40 registers; the row-range arguments had pushed ptxas to 46 -> 10 CTAs)
 template <int MODE>
-__global__ void __launch_bounds__(128, 12) k_p2_edge_rows(int first, int end, int n_edges, int row0, const int32_t* __restrict__ enb,
+__global__ void __launch_bounds__(128, 12) k_p2_edge_rows(int n_edges, int row0, const int32_t* __restrict__ enb,
                                                        const uint32_t* __restrict__ eslots, const double* __restrict__ node_coords,
                                                        const int32_t* __restrict__ outer, int pf_dist, int pfc_dist, P2Params P,
-                                                       double* __restrict__ values) {
+                                                       double* __restrict__ values, int first, int end) {
   // edge rows [first, end) of n_edges; edge e is matrix row row0 + e
   extern __shared__ double stage_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -648,17 +648,17 @@ int p2_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* 
   } else if (v_end > v_first) {
     const unsigned gv = static_cast<unsigned>(cdiv(v_end - v_first, threads));
     if (simple)
-      k_p2_vertex_rows<0><<<gv, threads, smem_v, ctx->stream>>>(v_first, v_end, nn, p->p2v_nbr, p->p2v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values);
+      k_p2_vertex_rows<0><<<gv, threads, smem_v, ctx->stream>>>(nn, p->p2v_nbr, p->p2v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values, v_first, v_end);
     else
-      k_p2_vertex_rows<1><<<gv, threads, smem_v, ctx->stream>>>(v_first, v_end, nn, p->p2v_nbr, p->p2v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values);
+      k_p2_vertex_rows<1><<<gv, threads, smem_v, ctx->stream>>>(nn, p->p2v_nbr, p->p2v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values, v_first, v_end);
     LFGPU_LAUNCH_CHECK(ctx);
   }
   if (e_end > e_first) {
     const unsigned ge = static_cast<unsigned>(cdiv(e_end - e_first, threads));
     if (simple)
-      k_p2_edge_rows<0><<<ge, threads, smem_e, ctx->stream>>>(e_first, e_end, ne, nn, p->p2e_nbr, p->p2e_slots, mesh->node_coords, p->outer, ipf_e, ipc_e, P, d_values);
+      k_p2_edge_rows<0><<<ge, threads, smem_e, ctx->stream>>>(ne, nn, p->p2e_nbr, p->p2e_slots, mesh->node_coords, p->outer, ipf_e, ipc_e, P, d_values, e_first, e_end);
     else
-      k_p2_edge_rows<1><<<ge, threads, smem_e, ctx->stream>>>(e_first, e_end, ne, nn, p->p2e_nbr, p->p2e_slots, mesh->node_coords, p->outer, ipf_e, ipc_e, P, d_values);
+      k_p2_edge_rows<1><<<ge, threads, smem_e, ctx->stream>>>(ne, nn, p->p2e_nbr, p->p2e_slots, mesh->node_coords, p->outer, ipf_e, ipc_e, P, d_values, e_first, e_end);
     LFGPU_LAUNCH_CHECK(ctx);
   }
   return LFGPU_OK;

@@ -117,12 +117,15 @@ __device__ __forceinline__ void write_rows(bool staged, bool regular, bool in_ra
   }
 }
 
-// MINB = 4 (opt-in, LFGPU_P3_VOCC=4; MODE 1 only): 128 registers instead of 168 -- a fourth CTA per SM for 328 bytes of spills
+// MINB = 4 (opt-in, LFGPU_P3_VOCC=4; MODE 1 only): 128 registers instead of 168 -- a fourth CTA per SM for 172 bytes of spills.
+// The row-range arguments come LAST in every row kernel: in front they moved `Params P` from a 16-byte to an 8-byte aligned
+// offset of the parameter space, and ptxas then spilled 52 bytes in this kernel (MODE 1, 168 registers = the cap of 3 CTAs per
+// SM) that the measured kernel did not spill.  With them at the end the layout up to `values` is the measured one.
 template <int MODE, int MINB = 3>
-__global__ void __launch_bounds__(128, MINB) k_p3_vertex_rows(int first, int end, int n_rows, const int32_t* __restrict__ nbr,
+__global__ void __launch_bounds__(128, MINB) k_p3_vertex_rows(int n_rows, const int32_t* __restrict__ nbr,
                                                          const uint32_t* __restrict__ slots, const double* __restrict__ node_coords,
                                                          const int32_t* __restrict__ outer, int pf_dist, Params P,
-                                                         double* __restrict__ values) {
+                                                         double* __restrict__ values, int first, int end) {
   // rows [first, end) of the n_rows vertex rows (the whole range, or one GPU's share of it)
   extern __shared__ double stage_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -236,10 +239,10 @@ __global__ void __launch_bounds__(128, 2) k_p3_vertex_rows_general(int first, in
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(128, 4) k_p3_edge_rows(int first, int end, int n_erows, int row0, const int32_t* __restrict__ enb,
+__global__ void __launch_bounds__(128, 4) k_p3_edge_rows(int n_erows, int row0, const int32_t* __restrict__ enb,
                                                        const uint32_t* __restrict__ eslots, const double* __restrict__ node_coords,
                                                        const int32_t* __restrict__ outer, int pf_dist, int pfc_dist, Params P,
-                                                       double* __restrict__ values) {
+                                                       double* __restrict__ values, int first, int end) {
   // edge-dof rows [first, end) of n_erows; row e of them is matrix row row0 + e
   extern __shared__ double stage_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -294,10 +297,10 @@ __global__ void __launch_bounds__(128, 4) k_p3_edge_rows(int first, int end, int
 
 // one thread per cell: row 9 of its element matrix; needs no plan (cell_nodes + the scatter-map row of list position 9)
 template <int MODE>
-__global__ void __launch_bounds__(128, 4) k_p3_cell_rows(int first, int end, int row0, int o_stride, int pos_row,
+__global__ void __launch_bounds__(128, 4) k_p3_cell_rows(int row0, int o_stride, int pos_row,
                                                        const uint32_t* __restrict__ cell_nodes, const uint8_t* __restrict__ pos,
                                                        const double* __restrict__ node_coords, const int32_t* __restrict__ outer, Params P,
-                                                       double* __restrict__ values) {
+                                                       double* __restrict__ values, int first, int end) {
   // cells [first, end); cell c is matrix row row0 + c
   extern __shared__ double stage_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -471,20 +474,20 @@ int p3_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* 
   } else if (v_end > v_first) {                                                                                                           \
     if (MODE == 1 && vocc_env == 4)                                                                                                       \
       k_p3_vertex_rows<1, 4><<<static_cast<unsigned>(cdiv(v_end - v_first, threads)), threads, smem_v, ctx->stream>>>(                    \
-          v_first, v_end, nn, p->p3v_nbr, p->p3v_slots, mesh->node_coords, p->outer, ipf_v * 4 / 3, P, d_values);                         \
+          nn, p->p3v_nbr, p->p3v_slots, mesh->node_coords, p->outer, ipf_v * 4 / 3, P, d_values, v_first, v_end);                         \
     else                                                                                                                                  \
       k_p3_vertex_rows<MODE><<<static_cast<unsigned>(cdiv(v_end - v_first, threads)), threads, smem_v, ctx->stream>>>(                    \
-          v_first, v_end, nn, p->p3v_nbr, p->p3v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values);                                 \
+          nn, p->p3v_nbr, p->p3v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values, v_first, v_end);                                 \
     LFGPU_LAUNCH_CHECK(ctx);                                                                                                              \
   }                                                                                                                                       \
   if (e_end > e_first) {                                                                                                                  \
     k_p3_edge_rows<MODE><<<static_cast<unsigned>(cdiv(e_end - e_first, threads)), threads, smem_e, ctx->stream>>>(                        \
-        e_first, e_end, ner, nn, p->p3e_nbr, p->p3e_slots, mesh->node_coords, p->outer, ipf_e, ipc_e, P, d_values);                       \
+        ner, nn, p->p3e_nbr, p->p3e_slots, mesh->node_coords, p->outer, ipf_e, ipc_e, P, d_values, e_first, e_end);                       \
     LFGPU_LAUNCH_CHECK(ctx);                                                                                                              \
   }                                                                                                                                       \
   if (c_end > c_first) {                                                                                                                  \
     k_p3_cell_rows<MODE><<<static_cast<unsigned>(cdiv(c_end - c_first, threads)), threads, smem_c, ctx->stream>>>(                        \
-        c_first, c_end, base_int, p->o_stride, p->pos_row, mesh->cell_nodes, pos, mesh->node_coords, p->outer, P, d_values);              \
+        base_int, p->o_stride, p->pos_row, mesh->cell_nodes, pos, mesh->node_coords, p->outer, P, d_values, c_first, c_end);              \
     LFGPU_LAUNCH_CHECK(ctx);                                                                                                              \
   }
   if (simple) {
