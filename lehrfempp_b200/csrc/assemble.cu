@@ -492,8 +492,11 @@ __global__ void __launch_bounds__(256) k_cell_metric(MeshView mv, int64_t n_cell
 // rounds: round k adds the k-th item of every dof (at most one item per dof and round -> plain read-modify-write, no
 // atomics; ascending cell order per entry = the reference's summation order, bitwise repeatable).  The image is laid
 // out exactly like the output and leaves as one coalesced copy.
-template <int NSF, typename P, bool TENSOR_ONLY>
-__global__ void __launch_bounds__(kItemThreads, TENSOR_ONLY ? (NSF <= 6 ? 6 : 5) : 4) k_assemble_items(Tables hdr, const double* __restrict__ blob, int table_mask, MeshView mv,
+// MINB > 0 (opt-in, LFGPU_ITEMS_OCC=3; P1 quadrature route only = config C2): 3 CTAs per SM instead of 4 -- 80 registers and
+// 12 bytes of spill stores instead of 64 registers and 80 (the ncu capture shows the kernel bound by LSU work per item, and
+// spill traffic is LSU work); not yet measured
+template <int NSF, typename P, bool TENSOR_ONLY, int MINB = 0>
+__global__ void __launch_bounds__(kItemThreads, MINB > 0 ? MINB : (TENSOR_ONLY ? (NSF <= 6 ? 6 : 5) : 4)) k_assemble_items(Tables hdr, const double* __restrict__ blob, int table_mask, MeshView mv,
                                                            const int4* __restrict__ blk_hdr, int pos_row, const P* __restrict__ pos_item,
                                                            const uint2* __restrict__ item_sorted, DevCoeff alpha, DevCoeff gamma,
                                                            const uint8_t* __restrict__ active, bool transpose_alpha, double beta,
@@ -816,6 +819,10 @@ int launch_matrix(lfgpu_ctx* ctx, const HostTables& ht, const double* d_blob, co
       const size_t smem_i = tab_bytes + sizeof(double) * static_cast<size_t>((p->max_item_block_nnz + 15) & ~15);
       if (smem_i <= 200 * 1024) {
         auto ki = tensor_only ? k_assemble_items<NSF, P, true> : k_assemble_items<NSF, P, false>;
+        if constexpr (NSF <= 4) {
+          static const bool occ3_env = [] { const char* e = std::getenv("LFGPU_ITEMS_OCC"); return e != nullptr && e[0] == '3'; }();
+          if (occ3_env && !tensor_only) ki = k_assemble_items<NSF, P, false, 3>;
+        }
         LFGPU_CUDA_CHECK(ctx, cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_i)));
         const double* metric = nullptr;
         if (tensor_only && NSF > 3) {

@@ -46,3 +46,5 @@ LFGPU_P3_VOCC=4 timeout 60 python tools/rows_probe.py 3 1448 > $out/r02_p3_rows_
 # 8. config C2 (7.6 % of the roofline in round 1): P1 pass on triangle / quadrilateral / hybrid meshes x constant / per-cell /
 #    per-point coefficients x every algorithm -- separates the cost of the quadrature loop, the non-affine geometry and the mixed warps
 timeout 150 python tools/c2_probe.py > $out/r02_c2_probe.json 2>$out/c2_probe.err; cat $out/r02_c2_probe.json
+# 8b. opt-in experiment: item kernel of the P1 quadrature route at 3 CTAs per SM (80 registers, 12 B of spills instead of 64 / 80 B)
+LFGPU_ITEMS_OCC=3 timeout 150 python tools/c2_probe.py > $out/r02_c2_probe_occ3.json 2>>$out/c2_probe.err; cat $out/r02_c2_probe_occ3.json
