@@ -961,6 +961,35 @@ int lfgpu::assemble_rd_impl(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_
       }
       return p1_fan_launch(ctx, mesh, p, a, tensor, dg.c[0], wsum, m_diag, m_off, beta, d_row_list, n_rows, d_values, row0);
     }
+    // P1 row kernel (assemble_p1h.cu): quadrilaterals / hybrid meshes, coefficients per cell or per quadrature point, activity
+    // masks, cell corners that are not bitwise the node positions; rules invariant under the rotations of the reference cell
+    static const bool p1h_env = [] { const char* e = std::getenv("LFGPU_P1_ROWS"); return e == nullptr || e[0] != '0'; }();
+    if (degree == 1 && fan_query == nullptr && p1h_env) {
+      FeTable ft, fq;
+      std::string err;
+      const bool dflt = qr_tria == nullptr && qr_quad == nullptr;
+      const bool have_t = mesh->n_tria > 0, have_q = mesh->n_quad > 0;
+      bool okh = true;
+      if (have_t) okh = okh && (dflt || qr_tria != nullptr) && build_fe_table(1, 3, qr_tria, &ft, &err) == LFGPU_OK;
+      if (have_q) okh = okh && (dflt || qr_quad != nullptr) && build_fe_table(1, 4, qr_quad, &fq, &err) == LFGPU_OK;
+      okh = okh && p1h_rules_ok(have_t ? &ft : nullptr, have_q ? &fq : nullptr);
+      if (okh) {
+        if ((rc = p1h_prepare(ctx, mesh, const_cast<lfgpu_pattern*>(p))) != LFGPU_OK) return rc;
+        okh = p->p1h_state == 1 && (d_row_list == nullptr || p->n_p1h_irregular == 0);
+      }
+      if (okh) {
+        const int64_t r0 = row0 >= 0 ? row0 : 0, r1 = row0 >= 0 ? row0 + n_rows : p->n_outer;
+        const auto& irr = p->p1h_irregular_host;
+        const int64_t i0 = std::lower_bound(irr.begin(), irr.end(), r0) - irr.begin(), i1 = std::lower_bound(irr.begin(), irr.end(), r1) - irr.begin();
+        if (i1 > i0) {
+          rc = lfgpu_assemble_reaction_diffusion_rows(ctx, mesh, p, degree, qr_tria, qr_quad, alpha, gamma, active, beta, d_values,
+                                                      LFGPU_ALGO_GATHER, p->p1h_irregular + i0, i1 - i0);
+          if (rc != LFGPU_OK) return rc;
+        }
+        return p1h_launch(ctx, mesh, p, have_t ? &ft : nullptr, have_q ? &fq : nullptr, alpha, gamma, active, beta, d_row_list, n_rows, row0,
+                          d_values);
+      }
+    }
     // P2 row kernels (assemble_p2.cu): triangles, constant coefficients, the provider's default rule (exact for P2, hence
     // independent of the local vertex numbering), every cell active, all rows, overwrite.  LFGPU_ALGO_FAN asks for them
     // explicitly; LFGPU_ALGO_AUTO takes them unless LFGPU_P2_ROWS=0.

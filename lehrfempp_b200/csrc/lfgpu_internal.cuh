@@ -117,6 +117,15 @@ struct lfgpu_pattern {
   uint32_t* fan_info32 = nullptr;    // [n_outer] 4 bits slot-in-row per ring position | diagonal slot << 24 | closed << 28
   int32_t* fan_irregular = nullptr;  // rows that are not a single fan (generic kernel)
   int64_t n_irregular = 0;
+  // P1 row-kernel plan for hybrid meshes / variable coefficients (assemble_p1h.cu), built on first use
+  int p1h_state = 0;
+  int p1h_kq = 0, p1h_kt = 0;        // quadrilateral / triangle item slots per row
+  uint32_t* p1h_qw = nullptr;        // [4 * kq][n_outer] cell | rot << 28, then three corners node | slot << 28
+  uint32_t* p1h_tw = nullptr;        // [3 * kt][n_outer]
+  uint8_t* p1h_rowinfo = nullptr;    // [n_outer] slot of the diagonal; 0xFF = generic kernel, 0xFE = no cells
+  int32_t* p1h_irregular = nullptr;
+  int64_t n_p1h_irregular = 0;
+  std::vector<int32_t> p1h_irregular_host;
   // P2 row-kernel plan (assemble_p2.cu), built on first use: 0 = not tried, 1 = ready, -1 = not applicable
   int p2_state = 0;
   int64_t p2_nn = 0;                 // number of vertex rows (= mesh nodes); the edge rows follow
@@ -226,6 +235,13 @@ int p1_fan_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p);
 int p1_fan_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, const double alpha[4], int tensor, double gamma,
                   double wsum, double m_diag, double m_off, double beta, const int32_t* row_list, int64_t n_rows, double* d_values,
                   int64_t row0 = -1);
+// P1 row kernel for quadrilaterals / hybrid meshes / variable coefficients / activity masks (assemble_p1h.cu);
+// tt / tq: tables of the rules in use (null = cell type absent from the mesh)
+int p1h_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p);
+bool p1h_rules_ok(const FeTable* tt, const FeTable* tq);
+int p1h_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, const FeTable* tt, const FeTable* tq, const lfgpu_coeff* alpha,
+               const lfgpu_coeff* gamma, const uint8_t* active, double beta, const int32_t* row_list, int64_t n_rows, int64_t row0,
+               double* d_values);
 // P2 row kernels (assemble_p2.cu): k00 .. km = reference tensors of FeLagrangeO2Tria, [6 * 6] row-major each
 int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p);
 int p2_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, const double alpha[4], int tensor, double gamma,

@@ -244,6 +244,10 @@ void lfgpu_pattern_destroy(lfgpu_pattern* p) {
   cudaFree(p->fan_nbr16);
   cudaFree(p->fan_info32);
   cudaFree(p->fan_irregular);
+  cudaFree(p->p1h_qw);
+  cudaFree(p->p1h_tw);
+  cudaFree(p->p1h_rowinfo);
+  cudaFree(p->p1h_irregular);
   cudaFree(p->p2v_nbr);
   cudaFree(p->p2v_slots);
   cudaFree(p->p2e_nbr);
