@@ -152,20 +152,34 @@ __device__ __forceinline__ double rcp_fast(double x) {
 __device__ __forceinline__ void prefetch_l2(const void* a) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a)); }
 __device__ __forceinline__ int swz(int k) { return k ^ ((k >> 4) & 15); }
 
+// Coefficient kinds as compile-time facts where it pays (ncu / SASS of the first version: the run-time kind switches cost
+// predicated-off loads, branches and ~230 register moves per row): MODE 0 reads the kinds from the parameter block (any
+// combination), MODE 1 = alpha and gamma per quadrature point from 32-byte aligned tables of stride 4 and equal triangle
+// weights (config C2), MODE 2 = both constant.
+template <int MODE>
+struct Kinds {
+  static __device__ __forceinline__ int a(const P1HParams& P) { return MODE == 1 ? LFGPU_COEFF_PER_QP : (MODE == 2 ? LFGPU_COEFF_CONST : P.alpha.kind); }
+  static __device__ __forceinline__ int g(const P1HParams& P) { return MODE == 1 ? LFGPU_COEFF_PER_QP : (MODE == 2 ? LFGPU_COEFF_CONST : P.gamma.kind); }
+  static __device__ __forceinline__ bool avec(const P1HParams& P) { return MODE == 1 ? true : P.alpha.vec != 0; }
+  static __device__ __forceinline__ bool gvec(const P1HParams& P) { return MODE == 1 ? true : P.gamma.vec != 0; }
+  static __device__ __forceinline__ bool mass(const P1HParams& P) { return MODE == 1 ? true : P.has_mass != 0; }
+  static __device__ __forceinline__ bool tri_eqw(const P1HParams& P) { return MODE == 1 ? true : false; }
+};
+
 // Per-cell coefficient data is GATHERED by the row-owner threads, and a gather costs one L1 wavefront per distinct line whatever
 // its width: the values of all points of a cell come with ONE 256-bit load per coefficient (tables of stride 4), in the cell's
 // own point numbering; the rotation is applied afterwards by register selects.
 struct Raw4 {
   double v0, v1, v2, v3;
 };
-__device__ __forceinline__ Raw4 coeff_issue(const RowCoeff& C, uint32_t cell, bool four) {
+__device__ __forceinline__ Raw4 coeff_issue(const RowCoeff& C, int kind, bool vec, uint32_t cell, bool four) {
   Raw4 r;
-  if (C.kind <= LFGPU_COEFF_PER_CELL) {
-    r.v0 = C.kind == LFGPU_COEFF_CONST ? C.c[0] : __ldg(C.data + cell);
+  if (kind <= LFGPU_COEFF_PER_CELL) {
+    r.v0 = kind == LFGPU_COEFF_CONST ? C.c[0] : __ldg(C.data + cell);
     r.v1 = r.v2 = r.v3 = r.v0;
-  } else if (C.kind == LFGPU_COEFF_PER_QP) {
+  } else if (kind == LFGPU_COEFF_PER_QP) {
     const double* base = C.data + static_cast<long long>(cell) * C.stride;
-    if (C.vec) {
+    if (vec) {
       asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.v0), "=d"(r.v1), "=d"(r.v2), "=d"(r.v3) : "l"(base));
     } else {
       r.v0 = __ldg(base); r.v1 = __ldg(base + 1); r.v2 = __ldg(base + 2);
@@ -181,8 +195,8 @@ __device__ __forceinline__ double pick4(int k, const Raw4& r) {
   return (k & 2) ? hi : lo;
 }
 template <int NQ>
-__device__ __forceinline__ void coeff_points(const RowCoeff& C, const Raw4& r, const int (&kk)[NQ], double (&out)[NQ]) {
-  if (C.kind != LFGPU_COEFF_PER_QP) {
+__device__ __forceinline__ void coeff_points(int kind, const Raw4& r, const int (&kk)[NQ], double (&out)[NQ]) {
+  if (kind != LFGPU_COEFF_PER_QP) {
 #pragma unroll
     for (int k = 0; k < NQ; ++k) out[k] = r.v0;
   } else {
@@ -206,7 +220,7 @@ __device__ __forceinline__ void coeff_tensor(const RowCoeff& C, uint32_t cell, i
 }
 
 // row 0 of the element matrix of the triangle (p0, p1, p2), a = p1 - p0, b = p2 - p0: e0 (diagonal), e1, e2
-template <bool TENSOR>
+template <bool TENSOR, int MODE>
 __device__ __forceinline__ void tri_row(const P1HParams& P, uint32_t cell, int rot, const Raw4& ra, const Raw4& rg, double ax, double ay,
                                         double bx, double by, double& e0, double& e1, double& e2) {
   const double det = ax * by - ay * bx;
@@ -215,13 +229,17 @@ __device__ __forceinline__ void tri_row(const P1HParams& P, uint32_t cell, int r
   const int k0 = (P.perm_t >> (8 * rot)) & 3, k1 = (P.perm_t >> (8 * rot + 2)) & 3, k2 = (P.perm_t >> (8 * rot + 4)) & 3;
   const int kk[3] = {k0, k1, k2};
   if (!TENSOR) {
-    // grad phi_b constant on the cell: sum_k w_k alpha_k |det| G_0 . G_b = (sum_k w_k alpha_k) / |det| * (N^T g_0) . (N^T g_b);
-    // the weighted sum runs over all points, so the rotation does not matter when the weights are equal -- they need not be
-    double al[3];
-    coeff_points<3>(P.alpha, ra, kk, al);
-    double abar = P.wt[0] * al[0];
-    abar = fma(P.wt[1], al[1], abar);
-    abar = fma(P.wt[2], al[2], abar);
+    // grad phi_b constant on the cell: sum_k w_k alpha_k |det| G_0 . G_b = (sum_k w_k alpha_k) / |det| * (N^T g_0) . (N^T g_b)
+    double abar;
+    if (Kinds<MODE>::tri_eqw(P)) {
+      abar = P.wt[0] * ((ra.v0 + ra.v1) + ra.v2);  // equal weights: the sum over the points does not see the rotation
+    } else {
+      double al[3];
+      coeff_points<3>(Kinds<MODE>::a(P), ra, kk, al);
+      abar = P.wt[0] * al[0];
+      abar = fma(P.wt[1], al[1], abar);
+      abar = fma(P.wt[2], al[2], abar);
+    }
     const double aa = ax * ax + ay * ay, bb = bx * bx + by * by, ab = ax * bx + ay * by;
     const double s = abar * ridet;
     e1 = s * (ab - bb);
@@ -250,9 +268,9 @@ __device__ __forceinline__ void tri_row(const P1HParams& P, uint32_t cell, int r
     e2 = vy * ridet;
     e0 = -(e1 + e2);
   }
-  if (P.has_mass) {
+  if (Kinds<MODE>::mass(P)) {
     double gv[3];
-    coeff_points<3>(P.gamma, rg, kk, gv);
+    coeff_points<3>(Kinds<MODE>::g(P), rg, kk, gv);
     const double g0 = adet * gv[0], g1 = adet * gv[1], g2 = adet * gv[2];
     e0 = fma(P.ct[0][0], g0, e0); e0 = fma(P.ct[0][1], g1, e0); e0 = fma(P.ct[0][2], g2, e0);
     e1 = fma(P.ct[1][0], g0, e1); e1 = fma(P.ct[1][1], g1, e1); e1 = fma(P.ct[1][2], g2, e1);
@@ -260,64 +278,76 @@ __device__ __forceinline__ void tri_row(const P1HParams& P, uint32_t cell, int r
   }
 }
 
-// row 0 of the element matrix of the quadrilateral (p0, p1, p2, p3) given e0v = p1 - p0, e1v = p3 - p0, d = p2 - p3 - e0v:
-// J(xhat) = [e0v + d xhat_1, e1v + d xhat_0]  (quad_o1.cc:114-117)
-template <bool TENSOR>
-__device__ __forceinline__ void quad_row(const P1HParams& P, uint32_t cell, int rot, const Raw4& ra, const Raw4& rg, double e0x, double e0y,
-                                         double e1x, double e1y, double dx, double dy, double& r0, double& r1, double& r2, double& r3) {
-  r0 = r1 = r2 = r3 = 0.0;
-  const uint32_t pq = P.perm_q >> (8 * rot);
-  const int kq[4] = {static_cast<int>(pq & 3), static_cast<int>((pq >> 2) & 3), static_cast<int>((pq >> 4) & 3), static_cast<int>((pq >> 6) & 3)};
-  double al[4], gv[4];
-  coeff_points<4>(P.alpha, ra, kq, al);
-  coeff_points<4>(P.gamma, rg, kq, gv);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const double c0x = fma(dx, P.qy[k], e0x), c0y = fma(dy, P.qy[k], e0y);
-    const double c1x = fma(dx, P.qx[k], e1x), c1y = fma(dy, P.qx[k], e1y);
-    const double det = c0x * c1y - c0y * c1x;
-    const double adet = fabs(det);
-    const double ridet = rcp_fast(adet);
-    // u = N^T ghat_0, N = adj(J) = [c1y -c1x; -c0y c0x]
-    const double ux = c1y * P.gx[0][k] - c0y * P.gy[0][k];
-    const double uy = c0x * P.gy[0][k] - c1x * P.gx[0][k];
-    double tx, ty;
-    if (!TENSOR) {
-      const double s = P.wq[k] * al[k] * ridet;
-      tx = s * ux;
-      ty = s * uy;
-    } else {
-      double a00, a01, a10, a11;
-      coeff_tensor(P.alpha, cell, kq[k], P.transpose != 0, a00, a01, a10, a11);
-      const double s = P.wq[k] * ridet;
-      tx = s * (a00 * ux + a01 * uy);
-      ty = s * (a10 * ux + a11 * uy);
-    }
-    const double vx = c1y * tx - c1x * ty, vy = c0x * ty - c0y * tx;
-    r0 = fma(vx, P.gx[0][k], r0); r0 = fma(vy, P.gy[0][k], r0);
-    r1 = fma(vx, P.gx[1][k], r1); r1 = fma(vy, P.gy[1][k], r1);
-    r2 = fma(vx, P.gx[2][k], r2); r2 = fma(vy, P.gy[2][k], r2);
-    r3 = fma(vx, P.gx[3][k], r3); r3 = fma(vy, P.gy[3][k], r3);
-    if (P.has_mass) {
-      const double mm = P.wq[k] * adet * gv[k] * P.ph[0][k];
-      r0 = fma(mm, P.ph[0][k], r0);
-      r1 = fma(mm, P.ph[1][k], r1);
-      r2 = fma(mm, P.ph[2][k], r2);
-      r3 = fma(mm, P.ph[3][k], r3);
-    }
-  }
-}
-
-// everything one cell of the row needs, loaded DEPTH items ahead of its use (ncu on the first version: 16 warps per SM, each
-// waiting on plan word -> coordinates / coefficients -> arithmetic per cell in turn; long-scoreboard stalls 8 per issue)
+// everything one cell of the row needs, loaded ahead of its use (ncu on the first version: 16 warps per SM, each waiting on
+// plan word -> coordinates / coefficients -> arithmetic per cell in turn; long-scoreboard stalls 8 per issue)
 struct ItemData {
   double2 p0, p1, p2, p3;
   Raw4 ra, rg;
   uint32_t cell;
-  uint32_t meta;  // rot | slot_1 << 4 | slot_2 << 8 | slot_3 << 12 | valid << 16
+  uint32_t meta;  // rot | slot_1 << 4 | slot_2 << 8 | slot_3 << 12 | on << 16
 };
 
-template <bool QUAD, bool CC>
+// row 0 of the element matrices of NB quadrilaterals (p0, p1, p2, p3) at once -- the NB cells share every table operand
+// of a quadrature point while it sits in a uniform register, and their dependency chains interleave.
+// With e0v = p1 - p0, e1v = p3 - p0, d = p2 - p3 - e0v:  J(xhat) = [e0v + d xhat_1, e1v + d xhat_0]  (quad_o1.cc:114-117)
+template <int NB, bool TENSOR, bool CC, int MODE>
+__device__ __forceinline__ void quad_rows(const P1HParams& P, const ItemData* d, double2 xi, double (&r0)[NB], double (&r1)[NB], double (&r2)[NB],
+                                          double (&r3)[NB]) {
+  double e0x[NB], e0y[NB], e1x[NB], e1y[NB], dx[NB], dy[NB], al[NB][4], gv[NB][4];
+  int kq[NB][4];
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    const double2 p0 = CC ? d[q].p0 : xi;
+    e0x[q] = d[q].p1.x - p0.x; e0y[q] = d[q].p1.y - p0.y; e1x[q] = d[q].p3.x - p0.x; e1y[q] = d[q].p3.y - p0.y;
+    dx[q] = (d[q].p2.x - d[q].p3.x) - e0x[q]; dy[q] = (d[q].p2.y - d[q].p3.y) - e0y[q];
+    const uint32_t pq = P.perm_q >> (8 * (d[q].meta & 15U));
+    kq[q][0] = static_cast<int>(pq & 3); kq[q][1] = static_cast<int>((pq >> 2) & 3); kq[q][2] = static_cast<int>((pq >> 4) & 3);
+    kq[q][3] = static_cast<int>((pq >> 6) & 3);
+    coeff_points<4>(Kinds<MODE>::a(P), d[q].ra, kq[q], al[q]);
+    coeff_points<4>(Kinds<MODE>::g(P), d[q].rg, kq[q], gv[q]);
+    r0[q] = r1[q] = r2[q] = r3[q] = 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      const double c0x = fma(dx[q], P.qy[k], e0x[q]), c0y = fma(dy[q], P.qy[k], e0y[q]);
+      const double c1x = fma(dx[q], P.qx[k], e1x[q]), c1y = fma(dy[q], P.qx[k], e1y[q]);
+      const double det = c0x * c1y - c0y * c1x;
+      const double adet = fabs(det);
+      const double ridet = rcp_fast(adet);
+      // u = N^T ghat_0, N = adj(J) = [c1y -c1x; -c0y c0x]
+      const double ux = c1y * P.gx[0][k] - c0y * P.gy[0][k];
+      const double uy = c0x * P.gy[0][k] - c1x * P.gx[0][k];
+      double tx, ty;
+      if (!TENSOR) {
+        const double s = P.wq[k] * al[q][k] * ridet;
+        tx = s * ux;
+        ty = s * uy;
+      } else {
+        double a00, a01, a10, a11;
+        coeff_tensor(P.alpha, d[q].cell, kq[q][k], P.transpose != 0, a00, a01, a10, a11);
+        const double s = P.wq[k] * ridet;
+        tx = s * (a00 * ux + a01 * uy);
+        ty = s * (a10 * ux + a11 * uy);
+      }
+      const double vx = c1y * tx - c1x * ty, vy = c0x * ty - c0y * tx;
+      r0[q] = fma(vx, P.gx[0][k], r0[q]); r0[q] = fma(vy, P.gy[0][k], r0[q]);
+      r1[q] = fma(vx, P.gx[1][k], r1[q]); r1[q] = fma(vy, P.gy[1][k], r1[q]);
+      r2[q] = fma(vx, P.gx[2][k], r2[q]); r2[q] = fma(vy, P.gy[2][k], r2[q]);
+      r3[q] = fma(vx, P.gx[3][k], r3[q]); r3[q] = fma(vy, P.gy[3][k], r3[q]);
+      if (Kinds<MODE>::mass(P)) {
+        const double mm = P.wq[k] * adet * gv[q][k] * P.ph[0][k];
+        r0[q] = fma(mm, P.ph[0][k], r0[q]);
+        r1[q] = fma(mm, P.ph[1][k], r1[q]);
+        r2[q] = fma(mm, P.ph[2][k], r2[q]);
+        r3[q] = fma(mm, P.ph[3][k], r3[q]);
+      }
+    }
+  }
+}
+
+template <bool QUAD, bool CC, int MODE>
 __device__ __forceinline__ void item_issue(ItemData& d, const P1HParams& P, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, int32_t r,
                                            const double2* __restrict__ nc, const double2* __restrict__ cc, const uint8_t* __restrict__ active) {
   const bool valid = w0 != kNil;
@@ -340,48 +370,62 @@ __device__ __forceinline__ void item_issue(ItemData& d, const P1HParams& P, uint
     d.p2 = __ldg(nc + (valid ? (w2 & 0x0fffffffU) : static_cast<uint32_t>(r)));
     if (QUAD) d.p3 = __ldg(nc + (valid ? (w3 & 0x0fffffffU) : static_cast<uint32_t>(r)));
   }
-  d.ra = coeff_issue(P.alpha, cell, QUAD);
-  d.rg = coeff_issue(P.gamma, cell, QUAD);
+  d.ra = coeff_issue(P.alpha, Kinds<MODE>::a(P), Kinds<MODE>::avec(P), cell, QUAD);
+  d.rg = coeff_issue(P.gamma, Kinds<MODE>::g(P), Kinds<MODE>::gvec(P), cell, QUAD);
 }
 
-template <bool QUAD, bool TENSOR, bool CC>
-__device__ __forceinline__ void item_consume(const ItemData& d, const P1HParams& P, double2 xi, double* __restrict__ stage, int off, double& diag) {
-  const bool on = (d.meta >> 16) != 0;
-  if (!__any_sync(0xffffffffU, on)) return;  // a slot no row of the warp uses
-  const int rot = static_cast<int>(d.meta & 15U);
-  const double2 p0 = CC ? d.p0 : xi;
+__device__ __forceinline__ void stage_add(double* __restrict__ stage, int off, uint32_t meta, int shift, double v) {
+  stage[swz(off + static_cast<int>((meta >> shift) & 15U))] += v;
+}
+
+// NB cells of one kind at once (quadrilaterals in pairs, triangles singly)
+template <bool QUAD, int NB, bool TENSOR, bool CC, int MODE>
+__device__ __forceinline__ void group_consume(const ItemData* d, const P1HParams& P, double2 xi, double* __restrict__ stage, int off, double& diag) {
+  bool any = false;
+#pragma unroll
+  for (int q = 0; q < NB; ++q) any = any || (d[q].meta >> 16) != 0;
+  if (!__any_sync(0xffffffffU, any)) return;  // slots no row of the warp uses
   if (QUAD) {
-    const double e0x = d.p1.x - p0.x, e0y = d.p1.y - p0.y, e1x = d.p3.x - p0.x, e1y = d.p3.y - p0.y;
-    const double dx = (d.p2.x - d.p3.x) - e0x, dy = (d.p2.y - d.p3.y) - e0y;
-    double r0, r1, r2, r3;
-    quad_row<TENSOR>(P, d.cell, rot, d.ra, d.rg, e0x, e0y, e1x, e1y, dx, dy, r0, r1, r2, r3);
-    if (on) {
-      diag += r0;
-      stage[swz(off + static_cast<int>((d.meta >> 4) & 15U))] += r1;
-      stage[swz(off + static_cast<int>((d.meta >> 8) & 15U))] += r2;
-      stage[swz(off + static_cast<int>((d.meta >> 12) & 15U))] += r3;
+    double r0[NB], r1[NB], r2[NB], r3[NB];
+    quad_rows<NB, TENSOR, CC, MODE>(P, d, xi, r0, r1, r2, r3);
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      if ((d[q].meta >> 16) != 0) {
+        diag += r0[q];
+        stage_add(stage, off, d[q].meta, 4, r1[q]);
+        stage_add(stage, off, d[q].meta, 8, r2[q]);
+        stage_add(stage, off, d[q].meta, 12, r3[q]);
+      }
     }
   } else {
-    double e0, e1, e2;
-    tri_row<TENSOR>(P, d.cell, rot, d.ra, d.rg, d.p1.x - p0.x, d.p1.y - p0.y, d.p2.x - p0.x, d.p2.y - p0.y, e0, e1, e2);
-    if (on) {
-      diag += e0;
-      stage[swz(off + static_cast<int>((d.meta >> 4) & 15U))] += e1;
-      stage[swz(off + static_cast<int>((d.meta >> 8) & 15U))] += e2;
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      const double2 p0 = CC ? d[q].p0 : xi;
+      double e0, e1, e2;
+      tri_row<TENSOR, MODE>(P, d[q].cell, static_cast<int>(d[q].meta & 15U), d[q].ra, d[q].rg, d[q].p1.x - p0.x, d[q].p1.y - p0.y,
+                            d[q].p2.x - p0.x, d[q].p2.y - p0.y, e0, e1, e2);
+      if ((d[q].meta >> 16) != 0) {
+        diag += e0;
+        stage_add(stage, off, d[q].meta, 4, e1);
+        stage_add(stage, off, d[q].meta, 8, e2);
+      }
     }
   }
 }
 
-// CC: cell corners come from the mesh's cell_coords array (cells whose geometry is not bitwise the node positions)
-template <int KQ, int KT, bool TENSOR, bool CC, int DEPTH>
-__global__ void __launch_bounds__(128, 4) k_assemble_p1_rows(int n_rows, int n_total_rows, const uint32_t* __restrict__ qw,
+// CC: cell corners come from the mesh's cell_coords array (cells whose geometry is not bitwise the node positions).
+// The cells of a row are processed in groups -- KQ / 2 pairs of quadrilaterals, then KT triangles -- and the loads of group
+// g + DEPTH are issued before group g is computed.
+template <int KQ, int KT, bool TENSOR, bool CC, int DEPTH, int MODE>
+__global__ void __launch_bounds__(128, KQ == 4 ? 3 : 4) k_assemble_p1_rows(int n_rows, int n_total_rows, const uint32_t* __restrict__ qw,
                                                              const uint32_t* __restrict__ tw, const uint8_t* __restrict__ rowinfo,
                                                              const double* __restrict__ node_coords, const double* __restrict__ cell_coords,
                                                              const int32_t* __restrict__ outer, const uint8_t* __restrict__ active,
                                                              const int32_t* __restrict__ row_list, int row0, int pf_dist,
                                                              const __grid_constant__ P1HParams P, double* __restrict__ values) {
   extern __shared__ double stage_all[];
-  constexpr int NI = KQ + KT;
+  static_assert(KQ % 2 == 0, "quadrilaterals are processed in pairs");
+  constexpr int NI = KQ + KT, NG = KQ / 2 + KT;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = t < n_rows;
@@ -442,19 +486,22 @@ __global__ void __launch_bounds__(128, 4) k_assemble_p1_rows(int n_rows, int n_t
   double diag = 0.0;
   ItemData D[NI];
 #pragma unroll
-  for (int s = 0; s < NI + DEPTH; ++s) {
-    if (s < NI) {
-      if (s < KQ)
-        item_issue<true, CC>(D[s], P, w[4 * s], w[4 * s + 1], w[4 * s + 2], w[4 * s + 3], r, nc, cc, active);
-      else
-        item_issue<false, CC>(D[s], P, w[4 * KQ + 3 * (s - KQ)], w[4 * KQ + 3 * (s - KQ) + 1], w[4 * KQ + 3 * (s - KQ) + 2], 0U, r, nc, cc, active);
+  for (int s = 0; s < NG + DEPTH; ++s) {
+    if (s < NG) {
+      if (s < KQ / 2) {
+        item_issue<true, CC, MODE>(D[2 * s], P, w[8 * s], w[8 * s + 1], w[8 * s + 2], w[8 * s + 3], r, nc, cc, active);
+        item_issue<true, CC, MODE>(D[2 * s + 1], P, w[8 * s + 4], w[8 * s + 5], w[8 * s + 6], w[8 * s + 7], r, nc, cc, active);
+      } else {
+        const int i = s - KQ / 2;
+        item_issue<false, CC, MODE>(D[KQ + i], P, w[4 * KQ + 3 * i], w[4 * KQ + 3 * i + 1], w[4 * KQ + 3 * i + 2], 0U, r, nc, cc, active);
+      }
     }
     if (s >= DEPTH) {
-      const int c = s - DEPTH;
-      if (c < KQ)
-        item_consume<true, TENSOR, CC>(D[c], P, xi, stage, off, diag);
+      const int g = s - DEPTH;
+      if (g < KQ / 2)
+        group_consume<true, 2, TENSOR, CC, MODE>(&D[2 * g], P, xi, stage, off, diag);
       else
-        item_consume<false, TENSOR, CC>(D[c], P, xi, stage, off, diag);
+        group_consume<false, 1, TENSOR, CC, MODE>(&D[KQ + g - KQ / 2], P, xi, stage, off, diag);
     }
   }
   if (regular) stage[swz(off + info)] = diag;
@@ -674,14 +721,25 @@ int p1h_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, c
   static const int pfd_env = [] { const char* e = std::getenv("LFGPU_P1H_PFD"); return e != nullptr ? std::atoi(e) : 100; }();
   const int ipf = cc ? 0 : static_cast<int>((static_cast<int64_t>(ctx->sm_count) * 4 * threads * pfd_env / 100) & ~static_cast<int64_t>(127));
   const int irows = static_cast<int>(rows), itotal = static_cast<int>(p->n_outer), ifirst = static_cast<int>(first_row);
-  // items loaded this many cells ahead of their use (LFGPU_P1H_DEPTH = 1 or 2; 2 = measured best on config C2)
-  static const int depth_env = [] { const char* e = std::getenv("LFGPU_P1H_DEPTH"); return e != nullptr ? std::atoi(e) : 2; }();
-#define P1H_KERN(KQ, KT, D)                                                                                                        \
-  (tensor ? (cc ? k_assemble_p1_rows<KQ, KT, true, true, D> : k_assemble_p1_rows<KQ, KT, true, false, D>)                           \
-          : (cc ? k_assemble_p1_rows<KQ, KT, false, true, D> : k_assemble_p1_rows<KQ, KT, false, false, D>))
+  // groups of cells loaded this many groups ahead of their use (LFGPU_P1H_DEPTH = 1 or 2)
+  static const int depth_env = [] { const char* e = std::getenv("LFGPU_P1H_DEPTH"); return e != nullptr ? std::atoi(e) : 1; }();
+  static const int mode_env = [] { const char* e = std::getenv("LFGPU_P1H_MODE"); return e != nullptr ? std::atoi(e) : -1; }();
+  // compile-time coefficient kinds where they apply (Kinds<> above); LFGPU_P1H_MODE=0 keeps the run-time switches
+  int mode = 0;
+  if (!tensor && !cc) {
+    const bool eqw = tt == nullptr || (tt->w[0] == tt->w[1] && tt->w[1] == tt->w[2]);
+    if (P.alpha.vec && P.gamma.vec && eqw) mode = 1;
+    if (alpha->kind == LFGPU_COEFF_CONST && gamma->kind == LFGPU_COEFF_CONST) mode = 2;
+  }
+  if (mode_env == 0) mode = 0;
+#define P1H_KERN(KQ, KT, D)                                                                                                          \
+  (tensor ? (cc ? k_assemble_p1_rows<KQ, KT, true, true, D, 0> : k_assemble_p1_rows<KQ, KT, true, false, D, 0>)                       \
+          : (cc ? k_assemble_p1_rows<KQ, KT, false, true, D, 0>                                                                      \
+                : (mode == 1 ? k_assemble_p1_rows<KQ, KT, false, false, D, 1>                                                        \
+                             : (mode == 2 ? k_assemble_p1_rows<KQ, KT, false, false, D, 2> : k_assemble_p1_rows<KQ, KT, false, false, D, 0>))))
 #define P1H_LAUNCH(KQ, KT)                                                                                                         \
   do {                                                                                                                             \
-    auto kern = depth_env == 1 ? P1H_KERN(KQ, KT, 1) : P1H_KERN(KQ, KT, 2);                                                         \
+    auto kern = depth_env == 2 ? P1H_KERN(KQ, KT, 2) : P1H_KERN(KQ, KT, 1);                                                         \
     kern<<<grid, threads, smem, ctx->stream>>>(irows, itotal, p->p1h_qw, p->p1h_tw, p->p1h_rowinfo, mesh->node_coords, mesh->cell_coords, \
                                                p->outer, active, row_list, ifirst, ipf, P, d_values);                                  \
   } while (0)
