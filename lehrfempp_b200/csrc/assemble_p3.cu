@@ -98,9 +98,11 @@ __global__ void k_p3_cell_flags(int64_t n_cells, int64_t base_int, const int32_t
 __device__ __forceinline__ void prefetch_l2(const void* a) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a)); }
 
 // copy-out shared by the kernels: the warp's stage is the image of the contiguous value range of its 32 rows
-template <int LEN>
+// SWZ: the stage is addressed through stage_ix<true> (rows_p3_core.h); `off` = start of the lane's row inside the stage
+template <int LEN, bool SWZ = false>
 __device__ __forceinline__ void write_rows(bool staged, bool regular, bool in_range, int lane, int32_t v0, int32_t v1, int32_t wbase,
-                                           const double* __restrict__ stage, const double* __restrict__ dst, double* __restrict__ values) {
+                                           const double* __restrict__ stage, const double* __restrict__ dst, double* __restrict__ values,
+                                           int off = 0) {
   __syncwarp();
   if (staged) {
     const unsigned ballot = __ballot_sync(0xffffffffU, in_range);
@@ -110,10 +112,14 @@ __device__ __forceinline__ void write_rows(bool staged, bool regular, bool in_ra
 #pragma unroll
     for (int k = 0; k < LEN; ++k) {
       const int idx = k * 32 + lane;
-      if (idx < total) out[idx] = stage[idx];
+      if (idx < total) out[idx] = stage[stage_ix<SWZ>(idx)];
     }
   } else if (regular) {
-    for (int k = 0; k < LEN; ++k) values[v0 + k] = dst[k];
+    if (SWZ) {
+      for (int k = 0; k < LEN; ++k) values[v0 + k] = stage[stage_ix<true>(off + k)];
+    } else {
+      for (int k = 0; k < LEN; ++k) values[v0 + k] = dst[k];
+    }
   }
 }
 
@@ -285,44 +291,65 @@ __global__ void __launch_bounds__(128, 4) k_p3_edge_rows(int n_erows, int row0, 
   const bool regular = in_range && ip >= 0;
   const int32_t wbase = __shfl_sync(0xffffffffU, v0, 0);
   const bool staged = !__any_sync(0xffffffffU, in_range && !regular && v1 > v0);
-  double* stage = stage_all + warp * (32 * (kEdgeRowLen + 1));
-  double* dst = stage + (staged ? v0 - wbase : lane * (kEdgeRowLen + 1));
+  double* stage = stage_all + warp * (32 * kEdgeRowLen);
+  const int off = staged ? v0 - wbase : lane * kEdgeRowLen;
   if (regular) {
     const double2* nc = reinterpret_cast<const double2*>(node_coords);
     const double2 xp = __ldg(nc + ip), xq = __ldg(nc + iq), x1 = __ldg(nc + io1), x2 = __ldg(nc + io2);
-    edge_row<MODE>(P, xq.x - xp.x, xq.y - xp.y, x1.x - xp.x, x1.y - xp.y, x2.x - xp.x, x2.y - xp.y, w, dst);
+    edge_row<MODE, true>(P, xq.x - xp.x, xq.y - xp.y, x1.x - xp.x, x1.y - xp.y, x2.x - xp.x, x2.y - xp.y, w, stage, off);
   }
-  write_rows<kEdgeRowLen>(staged, regular, in_range, lane, v0, v1, wbase, stage, dst, values);
+  write_rows<kEdgeRowLen, true>(staged, regular, in_range, lane, v0, v1, wbase, stage, stage, values, off);
 }
 
-// one thread per cell: row 9 of its element matrix; needs no plan (cell_nodes + the scatter-map row of list position 9)
+// slots of the ten list positions of every cell in its own row (list position 9), one nibble each: 8 bytes per cell instead
+// of a 12-byte gather out of the cell's 120-byte block of the scatter map (ncu: k_p3_cell_rows read 654 MB for 4.2e6 cells)
+__global__ void k_p3_cell_plan(int64_t n_cells, int o_stride, int pos_row, const uint8_t* __restrict__ pos, uint2* __restrict__ cslots) {
+  const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (c >= n_cells) return;
+  const uint8_t* pp = pos + (static_cast<size_t>(c) * o_stride + 9) * pos_row;
+  uint32_t w0 = 0, w1 = 0;
+  for (int b = 0; b < 8; ++b) w0 |= static_cast<uint32_t>(pp[b] & 15U) << (4 * b);
+  for (int b = 8; b < 10; ++b) w1 |= static_cast<uint32_t>(pp[b] & 15U) << (4 * (b - 8));
+  cslots[c] = make_uint2(w0, w1);
+}
+
+// one thread per cell: row 9 of its element matrix (cell_nodes + the compact slot word pair)
 template <int MODE>
-__global__ void __launch_bounds__(128, 4) k_p3_cell_rows(int row0, int o_stride, int pos_row,
-                                                       const uint32_t* __restrict__ cell_nodes, const uint8_t* __restrict__ pos,
-                                                       const double* __restrict__ node_coords, const int32_t* __restrict__ outer, Params P,
-                                                       double* __restrict__ values, int first, int end) {
+__global__ void __launch_bounds__(128, 4) k_p3_cell_rows(int row0, const uint32_t* __restrict__ cell_nodes, const uint2* __restrict__ cslots,
+                                                       const double* __restrict__ node_coords, const int32_t* __restrict__ outer, int pf_dist,
+                                                       Params P, double* __restrict__ values, int first, int end) {
   // cells [first, end); cell c is matrix row row0 + c
   extern __shared__ double stage_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = first + blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = c < end;
+  if (pf_dist > 0 && warp == 0) {
+    const int cp = first + blockIdx.x * blockDim.x + pf_dist;
+    if (cp + 128 <= end && lane < 28) {  // 16 lines of cell corners, 8 of slot words, 4 of row pointers
+      const char* a;
+      if (lane < 16) a = reinterpret_cast<const char*>(cell_nodes + 4 * static_cast<size_t>(cp)) + lane * 128;
+      else if (lane < 24) a = reinterpret_cast<const char*>(cslots + cp) + (lane - 16) * 128;
+      else a = reinterpret_cast<const char*>(outer + row0 + cp) + (lane - 24) * 128;
+      prefetch_l2(a);
+    }
+  }
   int32_t v0 = 0, v1 = 0;
   if (in_range) {
     v0 = __ldg(outer + row0 + c);
     v1 = __ldg(outer + row0 + c + 1);
   }
   const int32_t wbase = __shfl_sync(0xffffffffU, v0, 0);
-  double* stage = stage_all + warp * (32 * (kCellRowLen + 1));
-  double* dst = stage + (v0 - wbase);
+  double* stage = stage_all + warp * (32 * kCellRowLen);
+  const int off = v0 - wbase;
   if (in_range) {
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(cell_nodes) + c);
-    const uint32_t* pp = reinterpret_cast<const uint32_t*>(pos + (static_cast<size_t>(c) * o_stride + 9) * pos_row);
-    const uint32_t pw[3] = {__ldg(pp), __ldg(pp + 1), __ldg(pp + 2)};
+    const uint2 sw = __ldg(cslots + c);
+    const uint32_t pw[3] = {sw.x, sw.y, 0U};
     const double2* nc = reinterpret_cast<const double2*>(node_coords);
     const double2 x0 = __ldg(nc + v.x), x1 = __ldg(nc + v.y), x2 = __ldg(nc + v.z);
-    cell_row<MODE>(P, x1.x - x0.x, x1.y - x0.y, x2.x - x0.x, x2.y - x0.y, pw, dst);
+    cell_row<MODE, true, true>(P, x1.x - x0.x, x1.y - x0.y, x2.x - x0.x, x2.y - x0.y, pw, stage, off);
   }
-  write_rows<kCellRowLen>(true, in_range, in_range, lane, v0, v1, wbase, stage, dst, values);
+  write_rows<kCellRowLen, true>(true, in_range, in_range, lane, v0, v1, wbase, stage, stage, values, off);
 }
 
 }  // namespace
@@ -359,7 +386,8 @@ int p3_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
   auto cleanup = [&]() { cudaFree(flag); cudaFree(iota); cudaFree(d_num); cudaFree(tmp); };
   auto drop_plan = [&]() {
     cudaFree(p->p3v_nbr); cudaFree(p->p3v_slots); cudaFree(p->p3e_nbr); cudaFree(p->p3e_slots); cudaFree(p->p3_irregular);
-    cudaFree(p->p3g_nbr); cudaFree(p->p3g_slots);
+    cudaFree(p->p3g_nbr); cudaFree(p->p3g_slots); cudaFree(p->p3c_slots);
+    p->p3c_slots = nullptr;
     p->p3v_nbr = nullptr; p->p3v_slots = nullptr; p->p3e_nbr = nullptr; p->p3e_slots = nullptr; p->p3_irregular = nullptr;
     p->p3g_nbr = nullptr; p->p3g_slots = nullptr; p->p3_general = false;
   };
@@ -378,6 +406,10 @@ int p3_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
   P3_CHECK(cudaMalloc(&p->p3v_slots, sizeof(uint32_t) * (kVertexSlotWords * static_cast<size_t>(nn) + 128)));
   P3_CHECK(cudaMalloc(&p->p3e_nbr, sizeof(int32_t) * (4 * static_cast<size_t>(ner) + 128)));
   P3_CHECK(cudaMalloc(&p->p3e_slots, sizeof(uint32_t) * (kEdgeSlotWords * static_cast<size_t>(ner) + 128)));
+  P3_CHECK(cudaMalloc(&p->p3c_slots, sizeof(uint2) * (static_cast<size_t>(p->n_cells) + 128)));
+  k_p3_cell_plan<<<static_cast<unsigned>(cdiv(p->n_cells, 256)), 256, 0, st>>>(p->n_cells, p->o_stride, p->pos_row,
+                                                                                static_cast<const uint8_t*>(p->pos), static_cast<uint2*>(p->p3c_slots));
+  ctx->launches++;
   k_p3_vertex_plan<<<static_cast<unsigned>(cdiv(nn, 128)), 128, 0, st>>>(nn, p->o_stride, p->pos_row, p->adj_ptr, p->adj, mesh->cell_nodes,
                                                                           static_cast<const uint8_t*>(p->pos), p->outer, p->p3v_nbr,
                                                                           p->p3v_slots, flag);
@@ -454,9 +486,9 @@ int p3_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* 
   static const int pfc_env = [] { const char* e = std::getenv("LFGPU_EDGE_PFC"); return e != nullptr ? std::atoi(e) : 0; }();
   const int ipc_e = pfc_env > 0 && ipf_e > 0 ? std::max(128, static_cast<int>((static_cast<int64_t>(ipf_e) * pfc_env / 100) & ~static_cast<int64_t>(127))) : 0;
   const size_t smem_v = sizeof(double) * (threads / 32) * 32 * (kVertexRowLen + 1);
-  const size_t smem_e = sizeof(double) * (threads / 32) * 32 * (kEdgeRowLen + 1);
-  const size_t smem_c = sizeof(double) * (threads / 32) * 32 * (kCellRowLen + 1);
-  const uint8_t* pos = static_cast<const uint8_t*>(p->pos);
+  const size_t smem_e = sizeof(double) * (threads / 32) * 32 * kEdgeRowLen;
+  const size_t smem_c = sizeof(double) * (threads / 32) * 32 * kCellRowLen;
+  const int ipf_c = static_cast<int>((static_cast<int64_t>(ctx->sm_count) * 12 * threads * pfd_env / 100) & ~static_cast<int64_t>(127));
   // the share of the range in the vertex rows [0, nn), the edge-dof rows [nn, base_int) and the cell rows [base_int, N)
   auto clip = [](int64_t v, int64_t lo, int64_t hi) { return static_cast<int>(std::min<int64_t>(std::max<int64_t>(v, lo), hi)); };
   const int v_first = clip(r0, 0, nn), v_end = clip(r1, 0, nn);
@@ -487,7 +519,7 @@ int p3_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* 
   }                                                                                                                                       \
   if (c_end > c_first) {                                                                                                                  \
     k_p3_cell_rows<MODE><<<static_cast<unsigned>(cdiv(c_end - c_first, threads)), threads, smem_c, ctx->stream>>>(                        \
-        base_int, p->o_stride, p->pos_row, mesh->cell_nodes, pos, mesh->node_coords, p->outer, P, d_values, c_first, c_end);              \
+        base_int, mesh->cell_nodes, static_cast<const uint2*>(p->p3c_slots), mesh->node_coords, p->outer, ipf_c, P, d_values, c_first, c_end);               \
     LFGPU_LAUNCH_CHECK(ctx);                                                                                                              \
   }
   if (simple) {

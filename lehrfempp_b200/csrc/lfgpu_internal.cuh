@@ -146,6 +146,7 @@ struct lfgpu_pattern {
   uint32_t* p3v_slots = nullptr;     // [9][p3_nn] 36 slot bytes per row
   int32_t* p3e_nbr = nullptr;        // [4][n_edge_rows] P, Q, o_1, o_2
   uint32_t* p3e_slots = nullptr;     // [2][n_edge_rows] 16 slot nibbles per row
+  void* p3c_slots = nullptr;         // uint2 [n_cells] slots of the ten list positions in the cell's own row, one nibble each
   bool p3_general = false;           // vertex rows planned for closed rings of 3..8 cells instead of exactly 6
   int32_t* p3g_nbr = nullptr;        // [8][p3_nn]
   uint32_t* p3g_slots = nullptr;     // [13][p3_nn]

@@ -49,6 +49,13 @@ struct Params {
   double k00[3][10], k01[3][10], k10[3][10], k11[3][10], km[3][10];
 };
 
+// Position of value `k` of a warp's value range inside its shared-memory stage.  SWZ (device kernels): XOR of the low four
+// index bits with the next four -- a bijection inside every aligned group of 16 that spreads the same slot of rows of 16
+// (or 10) values over all banks (ncu on k_p3_edge_rows: 113 M of 139 M shared-memory wavefronts were bank conflicts, the
+// L1 pipe 98 % busy).  The host emulation keeps the identity.
+template <bool SWZ>
+LFGPU_HD int stage_ix(int k) { return SWZ ? (k ^ ((k >> 4) & 15)) : k; }
+
 LFGPU_HD double rcp(double x) {
 #if defined(__CUDA_ARCH__)
   // hardware seed + two Newton steps (Jacobian determinants: no denormals, no zeros), as in assemble.cu
@@ -422,38 +429,42 @@ LFGPU_HD void vertex_row_general(const Params& P, const double (&dx)[kMaxRing], 
   dst[len * (len - 1) / 2 - ssum] = diag;
 }
 
-// (ax, ay) = Q - P, (b1x, b1y) = o_1 - P, (b2x, b2y) = o_2 - P
-template <int MODE>
+// (ax, ay) = Q - P, (b1x, b1y) = o_1 - P, (b2x, b2y) = o_2 - P; value k of the row goes to dst[stage_ix<SWZ>(off + k)]
+template <int MODE, bool SWZ = false>
 LFGPU_HD void edge_row(const Params& P, double ax, double ay, double b1x, double b1y, double b2x, double b2y,
-                       const uint32_t (&w)[kEdgeSlotWords], double* dst) {
+                       const uint32_t (&w)[kEdgeSlotWords], double* dst, int off = 0) {
   double t1[10], t2[10];
   row<MODE, 1>(P, ax, ay, b1x, b1y, t1);
   row<MODE, 1>(P, ax, ay, b2x, b2y, t2);
-  dst[nibble_at(w, 0)] = t1[0] + t2[0];
-  dst[nibble_at(w, 1)] = t1[1] + t2[1];
-  dst[nibble_at(w, 2)] = t1[3] + t2[3];
-  dst[nibble_at(w, 3)] = t1[4] + t2[4];
-  dst[nibble_at(w, 4)] = t1[2];
-  dst[nibble_at(w, 10)] = t2[2];
+  dst[stage_ix<SWZ>(off + nibble_at(w, 0))] = t1[0] + t2[0];
+  dst[stage_ix<SWZ>(off + nibble_at(w, 1))] = t1[1] + t2[1];
+  dst[stage_ix<SWZ>(off + nibble_at(w, 2))] = t1[3] + t2[3];
+  dst[stage_ix<SWZ>(off + nibble_at(w, 3))] = t1[4] + t2[4];
+  dst[stage_ix<SWZ>(off + nibble_at(w, 4))] = t1[2];
+  dst[stage_ix<SWZ>(off + nibble_at(w, 10))] = t2[2];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int k = 0; k < 5; ++k) {
-    dst[nibble_at(w, 5 + k)] = t1[5 + k];
-    dst[nibble_at(w, 11 + k)] = t2[5 + k];
+    dst[stage_ix<SWZ>(off + nibble_at(w, 5 + k))] = t1[5 + k];
+    dst[stage_ix<SWZ>(off + nibble_at(w, 11 + k))] = t2[5 + k];
   }
 }
 
-// the cell in its own numbering: (ax, ay) = v1 - v0, (bx, by) = v2 - v0; pw: the first 12 bytes of the scatter-map row of
-// list position 9
-template <int MODE>
-LFGPU_HD void cell_row(const Params& P, double ax, double ay, double bx, double by, const uint32_t (&pw)[3], double* dst) {
+// the cell in its own numbering: (ax, ay) = v1 - v0, (bx, by) = v2 - v0; pw: the slots of the ten list positions in the row of
+// list position 9, one byte each (NIB = false: the first bytes of the scatter-map row) or one nibble each (NIB = true: the
+// compact plan word pair of the device kernel)
+template <int MODE, bool SWZ = false, bool NIB = false>
+LFGPU_HD void cell_row(const Params& P, double ax, double ay, double bx, double by, const uint32_t (&pw)[3], double* dst, int off = 0) {
   double t[10];
   row<MODE, 2>(P, ax, ay, bx, by, t);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int b = 0; b < 10; ++b) dst[byte_at(pw, b)] = t[b];
+  for (int b = 0; b < 10; ++b) {
+    const int slot = NIB ? static_cast<int>((pw[b >> 3] >> (4 * (b & 7))) & 15U) : byte_at(pw, b);
+    dst[stage_ix<SWZ>(off + slot)] = t[b];
+  }
 }
 
 }  // namespace p3

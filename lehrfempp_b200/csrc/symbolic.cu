@@ -259,6 +259,7 @@ void lfgpu_pattern_destroy(lfgpu_pattern* p) {
   cudaFree(p->p3v_slots);
   cudaFree(p->p3e_nbr);
   cudaFree(p->p3e_slots);
+  cudaFree(p->p3c_slots);
   cudaFree(p->p3_irregular);
   cudaFree(p->p3g_nbr);
   cudaFree(p->p3g_slots);
