@@ -332,6 +332,36 @@ int lfgpu_rows_pack(lfgpu_ctx* ctx, const lfgpu_pattern* pattern, const int32_t*
                     const double* d_values, double* d_buf);
 int lfgpu_rows_unpack_add(lfgpu_ctx* ctx, const lfgpu_pattern* pattern, const int32_t* d_rows, int64_t n_rows,
                           const int64_t* d_offsets, const double* d_buf, double* d_values);
+/* ---- distributed ownership: "the mesh is partitioned across the GPUs ... by Morton-ordered cell ranges, with each GPU owning
+ * the matrix rows for its cells" (BASELINE.json north_star).  The reference's cell loop (assemble/assembler.h:125-180) is
+ * serial; these calls cut it into per-GPU sub-problems that are ordinary lfgpu_mesh / lfgpu_dofmap pairs with LOCAL indices,
+ * so that symbolic pass, plans and numeric kernels run unchanged on 1/N of the matrix (int32 indices stay valid when the global
+ * number of stored values exceeds 2^31).  The local numbering is the order-preserving restriction of the global one: the local
+ * pattern of an OWNED row, mapped through local -> global, is bit-exactly the global pattern of that row; values are added in
+ * the reference's cell order.                                                                                                */
+/* cell -> part: cells sorted by the Morton code of their centroid, n_parts contiguous ranges of equal cell counts.
+ * d_cell_part: device uint8 [n_cells].                                                                                       */
+int lfgpu_partition_morton(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, int n_parts, uint8_t* d_cell_part);
+/* dof -> owner = the lowest part with a cell touching the dof; d_dof_owner: device uint8 [n_dofs] (255 = untouched)           */
+int lfgpu_partition_dof_owner(lfgpu_ctx* ctx, const lfgpu_dofmap* dofmap, const uint8_t* d_cell_part, uint8_t* d_dof_owner);
+/* d_cell_sel [n_cells] = 1 for the cells of part `rank` (halo == 0: every rank assembles its own cells, interface rows are
+ * summed at their owner) or for every cell that touches a dof owned by `rank` (halo != 0: owner-computes, the rows a rank owns
+ * are complete without any exchange)                                                                                           */
+int lfgpu_partition_select_cells(lfgpu_ctx* ctx, const lfgpu_dofmap* dofmap, const uint8_t* d_cell_part, const uint8_t* d_dof_owner,
+                                 int rank, int halo, uint8_t* d_cell_sel);
+/* the selected cells as a mesh + dof map of their own, and the local -> global index lists (ascending)                        */
+typedef struct lfgpu_submesh lfgpu_submesh;
+int lfgpu_submesh_extract(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* dofmap, const uint8_t* d_cell_sel,
+                          lfgpu_submesh** out);
+void lfgpu_submesh_destroy(lfgpu_submesh* s);     /* also destroys its mesh and dof map */
+lfgpu_mesh* lfgpu_submesh_mesh(lfgpu_submesh* s);     /* owned by the submesh */
+lfgpu_dofmap* lfgpu_submesh_dofmap(lfgpu_submesh* s); /* owned by the submesh */
+int lfgpu_submesh_counts(const lfgpu_submesh* s, int64_t* n_cells, int64_t* n_nodes, int64_t* n_dofs);
+const int32_t* lfgpu_submesh_l2g_cells_device(const lfgpu_submesh* s);
+const int32_t* lfgpu_submesh_l2g_nodes_device(const lfgpu_submesh* s);
+const int32_t* lfgpu_submesh_l2g_dofs_device(const lfgpu_submesh* s);
+/* d_owned [n_local_dofs] = 1 where the local dof is owned by `rank` (d_dof_owner: the GLOBAL owner array)                     */
+int lfgpu_submesh_owned_dofs(lfgpu_ctx* ctx, const lfgpu_submesh* s, const uint8_t* d_dof_owner, int rank, uint8_t* d_owned);
 /* read-only device views used by the host-side partitioner: gather lists (items = cell << 4 | local index), mesh arrays */
 const int32_t* lfgpu_pattern_adj_ptr_device(const lfgpu_pattern* p);
 const uint32_t* lfgpu_pattern_adj_device(const lfgpu_pattern* p);

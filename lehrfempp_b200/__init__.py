@@ -28,6 +28,7 @@ from .api import (  # noqa: F401
     Mesh,
     Pattern,
     QuadRule,
+    SubMesh,
     build_library,
     default_quad_rule,
     fe_tabulate,
@@ -36,5 +37,5 @@ from .api import (  # noqa: F401
 
 __all__ = [
     "ALGO_ATOMIC", "ALGO_AUTO", "ALGO_FAN", "ALGO_GATHER", "COL_MAJOR", "ROW_MAJOR", "Coeff", "Context", "DeviceArray", "DofMap",
-    "GmshReader",    "LfgpuError", "Mesh", "Pattern", "QuadRule", "build_library", "default_quad_rule", "fe_tabulate", "library_path",
+    "GmshReader",    "LfgpuError", "Mesh", "Pattern", "QuadRule", "SubMesh", "build_library", "default_quad_rule", "fe_tabulate", "library_path",
 ]

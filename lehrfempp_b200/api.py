@@ -143,6 +143,18 @@ def _lib():
         "lfgpu_mesh_node_coords_device": (vp, [vp]),
         "lfgpu_mesh_cell_nodes_device": (vp, [vp]),
         "lfgpu_ctx_wait_event": (i32, [vp, vp]),
+        "lfgpu_partition_morton": (i32, [vp, vp, i32, vp]),
+        "lfgpu_partition_dof_owner": (i32, [vp, vp, vp, vp]),
+        "lfgpu_partition_select_cells": (i32, [vp, vp, vp, vp, i32, i32, vp]),
+        "lfgpu_submesh_extract": (i32, [vp, vp, vp, vp, pp]),
+        "lfgpu_submesh_destroy": (None, [vp]),
+        "lfgpu_submesh_mesh": (vp, [vp]),
+        "lfgpu_submesh_dofmap": (vp, [vp]),
+        "lfgpu_submesh_counts": (i32, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
+        "lfgpu_submesh_l2g_cells_device": (vp, [vp]),
+        "lfgpu_submesh_l2g_nodes_device": (vp, [vp]),
+        "lfgpu_submesh_l2g_dofs_device": (vp, [vp]),
+        "lfgpu_submesh_owned_dofs": (i32, [vp, vp, vp, i32, vp]),
         "lfgpu_qp_coords": (i32, [vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), i32, vp]),
         "lfgpu_fe_tabulate": (i32, [i32, i32, C.POINTER(_CQuad), vp, vp]),
         "lfgpu_default_quad_rule": (i32, [i32, i32, i32, vp, vp]),
@@ -458,9 +470,10 @@ class DeviceArray:
 
 
 class Mesh:
-    def __init__(self, ctx, handle):
+    def __init__(self, ctx, handle, owner=None):
         self.ctx = ctx
         self.h = handle
+        self._owner = owner  # a SubMesh that owns the handle (then this object must not destroy it)
         self._refresh()
 
     def _refresh(self):
@@ -469,7 +482,7 @@ class Mesh:
         self.n_nodes, self.n_edges, self.n_cells, self.n_tria, self.n_quad = [x.value for x in v]
 
     def __del__(self):
-        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None) and getattr(self, "_owner", None) is None:
             self.ctx.L.lfgpu_mesh_destroy(self.h)
             self.h = None
 
@@ -582,17 +595,36 @@ class Mesh:
 
 
 class DofMap:
-    def __init__(self, mesh, handle):
+    def __init__(self, mesh, handle, owner=None):
         self.mesh = mesh
         self.ctx = mesh.ctx
         self.h = handle
+        self._owner = owner
         self.num_dofs = self.ctx.L.lfgpu_dofmap_num_dofs(self.h)
         self.stride = self.ctx.L.lfgpu_dofmap_stride(self.h)
 
     def __del__(self):
-        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None) and getattr(self, "_owner", None) is None:
             self.ctx.L.lfgpu_dofmap_destroy(self.h)
             self.h = None
+
+    # ---- distributed ownership (include/lfgpu.h "distributed ownership") --------------------------------------------------
+    def partition_morton(self, n_parts):
+        """(cell_part, dof_owner): DeviceArray(uint8) [n_cells], [n_dofs] -- Morton cell ranges, dof owned by the lowest part touching it."""
+        part = self.ctx.empty(self.mesh.n_cells, np.uint8)
+        self.ctx.check(self.ctx.L.lfgpu_partition_morton(self.ctx.h, self.mesh.h, int(n_parts), part.ptr))
+        owner = self.ctx.empty(self.num_dofs, np.uint8)
+        self.ctx.check(self.ctx.L.lfgpu_partition_dof_owner(self.ctx.h, self.h, part.ptr, owner.ptr))
+        return part, owner
+
+    def submesh(self, cell_part, dof_owner, rank, halo=True):
+        """The sub-problem of part `rank`: its cells (+ the one-cell halo around the dofs it owns when halo) as a SubMesh."""
+        sel = self.ctx.empty(self.mesh.n_cells, np.uint8)
+        self.ctx.check(self.ctx.L.lfgpu_partition_select_cells(self.ctx.h, self.h, cell_part.ptr, dof_owner.ptr, int(rank), 1 if halo else 0,
+                                                               sel.ptr))
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.L.lfgpu_submesh_extract(self.ctx.h, self.mesh.h, self.h, sel.ptr, C.byref(h)))
+        return SubMesh(self.ctx, h, dof_owner, rank)
 
     def download(self):
         d = np.zeros((self.mesh.n_cells, self.stride), np.int64)
@@ -643,6 +675,46 @@ class DofMap:
         self.ctx.check(self.ctx.L.lfgpu_assemble_load(self.ctx.h, self.mesh.h, self.h, degree, _qref(qr_tria), _qref(qr_quad),
                                                       f.ref(), active.ptr if active is not None else None, beta, out.ptr, algo))
         return out
+
+
+class SubMesh:
+    """One GPU's share of a partitioned problem: mesh + dof map with local indices, local -> global lists, owned-dof flags."""
+
+    def __init__(self, ctx, handle, dof_owner, rank):
+        self.ctx, self.h, self.rank = ctx, handle, rank
+        L = ctx.L
+        v = [C.c_int64() for _ in range(3)]
+        ctx.check(L.lfgpu_submesh_counts(self.h, *[C.byref(x) for x in v]))
+        self.n_cells, self.n_nodes, self.n_dofs = [x.value for x in v]
+        self.mesh = Mesh(ctx, C.c_void_p(L.lfgpu_submesh_mesh(self.h)), owner=self)
+        self.dofmap = DofMap(self.mesh, C.c_void_p(L.lfgpu_submesh_dofmap(self.h)), owner=self)
+        self.owned = ctx.empty(self.n_dofs, np.uint8)
+        ctx.check(L.lfgpu_submesh_owned_dofs(ctx.h, self.h, dof_owner.ptr, int(rank), self.owned.ptr))
+
+    def _list(self, fn, n):
+        out = np.zeros(n, np.int32)
+        self.ctx.check(self.ctx.L.lfgpu_memcpy_d2h(self.ctx.h, _p(out), C.c_void_p(fn(self.h)), 4 * n))
+        self.ctx.synchronize()
+        return out
+
+    def l2g_cells(self):
+        return self._list(self.ctx.L.lfgpu_submesh_l2g_cells_device, self.n_cells)
+
+    def l2g_nodes(self):
+        return self._list(self.ctx.L.lfgpu_submesh_l2g_nodes_device, self.n_nodes)
+
+    def l2g_dofs(self):
+        return self._list(self.ctx.L.lfgpu_submesh_l2g_dofs_device, self.n_dofs)
+
+    def l2g_cells_ptr(self):
+        return C.c_void_p(self.ctx.L.lfgpu_submesh_l2g_cells_device(self.h))
+
+    def __del__(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.mesh.h = None
+            self.dofmap.h = None
+            self.ctx.L.lfgpu_submesh_destroy(self.h)
+            self.h = None
 
 
 class Pattern:

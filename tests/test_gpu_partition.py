@@ -1,0 +1,127 @@
+"""Distributed ownership (lehrfempp_b200/csrc/partition.cu): Morton cell partition, dof ownership, per-GPU sub-problems with local
+indices.  One GPU plays every rank in turn, so the whole scheme except the NCCL plumbing is checked on a single-GPU box:
+  * the local pattern of every OWNED row, mapped through local -> global, is bit-exactly the row of the global pattern (and of
+    the oracle's pattern), the owned rows of all ranks cover every row exactly once,
+  * the values of the owned rows agree with the oracle within 1e-12 (owner-computes: halo cells recomputed),
+  * without halo (every rank assembles only its own cells) the local matrices SUM to the global one -- the owner-adds exchange."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import lfo
+from tests.helpers import rel_max_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def lf():
+    import lehrfempp_b200 as lf
+    return lf
+
+
+@pytest.fixture(scope="module")
+def ctx(lf):
+    c = lf.Context(0)
+    yield c
+    c.close()
+
+
+def meshes(ctx, kind):
+    if kind == "tria":
+        return ctx.mesh_tp_tria(41, 33), lfo.Mesh.tp_tria(41, 33)
+    if kind == "quad":
+        return ctx.mesh_tp_quad(23, 31), lfo.Mesh.tp_quad(23, 31)
+    if kind == "refined":
+        return ctx.mesh_tp_tria(5, 4).refine_regular().refine_regular(), lfo.Mesh.tp_tria(5, 4).refine_regular().refine_regular()
+    return ctx.mesh_hybrid(26, 0.2, 12345), lfo.Mesh.hybrid(26, 0.2, 12345)
+
+
+@pytest.mark.parametrize("kind", ["tria", "hybrid", "quad", "refined"])
+@pytest.mark.parametrize("degree", [1, 2, 3])
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_owned_rows_reproduce_the_global_matrix(ctx, lf, kind, degree, world):
+    gm, om = meshes(ctx, kind)
+    dm = gm.dofmap_lagrange(degree)
+    o_outer, o_inner, o_vals, shape, _ = om.assemble_rd(degree, lfo.coeff.const(1.5), lfo.coeff.const(0.5), csr=True)
+    part, owner = dm.partition_morton(world)
+    h_part, h_owner = part.to_host(), owner.to_host()
+    counts = np.bincount(h_part, minlength=world)
+    assert counts.max() - counts.min() <= -(-gm.n_cells // world)  # equal cell counts (last part takes the remainder)
+    assert h_owner.max() < world
+    covered = np.zeros(dm.num_dofs, np.int32)
+    alpha, gamma = lf.Coeff.const(1.5), lf.Coeff.const(0.5)
+    for r in range(world):
+        sub = dm.submesh(part, owner, r, halo=True)
+        l2g = sub.l2g_dofs()
+        assert np.all(np.diff(l2g) > 0) and np.all(np.diff(sub.l2g_cells()) > 0) and np.all(np.diff(sub.l2g_nodes()) > 0)
+        own = sub.owned.to_host().astype(bool)
+        assert np.array_equal(np.nonzero(h_owner == r)[0], l2g[own])  # the sub-problem contains exactly the dofs the rank owns
+        lpat = sub.dofmap.symbolic(major=lf.ROW_MAJOR)
+        l_outer, l_inner = lpat.download()
+        vals = lpat.assemble_reaction_diffusion(degree, alpha, gamma).to_host()
+        rows_l = np.nonzero(own)[0]
+        rows_g = l2g[rows_l]
+        covered[rows_g] += 1
+        lens = l_outer[rows_l + 1] - l_outer[rows_l]
+        assert np.array_equal(lens, o_outer[rows_g + 1] - o_outer[rows_g])
+        # entries of the owned rows, local and global, in row order
+        idx_l = np.repeat(l_outer[rows_l] - np.cumsum(lens) + lens, lens) + np.arange(lens.sum())
+        idx_g = np.repeat(o_outer[rows_g] - np.cumsum(lens) + lens, lens) + np.arange(lens.sum())
+        assert np.array_equal(l2g[l_inner[idx_l]], o_inner[idx_g]), "pattern of an owned row differs from the reference's"
+        assert np.abs(vals[idx_l] - o_vals[idx_g]).max() <= TOL * np.abs(o_vals).max()
+    assert np.all(covered == 1)
+
+
+@pytest.mark.parametrize("kind,degree", [("tria", 1), ("hybrid", 2), ("tria", 3)])
+def test_without_halo_the_local_matrices_sum_to_the_global_one(ctx, lf, kind, degree):
+    gm, om = meshes(ctx, kind)
+    dm = gm.dofmap_lagrange(degree)
+    o_outer, o_inner, o_vals, shape, _ = om.assemble_rd(degree, lfo.coeff.const(1.0), lfo.coeff.const(2.0), csr=True)
+    A = sp.csr_matrix((o_vals, o_inner, o_outer), shape=shape)
+    world = 4
+    part, owner = dm.partition_morton(world)
+    S = sp.csr_matrix(shape)
+    n_cells = 0
+    for r in range(world):
+        sub = dm.submesh(part, owner, r, halo=False)
+        n_cells += sub.n_cells
+        l2g = sub.l2g_dofs()
+        lpat = sub.dofmap.symbolic(major=lf.ROW_MAJOR)
+        l_outer, l_inner = lpat.download()
+        vals = lpat.assemble_reaction_diffusion(degree, lf.Coeff.const(1.0), lf.Coeff.const(2.0)).to_host()
+        rows = np.repeat(l2g, np.diff(l_outer))
+        S = S + sp.csr_matrix((vals, (rows, l2g[l_inner])), shape=shape)
+    assert n_cells == gm.n_cells  # a partition: every cell in exactly one part
+    assert abs(S - A).max() <= TOL * np.abs(o_vals).max()
+
+
+def test_large_partition_against_the_single_gpu_matrix(ctx, lf):
+    # 2.0e6 triangles, 8 parts: the fan kernel with its compact plan and L2 prefetch runs on the sub-problems
+    gm = ctx.mesh_tp_tria(1000, 1000)
+    dm = gm.dofmap_lagrange(1)
+    gpat = dm.symbolic(major=lf.ROW_MAJOR)
+    g_outer, g_inner = gpat.download()
+    g_vals = gpat.assemble_reaction_diffusion(1, lf.Coeff.const(1.0), lf.Coeff.const(0.0)).to_host()
+    part, owner = dm.partition_morton(8)
+    covered = np.zeros(dm.num_dofs, np.int32)
+    total_cells = 0
+    for r in range(8):
+        sub = dm.submesh(part, owner, r, halo=True)
+        total_cells += sub.n_cells
+        l2g = sub.l2g_dofs()
+        own = sub.owned.to_host().astype(bool)
+        lpat = sub.dofmap.symbolic(major=lf.ROW_MAJOR)
+        l_outer, l_inner = lpat.download()
+        vals = lpat.assemble_reaction_diffusion(1, lf.Coeff.const(1.0), lf.Coeff.const(0.0)).to_host()
+        rows_l = np.nonzero(own)[0]
+        rows_g = l2g[rows_l]
+        covered[rows_g] += 1
+        lens = l_outer[rows_l + 1] - l_outer[rows_l]
+        idx_l = np.repeat(l_outer[rows_l] - np.cumsum(lens) + lens, lens) + np.arange(lens.sum())
+        idx_g = np.repeat(g_outer[rows_g] - np.cumsum(lens) + lens, lens) + np.arange(lens.sum())
+        assert np.array_equal(l2g[l_inner[idx_l]], g_inner[idx_g])
+        assert rel_max_err(vals[idx_l], g_vals[idx_g]) <= TOL
+    assert np.all(covered == 1)
+    assert total_cells < 1.05 * gm.n_cells  # the halo is a perimeter effect
