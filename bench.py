@@ -45,6 +45,8 @@ WORKLOADS = {
     # valences 3..10) for the row kernels on Gmsh-like input; LFGPU_P2_GENERAL=1 selects the general-valence P2 vertex kernel
     "u2": ("U2: P2 Laplacian on an unstructured mesh (Delaunay triangulation of 5.0e5 random points, about 1.0e6 triangles), CSR",
            "delaunay", 500000, 2),
+    "c4_full": ("C4 at its configured size: P3 stiffness+mass on a MeshHierarchy-refined mesh: TP-triangle mesh 2x2 (8 cells), 11 x RefineRegular "
+                "(3.36e7 cells, 2.5e9 stored values: needs the distributed pattern, i.e. --gpus >= 2), CSR", "refined:11", 2, 3),
     "c4_27m": ("C4: P3 stiffness+mass on a MeshHierarchy-refined mesh: TP-triangle mesh n=232, 4 x RefineRegular (2.76e7 cells, the "
                "largest of the family whose nnz fits the reference's int32 storage index), CSR", "refined:4", 232, 3),
 }
@@ -200,6 +202,7 @@ def main():
     ap.add_argument("--algo", default="auto", choices=["auto", "fan", "gather", "atomic"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short C2 / C3 / C4 lines of the default single-GPU run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -251,76 +254,53 @@ def main():
         desc += " [n overridden to %d]" % n
     ctx = lf.Context(local_rank)
     algo = {"auto": lf.ALGO_AUTO, "fan": lf.ALGO_FAN, "gather": lf.ALGO_GATHER, "atomic": lf.ALGO_ATOMIC}[args.algo]
-    structured = kind == "tp_tria" or kind.startswith("refined:") or kind == "delaunay"  # triangle meshes: the row kernels apply
-    # kernels that own matrix rows in registers (LFGPU_ALGO_AUTO takes them on triangle meshes with constant coefficients)
-    row_kernels = {1: "k_assemble_p1_fan", 2: "k_p2_vertex_rows + k_p2_edge_rows", 3: "k_p3_vertex_rows + k_p3_edge_rows + k_p3_cell_rows"}
-    if args.algo == "auto":
-        kernel_name = row_kernels[degree] if (structured and degree in AUTO_ROW_DEGREES) else "k_assemble_items"
-    elif args.algo == "fan":
-        kernel_name = row_kernels[degree]
-    else:
-        kernel_name = {"gather": "k_assemble_items", "atomic": "k_assemble_atomic"}[args.algo]
+    kernel_name = kernel_of(args.workload, kind, degree, args.algo)
 
     # ---- setup (untimed, like mesh / DofHandler construction on the CPU side) ----------------------------------------------
     t_setup = time.time()
-    if kind == "tp_tria":
-        mesh = ctx.mesh_tp_tria(n, n)
-    elif kind.startswith("refined:"):
-        # MeshHierarchy-refined mesh (BASELINE config 4): builder mesh + regular refinement steps with the reference's numbering
-        mesh = ctx.mesh_tp_tria(n, n)
-        for _ in range(int(kind.split(":")[1])):
-            mesh = mesh.refine_regular()
-    elif kind == "delaunay":
-        from scipy.spatial import Delaunay
-        pts = np.random.default_rng(12345).random((n, 2))
-        tri = Delaunay(pts).simplices
-        a, b, c = pts[tri[:, 0]], pts[tri[:, 1]], pts[tri[:, 2]]
-        area2 = np.abs((b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (c[:, 0] - a[:, 0]) * (b[:, 1] - a[:, 1]))
-        longest2 = np.maximum.reduce([((b - a) ** 2).sum(1), ((c - b) ** 2).sum(1), ((a - c) ** 2).sum(1)])
-        tri = tri[area2 > 0.05 * longest2]  # slivers along the convex hull
-        used = np.unique(tri)
-        remap = np.full(n, -1, dtype=np.int64)
-        remap[used] = np.arange(used.size)
-        cn = np.full((tri.shape[0], 4), 0xFFFFFFFF, dtype=np.uint32)
-        cn[:, :3] = remap[tri]
-        mesh = ctx.mesh_upload(pts[used], cn)
-        del pts, tri, a, b, c, area2, longest2, cn
-    else:
-        mesh = ctx.mesh_hybrid(n, 0.2, 12345)
+    mesh = build_mesh(ctx, np, kind, n)
     dm = mesh.dofmap_lagrange(degree)
-    t_sym = time.time()
-    pat = dm.symbolic(major=lf.ROW_MAJOR)
-    ctx.synchronize()
-    t_sym = time.time() - t_sym
-    if args.workload == "c2":
-        stride = 4
-        xy = mesh.qp_coords(degree, stride).to_host().reshape(mesh.n_cells, stride, 2)
-        r2 = xy[..., 0] ** 2 + xy[..., 1] ** 2
-        alpha = lf.Coeff.per_qp(ctx.to_device(1.0 + r2), stride)
-        gamma = lf.Coeff.per_qp(ctx.to_device(1.0 / (1.0 + r2)), stride)
-        coef_bytes = 2 * 8.0 * (3 * mesh.n_tria + 4 * mesh.n_quad)
-    elif args.workload in ("c4s", "c4", "c4_27m"):
-        alpha, gamma, coef_bytes = lf.Coeff.const(1.0), lf.Coeff.const(1.0), 0.0
+    n_cells, n_nodes, n_dofs, n_tria, n_quad = mesh.n_cells, mesh.n_nodes, dm.num_dofs, mesh.n_tria, mesh.n_quad
+
+    # N > 1.  Default "owned": distributed ownership -- Morton cell ranges, every rank keeps only its sub-problem (its cells + the
+    # one-cell halo around the rows it owns, local indices), owner-computes, no collective in the data path.  The round-1 modes
+    # on a replicated pattern stay selectable: owner_rows (contiguous row blocks), owner (Morton row lists), exchange (partial
+    # interface rows to their owner by one NCCL all-to-all-v overlapped with the interior rows).
+    dist_mode = os.environ.get("LFGPU_DIST_MODE", "owned") if world > 1 else None
+    asm = None
+    t_part = 0.0
+    if dist_mode == "owned":
+        from lehrfempp_b200.distributed import OwnedAssembler
+        asm = OwnedAssembler(ctx, mesh, dm, degree, rank, world)
+        t_part, t_sym = asm.partition_s, asm.symbolic_s
+        del dm, mesh  # the global mesh and dof map are not needed any more
+        mesh, pat = asm.mesh, asm.pattern
+        t = torch.tensor([float(asm.owned_nnz)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        nnz_global = int(t.item())
     else:
-        alpha, gamma, coef_bytes = lf.Coeff.const(1.0), lf.Coeff.const(0.0), 0.0
+        if args.workload == "c4_full":
+            raise SystemExit("c4_full has 2.5e9 stored values: it needs the distributed pattern (--gpus >= 2, LFGPU_DIST_MODE=owned)")
+        t_sym = time.time()
+        pat = dm.symbolic(major=lf.ROW_MAJOR)
+        ctx.synchronize()
+        t_sym = time.time() - t_sym
+        nnz_global = pat.nnz
+    alpha, gamma, coef_bytes = make_coeffs(ctx, lf, args.workload, mesh, degree)  # per-cell tables live on the (sub-)mesh in use
+    if dist_mode == "owned" and coef_bytes:
+        t = torch.tensor([float(coef_bytes)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        coef_bytes = float(t.item())  # includes the halo cells (read twice): an upper bound of the algorithmic count
     values = ctx.empty(pat.nnz)
     t_setup = time.time() - t_setup
 
-    # N > 1: Morton partition of the cells; every rank assembles the contributions of its cells, partial sums of
-    # interface rows go to the row owner in one all-to-all-v (NCCL) overlapped with the interior rows
-    asm = None
-    t_part = 0.0
-    if world > 1:
+    if world > 1 and dist_mode != "owned":
         from lehrfempp_b200.distributed import DistributedAssembler
         t_part = time.time()
-        # default: owner-computes (faster: one launch per rank, no collective); LFGPU_DIST_MODE=exchange selects the
-        # contributions-to-owner variant with the NCCL all-to-all-v (both are parity-tested by tests/dist_gpu_check.py)
-        # owner_rows (default): the same owner-computes scheme over contiguous row blocks -- one range launch per rank
-        dist_mode = os.environ.get("LFGPU_DIST_MODE", "owner_rows")
         asm = DistributedAssembler(ctx, mesh, pat, degree, mode=dist_mode)
         t_part = time.time() - t_part
 
-    use_graph = asm is not None and os.environ.get("LFGPU_BENCH_GRAPH", "0") == "1"
+    use_graph = asm is not None and dist_mode != "owned" and os.environ.get("LFGPU_BENCH_GRAPH", "0") == "1"
     if use_graph:
         asm.capture(alpha, gamma, values)  # the partitioned step (4 launches + 1 collective) as one CUDA graph
 
@@ -370,6 +350,33 @@ def main():
         barrier()
         t_timed1 = time.time()
 
+    # ---- size-independent witness that the matrix left in `values` at the FULL size is the right operator (not part of any
+    # timing): one device SpMV with the constant vector -- constants are in the kernel of the stiffness part, 1^T M 1 = |Omega|.
+    # N > 1: every rank checks the rows it owns; max / sum over the ranks.
+    check = None
+    try:
+        if dist_mode == "owned":
+            wmax, wsum = asm.witness(values)
+        elif asm is not None:
+            y = pat.spmv(values, ctx.to_device(np.ones(n_dofs))).to_host()
+            own = asm.plan.owned_rows.cpu().numpy()
+            wmax, wsum = (float(np.abs(y[own]).max()) if own.size else 0.0), float(y[own].sum())
+            del y
+        else:
+            y = pat.spmv(values, ctx.to_device(np.ones(n_dofs))).to_host()
+            wmax, wsum = float(np.abs(y).max()), float(y.sum())
+            del y
+        if dist is not None:
+            t = torch.tensor([wmax], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            wmax = float(t.item())
+            t = torch.tensor([wsum], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            wsum = float(t.item())
+        check = witness_record(args.workload, wmax, wsum, world)
+    except Exception as e:  # a witness must never cost the bench line
+        check = {"error": str(e)[:200]}
+
     # ---- end to end through the C ABI with host buffers ---------------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -377,12 +384,15 @@ def main():
         d = mesh.download()
         h_xy[:] = d["node_coords"].ravel()
         del d
-        if asm is None:
+        h2d_rank = 16 * mesh.n_nodes
+        e2e_blocks = int(os.environ.get("LFGPU_E2E_BLOCKS", "16"))
+        range_mode = False
+        if asm is None or dist_mode == "owned":
+            # one rank (or every rank on its sub-problem): pinned coordinates of the (sub-)mesh in, pinned CSR values out
             h_vals = ctx.pinned(pat.nnz)
-            d2h = lambda: ctx.d2h_async(h_vals, values)  # noqa: E731
             d2h_bytes = 8 * pat.nnz
         else:
-            # every rank returns the rows it owns: pack their segments, then one D2H copy
+            # replicated pattern: every rank returns the rows it owns: pack their segments, then one D2H copy
             pl = asm.plan
             outer_t = torch.as_tensor(pat.download()[0], device="cuda").to(torch.int64)
             own = pl.owned_rows.to(torch.int64)
@@ -397,28 +407,23 @@ def main():
                                                 values.ptr, own_buf.ptr))
                 ctx.check(ctx.L.lfgpu_memcpy_d2h(ctx.h, h_vals.ctypes.data, own_buf.ptr, 8 * n_own))
             d2h_bytes = 8 * n_own
+            # owner_rows on the fan kernel: every rank runs the host-buffer call for ITS row block -- uploads only the coordinate
+            # window its rows refer to and downloads only its rows (lfgpu_assemble_reaction_diffusion_host_range)
+            range_mode = (asm.mode == "owner_rows" and getattr(asm, "_range_ok", False) and args.algo in ("auto", "fan") and degree == 1)
+            if range_mode:
+                inner_t = torch.as_tensor(pat.download()[1], device="cuda")
+                seg = inner_t[int(outer_t[asm.row0].item()):int(outer_t[asm.row0 + asm.n_rows].item())]
+                h2d_rank = 16 * (int(seg.max().item()) + 1 - int(seg.min().item())) if seg.numel() > 0 else 0
+                del inner_t, seg
         e2e_steps = max(3, min(args.steps, 10))
-
-        e2e_blocks = int(os.environ.get("LFGPU_E2E_BLOCKS", "16"))
-        # owner_rows on the fan kernel: every rank runs the host-buffer call for ITS row block -- uploads only the coordinate
-        # window its rows refer to and downloads only its rows (lfgpu_assemble_reaction_diffusion_host_range)
-        # (P1 only: the P2 / P3 row kernels also take row ranges, but the host-buffer range call knows the coordinate window of
-        # the fan kernel only -- they go through the generic upload / step / download sequence below)
-        range_mode = (asm is not None and asm.mode == "owner_rows" and getattr(asm, "_range_ok", False) and args.algo in ("auto", "fan")
-                      and degree == 1)
-        h2d_rank = 16 * mesh.n_nodes
-        if range_mode:
-            inner_t = torch.as_tensor(pat.download()[1], device="cuda")
-            seg = inner_t[int(outer_t[asm.row0].item()):int(outer_t[asm.row0 + asm.n_rows].item())]
-            h2d_rank = 16 * (int(seg.max().item()) + 1 - int(seg.min().item())) if seg.numel() > 0 else 0
-            del inner_t, seg
+        host_call = asm is None or dist_mode == "owned"
 
         def e2e_step():
             if range_mode:
                 pat.assemble_reaction_diffusion_host_range(degree, alpha, gamma, h_xy, h_vals, asm.row0, asm.n_rows, out=values, algo=algo,
                                                            n_blocks=max(2, e2e_blocks // world))
                 return
-            if asm is None:
+            if host_call:
                 # the host-buffer C-ABI call: pinned coordinates in, pinned CSR values out; upload, kernel and download
                 # are pipelined over row blocks inside the call (csrc/hostpipe.cu); returns when h_vals is complete
                 pat.assemble_reaction_diffusion_host(degree, alpha, gamma, h_xy, h_vals, out=values, algo=algo, n_blocks=e2e_blocks)
@@ -445,10 +450,13 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             d2h_bytes = int(t[0].item())
             h2d_b = int(t[1].item())
-        e2e = {"value": mesh.n_cells / e2e_s, "unit": "cells/s", "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_bytes),
+        e2e = {"value": n_cells / e2e_s, "unit": "cells/s", "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_bytes),
                "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                "what": ("per step: one lfgpu_assemble_reaction_diffusion_host call = H2D node coordinates (pinned) -> kernel -> D2H CSR "
                         "values (pinned), pipelined over %d row blocks" % e2e_blocks) if asm is None else
+                       ("per step and rank: one lfgpu_assemble_reaction_diffusion_host call on the rank's sub-problem = H2D of its node "
+                        "coordinates (pinned) -> kernel -> D2H of its CSR rows (pinned; incl. the few halo rows), pipelined over %d row "
+                        "blocks" % e2e_blocks) if dist_mode == "owned" else
                        ("per step and rank: one lfgpu_assemble_reaction_diffusion_host_range call = H2D of the coordinate window of the "
                         "rank's row block (pinned) -> kernel -> D2H of its CSR rows (pinned), pipelined") if range_mode else
                        "per step: H2D node coordinates (pinned) -> partitioned assembly -> D2H of the owned CSR rows (pinned)"}
@@ -466,37 +474,24 @@ def main():
         if dist is not None:
             dist.destroy_process_group()
 
+    # per-rank facts the line reports for N > 1 (max over the ranks)
+    rank_facts = None
+    if dist is not None:
+        t = torch.tensor([t_sym, t_part, float(pat.nnz), float(mesh.n_cells)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        rank_facts = {"symbolic_pass_s_max": round(float(t[0].item()), 3), "partition_s_max": round(float(t[1].item()), 3),
+                      "stored_values_per_rank_max": int(t[2].item()), "cells_per_rank_max": int(t[3].item())}
+
     if rank != 0:
         teardown()
         return
 
-    # size-independent witness that the matrix left in `values` at the FULL size is the right operator (not part of any timing):
-    # one device SpMV with the constant vector -- constants are in the kernel of the stiffness part, 1^T M 1 = |Omega| = 1
-    check = None
-    if asm is None:
-        try:
-            y = pat.spmv(values, ctx.to_device(np.ones(dm.num_dofs))).to_host()
-            if args.workload in ("c4s", "c4", "c4_27m"):
-                check = {"what": "1^T A 1 for stiffness + mass with alpha = gamma = 1 on the unit square", "value": float(y.sum()), "expected": 1.0}
-            elif args.workload == "c2":
-                from scipy.integrate import dblquad
-                expected = dblquad(lambda yy, xx: 1.0 / (1.0 + xx * xx + yy * yy), 0.0, 1.0, 0.0, 1.0)[0]
-                check = {"what": "1^T A 1 = integral of gamma = 1 / (1 + |x|^2) over the unit square (quadrature error O(h^2))",
-                         "value": float(y.sum()), "expected": expected}
-            else:
-                check = {"what": "max |A 1| for the Laplacian (constants are in its kernel; entries are O(1))", "value": float(np.abs(y).max()),
-                         "expected": 0.0}
-            del y
-        except Exception as e:  # a witness must never cost the bench line
-            check = {"error": str(e)[:200]}
-
     peak, peak_src = measured_peak()
     # algorithmic bytes (SURVEY.md 8d / DESIGN.md): int32 connectivity + each vertex coordinate once + coefficients +
     # each stored value written once
-    nldof_sum = dm.stride * mesh.n_cells if mesh.n_quad == 0 or mesh.n_tria == 0 else None
     nsf_t, nsf_q = {1: (3, 4), 2: (6, 9), 3: (10, 16)}[degree]
-    conn = 4.0 * (nsf_t * mesh.n_tria + nsf_q * mesh.n_quad)
-    alg_bytes = conn + 16.0 * mesh.n_nodes + coef_bytes + 8.0 * pat.nnz
+    conn = 4.0 * (nsf_t * n_tria + nsf_q * n_quad)
+    alg_bytes = conn + 16.0 * n_nodes + coef_bytes + 8.0 * nnz_global
     # per launch (= per rank for N > 1) the kernel covers 1/world of the rows
     alg_bytes_launch = alg_bytes / world
     achieved = alg_bytes_launch / (ms_per_step * 1e-3) / 1e9
@@ -506,32 +501,48 @@ def main():
         try:
             tj = json.load(open(tp)).get(args.workload + ":" + args.algo)
             if tj:
-                traffic = tj["dram_bytes_per_cell"] * mesh.n_cells / world
+                traffic = tj["dram_bytes_per_cell"] * n_cells / world
         except Exception:
             pass
+    parallelism = {None: "1 GPU",
+                   "owned": "distributed ownership: Morton cell ranges x%d, every rank holds only its cells + one-cell halo (local indices, "
+                            "own symbolic pass), owner-computes rows, no data-path collective" % world,
+                   "exchange": "Morton cell partition x%d on a replicated pattern, interface rows to owner by one NCCL all-to-all-v "
+                               "overlapped with interior rows%s" % (world, ", step replayed as a CUDA graph" if use_graph else ""),
+                   "owner": "Morton cell partition x%d on a replicated pattern, owner-computes rows (halo cells recomputed, no data-path "
+                            "collective)" % world,
+                   "owner_rows": "%d contiguous row blocks of equal nnz on a replicated pattern, owner-computes (halo cells recomputed, no "
+                                 "data-path collective)" % world}[dist_mode]
     out = {
-        "metric": "cells assembled/sec into CSR", "value": mesh.n_cells / (ms_per_step * 1e-3), "unit": "cells/s",
+        "metric": "cells assembled/sec into CSR", "value": n_cells / (ms_per_step * 1e-3), "unit": "cells/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "cells": mesh.n_cells, "dofs": dm.num_dofs, "nnz": pat.nnz, "degree": degree,
+        "config": {"workload": desc, "cells": n_cells, "dofs": n_dofs, "nnz": nnz_global, "degree": degree,
                    "algo": args.algo, "l2": "inputs+outputs per step (%.2f GB) exceed the 126 MB L2; no explicit flush" % (alg_bytes / 1e9),
-                   "parallelism": "1 GPU" if world == 1 else (
-                       "Morton cell partition x%d, interface rows to owner by one NCCL all-to-all-v overlapped with interior rows%s" % (world, ", step replayed as a CUDA graph" if use_graph else "")
-                       if asm.mode == "exchange" else
-                       "Morton cell partition x%d, owner-computes rows (halo cells recomputed, no data-path collective)" % world
-                       if asm.mode == "owner" else
-                       "%d contiguous row blocks of equal nnz, owner-computes (halo cells recomputed, no data-path collective)" % world),
+                   "parallelism": parallelism,
                    "symbolic_pass_s": round(t_sym, 3), "setup_s": round(t_setup, 3), "partition_s": round(t_part, 3)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_cell": alg_bytes / mesh.n_cells,
+                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_cell": alg_bytes / n_cells,
                      "kernel": kernel_name},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(t_timed0, max(t_timed1, t_end)),
     }
+    if rank_facts is not None:
+        out["config"]["per_rank"] = rank_facts
     if check is not None:
         out["check"] = check
     if e2e is not None:
         out["e2e"] = e2e
+    # the other BASELINE configurations that fit one GPU, each as a short measured line (ms, roofline fraction, witness)
+    if world == 1 and args.workload == "c5_1e8" and args.algo == "auto" and not args.no_other_configs:
+        del values, pat, dm, mesh
+        others = {}
+        for name in ("c2", "c3", "c4"):
+            try:
+                others[name] = short_run(ctx, lf, np, name, peak)
+            except Exception as e:
+                others[name] = {"error": str(e)[:200]}
+        out["other_configs"] = others
     if not args.no_cpu_baseline:
         ncpu = 1000
         cells, sec = cpu_reference_sample(ncpu)
@@ -540,6 +551,98 @@ def main():
                                          "%.2f s; host has %d cores, the reference is serial" % (ncpu, cells, sec, os.cpu_count())}
     print_result(out)
     teardown()
+
+
+def kernel_of(workload, kind, degree, algo):
+    """Name of the kernel that dominates the step (what LFGPU_ALGO_AUTO runs, lehrfempp_b200/csrc/assemble.cu)."""
+    tri = kind == "tp_tria" or kind.startswith("refined:") or kind == "delaunay"
+    row_kernels = {1: "k_assemble_p1_fan", 2: "k_p2_vertex_rows + k_p2_edge_rows", 3: "k_p3_vertex_rows + k_p3_edge_rows + k_p3_cell_rows"}
+    if algo in ("auto", "fan"):
+        if tri and degree in AUTO_ROW_DEGREES:
+            return row_kernels[degree]
+        return "k_assemble_p1_rows" if degree == 1 else "k_assemble_items"
+    return {"gather": "k_assemble_items", "atomic": "k_assemble_atomic"}[algo]
+
+
+def build_mesh(ctx, np, kind, n):
+    if kind == "tp_tria":
+        return ctx.mesh_tp_tria(n, n)
+    if kind.startswith("refined:"):
+        # MeshHierarchy-refined mesh (BASELINE config 4): builder mesh + regular refinement steps with the reference's numbering
+        mesh = ctx.mesh_tp_tria(n, n)
+        for _ in range(int(kind.split(":")[1])):
+            mesh = mesh.refine_regular()
+        return mesh
+    if kind == "delaunay":
+        from scipy.spatial import Delaunay
+        pts = np.random.default_rng(12345).random((n, 2))
+        tri = Delaunay(pts).simplices
+        a, b, c = pts[tri[:, 0]], pts[tri[:, 1]], pts[tri[:, 2]]
+        area2 = np.abs((b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (c[:, 0] - a[:, 0]) * (b[:, 1] - a[:, 1]))
+        longest2 = np.maximum.reduce([((b - a) ** 2).sum(1), ((c - b) ** 2).sum(1), ((a - c) ** 2).sum(1)])
+        tri = tri[area2 > 0.05 * longest2]  # slivers along the convex hull
+        used = np.unique(tri)
+        remap = np.full(n, -1, dtype=np.int64)
+        remap[used] = np.arange(used.size)
+        cn = np.full((tri.shape[0], 4), 0xFFFFFFFF, dtype=np.uint32)
+        cn[:, :3] = remap[tri]
+        return ctx.mesh_upload(pts[used], cn)
+    return ctx.mesh_hybrid(n, 0.2, 12345)
+
+
+def make_coeffs(ctx, lf, workload, mesh, degree):
+    """(alpha, gamma, bytes of coefficient data one pass reads) of the workload on `mesh` (the whole mesh or a rank's share)."""
+    if workload == "c2":
+        stride = 4
+        xy = mesh.qp_coords(degree, stride).to_host().reshape(mesh.n_cells, stride, 2)
+        r2 = xy[..., 0] ** 2 + xy[..., 1] ** 2
+        return (lf.Coeff.per_qp(ctx.to_device(1.0 + r2), stride), lf.Coeff.per_qp(ctx.to_device(1.0 / (1.0 + r2)), stride),
+                2 * 8.0 * (3 * mesh.n_tria + 4 * mesh.n_quad))
+    if workload in ("c4s", "c4", "c4_27m", "c4_full"):
+        return lf.Coeff.const(1.0), lf.Coeff.const(1.0), 0.0
+    return lf.Coeff.const(1.0), lf.Coeff.const(0.0), 0.0
+
+
+def witness_record(workload, wmax, wsum, world):
+    where = "" if world == 1 else " (every rank on the rows it owns; max / sum over %d ranks)" % world
+    if workload in ("c4s", "c4", "c4_27m", "c4_full"):
+        return {"what": "1^T A 1 for stiffness + mass with alpha = gamma = 1 on the unit square" + where, "value": wsum, "expected": 1.0}
+    if workload == "c2":
+        from scipy.integrate import dblquad
+        expected = dblquad(lambda yy, xx: 1.0 / (1.0 + xx * xx + yy * yy), 0.0, 1.0, 0.0, 1.0)[0]
+        return {"what": "1^T A 1 = integral of gamma = 1 / (1 + |x|^2) over the unit square (quadrature error O(h^2))" + where,
+                "value": wsum, "expected": expected}
+    return {"what": "max |A 1| for the Laplacian (constants are in its kernel; entries are O(1))" + where, "value": wmax, "expected": 0.0}
+
+
+def short_run(ctx, lf, np, workload, peak, steps=20, warmup=3):
+    """One of the other single-GPU BASELINE configurations, measured like the main one (CUDA events on the ctx stream, inputs
+    resident, working set far above L2) but with few steps: ms per pass, fraction of the HBM roofline, witness."""
+    desc, kind, n, degree = WORKLOADS[workload]
+    mesh = build_mesh(ctx, np, kind, n)
+    dm = mesh.dofmap_lagrange(degree)
+    pat = dm.symbolic(major=lf.ROW_MAJOR)
+    alpha, gamma, coef_bytes = make_coeffs(ctx, lf, workload, mesh, degree)
+    values = ctx.empty(pat.nnz)
+    for _ in range(warmup):
+        pat.assemble_reaction_diffusion(degree, alpha, gamma, out=values)
+    ctx.synchronize()
+    e0, e1 = ctx.event(), ctx.event()
+    ctx.record(e0)
+    for _ in range(steps):
+        pat.assemble_reaction_diffusion(degree, alpha, gamma, out=values)
+    ctx.record(e1)
+    ms = ctx.elapsed_ms(e0, e1) / steps
+    y = pat.spmv(values, ctx.to_device(np.ones(dm.num_dofs))).to_host()
+    check = witness_record(workload, float(np.abs(y).max()), float(y.sum()), 1)
+    nsf_t, nsf_q = {1: (3, 4), 2: (6, 9), 3: (10, 16)}[degree]
+    alg = 4.0 * (nsf_t * mesh.n_tria + nsf_q * mesh.n_quad) + 16.0 * mesh.n_nodes + coef_bytes + 8.0 * pat.nnz
+    achieved = alg / (ms * 1e-3) / 1e9
+    return {"workload": desc, "cells": mesh.n_cells, "nnz": pat.nnz, "ms_per_step": ms, "steps": steps, "value": mesh.n_cells / (ms * 1e-3),
+            "unit": "cells/s", "roofline": {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                                            "algorithmic_bytes_per_cell": alg / mesh.n_cells,
+                                            "kernel": kernel_of(workload, kind, degree, "auto")},
+            "check": check}
 
 
 if __name__ == "__main__":

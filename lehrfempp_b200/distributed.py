@@ -282,3 +282,54 @@ class DistributedAssembler:
         for r in owned:
             m[outer_host[r]:outer_host[r + 1]] = True
         return m
+
+
+class OwnedAssembler:
+    """Distributed ownership (BASELINE.json north star: "Morton-ordered cell ranges, each GPU owning the matrix rows for its
+    cells"): this rank keeps ONLY its sub-problem -- its cells plus the one-cell halo around the dofs it owns, with local indices
+    (lehrfempp_b200/csrc/partition.cu) -- and runs symbolic pass, plans and numeric kernels on it unchanged.  Owner-computes: the
+    rows a rank owns are complete without any exchange (halo cells are recomputed), so the data path has no collective; setup has
+    none either, because the partition is a deterministic function of the replicated mesh.  Memory and symbolic time per GPU fall
+    like 1/N, and int32 indices only have to address 1/N of the matrix (config 4: 2.5e9 stored values globally).
+
+    After construction the caller may drop the global mesh / dof map: nothing here refers to them."""
+
+    def __init__(self, ctx, mesh, dofmap, degree, rank, world, major=None, halo=True):
+        import time
+
+        import lehrfempp_b200 as lf
+        self.lf, self.ctx, self.degree, self.rank, self.world = lf, ctx, degree, rank, world
+        self.mode = "owned"
+        self.global_cells, self.global_dofs = mesh.n_cells, dofmap.num_dofs
+        t0 = time.time()
+        part, owner = dofmap.partition_morton(world)
+        self.sub = dofmap.submesh(part, owner, rank, halo=halo)
+        del part, owner
+        ctx.synchronize()
+        self.partition_s = time.time() - t0
+        t0 = time.time()
+        self.pattern = self.sub.dofmap.symbolic(major=lf.ROW_MAJOR if major is None else major)
+        ctx.synchronize()
+        self.symbolic_s = time.time() - t0
+        own = self.sub.owned.to_host().astype(bool)
+        self.n_owned_rows = int(own.sum())
+        outer = self.pattern.download()[0]
+        self.owned_nnz = int((np.diff(outer)[own]).sum())
+        self._own = own
+        self.mesh = self.sub.mesh
+        self.graph = None
+
+    def assemble(self, alpha, gamma, values=None, qr_tria=None, qr_quad=None):
+        """One numeric pass over the sub-problem; the rows flagged in `self.sub.owned` are final."""
+        return self.pattern.assemble_reaction_diffusion(self.degree, alpha, gamma, qr_tria, qr_quad, out=values)
+
+    def owned_rows_global(self):
+        """(global row ids, local row ids) of the rows this rank owns, ascending."""
+        l2g = self.sub.l2g_dofs()
+        rows_l = np.nonzero(self._own)[0]
+        return l2g[rows_l], rows_l
+
+    def witness(self, values):
+        """(max |A 1| over the owned rows, sum of A 1 over the owned rows): size-independent checks of the distributed matrix."""
+        y = self.pattern.spmv(values, self.ctx.to_device(np.ones(self.pattern.cols))).to_host()[self._own]
+        return (float(np.abs(y).max()) if y.size else 0.0), float(y.sum())

@@ -29,7 +29,7 @@ def run_bench(*args):
     return json.loads(lines[0])
 
 
-KERNEL = {"c5_1e8": "k_assemble_p1_fan", "c1": "k_assemble_p1_fan", "c2": "k_assemble_items", "c3": "k_p2_vertex_rows + k_p2_edge_rows",
+KERNEL = {"c5_1e8": "k_assemble_p1_fan", "c1": "k_assemble_p1_fan", "c2": "k_assemble_p1_rows", "c3": "k_p2_vertex_rows + k_p2_edge_rows",
           "c4": "k_p3_vertex_rows + k_p3_edge_rows + k_p3_cell_rows", "c4s": "k_p3_vertex_rows + k_p3_edge_rows + k_p3_cell_rows",
           "c4_27m": "k_p3_vertex_rows + k_p3_edge_rows + k_p3_cell_rows"}
 
@@ -79,3 +79,14 @@ def test_reference_arm_line():
     assert out["impl"] == "reference" and out["value"] > 0 and out["cpu_baseline"]["kind"] == "port" and out["cpu_baseline"]["cores"] == 1
     assert out["e2e"] == {"value": out["value"], "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert out["cpu_baseline"]["all_cores"]["cores"] >= 1
+
+
+def test_default_line_carries_the_other_configs():
+    out = run_bench("--steps", "3", "--no-cpu-baseline", "--no-e2e")
+    check_line(out, 3)
+    oc = out["other_configs"]
+    assert set(oc) == {"c2", "c3", "c4"}
+    for name, rec in oc.items():
+        assert "error" not in rec, rec
+        assert rec["ms_per_step"] > 0 and 0 < rec["roofline"]["frac"] and {"what", "value", "expected"} <= set(rec["check"])
+    assert oc["c2"]["roofline"]["kernel"] == "k_assemble_p1_rows"
