@@ -111,7 +111,9 @@ int lfgpu_mesh_counts(const lfgpu_mesh* mesh, int64_t* n_nodes, int64_t* n_edges
 /* every output nullable; layouts as in lfgpu_mesh_upload, cell_edges [n_cells][4], cell_edge_ori int8 [n_cells][4] (+1/-1) */
 int lfgpu_mesh_download(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, uint8_t* cell_type, uint32_t* cell_nodes, double* cell_coords,
                         uint32_t* cell_edges, int8_t* cell_edge_ori, uint32_t* edge_nodes, double* node_coords);
-/* replace the node positions (per-step input of a moving-mesh / re-assembly loop); host array [n_nodes][2] */
+/* replace the node positions (per-step input of a moving-mesh / re-assembly loop); host array [n_nodes][2].  The copy is
+ * asynchronous on the ctx stream: a page-locked host buffer must stay valid until lfgpu_ctx_synchronize.  The new geometry is
+ * checked like that of lfgpu_mesh_upload; a degenerate cell makes the NEXT lfgpu_ctx_synchronize return LFGPU_ERR_DEGENERATE. */
 int lfgpu_mesh_update_node_coords(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const double* node_coords);
 void lfgpu_mesh_destroy(lfgpu_mesh* mesh);
 

@@ -196,39 +196,40 @@ __device__ __forceinline__ void tensor_row(const TabView& T, int a, double m00, 
   }
 }
 
-// The same with the reference tensors in CONSTANT memory (the table blob of the current call, uploaded by the host
-// before the launch).  ncu on the P2 workload showed the item kernel limited by the L1/shared-memory pipe (84 % busy):
-// 24-40 table loads per item came from shared memory plus a per-block copy of the tables; threads of a warp share `a`
-// (items are ordered by rank, local index, dof), so the constant cache serves them as broadcasts and the LSU pipe is
-// left to the accumulation rounds.
-constexpr int kConstTableDoubles = 4096;
-__constant__ double c_tables[kConstTableDoubles];
+// The same with the reference tensors in the kernel's PARAMETER block (constant bank).  ncu on the P2 workload showed the item
+// kernel limited by the L1/shared-memory pipe (84 % busy): 24-40 table loads per item came from shared memory plus a per-block
+// copy of the tables; threads of a warp share `a` (items are ordered by rank, local index, dof), so the constant cache serves
+// them as broadcasts and the LSU pipe is left to the accumulation rounds.  A by-value parameter instead of a module-wide
+// __constant__ array: every launch carries its own copy, so two contexts (or streams) assembling different degrees or rules
+// on one device cannot overwrite each other's tables, and nothing is copied from a host stack buffer asynchronously.
+constexpr int kParamTensorNsf = 10;  // triangles up to FeLagrangeO3Tria: 5 tensors x 100 doubles = 4000 bytes
+struct KTensors {
+  double k[5 * kParamTensorNsf * kParamTensorNsf];  // k00 | k01 | k10 | k11 | m, each [nsf * nsf] row-major, packed for the nsf in use
+};
 
 template <int NSF>
-__device__ __forceinline__ void tensor_row_const(int kbase, int nsf, int a, double m00, double m01, double m10, double m11, double gm,
+__device__ __forceinline__ void tensor_row_const(const KTensors& KT, int nsf, int a, double m00, double m01, double m10, double m11, double gm,
                                                  bool sym, double (&acc)[NSF]) {
   const int nn = nsf * nsf;
-  const int r0 = kbase + a * nsf;  // k00; then k01, k10, k11, m at multiples of nn (make_view)
+  const int r0 = a * nsf;  // k00; then k01, k10, k11, m at multiples of nn
   if (sym) {
     if (gm == 0.0) {
 #pragma unroll
       for (int b = 0; b < NSF; ++b) {
-        if (b < nsf) acc[b] = m00 * c_tables[r0 + b] + m01 * (c_tables[r0 + 2 * nn + b] + c_tables[r0 + nn + b]) + m11 * c_tables[r0 + 3 * nn + b];
+        if (b < nsf) acc[b] = m00 * KT.k[r0 + b] + m01 * (KT.k[r0 + 2 * nn + b] + KT.k[r0 + nn + b]) + m11 * KT.k[r0 + 3 * nn + b];
       }
     } else {
 #pragma unroll
       for (int b = 0; b < NSF; ++b) {
         if (b < nsf)
-          acc[b] = m00 * c_tables[r0 + b] + m01 * (c_tables[r0 + 2 * nn + b] + c_tables[r0 + nn + b]) + m11 * c_tables[r0 + 3 * nn + b] +
-                   gm * c_tables[r0 + 4 * nn + b];
+          acc[b] = m00 * KT.k[r0 + b] + m01 * (KT.k[r0 + 2 * nn + b] + KT.k[r0 + nn + b]) + m11 * KT.k[r0 + 3 * nn + b] + gm * KT.k[r0 + 4 * nn + b];
       }
     }
   } else {
 #pragma unroll
     for (int b = 0; b < NSF; ++b) {
       if (b < nsf)
-        acc[b] = m00 * c_tables[r0 + b] + m01 * c_tables[r0 + 2 * nn + b] + m10 * c_tables[r0 + nn + b] + m11 * c_tables[r0 + 3 * nn + b] +
-                 gm * c_tables[r0 + 4 * nn + b];
+        acc[b] = m00 * KT.k[r0 + b] + m01 * KT.k[r0 + 2 * nn + b] + m10 * KT.k[r0 + nn + b] + m11 * KT.k[r0 + 3 * nn + b] + gm * KT.k[r0 + 4 * nn + b];
     }
   }
 }
@@ -501,7 +502,7 @@ __global__ void __launch_bounds__(kItemThreads, MINB > 0 ? MINB : (TENSOR_ONLY ?
                                                            const uint2* __restrict__ item_sorted, DevCoeff alpha, DevCoeff gamma,
                                                            const uint8_t* __restrict__ active, bool transpose_alpha, double beta,
                                                            const double* __restrict__ cell_metric_tab, double* __restrict__ values,
-                                                           bool const_tables) {
+                                                           bool const_tables, const __grid_constant__ KTensors KT) {
   extern __shared__ double smem[];
   const int tid = threadIdx.x;
   const int4 bh = __ldg(blk_hdr + blockIdx.x);
@@ -547,8 +548,7 @@ __global__ void __launch_bounds__(kItemThreads, MINB > 0 ? MINB : (TENSOR_ONLY ?
         }
         nsf = hdr.nsf[0];
         if (ctab) {
-          const int kbase = hdr.off[0] + 3 * hdr.nq[0] + 3 * nsf * hdr.nq[0];
-          tensor_row_const<NSF>(kbase, nsf, a, m00, m01, m10, m11, gm, sym, acc);
+          tensor_row_const<NSF>(KT, nsf, a, m00, m01, m10, m11, gm, sym, acc);
         } else {
           tensor_row<NSF>(tt, a, m00, m01, m10, m11, gm, sym, acc);
         }
@@ -627,12 +627,13 @@ __global__ void __launch_bounds__(256) k_load_atomic(Tables hdr, const double* _
 __global__ void __launch_bounds__(256) k_load_gather(Tables hdr, const double* __restrict__ blob, MeshView mv, int64_t n_dofs,
                                                      const int32_t* __restrict__ ptr, const uint32_t* __restrict__ items, DevCoeff f,
                                                      const uint8_t* __restrict__ active, double beta, double* __restrict__ vec,
-                                                     int* __restrict__ flags) {
+                                                     int* __restrict__ flags, const int32_t* __restrict__ row_list) {
   extern __shared__ double smem[];
   TabView tt, tq;
   load_tables(hdr, blob, smem, tt, tq);
-  const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (r >= n_dofs) return;
+  const int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t0 >= n_dofs) return;  // n_dofs = number of listed rows when a list is given
+  const int64_t r = row_list != nullptr ? row_list[t0] : t0;
   double sum = (beta == 0.0) ? 0.0 : beta * vec[r];
   const int32_t t1 = ptr[r + 1];
   for (int32_t t = ptr[r]; t < t1; ++t) {
@@ -836,32 +837,42 @@ int launch_matrix(lfgpu_ctx* ctx, const HostTables& ht, const double* d_blob, co
         }
         // metric route: reference tensors through the constant cache (LFGPU_CONST_TABLES=0 keeps them in shared memory)
         static const bool ctab_env = [] { const char* e = std::getenv("LFGPU_CONST_TABLES"); return e == nullptr || e[0] != '0'; }();
-        const bool const_tables = ctab_env && metric != nullptr && ht.hdr.total <= kConstTableDoubles;
-        if (const_tables)
-          LFGPU_CUDA_CHECK(ctx, cudaMemcpyToSymbolAsync(c_tables, ht.blob.data(), sizeof(double) * ht.hdr.total, 0, cudaMemcpyHostToDevice,
-                                                        ctx->stream));
+        const int nsf0 = ht.hdr.nsf[0];
+        const bool const_tables = ctab_env && metric != nullptr && nsf0 <= kParamTensorNsf;
+        KTensors KT;
+        if (const_tables) {
+          const double* k00 = ht.blob.data() + ht.hdr.off[0] + 3 * ht.hdr.nq[0] + 3 * nsf0 * ht.hdr.nq[0];
+          std::copy(k00, k00 + 5 * nsf0 * nsf0, KT.k);
+        }
         ki<<<static_cast<unsigned>(p->n_item_blocks), kItemThreads, smem_i, ctx->stream>>>(
             ht.hdr, d_blob, table_mask, mv, static_cast<const int4*>(p->blk_hdr), p->pos_row, static_cast<const P*>(p->pos_item),
-            static_cast<const uint2*>(p->item_sorted), alpha, gamma, active, transpose_alpha, beta, metric, d_values, const_tables);
+            static_cast<const uint2*>(p->item_sorted), alpha, gamma, active, transpose_alpha, beta, metric, d_values, const_tables, KT);
         LFGPU_LAUNCH_CHECK(ctx);
         return LFGPU_OK;
       }
     }
-    constexpr int threads = 128;
     // shared-memory image of the block's value range: exact maximum over the blocks of consecutive rows (symbolic pass)
-    // or, with a row list, the safe bound threads * longest row
-    const int64_t image_len = row_list != nullptr ? static_cast<int64_t>(threads) * p->max_row_len : p->max_block_nnz;
-    const size_t smem = tab_bytes + sizeof(double) * static_cast<size_t>((image_len + 15) & ~15);
-    if (smem > 200 * 1024) LFGPU_FAIL(ctx, LFGPU_ERR_UNSUPPORTED, "rows too long for the gather kernel; use LFGPU_ALGO_ATOMIC");
-    auto kern = tensor_only ? k_assemble_gather<NSF, P, threads, true> : k_assemble_gather<NSF, P, threads, false>;
-    LFGPU_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    // or, with a row list, the safe bound threads * longest row; long rows (a vertex of high valence) take fewer threads per
+    // block instead of failing
     const int64_t rows = row_list != nullptr ? n_rows : p->n_outer;
-    if (rows > 0) {
-      kern<<<static_cast<unsigned>(cdiv(rows, threads)), threads, smem, ctx->stream>>>(
-          ht.hdr, d_blob, table_mask, mv, rows, p->o_stride, p->pos_row, p->outer, p->adj_ptr, p->adj,
-          static_cast<const P*>(p->pos), alpha, gamma, active, transpose_alpha, beta, row_list, d_values, d_flags);
-    }
-    LFGPU_LAUNCH_CHECK(ctx);
+    auto launch = [&](auto kern, int threads) -> int {
+      const int64_t image_len = row_list != nullptr ? static_cast<int64_t>(threads) * p->max_row_len
+                                                    : (threads == 128 ? static_cast<int64_t>(p->max_block_nnz) : static_cast<int64_t>(threads) * p->max_row_len);
+      const size_t smem = tab_bytes + sizeof(double) * static_cast<size_t>((image_len + 15) & ~15);
+      if (smem > 200 * 1024) return 1;
+      LFGPU_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      if (rows > 0) {
+        kern<<<static_cast<unsigned>(cdiv(rows, threads)), threads, smem, ctx->stream>>>(
+            ht.hdr, d_blob, table_mask, mv, rows, p->o_stride, p->pos_row, p->outer, p->adj_ptr, p->adj, static_cast<const P*>(p->pos), alpha,
+            gamma, active, transpose_alpha, beta, row_list, d_values, d_flags);
+      }
+      LFGPU_LAUNCH_CHECK(ctx);
+      return LFGPU_OK;
+    };
+    int lr = tensor_only ? launch(k_assemble_gather<NSF, P, 128, true>, 128) : launch(k_assemble_gather<NSF, P, 128, false>, 128);
+    if (lr == 1) lr = tensor_only ? launch(k_assemble_gather<NSF, P, 32, true>, 32) : launch(k_assemble_gather<NSF, P, 32, false>, 32);
+    if (lr == 1) LFGPU_FAIL(ctx, LFGPU_ERR_UNSUPPORTED, "rows too long for the gather kernel; use LFGPU_ALGO_ATOMIC");
+    if (lr != LFGPU_OK) return lr;
   }
   return LFGPU_OK;
 }
@@ -1092,9 +1103,32 @@ int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofm
     const MeshView mvg{mesh->node_coords, mesh->cell_nodes, mesh->cell_coords};
     const size_t tbg = sizeof(double) * ((ht.hdr.total + 1) & ~1);
     k_load_gather<<<static_cast<unsigned>(cdiv(dofmap->n_dofs, 256)), 256, tbg, ctx->stream>>>(
-        ht.hdr, blob.d, mvg, dofmap->n_dofs, dofmap->g_ptr, dofmap->g_items, df, active, beta, d_vec, d_flags);
+        ht.hdr, blob.d, mvg, dofmap->n_dofs, dofmap->g_ptr, dofmap->g_items, df, active, beta, d_vec, d_flags, nullptr);
     LFGPU_LAUNCH_CHECK(ctx);
     return LFGPU_OK;
+  }
+  // P1 triangles, constant source, every cell active: the vertex-ring kernel (assemble_p1.cu), deterministic, no atomics;
+  // rows that are not a single fan go through the gather kernel.  LFGPU_LOAD_FAN=0 keeps the atomic kernel.
+  static const bool lfan_env = [] { const char* e = std::getenv("LFGPU_LOAD_FAN"); return e == nullptr || e[0] != '0'; }();
+  if (algo == LFGPU_ALGO_AUTO && lfan_env && degree == 1 && df.kind == LFGPU_COEFF_CONST && active == nullptr && mesh->n_quad == 0 &&
+      mesh->cell_coords == nullptr && ht.hdr.nsf[0] == 3) {
+    const int nq = ht.hdr.nq[0];
+    const double* l = ht.blob.data() + ht.hdr.off[0] + 3 * nq + 3 * 3 * nq + 5 * 9;  // pack_type: ... k00 k01 k10 k11 m | l
+    if (std::fabs(l[1] - l[0]) <= 1e-15 && std::fabs(l[2] - l[0]) <= 1e-15) {
+      int handled = 0;
+      if ((rc = p1_load_fan(ctx, mesh, dofmap, df.c[0] * l[0], beta, d_vec, &handled)) != LFGPU_OK) return rc;
+      if (handled) {
+        if (dofmap->n_lv_irregular > 0) {
+          const MeshView mvg{mesh->node_coords, mesh->cell_nodes, mesh->cell_coords};
+          const size_t tbg = sizeof(double) * ((ht.hdr.total + 1) & ~1);
+          k_load_gather<<<static_cast<unsigned>(cdiv(dofmap->n_lv_irregular, 256)), 256, tbg, ctx->stream>>>(
+              ht.hdr, blob.d, mvg, dofmap->n_lv_irregular, dofmap->g_ptr, dofmap->g_items, df, active, beta, d_vec, d_flags,
+              dofmap->lv_irregular);
+          LFGPU_LAUNCH_CHECK(ctx);
+        }
+        return LFGPU_OK;
+      }
+    }
   }
   if (beta == 0.0) {
     LFGPU_CUDA_CHECK(ctx, cudaMemsetAsync(d_vec, 0, sizeof(double) * dofmap->n_dofs, ctx->stream));

@@ -71,6 +71,12 @@ const char* lfgpu_last_error(const lfgpu_ctx* ctx) {
 int lfgpu_ctx_synchronize(lfgpu_ctx* ctx) {
   if (ctx == nullptr) return LFGPU_ERR_INVALID;
   LFGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->geom_check_pending) {  // degeneracy check queued by lfgpu_mesh_update_node_coords
+    ctx->geom_check_pending = false;
+    int h[2] = {0, 0};
+    LFGPU_CUDA_CHECK(ctx, cudaMemcpy(h, static_cast<char*>(ctx->d_scratch) + 1024, sizeof(h), cudaMemcpyDeviceToHost));
+    if (h[1]) LFGPU_FAIL(ctx, LFGPU_ERR_DEGENERATE, "degenerate cell geometry after a coordinate update (collapsed edge or zero area)");
+  }
   return LFGPU_OK;
 }
 

@@ -309,6 +309,10 @@ void lfgpu_dofmap_destroy(lfgpu_dofmap* d) {
   cudaFree(d->n_ldof);
   cudaFree(d->g_ptr);
   cudaFree(d->g_items);
+  cudaFree(d->lv_nbr);
+  cudaFree(d->lv_nbr16);
+  cudaFree(d->lv_info);
+  cudaFree(d->lv_irregular);
   delete d;
 }
 

@@ -126,8 +126,8 @@ __global__ void k_edge_load(int64_t n_edges, const uint32_t* __restrict__ edge_n
 // owns the DofHandler uses (it passes the ACTIVE edges only, typically a boundary part): seg_xy [n][4] = x0 y0 x1 y1,
 // seg_dofs [n][nsf] = GlobalDofIndices(edge).
 __global__ void k_segment_mass(int64_t n, const double* __restrict__ seg_xy, const int32_t* __restrict__ seg_dofs, SegTable T, EdgeCoeff G,
-                               bool row_major, const int32_t* __restrict__ outer, const int32_t* __restrict__ inner,
-                               double* __restrict__ values, int* __restrict__ flags) {
+                               bool row_major, const int32_t* __restrict__ outer, const int32_t* __restrict__ inner, int64_t n_outer,
+                               int64_t n_inner, double* __restrict__ values, int* __restrict__ flags) {
   const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (e >= n) return;
   const double dx = seg_xy[4 * e + 2] - seg_xy[4 * e], dy = seg_xy[4 * e + 3] - seg_xy[4 * e + 1];
@@ -140,6 +140,10 @@ __global__ void k_segment_mass(int64_t n, const double* __restrict__ seg_xy, con
       double m = 0.0;
       for (int k = 0; k < T.nq; ++k) m += (T.phi[a * kMaxSegNq + k] * T.phi[b * kMaxSegNq + k]) * ((T.w[k] * len) * eval_edge_coeff(G, e, k));
       const int32_t o = row_major ? da : db, i = row_major ? db : da;
+      if (o < 0 || o >= n_outer || i < 0 || i >= n_inner) {  // a dof outside the matrix: reported like a missing entry
+        flags[0] = 1;
+        continue;
+      }
       const int slot = find_slot(inner, outer[o], outer[o + 1], i);
       if (slot < 0) {
         flags[0] = 1;
@@ -327,7 +331,7 @@ int lfgpu_assemble_segment_mass(lfgpu_ctx* ctx, const lfgpu_pattern* p, int degr
   int* d_flags = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 768);
   LFGPU_CUDA_CHECK(ctx, cudaMemsetAsync(d_flags, 0, sizeof(int), ctx->stream));
   k_segment_mass<<<static_cast<unsigned>(cdiv(n_segments, kThreads)), kThreads, 0, ctx->stream>>>(
-      n_segments, d_seg_xy, d_seg_dofs, T, G, p->major == LFGPU_ROW_MAJOR, p->outer, p->inner, d_values, d_flags);
+      n_segments, d_seg_xy, d_seg_dofs, T, G, p->major == LFGPU_ROW_MAJOR, p->outer, p->inner, p->n_outer, p->n_inner, d_values, d_flags);
   LFGPU_LAUNCH_CHECK(ctx);
   int h = 0;
   LFGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(&h, d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

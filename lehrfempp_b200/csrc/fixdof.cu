@@ -93,6 +93,10 @@ int fix_impl(lfgpu_ctx* ctx, const lfgpu_pattern* p, double* d_values, double* d
   cudaStream_t st = ctx->stream;
   const int64_t N = p->n_outer, nnz = p->nnz;
   const unsigned gn = static_cast<unsigned>(cdiv(N, kThreads));
+  if (N == 0) {  // nothing to fix: no launch with an empty grid
+    if (nnz_out != nullptr) *nnz_out = 0;
+    return LFGPU_OK;
+  }
   // 1. right-hand side
   if (!rows_only) {
     if (p->major == LFGPU_ROW_MAJOR) {
@@ -121,21 +125,29 @@ int fix_impl(lfgpu_ctx* ctx, const lfgpu_pattern* p, double* d_values, double* d
   const bool by_inner = !rows_only || p->major != LFGPU_ROW_MAJOR;  // inner index is a row
   k_mark<<<gn, kThreads, 0, st>>>(N, p->outer, p->inner, d_values, d_fixed, keep, d_flags, by_outer, by_inner);
   ctx->launches++;
+  e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    cleanup();
+    LFGPU_CUDA_CHECK(ctx, e);
+  }
   int h_flags[2] = {0, 0};
   if (compact) {
     e = cudaMalloc(&keep32, sizeof(int32_t) * (nnz + 1));
     if (e == cudaSuccess) e = cudaMalloc(&scan, sizeof(int32_t) * (nnz + 1));
     if (e == cudaSuccess) e = cudaMalloc(&d_num, sizeof(int64_t));
     if (e == cudaSuccess) {
-      k_widen<<<static_cast<unsigned>(cdiv(nnz, kThreads)), kThreads, 0, st>>>(nnz, keep, keep32);
-      ctx->launches++;
+      if (nnz > 0) {
+        k_widen<<<static_cast<unsigned>(cdiv(nnz, kThreads)), kThreads, 0, st>>>(nnz, keep, keep32);
+        ctx->launches++;
+        e = cudaGetLastError();
+      }
       size_t tb = 0, tb2 = 0, tb3 = 0;
-      cub::DeviceScan::ExclusiveSum(nullptr, tb, keep32, scan, nnz, st);
+      if (e == cudaSuccess) cub::DeviceScan::ExclusiveSum(nullptr, tb, keep32, scan, nnz, st);
       cub::DeviceSelect::Flagged(nullptr, tb2, p->inner, keep, d_inner_out, d_num, nnz, st);
       cub::DeviceSelect::Flagged(nullptr, tb3, d_values, keep, d_values_out, d_num, nnz, st);
       tb = tb > tb2 ? tb : tb2;
       tb = tb > tb3 ? tb : tb3;
-      e = cudaMalloc(&tmp, tb);
+      if (e == cudaSuccess) e = cudaMalloc(&tmp, tb > 0 ? tb : 1);
       if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tb, keep32, scan, nnz, st);
       if (e == cudaSuccess) e = cub::DeviceSelect::Flagged(tmp, tb, p->inner, keep, d_inner_out, d_num, nnz, st);
       if (e == cudaSuccess) e = cub::DeviceSelect::Flagged(tmp, tb, d_values, keep, d_values_out, d_num, nnz, st);
@@ -145,6 +157,7 @@ int fix_impl(lfgpu_ctx* ctx, const lfgpu_pattern* p, double* d_values, double* d
       if (e == cudaSuccess) {
         k_new_outer<<<static_cast<unsigned>(cdiv(N + 1, kThreads)), kThreads, 0, st>>>(N + 1, p->outer, scan, nnz, static_cast<int32_t>(kept), d_outer_out);
         ctx->launches++;
+        e = cudaGetLastError();
         *nnz_out = kept;
       }
     }

@@ -28,6 +28,7 @@ struct lfgpu_ctx {
   int64_t launches = 0;
   std::string last_error;
   void* d_scratch = nullptr;  // small device scratch (flags, counters)
+  bool geom_check_pending = false;  // a coordinate update queued a degeneracy check whose flag (scratch + 1024) is read at the next synchronize
   struct TableEntry {
     std::vector<double> host;
     double* dev;
@@ -72,6 +73,13 @@ struct lfgpu_dofmap {
   int32_t* g_ptr = nullptr;
   uint32_t* g_items = nullptr;
   int64_t g_n_items = 0;
+  // vertex-ring plan of the P1 load vector (assemble_p1.cu: p1_load_fan), built on first use: 0 = not tried, 1 = ready, -1 = n/a
+  int lv_state = 0, lv_w = 0;
+  uint32_t* lv_nbr = nullptr;      // [lv_w][n_dofs] ring node ids (0xFFFFFFFF = empty), or
+  int16_t* lv_nbr16 = nullptr;     // [6][n_dofs] ring ids as offsets from the row id (0 = empty)
+  uint8_t* lv_info = nullptr;      // [n_dofs] 0 open fan, 1 closed fan, 2 not a single fan (generic kernel), 3 no cells
+  int32_t* lv_irregular = nullptr;
+  int64_t n_lv_irregular = 0;
 };
 
 struct lfgpu_pattern {
@@ -243,6 +251,8 @@ bool p1h_rules_ok(const FeTable* tt, const FeTable* tq);
 int p1h_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, const FeTable* tt, const FeTable* tq, const lfgpu_coeff* alpha,
                const lfgpu_coeff* gamma, const uint8_t* active, double beta, const int32_t* row_list, int64_t n_rows, int64_t row0,
                double* d_values);
+// P1 load vector with a constant source on the vertex rings (assemble_p1.cu)
+int p1_load_fan(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* d, double c, double beta, double* d_vec, int* handled);
 // P2 row kernels (assemble_p2.cu): k00 .. km = reference tensors of FeLagrangeO2Tria, [6 * 6] row-major each
 int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p);
 int p2_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, const double alpha[4], int tensor, double gamma,

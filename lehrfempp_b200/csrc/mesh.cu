@@ -378,6 +378,14 @@ int lfgpu_mesh_update_node_coords(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const double
   if (ctx == nullptr || mesh == nullptr || node_coords == nullptr) return LFGPU_ERR_INVALID;
   if (mesh->cell_coords != nullptr) LFGPU_FAIL(ctx, LFGPU_ERR_UNSUPPORTED, "mesh carries explicit cell corner coordinates");
   LFGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(mesh->node_coords, node_coords, sizeof(double) * 2 * mesh->n_nodes, cudaMemcpyHostToDevice, ctx->stream));
+  // the new positions are checked like those of lfgpu_mesh_upload (the reference asserts on a degenerate cell, tria_o1.cc:10-48;
+  // the kernels' 1 / det has no slow path), asynchronously: the flag is read by the next lfgpu_ctx_synchronize
+  int* d_flag = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 1024);
+  if (!ctx->geom_check_pending) LFGPU_CUDA_CHECK(ctx, cudaMemsetAsync(d_flag, 0, 16, ctx->stream));
+  k_validate_cells<<<static_cast<unsigned>(cdiv(mesh->n_cells, kThreads)), kThreads, 0, ctx->stream>>>(mesh->n_cells, mesh->n_nodes, mesh->cell_nodes,
+                                                                                                    mesh->node_coords, mesh->cell_coords, d_flag);
+  LFGPU_LAUNCH_CHECK(ctx);
+  ctx->geom_check_pending = true;
   return LFGPU_OK;
 }
 

@@ -144,7 +144,7 @@ def test_host_entry_row_ranges_tile_the_matrix(ctx, lf, parts):
     for k in range(parts):
         r0, r1 = bounds[k], bounds[k + 1]
         # poison the device coordinates so that every range must bring its own window
-        gm.update_node_coords(np.full_like(xy0, 1e30))
+        gm.update_node_coords((xy0 + 1.0) * 1e30)  # far away, but still a valid (non-degenerate) geometry
         ctx.synchronize()
         h_part = ctx.pinned(int(outer[r1] - outer[r0]))
         h_part[:] = np.nan

@@ -391,8 +391,14 @@ def test_p1_fan_not_applicable(ctx, lf, golden_meshes):
     om = lfo.Mesh.from_golden(golden_meshes["0"])          # hybrid mesh
     gm = upload_oracle_mesh(ctx, om)[0]
     pat = gm.dofmap_lagrange(1).symbolic()
+    # round 2: hybrid meshes have a row kernel of their own (assemble_p1h.cu), so LFGPU_ALGO_FAN is served ...
+    o = om.assemble_rd(1, lfo.coeff.const(1.0), lfo.coeff.const(0.0), csr=False)
+    v = pat.assemble_reaction_diffusion(1, lf.Coeff.const(1.0), lf.Coeff.const(0.0), algo=lf.ALGO_FAN).to_host()
+    assert rel_max_err(v, o[2]) <= TOL
+    # ... unless the rule has other point counts than the kernels are compiled for: LFGPU_ERR_UNSUPPORTED, no silent fallback
+    qt, qq = lf.QuadRule(*lfo.quad_rule(3, 6)), lf.QuadRule(*lfo.quad_rule(4, 6))
     with pytest.raises(lf.LfgpuError) as e:
-        pat.assemble_reaction_diffusion(1, lf.Coeff.const(1.0), lf.Coeff.const(0.0), algo=lf.ALGO_FAN)
+        pat.assemble_reaction_diffusion(1, lf.Coeff.const(1.0), lf.Coeff.const(0.0), qt, qq, algo=lf.ALGO_FAN)
     assert e.value.code == -7
     # AUTO falls back to the generic kernel
     o = om.assemble_rd(1, lfo.coeff.const(1.0), lfo.coeff.const(0.0), csr=True)
@@ -415,3 +421,31 @@ def test_p1_fan_row_list(ctx, lf):
     lo, hi = outer[100], outer[900]
     assert rel_max_err(h[lo:hi], o[2][lo:hi]) <= TOL
     assert np.all(h[:lo] == -7.0) and np.all(h[hi:] == -7.0)
+
+
+# ---- the kernels that own rows in registers, at sizes where their prefetch branches and compact plans are active ---------------
+@pytest.mark.parametrize("degree,n", [(1, 707), (2, 400), (3, 250)])
+def test_row_kernels_against_the_oracle_at_scale(ctx, lf, degree, n):
+    # P1: 1.0e6 triangles = the smallest size of BASELINE config 5; more rows than one wave of resident CTAs (151 552), so the
+    # L2-prefetch branch, the compact 16-bit ring plan and the staged line writes of the fan kernel are all compared with the oracle
+    om = lfo.Mesh.tp_tria(n, n)
+    gm = ctx.mesh_tp_tria(n, n)
+    pat = gm.dofmap_lagrange(degree).symbolic(major=lf.ROW_MAJOR)
+    o_outer, o_inner, o_vals, _, _ = om.assemble_rd(degree, lfo.coeff.const(1.0), lfo.coeff.const(0.0), csr=True)
+    outer, inner = pat.download()
+    assert np.array_equal(outer, o_outer) and np.array_equal(inner, o_inner)
+    vals = pat.assemble_reaction_diffusion(degree, lf.Coeff.const(1.0), lf.Coeff.const(0.0), algo=lf.ALGO_FAN).to_host()
+    assert rel_max_err(vals, o_vals) <= TOL
+    o2 = om.assemble_rd(degree, lfo.coeff.const2x2([[2.0, 0.5], [-0.25, 1.0]]), lfo.coeff.const(0.75), csr=True)
+    vals = pat.assemble_reaction_diffusion(degree, lf.Coeff.const2x2([[2.0, 0.5], [-0.25, 1.0]]), lf.Coeff.const(0.75), algo=lf.ALGO_FAN).to_host()
+    assert rel_max_err(vals, o2[2]) <= TOL
+
+
+@pytest.mark.parametrize("degree,n", [(1, 1800), (2, 900), (3, 500)])
+def test_row_kernels_against_the_generic_kernel_large(ctx, lf, degree, n):
+    gm = ctx.mesh_tp_tria(n, n)
+    pat = gm.dofmap_lagrange(degree).symbolic(major=lf.ROW_MAJOR)
+    for alpha, gamma in ((lf.Coeff.const(1.0), lf.Coeff.const(0.0)), (lf.Coeff.const2x2([[2.0, 0.5], [-0.25, 1.0]]), lf.Coeff.const(0.75))):
+        rows = pat.assemble_reaction_diffusion(degree, alpha, gamma, algo=lf.ALGO_FAN).to_host()
+        gen = pat.assemble_reaction_diffusion(degree, alpha, gamma, algo=lf.ALGO_GATHER).to_host()
+        assert rel_max_err(rows, gen) <= TOL

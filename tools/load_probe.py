@@ -23,7 +23,7 @@ dm.assemble_load(degree, f, out=vec, algo=lf.ALGO_GATHER)
 ctx.synchronize()
 out["gather_first_call_s"] = time.time() - t
 res = {}
-for name, algo in (("gather", lf.ALGO_GATHER), ("atomic", lf.ALGO_ATOMIC)):
+for name, algo in (("gather", lf.ALGO_GATHER), ("atomic", lf.ALGO_ATOMIC), ("auto", lf.ALGO_AUTO)):
     for _ in range(3):
         dm.assemble_load(degree, f, out=vec, algo=algo)
     e0, e1 = ctx.event(), ctx.event()
