@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <array>
+#include <cmath>
 #include <cstdint>
 #include <map>
 #include <memory>
@@ -380,9 +381,32 @@ template <class R>
 struct MeshFunctionConstant {
   R value;
 };
+// Point type handed to functors that take ONE argument, like the reference's MeshFunctionGlobal (mesh_function_global.h:77-88:
+// f(Eigen::Vector2d)).  With Eigen available define LFGPU_SHIM_POINT_TYPE=Eigen::Vector2d before including this header and
+// the user's lambdas compile unchanged; Vec2 offers the members such lambdas typically use.
+struct Vec2 {
+  double v[2];
+  Vec2(double x, double y) : v{x, y} {}
+  double operator[](int i) const { return v[i]; }
+  double operator()(int i) const { return v[i]; }
+  [[nodiscard]] double x() const { return v[0]; }
+  [[nodiscard]] double y() const { return v[1]; }
+  [[nodiscard]] double squaredNorm() const { return v[0] * v[0] + v[1] * v[1]; }
+  [[nodiscard]] double norm() const { return std::sqrt(squaredNorm()); }
+};
+#ifndef LFGPU_SHIM_POINT_TYPE
+#define LFGPU_SHIM_POINT_TYPE ::lfgpu::Vec2
+#endif
 template <class F>
 struct MeshFunctionGlobal {
-  F f;  // double f(double x, double y)  or  Matrix2 f(double x, double y)
+  F f;  // R f(double x, double y)  or  R f(point) with point = LFGPU_SHIM_POINT_TYPE;  R = double or Matrix2
+  [[nodiscard]] auto operator()(double x, double y) const {
+    if constexpr (std::is_invocable_v<const F&, double, double>) {
+      return f(x, y);
+    } else {
+      return f(LFGPU_SHIM_POINT_TYPE(x, y));
+    }
+  }
 };
 
 template <class MF>
@@ -411,7 +435,7 @@ struct CoeffTraits<MeshFunctionConstant<Matrix2>> {
 template <class F>
 struct CoeffTraits<MeshFunctionGlobal<F>> {
   static constexpr bool needs_points = true;
-  using R = decltype(std::declval<F>()(0.0, 0.0));
+  using R = decltype(std::declval<const MeshFunctionGlobal<F>&>()(0.0, 0.0));
   static HostCoeff describe(const MeshFunctionGlobal<F>& mf, const double* xy, std::int64_t n_cells, long stride) {
     HostCoeff c;
     c.stride = stride;
@@ -419,13 +443,13 @@ struct CoeffTraits<MeshFunctionGlobal<F>> {
       c.kind = LFGPU_COEFF_PER_QP_2X2;
       c.table.resize(static_cast<std::size_t>(n_cells) * stride * 4);
       for (std::int64_t i = 0; i < n_cells * stride; ++i) {
-        const Matrix2 m = mf.f(xy[2 * i], xy[2 * i + 1]);
+        const Matrix2 m = mf(xy[2 * i], xy[2 * i + 1]);
         c.table[4 * i] = m.a[0][0]; c.table[4 * i + 1] = m.a[0][1]; c.table[4 * i + 2] = m.a[1][0]; c.table[4 * i + 3] = m.a[1][1];
       }
     } else {
       c.kind = LFGPU_COEFF_PER_QP;
       c.table.resize(static_cast<std::size_t>(n_cells) * stride);
-      for (std::int64_t i = 0; i < n_cells * stride; ++i) c.table[i] = mf.f(xy[2 * i], xy[2 * i + 1]);
+      for (std::int64_t i = 0; i < n_cells * stride; ++i) c.table[i] = mf(xy[2 * i], xy[2 * i + 1]);
     }
     return c;
   }
@@ -452,6 +476,12 @@ class ReactionDiffusionElementMatrixProvider {
   }
   ReactionDiffusionElementMatrixProvider(const ReactionDiffusionElementMatrixProvider&) = delete;
   ReactionDiffusionElementMatrixProvider(ReactionDiffusionElementMatrixProvider&&) noexcept = default;
+  using alpha_type = DIFF_COEFF;
+  using gamma_type = REACTION_COEFF;
+  // loc_comp_ellbvp.h:155: "all cells are active"; a derived provider that declares its own isActive(cell) is honoured by the GPU
+  // overload (assembler.h:127 skips inactive cells): the predicate is evaluated on the host, the mask travels to the device
+  template <class CELL>
+  bool isActive(const CELL& /*cell*/) { return true; }
   [[nodiscard]] const DIFF_COEFF& Alpha() const { return alpha_; }
   [[nodiscard]] const REACTION_COEFF& Gamma() const { return gamma_; }
   [[nodiscard]] int Degree() const { return degree_; }
@@ -487,12 +517,40 @@ class ScalarLoadElementVectorProvider {
   static_assert(std::is_same_v<SCALAR, double>, "the GPU path computes in double");
   template <class FE_SPACE>
   ScalarLoadElementVectorProvider(std::shared_ptr<const FE_SPACE> fe_space, MESH_FUNCTION f) : f_(std::move(f)), degree_(fe_space->Degree()) {}
+  // loc_comp_ellbvp.h:660-686: user rules per reference element
+  template <class FE_SPACE, class QR_MAP>
+  ScalarLoadElementVectorProvider(std::shared_ptr<const FE_SPACE> fe_space, MESH_FUNCTION f, const QR_MAP& qr_collection)
+      : f_(std::move(f)), degree_(fe_space->Degree()) {
+    custom_rules_ = true;
+    for (const auto& kv : qr_collection) {
+      const auto& qr = kv.second;
+      const int n = static_cast<int>(qr.NumPoints());
+      const bool tria = kv.first.Id() == 3;
+      auto& pts = tria ? rules_.pts_tria : rules_.pts_quad;
+      auto& w = tria ? rules_.w_tria : rules_.w_quad;
+      pts.resize(2 * n);
+      w.resize(n);
+      for (int k = 0; k < n; ++k) {
+        pts[k] = qr.Points()(0, k);
+        pts[n + k] = qr.Points()(1, k);
+        w[k] = qr.Weights()[k];
+      }
+      (tria ? rules_.has_tria : rules_.has_quad) = true;
+    }
+  }
+  using function_type = MESH_FUNCTION;
+  template <class CELL>
+  bool isActive(const CELL& /*cell*/) { return true; }  // loc_comp_ellbvp.h:608
   [[nodiscard]] const MESH_FUNCTION& F() const { return f_; }
   [[nodiscard]] int Degree() const { return degree_; }
+  [[nodiscard]] const Rules& QuadRules() const { return rules_; }
+  [[nodiscard]] bool HasCustomRules() const { return custom_rules_; }
 
  private:
   MESH_FUNCTION f_;
   int degree_;
+  Rules rules_;
+  bool custom_rules_ = false;
 };
 
 namespace detail {
@@ -528,15 +586,46 @@ inline std::vector<double> qp_coords(Context& ctx, lfgpu_mesh* mesh, std::int64_
   lfgpu_free(ctx.get(), d);
   return xy;
 }
+// provider.isActive(cell) for every cell (assembler.h:127), evaluated on the host like every user predicate; null if all active
+struct DeviceMask {
+  void* d = nullptr;
+  lfgpu_ctx* ctx = nullptr;
+  ~DeviceMask() {
+    if (d) lfgpu_free(ctx, d);
+  }
+  [[nodiscard]] const std::uint8_t* get() const { return static_cast<const std::uint8_t*>(d); }
+};
+template <class A, class MESH, class PROVIDER>
+std::vector<std::uint8_t> activity_flags(const MESH& mesh, PROVIDER& prov, bool* all_active) {
+  std::vector<std::uint8_t> act(static_cast<std::size_t>(A::num_entities(mesh, 0)), 1);
+  *all_active = true;
+  for (const auto* cell : A::entities(mesh, 0)) {
+    if (!prov.isActive(*cell)) {
+      act[A::index(mesh, *cell)] = 0;
+      *all_active = false;
+    }
+  }
+  return act;
+}
+template <class A, class MESH, class PROVIDER>
+void activity_mask(Context& ctx, const MESH& mesh, PROVIDER& prov, DeviceMask& m) {
+  bool all = true;
+  const auto act = activity_flags<A>(mesh, prov, &all);
+  if (all) return;
+  m.ctx = ctx.get();
+  ctx.check(lfgpu_malloc(ctx.get(), static_cast<std::int64_t>(act.size()), &m.d), "lfgpu_malloc");
+  ctx.check(lfgpu_memcpy_h2d(ctx.get(), m.d, act.data(), static_cast<std::int64_t>(act.size())), "lfgpu_memcpy_h2d");
+  ctx.check(lfgpu_ctx_synchronize(ctx.get()), "lfgpu_ctx_synchronize");  // `act` goes out of scope
+}
 }  // namespace detail
 
 inline constexpr int kMaxPoints = 36;  // table stride for host-evaluated coefficients (largest rule the library holds)
 
 // ---- the overloads ------------------------------------------------------------------------------------------------------------
 // GPU overload of lf::assemble::AssembleMatrixLocally (assembler.h:114-186): same arguments, TMPMATRIX = lfgpu::CsrMatrix.
-template <class A, class DOFH, class ALPHA, class GAMMA>
-void AssembleMatrixLocally(unsigned codim, const DOFH& dof_handler_trial, const DOFH& dof_handler_test,
-                           ReactionDiffusionElementMatrixProvider<double, ALPHA, GAMMA>& emp, CsrMatrix& matrix) {
+// PROVIDER: ReactionDiffusionElementMatrixProvider<double, ALPHA, GAMMA> or a class derived from it (its own isActive is used).
+template <class A, class DOFH, class PROVIDER, class ALPHA = typename PROVIDER::alpha_type, class GAMMA = typename PROVIDER::gamma_type>
+void AssembleMatrixLocally(unsigned codim, const DOFH& dof_handler_trial, const DOFH& dof_handler_test, PROVIDER& emp, CsrMatrix& matrix) {
   if (codim != 0) throw Error(LFGPU_ERR_UNSUPPORTED, "the GPU overload assembles cell (codim 0) contributions");
   if (&A::mesh(dof_handler_trial) != &A::mesh(dof_handler_test))
     throw Error(LFGPU_ERR_INVALID, "Trial and test space must be defined on the same mesh");  // assembler.h:121-122
@@ -558,31 +647,40 @@ void AssembleMatrixLocally(unsigned codim, const DOFH& dof_handler_trial, const 
   detail::DeviceCoeff da, dg;
   detail::to_device(ctx, CoeffTraits<ALPHA>::describe(emp.Alpha(), xy.data(), n_cells, stride), da);
   detail::to_device(ctx, CoeffTraits<GAMMA>::describe(emp.Gamma(), xy.data(), n_cells, stride), dg);
+  detail::DeviceMask active;
+  detail::activity_mask<A>(ctx, A::mesh(dof_handler_trial), emp, active);
   // accumulate like the reference (assembler.h:84-88); a freshly zeroed matrix is simply overwritten
   const double beta = matrix.empty_ ? 0.0 : 1.0;
   ctx.check(lfgpu_assemble_reaction_diffusion(ctx.get(), matrix.mesh(), matrix.pattern(), emp.Degree(), pqt, pqq, &da.c, &dg.c,
-                                              nullptr, beta, matrix.device_values(), LFGPU_ALGO_AUTO),
+                                              active.get(), beta, matrix.device_values(), LFGPU_ALGO_AUTO),
             "lfgpu_assemble_reaction_diffusion");
   ctx.check(lfgpu_ctx_synchronize(ctx.get()), "lfgpu_ctx_synchronize");
   matrix.empty_ = false;
 }
 // GPU overload of lf::assemble::AssembleVectorLocally (assembler.h:298-327): VECTOR = lfgpu::Vector
-template <class A, class DOFH, class F>
-void AssembleVectorLocally(unsigned codim, const DOFH& dof_handler, ScalarLoadElementVectorProvider<double, F>& evp, Vector& v) {
+template <class A, class DOFH, class PROVIDER, class F = typename PROVIDER::function_type>
+void AssembleVectorLocally(unsigned codim, const DOFH& dof_handler, PROVIDER& evp, Vector& v) {
   if (codim != 0) throw Error(LFGPU_ERR_UNSUPPORTED, "the GPU overload assembles cell (codim 0) contributions");
   Context& ctx = v.ctx();
   v.template Prepare<A>(dof_handler);
   std::int64_t n_cells = 0;
   lfgpu_mesh_counts(v.mesh(), nullptr, nullptr, &n_cells, nullptr, nullptr);
+  const Rules& r = evp.QuadRules();
+  lfgpu_quad qt{static_cast<int>(r.w_tria.size()), r.pts_tria.data(), r.w_tria.data()};
+  lfgpu_quad qq{static_cast<int>(r.w_quad.size()), r.pts_quad.data(), r.w_quad.data()};
+  const lfgpu_quad* pqt = (evp.HasCustomRules() && r.has_tria) ? &qt : nullptr;
+  const lfgpu_quad* pqq = (evp.HasCustomRules() && r.has_quad) ? &qq : nullptr;
   std::vector<double> xy;
   int stride = 0;
   if (CoeffTraits<F>::needs_points) {
     stride = 36;
-    xy = detail::qp_coords(ctx, v.mesh(), n_cells, evp.Degree(), nullptr, nullptr, stride);
+    xy = detail::qp_coords(ctx, v.mesh(), n_cells, evp.Degree(), pqt, pqq, stride);
   }
   detail::DeviceCoeff df;
   detail::to_device(ctx, CoeffTraits<F>::describe(evp.F(), xy.data(), n_cells, stride), df);
-  ctx.check(lfgpu_assemble_load(ctx.get(), v.mesh(), v.dofs(), evp.Degree(), nullptr, nullptr, &df.c, nullptr, 1.0, v.device(), LFGPU_ALGO_AUTO),
+  detail::DeviceMask active;
+  detail::activity_mask<A>(ctx, A::mesh(dof_handler), evp, active);
+  ctx.check(lfgpu_assemble_load(ctx.get(), v.mesh(), v.dofs(), evp.Degree(), pqt, pqq, &df.c, active.get(), 1.0, v.device(), LFGPU_ALGO_AUTO),
             "lfgpu_assemble_load");
   ctx.check(lfgpu_ctx_synchronize(ctx.get()), "lfgpu_ctx_synchronize");
 }

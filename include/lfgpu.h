@@ -364,6 +364,33 @@ const int32_t* lfgpu_submesh_l2g_nodes_device(const lfgpu_submesh* s);
 const int32_t* lfgpu_submesh_l2g_dofs_device(const lfgpu_submesh* s);
 /* d_owned [n_local_dofs] = 1 where the local dof is owned by `rank` (d_dof_owner: the GLOBAL owner array)                     */
 int lfgpu_submesh_owned_dofs(lfgpu_ctx* ctx, const lfgpu_submesh* s, const uint8_t* d_dof_owner, int rank, uint8_t* d_owned);
+/* ---- several GPUs from one process ("lfgpu_ctx_create(device_ids, n_dev, ...)") ---------------------------
+ * The drop-in form of the distributed-ownership scheme for a C / C++ caller: one lfgpu_ctx per listed device inside one handle.
+ * lfgpu_multi_setup takes the flattened mesh and dof table exactly as lfgpu_mesh_upload / lfgpu_dofmap_upload do (host arrays of
+ * the WHOLE problem), cuts them into one sub-problem per device (Morton cell ranges, every device owns the rows of its cells,
+ * one-cell halo) and runs the symbolic pass per device; afterwards no device holds more than its share.  The numeric pass queues
+ * the kernels on every device and waits for all of them; it needs no exchange between the devices.                              */
+typedef struct lfgpu_multi lfgpu_multi;
+int lfgpu_multi_create(const int* device_ids, int n_dev, lfgpu_multi** out);
+void lfgpu_multi_destroy(lfgpu_multi* m);
+int lfgpu_multi_num_devices(const lfgpu_multi* m);
+lfgpu_ctx* lfgpu_multi_ctx(lfgpu_multi* m, int k); /* the context of device k (owned by the handle) */
+const char* lfgpu_multi_last_error(const lfgpu_multi* m);
+int lfgpu_multi_setup(lfgpu_multi* m, int64_t n_nodes, const double* node_coords, int64_t n_cells, const uint32_t* cell_nodes,
+                      const double* cell_coords, int64_t n_dofs, int stride, const int64_t* cell_dofs, const uint8_t* n_ldof, int major);
+int lfgpu_multi_set_zero(lfgpu_multi* m);
+/* AssembleMatrixLocally with ReactionDiffusionElementMatrixProvider on all devices.  alpha / gamma as in
+ * lfgpu_assemble_reaction_diffusion, except that the tables of the PER_* kinds are HOST arrays over the cells of the WHOLE mesh
+ * (every device receives the entries of its cells).  accumulate != 0: add to what the matrix holds (assembler.h:84-88).        */
+int lfgpu_multi_assemble_reaction_diffusion(lfgpu_multi* m, int degree, const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad,
+                                            const lfgpu_coeff* alpha, const lfgpu_coeff* gamma, int accumulate);
+/* share of device k: n_rows / nnz of the rows it OWNS; cells, rows and stored values of its sub-problem incl. the halo           */
+int lfgpu_multi_part_sizes(const lfgpu_multi* m, int k, int64_t* n_rows, int64_t* nnz, int64_t* n_local_cells, int64_t* n_local_rows,
+                           int64_t* n_local_nnz);
+/* the rows device k owns as a compressed block with GLOBAL indices: rows [n_rows] (global outer index, ascending), row_ptr
+ * [n_rows + 1], cols [nnz] (global inner index, ascending inside a row = the reference's pattern), values [nnz]; every output
+ * nullable.  The blocks of all devices together are the matrix makeSparse() returns (assemble/coomatrix.h:172-180).             */
+int lfgpu_multi_part_download(lfgpu_multi* m, int k, int64_t* rows, int64_t* row_ptr, int32_t* cols, double* values);
 /* read-only device views used by the host-side partitioner: gather lists (items = cell << 4 | local index), mesh arrays */
 const int32_t* lfgpu_pattern_adj_ptr_device(const lfgpu_pattern* p);
 const uint32_t* lfgpu_pattern_adj_device(const lfgpu_pattern* p);

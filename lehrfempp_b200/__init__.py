@@ -26,6 +26,7 @@ from .api import (  # noqa: F401
     GmshReader,
     LfgpuError,
     Mesh,
+    MultiAssembler,
     Pattern,
     QuadRule,
     SubMesh,
@@ -37,5 +38,5 @@ from .api import (  # noqa: F401
 
 __all__ = [
     "ALGO_ATOMIC", "ALGO_AUTO", "ALGO_FAN", "ALGO_GATHER", "COL_MAJOR", "ROW_MAJOR", "Coeff", "Context", "DeviceArray", "DofMap",
-    "GmshReader",    "LfgpuError", "Mesh", "Pattern", "QuadRule", "SubMesh", "build_library", "default_quad_rule", "fe_tabulate", "library_path",
+    "GmshReader",    "LfgpuError", "Mesh", "MultiAssembler", "Pattern", "QuadRule", "SubMesh", "build_library", "default_quad_rule", "fe_tabulate", "library_path",
 ]

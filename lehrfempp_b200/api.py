@@ -155,6 +155,17 @@ def _lib():
         "lfgpu_submesh_l2g_nodes_device": (vp, [vp]),
         "lfgpu_submesh_l2g_dofs_device": (vp, [vp]),
         "lfgpu_submesh_owned_dofs": (i32, [vp, vp, vp, i32, vp]),
+        "lfgpu_multi_create": (i32, [vp, i32, pp]),
+        "lfgpu_multi_destroy": (None, [vp]),
+        "lfgpu_multi_num_devices": (i32, [vp]),
+        "lfgpu_multi_ctx": (vp, [vp, i32]),
+        "lfgpu_multi_last_error": (C.c_char_p, [vp]),
+        "lfgpu_multi_setup": (i32, [vp, i64, vp, i64, vp, vp, i64, i32, vp, vp, i32]),
+        "lfgpu_multi_set_zero": (i32, [vp]),
+        "lfgpu_multi_assemble_reaction_diffusion": (i32, [vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), C.POINTER(_CCoeff),
+                                                          C.POINTER(_CCoeff), i32]),
+        "lfgpu_multi_part_sizes": (i32, [vp, i32] + [C.POINTER(i64)] * 5),
+        "lfgpu_multi_part_download": (i32, [vp, i32, vp, vp, vp, vp]),
         "lfgpu_qp_coords": (i32, [vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), i32, vp]),
         "lfgpu_fe_tabulate": (i32, [i32, i32, C.POINTER(_CQuad), vp, vp]),
         "lfgpu_default_quad_rule": (i32, [i32, i32, i32, vp, vp]),
@@ -221,8 +232,13 @@ class Coeff:
         self._c = _CCoeff(kind=kind)
         for i in range(4):
             self._c.c[i] = float(c[i])
-        self._data = data  # keeps the DeviceArray alive
-        self._c.data = data.ptr if data is not None else None
+        self._data = data  # keeps the DeviceArray (or, for the multi-device calls, the host array) alive
+        if data is None:
+            self._c.data = None
+        elif isinstance(data, np.ndarray):  # HOST table over the cells of the whole mesh (lfgpu_multi_assemble_reaction_diffusion)
+            self._c.data = data.ctypes.data
+        else:
+            self._c.data = data.ptr
         self._c.stride = stride
 
     @staticmethod
@@ -675,6 +691,61 @@ class DofMap:
         self.ctx.check(self.ctx.L.lfgpu_assemble_load(self.ctx.h, self.mesh.h, self.h, degree, _qref(qr_tria), _qref(qr_quad),
                                                       f.ref(), active.ptr if active is not None else None, beta, out.ptr, algo))
         return out
+
+
+class MultiAssembler:
+    """Several GPUs from one process through the C ABI (lfgpu_multi_*): the flattened problem is cut into one sub-problem per
+    listed device (distributed ownership, owner-computes); `parts()` returns every device's owned rows with global indices."""
+
+    def __init__(self, device_ids):
+        self.L = _lib()
+        ids = (C.c_int * len(device_ids))(*device_ids)
+        self.h = C.c_void_p()
+        rc = self.L.lfgpu_multi_create(ids, len(device_ids), C.byref(self.h))
+        if rc != 0:
+            raise LfgpuError(rc, self.L.lfgpu_last_error(None).decode())
+        self.n_dev = len(device_ids)
+
+    def check(self, rc):
+        if rc != 0:
+            raise LfgpuError(rc, self.L.lfgpu_multi_last_error(self.h).decode())
+
+    def setup(self, node_coords, cell_nodes, n_dofs, cell_dofs, n_ldof=None, cell_coords=None, major=ROW_MAJOR):
+        xy = np.ascontiguousarray(node_coords, dtype=np.float64)
+        cn = np.ascontiguousarray(cell_nodes, dtype=np.uint32)
+        cd = np.ascontiguousarray(cell_dofs, dtype=np.int64)
+        nl = None if n_ldof is None else np.ascontiguousarray(n_ldof, dtype=np.uint8)
+        cc = None if cell_coords is None else np.ascontiguousarray(cell_coords, dtype=np.float64)
+        self.check(self.L.lfgpu_multi_setup(self.h, xy.shape[0], _p(xy), cn.shape[0], _p(cn), _p(cc), int(n_dofs), cd.shape[1], _p(cd), _p(nl),
+                                            major))
+
+    def assemble_reaction_diffusion(self, degree, alpha, gamma, qr_tria=None, qr_quad=None, accumulate=False):
+        self.check(self.L.lfgpu_multi_assemble_reaction_diffusion(self.h, degree, _qref(qr_tria), _qref(qr_quad), alpha.ref(), gamma.ref(),
+                                                                  1 if accumulate else 0))
+
+    def set_zero(self):
+        self.check(self.L.lfgpu_multi_set_zero(self.h))
+
+    def part_sizes(self, k):
+        v = [C.c_int64() for _ in range(5)]
+        self.check(self.L.lfgpu_multi_part_sizes(self.h, k, *[C.byref(x) for x in v]))
+        return dict(zip(("rows", "nnz", "local_cells", "local_rows", "local_nnz"), [x.value for x in v]))
+
+    def part(self, k):
+        """(rows, row_ptr, cols, values) of the rows device k owns, global indices."""
+        sz = self.part_sizes(k)
+        rows, ptr = np.zeros(sz["rows"], np.int64), np.zeros(sz["rows"] + 1, np.int64)
+        cols, vals = np.zeros(sz["nnz"], np.int32), np.zeros(sz["nnz"], np.float64)
+        self.check(self.L.lfgpu_multi_part_download(self.h, k, _p(rows), _p(ptr), _p(cols), _p(vals)))
+        return rows, ptr, cols, vals
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.lfgpu_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
 
 
 class SubMesh:
