@@ -183,6 +183,11 @@ int64_t lfgpu_pattern_cols(const lfgpu_pattern* p);
 int lfgpu_pattern_download(lfgpu_ctx* ctx, const lfgpu_pattern* p, int32_t* outer, int32_t* inner);
 const int32_t* lfgpu_pattern_outer_device(const lfgpu_pattern* p);
 const int32_t* lfgpu_pattern_inner_device(const lfgpu_pattern* p);
+/* Only the outer indices flagged in d_keep (device uint8 [n_outer]) have to be produced by later numeric passes; the values of
+ * the others are unspecified afterwards.  For the sub-problems of the distributed-ownership scheme: halo rows are incomplete by
+ * construction, so the kernels need not spend a generic pass on those of them that do not fit the fast plans.  Must be called
+ * before the first numeric pass on the pattern.                                                                              */
+int lfgpu_pattern_restrict_rows(lfgpu_ctx* ctx, lfgpu_pattern* p, const uint8_t* d_keep);
 void lfgpu_pattern_destroy(lfgpu_pattern* p);
 
 /* ---- numeric pass ---------------------------------------------------------------------------------------------------- */

@@ -110,6 +110,7 @@ def _lib():
         "lfgpu_pattern_outer_device": (vp, [vp]),
         "lfgpu_pattern_inner_device": (vp, [vp]),
         "lfgpu_pattern_destroy": (None, [vp]),
+        "lfgpu_pattern_restrict_rows": (i32, [vp, vp, vp]),
         "lfgpu_assemble_reaction_diffusion": (i32, [vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), C.POINTER(_CCoeff),
                                                     C.POINTER(_CCoeff), vp, dbl, vp, i32]),
         "lfgpu_assemble_reaction_diffusion_rows": (i32, [vp, vp, vp, i32, C.POINTER(_CQuad), C.POINTER(_CQuad), C.POINTER(_CCoeff),
@@ -803,6 +804,10 @@ class Pattern:
         if getattr(self, "h", None) and getattr(self.ctx, "h", None):
             self.ctx.L.lfgpu_pattern_destroy(self.h)
             self.h = None
+
+    def restrict_rows(self, keep):
+        """Only the outer indices flagged in `keep` (DeviceArray uint8) have to be produced by later numeric passes."""
+        self.ctx.check(self.ctx.L.lfgpu_pattern_restrict_rows(self.ctx.h, self.h, keep.ptr))
 
     def download(self):
         n_outer = self.rows if self.major == ROW_MAJOR else self.cols

@@ -676,6 +676,11 @@ __global__ void k_qp_coords(Tables hdr, const double* __restrict__ blob, MeshVie
   }
 }
 
+__global__ void k_and_keep(int64_t n, uint8_t* __restrict__ flag, const uint8_t* __restrict__ keep) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n && keep[i] == 0) flag[i] = 0;
+}
+
 __global__ void k_scale(int64_t n, double beta, double* v) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) v[i] *= beta;
@@ -878,11 +883,28 @@ int launch_matrix(lfgpu_ctx* ctx, const HostTables& ht, const double* d_blob, co
 }
 
 }  // namespace
+
+int and_row_keep(lfgpu_ctx* ctx, int64_t n, uint8_t* d_flag, const uint8_t* d_keep) {
+  if (d_keep == nullptr || n <= 0) return LFGPU_OK;
+  k_and_keep<<<static_cast<unsigned>(cdiv(n, 256)), 256, 0, ctx->stream>>>(n, d_flag, d_keep);
+  LFGPU_LAUNCH_CHECK(ctx);
+  return LFGPU_OK;
+}
 }  // namespace lfgpu
 
 using namespace lfgpu;
 
 extern "C" {
+
+int lfgpu_pattern_restrict_rows(lfgpu_ctx* ctx, lfgpu_pattern* p, const uint8_t* d_keep) {
+  if (ctx == nullptr || p == nullptr || d_keep == nullptr) return LFGPU_ERR_INVALID;
+  if (p->fan_state != 0 || p->p1h_state != 0 || p->p2_state != 0 || p->p3_state != 0)
+    LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "lfgpu_pattern_restrict_rows must be called before the first numeric pass on the pattern");
+  LFGPU_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  if (p->row_keep == nullptr) LFGPU_CUDA_CHECK(ctx, cudaMalloc(&p->row_keep, p->n_outer > 0 ? p->n_outer : 1));
+  LFGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(p->row_keep, d_keep, p->n_outer, cudaMemcpyDeviceToDevice, ctx->stream));
+  return LFGPU_OK;
+}
 
 int lfgpu_assemble_reaction_diffusion(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, int degree,
                                       const lfgpu_quad* qr_tria, const lfgpu_quad* qr_quad, const lfgpu_coeff* alpha,

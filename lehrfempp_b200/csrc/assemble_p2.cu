@@ -578,6 +578,7 @@ int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
   P2_CHECK(cudaMalloc(&d_num, sizeof(int64_t)));
   cub::CountingInputIterator<int32_t> count_it(0);
   size_t tb = 0;
+  if (and_row_keep(ctx, p->n_outer, flag, p->row_keep) != LFGPU_OK) return LFGPU_ERR_CUDA;  // rows nobody asks for need no generic kernel
   cub::DeviceSelect::Flagged(nullptr, tb, count_it, flag, iota, d_num, p->n_outer, st);
   P2_CHECK(cudaMalloc(&tmp, tb));
   P2_CHECK(cub::DeviceSelect::Flagged(tmp, tb, count_it, flag, iota, d_num, p->n_outer, st));

@@ -436,6 +436,7 @@ int p3_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
   P3_CHECK(cudaMalloc(&d_num, sizeof(int64_t)));
   cub::CountingInputIterator<int32_t> count_it(0);
   size_t tb = 0;
+  if (and_row_keep(ctx, p->n_outer, flag, p->row_keep) != LFGPU_OK) return LFGPU_ERR_CUDA;  // rows nobody asks for need no generic kernel
   cub::DeviceSelect::Flagged(nullptr, tb, count_it, flag, iota, d_num, p->n_outer, st);
   P3_CHECK(cudaMalloc(&tmp, tb));
   P3_CHECK(cub::DeviceSelect::Flagged(tmp, tb, count_it, flag, iota, d_num, p->n_outer, st));

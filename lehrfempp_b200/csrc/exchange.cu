@@ -21,7 +21,10 @@ __global__ void k_rows_copy(int64_t n_rows, const int32_t* __restrict__ rows, co
   const int64_t o = offsets[w];
   for (int k = lane; k < len; k += 32) {
     if (UNPACK_ADD) {
-      values[v0 + k] += buf[o + k];
+      // a row at a corner of the partition is touched by three or more GPUs and then appears once per sender in the list: the
+      // additions of two warps to one entry must not be a plain read-modify-write (found by the 8-GPU parity run of round 2:
+      // lost updates, errors of order one; two GPUs never list a row twice)
+      atomicAdd(values + v0 + k, buf[o + k]);
     } else {
       buf[o + k] = values[v0 + k];
     }

@@ -110,6 +110,9 @@ struct lfgpu_pattern {
   int max_item_block_nnz = 0;
   double* cell_metric = nullptr; // [n_cells][6] scratch of the numeric pass (assemble.cu: k_cell_metric)
   int max_items = 0;  // max number of cells adjacent to one outer dof
+  // rows a later numeric pass has to produce (lfgpu_pattern_restrict_rows; null = all): the row kernels do not send the other
+  // rows through the generic kernel when their plan does not cover them (halo rows of a distributed sub-problem)
+  uint8_t* row_keep = nullptr;  // [n_outer]
   // dof tables the plan was built from (device copies owned by the pattern)
   int32_t* o_dofs = nullptr;  // [n_cells][o_stride]
   int32_t* i_dofs = nullptr;  // [n_cells][i_stride]
@@ -233,6 +236,8 @@ int build_fe_table(int degree, int cell_type, const lfgpu_quad* qr, FeTable* out
 void build_fe_tensors(const FeTable& t, FeTensors* out);
 int default_quad_rule(int cell_type, int degree, int capacity, double* points, double* weights);
 
+// flag[r] &= keep[r] on the ctx stream (no-op for keep == nullptr); assemble.cu
+int and_row_keep(lfgpu_ctx* ctx, int64_t n, uint8_t* d_flag, const uint8_t* d_keep);
 // per-dof gather lists of a dofmap (dofs.cu), cached in the handle
 int dofmap_gather_plan(lfgpu_ctx* ctx, const lfgpu_dofmap* d);
 

@@ -113,6 +113,15 @@ void setup_part(lfgpu_multi::Part& part, int k, int n_parts, int64_t n_nodes, co
   d_part = d_owner = d_sel = d_owned = nullptr;
   lfgpu_dofmap* sd = lfgpu_submesh_dofmap(part.sub);
   PART_CHECK(lfgpu_symbolic(ctx, lfgpu_submesh_mesh(part.sub), sd, sd, major, &part.pattern));
+  {
+    uint8_t* d_keep = nullptr;
+    PART_CUDA(cudaMalloc(&d_keep, part.n_dofs));
+    cudaError_t e = cudaMemcpy(d_keep, part.owned.data(), part.n_dofs, cudaMemcpyHostToDevice);
+    const int rk = e == cudaSuccess ? lfgpu_pattern_restrict_rows(ctx, part.pattern, d_keep) : LFGPU_ERR_CUDA;
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_keep);
+    PART_CHECK(rk);
+  }
   const int64_t nnz = lfgpu_pattern_nnz(part.pattern);
   PART_CUDA(cudaMalloc(&part.d_values, sizeof(double) * (nnz > 0 ? nnz : 1)));
   PART_CUDA(cudaMemsetAsync(part.d_values, 0, sizeof(double) * nnz, ctx->stream));

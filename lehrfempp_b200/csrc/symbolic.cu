@@ -239,6 +239,7 @@ void lfgpu_pattern_destroy(lfgpu_pattern* p) {
   cudaFree(p->item_sorted);
   cudaFree(p->blk_hdr);
   cudaFree(p->cell_metric);
+  cudaFree(p->row_keep);
   cudaFree(p->fan_nbr);
   cudaFree(p->fan_rowinfo);
   cudaFree(p->fan_nbr16);

@@ -309,6 +309,7 @@ class OwnedAssembler:
         self.partition_s = time.time() - t0
         t0 = time.time()
         self.pattern = self.sub.dofmap.symbolic(major=lf.ROW_MAJOR if major is None else major)
+        self.pattern.restrict_rows(self.sub.owned)  # halo rows are incomplete anyway: no generic pass for those outside the fast plans
         ctx.synchronize()
         self.symbolic_s = time.time() - t0
         own = self.sub.owned.to_host().astype(bool)

@@ -125,3 +125,41 @@ def test_large_partition_against_the_single_gpu_matrix(ctx, lf):
         assert rel_max_err(vals[idx_l], g_vals[idx_g]) <= TOL
     assert np.all(covered == 1)
     assert total_cells < 1.05 * gm.n_cells  # the halo is a perimeter effect
+
+
+def test_unpack_add_with_a_row_listed_twice(ctx, lf):
+    # a row at a corner of the partition receives partial sums from two senders: lfgpu_rows_unpack_add then lists it twice
+    # (the 8-GPU parity run of round 2 found lost updates in the plain read-modify-write version)
+    gm = ctx.mesh_tp_tria(9, 7)
+    pat = gm.dofmap_lagrange(2).symbolic(major=lf.ROW_MAJOR)
+    outer, _ = pat.download()
+    rows = np.array([5, 17, 5, 5, 40, 17], np.int32)
+    lens = (outer[rows + 1] - outer[rows]).astype(np.int64)
+    offs = np.cumsum(lens) - lens
+    buf = np.arange(1, lens.sum() + 1, dtype=np.float64)
+    values = ctx.to_device(np.full(pat.nnz, 0.5))
+    d_rows, d_offs, d_buf = ctx.to_device(rows), ctx.to_device(offs), ctx.to_device(buf)
+    ctx.check(ctx.L.lfgpu_rows_unpack_add(ctx.h, pat.h, d_rows.ptr, len(rows), d_offs.ptr, d_buf.ptr, values.ptr))
+    expect = np.full(pat.nnz, 0.5)
+    for r, o, l in zip(rows, offs, lens):
+        expect[outer[r]:outer[r] + l] += buf[o:o + l]
+    assert np.array_equal(values.to_host(), expect)
+
+
+def test_restrict_rows_keeps_the_owned_rows_exact(ctx, lf):
+    # lfgpu_pattern_restrict_rows: rows outside the mask may hold anything, the kept ones are those of the unrestricted pass
+    for degree in (1, 2, 3):
+        gm = ctx.mesh_hybrid(14, 0.2, 3) if degree == 2 else ctx.mesh_tp_tria(31, 17)
+        dm = gm.dofmap_lagrange(degree)
+        full = dm.symbolic(major=lf.ROW_MAJOR)
+        ref = full.assemble_reaction_diffusion(degree, lf.Coeff.const(1.0), lf.Coeff.const(1.0)).to_host()
+        outer, _ = full.download()
+        keep = (np.random.default_rng(degree).random(dm.num_dofs) < 0.7).astype(np.uint8)
+        pat = dm.symbolic(major=lf.ROW_MAJOR)
+        pat.restrict_rows(ctx.to_device(keep))
+        got = pat.assemble_reaction_diffusion(degree, lf.Coeff.const(1.0), lf.Coeff.const(1.0)).to_host()
+        mask = np.repeat(keep.astype(bool), np.diff(outer))
+        assert np.array_equal(got[mask], ref[mask])
+        if degree != 2:  # (P2 on a hybrid mesh runs the generic kernel: no row plan was built, the call stays legal)
+            with pytest.raises(lf.LfgpuError):
+                pat.restrict_rows(ctx.to_device(keep))  # too late: plans exist
