@@ -416,8 +416,8 @@ __device__ __forceinline__ void group_consume(const ItemData* d, const P1HParams
 // CC: cell corners come from the mesh's cell_coords array (cells whose geometry is not bitwise the node positions).
 // The cells of a row are processed in groups -- KQ / 2 pairs of quadrilaterals, then KT triangles -- and the loads of group
 // g + DEPTH are issued before group g is computed.
-template <int KQ, int KT, bool TENSOR, bool CC, int DEPTH, int MODE>
-__global__ void __launch_bounds__(128, KQ == 4 ? 3 : 4) k_assemble_p1_rows(int n_rows, int n_total_rows, const uint32_t* __restrict__ qw,
+template <int KQ, int KT, bool TENSOR, bool CC, int DEPTH, int MODE, int MINB = 0>
+__global__ void __launch_bounds__(128, MINB > 0 ? MINB : (KQ == 4 ? 3 : 4)) k_assemble_p1_rows(int n_rows, int n_total_rows, const uint32_t* __restrict__ qw,
                                                              const uint32_t* __restrict__ tw, const uint8_t* __restrict__ rowinfo,
                                                              const double* __restrict__ node_coords, const double* __restrict__ cell_coords,
                                                              const int32_t* __restrict__ outer, const uint8_t* __restrict__ active,
@@ -525,6 +525,136 @@ __global__ void __launch_bounds__(128, KQ == 4 ? 3 : 4) k_assemble_p1_rows(int n
       }
     }
   } else if (regular) {
+    const int len = v1 - v0;
+    for (int k = 0; k < len; ++k) {
+      const double v = stage[swz(off + k)];
+      values[v0 + k] = P.beta == 0.0 ? v : fma(P.beta, values[v0 + k], v);
+    }
+  }
+}
+
+// Hybrid rows with the work of a row split over TWO threads in different warps of the CTA (mixed meshes: KQ > 0 and KT > 0):
+// warps 0-1 take the quadrilaterals of 64 rows, warps 2-3 the triangles of the same rows.  ncu on the one-thread-per-row kernel
+// at config C2: 16 warps per SM at 128 registers, each walking its row's six cells in turn -- issue slots 51 % busy, stall
+// samples on the first use of every group of loads.  Two threads per row halve the serial chain of a row, every warp still runs one
+// code path (no divergence), and each role keeps fewer values alive.  The quadrilateral warps accumulate into the shared image
+// first; the triangle warps compute meanwhile and add after a CTA barrier; all four warps copy the two images out.
+template <int KQ, int KT, bool TENSOR, bool CC, int MODE>
+__global__ void __launch_bounds__(128, KQ == 4 ? 3 : 5) k_assemble_p1_rows_split(int n_rows, int n_total_rows, const uint32_t* __restrict__ qw,
+                                                                   const uint32_t* __restrict__ tw, const uint8_t* __restrict__ rowinfo,
+                                                                   const double* __restrict__ node_coords,
+                                                                   const double* __restrict__ cell_coords, const int32_t* __restrict__ outer,
+                                                                   const uint8_t* __restrict__ active, const int32_t* __restrict__ row_list,
+                                                                   int row0, int pf_dist, const __grid_constant__ P1HParams P,
+                                                                   double* __restrict__ values) {
+  extern __shared__ double stage_all[];
+  static_assert(KQ % 2 == 0 && KQ > 0 && KT > 0, "mixed rows only");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int half = warp & 1, role = warp >> 1;  // role 0: quadrilaterals, role 1: triangles
+  const int t = blockIdx.x * 64 + half * 32 + lane;
+  const bool in_range = t < n_rows;
+  const int32_t r = in_range ? (row_list != nullptr ? row_list[t] : t + row0) : 0;
+  if (pf_dist > 0 && row_list == nullptr && warp == 0) {
+    const int tp = blockIdx.x * 64 + pf_dist;
+    if (tp + 64 <= n_rows) {
+      const size_t rp = static_cast<size_t>(tp) + row0;
+      constexpr int nq_lines = 8 * KQ, nt_lines = 6 * KT;  // 2 lines of 128 B per plan array and CTA
+      for (int L = lane; L < nq_lines + nt_lines + 11; L += 32) {
+        const char* a;
+        if (L < nq_lines) {
+          a = reinterpret_cast<const char*>(qw + static_cast<size_t>(L >> 1) * n_total_rows + rp) + (L & 1) * 128;
+        } else if (L < nq_lines + nt_lines) {
+          const int M = L - nq_lines;
+          a = reinterpret_cast<const char*>(tw + static_cast<size_t>(M >> 1) * n_total_rows + rp) + (M & 1) * 128;
+        } else if (L == nq_lines + nt_lines) {
+          a = reinterpret_cast<const char*>(rowinfo + rp);
+        } else if (L < nq_lines + nt_lines + 3) {
+          a = reinterpret_cast<const char*>(outer + rp) + (L - nq_lines - nt_lines - 1) * 128;
+        } else {
+          a = reinterpret_cast<const char*>(node_coords + 2 * rp) + (L - nq_lines - nt_lines - 3) * 128;
+        }
+        prefetch_l2(a);
+      }
+    }
+  }
+  int32_t v0 = 0, v1 = 0;
+  int info = 0xFE;
+  if (in_range) {
+    v0 = __ldg(outer + r);
+    v1 = __ldg(outer + r + 1);
+    info = __ldg(rowinfo + r);
+  }
+  const bool regular = in_range && info < 0xFE;
+  const int32_t wbase = __shfl_sync(0xffffffffU, v0, 0);
+  const int32_t r_first = __shfl_sync(0xffffffffU, r, 0);
+  const bool consecutive = row_list == nullptr || !__any_sync(0xffffffffU, in_range && r != r_first + lane);
+  const bool staged = consecutive && !__any_sync(0xffffffffU, in_range && info == 0xFF);
+  double* stage = stage_all + half * (32 * kMaxLen);
+  const int off = staged ? v0 - wbase : lane * kMaxLen;
+  const double2* nc = reinterpret_cast<const double2*>(node_coords);
+  const double2* cc = reinterpret_cast<const double2*>(cell_coords);
+  double2 xi = make_double2(0.0, 0.0);
+  if (!CC) xi = __ldg(nc + r);
+  double diag = 0.0;
+  if (role == 0) {
+    uint32_t w[4 * KQ];
+#pragma unroll
+    for (int k = 0; k < 4 * KQ; ++k) w[k] = regular ? __ldg(qw + static_cast<size_t>(k) * n_total_rows + r) : kNil;
+    if (regular) {
+      const int len = v1 - v0;
+      for (int s = 0; s < len; ++s) stage[swz(off + s)] = 0.0;
+    }
+    ItemData D[KQ];
+#pragma unroll
+    for (int g = 0; g < KQ / 2 + 1; ++g) {  // pair g + 1 is loaded before pair g is computed
+      if (g < KQ / 2) {
+        item_issue<true, CC, MODE>(D[2 * g], P, w[8 * g], w[8 * g + 1], w[8 * g + 2], w[8 * g + 3], r, nc, cc, active);
+        item_issue<true, CC, MODE>(D[2 * g + 1], P, w[8 * g + 4], w[8 * g + 5], w[8 * g + 6], w[8 * g + 7], r, nc, cc, active);
+      }
+      if (g >= 1) group_consume<true, 2, TENSOR, CC, MODE>(&D[2 * (g - 1)], P, xi, stage, off, diag);
+    }
+    if (regular) stage[swz(off + info)] = diag;
+    __syncthreads();
+  } else {
+    uint32_t w[3 * KT];
+#pragma unroll
+    for (int k = 0; k < 3 * KT; ++k) w[k] = regular ? __ldg(tw + static_cast<size_t>(k) * n_total_rows + r) : kNil;
+    ItemData D[KT];
+    double e1[KT], e2[KT];
+#pragma unroll
+    for (int s = 0; s < KT + 2; ++s) {  // triangle s + 2 is loaded before triangle s is computed
+      if (s < KT) item_issue<false, CC, MODE>(D[s], P, w[3 * s], w[3 * s + 1], w[3 * s + 2], 0U, r, nc, cc, active);
+      if (s >= 2) {
+        const int c = s - 2;
+        const double2 p0 = CC ? D[c].p0 : xi;
+        double e0;
+        tri_row<TENSOR, MODE>(P, D[c].cell, static_cast<int>(D[c].meta & 15U), D[c].ra, D[c].rg, D[c].p1.x - p0.x, D[c].p1.y - p0.y,
+                              D[c].p2.x - p0.x, D[c].p2.y - p0.y, e0, e1[c], e2[c]);
+        if ((D[c].meta >> 16) != 0) diag += e0;
+      }
+    }
+    __syncthreads();  // the quadrilateral warps have zeroed and filled the image
+#pragma unroll
+    for (int c = 0; c < KT; ++c) {
+      if ((D[c].meta >> 16) != 0) {
+        stage_add(stage, off, D[c].meta, 4, e1[c]);
+        stage_add(stage, off, D[c].meta, 8, e2[c]);
+      }
+    }
+    if (regular) stage[swz(off + info)] += diag;
+  }
+  __syncthreads();
+  if (staged) {
+    const unsigned ballot = __ballot_sync(0xffffffffU, in_range);
+    if (ballot == 0) return;
+    const int total = __shfl_sync(0xffffffffU, v1, 31 - __clz(ballot)) - wbase;
+    double* out = values + wbase;
+    // the two warps of a half share the copy of its image
+    for (int idx = role * 32 + lane; idx < total; idx += 64) {
+      const double v = stage[swz(idx)];
+      out[idx] = P.beta == 0.0 ? v : fma(P.beta, out[idx], v);
+    }
+  } else if (regular && role == 0) {
     const int len = v1 - v0;
     for (int k = 0; k < len; ++k) {
       const double v = stage[swz(off + k)];
@@ -744,10 +874,41 @@ int p1h_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, c
     kern<<<grid, threads, smem, ctx->stream>>>(irows, itotal, p->p1h_qw, p->p1h_tw, p->p1h_rowinfo, mesh->node_coords, mesh->cell_coords, \
                                                p->outer, active, row_list, ifirst, ipf, P, d_values);                                  \
   } while (0)
+  // mixed rows, opt-in (LFGPU_P1H_SPLIT=1): two threads per row in warps of different roles.  Measured on config C2: 0.277 ms
+  // against 0.273 ms with one thread per row -- the serial chain of a row is not what limits the kernel -- so it stays off.
+  static const bool split_env = [] { const char* e = std::getenv("LFGPU_P1H_SPLIT"); return e != nullptr && e[0] == '1'; }();
+#define P1H_SPLIT_KERN(KQ, KT)                                                                                                       \
+  (tensor ? (cc ? k_assemble_p1_rows_split<KQ, KT, true, true, 0> : k_assemble_p1_rows_split<KQ, KT, true, false, 0>)                  \
+          : (cc ? k_assemble_p1_rows_split<KQ, KT, false, true, 0>                                                                    \
+                : (mode == 1 ? k_assemble_p1_rows_split<KQ, KT, false, false, 1>                                                      \
+                             : (mode == 2 ? k_assemble_p1_rows_split<KQ, KT, false, false, 2> : k_assemble_p1_rows_split<KQ, KT, false, false, 0>))))
+#define P1H_SPLIT_LAUNCH(KQ, KT)                                                                                                     \
+  do {                                                                                                                             \
+    auto kern = P1H_SPLIT_KERN(KQ, KT);                                                                                            \
+    const unsigned grid2 = static_cast<unsigned>(cdiv(rows, 64));                                                                  \
+    const size_t smem2 = sizeof(double) * 2 * 32 * kMaxLen;                                                                        \
+    const int ipf2 = cc ? 0 : static_cast<int>((static_cast<int64_t>(ctx->sm_count) * 5 * 64 * pfd_env / 100) & ~static_cast<int64_t>(63)); \
+    kern<<<grid2, 128, smem2, ctx->stream>>>(irows, itotal, p->p1h_qw, p->p1h_tw, p->p1h_rowinfo, mesh->node_coords, mesh->cell_coords,   \
+                                             p->outer, active, row_list, ifirst, ipf2, P, d_values);                                  \
+  } while (0)
   if (p->p1h_kq == 0) P1H_LAUNCH(0, 8);
   else if (p->p1h_kt == 0) P1H_LAUNCH(4, 0);
-  else if (p->p1h_kq == 2) P1H_LAUNCH(2, 4);
-  else P1H_LAUNCH(4, 8);
+  else if (p->p1h_kq == 2) {
+    static const int minb_env = [] { const char* e = std::getenv("LFGPU_P1H_MINB"); return e != nullptr ? std::atoi(e) : 0; }();
+    if (minb_env >= 5 && mode == 1 && !tensor && !cc) {  // experiment: more resident CTAs at fewer registers (config C2's instantiation)
+      auto kern = minb_env == 5 ? k_assemble_p1_rows<2, 4, false, false, 1, 1, 5> : k_assemble_p1_rows<2, 4, false, false, 1, 1, 6>;
+      const int ipf5 = static_cast<int>((static_cast<int64_t>(ctx->sm_count) * minb_env * threads * pfd_env / 100) & ~static_cast<int64_t>(127));
+      kern<<<grid, threads, smem, ctx->stream>>>(irows, itotal, p->p1h_qw, p->p1h_tw, p->p1h_rowinfo, mesh->node_coords, mesh->cell_coords,
+                                                 p->outer, active, row_list, ifirst, ipf5, P, d_values);
+    } else if (split_env) {
+      P1H_SPLIT_LAUNCH(2, 4);
+    } else {
+      P1H_LAUNCH(2, 4);
+    }
+  }
+  else { if (split_env) P1H_SPLIT_LAUNCH(4, 8); else P1H_LAUNCH(4, 8); }
+#undef P1H_SPLIT_KERN
+#undef P1H_SPLIT_LAUNCH
 #undef P1H_KERN
 #undef P1H_LAUNCH
   LFGPU_LAUNCH_CHECK(ctx);

@@ -269,16 +269,38 @@ __device__ __forceinline__ void p2_row(const P2Params& P, const double (&k00)[6]
 
 __device__ __forceinline__ void prefetch_l2(const void* a) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a)); }
 
-// copy-out shared by both kernels: the warp's stage is the image of the contiguous value range of its 32 rows
-template <int LEN>
+// copy-out shared by both kernels: the warp's stage is the image of the contiguous value range of its 32 rows.
+// BULK: the image leaves through ONE bulk copy of the TMA unit (cp.async.bulk shared -> global, SASS UBLKCP) issued by lane 0
+// instead of LEN shared-memory loads + LEN global stores per lane -- ncu showed the edge-row kernel limited by the L1 / LSU pipe
+// (82 % busy: 9 scattered STS, 9 LDS, 9 STG and 11 loads per row), and the copy-out was half of that work.  A bulk copy needs
+// 16-byte aligned addresses and sizes: the image is kept at the parity of its first global element (stage[odd + k] <-> values[wbase
+// + k], odd = wbase & 1), a leading / trailing odd element is stored by an ordinary lane.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+template <int LEN, bool BULK>
 __device__ __forceinline__ void write_rows(bool staged, bool regular, bool in_range, int lane, int32_t v0, int32_t v1, int32_t wbase,
                                            const double* __restrict__ stage, const double* __restrict__ dst, double* __restrict__ values) {
+  if (BULK) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my shared-memory writes -> visible to the async proxy
   __syncwarp();
   if (staged) {
     const unsigned ballot = __ballot_sync(0xffffffffU, in_range);
     if (ballot == 0) return;
     const int total = __shfl_sync(0xffffffffU, v1, 31 - __clz(ballot)) - wbase;
     double* out = values + wbase;
+    if (BULK) {
+      const int odd = wbase & 1;
+      const int n_bulk = (total - odd) & ~1;  // elements [odd, odd + n_bulk) start and end on 16-byte boundaries
+      if (lane == 0 && n_bulk > 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + odd), "r"(smem_u32(stage + 2 * odd)),
+                     "r"(n_bulk * 8)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      if (lane == 1 && odd && total > 0) out[0] = stage[odd];
+      if (lane == 2 && odd + n_bulk < total) out[total - 1] = stage[odd + total - 1];
+      if (lane == 0 && n_bulk > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the stage may go away now
+      return;
+    }
 #pragma unroll
     for (int k = 0; k < LEN; ++k) {
       const int idx = k * 32 + lane;
@@ -289,13 +311,13 @@ __device__ __forceinline__ void write_rows(bool staged, bool regular, bool in_ra
   }
 }
 
-template <int MODE>
+template <int MODE, bool BULK>
 __global__ void __launch_bounds__(128, 4) k_p2_vertex_rows(int n_rows, const int32_t* __restrict__ nbr,
                                                          const uint32_t* __restrict__ slots, const double* __restrict__ node_coords,
                                                          const int32_t* __restrict__ outer, int pf_dist, P2Params P,
                                                          double* __restrict__ values, int first, int end) {
   // rows [first, end) of the n_rows vertex rows (the whole range, or one GPU's share of it)
-  extern __shared__ double stage_all[];
+  extern __shared__ __align__(16) double stage_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = first + blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = r < end;
@@ -332,7 +354,7 @@ __global__ void __launch_bounds__(128, 4) k_p2_vertex_rows(int n_rows, const int
   const int32_t wbase = __shfl_sync(0xffffffffU, v0, 0);
   const bool staged = !__any_sync(0xffffffffU, in_range && !regular && v1 > v0);
   double* stage = stage_all + warp * (32 * (kVertexRowLen + 1));
-  double* dst = stage + (staged ? v0 - wbase : lane * (kVertexRowLen + 1));
+  double* dst = stage + (staged ? (v0 - wbase) + (BULK ? (wbase & 1) : 0) : lane * (kVertexRowLen + 1));
   if (regular) {
     const double2* nc = reinterpret_cast<const double2*>(node_coords);
     const double2 xi = __ldg(nc + r);
@@ -368,7 +390,7 @@ __global__ void __launch_bounds__(128, 4) k_p2_vertex_rows(int n_rows, const int
     dst[w1 & 31U] = first_s + carry_s;
     dst[171 - ssum] = diag;
   }
-  write_rows<kVertexRowLen>(staged, regular, in_range, lane, v0, v1, wbase, stage, dst, values);
+  write_rows<kVertexRowLen, BULK>(staged, regular, in_range, lane, v0, v1, wbase, stage, dst, values);
 }
 
 // vertex rows with closed rings of 3..8 cells (rows_p2_core.h); rows of different lengths (1 + 3m) share a warp, the staged
@@ -431,13 +453,13 @@ __global__ void __launch_bounds__(128, 4) k_p2_vertex_rows_general(int first, in
 }
 
 // 12 CTAs per SM = the occupancy of the measured kernel (40 registers; the row-range arguments had pushed ptxas to 46 -> 10 CTAs)
-template <int MODE>
+template <int MODE, bool BULK>
 __global__ void __launch_bounds__(128, 12) k_p2_edge_rows(int n_edges, int row0, const int32_t* __restrict__ enb,
                                                        const uint32_t* __restrict__ eslots, const double* __restrict__ node_coords,
                                                        const int32_t* __restrict__ outer, int pf_dist, int pfc_dist, P2Params P,
                                                        double* __restrict__ values, int first, int end) {
   // edge rows [first, end) of n_edges; edge e is matrix row row0 + e
-  extern __shared__ double stage_all[];
+  extern __shared__ __align__(16) double stage_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int e = first + blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = e < end;
@@ -480,7 +502,7 @@ __global__ void __launch_bounds__(128, 12) k_p2_edge_rows(int n_edges, int row0,
   const int32_t wbase = __shfl_sync(0xffffffffU, v0, 0);
   const bool staged = !__any_sync(0xffffffffU, in_range && !regular && v1 > v0);
   double* stage = stage_all + warp * (32 * (kEdgeRowLen + 1));
-  double* dst = stage + (staged ? v0 - wbase : lane * (kEdgeRowLen + 1));
+  double* dst = stage + (staged ? (v0 - wbase) + (BULK ? (wbase & 1) : 0) : lane * (kEdgeRowLen + 1));
   if (regular) {
     const double2* nc = reinterpret_cast<const double2*>(node_coords);
     const double2 xp = __ldg(nc + ip), xq = __ldg(nc + iq), x1 = __ldg(nc + io1), x2 = __ldg(nc + io2);
@@ -501,7 +523,13 @@ __global__ void __launch_bounds__(128, 12) k_p2_edge_rows(int n_edges, int row0,
     dst[(w >> 28) & 15U] = t2[5];
     dst[36 - ssum] = t1[3] + t2[3];
   }
-  write_rows<kEdgeRowLen>(staged, regular, in_range, lane, v0, v1, wbase, stage, dst, values);
+  write_rows<kEdgeRowLen, BULK>(staged, regular, in_range, lane, v0, v1, wbase, stage, dst, values);
+}
+
+__global__ void k_count_flags(int64_t n, const uint8_t* __restrict__ flag, int* __restrict__ cnt) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const unsigned b = __ballot_sync(0xffffffffU, i < n && flag[i] != 0);
+  if ((threadIdx.x & 31) == 0 && b != 0) atomicAdd(cnt, __popc(b));
 }
 
 }  // namespace
@@ -563,16 +591,48 @@ int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
   // Unstructured meshes: vertex rows whose ring is not exactly six cells would all go to the generic kernel.  On request
   // (LFGPU_P2_GENERAL=1; the kernel's host/device core is checked on the CPU, its CUDA wrapper has not been on a B200 yet)
   // the plan for closed rings of 3..8 cells replaces the valence-6 plan of the vertex rows.
-  static const bool general_env = [] { const char* e = std::getenv("LFGPU_P2_GENERAL"); return e != nullptr && e[0] == '1'; }();
-  if (general_env) {
-    P2_CHECK(cudaMalloc(&p->p2g_nbr, sizeof(int32_t) * (p2::kMaxRing * static_cast<size_t>(nn) + 128)));
-    P2_CHECK(cudaMalloc(&p->p2g_slots, sizeof(uint32_t) * (p2::kSlotWords * static_cast<size_t>(nn) + 128)));
-    k_p2_vertex_plan_general<<<static_cast<unsigned>(cdiv(nn, 128)), 128, 0, st>>>(nn, p->o_stride, p->pos_row, p->adj_ptr, p->adj,
-                                                                                    mesh->cell_nodes, static_cast<const uint8_t*>(p->pos),
-                                                                                    p->outer, p->p2g_nbr, p->p2g_slots, flag);
-    ctx->launches++;
-    P2_CHECK(cudaGetLastError());
-    p->p2_general = true;
+  // automatic (default): the general plan when more than 5 % of the vertex rows miss the valence-6 plan (Gmsh / Delaunay meshes:
+  // measured on workload u2, 1.0e6 triangles: 0.297 -> 0.153 ms); LFGPU_P2_GENERAL=1 forces it, =0 never builds it
+  static const int general_env = [] { const char* e = std::getenv("LFGPU_P2_GENERAL"); return e == nullptr ? -1 : (e[0] == '1' ? 1 : 0); }();
+  if (general_env != 0) {
+    int* d_cnt = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 384);
+    auto count_flags = [&](const uint8_t* fl, int* h) -> cudaError_t {
+      cudaError_t e = cudaMemsetAsync(d_cnt, 0, sizeof(int), st);
+      if (e != cudaSuccess) return e;
+      k_count_flags<<<static_cast<unsigned>(cdiv(nn, 256)), 256, 0, st>>>(nn, fl, d_cnt);
+      ctx->launches++;
+      e = cudaMemcpyAsync(h, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, st);
+      return e == cudaSuccess ? cudaStreamSynchronize(st) : e;
+    };
+    int cnt6 = 0, cntg = 0;
+    P2_CHECK(count_flags(flag, &cnt6));
+    if (general_env == 1 || static_cast<int64_t>(cnt6) * 20 > nn) {
+      // candidate: plan the vertex rows for closed rings of 3..8 cells; adopted if it takes more than 5 % of the vertex rows off
+      // the generic kernel (boundary rows fail both plans, so a small structured mesh keeps the leaner valence-6 kernel)
+      uint8_t* flag_g = nullptr;
+      P2_CHECK(cudaMalloc(&flag_g, nn));
+      cudaError_t eg = cudaMalloc(&p->p2g_nbr, sizeof(int32_t) * (p2::kMaxRing * static_cast<size_t>(nn) + 128));
+      if (eg == cudaSuccess) eg = cudaMalloc(&p->p2g_slots, sizeof(uint32_t) * (p2::kSlotWords * static_cast<size_t>(nn) + 128));
+      if (eg == cudaSuccess) {
+        k_p2_vertex_plan_general<<<static_cast<unsigned>(cdiv(nn, 128)), 128, 0, st>>>(nn, p->o_stride, p->pos_row, p->adj_ptr, p->adj, mesh->cell_nodes,
+                                                                         static_cast<const uint8_t*>(p->pos), p->outer, p->p2g_nbr, p->p2g_slots, flag_g);
+        ctx->launches++;
+        eg = cudaGetLastError();
+      }
+      if (eg == cudaSuccess) eg = count_flags(flag_g, &cntg);
+      const bool adopt = eg == cudaSuccess && (general_env == 1 || static_cast<int64_t>(cnt6 - cntg) * 20 > nn);
+      if (adopt) eg = cudaMemcpyAsync(flag, flag_g, nn, cudaMemcpyDeviceToDevice, st);
+      if (eg == cudaSuccess) eg = cudaStreamSynchronize(st);
+      cudaFree(flag_g);
+      if (!adopt || eg != cudaSuccess) {
+        cudaFree(p->p2g_nbr);
+        cudaFree(p->p2g_slots);
+        p->p2g_nbr = nullptr;
+        p->p2g_slots = nullptr;
+      }
+      P2_CHECK(eg);
+      p->p2_general = adopt;
+    }
   }
   P2_CHECK(cudaMalloc(&iota, sizeof(int32_t) * p->n_outer));
   P2_CHECK(cudaMalloc(&d_num, sizeof(int64_t)));
@@ -628,6 +688,9 @@ int p2_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* 
   // LFGPU_EDGE_PFC (percent of the plan distance, default 0 = off): coordinate prefetch of the edge rows through the plan
   static const int pfc_env = [] { const char* e = std::getenv("LFGPU_EDGE_PFC"); return e != nullptr ? std::atoi(e) : 0; }();
   const int ipc_e = pfc_env > 0 && ipf_e > 0 ? std::max(128, static_cast<int>((static_cast<int64_t>(ipf_e) * pfc_env / 100) & ~static_cast<int64_t>(127))) : 0;
+  // copy-out of the staged rows by the TMA unit (LFGPU_P2_BULK=0: by the lanes); needs a 16-byte aligned value array
+  static const bool bulk_env = [] { const char* e = std::getenv("LFGPU_P2_BULK"); return e == nullptr || e[0] != '0'; }();
+  const bool bulk = bulk_env && (reinterpret_cast<uintptr_t>(d_values) & 15) == 0;
   const size_t smem_v = sizeof(double) * (threads / 32) * 32 * (kVertexRowLen + 1);
   const size_t smem_e = sizeof(double) * (threads / 32) * 32 * (kEdgeRowLen + 1);
   // the share of the range in the vertex rows [0, nn) and in the edge rows [nn, nn + ne)
@@ -649,17 +712,17 @@ int p2_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* 
   } else if (v_end > v_first) {
     const unsigned gv = static_cast<unsigned>(cdiv(v_end - v_first, threads));
     if (simple)
-      k_p2_vertex_rows<0><<<gv, threads, smem_v, ctx->stream>>>(nn, p->p2v_nbr, p->p2v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values, v_first, v_end);
+      (bulk ? k_p2_vertex_rows<0, true> : k_p2_vertex_rows<0, false>)<<<gv, threads, smem_v, ctx->stream>>>(nn, p->p2v_nbr, p->p2v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values, v_first, v_end);
     else
-      k_p2_vertex_rows<1><<<gv, threads, smem_v, ctx->stream>>>(nn, p->p2v_nbr, p->p2v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values, v_first, v_end);
+      (bulk ? k_p2_vertex_rows<1, true> : k_p2_vertex_rows<1, false>)<<<gv, threads, smem_v, ctx->stream>>>(nn, p->p2v_nbr, p->p2v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values, v_first, v_end);
     LFGPU_LAUNCH_CHECK(ctx);
   }
   if (e_end > e_first) {
     const unsigned ge = static_cast<unsigned>(cdiv(e_end - e_first, threads));
     if (simple)
-      k_p2_edge_rows<0><<<ge, threads, smem_e, ctx->stream>>>(ne, nn, p->p2e_nbr, p->p2e_slots, mesh->node_coords, p->outer, ipf_e, ipc_e, P, d_values, e_first, e_end);
+      (bulk ? k_p2_edge_rows<0, true> : k_p2_edge_rows<0, false>)<<<ge, threads, smem_e, ctx->stream>>>(ne, nn, p->p2e_nbr, p->p2e_slots, mesh->node_coords, p->outer, ipf_e, ipc_e, P, d_values, e_first, e_end);
     else
-      k_p2_edge_rows<1><<<ge, threads, smem_e, ctx->stream>>>(ne, nn, p->p2e_nbr, p->p2e_slots, mesh->node_coords, p->outer, ipf_e, ipc_e, P, d_values, e_first, e_end);
+      (bulk ? k_p2_edge_rows<1, true> : k_p2_edge_rows<1, false>)<<<ge, threads, smem_e, ctx->stream>>>(ne, nn, p->p2e_nbr, p->p2e_slots, mesh->node_coords, p->outer, ipf_e, ipc_e, P, d_values, e_first, e_end);
     LFGPU_LAUNCH_CHECK(ctx);
   }
   return LFGPU_OK;

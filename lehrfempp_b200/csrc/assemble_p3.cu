@@ -352,6 +352,12 @@ __global__ void __launch_bounds__(128, 4) k_p3_cell_rows(int row0, const uint32_
   write_rows<kCellRowLen, true>(true, in_range, in_range, lane, v0, v1, wbase, stage, stage, values, off);
 }
 
+__global__ void k_count_flags(int64_t n, const uint8_t* __restrict__ flag, int* __restrict__ cnt) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const unsigned b = __ballot_sync(0xffffffffU, i < n && flag[i] != 0);
+  if ((threadIdx.x & 31) == 0 && b != 0) atomicAdd(cnt, __popc(b));
+}
+
 }  // namespace
 
 // ---- host side -----------------------------------------------------------------------------------------------------------
@@ -421,16 +427,48 @@ int p3_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
   P3_CHECK(cudaGetLastError());
   // unstructured meshes, on request (LFGPU_P3_GENERAL=1; core checked on the CPU, wrapper not yet run on a B200): the plan
   // for closed rings of 3..8 cells replaces the valence-6 plan of the vertex rows
-  static const bool general_env = [] { const char* e = std::getenv("LFGPU_P3_GENERAL"); return e != nullptr && e[0] == '1'; }();
-  if (general_env) {
-    P3_CHECK(cudaMalloc(&p->p3g_nbr, sizeof(int32_t) * (kMaxRing * static_cast<size_t>(nn) + 128)));
-    P3_CHECK(cudaMalloc(&p->p3g_slots, sizeof(uint32_t) * (kGeneralSlotWords * static_cast<size_t>(nn) + 128)));
-    k_p3_vertex_plan_general<<<static_cast<unsigned>(cdiv(nn, 128)), 128, 0, st>>>(nn, p->o_stride, p->pos_row, p->adj_ptr, p->adj,
-                                                                                    mesh->cell_nodes, static_cast<const uint8_t*>(p->pos),
-                                                                                    p->outer, p->p3g_nbr, p->p3g_slots, flag);
-    ctx->launches++;
-    P3_CHECK(cudaGetLastError());
-    p->p3_general = true;
+  // automatic (default): the general plan when more than 5 % of the vertex rows miss the valence-6 plan (Gmsh / Delaunay meshes:
+  // measured on workload u2, 1.0e6 triangles: 0.297 -> 0.153 ms); LFGPU_P3_GENERAL=1 forces it, =0 never builds it
+  static const int general_env = [] { const char* e = std::getenv("LFGPU_P3_GENERAL"); return e == nullptr ? -1 : (e[0] == '1' ? 1 : 0); }();
+  if (general_env != 0) {
+    int* d_cnt = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 384);
+    auto count_flags = [&](const uint8_t* fl, int* h) -> cudaError_t {
+      cudaError_t e = cudaMemsetAsync(d_cnt, 0, sizeof(int), st);
+      if (e != cudaSuccess) return e;
+      k_count_flags<<<static_cast<unsigned>(cdiv(nn, 256)), 256, 0, st>>>(nn, fl, d_cnt);
+      ctx->launches++;
+      e = cudaMemcpyAsync(h, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, st);
+      return e == cudaSuccess ? cudaStreamSynchronize(st) : e;
+    };
+    int cnt6 = 0, cntg = 0;
+    P3_CHECK(count_flags(flag, &cnt6));
+    if (general_env == 1 || static_cast<int64_t>(cnt6) * 20 > nn) {
+      // candidate: plan the vertex rows for closed rings of 3..8 cells; adopted if it takes more than 5 % of the vertex rows off
+      // the generic kernel (boundary rows fail both plans, so a small structured mesh keeps the leaner valence-6 kernel)
+      uint8_t* flag_g = nullptr;
+      P3_CHECK(cudaMalloc(&flag_g, nn));
+      cudaError_t eg = cudaMalloc(&p->p3g_nbr, sizeof(int32_t) * (kMaxRing * static_cast<size_t>(nn) + 128));
+      if (eg == cudaSuccess) eg = cudaMalloc(&p->p3g_slots, sizeof(uint32_t) * (kGeneralSlotWords * static_cast<size_t>(nn) + 128));
+      if (eg == cudaSuccess) {
+        k_p3_vertex_plan_general<<<static_cast<unsigned>(cdiv(nn, 128)), 128, 0, st>>>(nn, p->o_stride, p->pos_row, p->adj_ptr, p->adj, mesh->cell_nodes,
+                                                                         static_cast<const uint8_t*>(p->pos), p->outer, p->p3g_nbr, p->p3g_slots, flag_g);
+        ctx->launches++;
+        eg = cudaGetLastError();
+      }
+      if (eg == cudaSuccess) eg = count_flags(flag_g, &cntg);
+      const bool adopt = eg == cudaSuccess && (general_env == 1 || static_cast<int64_t>(cnt6 - cntg) * 20 > nn);
+      if (adopt) eg = cudaMemcpyAsync(flag, flag_g, nn, cudaMemcpyDeviceToDevice, st);
+      if (eg == cudaSuccess) eg = cudaStreamSynchronize(st);
+      cudaFree(flag_g);
+      if (!adopt || eg != cudaSuccess) {
+        cudaFree(p->p3g_nbr);
+        cudaFree(p->p3g_slots);
+        p->p3g_nbr = nullptr;
+        p->p3g_slots = nullptr;
+      }
+      P3_CHECK(eg);
+      p->p3_general = adopt;
+    }
   }
   P3_CHECK(cudaMalloc(&iota, sizeof(int32_t) * p->n_outer));
   P3_CHECK(cudaMalloc(&d_num, sizeof(int64_t)));
