@@ -409,6 +409,13 @@ struct MeshFunctionGlobal {
   }
 };
 
+// A continuous piecewise (bi)linear coefficient given by its values at the mesh nodes, in node-index order: what
+// lf::fe::MeshFunctionFE(fe_space_o1, coeff_vector) evaluates (fe/mesh_function_fe.h).  Travels as LFGPU_COEFF_NODAL: 8 bytes per
+// node instead of 8 bytes per quadrature point.
+struct MeshFunctionNodal {
+  std::vector<double> values;  // [n_nodes]
+};
+
 template <class MF>
 struct CoeffTraits;  // static HostCoeff describe(const MF&, const double* qp_xy /*[n_cells][stride][2]*/, n_cells, stride)
 
@@ -429,6 +436,17 @@ struct CoeffTraits<MeshFunctionConstant<Matrix2>> {
     HostCoeff c;
     c.kind = LFGPU_COEFF_CONST_2X2;
     c.c[0] = mf.value.a[0][0]; c.c[1] = mf.value.a[0][1]; c.c[2] = mf.value.a[1][0]; c.c[3] = mf.value.a[1][1];
+    return c;
+  }
+};
+template <>
+struct CoeffTraits<MeshFunctionNodal> {
+  static constexpr bool needs_points = false;
+  static HostCoeff describe(const MeshFunctionNodal& mf, const double*, std::int64_t, long) {
+    HostCoeff c;
+    c.kind = LFGPU_COEFF_NODAL;
+    c.table = mf.values;
+    c.stride = 1;
     return c;
   }
 };
@@ -731,6 +749,139 @@ Vector AssembleVectorLocally(Context& ctx, unsigned codim, const DOFH& dof_handl
   Vector v(ctx);
   AssembleVectorLocally<A>(codim, dof_handler, entity_vector_provider, v);
   return v;
+}
+
+// ---- several GPUs (include/lfgpu.h: lfgpu_multi_*) ------------------------------------------------------------------------------
+// TMPMATRIX for a device LIST: the GPU overload below cuts the problem into one sub-problem per device (Morton cell ranges, every
+// device owns the rows of its cells, one-cell halo), assembles on all devices at once and leaves the rows where they were computed.
+// Accumulates like COOMatrix (assembler.h:84-88).  Part(k) hands out device k's rows with GLOBAL indices; Gather() concatenates
+// the parts into one compressed matrix in the reference's row order (for checks and for callers that want makeSparse()'s result).
+class MultiCsrMatrix {
+ public:
+  explicit MultiCsrMatrix(const std::vector<int>& device_ids, int major = LFGPU_COL_MAJOR) : major_(major) {
+    const int rc = lfgpu_multi_create(device_ids.data(), static_cast<int>(device_ids.size()), &m_);
+    if (rc != 0) throw Error(rc, std::string("lfgpu_multi_create: ") + lfgpu_last_error(nullptr));
+  }
+  ~MultiCsrMatrix() { lfgpu_multi_destroy(m_); }
+  MultiCsrMatrix(const MultiCsrMatrix&) = delete;
+  MultiCsrMatrix& operator=(const MultiCsrMatrix&) = delete;
+  void check(int rc, const char* where) const {
+    if (rc != 0) throw Error(rc, std::string(where) + ": " + lfgpu_multi_last_error(m_));
+  }
+  [[nodiscard]] int NumDevices() const { return lfgpu_multi_num_devices(m_); }
+  [[nodiscard]] lfgpu_multi* get() const { return m_; }
+  void setZero() {
+    if (ready_) check(lfgpu_multi_set_zero(m_), "lfgpu_multi_set_zero");
+    empty_ = true;
+  }
+  struct Block {
+    std::vector<std::int64_t> rows, row_ptr;  // global outer indices (ascending), offsets into cols / values
+    std::vector<std::int32_t> cols;           // global inner indices, ascending inside a row
+    std::vector<double> values;
+  };
+  [[nodiscard]] Block Part(int k) const {
+    Block b;
+    std::int64_t nr = 0, nnz = 0;
+    check(lfgpu_multi_part_sizes(m_, k, &nr, &nnz, nullptr, nullptr, nullptr), "lfgpu_multi_part_sizes");
+    b.rows.resize(nr);
+    b.row_ptr.resize(nr + 1);
+    b.cols.resize(nnz);
+    b.values.resize(nnz);
+    check(lfgpu_multi_part_download(m_, k, b.rows.data(), b.row_ptr.data(), b.cols.data(), b.values.data()), "lfgpu_multi_part_download");
+    return b;
+  }
+  // all parts as ONE compressed matrix with the reference's index arrays (outer [n + 1], inner, values)
+  void Gather(std::vector<std::int64_t>& outer, std::vector<std::int32_t>& inner, std::vector<double>& values) const {
+    outer.assign(n_outer_ + 1, 0);
+    std::vector<Block> blocks;
+    for (int k = 0; k < NumDevices(); ++k) blocks.push_back(Part(k));
+    for (const auto& b : blocks)
+      for (std::size_t i = 0; i < b.rows.size(); ++i) outer[b.rows[i] + 1] = b.row_ptr[i + 1] - b.row_ptr[i];
+    for (std::int64_t r = 0; r < n_outer_; ++r) outer[r + 1] += outer[r];
+    inner.resize(outer[n_outer_]);
+    values.resize(outer[n_outer_]);
+    for (const auto& b : blocks)
+      for (std::size_t i = 0; i < b.rows.size(); ++i) {
+        std::copy(b.cols.begin() + b.row_ptr[i], b.cols.begin() + b.row_ptr[i + 1], inner.begin() + outer[b.rows[i]]);
+        std::copy(b.values.begin() + b.row_ptr[i], b.values.begin() + b.row_ptr[i + 1], values.begin() + outer[b.rows[i]]);
+      }
+  }
+  template <class A, class DOFH>
+  void Prepare(const DOFH& trial, const DOFH& test) {
+    if (ready_) return;
+    if (&trial != &test) throw Error(LFGPU_ERR_UNSUPPORTED, "the multi-device matrix needs trial space == test space");
+    const auto& mesh = A::mesh(test);
+    flat_ = Flatten<A>(mesh);
+    std::vector<std::int64_t> dofs;
+    std::vector<std::uint8_t> nl;
+    int stride = 0;
+    FlattenDofs<A>(test, mesh, dofs, nl, stride);
+    n_outer_ = A::num_dofs(test);
+    check(lfgpu_multi_setup(m_, flat_.n_nodes, flat_.node_coords.data(), flat_.n_cells, flat_.cell_nodes.data(),
+                            flat_.coords_match_nodes ? nullptr : flat_.cell_coords.data(), n_outer_, stride, dofs.data(), nl.data(), major_),
+          "lfgpu_multi_setup");
+    ready_ = true;
+    empty_ = true;
+  }
+  [[nodiscard]] const FlatMesh& flat() const { return flat_; }
+  bool empty_ = true;
+
+ private:
+  lfgpu_multi* m_ = nullptr;
+  int major_;
+  bool ready_ = false;
+  std::int64_t n_outer_ = 0;
+  FlatMesh flat_;
+};
+
+// GPU overload of AssembleMatrixLocally for a device list.  Coefficient functors are tabulated on the host at the quadrature points
+// of ALL cells (on device 0, which sees the whole mesh for the time of that call); every device then receives its cells' entries.
+template <class A, class DOFH, class PROVIDER, class ALPHA = typename PROVIDER::alpha_type, class GAMMA = typename PROVIDER::gamma_type>
+void AssembleMatrixLocally(unsigned codim, const DOFH& dof_handler_trial, const DOFH& dof_handler_test, PROVIDER& emp, MultiCsrMatrix& matrix) {
+  if (codim != 0) throw Error(LFGPU_ERR_UNSUPPORTED, "the GPU overload assembles cell (codim 0) contributions");
+  matrix.template Prepare<A>(dof_handler_trial, dof_handler_test);
+  const Rules& r = emp.QuadRules();
+  lfgpu_quad qt{static_cast<int>(r.w_tria.size()), r.pts_tria.data(), r.w_tria.data()};
+  lfgpu_quad qq{static_cast<int>(r.w_quad.size()), r.pts_quad.data(), r.w_quad.data()};
+  const lfgpu_quad* pqt = (emp.HasCustomRules() && r.has_tria) ? &qt : nullptr;
+  const lfgpu_quad* pqq = (emp.HasCustomRules() && r.has_quad) ? &qq : nullptr;
+  bool all_active = true;
+  detail::activity_flags<A>(A::mesh(dof_handler_trial), emp, &all_active);
+  if (!all_active) throw Error(LFGPU_ERR_UNSUPPORTED, "the multi-device overload assembles all cells (isActive must be true)");
+  const FlatMesh& f = matrix.flat();
+  std::vector<double> xy;
+  int stride = 0;
+  if (CoeffTraits<ALPHA>::needs_points || CoeffTraits<GAMMA>::needs_points) {
+    stride = kMaxPoints;
+    lfgpu_ctx* c0 = lfgpu_multi_ctx(matrix.get(), 0);
+    lfgpu_mesh* whole = nullptr;
+    int rc = lfgpu_mesh_upload(c0, f.n_nodes, f.node_coords.data(), f.n_cells, f.cell_nodes.data(),
+                               f.coords_match_nodes ? nullptr : f.cell_coords.data(), &whole);
+    if (rc != 0) throw Error(rc, std::string("lfgpu_mesh_upload: ") + lfgpu_last_error(c0));
+    xy.resize(static_cast<std::size_t>(f.n_cells) * stride * 2);
+    void* d = nullptr;
+    rc = lfgpu_malloc(c0, 8 * static_cast<std::int64_t>(xy.size()), &d);
+    if (rc == 0) rc = lfgpu_qp_coords(c0, whole, emp.Degree(), pqt, pqq, stride, static_cast<double*>(d));
+    if (rc == 0) rc = lfgpu_memcpy_d2h(c0, xy.data(), d, 8 * static_cast<std::int64_t>(xy.size()));
+    if (rc == 0) rc = lfgpu_ctx_synchronize(c0);
+    if (d) lfgpu_free(c0, d);
+    lfgpu_mesh_destroy(whole);
+    if (rc != 0) throw Error(rc, std::string("quadrature points: ") + lfgpu_last_error(c0));
+  }
+  const HostCoeff ha = CoeffTraits<ALPHA>::describe(emp.Alpha(), xy.data(), f.n_cells, stride);
+  const HostCoeff hg = CoeffTraits<GAMMA>::describe(emp.Gamma(), xy.data(), f.n_cells, stride);
+  auto as_c = [](const HostCoeff& h) {
+    lfgpu_coeff c{};
+    c.kind = h.kind;
+    for (int i = 0; i < 4; ++i) c.c[i] = h.c[i];
+    c.stride = h.stride;
+    c.data = h.table.empty() ? nullptr : h.table.data();  // HOST tables over the whole mesh (lfgpu_multi_assemble_reaction_diffusion)
+    return c;
+  };
+  const lfgpu_coeff ca = as_c(ha), cg = as_c(hg);
+  matrix.check(lfgpu_multi_assemble_reaction_diffusion(matrix.get(), emp.Degree(), pqt, pqq, &ca, &cg, matrix.empty_ ? 0 : 1),
+               "lfgpu_multi_assemble_reaction_diffusion");
+  matrix.empty_ = false;
 }
 
 // ---- edge (codim-1) providers ------------------------------------------------------------------------------------------------

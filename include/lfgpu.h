@@ -204,6 +204,10 @@ typedef struct {
 #define LFGPU_COEFF_PER_CELL 2     /* data[n_cells]                                                                  */
 #define LFGPU_COEFF_PER_QP 3       /* data[n_cells][stride], value at quadrature point k of the cell's rule          */
 #define LFGPU_COEFF_PER_QP_2X2 4   /* data[n_cells][stride][4] row-major 2x2                                         */
+#define LFGPU_COEFF_NODAL 5        /* data[n_nodes]: a continuous piecewise (bi)linear function given by its values at the mesh
+                                      nodes (lf::fe::MeshFunctionFE of a FeSpaceLagrangeO1 function, fe/mesh_function_fe.h),
+                                      evaluated at the quadrature points with the cell's vertex shape functions; scalar.
+                                      8 B per node of traffic instead of 8 B per quadrature point.  Cell terms only.        */
 typedef struct {
   int kind;
   double c[4];

@@ -262,6 +262,11 @@ class Coeff:
     def per_qp_2x2(dev, stride):
         return Coeff(4, data=dev, stride=stride)
 
+    @staticmethod
+    def nodal(dev):
+        """Continuous piecewise (bi)linear coefficient given by its values at the mesh nodes (LFGPU_COEFF_NODAL)."""
+        return Coeff(5, data=dev, stride=1)
+
     def ref(self):
         return C.byref(self._c)
 

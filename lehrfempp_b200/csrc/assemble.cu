@@ -77,6 +77,7 @@ struct MeshView {
 
 struct CellGeom {
   double x[4], y[4];
+  uint32_t v[4];  // node indices (slot 3 = LFGPU_IDX_NIL for a triangle)
   bool quad;
 };
 
@@ -84,6 +85,7 @@ __device__ __forceinline__ CellGeom load_geom(const MeshView& mv, int64_t cell) 
   CellGeom g;
   const uint4 v = __ldg(reinterpret_cast<const uint4*>(mv.cell_nodes) + cell);
   g.quad = (v.w != LFGPU_IDX_NIL);
+  g.v[0] = v.x; g.v[1] = v.y; g.v[2] = v.z; g.v[3] = v.w;
   if (mv.cell_coords != nullptr) {
     const double2* cc = reinterpret_cast<const double2*>(mv.cell_coords) + 4 * cell;
 #pragma unroll
@@ -147,6 +149,9 @@ __device__ __forceinline__ void eval_alpha(const DevCoeff& A, int64_t cell, int 
     case LFGPU_COEFF_PER_QP:
       a00 = a11 = __ldg(A.data + cell * A.stride + k); a01 = a10 = 0.0;
       break;
+    case LFGPU_COEFF_NODAL:  // the caller overwrites a00 = a11 with the interpolated value (element_row)
+      a00 = a11 = 0.0; a01 = a10 = 0.0;
+      break;
     default: {  // PER_QP_2X2
       const double* p = A.data + (cell * A.stride + k) * 4;
       a00 = __ldg(p); a01 = __ldg(p + 1); a10 = __ldg(p + 2); a11 = __ldg(p + 3);
@@ -158,12 +163,24 @@ __device__ __forceinline__ void eval_alpha(const DevCoeff& A, int64_t cell, int 
     a10 = t;
   }
 }
+// LFGPU_COEFF_NODAL: sum over the cell's vertices of N_a(xhat) data[node_a], N_a = FeLagrangeO1Tria / Quad (lagr_fe.h:110-128,
+// 218-240) at the reference point (x0, x1) of quadrature point k
+__device__ __forceinline__ double eval_nodal(const DevCoeff& G, const CellGeom& g, double x0, double x1) {
+  if (!g.quad) return (1.0 - x0 - x1) * __ldg(G.data + g.v[0]) + x0 * __ldg(G.data + g.v[1]) + x1 * __ldg(G.data + g.v[2]);
+  return (1.0 - x0) * (1.0 - x1) * __ldg(G.data + g.v[0]) + x0 * (1.0 - x1) * __ldg(G.data + g.v[1]) + x0 * x1 * __ldg(G.data + g.v[2]) +
+         (1.0 - x0) * x1 * __ldg(G.data + g.v[3]);
+}
 __device__ __forceinline__ double eval_scalar(const DevCoeff& G, int64_t cell, int k) {
   switch (G.kind) {
     case LFGPU_COEFF_CONST: return G.c[0];
     case LFGPU_COEFF_PER_CELL: return __ldg(G.data + cell);
     default: return __ldg(G.data + cell * G.stride + k);  // PER_QP
   }
+}
+// with the cell at hand (needed by LFGPU_COEFF_NODAL)
+__device__ __forceinline__ double eval_scalar(const DevCoeff& G, int64_t cell, int k, const CellGeom& g, const TabView& T) {
+  if (G.kind == LFGPU_COEFF_NODAL) return eval_nodal(G, g, T.qx[k], T.qy[k]);
+  return eval_scalar(G, cell, k);
 }
 __device__ __forceinline__ bool cellwise_const(const DevCoeff& c) { return c.kind <= LFGPU_COEFF_PER_CELL; }
 __device__ __forceinline__ double fast_rcp(double x);
@@ -270,12 +287,13 @@ __device__ __forceinline__ void element_row(const CellGeom& g, const TabView& T,
     const double i00 = j11 * idet, i01 = -j01 * idet, i10 = -j10 * idet, i11 = j00 * idet;
     double a00, a01, a10, a11;
     eval_alpha(alpha, cell, k, transpose_alpha, a00, a01, a10, a11);
+    if (alpha.kind == LFGPU_COEFF_NODAL) a00 = a11 = eval_nodal(alpha, g, T.qx[k], T.qy[k]);
     const double gxa = T.gx[a * nq + k], gya = T.gy[a * nq + k];
     // G_a = Jinv^T ghat_a ; u = A G_a ; s = wd * Jinv u
     const double Gx = i00 * gxa + i10 * gya, Gy = i01 * gxa + i11 * gya;
     const double ux = a00 * Gx + a01 * Gy, uy = a10 * Gx + a11 * Gy;
     const double sx = wd * (i00 * ux + i01 * uy), sy = wd * (i10 * ux + i11 * uy);
-    const double mm = wd * eval_scalar(gamma, cell, k) * T.phi[a * nq + k];
+    const double mm = wd * eval_scalar(gamma, cell, k, g, T) * T.phi[a * nq + k];
 #pragma unroll
     for (int b = 0; b < NSF; ++b) {
       if (b < nsf) acc[b] += sx * T.gx[b * nq + k] + sy * T.gy[b * nq + k] + mm * T.phi[b * nq + k];
@@ -607,7 +625,7 @@ __global__ void __launch_bounds__(256) k_load_atomic(Tables hdr, const double* _
   if (!g.quad) jacobian(g, 0.0, 0.0, j00, j01, j10, j11);
   for (int k = 0; k < T.nq; ++k) {
     if (g.quad) jacobian(g, T.qx[k], T.qy[k], j00, j01, j10, j11);
-    const double s = T.w[k] * fabs(j00 * j11 - j01 * j10) * eval_scalar(f, cell, k);
+    const double s = T.w[k] * fabs(j00 * j11 - j01 * j10) * eval_scalar(f, cell, k, g, T);
 #pragma unroll
     for (int b = 0; b < NSF; ++b) {
       if (b < T.nsf) acc[b] += s * T.phi[b * T.nq + k];
@@ -652,7 +670,7 @@ __global__ void __launch_bounds__(256) k_load_gather(Tables hdr, const double* _
     double e = 0.0;
     for (int k = 0; k < T.nq; ++k) {
       if (g.quad) jacobian(g, T.qx[k], T.qy[k], j00, j01, j10, j11);
-      const double s = T.w[k] * fabs(j00 * j11 - j01 * j10) * eval_scalar(f, cell, k);
+      const double s = T.w[k] * fabs(j00 * j11 - j01 * j10) * eval_scalar(f, cell, k, g, T);
       e += s * T.phi[a * T.nq + k];
     }
     sum += e;
@@ -746,6 +764,9 @@ int check_coeff(lfgpu_ctx* ctx, const lfgpu_coeff* c, bool allow_tensor, const H
       break;
     case LFGPU_COEFF_PER_CELL:
       if (c->data == nullptr) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "PER_CELL coefficient without data");
+      break;
+    case LFGPU_COEFF_NODAL:
+      if (c->data == nullptr) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "NODAL coefficient without data");
       break;
     case LFGPU_COEFF_PER_QP_2X2:
       if (!allow_tensor) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "this coefficient must be scalar valued");
@@ -997,7 +1018,7 @@ int lfgpu::assemble_rd_impl(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_
     // P1 row kernel (assemble_p1h.cu): quadrilaterals / hybrid meshes, coefficients per cell or per quadrature point, activity
     // masks, cell corners that are not bitwise the node positions; rules invariant under the rotations of the reference cell
     static const bool p1h_env = [] { const char* e = std::getenv("LFGPU_P1_ROWS"); return e == nullptr || e[0] != '0'; }();
-    if (degree == 1 && fan_query == nullptr && p1h_env) {
+    if (degree == 1 && fan_query == nullptr && p1h_env && da.kind != LFGPU_COEFF_NODAL && dg.kind != LFGPU_COEFF_NODAL) {
       FeTable ft, fq;
       std::string err;
       const bool dflt = qr_tria == nullptr && qr_quad == nullptr;
@@ -1027,7 +1048,7 @@ int lfgpu::assemble_rd_impl(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_
     // independent of the local vertex numbering), every cell active, all rows, overwrite.  LFGPU_ALGO_FAN asks for them
     // explicitly; LFGPU_ALGO_AUTO takes them unless LFGPU_P2_ROWS=0.
     static const bool p2_env = [] { const char* e = std::getenv("LFGPU_P2_ROWS"); return e == nullptr || e[0] != '0'; }();
-    if (degree == 2 && fan_query == nullptr && (algo == LFGPU_ALGO_FAN || p2_env) && active == nullptr && beta == 0.0 &&
+    if (degree == 2 && fan_query == nullptr && (algo == LFGPU_ALGO_FAN || p2_env) && active == nullptr &&
         d_row_list == nullptr && qr_tria == nullptr && qr_quad == nullptr && da.kind <= LFGPU_COEFF_CONST_2X2 &&
         dg.kind == LFGPU_COEFF_CONST && mesh->n_quad == 0 && mesh->cell_coords == nullptr && ht.hdr.nsf[0] == 6) {
       if ((rc = p2_rows_prepare(ctx, mesh, const_cast<lfgpu_pattern*>(p))) != LFGPU_OK) return rc;
@@ -1047,13 +1068,13 @@ int lfgpu::assemble_rd_impl(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_
         }
         const int nq = ht.hdr.nq[0];
         const double* k00 = ht.blob.data() + ht.hdr.off[0] + 3 * nq + 3 * 6 * nq;  // pack_type: w qx qy | phi gx gy | k00 k01 k10 k11 m
-        return p2_rows_launch(ctx, mesh, p, a, tensor, dg.c[0], k00, k00 + 36, k00 + 72, k00 + 108, k00 + 144, d_values, r0, r1);
+        return p2_rows_launch(ctx, mesh, p, a, tensor, dg.c[0], k00, k00 + 36, k00 + 72, k00 + 108, k00 + 144, d_values, r0, r1, beta);
       }
     }
     // P3 row kernels (assemble_p3.cu), same conditions (their host/device core is also checked against the oracle on the CPU);
     // LFGPU_P3_ROWS=0 keeps LFGPU_ALGO_AUTO on the item kernel.
     static const bool p3_env = [] { const char* e = std::getenv("LFGPU_P3_ROWS"); return e == nullptr || e[0] != '0'; }();
-    if (degree == 3 && fan_query == nullptr && (algo == LFGPU_ALGO_FAN || p3_env) && active == nullptr && beta == 0.0 &&
+    if (degree == 3 && fan_query == nullptr && (algo == LFGPU_ALGO_FAN || p3_env) && active == nullptr &&
         d_row_list == nullptr && qr_tria == nullptr && qr_quad == nullptr && da.kind <= LFGPU_COEFF_CONST_2X2 &&
         dg.kind == LFGPU_COEFF_CONST && mesh->n_quad == 0 && mesh->cell_coords == nullptr && ht.hdr.nsf[0] == 10) {
       if ((rc = p3_rows_prepare(ctx, mesh, const_cast<lfgpu_pattern*>(p))) != LFGPU_OK) return rc;
@@ -1072,7 +1093,7 @@ int lfgpu::assemble_rd_impl(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_
         }
         const int nq = ht.hdr.nq[0];
         const double* k00 = ht.blob.data() + ht.hdr.off[0] + 3 * nq + 3 * 10 * nq;
-        return p3_rows_launch(ctx, mesh, p, a, tensor, dg.c[0], k00, k00 + 100, k00 + 200, k00 + 300, k00 + 400, d_values, r0, r1);
+        return p3_rows_launch(ctx, mesh, p, a, tensor, dg.c[0], k00, k00 + 100, k00 + 200, k00 + 300, k00 + 400, d_values, r0, r1, beta);
       }
     }
     if (algo == LFGPU_ALGO_FAN) LFGPU_FAIL(ctx, LFGPU_ERR_UNSUPPORTED, "LFGPU_ALGO_FAN needs P1, P2 or P3 on a triangle mesh with constant coefficients and no activity mask");

@@ -279,7 +279,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast
 
 template <int LEN, bool BULK>
 __device__ __forceinline__ void write_rows(bool staged, bool regular, bool in_range, int lane, int32_t v0, int32_t v1, int32_t wbase,
-                                           const double* __restrict__ stage, const double* __restrict__ dst, double* __restrict__ values) {
+                                           const double* __restrict__ stage, const double* __restrict__ dst, double* __restrict__ values,
+                                           double beta) {
   if (BULK) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my shared-memory writes -> visible to the async proxy
   __syncwarp();
   if (staged) {
@@ -287,6 +288,15 @@ __device__ __forceinline__ void write_rows(bool staged, bool regular, bool in_ra
     if (ballot == 0) return;
     const int total = __shfl_sync(0xffffffffU, v1, 31 - __clz(ballot)) - wbase;
     double* out = values + wbase;
+    if (beta != 0.0) {  // accumulate (assembler.h:84-88): the lanes read what is there; image element k sits at stage[odd + k]
+      const int odd = BULK ? (wbase & 1) : 0;
+#pragma unroll
+      for (int k = 0; k < LEN; ++k) {
+        const int idx = k * 32 + lane;
+        if (idx < total) out[idx] = fma(beta, out[idx], stage[odd + idx]);
+      }
+      return;
+    }
     if (BULK) {
       const int odd = wbase & 1;
       const int n_bulk = (total - odd) & ~1;  // elements [odd, odd + n_bulk) start and end on 16-byte boundaries
@@ -307,15 +317,15 @@ __device__ __forceinline__ void write_rows(bool staged, bool regular, bool in_ra
       if (idx < total) out[idx] = stage[idx];
     }
   } else if (regular) {
-    for (int k = 0; k < LEN; ++k) values[v0 + k] = dst[k];
+    for (int k = 0; k < LEN; ++k) values[v0 + k] = beta == 0.0 ? dst[k] : fma(beta, values[v0 + k], dst[k]);
   }
 }
 
 template <int MODE, bool BULK>
-__global__ void __launch_bounds__(128, 4) k_p2_vertex_rows(int n_rows, const int32_t* __restrict__ nbr,
+__global__ void __launch_bounds__(128, 6) k_p2_vertex_rows(int n_rows, const int32_t* __restrict__ nbr,
                                                          const uint32_t* __restrict__ slots, const double* __restrict__ node_coords,
                                                          const int32_t* __restrict__ outer, int pf_dist, P2Params P,
-                                                         double* __restrict__ values, int first, int end) {
+                                                         double* __restrict__ values, int first, int end, double beta) {
   // rows [first, end) of the n_rows vertex rows (the whole range, or one GPU's share of it)
   extern __shared__ __align__(16) double stage_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -390,7 +400,7 @@ __global__ void __launch_bounds__(128, 4) k_p2_vertex_rows(int n_rows, const int
     dst[w1 & 31U] = first_s + carry_s;
     dst[171 - ssum] = diag;
   }
-  write_rows<kVertexRowLen, BULK>(staged, regular, in_range, lane, v0, v1, wbase, stage, dst, values);
+  write_rows<kVertexRowLen, BULK>(staged, regular, in_range, lane, v0, v1, wbase, stage, dst, values, beta);
 }
 
 // vertex rows with closed rings of 3..8 cells (rows_p2_core.h); rows of different lengths (1 + 3m) share a warp, the staged
@@ -399,7 +409,7 @@ template <int MODE>
 __global__ void __launch_bounds__(128, 4) k_p2_vertex_rows_general(int first, int end, int n_rows, const int32_t* __restrict__ gnbr,
                                                                  const uint32_t* __restrict__ gslots, const double* __restrict__ node_coords,
                                                                  const int32_t* __restrict__ outer, p2::VertexParams P,
-                                                                 double* __restrict__ values) {
+                                                                 double* __restrict__ values, double beta) {
   extern __shared__ double stage_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = first + blockIdx.x * blockDim.x + threadIdx.x;
@@ -445,10 +455,10 @@ __global__ void __launch_bounds__(128, 4) k_p2_vertex_rows_general(int first, in
 #pragma unroll
     for (int k = 0; k < p2::kMaxVertexRowLen; ++k) {
       const int idx = k * 32 + lane;
-      if (idx < total) out[idx] = stage[idx];
+      if (idx < total) out[idx] = beta == 0.0 ? stage[idx] : fma(beta, out[idx], stage[idx]);
     }
   } else if (regular) {
-    for (int k = 0; k < v1 - v0; ++k) values[v0 + k] = dst[k];
+    for (int k = 0; k < v1 - v0; ++k) values[v0 + k] = beta == 0.0 ? dst[k] : fma(beta, values[v0 + k], dst[k]);
   }
 }
 
@@ -457,7 +467,7 @@ template <int MODE, bool BULK>
 __global__ void __launch_bounds__(128, 12) k_p2_edge_rows(int n_edges, int row0, const int32_t* __restrict__ enb,
                                                        const uint32_t* __restrict__ eslots, const double* __restrict__ node_coords,
                                                        const int32_t* __restrict__ outer, int pf_dist, int pfc_dist, P2Params P,
-                                                       double* __restrict__ values, int first, int end) {
+                                                       double* __restrict__ values, int first, int end, double beta) {
   // edge rows [first, end) of n_edges; edge e is matrix row row0 + e
   extern __shared__ __align__(16) double stage_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -523,7 +533,7 @@ __global__ void __launch_bounds__(128, 12) k_p2_edge_rows(int n_edges, int row0,
     dst[(w >> 28) & 15U] = t2[5];
     dst[36 - ssum] = t1[3] + t2[3];
   }
-  write_rows<kEdgeRowLen, BULK>(staged, regular, in_range, lane, v0, v1, wbase, stage, dst, values);
+  write_rows<kEdgeRowLen, BULK>(staged, regular, in_range, lane, v0, v1, wbase, stage, dst, values, beta);
 }
 
 __global__ void k_count_flags(int64_t n, const uint8_t* __restrict__ flag, int* __restrict__ cnt) {
@@ -669,7 +679,7 @@ int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
 // rows [r0, r1) of the matrix (the caller has already sent the irregular rows of the range through the generic kernel)
 int p2_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, const double alpha[4], int tensor, double gamma,
                    const double* k00, const double* k01, const double* k10, const double* k11, const double* km, double* d_values,
-                   int64_t r0, int64_t r1) {
+                   int64_t r0, int64_t r1, double beta) {
   P2Params P;
   P.a00 = alpha[0]; P.a01 = tensor ? alpha[1] : 0.0; P.a10 = tensor ? alpha[2] : 0.0; P.a11 = tensor ? alpha[3] : alpha[0];
   P.gamma = gamma;
@@ -705,24 +715,24 @@ int p2_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* 
     const size_t smem_g = sizeof(double) * (threads / 32) * 32 * (p2::kMaxVertexRowLen + 1);
     const unsigned gg = static_cast<unsigned>(cdiv(v_end - v_first, threads));
     if (simple)
-      k_p2_vertex_rows_general<0><<<gg, threads, smem_g, ctx->stream>>>(v_first, v_end, nn, p->p2g_nbr, p->p2g_slots, mesh->node_coords, p->outer, G, d_values);
+      k_p2_vertex_rows_general<0><<<gg, threads, smem_g, ctx->stream>>>(v_first, v_end, nn, p->p2g_nbr, p->p2g_slots, mesh->node_coords, p->outer, G, d_values, beta);
     else
-      k_p2_vertex_rows_general<1><<<gg, threads, smem_g, ctx->stream>>>(v_first, v_end, nn, p->p2g_nbr, p->p2g_slots, mesh->node_coords, p->outer, G, d_values);
+      k_p2_vertex_rows_general<1><<<gg, threads, smem_g, ctx->stream>>>(v_first, v_end, nn, p->p2g_nbr, p->p2g_slots, mesh->node_coords, p->outer, G, d_values, beta);
     LFGPU_LAUNCH_CHECK(ctx);
   } else if (v_end > v_first) {
     const unsigned gv = static_cast<unsigned>(cdiv(v_end - v_first, threads));
     if (simple)
-      (bulk ? k_p2_vertex_rows<0, true> : k_p2_vertex_rows<0, false>)<<<gv, threads, smem_v, ctx->stream>>>(nn, p->p2v_nbr, p->p2v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values, v_first, v_end);
+      (bulk ? k_p2_vertex_rows<0, true> : k_p2_vertex_rows<0, false>)<<<gv, threads, smem_v, ctx->stream>>>(nn, p->p2v_nbr, p->p2v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values, v_first, v_end, beta);
     else
-      (bulk ? k_p2_vertex_rows<1, true> : k_p2_vertex_rows<1, false>)<<<gv, threads, smem_v, ctx->stream>>>(nn, p->p2v_nbr, p->p2v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values, v_first, v_end);
+      (bulk ? k_p2_vertex_rows<1, true> : k_p2_vertex_rows<1, false>)<<<gv, threads, smem_v, ctx->stream>>>(nn, p->p2v_nbr, p->p2v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values, v_first, v_end, beta);
     LFGPU_LAUNCH_CHECK(ctx);
   }
   if (e_end > e_first) {
     const unsigned ge = static_cast<unsigned>(cdiv(e_end - e_first, threads));
     if (simple)
-      (bulk ? k_p2_edge_rows<0, true> : k_p2_edge_rows<0, false>)<<<ge, threads, smem_e, ctx->stream>>>(ne, nn, p->p2e_nbr, p->p2e_slots, mesh->node_coords, p->outer, ipf_e, ipc_e, P, d_values, e_first, e_end);
+      (bulk ? k_p2_edge_rows<0, true> : k_p2_edge_rows<0, false>)<<<ge, threads, smem_e, ctx->stream>>>(ne, nn, p->p2e_nbr, p->p2e_slots, mesh->node_coords, p->outer, ipf_e, ipc_e, P, d_values, e_first, e_end, beta);
     else
-      (bulk ? k_p2_edge_rows<1, true> : k_p2_edge_rows<1, false>)<<<ge, threads, smem_e, ctx->stream>>>(ne, nn, p->p2e_nbr, p->p2e_slots, mesh->node_coords, p->outer, ipf_e, ipc_e, P, d_values, e_first, e_end);
+      (bulk ? k_p2_edge_rows<1, true> : k_p2_edge_rows<1, false>)<<<ge, threads, smem_e, ctx->stream>>>(ne, nn, p->p2e_nbr, p->p2e_slots, mesh->node_coords, p->outer, ipf_e, ipc_e, P, d_values, e_first, e_end, beta);
     LFGPU_LAUNCH_CHECK(ctx);
   }
   return LFGPU_OK;

@@ -102,23 +102,30 @@ __device__ __forceinline__ void prefetch_l2(const void* a) { asm volatile("prefe
 template <int LEN, bool SWZ = false>
 __device__ __forceinline__ void write_rows(bool staged, bool regular, bool in_range, int lane, int32_t v0, int32_t v1, int32_t wbase,
                                            const double* __restrict__ stage, const double* __restrict__ dst, double* __restrict__ values,
-                                           int off = 0) {
+                                           double beta, int off = 0) {
   __syncwarp();
   if (staged) {
     const unsigned ballot = __ballot_sync(0xffffffffU, in_range);
     if (ballot == 0) return;
     const int total = __shfl_sync(0xffffffffU, v1, 31 - __clz(ballot)) - wbase;
     double* out = values + wbase;
+    if (beta == 0.0) {
 #pragma unroll
-    for (int k = 0; k < LEN; ++k) {
-      const int idx = k * 32 + lane;
-      if (idx < total) out[idx] = stage[stage_ix<SWZ>(idx)];
+      for (int k = 0; k < LEN; ++k) {
+        const int idx = k * 32 + lane;
+        if (idx < total) out[idx] = stage[stage_ix<SWZ>(idx)];
+      }
+    } else {  // accumulate (assembler.h:84-88)
+      for (int idx = lane; idx < total; idx += 32) out[idx] = fma(beta, out[idx], stage[stage_ix<SWZ>(idx)]);
     }
   } else if (regular) {
     if (SWZ) {
-      for (int k = 0; k < LEN; ++k) values[v0 + k] = stage[stage_ix<true>(off + k)];
+      for (int k = 0; k < LEN; ++k) {
+        const double v = stage[stage_ix<true>(off + k)];
+        values[v0 + k] = beta == 0.0 ? v : fma(beta, values[v0 + k], v);
+      }
     } else {
-      for (int k = 0; k < LEN; ++k) values[v0 + k] = dst[k];
+      for (int k = 0; k < LEN; ++k) values[v0 + k] = beta == 0.0 ? dst[k] : fma(beta, values[v0 + k], dst[k]);
     }
   }
 }
@@ -131,7 +138,7 @@ template <int MODE, int MINB = 3>
 __global__ void __launch_bounds__(128, MINB) k_p3_vertex_rows(int n_rows, const int32_t* __restrict__ nbr,
                                                          const uint32_t* __restrict__ slots, const double* __restrict__ node_coords,
                                                          const int32_t* __restrict__ outer, int pf_dist, Params P,
-                                                         double* __restrict__ values, int first, int end) {
+                                                         double* __restrict__ values, int first, int end, double beta) {
   // rows [first, end) of the n_rows vertex rows (the whole range, or one GPU's share of it)
   extern __shared__ double stage_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -183,7 +190,7 @@ __global__ void __launch_bounds__(128, MINB) k_p3_vertex_rows(int n_rows, const 
     }
     vertex_row<MODE>(P, dx, dy, w, dst);
   }
-  write_rows<kVertexRowLen>(staged, regular, in_range, lane, v0, v1, wbase, stage, dst, values);
+  write_rows<kVertexRowLen>(staged, regular, in_range, lane, v0, v1, wbase, stage, dst, values, beta);
 }
 
 // vertex rows with closed rings of 3..8 cells (rows_p3_core.h: vertex_row_general); rows of different lengths (1 + 6m) share a
@@ -191,7 +198,8 @@ __global__ void __launch_bounds__(128, MINB) k_p3_vertex_rows(int n_rows, const 
 template <int MODE>
 __global__ void __launch_bounds__(128, 2) k_p3_vertex_rows_general(int first, int end, int n_rows, const int32_t* __restrict__ gnbr,
                                                                  const uint32_t* __restrict__ gslots, const double* __restrict__ node_coords,
-                                                                 const int32_t* __restrict__ outer, Params P, double* __restrict__ values) {
+                                                                 const int32_t* __restrict__ outer, Params P, double* __restrict__ values,
+                                                                 double beta) {
   extern __shared__ double stage_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = first + blockIdx.x * blockDim.x + threadIdx.x;
@@ -237,10 +245,10 @@ __global__ void __launch_bounds__(128, 2) k_p3_vertex_rows_general(int first, in
 #pragma unroll
     for (int k = 0; k < kMaxVertexRowLen; ++k) {
       const int idx = k * 32 + lane;
-      if (idx < total) out[idx] = stage[idx];
+      if (idx < total) out[idx] = beta == 0.0 ? stage[idx] : fma(beta, out[idx], stage[idx]);
     }
   } else if (regular) {
-    for (int k = 0; k < v1 - v0; ++k) values[v0 + k] = dst[k];
+    for (int k = 0; k < v1 - v0; ++k) values[v0 + k] = beta == 0.0 ? dst[k] : fma(beta, values[v0 + k], dst[k]);
   }
 }
 
@@ -248,7 +256,7 @@ template <int MODE>
 __global__ void __launch_bounds__(128, 4) k_p3_edge_rows(int n_erows, int row0, const int32_t* __restrict__ enb,
                                                        const uint32_t* __restrict__ eslots, const double* __restrict__ node_coords,
                                                        const int32_t* __restrict__ outer, int pf_dist, int pfc_dist, Params P,
-                                                       double* __restrict__ values, int first, int end) {
+                                                       double* __restrict__ values, int first, int end, double beta) {
   // edge-dof rows [first, end) of n_erows; row e of them is matrix row row0 + e
   extern __shared__ double stage_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -298,7 +306,7 @@ __global__ void __launch_bounds__(128, 4) k_p3_edge_rows(int n_erows, int row0, 
     const double2 xp = __ldg(nc + ip), xq = __ldg(nc + iq), x1 = __ldg(nc + io1), x2 = __ldg(nc + io2);
     edge_row<MODE, true>(P, xq.x - xp.x, xq.y - xp.y, x1.x - xp.x, x1.y - xp.y, x2.x - xp.x, x2.y - xp.y, w, stage, off);
   }
-  write_rows<kEdgeRowLen, true>(staged, regular, in_range, lane, v0, v1, wbase, stage, stage, values, off);
+  write_rows<kEdgeRowLen, true>(staged, regular, in_range, lane, v0, v1, wbase, stage, stage, values, beta, off);
 }
 
 // slots of the ten list positions of every cell in its own row (list position 9), one nibble each: 8 bytes per cell instead
@@ -317,7 +325,7 @@ __global__ void k_p3_cell_plan(int64_t n_cells, int o_stride, int pos_row, const
 template <int MODE>
 __global__ void __launch_bounds__(128, 4) k_p3_cell_rows(int row0, const uint32_t* __restrict__ cell_nodes, const uint2* __restrict__ cslots,
                                                        const double* __restrict__ node_coords, const int32_t* __restrict__ outer, int pf_dist,
-                                                       Params P, double* __restrict__ values, int first, int end) {
+                                                       Params P, double* __restrict__ values, int first, int end, double beta) {
   // cells [first, end); cell c is matrix row row0 + c
   extern __shared__ double stage_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -349,7 +357,7 @@ __global__ void __launch_bounds__(128, 4) k_p3_cell_rows(int row0, const uint32_
     const double2 x0 = __ldg(nc + v.x), x1 = __ldg(nc + v.y), x2 = __ldg(nc + v.z);
     cell_row<MODE, true, true>(P, x1.x - x0.x, x1.y - x0.y, x2.x - x0.x, x2.y - x0.y, pw, stage, off);
   }
-  write_rows<kCellRowLen, true>(true, in_range, in_range, lane, v0, v1, wbase, stage, stage, values, off);
+  write_rows<kCellRowLen, true>(true, in_range, in_range, lane, v0, v1, wbase, stage, stage, values, beta, off);
 }
 
 __global__ void k_count_flags(int64_t n, const uint8_t* __restrict__ flag, int* __restrict__ cnt) {
@@ -504,7 +512,7 @@ int p3_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
 // rows [r0, r1) of the matrix (the caller has already sent the irregular rows of the range through the generic kernel)
 int p3_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, const double alpha[4], int tensor, double gamma,
                    const double* k00, const double* k01, const double* k10, const double* k11, const double* km, double* d_values,
-                   int64_t r0, int64_t r1) {
+                   int64_t r0, int64_t r1, double beta) {
   Params P;
   P.a00 = alpha[0]; P.a01 = tensor ? alpha[1] : 0.0; P.a10 = tensor ? alpha[2] : 0.0; P.a11 = tensor ? alpha[3] : alpha[0];
   P.gamma = gamma;
@@ -540,25 +548,25 @@ int p3_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* 
     LFGPU_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_p3_vertex_rows_general<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,               \
                                                static_cast<int>(smem_g)));                                                                \
     k_p3_vertex_rows_general<MODE><<<static_cast<unsigned>(cdiv(v_end - v_first, threads)), threads, smem_g, ctx->stream>>>(              \
-        v_first, v_end, nn, p->p3g_nbr, p->p3g_slots, mesh->node_coords, p->outer, P, d_values);                                          \
+        v_first, v_end, nn, p->p3g_nbr, p->p3g_slots, mesh->node_coords, p->outer, P, d_values, beta);                                          \
     LFGPU_LAUNCH_CHECK(ctx);                                                                                                              \
   } else if (v_end > v_first) {                                                                                                           \
     if (MODE == 1 && vocc_env == 4)                                                                                                       \
       k_p3_vertex_rows<1, 4><<<static_cast<unsigned>(cdiv(v_end - v_first, threads)), threads, smem_v, ctx->stream>>>(                    \
-          nn, p->p3v_nbr, p->p3v_slots, mesh->node_coords, p->outer, ipf_v * 4 / 3, P, d_values, v_first, v_end);                         \
+          nn, p->p3v_nbr, p->p3v_slots, mesh->node_coords, p->outer, ipf_v * 4 / 3, P, d_values, v_first, v_end, beta);                         \
     else                                                                                                                                  \
       k_p3_vertex_rows<MODE><<<static_cast<unsigned>(cdiv(v_end - v_first, threads)), threads, smem_v, ctx->stream>>>(                    \
-          nn, p->p3v_nbr, p->p3v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values, v_first, v_end);                                 \
+          nn, p->p3v_nbr, p->p3v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values, v_first, v_end, beta);                                 \
     LFGPU_LAUNCH_CHECK(ctx);                                                                                                              \
   }                                                                                                                                       \
   if (e_end > e_first) {                                                                                                                  \
     k_p3_edge_rows<MODE><<<static_cast<unsigned>(cdiv(e_end - e_first, threads)), threads, smem_e, ctx->stream>>>(                        \
-        ner, nn, p->p3e_nbr, p->p3e_slots, mesh->node_coords, p->outer, ipf_e, ipc_e, P, d_values, e_first, e_end);                       \
+        ner, nn, p->p3e_nbr, p->p3e_slots, mesh->node_coords, p->outer, ipf_e, ipc_e, P, d_values, e_first, e_end, beta);                       \
     LFGPU_LAUNCH_CHECK(ctx);                                                                                                              \
   }                                                                                                                                       \
   if (c_end > c_first) {                                                                                                                  \
     k_p3_cell_rows<MODE><<<static_cast<unsigned>(cdiv(c_end - c_first, threads)), threads, smem_c, ctx->stream>>>(                        \
-        base_int, mesh->cell_nodes, static_cast<const uint2*>(p->p3c_slots), mesh->node_coords, p->outer, ipf_c, P, d_values, c_first, c_end);               \
+        base_int, mesh->cell_nodes, static_cast<const uint2*>(p->p3c_slots), mesh->node_coords, p->outer, ipf_c, P, d_values, c_first, c_end, beta);               \
     LFGPU_LAUNCH_CHECK(ctx);                                                                                                              \
   }
   if (simple) {

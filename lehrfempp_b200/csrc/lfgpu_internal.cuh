@@ -262,12 +262,12 @@ int p1_load_fan(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* d, d
 int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p);
 int p2_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, const double alpha[4], int tensor, double gamma,
                    const double* k00, const double* k01, const double* k10, const double* k11, const double* km, double* d_values,
-                   int64_t r0, int64_t r1);
+                   int64_t r0, int64_t r1, double beta = 0.0);
 // P3 row kernels (assemble_p3.cu): k00 .. km = reference tensors of FeLagrangeO3Tria, [10 * 10] row-major each
 int p3_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p);
 int p3_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, const double alpha[4], int tensor, double gamma,
                    const double* k00, const double* k01, const double* k10, const double* k11, const double* km, double* d_values,
-                   int64_t r0, int64_t r1);
+                   int64_t r0, int64_t r1, double beta = 0.0);
 // body of lfgpu_assemble_reaction_diffusion_rows (assemble.cu) with two extras used by the host pipeline (hostpipe.cu)
 int assemble_rd_impl(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, int degree, const lfgpu_quad* qr_tria,
                      const lfgpu_quad* qr_quad, const lfgpu_coeff* alpha, const lfgpu_coeff* gamma, const uint8_t* active, double beta,

@@ -19,7 +19,7 @@ struct lfgpu_multi {
     double* d_values = nullptr;
     bool empty = true;
     int64_t n_cells = 0, n_nodes = 0, n_dofs = 0, n_owned_rows = 0, owned_nnz = 0;
-    std::vector<int32_t> l2g_cells, l2g_dofs, outer, inner;
+    std::vector<int32_t> l2g_cells, l2g_dofs, l2g_nodes, outer, inner;
     std::vector<uint8_t> owned;
     double* d_alpha = nullptr;  // per-cell / per-point coefficient tables of this device's cells
     double* d_gamma = nullptr;
@@ -101,7 +101,9 @@ void setup_part(lfgpu_multi::Part& part, int k, int n_parts, int64_t n_nodes, co
   PART_CHECK(lfgpu_submesh_owned_dofs(ctx, part.sub, d_owner, k, d_owned));
   part.l2g_cells.resize(part.n_cells);
   part.l2g_dofs.resize(part.n_dofs);
+  part.l2g_nodes.resize(part.n_nodes);
   part.owned.resize(part.n_dofs);
+  PART_CUDA(cudaMemcpyAsync(part.l2g_nodes.data(), lfgpu_submesh_l2g_nodes_device(part.sub), 4 * part.n_nodes, cudaMemcpyDeviceToHost, ctx->stream));
   PART_CUDA(cudaMemcpyAsync(part.l2g_cells.data(), lfgpu_submesh_l2g_cells_device(part.sub), 4 * part.n_cells, cudaMemcpyDeviceToHost, ctx->stream));
   PART_CUDA(cudaMemcpyAsync(part.l2g_dofs.data(), lfgpu_submesh_l2g_dofs_device(part.sub), 4 * part.n_dofs, cudaMemcpyDeviceToHost, ctx->stream));
   PART_CUDA(cudaMemcpyAsync(part.owned.data(), d_owned, part.n_dofs, cudaMemcpyDeviceToHost, ctx->stream));
@@ -144,11 +146,14 @@ int local_coeff(lfgpu_multi::Part& part, const lfgpu_coeff* c, double** d_buf, i
   *out = *c;
   if (c->kind == LFGPU_COEFF_CONST || c->kind == LFGPU_COEFF_CONST_2X2) return LFGPU_OK;
   if (c->data == nullptr) return LFGPU_ERR_INVALID;
-  const int64_t per_cell = c->kind == LFGPU_COEFF_PER_CELL ? 1 : (c->kind == LFGPU_COEFF_PER_QP ? c->stride : 4 * c->stride);
-  const int64_t n = part.n_cells * per_cell;
+  const bool nodal = c->kind == LFGPU_COEFF_NODAL;  // one value per mesh node instead of per cell
+  const int64_t per_cell = (nodal || c->kind == LFGPU_COEFF_PER_CELL) ? 1 : (c->kind == LFGPU_COEFF_PER_QP ? c->stride : 4 * c->stride);
+  const int64_t n_ent = nodal ? part.n_nodes : part.n_cells;
+  const std::vector<int32_t>& l2g = nodal ? part.l2g_nodes : part.l2g_cells;
+  const int64_t n = n_ent * per_cell;
   std::vector<double> h(static_cast<size_t>(n));
-  for (int64_t i = 0; i < part.n_cells; ++i)
-    std::memcpy(h.data() + i * per_cell, c->data + static_cast<int64_t>(part.l2g_cells[i]) * per_cell, sizeof(double) * per_cell);
+  for (int64_t i = 0; i < n_ent; ++i)
+    std::memcpy(h.data() + i * per_cell, c->data + static_cast<int64_t>(l2g[i]) * per_cell, sizeof(double) * per_cell);
   cudaSetDevice(part.ctx->device);
   if (*buf_len < n) {
     cudaStreamSynchronize(part.ctx->stream);

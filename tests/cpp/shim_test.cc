@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 #include <string>
 
 #include "../../include/lf_gpu_shim.hpp"
@@ -288,6 +289,105 @@ int main(int argc, char** argv) {
       }
       CHECK(same && err <= 1e-12 * scale && berr <= 1e-12 * bscale, "impedance terms P%d: same=%d matrix err %.3e rhs err %.3e", p, static_cast<int>(same), err, berr);
       std::printf("cell + edge (impedance) terms P%d on hybrid mesh     N=%6zu nnz=%8zu rel.err=%.2e rhs=%.2e\n", p, n, vals.size(), err / scale, berr / bscale);
+    }
+    // ---- round 2: boundary fixes of the shim ----------------------------------------------------------------------------
+    if (extra) {
+      using OC2 = uscalfe::MeshFunctionConstant<double>;
+      for (int p = 1; p <= 3; ++p) {
+        auto fes = std::make_shared<uscalfe::UniformScalarFESpace>(hyb, p);
+        const assemble::DofHandler& dofh = fes->LocGlobMap();
+        auto gfes = std::make_shared<const FeSpace>(FeSpace{fes, p});
+        // (1) isActive of a cell provider (assembler.h:127): a derived provider that switches every third cell off
+        struct OSel : uscalfe::ReactionDiffusionElementMatrixProvider<OC2, OC2> {
+          using Base = uscalfe::ReactionDiffusionElementMatrixProvider<OC2, OC2>;
+          const mesh::Mesh* m;
+          OSel(std::shared_ptr<uscalfe::UniformScalarFESpace> f, const mesh::Mesh* mm) : Base(f, OC2(2.0), OC2(3.0)), m(mm) {}
+          bool isActive(const mesh::Entity& c) override { return m->Index(c) % 3 != 0; }
+        };
+        struct GSel : lfgpu::ReactionDiffusionElementMatrixProvider<double, GC, GC> {
+          using Base = lfgpu::ReactionDiffusionElementMatrixProvider<double, GC, GC>;
+          const mesh::Mesh* m;
+          GSel(std::shared_ptr<const FeSpace> f, const mesh::Mesh* mm) : Base(f, GC{2.0}, GC{3.0}), m(mm) {}
+          bool isActive(const mesh::Entity& c) { return m->Index(c) % 3 != 0; }
+        };
+        OSel osel(fes, hyb.get());
+        assemble::COOMatrix coo(dofh.NumDofs(), dofh.NumDofs());
+        assemble::AssembleMatrixLocally(0, dofh, dofh, osel, coo);
+        GSel gsel(gfes, hyb.get());
+        lfgpu::CsrMatrix M(ctx, LFGPU_COL_MAJOR);
+        lfgpu::AssembleMatrixLocally<OracleAdaptor>(0, dofh, dofh, gsel, M);
+        std::vector<std::int32_t> outer, inner;
+        std::vector<double> vals;
+        M.Download(outer, inner, vals);
+        // the GPU pattern is the full one (inactive cells leave explicit zeros); compare as operators
+        const auto ref = coo.makeSparse();
+        double scale = 0, err = 0;
+        for (std::size_t c = 0; c + 1 < outer.size(); ++c) {
+          std::int32_t kr = ref.outer[c];
+          for (std::int32_t k = outer[c]; k < outer[c + 1]; ++k) {
+            double rv = 0.0;
+            if (kr < ref.outer[c + 1] && ref.inner[kr] == inner[k]) rv = ref.values[kr++];
+            scale = std::max(scale, std::fabs(rv));
+            err = std::max(err, std::fabs(vals[k] - rv));
+          }
+          CHECK(kr == ref.outer[c + 1], "isActive P%d: reference entry outside the GPU pattern in column %zu", p, c);
+        }
+        CHECK(err <= 1e-12 * scale, "isActive P%d: error %.3e", p, err);
+        std::printf("isActive (every third cell off) P%d             rel.err=%.2e\n", p, err / scale);
+        // (2) MeshFunctionGlobal with a functor of ONE point argument (mesh_function_global.h:77-88)
+        auto f1 = [](auto x) { return 1.0 + x[0] * x[0] + x[1]; };
+        auto f2 = [](double x, double y) { return 1.0 + x * x + y; };
+        uscalfe::MeshFunctionGlobal<double> o2(f2);
+        lfgpu::MeshFunctionGlobal<decltype(f1)> g1{f1};
+        compare_matrix(ctx, hyb, p, o2, OC2(0.5), g1, GC{0.5}, "hybrid, one-argument functor");
+        // (3) load provider with a rule collection (loc_comp_ellbvp.h:660-686)
+        {
+          std::map<RefEl, quad::QuadRule> qrs{{RefEl::kTria(), quad::make_QuadRule(RefEl::kTria(), 2 * p + 2)},
+                                              {RefEl::kQuad(), quad::make_QuadRule(RefEl::kQuad(), 2 * p + 2)}};
+          uscalfe::ScalarLoadElementVectorProvider<uscalfe::MeshFunctionGlobal<double>> oprov(fes, uscalfe::MeshFunctionGlobal<double>(f2), qrs);
+          std::vector<double> refv(dofh.NumDofs(), 0.0);
+          assemble::AssembleVectorLocally(0, dofh, oprov, refv);
+          lfgpu::ScalarLoadElementVectorProvider<double, lfgpu::MeshFunctionGlobal<decltype(f2)>> gprov(
+              gfes, lfgpu::MeshFunctionGlobal<decltype(f2)>{f2}, qrs);
+          lfgpu::Vector v(ctx);
+          lfgpu::AssembleVectorLocally<OracleAdaptor>(0, dofh, gprov, v);
+          const auto h = v.Download();
+          double s2 = 0, e2 = 0;
+          for (std::size_t i = 0; i < h.size(); ++i) {
+            s2 = std::max(s2, std::fabs(refv[i]));
+            e2 = std::max(e2, std::fabs(h[i] - refv[i]));
+          }
+          CHECK(e2 <= 1e-12 * s2, "load vector with a rule collection P%d: error %.3e", p, e2);
+          std::printf("load vector, rule collection of degree %d P%d      rel.err=%.2e\n", 2 * p + 2, p, e2 / s2);
+        }
+        // (4) several devices from one process: the same device listed three times gets three contexts and three sub-problems
+        {
+          uscalfe::ReactionDiffusionElementMatrixProvider<uscalfe::MeshFunctionGlobal<double>, OC2> oprov(fes, o2, OC2(0.5));
+          assemble::COOMatrix coo2(dofh.NumDofs(), dofh.NumDofs());
+          assemble::AssembleMatrixLocally(0, dofh, dofh, oprov, coo2);
+          assemble::AssembleMatrixLocally(0, dofh, dofh, oprov, coo2);
+          const auto ref2 = coo2.makeSparse();
+          lfgpu::ReactionDiffusionElementMatrixProvider<double, lfgpu::MeshFunctionGlobal<decltype(f2)>, GC> gprov(
+              gfes, lfgpu::MeshFunctionGlobal<decltype(f2)>{f2}, GC{0.5});
+          lfgpu::MultiCsrMatrix MM({0, 0, 0}, LFGPU_COL_MAJOR);
+          lfgpu::AssembleMatrixLocally<OracleAdaptor>(0, dofh, dofh, gprov, MM);
+          lfgpu::AssembleMatrixLocally<OracleAdaptor>(0, dofh, dofh, gprov, MM);  // accumulates
+          std::vector<std::int64_t> mo;
+          std::vector<std::int32_t> mi;
+          std::vector<double> mv;
+          MM.Gather(mo, mi, mv);
+          bool same = mo.size() == ref2.outer.size() && mi.size() == ref2.inner.size();
+          for (std::size_t i = 0; same && i < mo.size(); ++i) same = mo[i] == ref2.outer[i];
+          for (std::size_t i = 0; same && i < mi.size(); ++i) same = mi[i] == ref2.inner[i];
+          double s4 = 0, e4 = 0;
+          for (std::size_t i = 0; same && i < mv.size(); ++i) {
+            s4 = std::max(s4, std::fabs(ref2.values[i]));
+            e4 = std::max(e4, std::fabs(mv[i] - ref2.values[i]));
+          }
+          CHECK(same && e4 <= 1e-12 * s4, "MultiCsrMatrix P%d: same=%d error %.3e", p, static_cast<int>(same), e4);
+          std::printf("MultiCsrMatrix on devices {0,0,0} P%d             nnz=%8zu rel.err=%.2e\n", p, mv.size(), s4 > 0 ? e4 / s4 : 0.0);
+        }
+      }
     }
     // missing rule -> error (loc_comp_ellbvp.h:278-287)
   } catch (const lfgpu::Error& e) {

@@ -114,8 +114,11 @@ def test_p2_rows_not_taken_for_other_inputs(ctx, lf):
     out = pat.assemble_reaction_diffusion(2, lf.Coeff.const(1.0), lf.Coeff.const(1.0))
     pat.assemble_reaction_diffusion(2, lf.Coeff.const(1.0), lf.Coeff.const(1.0), beta=1.0, out=out)
     assert rel_max_err(out.to_host(), 2 * o[2]) <= TOL
+    # round 2: accumulation stays in the row kernels (round 1 refused LFGPU_ALGO_FAN with beta != 0); the mask still does not
+    pat.assemble_reaction_diffusion(2, lf.Coeff.const(1.0), lf.Coeff.const(1.0), beta=1.0, out=out, algo=lf.ALGO_FAN)
+    assert rel_max_err(out.to_host(), 3 * o[2]) <= TOL
     with pytest.raises(lf.LfgpuError):
-        pat.assemble_reaction_diffusion(2, lf.Coeff.const(1.0), lf.Coeff.const(1.0), beta=1.0, out=out, algo=lf.ALGO_FAN)
+        pat.assemble_reaction_diffusion(2, lf.Coeff.const(1.0), lf.Coeff.const(1.0), active=ctx.to_device(act), algo=lf.ALGO_FAN)
 
 
 def test_p2_rows_large_mesh_properties(ctx, lf):

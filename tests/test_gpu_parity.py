@@ -449,3 +449,30 @@ def test_row_kernels_against_the_generic_kernel_large(ctx, lf, degree, n):
         rows = pat.assemble_reaction_diffusion(degree, alpha, gamma, algo=lf.ALGO_FAN).to_host()
         gen = pat.assemble_reaction_diffusion(degree, alpha, gamma, algo=lf.ALGO_GATHER).to_host()
         assert rel_max_err(rows, gen) <= TOL
+
+
+@pytest.mark.parametrize("degree", [2, 3])
+@pytest.mark.parametrize("kind", ["tp_tria:24", "delaunay"])
+def test_row_kernels_accumulate(ctx, lf, golden_meshes, degree, kind):
+    # assembler.h:84-88: the matrix is not zeroed -- a second call adds; the P2 / P3 row kernels keep this on their fast path
+    # (round 1 fell back to the item kernel for beta != 0)
+    if kind == "delaunay":
+        from scipy.spatial import Delaunay
+        pts = np.random.default_rng(3).random((900, 2))
+        tri = Delaunay(pts).simplices
+        cn = np.full((tri.shape[0], 4), 0xFFFFFFFF, dtype=np.uint32)
+        cn[:, :3] = tri
+        om = lfo.Mesh.from_arrays(pts, cn)
+        gm = ctx.mesh_upload(pts, cn)
+        gm.build_topology()
+    else:
+        om = oracle_mesh(kind, golden_meshes)
+        gm = gpu_mesh(ctx, kind, golden_meshes, om)
+    pat = gm.dofmap_lagrange(degree).symbolic(major=lf.ROW_MAJOR)
+    o = om.assemble_rd(degree, lfo.coeff.const(1.5), lfo.coeff.const(0.5), csr=True)
+    v = pat.assemble_reaction_diffusion(degree, lf.Coeff.const(1.5), lf.Coeff.const(0.5), algo=lf.ALGO_FAN)
+    assert rel_max_err(v.to_host(), o[2]) <= TOL
+    pat.assemble_reaction_diffusion(degree, lf.Coeff.const(1.5), lf.Coeff.const(0.5), beta=1.0, out=v, algo=lf.ALGO_FAN)
+    assert rel_max_err(v.to_host(), 2 * o[2]) <= TOL
+    pat.assemble_reaction_diffusion(degree, lf.Coeff.const(1.5), lf.Coeff.const(0.5), beta=-0.5, out=v, algo=lf.ALGO_FAN)
+    assert np.abs(v.to_host()).max() <= 1e-12 * np.abs(o[2]).max()
