@@ -482,20 +482,10 @@ __global__ void __launch_bounds__(128, 12) k_p2_edge_rows(int n_edges, int row0,
       else a = reinterpret_cast<const char*>(outer + row0 + ep) + (lane - 20) * 128;
       prefetch_l2(a);
     }
-    // opt-in (LFGPU_EDGE_PFC): the coordinates the CTA pfc_dist rows ahead will gather.  Its id lines were pulled into L2
-    // pf_dist - pfc_dist rows ago; lane l reads the four ids of every 4th edge of that CTA (neighbouring edges of a family
-    // share their coordinate lines) and pulls the lines they point to.
-    if (pfc_dist > 0) {
-      const int ec = first + blockIdx.x * blockDim.x + pfc_dist + 4 * lane;
-      if (ec < end) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int32_t id = __ldg(enb + static_cast<size_t>(k) * n_edges + ec);
-          if (id >= 0) prefetch_l2(node_coords + 2 * static_cast<size_t>(id));
-        }
-      }
-    }
   }
+  // (a per-thread L2 prefetch of the coordinates of the row one wave ahead, as in k_p3_edge_rows, was measured here in round 2:
+  // 0.53 -> 0.82 ms -- this kernel is bound by L1 / LSU work per row, and eight more memory instructions per row make it worse)
+  (void)pfc_dist;
   int32_t v0 = 0, v1 = 0;
   int32_t ip = -1, iq = 0, io1 = 0, io2 = 0;
   uint32_t w = 0;

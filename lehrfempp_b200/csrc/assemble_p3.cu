@@ -252,8 +252,8 @@ __global__ void __launch_bounds__(128, 2) k_p3_vertex_rows_general(int first, in
   }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(128, 4) k_p3_edge_rows(int n_erows, int row0, const int32_t* __restrict__ enb,
+template <int MODE, int MINB = 4>
+__global__ void __launch_bounds__(128, MINB) k_p3_edge_rows(int n_erows, int row0, const int32_t* __restrict__ enb,
                                                        const uint32_t* __restrict__ eslots, const double* __restrict__ node_coords,
                                                        const int32_t* __restrict__ outer, int pf_dist, int pfc_dist, Params P,
                                                        double* __restrict__ values, int first, int end, double beta) {
@@ -271,17 +271,16 @@ __global__ void __launch_bounds__(128, 4) k_p3_edge_rows(int n_erows, int row0, 
       else a = reinterpret_cast<const char*>(outer + row0 + ep) + (lane - 24) * 128;
       prefetch_l2(a);
     }
-    // opt-in (LFGPU_EDGE_PFC, see assemble_p2.cu): the coordinate lines the CTA pfc_dist rows ahead will gather, through its ids
-    if (pfc_dist > 0) {
-      const int ec = first + blockIdx.x * blockDim.x + pfc_dist + 4 * lane;
-      if (ec < end) {
+  }
+  // Coordinates of the row pfc_dist rows ahead (about one wave of resident CTAs): every thread reads that row's four ids now and
+  // asks L2 for the four coordinate lines at the END of its own work, when the ids have arrived.  ncu (round 2): 28 % of the
+  // kernel's stall samples sat on the first use of the gathered coordinates, 9 % on the ids -- edges are numbered column by
+  // column, nodes row by row, so a warp's 32 rows gather from 32 different lines per id and the one-wave-ahead prefetch of the
+  // PLAN lines (warp 0 above) does nothing for them.  (The round-1 variant read every 4th row's ids only: no gain.)
+  int32_t pf_id[4] = {-1, -1, -1, -1};
+  if (pfc_dist > 0 && e + pfc_dist < end) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int32_t id = __ldg(enb + static_cast<size_t>(k) * n_erows + ec);
-          if (id >= 0) prefetch_l2(node_coords + 2 * static_cast<size_t>(id));
-        }
-      }
-    }
+    for (int k = 0; k < 4; ++k) pf_id[k] = __ldg(enb + static_cast<size_t>(k) * n_erows + e + pfc_dist);
   }
   int32_t v0 = 0, v1 = 0;
   int32_t ip = -1, iq = 0, io1 = 0, io2 = 0;
@@ -306,6 +305,9 @@ __global__ void __launch_bounds__(128, 4) k_p3_edge_rows(int n_erows, int row0, 
     const double2 xp = __ldg(nc + ip), xq = __ldg(nc + iq), x1 = __ldg(nc + io1), x2 = __ldg(nc + io2);
     edge_row<MODE, true>(P, xq.x - xp.x, xq.y - xp.y, x1.x - xp.x, x1.y - xp.y, x2.x - xp.x, x2.y - xp.y, w, stage, off);
   }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (pf_id[k] >= 0) prefetch_l2(node_coords + 2 * static_cast<size_t>(pf_id[k]));
   write_rows<kEdgeRowLen, true>(staged, regular, in_range, lane, v0, v1, wbase, stage, stage, values, beta, off);
 }
 
@@ -528,9 +530,13 @@ int p3_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* 
   const int base_int = static_cast<int>(p->n_outer - p->n_cells), ner = base_int - nn;
   static const int pfd_env = [] { const char* e = std::getenv("LFGPU_P3_PFD"); return e != nullptr ? std::atoi(e) : 100; }();
   const int ipf_v = static_cast<int>((static_cast<int64_t>(ctx->sm_count) * 3 * threads * pfd_env / 100) & ~static_cast<int64_t>(127));
-  const int ipf_e = static_cast<int>((static_cast<int64_t>(ctx->sm_count) * 8 * threads * pfd_env / 100) & ~static_cast<int64_t>(127));
+  const int ipf_e = static_cast<int>((static_cast<int64_t>(ctx->sm_count) * 8 * threads * pfd_env / 100) & ~static_cast<int64_t>(127));  // one wave at 8 CTAs per SM
+  // resident CTAs per SM of the edge-dof kernel: 8 (64 registers) measured best on config C4 -- 4 (79 registers, 6 CTAs fit): 0.463 ms,
+  // 7: 0.435, 8: 0.423; LFGPU_P3_EOCC=4 / 10 select the other instantiations
+  static const int eocc_env = [] { const char* e = std::getenv("LFGPU_P3_EOCC"); return e != nullptr ? std::atoi(e) : 8; }();
   static const int vocc_env = [] { const char* e = std::getenv("LFGPU_P3_VOCC"); return e != nullptr ? std::atoi(e) : 3; }();
-  static const int pfc_env = [] { const char* e = std::getenv("LFGPU_EDGE_PFC"); return e != nullptr ? std::atoi(e) : 0; }();
+  // percent of the plan prefetch distance; measured on config C4's kernel (round 2): 0 -> 0.504 ms, 50 -> 0.466, 100 -> 0.511, 200 -> 0.559
+  static const int pfc_env = [] { const char* e = std::getenv("LFGPU_EDGE_PFC"); return e != nullptr ? std::atoi(e) : 50; }();
   const int ipc_e = pfc_env > 0 && ipf_e > 0 ? std::max(128, static_cast<int>((static_cast<int64_t>(ipf_e) * pfc_env / 100) & ~static_cast<int64_t>(127))) : 0;
   const size_t smem_v = sizeof(double) * (threads / 32) * 32 * (kVertexRowLen + 1);
   const size_t smem_e = sizeof(double) * (threads / 32) * 32 * kEdgeRowLen;
@@ -560,8 +566,9 @@ int p3_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* 
     LFGPU_LAUNCH_CHECK(ctx);                                                                                                              \
   }                                                                                                                                       \
   if (e_end > e_first) {                                                                                                                  \
-    k_p3_edge_rows<MODE><<<static_cast<unsigned>(cdiv(e_end - e_first, threads)), threads, smem_e, ctx->stream>>>(                        \
-        ner, nn, p->p3e_nbr, p->p3e_slots, mesh->node_coords, p->outer, ipf_e, ipc_e, P, d_values, e_first, e_end, beta);                       \
+    auto ke = eocc_env == 10 ? k_p3_edge_rows<MODE, 10> : (eocc_env == 4 ? k_p3_edge_rows<MODE, 4> : k_p3_edge_rows<MODE, 8>);             \
+    ke<<<static_cast<unsigned>(cdiv(e_end - e_first, threads)), threads, smem_e, ctx->stream>>>(                                          \
+        ner, nn, p->p3e_nbr, p->p3e_slots, mesh->node_coords, p->outer, ipf_e, ipc_e, P, d_values, e_first, e_end, beta);                 \
     LFGPU_LAUNCH_CHECK(ctx);                                                                                                              \
   }                                                                                                                                       \
   if (c_end > c_first) {                                                                                                                  \

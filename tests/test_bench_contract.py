@@ -69,7 +69,7 @@ def test_bench_algo_switch(algo, kernel):
 
 
 def test_reference_arm_line():
-    env = dict(os.environ)
+    env = dict(os.environ, LFGPU_REF_N="300")
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, env=env, cwd=ROOT, timeout=900)
     assert p.returncode == 0, p.stderr[-2000:]
