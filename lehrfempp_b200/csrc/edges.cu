@@ -44,7 +44,7 @@ __device__ __forceinline__ int32_t edge_dof(int a, uint32_t n0, uint32_t n1, int
 
 __device__ __forceinline__ int find_slot(const int32_t* __restrict__ inner, int32_t lo, int32_t hi, int32_t key) {
   while (lo < hi) {
-    const int32_t mid = (lo + hi) >> 1;
+    const int32_t mid = lo + ((hi - lo) >> 1);  // lo + hi overflows int32 above 2^30 stored values
     const int32_t v = __ldg(inner + mid);
     if (v == key) return mid;
     if (v < key) {

@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kItemThreads) k_item_perm(const int32_t* __res
   if (tid < n_items) {
     int lo = 0, hi = nrows;
     while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
+      const int mid = lo + ((hi - lo) >> 1);
       if (s_adj[mid] <= tid) lo = mid; else hi = mid;
     }
     const uint32_t rank = static_cast<uint32_t>(tid - s_adj[lo]);
@@ -205,7 +205,7 @@ __global__ void k_positions(int64_t n_cells, int o_stride, int i_stride, int pos
       const int32_t target = i_dofs[c * i_stride + b];
       int32_t lo = s, hi = e;
       while (lo < hi) {
-        const int32_t mid = (lo + hi) >> 1;
+        const int32_t mid = lo + ((hi - lo) >> 1);  // lo + hi overflows int32 once a pattern holds more than 2^30 values
         if (inner[mid] < target) lo = mid + 1; else hi = mid;
       }
       if (lo >= e || inner[lo] != target) flags[0] = 1;
