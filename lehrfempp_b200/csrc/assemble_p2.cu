@@ -221,6 +221,51 @@ __global__ void k_p2_edge_plan(int64_t n_nodes, int64_t n_edges, int o_stride, i
   irregular[r] = (!ok && m > 0) ? 1 : 0;
 }
 
+// ---- compact plan (round 2) ----------------------------------------------------------------------------------------------
+// Both kernels moved 1.23 x the algorithmic bytes, the difference being the plan: 36 B per vertex row, 20 B per edge row.  When
+// every ring / edge neighbour lies within +-32767 of the row's reference node (structured, refined and Morton-ordered meshes) and the
+// slot words take at most 65535 distinct values (plan_dict.cu), the plan shrinks to
+//   vertex row r: cd[0..2][r] = six 16-bit differences n_k - r, cidx[r] = number of its slot triple in the table     (14 B)
+//   edge row e:   ce[0][e] = p, ce[1][e] = (q - p) | (o_1 - p) << 16, ce[2][e] = (o_2 - p) | table index << 16          (12 B)
+// index 0xFFFF marks a row that is not planned.  Otherwise the plan stays as it was built.
+__global__ void k_p2_vertex_compact(int64_t nn, const int32_t* __restrict__ nbr, uint32_t* __restrict__ cd, uint16_t* __restrict__ cidx,
+                                    int* __restrict__ overflow) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= nn) return;
+  uint32_t w[3] = {0U, 0U, 0U};
+  if (nbr[r] < 0) {
+    cidx[r] = 0xFFFFU;
+  } else {
+    bool fits = true;
+    for (int s = 0; s < kRing; ++s) {
+      const int64_t d = static_cast<int64_t>(nbr[static_cast<int64_t>(s) * nn + r]) - r;
+      if (d < -32768 || d > 32767) fits = false;
+      w[s >> 1] |= (static_cast<uint32_t>(d) & 0xFFFFU) << (16 * (s & 1));
+    }
+    if (!fits) *overflow = 1;
+  }
+  for (int j = 0; j < 3; ++j) cd[static_cast<int64_t>(j) * nn + r] = w[j];
+}
+
+__global__ void k_p2_edge_compact(int64_t ne, const int32_t* __restrict__ enb, const uint16_t* __restrict__ idx, uint32_t* __restrict__ ce,
+                                  int* __restrict__ overflow) {
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  const int32_t p = enb[e];
+  uint32_t w0 = 0U, w1 = 0U, w2 = 0xFFFF0000U;
+  if (p >= 0) {
+    const int64_t dq = static_cast<int64_t>(enb[ne + e]) - p, d1 = static_cast<int64_t>(enb[2 * ne + e]) - p,
+                  d2 = static_cast<int64_t>(enb[3 * ne + e]) - p;
+    if (dq < -32768 || dq > 32767 || d1 < -32768 || d1 > 32767 || d2 < -32768 || d2 > 32767) *overflow = 1;
+    w0 = static_cast<uint32_t>(p);
+    w1 = (static_cast<uint32_t>(dq) & 0xFFFFU) | (static_cast<uint32_t>(d1) << 16);
+    w2 = (static_cast<uint32_t>(d2) & 0xFFFFU) | (static_cast<uint32_t>(idx[e]) << 16);
+  }
+  ce[e] = w0;
+  ce[ne + e] = w1;
+  ce[2 * ne + e] = w2;
+}
+
 // ---- the kernels --------------------------------------------------------------------------------------------------------
 struct P2Params {
   double a00, a01, a10, a11;  // diffusion tensor as the row routine of assemble.cu uses it (transposed for row-major output)
@@ -269,6 +314,30 @@ __device__ __forceinline__ void p2_row(const P2Params& P, const double (&k00)[6]
 
 __device__ __forceinline__ void prefetch_l2(const void* a) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a)); }
 
+// L2 eviction priorities (HINT variants of the kernels): the value stream is written once and never read again (evict first), the
+// node coordinates are gathered by several rows from different CTAs (evict last) -- the ncu capture of the edge-row kernel showed
+// the coordinate array being read three times from DRAM because the value stream pushes it out of L2
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+template <bool HINT>
+__device__ __forceinline__ double2 ld_coords(const double2* a, uint64_t pol) {
+  if (HINT) {
+    double2 v;
+    asm("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(a), "l"(pol));
+    return v;
+  }
+  return __ldg(a);
+}
+__device__ __forceinline__ int32_t sext16(uint32_t v) { return static_cast<int32_t>(static_cast<int16_t>(v & 0xFFFFU)); }
+
 // copy-out shared by both kernels: the warp's stage is the image of the contiguous value range of its 32 rows.
 // BULK: the image leaves through ONE bulk copy of the TMA unit (cp.async.bulk shared -> global, SASS UBLKCP) issued by lane 0
 // instead of LEN shared-memory loads + LEN global stores per lane -- ncu showed the edge-row kernel limited by the L1 / LSU pipe
@@ -277,7 +346,7 @@ __device__ __forceinline__ void prefetch_l2(const void* a) { asm volatile("prefe
 // + k], odd = wbase & 1), a leading / trailing odd element is stored by an ordinary lane.
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
-template <int LEN, bool BULK>
+template <int LEN, bool BULK, bool HINT = false>
 __device__ __forceinline__ void write_rows(bool staged, bool regular, bool in_range, int lane, int32_t v0, int32_t v1, int32_t wbase,
                                            const double* __restrict__ stage, const double* __restrict__ dst, double* __restrict__ values,
                                            double beta) {
@@ -301,9 +370,15 @@ __device__ __forceinline__ void write_rows(bool staged, bool regular, bool in_ra
       const int odd = wbase & 1;
       const int n_bulk = (total - odd) & ~1;  // elements [odd, odd + n_bulk) start and end on 16-byte boundaries
       if (lane == 0 && n_bulk > 0) {
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + odd), "r"(smem_u32(stage + 2 * odd)),
-                     "r"(n_bulk * 8)
-                     : "memory");
+        if (HINT) {
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(out + odd),
+                       "r"(smem_u32(stage + 2 * odd)), "r"(n_bulk * 8), "l"(l2_policy_evict_first())
+                       : "memory");
+        } else {
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + odd), "r"(smem_u32(stage + 2 * odd)),
+                       "r"(n_bulk * 8)
+                       : "memory");
+        }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
       if (lane == 1 && odd && total > 0) out[0] = stage[odd];
@@ -321,11 +396,14 @@ __device__ __forceinline__ void write_rows(bool staged, bool regular, bool in_ra
   }
 }
 
-template <int MODE, bool BULK>
+// COMPACT: nbr = the 16-bit differences cd[3][n_rows], slots = the table of slot triples (uint4), cidx[n_rows] = table index
+// HINT: L2 eviction priorities on the coordinate gathers and the value stream
+template <int MODE, bool BULK, bool COMPACT, bool HINT>
 __global__ void __launch_bounds__(128, 6) k_p2_vertex_rows(int n_rows, const int32_t* __restrict__ nbr,
                                                          const uint32_t* __restrict__ slots, const double* __restrict__ node_coords,
                                                          const int32_t* __restrict__ outer, int pf_dist, P2Params P,
-                                                         double* __restrict__ values, int first, int end, double beta) {
+                                                         double* __restrict__ values, int first, int end, double beta,
+                                                         const uint16_t* __restrict__ cidx) {
   // rows [first, end) of the n_rows vertex rows (the whole range, or one GPU's share of it)
   extern __shared__ __align__(16) double stage_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -333,45 +411,91 @@ __global__ void __launch_bounds__(128, 6) k_p2_vertex_rows(int n_rows, const int
   const bool in_range = r < end;
   if (pf_dist > 0 && warp == 0) {
     // pull the lines of the CTA that runs about one wave later into L2 (see assemble_p1.cu): 4 lines per plan array
-    // (6 ring + 3 slot arrays), 4 of row pointers, 16 of coordinates
+    // (6 ring + 3 slot arrays), 4 of row pointers, 16 of coordinates; COMPACT: 3 arrays of differences, 2 lines of indices, coordinates
     const int rp = first + blockIdx.x * blockDim.x + pf_dist;
     if (rp + 128 <= end) {
-      for (int L = lane; L < 56; L += 32) {
-        const char* a;
-        if (L < 24) a = reinterpret_cast<const char*>(nbr + static_cast<size_t>(L >> 2) * n_rows + rp) + (L & 3) * 128;
-        else if (L < 36) a = reinterpret_cast<const char*>(slots + static_cast<size_t>((L - 24) >> 2) * n_rows + rp) + (L & 3) * 128;
-        else if (L < 40) a = reinterpret_cast<const char*>(outer + rp) + (L - 36) * 128;
-        else a = reinterpret_cast<const char*>(node_coords + 2 * static_cast<size_t>(rp)) + (L - 40) * 128;
-        prefetch_l2(a);
+      if (COMPACT) {
+        // (the row pointers are not prefetched: one 32-byte sector per warp is read, and only the copy-out waits for it)
+        if (lane < 30) {
+          const char* a;
+          if (lane < 12) a = reinterpret_cast<const char*>(nbr + static_cast<size_t>(lane >> 2) * n_rows + rp) + (lane & 3) * 128;
+          else if (lane < 14) a = reinterpret_cast<const char*>(cidx + rp) + (lane - 12) * 128;
+          else a = reinterpret_cast<const char*>(node_coords + 2 * static_cast<size_t>(rp)) + (lane - 14) * 128;
+          prefetch_l2(a);
+        }
+      } else {
+        for (int L = lane; L < 56; L += 32) {
+          const char* a;
+          if (L < 24) a = reinterpret_cast<const char*>(nbr + static_cast<size_t>(L >> 2) * n_rows + rp) + (L & 3) * 128;
+          else if (L < 36) a = reinterpret_cast<const char*>(slots + static_cast<size_t>((L - 24) >> 2) * n_rows + rp) + (L & 3) * 128;
+          else if (L < 40) a = reinterpret_cast<const char*>(outer + rp) + (L - 36) * 128;
+          else a = reinterpret_cast<const char*>(node_coords + 2 * static_cast<size_t>(rp)) + (L - 40) * 128;
+          prefetch_l2(a);
+        }
       }
     }
   }
   int32_t v0 = 0, v1 = 0;
   int32_t nid[kRing];
   uint32_t w0 = 0, w1 = 0, w2 = 0;
+  bool regular;
+  int32_t wbase;
+  if (COMPACT) {
+    uint32_t d0 = 0, d1 = 0, d2 = 0, ix = 0xFFFFU;
+    if (in_range) {
+      d0 = __ldg(reinterpret_cast<const uint32_t*>(nbr) + r);
+      d1 = __ldg(reinterpret_cast<const uint32_t*>(nbr) + static_cast<size_t>(n_rows) + r);
+      d2 = __ldg(reinterpret_cast<const uint32_t*>(nbr) + 2 * static_cast<size_t>(n_rows) + r);
+      ix = __ldg(cidx + r);
+    }
+    regular = in_range && ix != 0xFFFFU;
+    nid[0] = r + sext16(d0); nid[1] = r + sext16(d0 >> 16);
+    nid[2] = r + sext16(d1); nid[3] = r + sext16(d1 >> 16);
+    nid[4] = r + sext16(d2); nid[5] = r + sext16(d2 >> 16);
+    if (regular) {
+      const uint4 t = __ldg(reinterpret_cast<const uint4*>(slots) + ix);
+      w0 = t.x; w1 = t.y; w2 = t.z;
+    }
+    if (__all_sync(0xffffffffU, regular)) {
+      // 32 planned rows: 19 values each, one after the other -- only the first row pointer is read
+      int32_t b = 0;
+      if (lane == 0) b = __ldg(outer + r);
+      wbase = __shfl_sync(0xffffffffU, b, 0);
+      v0 = wbase + kVertexRowLen * lane;
+      v1 = v0 + kVertexRowLen;
+    } else {
+      if (in_range) {
+        v0 = __ldg(outer + r);
+        v1 = __ldg(outer + r + 1);
+      }
+      wbase = __shfl_sync(0xffffffffU, v0, 0);
+    }
+  } else {
 #pragma unroll
-  for (int s = 0; s < kRing; ++s) nid[s] = -1;
-  if (in_range) {
-    v0 = __ldg(outer + r);
-    v1 = __ldg(outer + r + 1);
+    for (int s = 0; s < kRing; ++s) nid[s] = -1;
+    if (in_range) {
+      v0 = __ldg(outer + r);
+      v1 = __ldg(outer + r + 1);
 #pragma unroll
-    for (int s = 0; s < kRing; ++s) nid[s] = __ldg(nbr + static_cast<size_t>(s) * n_rows + r);
-    w0 = __ldg(slots + r);
-    w1 = __ldg(slots + static_cast<size_t>(n_rows) + r);
-    w2 = __ldg(slots + 2 * static_cast<size_t>(n_rows) + r);
+      for (int s = 0; s < kRing; ++s) nid[s] = __ldg(nbr + static_cast<size_t>(s) * n_rows + r);
+      w0 = __ldg(slots + r);
+      w1 = __ldg(slots + static_cast<size_t>(n_rows) + r);
+      w2 = __ldg(slots + 2 * static_cast<size_t>(n_rows) + r);
+    }
+    regular = in_range && nid[0] >= 0;
+    wbase = __shfl_sync(0xffffffffU, v0, 0);
   }
-  const bool regular = in_range && nid[0] >= 0;
-  const int32_t wbase = __shfl_sync(0xffffffffU, v0, 0);
   const bool staged = !__any_sync(0xffffffffU, in_range && !regular && v1 > v0);
   double* stage = stage_all + warp * (32 * (kVertexRowLen + 1));
   double* dst = stage + (staged ? (v0 - wbase) + (BULK ? (wbase & 1) : 0) : lane * (kVertexRowLen + 1));
   if (regular) {
+    const uint64_t keep = HINT ? l2_policy_evict_last() : 0ULL;
     const double2* nc = reinterpret_cast<const double2*>(node_coords);
     const double2 xi = __ldg(nc + r);
     double dx[kRing], dy[kRing];
 #pragma unroll
     for (int s = 0; s < kRing; ++s) {
-      const double2 p = __ldg(nc + nid[s]);
+      const double2 p = ld_coords<HINT>(nc + nid[s], keep);
       dx[s] = p.x - xi.x;
       dy[s] = p.y - xi.y;
     }
@@ -400,7 +524,7 @@ __global__ void __launch_bounds__(128, 6) k_p2_vertex_rows(int n_rows, const int
     dst[w1 & 31U] = first_s + carry_s;
     dst[171 - ssum] = diag;
   }
-  write_rows<kVertexRowLen, BULK>(staged, regular, in_range, lane, v0, v1, wbase, stage, dst, values, beta);
+  write_rows<kVertexRowLen, BULK, HINT>(staged, regular, in_range, lane, v0, v1, wbase, stage, dst, values, beta);
 }
 
 // vertex rows with closed rings of 3..8 cells (rows_p2_core.h); rows of different lengths (1 + 3m) share a warp, the staged
@@ -463,7 +587,8 @@ __global__ void __launch_bounds__(128, 4) k_p2_vertex_rows_general(int first, in
 }
 
 // 12 CTAs per SM = the occupancy of the measured kernel (40 registers; the row-range arguments had pushed ptxas to 46 -> 10 CTAs)
-template <int MODE, bool BULK>
+// COMPACT: enb = ce[3][n_edges] (p | differences | table index), eslots = the table of slot words (uint4, .x used)
+template <int MODE, bool BULK, bool COMPACT, bool HINT>
 __global__ void __launch_bounds__(128, 12) k_p2_edge_rows(int n_edges, int row0, const int32_t* __restrict__ enb,
                                                        const uint32_t* __restrict__ eslots, const double* __restrict__ node_coords,
                                                        const int32_t* __restrict__ outer, int pf_dist, int pfc_dist, P2Params P,
@@ -475,7 +600,15 @@ __global__ void __launch_bounds__(128, 12) k_p2_edge_rows(int n_edges, int row0,
   const bool in_range = e < end;
   if (pf_dist > 0 && warp == 0) {
     const int ep = first + blockIdx.x * blockDim.x + pf_dist;
-    if (ep + 128 <= end && lane < 24) {  // 4 lines per id array, 4 of slots, 4 of row pointers
+    if (COMPACT) {
+      // 4 lines per plan word array; the row pointers (one sector per warp is read) only on request: pfc_dist != 0
+      if (ep + 128 <= end && lane < (pfc_dist != 0 ? 16 : 12)) {
+        const char* a;
+        if (lane < 12) a = reinterpret_cast<const char*>(enb + static_cast<size_t>(lane >> 2) * n_edges + ep) + (lane & 3) * 128;
+        else a = reinterpret_cast<const char*>(outer + row0 + ep) + (lane - 12) * 128;
+        prefetch_l2(a);
+      }
+    } else if (ep + 128 <= end && lane < 24) {  // 4 lines per id array, 4 of slots, 4 of row pointers
       const char* a;
       if (lane < 16) a = reinterpret_cast<const char*>(enb + static_cast<size_t>(lane >> 2) * n_edges + ep) + (lane & 3) * 128;
       else if (lane < 20) a = reinterpret_cast<const char*>(eslots + ep) + (lane - 16) * 128;
@@ -484,28 +617,60 @@ __global__ void __launch_bounds__(128, 12) k_p2_edge_rows(int n_edges, int row0,
     }
   }
   // (a per-thread L2 prefetch of the coordinates of the row one wave ahead, as in k_p3_edge_rows, was measured here in round 2:
-  // 0.53 -> 0.82 ms -- this kernel is bound by L1 / LSU work per row, and eight more memory instructions per row make it worse)
-  (void)pfc_dist;
+  // 0.53 -> 0.82 ms -- this kernel is bound by L1 / LSU work per row, and eight more memory instructions per row make it worse;
+  // pfc_dist now only switches the row-pointer prefetch of the compact plan)
   int32_t v0 = 0, v1 = 0;
   int32_t ip = -1, iq = 0, io1 = 0, io2 = 0;
   uint32_t w = 0;
-  if (in_range) {
-    v0 = __ldg(outer + row0 + e);
-    v1 = __ldg(outer + row0 + e + 1);
-    ip = __ldg(enb + e);
-    iq = __ldg(enb + static_cast<size_t>(n_edges) + e);
-    io1 = __ldg(enb + 2 * static_cast<size_t>(n_edges) + e);
-    io2 = __ldg(enb + 3 * static_cast<size_t>(n_edges) + e);
-    w = __ldg(eslots + e);
+  bool regular;
+  int32_t wbase;
+  if (COMPACT) {
+    uint32_t c0 = 0, c1 = 0, c2 = 0xFFFF0000U;
+    if (in_range) {
+      c0 = __ldg(reinterpret_cast<const uint32_t*>(enb) + e);
+      c1 = __ldg(reinterpret_cast<const uint32_t*>(enb) + static_cast<size_t>(n_edges) + e);
+      c2 = __ldg(reinterpret_cast<const uint32_t*>(enb) + 2 * static_cast<size_t>(n_edges) + e);
+    }
+    regular = in_range && (c2 >> 16) != 0xFFFFU;
+    ip = static_cast<int32_t>(c0);
+    iq = ip + sext16(c1);
+    io1 = ip + sext16(c1 >> 16);
+    io2 = ip + sext16(c2);
+    if (regular) w = __ldg(eslots + 4 * static_cast<size_t>(c2 >> 16));
+    if (__all_sync(0xffffffffU, regular)) {
+      int32_t b = 0;
+      if (lane == 0) b = __ldg(outer + row0 + e);
+      wbase = __shfl_sync(0xffffffffU, b, 0);
+      v0 = wbase + kEdgeRowLen * lane;
+      v1 = v0 + kEdgeRowLen;
+    } else {
+      if (in_range) {
+        v0 = __ldg(outer + row0 + e);
+        v1 = __ldg(outer + row0 + e + 1);
+      }
+      wbase = __shfl_sync(0xffffffffU, v0, 0);
+    }
+  } else {
+    if (in_range) {
+      v0 = __ldg(outer + row0 + e);
+      v1 = __ldg(outer + row0 + e + 1);
+      ip = __ldg(enb + e);
+      iq = __ldg(enb + static_cast<size_t>(n_edges) + e);
+      io1 = __ldg(enb + 2 * static_cast<size_t>(n_edges) + e);
+      io2 = __ldg(enb + 3 * static_cast<size_t>(n_edges) + e);
+      w = __ldg(eslots + e);
+    }
+    regular = in_range && ip >= 0;
+    wbase = __shfl_sync(0xffffffffU, v0, 0);
   }
-  const bool regular = in_range && ip >= 0;
-  const int32_t wbase = __shfl_sync(0xffffffffU, v0, 0);
   const bool staged = !__any_sync(0xffffffffU, in_range && !regular && v1 > v0);
   double* stage = stage_all + warp * (32 * (kEdgeRowLen + 1));
   double* dst = stage + (staged ? (v0 - wbase) + (BULK ? (wbase & 1) : 0) : lane * (kEdgeRowLen + 1));
   if (regular) {
+    const uint64_t keep = HINT ? l2_policy_evict_last() : 0ULL;
     const double2* nc = reinterpret_cast<const double2*>(node_coords);
-    const double2 xp = __ldg(nc + ip), xq = __ldg(nc + iq), x1 = __ldg(nc + io1), x2 = __ldg(nc + io2);
+    const double2 xp = ld_coords<HINT>(nc + ip, keep), xq = ld_coords<HINT>(nc + iq, keep), x1 = ld_coords<HINT>(nc + io1, keep),
+                  x2 = ld_coords<HINT>(nc + io2, keep);
     const double ax = xq.x - xp.x, ay = xq.y - xp.y;
     double t1[6], t2[6];
     p2_row<MODE>(P, P.ek00, P.ek01, P.ek10, P.ek11, P.em, ax, ay, x1.x - xp.x, x1.y - xp.y, t1);
@@ -523,7 +688,7 @@ __global__ void __launch_bounds__(128, 12) k_p2_edge_rows(int n_edges, int row0,
     dst[(w >> 28) & 15U] = t2[5];
     dst[36 - ssum] = t1[3] + t2[3];
   }
-  write_rows<kEdgeRowLen, BULK>(staged, regular, in_range, lane, v0, v1, wbase, stage, dst, values, beta);
+  write_rows<kEdgeRowLen, BULK, HINT>(staged, regular, in_range, lane, v0, v1, wbase, stage, dst, values, beta);
 }
 
 __global__ void k_count_flags(int64_t n, const uint8_t* __restrict__ flag, int* __restrict__ cnt) {
@@ -559,7 +724,8 @@ int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
   auto cleanup = [&]() { cudaFree(flag); cudaFree(iota); cudaFree(d_num); cudaFree(tmp); };
   auto drop_plan = [&]() {
     cudaFree(p->p2v_nbr); cudaFree(p->p2v_slots); cudaFree(p->p2e_nbr); cudaFree(p->p2e_slots); cudaFree(p->p2_irregular);
-    cudaFree(p->p2g_nbr); cudaFree(p->p2g_slots);
+    cudaFree(p->p2g_nbr); cudaFree(p->p2g_slots); cudaFree(p->p2v_cidx);
+    p->p2v_cidx = nullptr; p->p2_compact_v = false; p->p2_compact_e = false;
     p->p2v_nbr = nullptr; p->p2v_slots = nullptr; p->p2e_nbr = nullptr; p->p2e_slots = nullptr; p->p2_irregular = nullptr;
     p->p2g_nbr = nullptr; p->p2g_slots = nullptr; p->p2_general = false;
   };
@@ -652,6 +818,79 @@ int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
     P2_CHECK(cudaMemcpyAsync(p->p2_irregular_host.data(), iota, sizeof(int32_t) * n_irr, cudaMemcpyDeviceToHost, st));
     P2_CHECK(cudaStreamSynchronize(st));
   }
+  // compact plan (see k_p2_vertex_compact): tried once the plan stands; any failure to fit leaves the arrays as they are
+  // LFGPU_P2_COMPACT: 1 = both row classes, v = vertex rows only, e = edge rows only; default off -- measured at config C3 (B200,
+  // profiles/r02_p2_rows_compact*_hints*.json): DRAM traffic 4.25 -> 3.87 GB (1.23 -> 1.12 x algorithmic), vertex rows 0.263 -> 0.257 ms,
+  // edge rows 0.524 -> 0.549 ms: the kernels wait on dependent loads (plan -> coordinates), not on DRAM bandwidth, and the table
+  // lookup adds one more
+  static const char compact_env = [] { const char* e = std::getenv("LFGPU_P2_COMPACT"); return e == nullptr ? '0' : e[0]; }();
+  const bool compact_v = compact_env == '1' || compact_env == 'v', compact_e = compact_env == '1' || compact_env == 'e';
+  if ((compact_v || compact_e) && n_irr * 2 <= p->n_outer) {
+    int* d_over = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 384);
+    if (compact_v && !p->p2_general) {
+      uint16_t* cidx = nullptr;
+      uint32_t* cd = nullptr;
+      void* dict = nullptr;
+      int n_dict = -1, over = 1;
+      P2_CHECK(cudaMalloc(&cidx, sizeof(uint16_t) * (static_cast<size_t>(nn) + 256)));
+      const int rc = build_row_dict(ctx, 3, nn, p->p2v_slots, cidx, &dict, &n_dict);
+      if (rc == LFGPU_OK && n_dict >= 0) {
+        cudaError_t e = cudaMalloc(&cd, sizeof(uint32_t) * (3 * static_cast<size_t>(nn) + 128));
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_over, 0, sizeof(int), st);
+        if (e == cudaSuccess) {
+          k_p2_vertex_compact<<<static_cast<unsigned>(cdiv(nn, 256)), 256, 0, st>>>(nn, p->p2v_nbr, cd, cidx, d_over);
+          ctx->launches++;
+          e = cudaMemcpyAsync(&over, d_over, sizeof(int), cudaMemcpyDeviceToHost, st);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) over = 1;
+      }
+      if (over == 0) {
+        cudaFree(p->p2v_nbr);
+        cudaFree(p->p2v_slots);
+        p->p2v_nbr = reinterpret_cast<int32_t*>(cd);
+        p->p2v_slots = static_cast<uint32_t*>(dict);
+        p->p2v_cidx = cidx;
+        p->p2_compact_v = true;
+      } else {
+        cudaFree(cidx);
+        cudaFree(cd);
+        cudaFree(dict);
+        (void)cudaGetLastError();
+      }
+    }
+    if (compact_e) {
+      uint16_t* idx = nullptr;
+      uint32_t* ce = nullptr;
+      void* dict = nullptr;
+      int n_dict = -1, over = 1;
+      P2_CHECK(cudaMalloc(&idx, sizeof(uint16_t) * static_cast<size_t>(ne)));
+      const int rc = build_row_dict(ctx, 1, ne, p->p2e_slots, idx, &dict, &n_dict);
+      if (rc == LFGPU_OK && n_dict >= 0) {
+        cudaError_t e = cudaMalloc(&ce, sizeof(uint32_t) * (3 * static_cast<size_t>(ne) + 128));
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_over, 0, sizeof(int), st);
+        if (e == cudaSuccess) {
+          k_p2_edge_compact<<<static_cast<unsigned>(cdiv(ne, 256)), 256, 0, st>>>(ne, p->p2e_nbr, idx, ce, d_over);
+          ctx->launches++;
+          e = cudaMemcpyAsync(&over, d_over, sizeof(int), cudaMemcpyDeviceToHost, st);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) over = 1;
+      }
+      cudaFree(idx);
+      if (over == 0) {
+        cudaFree(p->p2e_nbr);
+        cudaFree(p->p2e_slots);
+        p->p2e_nbr = reinterpret_cast<int32_t*>(ce);
+        p->p2e_slots = static_cast<uint32_t*>(dict);
+        p->p2_compact_e = true;
+      } else {
+        cudaFree(ce);
+        cudaFree(dict);
+        (void)cudaGetLastError();
+      }
+    }
+  }
 #undef P2_CHECK
   cleanup();
   p->n_p2_irregular = n_irr;
@@ -687,10 +926,15 @@ int p2_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* 
   const int ipf_e = static_cast<int>((static_cast<int64_t>(ctx->sm_count) * 12 * threads * pfd_env / 100) & ~static_cast<int64_t>(127));
   // LFGPU_EDGE_PFC (percent of the plan distance, default 0 = off): coordinate prefetch of the edge rows through the plan
   static const int pfc_env = [] { const char* e = std::getenv("LFGPU_EDGE_PFC"); return e != nullptr ? std::atoi(e) : 0; }();
+  // (with the compact edge plan the value only switches the prefetch of the row-pointer lines on)
   const int ipc_e = pfc_env > 0 && ipf_e > 0 ? std::max(128, static_cast<int>((static_cast<int64_t>(ipf_e) * pfc_env / 100) & ~static_cast<int64_t>(127))) : 0;
   // copy-out of the staged rows by the TMA unit (LFGPU_P2_BULK=0: by the lanes); needs a 16-byte aligned value array
   static const bool bulk_env = [] { const char* e = std::getenv("LFGPU_P2_BULK"); return e == nullptr || e[0] != '0'; }();
   const bool bulk = bulk_env && (reinterpret_cast<uintptr_t>(d_values) & 15) == 0;
+  // L2 eviction priorities (LFGPU_L2_HINTS=1; default off): evict-first on the value stream (bulk copy-out only), evict-last on the
+  // coordinate gathers.  Measured at config C3: 0.777 -> 0.791 ms, and the coordinate re-reads from DRAM did not go down
+  static const bool hint_env = [] { const char* e = std::getenv("LFGPU_L2_HINTS"); return e != nullptr && e[0] == '1'; }();
+  const bool hint = hint_env && bulk;
   const size_t smem_v = sizeof(double) * (threads / 32) * 32 * (kVertexRowLen + 1);
   const size_t smem_e = sizeof(double) * (threads / 32) * 32 * (kEdgeRowLen + 1);
   // the share of the range in the vertex rows [0, nn) and in the edge rows [nn, nn + ne)
@@ -711,18 +955,52 @@ int p2_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* 
     LFGPU_LAUNCH_CHECK(ctx);
   } else if (v_end > v_first) {
     const unsigned gv = static_cast<unsigned>(cdiv(v_end - v_first, threads));
-    if (simple)
-      (bulk ? k_p2_vertex_rows<0, true> : k_p2_vertex_rows<0, false>)<<<gv, threads, smem_v, ctx->stream>>>(nn, p->p2v_nbr, p->p2v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values, v_first, v_end, beta);
-    else
-      (bulk ? k_p2_vertex_rows<1, true> : k_p2_vertex_rows<1, false>)<<<gv, threads, smem_v, ctx->stream>>>(nn, p->p2v_nbr, p->p2v_slots, mesh->node_coords, p->outer, ipf_v, P, d_values, v_first, v_end, beta);
+    const bool cv = p->p2_compact_v;
+#define P2_LAUNCH_V(MODE, BULK, COMPACT, HINT)                                                                                         \
+  k_p2_vertex_rows<MODE, BULK, COMPACT, HINT><<<gv, threads, smem_v, ctx->stream>>>(nn, p->p2v_nbr, p->p2v_slots, mesh->node_coords, p->outer, \
+                                                                                  ipf_v, P, d_values, v_first, v_end, beta, p->p2v_cidx)
+#define P2_PICK_V(MODE)                                  \
+  do {                                                   \
+    if (!bulk) {                                         \
+      if (cv) P2_LAUNCH_V(MODE, false, true, false);     \
+      else P2_LAUNCH_V(MODE, false, false, false);       \
+    } else if (hint) {                                   \
+      if (cv) P2_LAUNCH_V(MODE, true, true, true);       \
+      else P2_LAUNCH_V(MODE, true, false, true);         \
+    } else {                                             \
+      if (cv) P2_LAUNCH_V(MODE, true, true, false);      \
+      else P2_LAUNCH_V(MODE, true, false, false);        \
+    }                                                    \
+  } while (0)
+    if (simple) P2_PICK_V(0);
+    else P2_PICK_V(1);
+#undef P2_PICK_V
+#undef P2_LAUNCH_V
     LFGPU_LAUNCH_CHECK(ctx);
   }
   if (e_end > e_first) {
     const unsigned ge = static_cast<unsigned>(cdiv(e_end - e_first, threads));
-    if (simple)
-      (bulk ? k_p2_edge_rows<0, true> : k_p2_edge_rows<0, false>)<<<ge, threads, smem_e, ctx->stream>>>(ne, nn, p->p2e_nbr, p->p2e_slots, mesh->node_coords, p->outer, ipf_e, ipc_e, P, d_values, e_first, e_end, beta);
-    else
-      (bulk ? k_p2_edge_rows<1, true> : k_p2_edge_rows<1, false>)<<<ge, threads, smem_e, ctx->stream>>>(ne, nn, p->p2e_nbr, p->p2e_slots, mesh->node_coords, p->outer, ipf_e, ipc_e, P, d_values, e_first, e_end, beta);
+    const bool ce = p->p2_compact_e;
+#define P2_LAUNCH_E(MODE, BULK, COMPACT, HINT)                                                                                         \
+  k_p2_edge_rows<MODE, BULK, COMPACT, HINT><<<ge, threads, smem_e, ctx->stream>>>(ne, nn, p->p2e_nbr, p->p2e_slots, mesh->node_coords, p->outer, \
+                                                                                ipf_e, ipc_e, P, d_values, e_first, e_end, beta)
+#define P2_PICK_E(MODE)                                  \
+  do {                                                   \
+    if (!bulk) {                                         \
+      if (ce) P2_LAUNCH_E(MODE, false, true, false);     \
+      else P2_LAUNCH_E(MODE, false, false, false);       \
+    } else if (hint) {                                   \
+      if (ce) P2_LAUNCH_E(MODE, true, true, true);       \
+      else P2_LAUNCH_E(MODE, true, false, true);         \
+    } else {                                             \
+      if (ce) P2_LAUNCH_E(MODE, true, true, false);      \
+      else P2_LAUNCH_E(MODE, true, false, false);        \
+    }                                                    \
+  } while (0)
+    if (simple) P2_PICK_E(0);
+    else P2_PICK_E(1);
+#undef P2_PICK_E
+#undef P2_LAUNCH_E
     LFGPU_LAUNCH_CHECK(ctx);
   }
   return LFGPU_OK;

@@ -144,6 +144,10 @@ struct lfgpu_pattern {
   uint32_t* p2v_slots = nullptr;     // [3][p2_nn] 6 x 5 bits each: slots of the neighbour / spoke-edge / rim-edge columns
   int32_t* p2e_nbr = nullptr;        // [4][n_edges] endpoints p, q and opposite vertices o_1, o_2 of every edge row
   uint32_t* p2e_slots = nullptr;     // [n_edges] 8 x 4 bits: slots of p, q, o_1, o_2, (q,o_1), (o_1,p), (q,o_2), (o_2,p)
+  // compact form (assemble_p2.cu "compact plan"): p2v_nbr = uint32 [3][p2_nn] 16-bit differences, p2v_slots = uint4 table of slot
+  // triples, p2v_cidx = table index per row (0xFFFF: not planned); p2e_nbr = uint32 [3][n_edges], p2e_slots = uint4 table
+  bool p2_compact_v = false, p2_compact_e = false;
+  uint16_t* p2v_cidx = nullptr;
   bool p2_general = false;           // vertex rows planned for closed rings of 3..8 cells (rows_p2_core.h) instead of exactly 6
   int32_t* p2g_nbr = nullptr;        // [8][p2_nn]
   uint32_t* p2g_slots = nullptr;     // [6][p2_nn]
@@ -259,6 +263,7 @@ int p1h_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, c
 // P1 load vector with a constant source on the vertex rings (assemble_p1.cu)
 int p1_load_fan(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* d, double c, double beta, double* d_vec, int* handled);
 // P2 row kernels (assemble_p2.cu): k00 .. km = reference tensors of FeLagrangeO2Tria, [6 * 6] row-major each
+int build_row_dict(lfgpu_ctx* ctx, int n_words, int64_t n, const uint32_t* words, uint16_t* idx, void** dict_out, int* n_dict);
 int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p);
 int p2_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, const double alpha[4], int tensor, double gamma,
                    const double* k00, const double* k01, const double* k10, const double* k11, const double* km, double* d_values,

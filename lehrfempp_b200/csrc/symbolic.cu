@@ -250,6 +250,7 @@ void lfgpu_pattern_destroy(lfgpu_pattern* p) {
   cudaFree(p->p1h_rowinfo);
   cudaFree(p->p1h_irregular);
   cudaFree(p->p2v_nbr);
+  cudaFree(p->p2v_cidx);
   cudaFree(p->p2v_slots);
   cudaFree(p->p2e_nbr);
   cudaFree(p->p2e_slots);
