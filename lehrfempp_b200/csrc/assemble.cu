@@ -1050,9 +1050,9 @@ int lfgpu::assemble_rd_impl(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_
     static const bool p2_env = [] { const char* e = std::getenv("LFGPU_P2_ROWS"); return e == nullptr || e[0] != '0'; }();
     if (degree == 2 && fan_query == nullptr && (algo == LFGPU_ALGO_FAN || p2_env) && active == nullptr &&
         d_row_list == nullptr && qr_tria == nullptr && qr_quad == nullptr && da.kind <= LFGPU_COEFF_CONST_2X2 &&
-        dg.kind == LFGPU_COEFF_CONST && mesh->n_quad == 0 && mesh->cell_coords == nullptr && ht.hdr.nsf[0] == 6) {
+        dg.kind == LFGPU_COEFF_CONST && mesh->n_quad == 0 && ht.hdr.nsf[0] == 6) {
       if ((rc = p2_rows_prepare(ctx, mesh, const_cast<lfgpu_pattern*>(p))) != LFGPU_OK) return rc;
-      if (p->p2_state == 1) {
+      if (p->p2_state == 1 && p->p2_cc == (mesh->cell_coords != nullptr)) {
         const bool tr = (p->major == LFGPU_ROW_MAJOR);
         double a[4] = {da.c[0], da.c[1], da.c[2], da.c[3]};
         const int tensor = da.kind == LFGPU_COEFF_CONST_2X2;
@@ -1076,9 +1076,9 @@ int lfgpu::assemble_rd_impl(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_
     static const bool p3_env = [] { const char* e = std::getenv("LFGPU_P3_ROWS"); return e == nullptr || e[0] != '0'; }();
     if (degree == 3 && fan_query == nullptr && (algo == LFGPU_ALGO_FAN || p3_env) && active == nullptr &&
         d_row_list == nullptr && qr_tria == nullptr && qr_quad == nullptr && da.kind <= LFGPU_COEFF_CONST_2X2 &&
-        dg.kind == LFGPU_COEFF_CONST && mesh->n_quad == 0 && mesh->cell_coords == nullptr && ht.hdr.nsf[0] == 10) {
+        dg.kind == LFGPU_COEFF_CONST && mesh->n_quad == 0 && ht.hdr.nsf[0] == 10) {
       if ((rc = p3_rows_prepare(ctx, mesh, const_cast<lfgpu_pattern*>(p))) != LFGPU_OK) return rc;
-      if (p->p3_state == 1) {
+      if (p->p3_state == 1 && p->p3_cc == (mesh->cell_coords != nullptr)) {
         const bool tr = (p->major == LFGPU_ROW_MAJOR);
         double a[4] = {da.c[0], da.c[1], da.c[2], da.c[3]};
         const int tensor = da.kind == LFGPU_COEFF_CONST_2X2;

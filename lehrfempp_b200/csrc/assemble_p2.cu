@@ -53,7 +53,9 @@ __global__ void k_p2_check(int64_t n_cells, int stride, int64_t n_nodes, const i
 __global__ void k_p2_vertex_plan(int64_t n_nodes, int o_stride, int pos_row, const int32_t* __restrict__ adj_ptr,
                                  const uint32_t* __restrict__ adj, const uint32_t* __restrict__ cell_nodes,
                                  const uint8_t* __restrict__ pos, const int32_t* __restrict__ outer, int32_t* __restrict__ nbr,
-                                 uint32_t* __restrict__ slots, uint8_t* __restrict__ irregular) {
+                                 uint32_t* __restrict__ slots, uint8_t* __restrict__ irregular, int cc) {
+  // cc != 0 (mesh with per-cell corner coordinates): nbr[k][r] = cell << 4 | (local index of n_k) << 2 | local index of n_k+1 of
+  // ring cell k (the node itself is the third corner) instead of the node number n_k
   const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (r >= n_nodes) return;
   const int32_t it0 = adj_ptr[r];
@@ -139,6 +141,13 @@ __global__ void k_p2_vertex_plan(int64_t n_nodes, int o_stride, int pos_row, con
       if (seen != (1U << kVertexRowLen) - 1U) ok = false;
     }
   }
+  if (ok && cc) {
+    for (int k = 0; k < kRing; ++k) {
+      const int u = ord[k];
+      const int a = cell_a[u], vb = (a + 1) % 3, vc = (a + 2) % 3;
+      ring[k] = (static_cast<uint32_t>(cell_id[u]) << 4) | static_cast<uint32_t>((fwd[k] ? vb : vc) << 2) | static_cast<uint32_t>(fwd[k] ? vc : vb);
+    }
+  }
   for (int k = 0; k < kRing; ++k) nbr[static_cast<int64_t>(k) * n_nodes + r] = ok ? static_cast<int32_t>(ring[k]) : -1;
   for (int j = 0; j < 3; ++j) slots[static_cast<int64_t>(j) * n_nodes + r] = ok ? w[j] : 0U;
   irregular[r] = (!ok && m > 0) ? 1 : 0;
@@ -167,7 +176,9 @@ __global__ void k_p2_vertex_plan_general(int64_t n_nodes, int o_stride, int pos_
 __global__ void k_p2_edge_plan(int64_t n_nodes, int64_t n_edges, int o_stride, int pos_row, const int32_t* __restrict__ adj_ptr,
                                const uint32_t* __restrict__ adj, const uint32_t* __restrict__ cell_nodes,
                                const uint8_t* __restrict__ pos, const int32_t* __restrict__ outer, int32_t* __restrict__ enb,
-                               uint32_t* __restrict__ eslots, uint8_t* __restrict__ irregular) {
+                               uint32_t* __restrict__ eslots, uint8_t* __restrict__ irregular, int cc) {
+  // cc != 0: enb[0..1][e] = cell << 4 | (local index of q) << 2 | local index of o for the two cells (p is the third corner: the
+  // origin of the cell's frame), enb[2..3] unused
   const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (e >= n_edges) return;
   const int64_t r = n_nodes + e;
@@ -214,6 +225,13 @@ __global__ void k_p2_edge_plan(int64_t n_nodes, int64_t n_edges, int o_stride, i
       }
       if (self != 36 - sum || seen != (1U << kEdgeRowLen) - 1U) ok = false;
       ids[0] = p; ids[1] = q; ids[2] = o1; ids[3] = o2;
+      if (cc) {
+        // cell 1 is (p, q, o_1) = local (j1, j1+1, j1+2); cell 2 lists the edge as (p, q) (same) or as (q, p)
+        const int q2 = same ? (j2 + 1) % 3 : j2;
+        ids[0] = (static_cast<uint32_t>(c1) << 4) | static_cast<uint32_t>(((j1 + 1) % 3) << 2) | static_cast<uint32_t>((j1 + 2) % 3);
+        ids[1] = (static_cast<uint32_t>(c2) << 4) | static_cast<uint32_t>(q2 << 2) | static_cast<uint32_t>((j2 + 2) % 3);
+        ids[2] = ids[3] = 0;
+      }
     }
   }
   for (int k = 0; k < 4; ++k) enb[static_cast<int64_t>(k) * n_edges + e] = ok ? static_cast<int32_t>(ids[k]) : -1;
@@ -336,6 +354,14 @@ __device__ __forceinline__ double2 ld_coords(const double2* a, uint64_t pol) {
   }
   return __ldg(a);
 }
+// edge vectors of a cell from ITS corners (cell_coords [n_cells][4] points): word = cell << 4 | ia << 2 | ib, origin = third corner
+__device__ __forceinline__ void cell_vectors(const double2* cc, uint32_t cw, double& ax, double& ay, double& bx, double& by) {
+  const double2* c = cc + 4 * static_cast<size_t>(cw >> 4);
+  const int ia = (cw >> 2) & 3, ib = cw & 3;
+  const double2 x0 = __ldg(c + (3 - ia - ib)), xa = __ldg(c + ia), xb = __ldg(c + ib);
+  ax = xa.x - x0.x; ay = xa.y - x0.y;
+  bx = xb.x - x0.x; by = xb.y - x0.y;
+}
 __device__ __forceinline__ int32_t sext16(uint32_t v) { return static_cast<int32_t>(static_cast<int16_t>(v & 0xFFFFU)); }
 
 // copy-out shared by both kernels: the warp's stage is the image of the contiguous value range of its 32 rows.
@@ -398,7 +424,8 @@ __device__ __forceinline__ void write_rows(bool staged, bool regular, bool in_ra
 
 // COMPACT: nbr = the 16-bit differences cd[3][n_rows], slots = the table of slot triples (uint4), cidx[n_rows] = table index
 // HINT: L2 eviction priorities on the coordinate gathers and the value stream
-template <int MODE, bool BULK, bool COMPACT, bool HINT>
+// CC: node_coords is the mesh's cell_coords array, nbr holds (cell, corner) words (k_p2_vertex_plan)
+template <int MODE, bool BULK, bool COMPACT, bool HINT, bool CC = false>
 __global__ void __launch_bounds__(128, 6) k_p2_vertex_rows(int n_rows, const int32_t* __restrict__ nbr,
                                                          const uint32_t* __restrict__ slots, const double* __restrict__ node_coords,
                                                          const int32_t* __restrict__ outer, int pf_dist, P2Params P,
@@ -424,7 +451,7 @@ __global__ void __launch_bounds__(128, 6) k_p2_vertex_rows(int n_rows, const int
           prefetch_l2(a);
         }
       } else {
-        for (int L = lane; L < 56; L += 32) {
+        for (int L = lane; L < (CC ? 40 : 56); L += 32) {  // CC: corners are indexed by cell, not by row
           const char* a;
           if (L < 24) a = reinterpret_cast<const char*>(nbr + static_cast<size_t>(L >> 2) * n_rows + rp) + (L & 3) * 128;
           else if (L < 36) a = reinterpret_cast<const char*>(slots + static_cast<size_t>((L - 24) >> 2) * n_rows + rp) + (L & 3) * 128;
@@ -491,20 +518,25 @@ __global__ void __launch_bounds__(128, 6) k_p2_vertex_rows(int n_rows, const int
   if (regular) {
     const uint64_t keep = HINT ? l2_policy_evict_last() : 0ULL;
     const double2* nc = reinterpret_cast<const double2*>(node_coords);
-    const double2 xi = __ldg(nc + r);
     double dx[kRing], dy[kRing];
+    if (!CC) {
+      const double2 xi = __ldg(nc + r);
 #pragma unroll
-    for (int s = 0; s < kRing; ++s) {
-      const double2 p = ld_coords<HINT>(nc + nid[s], keep);
-      dx[s] = p.x - xi.x;
-      dy[s] = p.y - xi.y;
+      for (int s = 0; s < kRing; ++s) {
+        const double2 p = ld_coords<HINT>(nc + nid[s], keep);
+        dx[s] = p.x - xi.x;
+        dy[s] = p.y - xi.y;
+      }
     }
     int ssum = 0;
 #pragma unroll
     for (int s = 0; s < kRing; ++s) ssum += static_cast<int>((w0 >> (5 * s)) & 31U) + static_cast<int>((w1 >> (5 * s)) & 31U) +
                                             static_cast<int>((w2 >> (5 * s)) & 31U);
     double t[6];
-    p2_row<MODE>(P, P.vk00, P.vk01, P.vk10, P.vk11, P.vm, dx[0], dy[0], dx[1], dy[1], t);
+    double ax, ay, bx, by;
+    if (CC) cell_vectors(nc, static_cast<uint32_t>(nid[0]), ax, ay, bx, by);
+    else { ax = dx[0]; ay = dy[0]; bx = dx[1]; by = dy[1]; }
+    p2_row<MODE>(P, P.vk00, P.vk01, P.vk10, P.vk11, P.vm, ax, ay, bx, by, t);
     double diag = t[0];
     const double first_n = t[1], first_s = t[3];
     double carry_n = t[2], carry_s = t[5];
@@ -512,7 +544,9 @@ __global__ void __launch_bounds__(128, 6) k_p2_vertex_rows(int n_rows, const int
 #pragma unroll
     for (int s = 1; s < kRing; ++s) {
       const int u = (s + 1 < kRing) ? s + 1 : 0;
-      p2_row<MODE>(P, P.vk00, P.vk01, P.vk10, P.vk11, P.vm, dx[s], dy[s], dx[u], dy[u], t);
+      if (CC) cell_vectors(nc, static_cast<uint32_t>(nid[s]), ax, ay, bx, by);
+      else { ax = dx[s]; ay = dy[s]; bx = dx[u]; by = dy[u]; }
+      p2_row<MODE>(P, P.vk00, P.vk01, P.vk10, P.vk11, P.vm, ax, ay, bx, by, t);
       diag += t[0];
       dst[(w0 >> (5 * s)) & 31U] = carry_n + t[1];
       dst[(w1 >> (5 * s)) & 31U] = carry_s + t[3];
@@ -588,7 +622,8 @@ __global__ void __launch_bounds__(128, 4) k_p2_vertex_rows_general(int first, in
 
 // 12 CTAs per SM = the occupancy of the measured kernel (40 registers; the row-range arguments had pushed ptxas to 46 -> 10 CTAs)
 // COMPACT: enb = ce[3][n_edges] (p | differences | table index), eslots = the table of slot words (uint4, .x used)
-template <int MODE, bool BULK, bool COMPACT, bool HINT>
+// CC: node_coords is the mesh's cell_coords array, enb[0..1] hold the (cell, corner) words of the two cells
+template <int MODE, bool BULK, bool COMPACT, bool HINT, bool CC = false>
 __global__ void __launch_bounds__(128, 12) k_p2_edge_rows(int n_edges, int row0, const int32_t* __restrict__ enb,
                                                        const uint32_t* __restrict__ eslots, const double* __restrict__ node_coords,
                                                        const int32_t* __restrict__ outer, int pf_dist, int pfc_dist, P2Params P,
@@ -656,8 +691,10 @@ __global__ void __launch_bounds__(128, 12) k_p2_edge_rows(int n_edges, int row0,
       v1 = __ldg(outer + row0 + e + 1);
       ip = __ldg(enb + e);
       iq = __ldg(enb + static_cast<size_t>(n_edges) + e);
-      io1 = __ldg(enb + 2 * static_cast<size_t>(n_edges) + e);
-      io2 = __ldg(enb + 3 * static_cast<size_t>(n_edges) + e);
+      if (!CC) {
+        io1 = __ldg(enb + 2 * static_cast<size_t>(n_edges) + e);
+        io2 = __ldg(enb + 3 * static_cast<size_t>(n_edges) + e);
+      }
       w = __ldg(eslots + e);
     }
     regular = in_range && ip >= 0;
@@ -669,12 +706,20 @@ __global__ void __launch_bounds__(128, 12) k_p2_edge_rows(int n_edges, int row0,
   if (regular) {
     const uint64_t keep = HINT ? l2_policy_evict_last() : 0ULL;
     const double2* nc = reinterpret_cast<const double2*>(node_coords);
-    const double2 xp = ld_coords<HINT>(nc + ip, keep), xq = ld_coords<HINT>(nc + iq, keep), x1 = ld_coords<HINT>(nc + io1, keep),
-                  x2 = ld_coords<HINT>(nc + io2, keep);
-    const double ax = xq.x - xp.x, ay = xq.y - xp.y;
     double t1[6], t2[6];
-    p2_row<MODE>(P, P.ek00, P.ek01, P.ek10, P.ek11, P.em, ax, ay, x1.x - xp.x, x1.y - xp.y, t1);
-    p2_row<MODE>(P, P.ek00, P.ek01, P.ek10, P.ek11, P.em, ax, ay, x2.x - xp.x, x2.y - xp.y, t2);
+    if (CC) {
+      double ax, ay, bx, by;
+      cell_vectors(nc, static_cast<uint32_t>(ip), ax, ay, bx, by);
+      p2_row<MODE>(P, P.ek00, P.ek01, P.ek10, P.ek11, P.em, ax, ay, bx, by, t1);
+      cell_vectors(nc, static_cast<uint32_t>(iq), ax, ay, bx, by);
+      p2_row<MODE>(P, P.ek00, P.ek01, P.ek10, P.ek11, P.em, ax, ay, bx, by, t2);
+    } else {
+      const double2 xp = ld_coords<HINT>(nc + ip, keep), xq = ld_coords<HINT>(nc + iq, keep), x1 = ld_coords<HINT>(nc + io1, keep),
+                    x2 = ld_coords<HINT>(nc + io2, keep);
+      const double ax = xq.x - xp.x, ay = xq.y - xp.y;
+      p2_row<MODE>(P, P.ek00, P.ek01, P.ek10, P.ek11, P.em, ax, ay, x1.x - xp.x, x1.y - xp.y, t1);
+      p2_row<MODE>(P, P.ek00, P.ek01, P.ek10, P.ek11, P.em, ax, ay, x2.x - xp.x, x2.y - xp.y, t2);
+    }
     int ssum = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) ssum += static_cast<int>((w >> (4 * k)) & 15U);
@@ -704,9 +749,12 @@ int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
   if (p->p2_state != 0) return LFGPU_OK;
   p->p2_state = -1;
   const int64_t nn = mesh->n_nodes, ne = p->n_outer - mesh->n_nodes;
-  if (mesh->n_quad != 0 || mesh->cell_coords != nullptr || p->i_dofs != p->o_dofs || ne <= 0 || p->pos_bytes != 1 || p->pos == nullptr ||
-      p->n_outer >= (1LL << 31) - 256)
+  // cells with their own corner coordinates (cc): the plan carries (cell, corner) words instead of node numbers -- 27 bits of cell
+  const int cc = mesh->cell_coords != nullptr ? 1 : 0;
+  if (mesh->n_quad != 0 || p->i_dofs != p->o_dofs || ne <= 0 || p->pos_bytes != 1 || p->pos == nullptr || p->n_outer >= (1LL << 31) - 256 ||
+      (cc && p->n_cells >= (1LL << 27)))
     return LFGPU_OK;
+  p->p2_cc = cc != 0;
   cudaStream_t st = ctx->stream;
   int* d_flags = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 256);
   LFGPU_CUDA_CHECK(ctx, cudaMemsetAsync(d_flags, 0, 16, st));
@@ -747,11 +795,11 @@ int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
   P2_CHECK(cudaMalloc(&flag, p->n_outer));
   k_p2_vertex_plan<<<static_cast<unsigned>(cdiv(nn, 128)), 128, 0, st>>>(nn, p->o_stride, p->pos_row, p->adj_ptr, p->adj, mesh->cell_nodes,
                                                                           static_cast<const uint8_t*>(p->pos), p->outer, p->p2v_nbr,
-                                                                          p->p2v_slots, flag);
+                                                                          p->p2v_slots, flag, cc);
   ctx->launches++;
   k_p2_edge_plan<<<static_cast<unsigned>(cdiv(ne, 128)), 128, 0, st>>>(nn, ne, p->o_stride, p->pos_row, p->adj_ptr, p->adj, mesh->cell_nodes,
                                                                         static_cast<const uint8_t*>(p->pos), p->outer, p->p2e_nbr,
-                                                                        p->p2e_slots, flag);
+                                                                        p->p2e_slots, flag, cc);
   ctx->launches++;
   P2_CHECK(cudaGetLastError());
   // Unstructured meshes: vertex rows whose ring is not exactly six cells would all go to the generic kernel.  On request
@@ -760,7 +808,7 @@ int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
   // automatic (default): the general plan when more than 5 % of the vertex rows miss the valence-6 plan (Gmsh / Delaunay meshes:
   // measured on workload u2, 1.0e6 triangles: 0.297 -> 0.153 ms); LFGPU_P2_GENERAL=1 forces it, =0 never builds it
   static const int general_env = [] { const char* e = std::getenv("LFGPU_P2_GENERAL"); return e == nullptr ? -1 : (e[0] == '1' ? 1 : 0); }();
-  if (general_env != 0) {
+  if (general_env != 0 && cc == 0) {  // (the general-valence kernel reads node positions)
     int* d_cnt = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 384);
     auto count_flags = [&](const uint8_t* fl, int* h) -> cudaError_t {
       cudaError_t e = cudaMemsetAsync(d_cnt, 0, sizeof(int), st);
@@ -825,7 +873,7 @@ int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
   // lookup adds one more
   static const char compact_env = [] { const char* e = std::getenv("LFGPU_P2_COMPACT"); return e == nullptr ? '0' : e[0]; }();
   const bool compact_v = compact_env == '1' || compact_env == 'v', compact_e = compact_env == '1' || compact_env == 'e';
-  if ((compact_v || compact_e) && n_irr * 2 <= p->n_outer) {
+  if ((compact_v || compact_e) && cc == 0 && n_irr * 2 <= p->n_outer) {
     int* d_over = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 384);
     if (compact_v && !p->p2_general) {
       uint16_t* cidx = nullptr;
@@ -909,6 +957,7 @@ int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
 int p2_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, const double alpha[4], int tensor, double gamma,
                    const double* k00, const double* k01, const double* k10, const double* k11, const double* km, double* d_values,
                    int64_t r0, int64_t r1, double beta) {
+  if (p->p2_cc != (mesh->cell_coords != nullptr)) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "the P2 plan was built for another kind of mesh geometry");
   P2Params P;
   P.a00 = alpha[0]; P.a01 = tensor ? alpha[1] : 0.0; P.a10 = tensor ? alpha[2] : 0.0; P.a11 = tensor ? alpha[3] : alpha[0];
   P.gamma = gamma;
@@ -953,6 +1002,13 @@ int p2_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* 
     else
       k_p2_vertex_rows_general<1><<<gg, threads, smem_g, ctx->stream>>>(v_first, v_end, nn, p->p2g_nbr, p->p2g_slots, mesh->node_coords, p->outer, G, d_values, beta);
     LFGPU_LAUNCH_CHECK(ctx);
+  } else if (v_end > v_first && p->p2_cc) {
+    const unsigned gv = static_cast<unsigned>(cdiv(v_end - v_first, threads));
+    auto kv = simple ? (bulk ? k_p2_vertex_rows<0, true, false, false, true> : k_p2_vertex_rows<0, false, false, false, true>)
+                     : (bulk ? k_p2_vertex_rows<1, true, false, false, true> : k_p2_vertex_rows<1, false, false, false, true>);
+    kv<<<gv, threads, smem_v, ctx->stream>>>(nn, p->p2v_nbr, p->p2v_slots, mesh->cell_coords, p->outer, ipf_v, P, d_values, v_first, v_end, beta,
+                                             nullptr);
+    LFGPU_LAUNCH_CHECK(ctx);
   } else if (v_end > v_first) {
     const unsigned gv = static_cast<unsigned>(cdiv(v_end - v_first, threads));
     const bool cv = p->p2_compact_v;
@@ -978,7 +1034,13 @@ int p2_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* 
 #undef P2_LAUNCH_V
     LFGPU_LAUNCH_CHECK(ctx);
   }
-  if (e_end > e_first) {
+  if (e_end > e_first && p->p2_cc) {
+    const unsigned ge = static_cast<unsigned>(cdiv(e_end - e_first, threads));
+    auto ke = simple ? (bulk ? k_p2_edge_rows<0, true, false, false, true> : k_p2_edge_rows<0, false, false, false, true>)
+                     : (bulk ? k_p2_edge_rows<1, true, false, false, true> : k_p2_edge_rows<1, false, false, false, true>);
+    ke<<<ge, threads, smem_e, ctx->stream>>>(ne, nn, p->p2e_nbr, p->p2e_slots, mesh->cell_coords, p->outer, ipf_e, 0, P, d_values, e_first, e_end, beta);
+    LFGPU_LAUNCH_CHECK(ctx);
+  } else if (e_end > e_first) {
     const unsigned ge = static_cast<unsigned>(cdiv(e_end - e_first, threads));
     const bool ce = p->p2_compact_e;
 #define P2_LAUNCH_E(MODE, BULK, COMPACT, HINT)                                                                                         \

@@ -37,14 +37,18 @@ __global__ void k_p3_check(int64_t n_cells, int stride, int64_t n_nodes, int64_t
 __global__ void k_p3_vertex_plan(int64_t n_nodes, int o_stride, int pos_row, const int32_t* __restrict__ adj_ptr,
                                  const uint32_t* __restrict__ adj, const uint32_t* __restrict__ cell_nodes,
                                  const uint8_t* __restrict__ pos, const int32_t* __restrict__ outer, int32_t* __restrict__ nbr,
-                                 uint32_t* __restrict__ slots, uint8_t* __restrict__ irregular) {
+                                 uint32_t* __restrict__ slots, uint8_t* __restrict__ irregular, int cc) {
+  // cc != 0 (mesh with per-cell corner coordinates): nbr holds the (cell, corner) words of rows_p3_core.h instead of node numbers
   const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (r >= n_nodes) return;
   const int32_t it0 = adj_ptr[r];
   const int m = adj_ptr[r + 1] - it0;
   int32_t ring[kRing] = {-1, -1, -1, -1, -1, -1};
   uint32_t w[kVertexSlotWords] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  const bool ok = vertex_plan(r, m, adj + it0, cell_nodes, pos, o_stride, pos_row, outer[r + 1] - outer[r], ring, w);
+  uint32_t cw[kRing] = {0, 0, 0, 0, 0, 0};
+  const bool ok = vertex_plan(r, m, adj + it0, cell_nodes, pos, o_stride, pos_row, outer[r + 1] - outer[r], ring, w, cw);
+  if (cc)
+    for (int k = 0; k < kRing; ++k) ring[k] = static_cast<int32_t>(cw[k]);
   for (int k = 0; k < kRing; ++k) nbr[static_cast<int64_t>(k) * n_nodes + r] = ok ? ring[k] : -1;
   for (int j = 0; j < kVertexSlotWords; ++j) slots[static_cast<int64_t>(j) * n_nodes + r] = ok ? w[j] : 0U;
   irregular[r] = (!ok && m > 0) ? 1 : 0;
@@ -70,7 +74,8 @@ __global__ void k_p3_vertex_plan_general(int64_t n_nodes, int o_stride, int pos_
 __global__ void k_p3_edge_plan(int64_t n_nodes, int64_t n_erows, int o_stride, int pos_row, const int32_t* __restrict__ adj_ptr,
                                const uint32_t* __restrict__ adj, const uint32_t* __restrict__ cell_nodes,
                                const uint8_t* __restrict__ pos, const int32_t* __restrict__ outer, int32_t* __restrict__ enb,
-                               uint32_t* __restrict__ eslots, uint8_t* __restrict__ irregular) {
+                               uint32_t* __restrict__ eslots, uint8_t* __restrict__ irregular, int cc) {
+  // cc != 0: enb[0..1] hold the (cell, corner) words of the two cells, enb[2..3] are unused
   const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (e >= n_erows) return;
   const int64_t r = n_nodes + e;
@@ -78,7 +83,13 @@ __global__ void k_p3_edge_plan(int64_t n_nodes, int64_t n_erows, int o_stride, i
   const int m = adj_ptr[r + 1] - it0;
   int32_t ids[4] = {-1, -1, -1, -1};
   uint32_t w[kEdgeSlotWords] = {0, 0};
-  const bool ok = edge_plan(m, adj + it0, cell_nodes, pos, o_stride, pos_row, outer[r + 1] - outer[r], ids, w);
+  uint32_t cw[2] = {0, 0};
+  const bool ok = edge_plan(m, adj + it0, cell_nodes, pos, o_stride, pos_row, outer[r + 1] - outer[r], ids, w, cw);
+  if (cc) {
+    ids[0] = static_cast<int32_t>(cw[0]);
+    ids[1] = static_cast<int32_t>(cw[1]);
+    ids[2] = ids[3] = 0;
+  }
   for (int k = 0; k < 4; ++k) enb[static_cast<int64_t>(k) * n_erows + e] = ok ? ids[k] : -1;
   for (int j = 0; j < kEdgeSlotWords; ++j) eslots[static_cast<int64_t>(j) * n_erows + e] = ok ? w[j] : 0U;
   irregular[r] = (!ok && m > 0) ? 1 : 0;
@@ -130,11 +141,26 @@ __device__ __forceinline__ void write_rows(bool staged, bool regular, bool in_ra
   }
 }
 
+// edge vectors of a cell from ITS corners: word = cell << 4 | ia << 2 | ib, origin = the third corner (rows_p3_core.h)
+struct DevCellVec {
+  const double2* cc;    // cell_coords as [n_cells][4] points
+  const int32_t* words;
+  __device__ __forceinline__ void operator()(int k, double& ax, double& ay, double& bx, double& by) const {
+    const uint32_t cw = static_cast<uint32_t>(words[k]);
+    const double2* c = cc + 4 * static_cast<size_t>(cw >> 4);
+    const int ia = (cw >> 2) & 3, ib = cw & 3;
+    const double2 x0 = __ldg(c + (3 - ia - ib)), xa = __ldg(c + ia), xb = __ldg(c + ib);
+    ax = xa.x - x0.x; ay = xa.y - x0.y;
+    bx = xb.x - x0.x; by = xb.y - x0.y;
+  }
+};
+
 // MINB = 4 (opt-in, LFGPU_P3_VOCC=4; MODE 1 only): 128 registers instead of 168 -- a fourth CTA per SM for 172 bytes of spills.
 // The row-range arguments come LAST in every row kernel: in front they moved `Params P` from a 16-byte to an 8-byte aligned
 // offset of the parameter space, and ptxas then spilled 52 bytes in this kernel (MODE 1, 168 registers = the cap of 3 CTAs per
 // SM) that the measured kernel did not spill.  With them at the end the layout up to `values` is the measured one.
-template <int MODE, int MINB = 3>
+// CC: node_coords is the mesh's cell_coords array, nbr holds (cell, corner) words
+template <int MODE, int MINB = 3, bool CC = false>
 __global__ void __launch_bounds__(128, MINB) k_p3_vertex_rows(int n_rows, const int32_t* __restrict__ nbr,
                                                          const uint32_t* __restrict__ slots, const double* __restrict__ node_coords,
                                                          const int32_t* __restrict__ outer, int pf_dist, Params P,
@@ -148,7 +174,7 @@ __global__ void __launch_bounds__(128, MINB) k_p3_vertex_rows(int n_rows, const 
     // lines of the CTA about one wave later: 4 per plan array (6 ring + 9 slot arrays), 4 of row pointers, 16 of coordinates
     const int rp = first + blockIdx.x * blockDim.x + pf_dist;
     if (rp + 128 <= end) {
-      for (int L = lane; L < 80; L += 32) {
+      for (int L = lane; L < (CC ? 64 : 80); L += 32) {  // CC: the corners are indexed by cell, not by row
         const char* a;
         if (L < 24) a = reinterpret_cast<const char*>(nbr + static_cast<size_t>(L >> 2) * n_rows + rp) + (L & 3) * 128;
         else if (L < 60) a = reinterpret_cast<const char*>(slots + static_cast<size_t>((L - 24) >> 2) * n_rows + rp) + (L & 3) * 128;
@@ -180,15 +206,19 @@ __global__ void __launch_bounds__(128, MINB) k_p3_vertex_rows(int n_rows, const 
   double* dst = stage + (staged ? v0 - wbase : lane * (kVertexRowLen + 1));
   if (regular) {
     const double2* nc = reinterpret_cast<const double2*>(node_coords);
-    const double2 xi = __ldg(nc + r);
-    double dx[kRing], dy[kRing];
+    if (CC) {
+      vertex_row_cv<MODE>(P, DevCellVec{nc, nid}, w, dst);
+    } else {
+      const double2 xi = __ldg(nc + r);
+      double dx[kRing], dy[kRing];
 #pragma unroll
-    for (int s = 0; s < kRing; ++s) {
-      const double2 p = __ldg(nc + nid[s]);
-      dx[s] = p.x - xi.x;
-      dy[s] = p.y - xi.y;
+      for (int s = 0; s < kRing; ++s) {
+        const double2 p = __ldg(nc + nid[s]);
+        dx[s] = p.x - xi.x;
+        dy[s] = p.y - xi.y;
+      }
+      vertex_row<MODE>(P, dx, dy, w, dst);
     }
-    vertex_row<MODE>(P, dx, dy, w, dst);
   }
   write_rows<kVertexRowLen>(staged, regular, in_range, lane, v0, v1, wbase, stage, dst, values, beta);
 }
@@ -252,7 +282,7 @@ __global__ void __launch_bounds__(128, 2) k_p3_vertex_rows_general(int first, in
   }
 }
 
-template <int MODE, int MINB = 4>
+template <int MODE, int MINB = 4, bool CC = false>
 __global__ void __launch_bounds__(128, MINB) k_p3_edge_rows(int n_erows, int row0, const int32_t* __restrict__ enb,
                                                        const uint32_t* __restrict__ eslots, const double* __restrict__ node_coords,
                                                        const int32_t* __restrict__ outer, int pf_dist, int pfc_dist, Params P,
@@ -280,7 +310,7 @@ __global__ void __launch_bounds__(128, MINB) k_p3_edge_rows(int n_erows, int row
   int32_t pf_id[4] = {-1, -1, -1, -1};
   if (pfc_dist > 0 && e + pfc_dist < end) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) pf_id[k] = __ldg(enb + static_cast<size_t>(k) * n_erows + e + pfc_dist);
+    for (int k = 0; k < (CC ? 2 : 4); ++k) pf_id[k] = __ldg(enb + static_cast<size_t>(k) * n_erows + e + pfc_dist);
   }
   int32_t v0 = 0, v1 = 0;
   int32_t ip = -1, iq = 0, io1 = 0, io2 = 0;
@@ -290,8 +320,10 @@ __global__ void __launch_bounds__(128, MINB) k_p3_edge_rows(int n_erows, int row
     v1 = __ldg(outer + row0 + e + 1);
     ip = __ldg(enb + e);
     iq = __ldg(enb + static_cast<size_t>(n_erows) + e);
-    io1 = __ldg(enb + 2 * static_cast<size_t>(n_erows) + e);
-    io2 = __ldg(enb + 3 * static_cast<size_t>(n_erows) + e);
+    if (!CC) {
+      io1 = __ldg(enb + 2 * static_cast<size_t>(n_erows) + e);
+      io2 = __ldg(enb + 3 * static_cast<size_t>(n_erows) + e);
+    }
     w[0] = __ldg(eslots + e);
     w[1] = __ldg(eslots + static_cast<size_t>(n_erows) + e);
   }
@@ -302,12 +334,21 @@ __global__ void __launch_bounds__(128, MINB) k_p3_edge_rows(int n_erows, int row
   const int off = staged ? v0 - wbase : lane * kEdgeRowLen;
   if (regular) {
     const double2* nc = reinterpret_cast<const double2*>(node_coords);
-    const double2 xp = __ldg(nc + ip), xq = __ldg(nc + iq), x1 = __ldg(nc + io1), x2 = __ldg(nc + io2);
-    edge_row<MODE, true>(P, xq.x - xp.x, xq.y - xp.y, x1.x - xp.x, x1.y - xp.y, x2.x - xp.x, x2.y - xp.y, w, stage, off);
+    if (CC) {
+      const int32_t cw[2] = {ip, iq};
+      const DevCellVec cv{nc, cw};
+      double a1x, a1y, b1x, b1y, a2x, a2y, b2x, b2y;
+      cv(0, a1x, a1y, b1x, b1y);
+      cv(1, a2x, a2y, b2x, b2y);
+      edge_row2<MODE, true>(P, a1x, a1y, b1x, b1y, a2x, a2y, b2x, b2y, w, stage, off);
+    } else {
+      const double2 xp = __ldg(nc + ip), xq = __ldg(nc + iq), x1 = __ldg(nc + io1), x2 = __ldg(nc + io2);
+      edge_row<MODE, true>(P, xq.x - xp.x, xq.y - xp.y, x1.x - xp.x, x1.y - xp.y, x2.x - xp.x, x2.y - xp.y, w, stage, off);
+    }
   }
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
-    if (pf_id[k] >= 0) prefetch_l2(node_coords + 2 * static_cast<size_t>(pf_id[k]));
+  for (int k = 0; k < (CC ? 2 : 4); ++k)
+    if (pf_id[k] >= 0) prefetch_l2(CC ? node_coords + 8 * static_cast<size_t>(static_cast<uint32_t>(pf_id[k]) >> 4) : node_coords + 2 * static_cast<size_t>(pf_id[k]));
   write_rows<kEdgeRowLen, true>(staged, regular, in_range, lane, v0, v1, wbase, stage, stage, values, beta, off);
 }
 
@@ -324,7 +365,8 @@ __global__ void k_p3_cell_plan(int64_t n_cells, int o_stride, int pos_row, const
 }
 
 // one thread per cell: row 9 of its element matrix (cell_nodes + the compact slot word pair)
-template <int MODE>
+// CC: node_coords is the mesh's cell_coords array (the cell's own corners, no gather through cell_nodes)
+template <int MODE, bool CC = false>
 __global__ void __launch_bounds__(128, 4) k_p3_cell_rows(int row0, const uint32_t* __restrict__ cell_nodes, const uint2* __restrict__ cslots,
                                                        const double* __restrict__ node_coords, const int32_t* __restrict__ outer, int pf_dist,
                                                        Params P, double* __restrict__ values, int first, int end, double beta) {
@@ -340,7 +382,11 @@ __global__ void __launch_bounds__(128, 4) k_p3_cell_rows(int row0, const uint32_
       if (lane < 16) a = reinterpret_cast<const char*>(cell_nodes + 4 * static_cast<size_t>(cp)) + lane * 128;
       else if (lane < 24) a = reinterpret_cast<const char*>(cslots + cp) + (lane - 16) * 128;
       else a = reinterpret_cast<const char*>(outer + row0 + cp) + (lane - 24) * 128;
-      prefetch_l2(a);
+      if (!CC || lane >= 16) prefetch_l2(a);
+    }
+    if (CC && cp + 128 <= end) {  // 64 lines of corner coordinates (64 bytes per cell)
+      prefetch_l2(reinterpret_cast<const char*>(node_coords + 8 * static_cast<size_t>(cp)) + lane * 128);
+      prefetch_l2(reinterpret_cast<const char*>(node_coords + 8 * static_cast<size_t>(cp)) + (32 + lane) * 128);
     }
   }
   int32_t v0 = 0, v1 = 0;
@@ -352,11 +398,20 @@ __global__ void __launch_bounds__(128, 4) k_p3_cell_rows(int row0, const uint32_
   double* stage = stage_all + warp * (32 * kCellRowLen);
   const int off = v0 - wbase;
   if (in_range) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(cell_nodes) + c);
     const uint2 sw = __ldg(cslots + c);
     const uint32_t pw[3] = {sw.x, sw.y, 0U};
     const double2* nc = reinterpret_cast<const double2*>(node_coords);
-    const double2 x0 = __ldg(nc + v.x), x1 = __ldg(nc + v.y), x2 = __ldg(nc + v.z);
+    double2 x0, x1, x2;
+    if (CC) {
+      x0 = __ldg(nc + 4 * static_cast<size_t>(c));
+      x1 = __ldg(nc + 4 * static_cast<size_t>(c) + 1);
+      x2 = __ldg(nc + 4 * static_cast<size_t>(c) + 2);
+    } else {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(cell_nodes) + c);
+      x0 = __ldg(nc + v.x);
+      x1 = __ldg(nc + v.y);
+      x2 = __ldg(nc + v.z);
+    }
     cell_row<MODE, true, true>(P, x1.x - x0.x, x1.y - x0.y, x2.x - x0.x, x2.y - x0.y, pw, stage, off);
   }
   write_rows<kCellRowLen, true>(true, in_range, in_range, lane, v0, v1, wbase, stage, stage, values, beta, off);
@@ -375,9 +430,13 @@ int p3_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
   if (p->p3_state != 0) return LFGPU_OK;
   p->p3_state = -1;
   const int64_t nn = mesh->n_nodes, base_int = p->n_outer - p->n_cells, ner = base_int - nn;
-  if (mesh->n_quad != 0 || mesh->cell_coords != nullptr || p->i_dofs != p->o_dofs || ner <= 0 || p->pos_bytes != 1 || p->pos == nullptr ||
+  if (mesh->n_quad != 0 || p->i_dofs != p->o_dofs || ner <= 0 || p->pos_bytes != 1 || p->pos == nullptr ||
       p->n_outer >= (1LL << 31) - 256 || p->n_cells >= (1LL << 27))
     return LFGPU_OK;
+  // cells with their own corner coordinates: the plan carries (cell, corner) words instead of node numbers (rows_p3_core.h);
+  // the general-valence vertex plan is not built for them (their other vertex rows go to the generic kernel)
+  const int cc = mesh->cell_coords != nullptr ? 1 : 0;
+  p->p3_cc = cc != 0;
   cudaStream_t st = ctx->stream;
   int* d_flags = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 256);
   LFGPU_CUDA_CHECK(ctx, cudaMemsetAsync(d_flags, 0, 16, st));
@@ -428,11 +487,11 @@ int p3_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
   ctx->launches++;
   k_p3_vertex_plan<<<static_cast<unsigned>(cdiv(nn, 128)), 128, 0, st>>>(nn, p->o_stride, p->pos_row, p->adj_ptr, p->adj, mesh->cell_nodes,
                                                                           static_cast<const uint8_t*>(p->pos), p->outer, p->p3v_nbr,
-                                                                          p->p3v_slots, flag);
+                                                                          p->p3v_slots, flag, cc);
   ctx->launches++;
   k_p3_edge_plan<<<static_cast<unsigned>(cdiv(ner, 128)), 128, 0, st>>>(nn, ner, p->o_stride, p->pos_row, p->adj_ptr, p->adj, mesh->cell_nodes,
                                                                          static_cast<const uint8_t*>(p->pos), p->outer, p->p3e_nbr,
-                                                                         p->p3e_slots, flag);
+                                                                         p->p3e_slots, flag, cc);
   ctx->launches++;
   P3_CHECK(cudaGetLastError());
   // unstructured meshes, on request (LFGPU_P3_GENERAL=1; core checked on the CPU, wrapper not yet run on a B200): the plan
@@ -440,7 +499,7 @@ int p3_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
   // automatic (default): the general plan when more than 5 % of the vertex rows miss the valence-6 plan (Gmsh / Delaunay meshes:
   // measured on workload u2, 1.0e6 triangles: 0.297 -> 0.153 ms); LFGPU_P3_GENERAL=1 forces it, =0 never builds it
   static const int general_env = [] { const char* e = std::getenv("LFGPU_P3_GENERAL"); return e == nullptr ? -1 : (e[0] == '1' ? 1 : 0); }();
-  if (general_env != 0) {
+  if (general_env != 0 && cc == 0) {
     int* d_cnt = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 384);
     auto count_flags = [&](const uint8_t* fl, int* h) -> cudaError_t {
       cudaError_t e = cudaMemsetAsync(d_cnt, 0, sizeof(int), st);
@@ -548,6 +607,23 @@ int p3_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* 
   const int e_first = clip(r0 - nn, 0, ner), e_end = clip(r1 - nn, 0, ner);
   const int c_first = clip(r0 - base_int, 0, nc), c_end = clip(r1 - base_int, 0, nc);
   const size_t smem_g = sizeof(double) * (threads / 32) * 32 * (kMaxVertexRowLen + 1);
+  // meshes with per-cell corners: the CC instantiations read mesh->cell_coords (default occupancies only)
+#define P3_LAUNCH_CC(MODE)                                                                                                                \
+  if (v_end > v_first) {                                                                                                                  \
+    k_p3_vertex_rows<MODE, 3, true><<<static_cast<unsigned>(cdiv(v_end - v_first, threads)), threads, smem_v, ctx->stream>>>(             \
+        nn, p->p3v_nbr, p->p3v_slots, mesh->cell_coords, p->outer, ipf_v, P, d_values, v_first, v_end, beta);                             \
+    LFGPU_LAUNCH_CHECK(ctx);                                                                                                              \
+  }                                                                                                                                       \
+  if (e_end > e_first) {                                                                                                                  \
+    k_p3_edge_rows<MODE, 8, true><<<static_cast<unsigned>(cdiv(e_end - e_first, threads)), threads, smem_e, ctx->stream>>>(               \
+        ner, nn, p->p3e_nbr, p->p3e_slots, mesh->cell_coords, p->outer, ipf_e, ipc_e, P, d_values, e_first, e_end, beta);                 \
+    LFGPU_LAUNCH_CHECK(ctx);                                                                                                              \
+  }                                                                                                                                       \
+  if (c_end > c_first) {                                                                                                                  \
+    k_p3_cell_rows<MODE, true><<<static_cast<unsigned>(cdiv(c_end - c_first, threads)), threads, smem_c, ctx->stream>>>(                  \
+        base_int, mesh->cell_nodes, static_cast<const uint2*>(p->p3c_slots), mesh->cell_coords, p->outer, ipf_c, P, d_values, c_first, c_end, beta); \
+    LFGPU_LAUNCH_CHECK(ctx);                                                                                                              \
+  }
 #define P3_LAUNCH(MODE)                                                                                                                   \
   if (v_end > v_first && p->p3_general) {                                                                                                 \
     /* 51 200 bytes of stage: above the 48 KB a kernel gets without asking */                                                             \
@@ -576,12 +652,20 @@ int p3_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* 
         base_int, mesh->cell_nodes, static_cast<const uint2*>(p->p3c_slots), mesh->node_coords, p->outer, ipf_c, P, d_values, c_first, c_end, beta);               \
     LFGPU_LAUNCH_CHECK(ctx);                                                                                                              \
   }
-  if (simple) {
+  if (p->p3_cc) {
+    if (mesh->cell_coords == nullptr) LFGPU_FAIL(ctx, LFGPU_ERR_INVALID, "the P3 plan was built for a mesh with cell corners");
+    if (simple) {
+      P3_LAUNCH_CC(0)
+    } else {
+      P3_LAUNCH_CC(1)
+    }
+  } else if (simple) {
     P3_LAUNCH(0)
   } else {
     P3_LAUNCH(1)
   }
 #undef P3_LAUNCH
+#undef P3_LAUNCH_CC
   return LFGPU_OK;
 }
 

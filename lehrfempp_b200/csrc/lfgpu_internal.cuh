@@ -148,6 +148,7 @@ struct lfgpu_pattern {
   // triples, p2v_cidx = table index per row (0xFFFF: not planned); p2e_nbr = uint32 [3][n_edges], p2e_slots = uint4 table
   bool p2_compact_v = false, p2_compact_e = false;
   uint16_t* p2v_cidx = nullptr;
+  bool p2_cc = false;                // plan built for a mesh with per-cell corners: p2v_nbr / p2e_nbr hold (cell, corner) words
   bool p2_general = false;           // vertex rows planned for closed rings of 3..8 cells (rows_p2_core.h) instead of exactly 6
   int32_t* p2g_nbr = nullptr;        // [8][p2_nn]
   uint32_t* p2g_slots = nullptr;     // [6][p2_nn]
@@ -162,6 +163,7 @@ struct lfgpu_pattern {
   int32_t* p3e_nbr = nullptr;        // [4][n_edge_rows] P, Q, o_1, o_2
   uint32_t* p3e_slots = nullptr;     // [2][n_edge_rows] 16 slot nibbles per row
   void* p3c_slots = nullptr;         // uint2 [n_cells] slots of the ten list positions in the cell's own row, one nibble each
+  bool p3_cc = false;                // plan built for a mesh with per-cell corners: p3v_nbr / p3e_nbr hold (cell, corner) words
   bool p3_general = false;           // vertex rows planned for closed rings of 3..8 cells instead of exactly 6
   int32_t* p3g_nbr = nullptr;        // [8][p3_nn]
   uint32_t* p3g_slots = nullptr;     // [13][p3_nn]

@@ -108,8 +108,12 @@ LFGPU_HD int nibble_at(const uint32_t* w, int i) { return static_cast<int>((w[i 
 // pos_row + b] = slot of list position b in the row of list position a; row_len: stored values of the row.
 
 // Vertex row r: false unless exactly six cells close around the node and the 37 slots are a permutation of 0..36.
+// cellw (optional, six entries): for meshes whose cells carry their own corner coordinates (lfgpu_mesh_upload: cell_coords) the
+// kernels read the corners of ring cell k instead of node positions: cellw[k] = cell << 4 | (local index of n_k) << 2 | local
+// index of n_k+1 (the node itself is the third corner).
 LFGPU_HD bool vertex_plan(int64_t r, int m, const uint32_t* items, const uint32_t* cell_nodes, const uint8_t* pos, int o_stride,
-                          int pos_row, int row_len, int32_t (&ring)[kRing], uint32_t (&words)[kVertexSlotWords]) {
+                          int pos_row, int row_len, int32_t (&ring)[kRing], uint32_t (&words)[kVertexSlotWords],
+                          uint32_t* cellw = nullptr) {
   if (m != kRing || row_len != kVertexRowLen) return false;
   uint32_t ja[kRing], ka[kRing];
   int la[kRing];
@@ -188,6 +192,13 @@ LFGPU_HD bool vertex_plan(int64_t r, int m, const uint32_t* items, const uint32_
   for (int j = 0; j < kVertexSlotWords; ++j)
     words[j] = static_cast<uint32_t>(s[4 * j]) | (static_cast<uint32_t>(s[4 * j + 1]) << 8) | (static_cast<uint32_t>(s[4 * j + 2]) << 16) |
                (static_cast<uint32_t>(s[4 * j + 3]) << 24);
+  if (cellw != nullptr) {
+    for (int k = 0; k < kRing; ++k) {
+      const int u = ord[k];
+      const int a = la[u], vb = (a + 1) % 3, vc = (a + 2) % 3;
+      cellw[k] = (static_cast<uint32_t>(cid[u]) << 4) | static_cast<uint32_t>((fwd[k] ? vb : vc) << 2) | static_cast<uint32_t>(fwd[k] ? vc : vb);
+    }
+  }
   return true;
 }
 
@@ -283,10 +294,13 @@ LFGPU_HD bool vertex_plan_general(int64_t r, int m, const uint32_t* items, const
 
 // Edge-dof row: false unless exactly two cells share the edge and the 16 slots are a permutation of 0..15.
 // ids = P (endpoint nearer to the dof), Q, o_1, o_2.
+// cellw (optional, two entries): cell << 4 | (local index of Q) << 2 | local index of o -- P, the origin of the cell's frame, is
+// the third corner (as the node itself is for vertex_plan).
 LFGPU_HD bool edge_plan(int m, const uint32_t* items, const uint32_t* cell_nodes, const uint8_t* pos, int o_stride, int pos_row, int row_len,
-                        int32_t (&ids)[4], uint32_t (&words)[kEdgeSlotWords]) {
+                        int32_t (&ids)[4], uint32_t (&words)[kEdgeSlotWords], uint32_t* cellw = nullptr) {
   if (m != 2 || row_len != kEdgeRowLen) return false;
   uint8_t s[16];
+  uint32_t cw[2] = {0U, 0U};
   uint32_t P = 0, Q = 0, o[2] = {0, 0};
   for (int c = 0; c < 2; ++c) {
     const int64_t cell = items[c] >> 4;
@@ -309,6 +323,7 @@ LFGPU_HD bool edge_plan(int m, const uint32_t* items, const uint32_t* cell_nodes
       if (prow[a] != s[2] || prow[w == 0 ? a + 1 : a - 1] != s[3]) return false;
     }
     o[c] = v[j2];
+    cw[c] = (static_cast<uint32_t>(cell) << 4) | static_cast<uint32_t>((w == 0 ? j1 : j) << 2) | static_cast<uint32_t>(j2);
     uint8_t* sc = s + 4 + 6 * c;
     sc[0] = prow[j2];
     if (w == 0) {
@@ -339,6 +354,10 @@ LFGPU_HD bool edge_plan(int m, const uint32_t* items, const uint32_t* cell_nodes
   ids[3] = static_cast<int32_t>(o[1]);
   words[0] = words[1] = 0U;
   for (int k = 0; k < 16; ++k) words[k >> 3] |= static_cast<uint32_t>(s[k]) << (4 * (k & 7));
+  if (cellw != nullptr) {
+    cellw[0] = cw[0];
+    cellw[1] = cw[1];
+  }
   return true;
 }
 
@@ -368,6 +387,52 @@ LFGPU_HD void vertex_row(const Params& P, const double (&dx)[kRing], const doubl
   for (int s = 1; s < kRing; ++s) {
     const int u = (s + 1 < kRing) ? s + 1 : 0;
     row<MODE, 0>(P, dx[s], dy[s], dx[u], dy[u], t);
+    diag += t[0];
+    dst[byte_at(w, 6 * s + 0)] = carry_n + t[1];
+    dst[byte_at(w, 6 * s + 1)] = carry_a + t[3];
+    dst[byte_at(w, 6 * s + 2)] = carry_b + t[4];
+    dst[byte_at(w, 6 * s + 3)] = t[5];
+    dst[byte_at(w, 6 * s + 4)] = t[6];
+    dst[byte_at(w, 6 * s + 5)] = t[9];
+    carry_n = t[2];
+    carry_b = t[7];
+    carry_a = t[8];
+  }
+  dst[byte_at(w, 0)] = first_n + carry_n;
+  dst[byte_at(w, 1)] = first_a + carry_a;
+  dst[byte_at(w, 2)] = first_b + carry_b;
+  dst[666 - ssum] = diag;
+}
+
+// The same row with the edge vectors of every ring cell supplied by the caller: cv(k, ax, ay, bx, by) returns A = n_k - i and
+// B = n_k+1 - i as cell k sees them (meshes with per-cell corner coordinates: the corners of two cells at one node may differ in
+// the last bit, and the reference computes every element matrix from the cell's own geometry object, tria_o1.cc:50-74).
+// (A separate function: vertex_row above is the measured kernel body and stays as it is.)
+template <int MODE, class CELLVEC>
+LFGPU_HD void vertex_row_cv(const Params& P, const CELLVEC& cv, const uint32_t (&w)[kVertexSlotWords], double* dst) {
+  int ssum = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+  for (int j = 0; j < kVertexSlotWords; ++j) ssum += static_cast<int>(__vsadu4(w[j], 0U));
+#else
+  for (int j = 0; j < 36; ++j) ssum += byte_at(w, j);
+#endif
+  double t[10];
+  double ax, ay, bx, by;
+  cv(0, ax, ay, bx, by);
+  row<MODE, 0>(P, ax, ay, bx, by, t);
+  double diag = t[0];
+  const double first_n = t[1], first_a = t[3], first_b = t[4];
+  double carry_n = t[2], carry_b = t[7], carry_a = t[8];
+  dst[byte_at(w, 3)] = t[5];
+  dst[byte_at(w, 4)] = t[6];
+  dst[byte_at(w, 5)] = t[9];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int s = 1; s < kRing; ++s) {
+    cv(s, ax, ay, bx, by);
+    row<MODE, 0>(P, ax, ay, bx, by, t);
     diag += t[0];
     dst[byte_at(w, 6 * s + 0)] = carry_n + t[1];
     dst[byte_at(w, 6 * s + 1)] = carry_a + t[3];
@@ -436,6 +501,28 @@ LFGPU_HD void edge_row(const Params& P, double ax, double ay, double b1x, double
   double t1[10], t2[10];
   row<MODE, 1>(P, ax, ay, b1x, b1y, t1);
   row<MODE, 1>(P, ax, ay, b2x, b2y, t2);
+  dst[stage_ix<SWZ>(off + nibble_at(w, 0))] = t1[0] + t2[0];
+  dst[stage_ix<SWZ>(off + nibble_at(w, 1))] = t1[1] + t2[1];
+  dst[stage_ix<SWZ>(off + nibble_at(w, 2))] = t1[3] + t2[3];
+  dst[stage_ix<SWZ>(off + nibble_at(w, 3))] = t1[4] + t2[4];
+  dst[stage_ix<SWZ>(off + nibble_at(w, 4))] = t1[2];
+  dst[stage_ix<SWZ>(off + nibble_at(w, 10))] = t2[2];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 5; ++k) {
+    dst[stage_ix<SWZ>(off + nibble_at(w, 5 + k))] = t1[5 + k];
+    dst[stage_ix<SWZ>(off + nibble_at(w, 11 + k))] = t2[5 + k];
+  }
+}
+
+// The same row with each cell's own edge vectors: (a1, b1) = (Q - P, o_1 - P) from the corners of cell 1, (a2, b2) from cell 2
+template <int MODE, bool SWZ = false>
+LFGPU_HD void edge_row2(const Params& P, double a1x, double a1y, double b1x, double b1y, double a2x, double a2y, double b2x, double b2y,
+                        const uint32_t (&w)[kEdgeSlotWords], double* dst, int off = 0) {
+  double t1[10], t2[10];
+  row<MODE, 1>(P, a1x, a1y, b1x, b1y, t1);
+  row<MODE, 1>(P, a2x, a2y, b2x, b2y, t2);
   dst[stage_ix<SWZ>(off + nibble_at(w, 0))] = t1[0] + t2[0];
   dst[stage_ix<SWZ>(off + nibble_at(w, 1))] = t1[1] + t2[1];
   dst[stage_ix<SWZ>(off + nibble_at(w, 2))] = t1[3] + t2[3];

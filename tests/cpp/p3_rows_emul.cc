@@ -12,6 +12,18 @@ using namespace lfgpu::p3;
 
 namespace {
 bool g_general = false;  // vertex rows through the general-valence functions
+const double* g_cell_xy = nullptr;  // [n_cells][4][2]: corners per cell (the kernels' cell_coords mode), else node positions
+
+struct HostCellVec {
+  const double* cell_xy;
+  const uint32_t* cw;
+  void operator()(int k, double& ax, double& ay, double& bx, double& by) const {
+    const double* c = cell_xy + 8 * static_cast<size_t>(cw[k] >> 4);
+    const int ia = (cw[k] >> 2) & 3, ib = cw[k] & 3, i0 = 3 - ia - ib;
+    ax = c[2 * ia] - c[2 * i0]; ay = c[2 * ia + 1] - c[2 * i0 + 1];
+    bx = c[2 * ib] - c[2 * i0]; by = c[2 * ib + 1] - c[2 * i0 + 1];
+  }
+};
 template <int MODE>
 void run(const Params& P, int64_t n_nodes, int64_t n_cells, const uint32_t* cell_nodes, const double* xy, int stride, int pos_row,
          const std::vector<int64_t>& adj_ptr, const std::vector<uint32_t>& adj, const std::vector<uint8_t>& pos, int64_t n_dofs,
@@ -35,6 +47,11 @@ void run(const Params& P, int64_t n_nodes, int64_t n_cells, const uint32_t* cell
           dy[k] = xy[2 * n + 1] - xy[2 * r + 1];
         }
         vertex_row_general<MODE>(P, dx, dy, w, dst);
+      } else if (g_cell_xy != nullptr) {
+        int32_t ring[kRing];
+        uint32_t w[kVertexSlotWords], cw[kRing];
+        if (!vertex_plan(r, m, items, cell_nodes, pos.data(), stride, pos_row, len, ring, w, cw)) continue;
+        vertex_row_cv<MODE>(P, HostCellVec{g_cell_xy, cw}, w, dst);
       } else {
         int32_t ring[kRing];
         uint32_t w[kVertexSlotWords];
@@ -50,8 +67,18 @@ void run(const Params& P, int64_t n_nodes, int64_t n_cells, const uint32_t* cell
       counts[0]++;
     } else if (r < base_int) {
       int32_t ids[4];
-      uint32_t w[kEdgeSlotWords];
-      if (!edge_plan(m, items, cell_nodes, pos.data(), stride, pos_row, len, ids, w)) continue;
+      uint32_t w[kEdgeSlotWords], cw[2];
+      if (!edge_plan(m, items, cell_nodes, pos.data(), stride, pos_row, len, ids, w, cw)) continue;
+      if (g_cell_xy != nullptr) {
+        double a1x, a1y, b1x, b1y, a2x, a2y, b2x, b2y;
+        const HostCellVec cv{g_cell_xy, cw};
+        cv(0, a1x, a1y, b1x, b1y);
+        cv(1, a2x, a2y, b2x, b2y);
+        edge_row2<MODE>(P, a1x, a1y, b1x, b1y, a2x, a2y, b2x, b2y, w, dst);
+        regular[r] = 1;
+        counts[1]++;
+        continue;
+      }
       const double px = xy[2 * ids[0]], py = xy[2 * ids[0] + 1];
       edge_row<MODE>(P, xy[2 * ids[1]] - px, xy[2 * ids[1] + 1] - py, xy[2 * ids[2]] - px, xy[2 * ids[2] + 1] - py, xy[2 * ids[3]] - px,
                      xy[2 * ids[3] + 1] - py, w, dst);
@@ -66,8 +93,13 @@ void run(const Params& P, int64_t n_nodes, int64_t n_cells, const uint32_t* cell
       for (int j = 0; j < 3; ++j)
         pw[j] = static_cast<uint32_t>(prow[4 * j]) | (static_cast<uint32_t>(prow[4 * j + 1]) << 8) |
                 (static_cast<uint32_t>(prow[4 * j + 2]) << 16) | (static_cast<uint32_t>(prow[4 * j + 3]) << 24);
-      const double x0 = xy[2 * v[0]], y0 = xy[2 * v[0] + 1];
-      cell_row<MODE>(P, xy[2 * v[1]] - x0, xy[2 * v[1] + 1] - y0, xy[2 * v[2]] - x0, xy[2 * v[2] + 1] - y0, pw, dst);
+      if (g_cell_xy != nullptr) {
+        const double* cx = g_cell_xy + 8 * static_cast<size_t>(c);
+        cell_row<MODE>(P, cx[2] - cx[0], cx[3] - cx[1], cx[4] - cx[0], cx[5] - cx[1], pw, dst);
+      } else {
+        const double x0 = xy[2 * v[0]], y0 = xy[2 * v[0] + 1];
+        cell_row<MODE>(P, xy[2 * v[1]] - x0, xy[2 * v[1] + 1] - y0, xy[2 * v[2]] - x0, xy[2 * v[2] + 1] - y0, pw, dst);
+      }
       regular[r] = 1;
       counts[2]++;
     }
@@ -76,6 +108,7 @@ void run(const Params& P, int64_t n_nodes, int64_t n_cells, const uint32_t* cell
 }  // namespace
 
 extern "C" void p3_rows_emulate_general(int on) { g_general = on != 0; }
+extern "C" void p3_rows_emulate_cell_coords(const double* cell_xy) { g_cell_xy = cell_xy; }
 
 extern "C" int p3_rows_emulate(int64_t n_nodes, int64_t n_cells, const uint32_t* cell_nodes, const double* node_xy, int stride,
                                const int32_t* dofs, int64_t n_dofs, const int32_t* outer, const int32_t* inner, const double* alpha4,

@@ -1,0 +1,129 @@
+"""P2 / P3 row kernels on meshes whose cells carry their own corner coordinates (lfgpu_mesh_upload: cell_coords -- what the
+reference's Geometry objects hold; after MeshHierarchy::RefineRegular they differ from the node positions in the last bits,
+refinement/mesh_hierarchy.cc, geometry/tria_o1.cc:99-151).  The reference computes every element matrix from the cell's own
+geometry (loc_comp_ellbvp.h:289-296), so the kernels must read THESE corners: the plan carries (cell, corner) words and the CC
+instantiations of the kernels gather from cell_coords.  LFGPU_ALGO_FAN refuses to fall back, so every case ran in the row kernels."""
+import numpy as np
+import pytest
+
+from oracle import lfo
+from tests.helpers import rel_max_err, upload_oracle_mesh
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def lf():
+    import lehrfempp_b200 as lf
+    return lf
+
+
+@pytest.fixture(scope="module")
+def ctx(lf):
+    c = lf.Context(0)
+    yield c
+    c.close()
+
+
+def moved_corners(om, amount, seed=3):
+    """per-cell corners moved independently by `amount` x cell size (a kernel reading node positions is then visibly wrong)"""
+    ex = om.export()
+    cn, xy = ex["cell_nodes"], ex["node_coords"]
+    corners = xy[cn[:, :3]]
+    e1, e2 = corners[:, 1] - corners[:, 0], corners[:, 2] - corners[:, 0]
+    size = np.sqrt(np.abs(e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0]))
+    cc = np.zeros((len(cn), 4, 2))
+    cc[:, :3] = corners + amount * size[:, None, None] * (np.random.default_rng(seed).random(corners.shape) - 0.5)
+    return ex, cc
+
+
+CASES = [
+    ("laplace", lambda lf: lf.Coeff.const(1.0), lambda lf: lf.Coeff.const(0.0), lfo.coeff.const(1.0), lfo.coeff.const(0.0)),
+    ("reaction_diffusion", lambda lf: lf.Coeff.const(2.5), lambda lf: lf.Coeff.const(0.75), lfo.coeff.const(2.5), lfo.coeff.const(0.75)),
+    ("tensor", lambda lf: lf.Coeff.const2x2([[2.0, 0.5], [-0.25, 1.5]]), lambda lf: lf.Coeff.const(1.25),
+     lfo.coeff.const2x2([[2.0, 0.5], [-0.25, 1.5]]), lfo.coeff.const(1.25)),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("major", ["row", "col"])
+@pytest.mark.parametrize("degree", [2, 3])
+def test_rows_read_the_cells_own_corners(ctx, lf, degree, major, case):
+    _, ga, gg, oa, og = case
+    mj = lf.ROW_MAJOR if major == "row" else lf.COL_MAJOR
+    for om0 in (lfo.Mesh.tp_tria(13, 11, 0.25, -0.5, 1.75, 0.5), lfo.Mesh.tp_tria(4, 3).refine_regular().refine_regular()):
+        ex, cc = moved_corners(om0, 0.05)
+        om = lfo.Mesh.from_arrays(ex["node_coords"], ex["cell_nodes"], cell_coords=cc, cell_geo=np.ones(om0.n_cells, np.uint8),
+                                  edge_nodes=ex["edge_nodes"])
+        gm = ctx.mesh_upload(ex["node_coords"], ex["cell_nodes"], cc)
+        gm.build_topology(ex["edge_nodes"])
+        pat = gm.dofmap_lagrange(degree).symbolic(major=mj)
+        o = om.assemble_rd(degree, oa, og, csr=(mj == lf.ROW_MAJOR))
+        outer, inner = pat.download()
+        assert np.array_equal(outer, o[0]) and np.array_equal(inner, o[1])
+        plain = om0.assemble_rd(degree, oa, og, csr=(mj == lf.ROW_MAJOR))[2]
+        assert rel_max_err(plain, o[2]) > 1e-4  # the moved corners are visible in the matrix
+        vals = pat.assemble_reaction_diffusion(degree, ga(lf), gg(lf), algo=lf.ALGO_FAN).to_host()
+        assert rel_max_err(vals, o[2]) <= TOL
+        auto = pat.assemble_reaction_diffusion(degree, ga(lf), gg(lf)).to_host()
+        assert np.array_equal(auto, vals)  # AUTO takes the same kernels
+        gen = pat.assemble_reaction_diffusion(degree, ga(lf), gg(lf), algo=lf.ALGO_GATHER).to_host()
+        assert rel_max_err(vals, gen) <= 1e-13
+        # accumulate, and a row range
+        out = ctx.to_device(gen.copy())
+        acc = pat.assemble_reaction_diffusion(degree, ga(lf), gg(lf), algo=lf.ALGO_FAN, out=out, beta=1.0).to_host()
+        assert rel_max_err(acc, 2.0 * gen) <= 1e-13
+        n = outer.size - 1
+        part = pat.assemble_reaction_diffusion_range(degree, ga(lf), gg(lf), n // 4, n // 2, algo=lf.ALGO_FAN).to_host()
+        lo, hi = outer[n // 4], outer[n // 4 + n // 2]
+        assert np.abs(part[lo:hi] - gen[lo:hi]).max() <= 1e-13 * np.abs(gen).max()
+
+
+@pytest.mark.parametrize("degree", [2, 3])
+def test_refined_mesh_and_corners_one_ulp_off(ctx, lf, degree):
+    """RefineRegular of the restated reference: child corners come from the parent's Global() (refinement/mesh_hierarchy.cc,
+    tria_o1.cc:99-151).  In the oracle they turn out bitwise equal to the node positions (then the flatten step drops them); the
+    second half moves a third of the corners by one ulp -- the situation the round-1 review asked about -- and the row kernels
+    must follow the cells' own corners there too."""
+    om = lfo.Mesh.tp_tria(6, 5, 0.1, 0.2, 1.3, 0.9).refine_regular().refine_regular().refine_regular()
+    gm, ex = upload_oracle_mesh(ctx, om)
+    gm.build_topology(ex["edge_nodes"])
+    pat = gm.dofmap_lagrange(degree).symbolic(major=lf.ROW_MAJOR)
+    o = om.assemble_rd(degree, lfo.coeff.const(1.5), lfo.coeff.const(0.5), csr=True)
+    outer, inner = pat.download()
+    assert np.array_equal(outer, o[0]) and np.array_equal(inner, o[1])
+    vals = pat.assemble_reaction_diffusion(degree, lf.Coeff.const(1.5), lf.Coeff.const(0.5), algo=lf.ALGO_FAN).to_host()
+    assert rel_max_err(vals, o[2]) <= TOL
+    rng = np.random.default_rng(17)
+    cc = ex["cell_coords"].copy()
+    up = rng.random(cc.shape) < 1.0 / 3.0
+    cc[up] = np.nextafter(cc[up], np.where(rng.random(int(up.sum())) < 0.5, -np.inf, np.inf))
+    cc[:, 3] = 0.0
+    om1 = lfo.Mesh.from_arrays(ex["node_coords"], ex["cell_nodes"], cell_coords=cc, cell_geo=np.ones(om.n_cells, np.uint8),
+                               edge_nodes=ex["edge_nodes"])
+    gm1 = ctx.mesh_upload(ex["node_coords"], ex["cell_nodes"], cc)
+    gm1.build_topology(ex["edge_nodes"])
+    pat1 = gm1.dofmap_lagrange(degree).symbolic(major=lf.ROW_MAJOR)
+    o1 = om1.assemble_rd(degree, lfo.coeff.const(1.5), lfo.coeff.const(0.5), csr=True)
+    v1 = pat1.assemble_reaction_diffusion(degree, lf.Coeff.const(1.5), lf.Coeff.const(0.5), algo=lf.ALGO_FAN).to_host()
+    assert rel_max_err(v1, o1[2]) <= TOL
+
+
+@pytest.mark.parametrize("degree", [2, 3])
+def test_large_mesh_with_cell_corners(ctx, lf, degree):
+    """3.2e5 triangles (above one wave of CTAs: the prefetch branches run) against the generic kernel, plus symmetry"""
+    import scipy.sparse as sp
+    om0 = lfo.Mesh.tp_tria(400, 400)
+    ex, cc = moved_corners(om0, 0.02, seed=9)
+    gm = ctx.mesh_upload(ex["node_coords"], ex["cell_nodes"], cc)
+    gm.build_topology(ex["edge_nodes"])
+    pat = gm.dofmap_lagrange(degree).symbolic(major=lf.ROW_MAJOR)
+    outer, inner = pat.download()
+    N = outer.size - 1
+    for ga, gg in ((lf.Coeff.const(1.0), lf.Coeff.const(0.0)), (lf.Coeff.const2x2([[2.0, 0.5], [0.5, 1.5]]), lf.Coeff.const(1.0))):
+        v = pat.assemble_reaction_diffusion(degree, ga, gg, algo=lf.ALGO_FAN).to_host()
+        gen = pat.assemble_reaction_diffusion(degree, ga, gg, algo=lf.ALGO_GATHER).to_host()
+        assert rel_max_err(v, gen) <= 1e-13
+        A = sp.csr_matrix((v, inner, outer), shape=(N, N))
+        assert abs(A - A.T).max() <= 1e-13 * np.abs(v).max()

@@ -25,6 +25,7 @@ def emul():
     L = C.CDLL(os.path.join(HERE, "cpp", "libp3emul.so"))
     L.p3_rows_emulate.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_int, C.c_double] + [C.c_void_p] * 8
+    L.p3_rows_emulate_cell_coords.argtypes = [C.c_void_p]
     return L
 
 
@@ -126,3 +127,56 @@ def test_rows_match_oracle(emul, coeff, csr, general):
     emul.p3_rows_emulate_general(0)
     if general:
         assert seen >= {3, 4, 5, 6, 7, 8}
+
+
+@pytest.mark.parametrize("csr", [True, False], ids=["csr", "csc"])
+@pytest.mark.parametrize("coeff", COEFFS, ids=[c[0] for c in COEFFS])
+def test_rows_with_cell_corners_match_oracle(emul, coeff, csr):
+    """Meshes whose cells carry their own corner coordinates (the reference's Geometry objects; after RefineRegular they differ
+    from the node positions in the last bits): vertex_plan / edge_plan hand out (cell, corner) words, vertex_row_cv / edge_row2
+    compute every cell from ITS corners.  The corners are moved by up to 5 % of the cell size here so that a kernel reading node
+    positions (or the wrong cell's corners) would be off by orders of magnitude more than the bar."""
+    _, a_scalar, a_tensor, gamma = coeff
+    K = reference_tensors()
+    rng = np.random.default_rng(3)
+    for name, om0 in meshes():
+        ex = om0.export()
+        cn = np.ascontiguousarray(ex["cell_nodes"], dtype=np.uint32)
+        xy = np.ascontiguousarray(ex["node_coords"], dtype=np.float64)
+        corners = xy[cn[:, :3]]                                            # [n_cells][3][2]
+        e1, e2 = corners[:, 1] - corners[:, 0], corners[:, 2] - corners[:, 0]
+        size = np.sqrt(np.abs(e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0]))
+        cc = np.zeros((len(cn), 4, 2))
+        cc[:, :3] = corners + 0.05 * size[:, None, None] * (rng.random(corners.shape) - 0.5)
+        om = lfo.Mesh.from_arrays(xy, cn, cell_coords=cc, cell_geo=np.ones(len(cn), np.uint8), edge_nodes=ex["edge_nodes"])
+        dofs, nl = om.cell_dofs(3)
+        oalpha = lfo.coeff.const(a_scalar) if a_tensor is None else lfo.coeff.const2x2(a_tensor)
+        outer, inner, vals, _, _ = om.assemble_rd(3, oalpha, lfo.coeff.const(gamma), csr=csr)
+        plain = om0.assemble_rd(3, oalpha, lfo.coeff.const(gamma), csr=csr)[2]
+        assert np.abs(plain - vals).max() > 1e-4 * np.abs(vals).max()      # the perturbation is visible
+        n_dofs = outer.size - 1
+        if a_tensor is None:
+            alpha4 = np.array([a_scalar, 0.0, 0.0, a_scalar])
+        else:
+            A = np.array(a_tensor)
+            alpha4 = (A.T if csr else A).ravel().copy()
+        d32 = np.ascontiguousarray(dofs, dtype=np.int32)
+        out = np.zeros(vals.size)
+        regular = np.zeros(n_dofs, np.uint8)
+        counts = np.zeros(3, np.int64)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        emul.p3_rows_emulate_general(0)
+        emul.p3_rows_emulate_cell_coords(p(cc))
+        try:
+            rc = emul.p3_rows_emulate(om.n_nodes, om.n_cells, p(cn), p(xy), d32.shape[1], p(d32), n_dofs, p(outer), p(inner), p(alpha4),
+                                      int(a_tensor is not None), gamma, p(K["k00"]), p(K["k01"]), p(K["k10"]), p(K["k11"]), p(K["km"]),
+                                      p(out), p(regular), p(counts))
+        finally:
+            emul.p3_rows_emulate_cell_coords(None)
+        assert rc == 0
+        bd = om.boundary_edges().astype(bool)
+        assert counts[2] == om.n_cells and counts[1] == 2 * int((~bd).sum()), name
+        row_of = np.repeat(np.arange(n_dofs), np.diff(outer))
+        sel = regular[row_of].astype(bool)
+        err = np.abs(out[sel] - vals[sel]).max() / np.abs(vals).max()
+        assert err <= TOL, (name, err)
