@@ -772,7 +772,8 @@ int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
   auto cleanup = [&]() { cudaFree(flag); cudaFree(iota); cudaFree(d_num); cudaFree(tmp); };
   auto drop_plan = [&]() {
     cudaFree(p->p2v_nbr); cudaFree(p->p2v_slots); cudaFree(p->p2e_nbr); cudaFree(p->p2e_slots); cudaFree(p->p2_irregular);
-    cudaFree(p->p2g_nbr); cudaFree(p->p2g_slots); cudaFree(p->p2v_cidx);
+    cudaFree(p->p2g_nbr); cudaFree(p->p2g_slots); cudaFree(p->p2v_cidx); cudaFree(p->p2e_newid); cudaFree(p->p2e_xy);
+    p->p2e_newid = nullptr; p->p2e_xy = nullptr;
     p->p2v_cidx = nullptr; p->p2_compact_v = false; p->p2_compact_e = false;
     p->p2v_nbr = nullptr; p->p2v_slots = nullptr; p->p2e_nbr = nullptr; p->p2e_slots = nullptr; p->p2_irregular = nullptr;
     p->p2g_nbr = nullptr; p->p2g_slots = nullptr; p->p2_general = false;
@@ -866,12 +867,28 @@ int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
     P2_CHECK(cudaMemcpyAsync(p->p2_irregular_host.data(), iota, sizeof(int32_t) * n_irr, cudaMemcpyDeviceToHost, st));
     P2_CHECK(cudaStreamSynchronize(st));
   }
+  // the edge rows' own copy of the node positions, in the order the rows use them (plan_dict.cu: edge_node_order; LFGPU_EDGE_ORDER=0
+  // keeps the mesh's array): on the builder's numbering the edge-row kernel is 30 % (P2) / 11 % (P3) faster with it
+  static const bool order_env = [] { const char* e = std::getenv("LFGPU_EDGE_ORDER"); return e == nullptr || e[0] != '0'; }();
+  if (order_env && cc == 0 && n_irr * 2 <= p->n_outer) {
+    if (edge_node_order(ctx, nn, ne, p->p2e_nbr, &p->p2e_newid) != LFGPU_OK) {
+      cleanup();
+      drop_plan();
+      return LFGPU_ERR_CUDA;
+    }
+    if (p->p2e_newid != nullptr) {
+      P2_CHECK(cudaMalloc(&p->p2e_xy, sizeof(double) * (2 * static_cast<size_t>(nn) + 32)));
+      p->p2e_xy_version = 0;
+      p->p2e_xy_mesh = nullptr;
+    }
+  }
   // compact plan (see k_p2_vertex_compact): tried once the plan stands; any failure to fit leaves the arrays as they are
-  // LFGPU_P2_COMPACT: 1 = both row classes, v = vertex rows only, e = edge rows only; default off -- measured at config C3 (B200,
+  // LFGPU_P2_COMPACT: 1 = both row classes, v = vertex rows only, e = edge rows only, 0 = off -- measured at config C3 (B200,
   // profiles/r02_p2_rows_compact*_hints*.json): DRAM traffic 4.25 -> 3.87 GB (1.23 -> 1.12 x algorithmic), vertex rows 0.263 -> 0.257 ms,
   // edge rows 0.524 -> 0.549 ms: the kernels wait on dependent loads (plan -> coordinates), not on DRAM bandwidth, and the table
   // lookup adds one more
-  static const char compact_env = [] { const char* e = std::getenv("LFGPU_P2_COMPACT"); return e == nullptr ? '0' : e[0]; }();
+  // -> default 'v': the vertex rows gain 2 % (0.2626 -> 0.2571 / 0.2622 -> 0.2565 ms in two runs) and their plan shrinks from 36 to 14 B
+  static const char compact_env = [] { const char* e = std::getenv("LFGPU_P2_COMPACT"); return e == nullptr ? 'v' : e[0]; }();
   const bool compact_v = compact_env == '1' || compact_env == 'v', compact_e = compact_env == '1' || compact_env == 'e';
   if ((compact_v || compact_e) && cc == 0 && n_irr * 2 <= p->n_outer) {
     int* d_over = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 384);
@@ -1043,8 +1060,19 @@ int p2_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* 
   } else if (e_end > e_first) {
     const unsigned ge = static_cast<unsigned>(cdiv(e_end - e_first, threads));
     const bool ce = p->p2_compact_e;
+    const double* exy = mesh->node_coords;
+    if (p->p2e_newid != nullptr) {  // the plan's node numbers are positions in the rows' own coordinate copy: bring it up to date
+      auto* pm = const_cast<lfgpu_pattern*>(p);
+      if (pm->p2e_xy_version != mesh->coords_version || pm->p2e_xy_mesh != mesh) {
+        const int rc = permute_node_coords(ctx, nn, p->p2e_newid, mesh->node_coords, pm->p2e_xy);
+        if (rc != LFGPU_OK) return rc;
+        pm->p2e_xy_version = mesh->coords_version;
+        pm->p2e_xy_mesh = mesh;
+      }
+      exy = p->p2e_xy;
+    }
 #define P2_LAUNCH_E(MODE, BULK, COMPACT, HINT)                                                                                         \
-  k_p2_edge_rows<MODE, BULK, COMPACT, HINT><<<ge, threads, smem_e, ctx->stream>>>(ne, nn, p->p2e_nbr, p->p2e_slots, mesh->node_coords, p->outer, \
+  k_p2_edge_rows<MODE, BULK, COMPACT, HINT><<<ge, threads, smem_e, ctx->stream>>>(ne, nn, p->p2e_nbr, p->p2e_slots, exy, p->outer, \
                                                                                 ipf_e, ipc_e, P, d_values, e_first, e_end, beta)
 #define P2_PICK_E(MODE)                                  \
   do {                                                   \

@@ -130,8 +130,10 @@ int host_impl(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const lfgpu_pattern* pattern, in
   if (!fan && !whole) LFGPU_FAIL(ctx, LFGPU_ERR_UNSUPPORTED, "contiguous row ranges are a fan-kernel feature");
   if (!fan || (whole && (n_blocks < 2 || (h_node_coords == nullptr && h_values == nullptr)))) {
     // plain sequence on the context stream
-    if (h_node_coords != nullptr)
+    if (h_node_coords != nullptr) {
       LFGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(mesh->node_coords, h_node_coords, sizeof(double) * 2 * mesh->n_nodes, cudaMemcpyHostToDevice, ctx->stream));
+      mesh->coords_version++;
+    }
     rc = assemble_rd_impl(ctx, mesh, p, degree, qr_tria, qr_quad, alpha, gamma, nullptr, 0.0, d_values, algo, nullptr, 0, -1, nullptr);
     if (rc != LFGPU_OK) return rc;
     if (h_values != nullptr)
@@ -154,6 +156,7 @@ int host_impl(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const lfgpu_pattern* pattern, in
       LFGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(mesh->node_coords + 2 * uploaded, h_node_coords + 2 * uploaded,
                                             sizeof(double) * 2 * (p->hp_need[b] - uploaded), cudaMemcpyHostToDevice, ctx->s_h2d));
       uploaded = p->hp_need[b];
+      mesh->coords_version++;
       LFGPU_CUDA_CHECK(ctx, cudaEventRecord(ctx->pipe_events[b], ctx->s_h2d));
       LFGPU_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipe_events[b], 0));
     }
@@ -171,6 +174,7 @@ int host_impl(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const lfgpu_pattern* pattern, in
   if (rc == LFGPU_OK && whole && h_node_coords != nullptr && uploaded < mesh->n_nodes) {  // nodes no row refers to
     LFGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(mesh->node_coords + 2 * uploaded, h_node_coords + 2 * uploaded,
                                           sizeof(double) * 2 * (mesh->n_nodes - uploaded), cudaMemcpyHostToDevice, ctx->s_h2d));
+    mesh->coords_version++;
   }
   cudaError_t e1 = cudaStreamSynchronize(ctx->s_h2d);
   cudaError_t e2 = cudaStreamSynchronize(ctx->stream);

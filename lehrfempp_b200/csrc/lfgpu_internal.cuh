@@ -45,6 +45,7 @@ struct lfgpu_mesh {
   double* node_coords = nullptr;    // [n_nodes][2]
   uint32_t* cell_nodes = nullptr;   // [n_cells][4], NIL padded
   double* cell_coords = nullptr;    // [n_cells][4][2] or nullptr (corners == node positions)
+  uint64_t coords_version = 1;      // bumped by every call that rewrites node_coords (the row-kernel plans keep reordered copies)
   // topology (optional, built by lfgpu_mesh_build_topology / tp generators)
   bool has_topology = false;
   uint32_t tp_nx = 0, tp_ny = 0;    // > 0: mesh of the triangle builder, whose explicit edge list is generated on demand
@@ -148,6 +149,12 @@ struct lfgpu_pattern {
   // triples, p2v_cidx = table index per row (0xFFFF: not planned); p2e_nbr = uint32 [3][n_edges], p2e_slots = uint4 table
   bool p2_compact_v = false, p2_compact_e = false;
   uint16_t* p2v_cidx = nullptr;
+  // edge rows: the kernels' own copy of the node positions in the order the edge plan uses them (plan_dict.cu: edge_node_order);
+  // p2e_nbr then holds positions in that copy.  Refreshed when the mesh's coords_version moves.
+  uint32_t* p2e_newid = nullptr;     // [p2_nn]
+  double* p2e_xy = nullptr;          // [p2_nn][2]
+  uint64_t p2e_xy_version = 0;
+  const void* p2e_xy_mesh = nullptr;
   bool p2_cc = false;                // plan built for a mesh with per-cell corners: p2v_nbr / p2e_nbr hold (cell, corner) words
   bool p2_general = false;           // vertex rows planned for closed rings of 3..8 cells (rows_p2_core.h) instead of exactly 6
   int32_t* p2g_nbr = nullptr;        // [8][p2_nn]
@@ -163,6 +170,10 @@ struct lfgpu_pattern {
   int32_t* p3e_nbr = nullptr;        // [4][n_edge_rows] P, Q, o_1, o_2
   uint32_t* p3e_slots = nullptr;     // [2][n_edge_rows] 16 slot nibbles per row
   void* p3c_slots = nullptr;         // uint2 [n_cells] slots of the ten list positions in the cell's own row, one nibble each
+  uint32_t* p3e_newid = nullptr;     // as p2e_newid / p2e_xy for the P3 edge-dof rows
+  double* p3e_xy = nullptr;
+  uint64_t p3e_xy_version = 0;
+  const void* p3e_xy_mesh = nullptr;
   bool p3_cc = false;                // plan built for a mesh with per-cell corners: p3v_nbr / p3e_nbr hold (cell, corner) words
   bool p3_general = false;           // vertex rows planned for closed rings of 3..8 cells instead of exactly 6
   int32_t* p3g_nbr = nullptr;        // [8][p3_nn]
@@ -265,6 +276,8 @@ int p1h_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, c
 // P1 load vector with a constant source on the vertex rings (assemble_p1.cu)
 int p1_load_fan(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* d, double c, double beta, double* d_vec, int* handled);
 // P2 row kernels (assemble_p2.cu): k00 .. km = reference tensors of FeLagrangeO2Tria, [6 * 6] row-major each
+int edge_node_order(lfgpu_ctx* ctx, int64_t nn, int64_t ne, int32_t* enb, uint32_t** new_id_out);
+int permute_node_coords(lfgpu_ctx* ctx, int64_t nn, const uint32_t* new_id, const double* xy, double* xy_perm);
 int build_row_dict(lfgpu_ctx* ctx, int n_words, int64_t n, const uint32_t* words, uint16_t* idx, void** dict_out, int* n_dict);
 int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p);
 int p2_rows_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, const double alpha[4], int tensor, double gamma,

@@ -378,6 +378,7 @@ int lfgpu_mesh_update_node_coords(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const double
   if (ctx == nullptr || mesh == nullptr || node_coords == nullptr) return LFGPU_ERR_INVALID;
   if (mesh->cell_coords != nullptr) LFGPU_FAIL(ctx, LFGPU_ERR_UNSUPPORTED, "mesh carries explicit cell corner coordinates");
   LFGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(mesh->node_coords, node_coords, sizeof(double) * 2 * mesh->n_nodes, cudaMemcpyHostToDevice, ctx->stream));
+  mesh->coords_version++;
   // the new positions are checked like those of lfgpu_mesh_upload (the reference asserts on a degenerate cell, tria_o1.cc:10-48;
   // the kernels' 1 / det has no slow path), asynchronously: the flag is read by the next lfgpu_ctx_synchronize
   int* d_flag = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 1024);

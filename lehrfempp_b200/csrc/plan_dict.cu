@@ -124,6 +124,93 @@ int build_dict_w(lfgpu_ctx* ctx, int64_t n, const uint32_t* words, uint16_t* idx
 
 }  // namespace
 
+// ---- node order of an edge plan ---------------------------------------------------------------------------------------------
+// The edge-row kernels gather four node positions per row.  The reference's mesh builders number nodes row by row but edges (and
+// cells) column by column, so the 32 consecutive edge rows of a warp read from 32 different 128-byte lines per gather; with the
+// nodes renumbered in the order the edge rows use them the same kernels ran 30 % (P2) / 11 % (P3) faster on B200
+// (profiles/r02_locality_p2.json).  The matrix keeps the reference's numbering -- only the kernels' private copy of the
+// coordinates is stored in "first use" order: rank of a node = (first edge row that has it as P) before (first row that has it as
+// Q) before (first row that has it as o_1 / o_2).
+namespace {
+__global__ void k_first_use(int64_t ne, const int32_t* __restrict__ enb, uint32_t* __restrict__ key) {
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  const int32_t p = enb[e];
+  if (p < 0) return;  // not a planned row
+  atomicMin(key + p, static_cast<uint32_t>(e));
+  atomicMin(key + enb[ne + e], static_cast<uint32_t>(ne + e));
+  atomicMin(key + enb[2 * ne + e], static_cast<uint32_t>(2 * ne + e));
+  atomicMin(key + enb[3 * ne + e], static_cast<uint32_t>(2 * ne + e));
+}
+__global__ void k_rank_of(int64_t n, const int32_t* __restrict__ order, uint32_t* __restrict__ new_id) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) new_id[order[i]] = static_cast<uint32_t>(i);
+}
+__global__ void k_remap_ids(int64_t ne, int32_t* __restrict__ enb, const uint32_t* __restrict__ new_id) {
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= ne || enb[e] < 0) return;
+  for (int k = 0; k < 4; ++k) enb[k * ne + e] = static_cast<int32_t>(new_id[enb[k * ne + e]]);
+}
+__global__ void k_permute_xy(int64_t n, const uint32_t* __restrict__ new_id, const double2* __restrict__ xy, double2* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[new_id[i]] = xy[i];
+}
+}  // namespace
+
+// enb: device [4][ne] node numbers of an edge plan (P, Q, o_1, o_2; P < 0: row not planned), rewritten to the new numbers.
+// *new_id_out: device [nn] (cudaMalloc, the caller frees): position of every node in the kernels' coordinate copy.
+int edge_node_order(lfgpu_ctx* ctx, int64_t nn, int64_t ne, int32_t* enb, uint32_t** new_id_out) {
+  *new_id_out = nullptr;
+  if (nn <= 0 || ne <= 0 || ne >= (1LL << 30) || nn >= (1LL << 31)) return LFGPU_OK;
+  cudaStream_t st = ctx->stream;
+  uint32_t *key = nullptr, *key2 = nullptr, *new_id = nullptr;
+  int32_t *ids = nullptr, *ids2 = nullptr;
+  void* tmp = nullptr;
+  auto cleanup = [&]() { cudaFree(key); cudaFree(key2); cudaFree(ids); cudaFree(ids2); cudaFree(tmp); };
+#define ORD_CHECK(expr)                                                           \
+  do {                                                                            \
+    cudaError_t _e = (expr);                                                      \
+    if (_e != cudaSuccess) {                                                      \
+      set_last_error(ctx, std::string(#expr) + ": " + cudaGetErrorString(_e));    \
+      cleanup();                                                                  \
+      cudaFree(new_id);                                                           \
+      return LFGPU_ERR_CUDA;                                                      \
+    }                                                                             \
+  } while (0)
+  ORD_CHECK(cudaMalloc(&key, sizeof(uint32_t) * nn));
+  ORD_CHECK(cudaMalloc(&key2, sizeof(uint32_t) * nn));
+  ORD_CHECK(cudaMalloc(&ids, sizeof(int32_t) * nn));
+  ORD_CHECK(cudaMalloc(&ids2, sizeof(int32_t) * nn));
+  ORD_CHECK(cudaMalloc(&new_id, sizeof(uint32_t) * nn));
+  ORD_CHECK(cudaMemsetAsync(key, 0xFF, sizeof(uint32_t) * nn, st));  // nodes no planned row uses come last, in their old order
+  k_first_use<<<static_cast<unsigned>(cdiv(ne, 256)), 256, 0, st>>>(ne, enb, key);
+  ctx->launches++;
+  k_iota<<<static_cast<unsigned>(cdiv(nn, 256)), 256, 0, st>>>(nn, ids);
+  ctx->launches++;
+  size_t tb = 0;
+  ORD_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tb, key, key2, ids, ids2, nn, 0, 32, st));
+  ORD_CHECK(cudaMalloc(&tmp, std::max<size_t>(tb, 16)));
+  ORD_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tb, key, key2, ids, ids2, nn, 0, 32, st));  // stable
+  k_rank_of<<<static_cast<unsigned>(cdiv(nn, 256)), 256, 0, st>>>(nn, ids2, new_id);
+  ctx->launches++;
+  k_remap_ids<<<static_cast<unsigned>(cdiv(ne, 256)), 256, 0, st>>>(ne, enb, new_id);
+  ctx->launches++;
+  ORD_CHECK(cudaGetLastError());
+  ORD_CHECK(cudaStreamSynchronize(st));
+#undef ORD_CHECK
+  cleanup();
+  *new_id_out = new_id;
+  return LFGPU_OK;
+}
+
+// xy_perm[new_id[i]] = xy[i] on the context stream
+int permute_node_coords(lfgpu_ctx* ctx, int64_t nn, const uint32_t* new_id, const double* xy, double* xy_perm) {
+  k_permute_xy<<<static_cast<unsigned>(cdiv(nn, 256)), 256, 0, ctx->stream>>>(nn, new_id, reinterpret_cast<const double2*>(xy),
+                                                                             reinterpret_cast<double2*>(xy_perm));
+  LFGPU_LAUNCH_CHECK(ctx);
+  return LFGPU_OK;
+}
+
 // words: device [n_words][n] (slot-major), n_words in 1..4.  idx: device [n], receives the tuple number of every row; *dict_out:
 // device uint4 [*n_dict] (cudaMalloc, the caller frees), unused components zero.  *n_dict = -1: too many distinct tuples, idx untouched.
 int build_row_dict(lfgpu_ctx* ctx, int n_words, int64_t n, const uint32_t* words, uint16_t* idx, void** dict_out, int* n_dict) {

@@ -251,6 +251,10 @@ void lfgpu_pattern_destroy(lfgpu_pattern* p) {
   cudaFree(p->p1h_irregular);
   cudaFree(p->p2v_nbr);
   cudaFree(p->p2v_cidx);
+  cudaFree(p->p2e_newid);
+  cudaFree(p->p2e_xy);
+  cudaFree(p->p3e_newid);
+  cudaFree(p->p3e_xy);
   cudaFree(p->p2v_slots);
   cudaFree(p->p2e_nbr);
   cudaFree(p->p2e_slots);

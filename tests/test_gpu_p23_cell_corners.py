@@ -127,3 +127,31 @@ def test_large_mesh_with_cell_corners(ctx, lf, degree):
         assert rel_max_err(v, gen) <= 1e-13
         A = sp.csr_matrix((v, inner, outer), shape=(N, N))
         assert abs(A - A.T).max() <= 1e-13 * np.abs(v).max()
+
+
+@pytest.mark.parametrize("degree", [2, 3])
+def test_row_kernels_follow_coordinate_updates(ctx, lf, degree):
+    """The edge-row kernels gather from their own copy of the node positions, stored in the order the rows use them
+    (plan_dict.cu: edge_node_order): it must be refreshed when the mesh's coordinates change -- through
+    lfgpu_mesh_update_node_coords and through the host-buffer call."""
+    om = lfo.Mesh.tp_tria(31, 17, 0.0, 0.0, 2.0, 1.0)
+    ex = om.export()
+    gm = ctx.mesh_tp_tria(31, 17, 0.0, 0.0, 2.0, 1.0)
+    pat = gm.dofmap_lagrange(degree).symbolic(major=lf.ROW_MAJOR)
+    ga, gg, oa, og = lf.Coeff.const(1.5), lf.Coeff.const(0.5), lfo.coeff.const(1.5), lfo.coeff.const(0.5)
+    v0 = pat.assemble_reaction_diffusion(degree, ga, gg, algo=lf.ALGO_FAN).to_host()
+    assert rel_max_err(v0, om.assemble_rd(degree, oa, og, csr=True)[2]) <= TOL
+    xy = ex["node_coords"].copy()
+    for step in range(3):
+        xy = xy + 0.2 / 31 * np.stack([np.sin(3 * xy[:, 1] + step), np.cos(2 * xy[:, 0] - step)], axis=1) * 0.3
+        om_s = lfo.Mesh.from_arrays(xy, ex["cell_nodes"], edge_nodes=ex["edge_nodes"])
+        o = om_s.assemble_rd(degree, oa, og, csr=True)[2]
+        if step < 2:
+            gm.update_node_coords(xy)
+            v = pat.assemble_reaction_diffusion(degree, ga, gg, algo=lf.ALGO_FAN).to_host()
+        else:
+            h_vals = np.empty(pat.nnz)
+            pat.assemble_reaction_diffusion_host(degree, ga, gg, np.ascontiguousarray(xy.ravel()), h_vals, algo=lf.ALGO_FAN)
+            v = h_vals
+        assert rel_max_err(v, o) <= TOL, step
+        assert rel_max_err(v, v0) > 1e-6  # the matrix did change

@@ -10,7 +10,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 VARIANTS = [
-    {},  # defaults: full plan, bulk copy-out, no L2 hints
+    {},  # defaults: compact vertex plan, full edge plan, bulk copy-out, no L2 hints
+    {"LFGPU_P2_COMPACT": "0"},
     {"LFGPU_P2_COMPACT": "1", "LFGPU_L2_HINTS": "1"},
     {"LFGPU_P2_COMPACT": "1", "LFGPU_EDGE_PFC": "50"},
     {"LFGPU_P2_COMPACT": "v"},
