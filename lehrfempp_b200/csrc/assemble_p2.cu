@@ -887,8 +887,10 @@ int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
   // profiles/r02_p2_rows_compact*_hints*.json): DRAM traffic 4.25 -> 3.87 GB (1.23 -> 1.12 x algorithmic), vertex rows 0.263 -> 0.257 ms,
   // edge rows 0.524 -> 0.549 ms: the kernels wait on dependent loads (plan -> coordinates), not on DRAM bandwidth, and the table
   // lookup adds one more
-  // -> default 'v': the vertex rows gain 2 % (0.2626 -> 0.2571 / 0.2622 -> 0.2565 ms in two runs) and their plan shrinks from 36 to 14 B
-  static const char compact_env = [] { const char* e = std::getenv("LFGPU_P2_COMPACT"); return e == nullptr ? 'v' : e[0]; }();
+  // The vertex rows gain 2 % (0.2626 -> 0.2571 / 0.2622 -> 0.2565 ms in two runs) and their plan shrinks from 36 to 14 B.  With the edge
+  // rows on their own coordinate copy (edge_node_order above) the compact edge plan costs nothing any more (0.4043 vs 0.4046 ms) and
+  // takes 8 B per row off the traffic -> default: both
+  static const char compact_env = [] { const char* e = std::getenv("LFGPU_P2_COMPACT"); return e == nullptr ? '1' : e[0]; }();
   const bool compact_v = compact_env == '1' || compact_env == 'v', compact_e = compact_env == '1' || compact_env == 'e';
   if ((compact_v || compact_e) && cc == 0 && n_irr * 2 <= p->n_outer) {
     int* d_over = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 384);

@@ -142,6 +142,24 @@ __global__ void k_first_use(int64_t ne, const int32_t* __restrict__ enb, uint32_
   atomicMin(key + enb[2 * ne + e], static_cast<uint32_t>(2 * ne + e));
   atomicMin(key + enb[3 * ne + e], static_cast<uint32_t>(2 * ne + e));
 }
+// locality of the gathers of consecutive rows: how often a row's node k lies in another 128-byte line (8 positions) than the
+// previous planned row's node k.  map == nullptr: the numbers as they are.
+__global__ void k_line_changes(int64_t ne, const int32_t* __restrict__ enb, const uint32_t* __restrict__ map, unsigned long long* __restrict__ count) {
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  int c = 0;
+  if (e > 0 && e < ne && enb[e] >= 0 && enb[e - 1] >= 0) {
+    for (int k = 0; k < 4; ++k) {
+      uint32_t a = static_cast<uint32_t>(enb[k * ne + e]), b = static_cast<uint32_t>(enb[k * ne + e - 1]);
+      if (map != nullptr) {
+        a = map[a];
+        b = map[b];
+      }
+      c += (a >> 3) != (b >> 3);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffU, c, o);
+  if ((threadIdx.x & 31) == 0 && c > 0) atomicAdd(count, static_cast<unsigned long long>(c));
+}
 __global__ void k_rank_of(int64_t n, const int32_t* __restrict__ order, uint32_t* __restrict__ new_id) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) new_id[order[i]] = static_cast<uint32_t>(i);
@@ -161,7 +179,7 @@ __global__ void k_permute_xy(int64_t n, const uint32_t* __restrict__ new_id, con
 // *new_id_out: device [nn] (cudaMalloc, the caller frees): position of every node in the kernels' coordinate copy.
 int edge_node_order(lfgpu_ctx* ctx, int64_t nn, int64_t ne, int32_t* enb, uint32_t** new_id_out) {
   *new_id_out = nullptr;
-  if (nn <= 0 || ne <= 0 || ne >= (1LL << 30) || nn >= (1LL << 31)) return LFGPU_OK;
+  if (nn < 8 || ne <= 0 || ne >= (1LL << 30) || nn >= (1LL << 31)) return LFGPU_OK;
   cudaStream_t st = ctx->stream;
   uint32_t *key = nullptr, *key2 = nullptr, *new_id = nullptr;
   int32_t *ids = nullptr, *ids2 = nullptr;
@@ -193,6 +211,23 @@ int edge_node_order(lfgpu_ctx* ctx, int64_t nn, int64_t ne, int32_t* enb, uint32
   ORD_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tb, key, key2, ids, ids2, nn, 0, 32, st));  // stable
   k_rank_of<<<static_cast<unsigned>(cdiv(nn, 256)), 256, 0, st>>>(nn, ids2, new_id);
   ctx->launches++;
+  // adopted only where it pays: at least a quarter fewer line changes between consecutive rows than the mesh's own numbering has
+  // (builder meshes: 4.0 -> 0.6 per row; MeshHierarchy-refined and Morton-ordered meshes are as local as they get: measured 1 % either
+  // way on config C4's mesh, 4 % slower on the Delaunay-numbered workload u2 -- those keep the mesh's array, and the memory)
+  unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(key);  // key is sorted out: reuse its first 16 bytes
+  unsigned long long h_cnt[2] = {0ULL, 0ULL};
+  ORD_CHECK(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), st));
+  k_line_changes<<<static_cast<unsigned>(cdiv(ne, 256)), 256, 0, st>>>(ne, enb, nullptr, d_cnt);
+  k_line_changes<<<static_cast<unsigned>(cdiv(ne, 256)), 256, 0, st>>>(ne, enb, new_id, d_cnt + 1);
+  ctx->launches += 2;
+  ORD_CHECK(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+  ORD_CHECK(cudaStreamSynchronize(st));
+  static const bool force = [] { const char* e = std::getenv("LFGPU_EDGE_ORDER"); return e != nullptr && e[0] == '2'; }();
+  if (!force && 4 * h_cnt[1] > 3 * h_cnt[0]) {
+    cleanup();
+    cudaFree(new_id);
+    return LFGPU_OK;  // *new_id_out stays null: the plan keeps the mesh's numbers
+  }
   k_remap_ids<<<static_cast<unsigned>(cdiv(ne, 256)), 256, 0, st>>>(ne, enb, new_id);
   ctx->launches++;
   ORD_CHECK(cudaGetLastError());

@@ -10,14 +10,13 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 VARIANTS = [
-    {},  # defaults: compact vertex plan, full edge plan, bulk copy-out, no L2 hints
+    {},  # defaults: compact plans, edge rows on their own coordinate copy, bulk copy-out, no L2 hints
+    {"LFGPU_EDGE_ORDER": "0", "LFGPU_P2_COMPACT": "0"},
     {"LFGPU_P2_COMPACT": "0"},
     {"LFGPU_P2_COMPACT": "1", "LFGPU_L2_HINTS": "1"},
-    {"LFGPU_P2_COMPACT": "1", "LFGPU_EDGE_PFC": "50"},
-    {"LFGPU_P2_COMPACT": "v"},
-    {"LFGPU_L2_HINTS": "1"},
+    {"LFGPU_P2_COMPACT": "v", "LFGPU_EDGE_PFC": "50", "LFGPU_EDGE_ORDER": "2"},  # 2: the coordinate copy on every mesh
     {"LFGPU_P2_BULK": "0"},
-    {"LFGPU_P2_BULK": "0", "LFGPU_P2_COMPACT": "e"},
+    {"LFGPU_P2_BULK": "0", "LFGPU_P2_COMPACT": "e", "LFGPU_EDGE_ORDER": "0"},
 ]
 
 

@@ -1,5 +1,5 @@
 """Times the numeric pass of degree p on a TP-triangle mesh with the row kernels (ALGO_FAN) and the item kernel (ALGO_GATHER):
-CUDA events on the ctx stream, warm-up 3, 10 steps each.  usage: rows_probe.py <degree> <n> [rows|items]
+CUDA events on the ctx stream, warm-up 3, 10 steps each.  usage: rows_probe.py <degree> <n> [rows|items|''] [refinement levels]
 Prints one JSON line (kept under profiles/)."""
 import json
 import os
@@ -13,11 +13,14 @@ import lehrfempp_b200 as lf  # noqa: E402
 degree = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1448
 only = sys.argv[3] if len(sys.argv) > 3 else ""
+levels = int(sys.argv[4]) if len(sys.argv) > 4 else 0   # RefineRegular steps on top of the n x n builder mesh (config C4's numbering)
 ctx = lf.Context(0)
 mesh = ctx.mesh_tp_tria(n, n)
+for _ in range(levels):
+    mesh = mesh.refine_regular()
 pat = mesh.dofmap_lagrange(degree).symbolic(major=lf.ROW_MAJOR)
 vals = ctx.empty(pat.nnz)
-out = {"degree": degree, "cells": mesh.n_cells, "nnz": pat.nnz}
+out = {"degree": degree, "cells": mesh.n_cells, "nnz": pat.nnz, "refined": levels}
 alpha, gamma = lf.Coeff.const(1.0), lf.Coeff.const(1.0 if degree == 3 else 0.0)  # config C4: stiffness + mass
 nldof = {1: 3, 2: 6, 3: 10}[degree]
 res = {}
