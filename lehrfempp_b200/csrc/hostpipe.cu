@@ -138,8 +138,9 @@ int host_impl(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const lfgpu_pattern* pattern, in
     if (rc != LFGPU_OK) return rc;
     if (h_values != nullptr)
       LFGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(h_values, d_values, sizeof(double) * p->nnz, cudaMemcpyDeviceToHost, ctx->stream));
-    LFGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    return LFGPU_OK;
+    // positions that came from the caller are checked like those of lfgpu_mesh_upload (degenerate cell -> LFGPU_ERR_DEGENERATE)
+    if (h_node_coords != nullptr && (rc = queue_geometry_check(ctx, mesh)) != LFGPU_OK) return rc;
+    return lfgpu_ctx_synchronize(ctx);
   }
   // pipelined: H2D stream -> compute stream -> D2H stream, one event per block and hop
   const int nb = n_blocks;
@@ -176,14 +177,18 @@ int host_impl(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const lfgpu_pattern* pattern, in
                                           sizeof(double) * 2 * (mesh->n_nodes - uploaded), cudaMemcpyHostToDevice, ctx->s_h2d));
     mesh->coords_version++;
   }
+  // the uploaded positions are checked behind the last block's kernel (hidden by the last download); whole-mesh form only: a
+  // row-range call sees a window of the coordinates
+  const bool check = rc == LFGPU_OK && whole && h_node_coords != nullptr;
   cudaError_t e1 = cudaStreamSynchronize(ctx->s_h2d);
+  if (check && e1 == cudaSuccess) rc = queue_geometry_check(ctx, mesh);
   cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
   cudaError_t e3 = cudaStreamSynchronize(ctx->s_d2h);
   if (rc != LFGPU_OK) return rc;
   LFGPU_CUDA_CHECK(ctx, e1);
   LFGPU_CUDA_CHECK(ctx, e2);
   LFGPU_CUDA_CHECK(ctx, e3);
-  return LFGPU_OK;
+  return lfgpu_ctx_synchronize(ctx);  // reads the flag of the check
 }
 }  // namespace
 }  // namespace lfgpu

@@ -276,6 +276,7 @@ int p1h_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, c
 // P1 load vector with a constant source on the vertex rings (assemble_p1.cu)
 int p1_load_fan(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* d, double c, double beta, double* d_vec, int* handled);
 // P2 row kernels (assemble_p2.cu): k00 .. km = reference tensors of FeLagrangeO2Tria, [6 * 6] row-major each
+int queue_geometry_check(lfgpu_ctx* ctx, const lfgpu_mesh* mesh);
 int edge_node_order(lfgpu_ctx* ctx, int64_t nn, int64_t ne, int32_t* enb, uint32_t** new_id_out);
 int permute_node_coords(lfgpu_ctx* ctx, int64_t nn, const uint32_t* new_id, const double* xy, double* xy_perm);
 int build_row_dict(lfgpu_ctx* ctx, int n_words, int64_t n, const uint32_t* words, uint16_t* idx, void** dict_out, int* n_dict);

@@ -330,6 +330,19 @@ int alloc_mesh(lfgpu_ctx* ctx, int64_t n_nodes, int64_t n_cells, bool with_cell_
 }
 
 }  // namespace
+
+// New node positions are checked like those of lfgpu_mesh_upload (the reference asserts on a degenerate cell, tria_o1.cc:10-48;
+// the kernels' 1 / det has no slow path), asynchronously on the context stream: the flag is read by the next lfgpu_ctx_synchronize.
+int queue_geometry_check(lfgpu_ctx* ctx, const lfgpu_mesh* mesh) {
+  int* d_flag = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 1024);
+  if (!ctx->geom_check_pending) LFGPU_CUDA_CHECK(ctx, cudaMemsetAsync(d_flag, 0, 16, ctx->stream));
+  k_validate_cells<<<static_cast<unsigned>(cdiv(mesh->n_cells, kThreads)), kThreads, 0, ctx->stream>>>(mesh->n_cells, mesh->n_nodes, mesh->cell_nodes,
+                                                                                                    mesh->node_coords, mesh->cell_coords, d_flag);
+  LFGPU_LAUNCH_CHECK(ctx);
+  ctx->geom_check_pending = true;
+  return LFGPU_OK;
+}
+
 }  // namespace lfgpu
 
 using namespace lfgpu;
@@ -379,15 +392,7 @@ int lfgpu_mesh_update_node_coords(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const double
   if (mesh->cell_coords != nullptr) LFGPU_FAIL(ctx, LFGPU_ERR_UNSUPPORTED, "mesh carries explicit cell corner coordinates");
   LFGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(mesh->node_coords, node_coords, sizeof(double) * 2 * mesh->n_nodes, cudaMemcpyHostToDevice, ctx->stream));
   mesh->coords_version++;
-  // the new positions are checked like those of lfgpu_mesh_upload (the reference asserts on a degenerate cell, tria_o1.cc:10-48;
-  // the kernels' 1 / det has no slow path), asynchronously: the flag is read by the next lfgpu_ctx_synchronize
-  int* d_flag = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 1024);
-  if (!ctx->geom_check_pending) LFGPU_CUDA_CHECK(ctx, cudaMemsetAsync(d_flag, 0, 16, ctx->stream));
-  k_validate_cells<<<static_cast<unsigned>(cdiv(mesh->n_cells, kThreads)), kThreads, 0, ctx->stream>>>(mesh->n_cells, mesh->n_nodes, mesh->cell_nodes,
-                                                                                                    mesh->node_coords, mesh->cell_coords, d_flag);
-  LFGPU_LAUNCH_CHECK(ctx);
-  ctx->geom_check_pending = true;
-  return LFGPU_OK;
+  return queue_geometry_check(ctx, mesh);
 }
 
 static int tp_common(lfgpu_ctx* ctx, uint32_t nx, uint32_t ny, double x0, double y0, double x1, double y1, int64_t n_cells,

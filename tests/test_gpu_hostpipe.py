@@ -172,3 +172,23 @@ def test_host_entry_optional_buffers(ctx, lf):
     h_xy[:] = xy.ravel()
     dv = pat.assemble_reaction_diffusion_host(1, alpha, gamma, h_xy, None, n_blocks=4)   # upload only
     assert np.array_equal(dv.to_host(), separate_calls(ctx, lf, gm, pat, 1, alpha, gamma, xy))
+
+
+@pytest.mark.parametrize("n_blocks", [1, 4])
+def test_host_entry_checks_the_uploaded_geometry(ctx, lf, n_blocks):
+    """Node positions that arrive through the host-buffer call are checked like those of lfgpu_mesh_upload (the reference asserts on
+    a degenerate cell when the geometry object is built, tria_o1.cc:10-48): LFGPU_ERR_DEGENERATE, and the mesh recovers with the
+    next valid upload."""
+    gm = ctx.mesh_tp_tria(96, 96)
+    pat = gm.dofmap_lagrange(1).symbolic(major=lf.ROW_MAJOR)
+    xy = gm.download()["node_coords"].copy()
+    alpha, gamma = lf.Coeff.const(1.0), lf.Coeff.const(0.0)
+    h_vals = np.empty(pat.nnz)
+    good = pat.assemble_reaction_diffusion_host(1, alpha, gamma, np.ascontiguousarray(xy.ravel()), h_vals, n_blocks=n_blocks).to_host()
+    bad = xy.copy()
+    bad[1000] = bad[1001]  # one collapsed edge
+    with pytest.raises(lf.LfgpuError) as e:
+        pat.assemble_reaction_diffusion_host(1, alpha, gamma, np.ascontiguousarray(bad.ravel()), h_vals, n_blocks=n_blocks)
+    assert e.value.code == -5
+    again = pat.assemble_reaction_diffusion_host(1, alpha, gamma, np.ascontiguousarray(xy.ravel()), h_vals, n_blocks=n_blocks).to_host()
+    assert np.array_equal(good, again) and np.array_equal(h_vals, good)
