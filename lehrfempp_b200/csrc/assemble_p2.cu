@@ -265,6 +265,8 @@ __global__ void k_p2_vertex_compact(int64_t nn, const int32_t* __restrict__ nbr,
   for (int j = 0; j < 3; ++j) cd[static_cast<int64_t>(j) * nn + r] = w[j];
 }
 
+// A row whose differences do not fit is written as "not planned" and counted: if they are few (first-use order leaves a handful at
+// the seams of the edge families) the caller hands them to the generic kernel (irregular[row] = 1) instead of giving the format up.
 __global__ void k_p2_edge_compact(int64_t ne, const int32_t* __restrict__ enb, const uint16_t* __restrict__ idx, uint32_t* __restrict__ ce,
                                   int* __restrict__ overflow) {
   const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -274,14 +276,22 @@ __global__ void k_p2_edge_compact(int64_t ne, const int32_t* __restrict__ enb, c
   if (p >= 0) {
     const int64_t dq = static_cast<int64_t>(enb[ne + e]) - p, d1 = static_cast<int64_t>(enb[2 * ne + e]) - p,
                   d2 = static_cast<int64_t>(enb[3 * ne + e]) - p;
-    if (dq < -32768 || dq > 32767 || d1 < -32768 || d1 > 32767 || d2 < -32768 || d2 > 32767) *overflow = 1;
-    w0 = static_cast<uint32_t>(p);
-    w1 = (static_cast<uint32_t>(dq) & 0xFFFFU) | (static_cast<uint32_t>(d1) << 16);
-    w2 = (static_cast<uint32_t>(d2) & 0xFFFFU) | (static_cast<uint32_t>(idx[e]) << 16);
+    if (dq < -32768 || dq > 32767 || d1 < -32768 || d1 > 32767 || d2 < -32768 || d2 > 32767) {
+      atomicAdd(overflow, 1);
+    } else {
+      w0 = static_cast<uint32_t>(p);
+      w1 = (static_cast<uint32_t>(dq) & 0xFFFFU) | (static_cast<uint32_t>(d1) << 16);
+      w2 = (static_cast<uint32_t>(d2) & 0xFFFFU) | (static_cast<uint32_t>(idx[e]) << 16);
+    }
   }
   ce[e] = w0;
   ce[ne + e] = w1;
   ce[2 * ne + e] = w2;
+}
+// rows the full plan covers but the compact one does not -> generic kernel
+__global__ void k_p2_edge_handback(int64_t ne, const int32_t* __restrict__ enb, const uint32_t* __restrict__ ce, uint8_t* __restrict__ irregular) {
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e < ne && enb[e] >= 0 && (ce[2 * ne + e] >> 16) == 0xFFFFU) irregular[e] = 1;
 }
 
 // ---- the kernels --------------------------------------------------------------------------------------------------------
@@ -849,23 +859,17 @@ int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
       p->p2_general = adopt;
     }
   }
-  P2_CHECK(cudaMalloc(&iota, sizeof(int32_t) * p->n_outer));
-  P2_CHECK(cudaMalloc(&d_num, sizeof(int64_t)));
-  cub::CountingInputIterator<int32_t> count_it(0);
-  size_t tb = 0;
-  if (and_row_keep(ctx, p->n_outer, flag, p->row_keep) != LFGPU_OK) return LFGPU_ERR_CUDA;  // rows nobody asks for need no generic kernel
-  cub::DeviceSelect::Flagged(nullptr, tb, count_it, flag, iota, d_num, p->n_outer, st);
-  P2_CHECK(cudaMalloc(&tmp, tb));
-  P2_CHECK(cub::DeviceSelect::Flagged(tmp, tb, count_it, flag, iota, d_num, p->n_outer, st));
+  // how many rows the plans do not cover (decides whether the plan is worth refining; the exact list is made at the end)
   int64_t n_irr = 0;
-  P2_CHECK(cudaMemcpyAsync(&n_irr, d_num, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  P2_CHECK(cudaStreamSynchronize(st));
-  if (n_irr > 0) {
-    P2_CHECK(cudaMalloc(&p->p2_irregular, sizeof(int32_t) * n_irr));
-    P2_CHECK(cudaMemcpyAsync(p->p2_irregular, iota, sizeof(int32_t) * n_irr, cudaMemcpyDeviceToDevice, st));
-    p->p2_irregular_host.resize(static_cast<size_t>(n_irr));  // ascending; lets a row range find its share of the list
-    P2_CHECK(cudaMemcpyAsync(p->p2_irregular_host.data(), iota, sizeof(int32_t) * n_irr, cudaMemcpyDeviceToHost, st));
+  {
+    int* d_cnt = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 384);
+    int h_cnt = 0;
+    P2_CHECK(cudaMemsetAsync(d_cnt, 0, sizeof(int), st));
+    k_count_flags<<<static_cast<unsigned>(cdiv(p->n_outer, 256)), 256, 0, st>>>(p->n_outer, flag, d_cnt);
+    ctx->launches++;
+    P2_CHECK(cudaMemcpyAsync(&h_cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
     P2_CHECK(cudaStreamSynchronize(st));
+    n_irr = h_cnt;
   }
   // the edge rows' own copy of the node positions, in the order the rows use them (plan_dict.cu: edge_node_order; LFGPU_EDGE_ORDER=0
   // keeps the mesh's array): on the builder's numbering the edge-row kernel is 30 % (P2) / 11 % (P3) faster with it
@@ -887,9 +891,8 @@ int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
   // profiles/r02_p2_rows_compact*_hints*.json): DRAM traffic 4.25 -> 3.87 GB (1.23 -> 1.12 x algorithmic), vertex rows 0.263 -> 0.257 ms,
   // edge rows 0.524 -> 0.549 ms: the kernels wait on dependent loads (plan -> coordinates), not on DRAM bandwidth, and the table
   // lookup adds one more
-  // The vertex rows gain 2 % (0.2626 -> 0.2571 / 0.2622 -> 0.2565 ms in two runs) and their plan shrinks from 36 to 14 B.  With the edge
-  // rows on their own coordinate copy (edge_node_order above) the compact edge plan costs nothing any more (0.4043 vs 0.4046 ms) and
-  // takes 8 B per row off the traffic -> default: both
+  // The vertex rows gain 2 % (0.2626 -> 0.2571 / 0.2622 -> 0.2565 ms in two runs) and their plan shrinks from 36 to 14 B.  The edge rows on
+  // their own coordinate copy (edge_node_order above) run at the HBM rate, where 8 B less per row count -> default: both
   static const char compact_env = [] { const char* e = std::getenv("LFGPU_P2_COMPACT"); return e == nullptr ? '1' : e[0]; }();
   const bool compact_v = compact_env == '1' || compact_env == 'v', compact_e = compact_env == '1' || compact_env == 'e';
   if ((compact_v || compact_e) && cc == 0 && n_irr * 2 <= p->n_outer) {
@@ -945,6 +948,13 @@ int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
         if (e != cudaSuccess) over = 1;
       }
       cudaFree(idx);
+      if (over > 0 && static_cast<int64_t>(over) * 1000 <= ne) {  // a few rows do not fit: they go to the generic kernel
+        k_p2_edge_handback<<<static_cast<unsigned>(cdiv(ne, 256)), 256, 0, st>>>(ne, p->p2e_nbr, ce, flag + nn);
+        ctx->launches++;
+        P2_CHECK(cudaStreamSynchronize(st));
+        n_irr += over;
+        over = 0;
+      }
       if (over == 0) {
         cudaFree(p->p2e_nbr);
         cudaFree(p->p2e_slots);
@@ -957,6 +967,25 @@ int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
         (void)cudaGetLastError();
       }
     }
+  }
+  // rows left to the generic kernel (after the compact edge plan has handed back the few rows it cannot code)
+  P2_CHECK(cudaMalloc(&iota, sizeof(int32_t) * p->n_outer));
+  P2_CHECK(cudaMalloc(&d_num, sizeof(int64_t)));
+  cub::CountingInputIterator<int32_t> count_it(0);
+  size_t tb = 0;
+  if (and_row_keep(ctx, p->n_outer, flag, p->row_keep) != LFGPU_OK) return LFGPU_ERR_CUDA;  // rows nobody asks for need no generic kernel
+  cub::DeviceSelect::Flagged(nullptr, tb, count_it, flag, iota, d_num, p->n_outer, st);
+  P2_CHECK(cudaMalloc(&tmp, tb));
+  P2_CHECK(cub::DeviceSelect::Flagged(tmp, tb, count_it, flag, iota, d_num, p->n_outer, st));
+  n_irr = 0;
+  P2_CHECK(cudaMemcpyAsync(&n_irr, d_num, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  P2_CHECK(cudaStreamSynchronize(st));
+  if (n_irr > 0) {
+    P2_CHECK(cudaMalloc(&p->p2_irregular, sizeof(int32_t) * n_irr));
+    P2_CHECK(cudaMemcpyAsync(p->p2_irregular, iota, sizeof(int32_t) * n_irr, cudaMemcpyDeviceToDevice, st));
+    p->p2_irregular_host.resize(static_cast<size_t>(n_irr));  // ascending; lets a row range find its share of the list
+    P2_CHECK(cudaMemcpyAsync(p->p2_irregular_host.data(), iota, sizeof(int32_t) * n_irr, cudaMemcpyDeviceToHost, st));
+    P2_CHECK(cudaStreamSynchronize(st));
   }
 #undef P2_CHECK
   cleanup();
