@@ -891,9 +891,11 @@ int p2_rows_prepare(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, lfgpu_pattern* p) {
   // profiles/r02_p2_rows_compact*_hints*.json): DRAM traffic 4.25 -> 3.87 GB (1.23 -> 1.12 x algorithmic), vertex rows 0.263 -> 0.257 ms,
   // edge rows 0.524 -> 0.549 ms: the kernels wait on dependent loads (plan -> coordinates), not on DRAM bandwidth, and the table
   // lookup adds one more
-  // The vertex rows gain 2 % (0.2626 -> 0.2571 / 0.2622 -> 0.2565 ms in two runs) and their plan shrinks from 36 to 14 B.  The edge rows on
-  // their own coordinate copy (edge_node_order above) run at the HBM rate, where 8 B less per row count -> default: both
-  static const char compact_env = [] { const char* e = std::getenv("LFGPU_P2_COMPACT"); return e == nullptr ? '1' : e[0]; }();
+  // The vertex rows gain 2 % (0.2626 -> 0.2571 / 0.2622 -> 0.2565 ms in two runs) and their plan shrinks from 36 to 14 B -> default 'v'.
+  // The edge rows stay on the full plan also on their own coordinate copy (edge_node_order above): compact 0.419 ms / 769 MB read,
+  // full 0.404 ms / 968 MB read (ncu: 5.9 against 6.75 TB/s -- the dependent table lookup and the unprefetched row pointer cost more
+  // than 8 B per row save)
+  static const char compact_env = [] { const char* e = std::getenv("LFGPU_P2_COMPACT"); return e == nullptr ? 'v' : e[0]; }();
   const bool compact_v = compact_env == '1' || compact_env == 'v', compact_e = compact_env == '1' || compact_env == 'e';
   if ((compact_v || compact_e) && cc == 0 && n_irr * 2 <= p->n_outer) {
     int* d_over = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 384);
