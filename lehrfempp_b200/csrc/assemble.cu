@@ -602,7 +602,8 @@ __global__ void __launch_bounds__(kItemThreads, MINB > 0 ? MINB : (TENSOR_ONLY ?
 }
 
 // load vector: one thread per cell, FP64 atomics (assembler.h:322-324)
-template <int NSF>
+// STORE: the element vector goes to vec[cell * NSF + b] instead (first pass of the two-pass load vector, see k_load_gather_ev)
+template <int NSF, bool STORE = false>
 __global__ void __launch_bounds__(256) k_load_atomic(Tables hdr, const double* __restrict__ blob, MeshView mv, int64_t n_cells, int stride,
                                                      const int32_t* __restrict__ dofs, const uint8_t* __restrict__ nldof, DevCoeff f,
                                                      const uint8_t* __restrict__ active, double* __restrict__ vec, int* __restrict__ flags) {
@@ -631,11 +632,36 @@ __global__ void __launch_bounds__(256) k_load_atomic(Tables hdr, const double* _
       if (b < T.nsf) acc[b] += s * T.phi[b * T.nq + k];
     }
   }
+  if (STORE) {
+#pragma unroll
+    for (int b = 0; b < NSF; ++b) vec[cell * NSF + b] = acc[b];
+    return;
+  }
   const int n = nldof[cell];
 #pragma unroll
   for (int b = 0; b < NSF; ++b) {
     if (b < n) atomicAdd(vec + dofs[cell * stride + b], acc[b]);
   }
+}
+
+// Second pass of the two-pass load vector: one thread per dof adds the entries elem_vec_K[a] of its (cell, local index) items in
+// ascending cell order -- result[dof] += elem_vec[a] of assembler.h:322-324 in the reference's order, no atomics, bitwise repeatable.
+// Against k_load_gather (which recomputes geometry, source and shape functions once per item, i.e. every element vector once per local
+// dof) every cell is evaluated once; the price is the [n_cells][NSF] array of element vectors in between.
+__global__ void __launch_bounds__(256) k_load_gather_ev(int64_t n_dofs, const int32_t* __restrict__ ptr, const uint32_t* __restrict__ items,
+                                                        const double* __restrict__ ev, int ev_stride, const uint8_t* __restrict__ active,
+                                                        double beta, double* __restrict__ vec) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= n_dofs) return;
+  double sum = (beta == 0.0) ? 0.0 : beta * vec[r];
+  const int32_t t1 = ptr[r + 1];
+  for (int32_t t = ptr[r]; t < t1; ++t) {
+    const uint32_t item = __ldg(items + t);
+    const int64_t cell = item >> 4;
+    if (active != nullptr && active[cell] == 0) continue;
+    sum += __ldg(ev + cell * ev_stride + (item & 15U));
+  }
+  vec[r] = sum;
 }
 
 // load vector, owner-computes: one thread per dof walks its (cell, local index) items in ascending cell order and adds
@@ -1173,16 +1199,47 @@ int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofm
       }
     }
   }
+  const MeshView mv{mesh->node_coords, mesh->cell_nodes, mesh->cell_coords};
+  const size_t tab_bytes = sizeof(double) * ((ht.hdr.total + 1) & ~1);
+  const unsigned grid = static_cast<unsigned>(cdiv(mesh->n_cells, 256));
+  const bool has_quads = mesh->n_quad > 0;
+  // AUTO: two passes -- every element vector once (one thread per cell) into [n_cells][NSF], then one thread per dof adds its entries
+  // in the reference's order: deterministic like GATHER, every cell evaluated once like ATOMIC.  LFGPU_LOAD_TWOPASS=0: atomics.
+  static const bool twopass_env = [] { const char* e = std::getenv("LFGPU_LOAD_TWOPASS"); return e == nullptr || e[0] != '0'; }();
+  if (algo == LFGPU_ALGO_AUTO && twopass_env) {
+    const int nsf = degree == 1 ? (has_quads ? 4 : 3) : degree == 2 ? (has_quads ? 9 : 6) : (has_quads ? 16 : 10);
+    if ((rc = dofmap_gather_plan(ctx, dofmap)) != LFGPU_OK) return rc;
+    auto* dmut = const_cast<lfgpu_dofmap*>(dofmap);
+    if (dmut->lv_ev == nullptr || dmut->lv_ev_stride != nsf) {
+      cudaFree(dmut->lv_ev);
+      dmut->lv_ev = nullptr;
+      LFGPU_CUDA_CHECK(ctx, cudaMalloc(&dmut->lv_ev, sizeof(double) * static_cast<size_t>(nsf) * mesh->n_cells));
+      dmut->lv_ev_stride = nsf;
+    }
+#define LFGPU_LOAD_EV(NSF)                                                                                                            \
+  k_load_atomic<NSF, true><<<grid, 256, tab_bytes, ctx->stream>>>(ht.hdr, blob.d, mv, mesh->n_cells, dofmap->stride, dofmap->cell_dofs, \
+                                                                  dofmap->n_ldof, df, active, dmut->lv_ev, d_flags)
+    switch (nsf) {
+      case 3: LFGPU_LOAD_EV(3); break;
+      case 4: LFGPU_LOAD_EV(4); break;
+      case 6: LFGPU_LOAD_EV(6); break;
+      case 9: LFGPU_LOAD_EV(9); break;
+      case 10: LFGPU_LOAD_EV(10); break;
+      default: LFGPU_LOAD_EV(16); break;
+    }
+#undef LFGPU_LOAD_EV
+    LFGPU_LAUNCH_CHECK(ctx);
+    k_load_gather_ev<<<static_cast<unsigned>(cdiv(dofmap->n_dofs, 256)), 256, 0, ctx->stream>>>(dofmap->n_dofs, dofmap->g_ptr, dofmap->g_items,
+                                                                                               dmut->lv_ev, nsf, active, beta, d_vec);
+    LFGPU_LAUNCH_CHECK(ctx);
+    return LFGPU_OK;
+  }
   if (beta == 0.0) {
     LFGPU_CUDA_CHECK(ctx, cudaMemsetAsync(d_vec, 0, sizeof(double) * dofmap->n_dofs, ctx->stream));
   } else if (beta != 1.0) {
     k_scale<<<static_cast<unsigned>(cdiv(dofmap->n_dofs, 256)), 256, 0, ctx->stream>>>(dofmap->n_dofs, beta, d_vec);
     LFGPU_LAUNCH_CHECK(ctx);
   }
-  const MeshView mv{mesh->node_coords, mesh->cell_nodes, mesh->cell_coords};
-  const size_t tab_bytes = sizeof(double) * ((ht.hdr.total + 1) & ~1);
-  const unsigned grid = static_cast<unsigned>(cdiv(mesh->n_cells, 256));
-  const bool has_quads = mesh->n_quad > 0;
 #define LFGPU_LOAD(NSF)                                                                                                         \
   k_load_atomic<NSF><<<grid, 256, tab_bytes, ctx->stream>>>(ht.hdr, blob.d, mv, mesh->n_cells, dofmap->stride, dofmap->cell_dofs, \
                                                             dofmap->n_ldof, df, active, d_vec, d_flags)

@@ -81,6 +81,9 @@ struct lfgpu_dofmap {
   uint8_t* lv_info = nullptr;      // [n_dofs] 0 open fan, 1 closed fan, 2 not a single fan (generic kernel), 3 no cells
   int32_t* lv_irregular = nullptr;
   int64_t n_lv_irregular = 0;
+  // element vectors of the two-pass load vector (assemble.cu: k_load_atomic<NSF, true> + k_load_gather_ev), [n_cells][lv_ev_stride]
+  double* lv_ev = nullptr;
+  int lv_ev_stride = 0;
 };
 
 struct lfgpu_pattern {

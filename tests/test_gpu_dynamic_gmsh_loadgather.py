@@ -197,3 +197,37 @@ def test_gmsh_second_order_mesh_is_rejected_on_the_device(ctx, lf):
     with pytest.raises(lf.LfgpuError) as e:
         g.mesh(ctx)
     assert e.value.code == -7
+
+
+# ---- two-pass load vector (LFGPU_ALGO_AUTO): element vectors once per cell, then added per dof in the reference's order ------------
+@pytest.mark.parametrize("kind", ["tp_tria:9", "hybrid:8", "golden0", "golden6"])
+@pytest.mark.parametrize("degree", [1, 2, 3])
+def test_load_vector_two_pass(ctx, lf, golden_meshes, kind, degree):
+    om, gm = oracle_and_gpu(ctx, kind, golden_meshes)
+    dm = gm.dofmap_lagrange(degree)
+    gf, _ = per_qp_scalar(ctx, gm, degree, 3)
+    ov, _ = om.assemble_load(degree, lfo.coeff.builtin(3))
+    gv = dm.assemble_load(degree, gf).to_host()
+    assert rel_max_err(gv, ov) <= TOL
+    # the same additions in the same order as the one-pass gather kernel; bitwise repeatable
+    gg = dm.assemble_load(degree, gf, algo=lf.ALGO_GATHER).to_host()
+    assert rel_max_err(gv, gg) <= 1e-15
+    assert np.array_equal(gv, dm.assemble_load(degree, gf).to_host())
+    out = dm.assemble_load(degree, gf)
+    dm.assemble_load(degree, gf, beta=1.0, out=out)
+    assert rel_max_err(out.to_host(), 2 * ov) <= TOL
+    act = (np.arange(om.n_cells) % 3 != 0).astype(np.uint8)
+    ov3, _ = om.assemble_load(degree, lfo.coeff.builtin(3), active=act)
+    gv3 = dm.assemble_load(degree, gf, active=ctx.to_device(act)).to_host()
+    assert rel_max_err(gv3, ov3) <= TOL
+
+
+def test_load_vector_two_pass_large(ctx, lf):
+    """1.0e6 hybrid cells / 2.9e6 triangles, P2 and P3: against the atomic kernel; sum of the load vector of f = 1 is |Omega|"""
+    for gm, area in ((ctx.mesh_hybrid(816, 0.2, 7), 1.0), (ctx.mesh_tp_tria(1200, 1200, 0.0, 0.0, 2.0, 1.0), 2.0)):
+        for degree in (2, 3):
+            dm = gm.dofmap_lagrange(degree)
+            v = dm.assemble_load(degree, lf.Coeff.const(1.0)).to_host()
+            assert abs(v.sum() - area) <= 1e-11
+            a = dm.assemble_load(degree, lf.Coeff.const(1.0), algo=lf.ALGO_ATOMIC).to_host()
+            assert rel_max_err(v, a) <= 1e-13
