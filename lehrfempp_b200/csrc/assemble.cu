@@ -602,7 +602,8 @@ __global__ void __launch_bounds__(kItemThreads, MINB > 0 ? MINB : (TENSOR_ONLY ?
 }
 
 // load vector: one thread per cell, FP64 atomics (assembler.h:322-324)
-// STORE: the element vector goes to vec[cell * NSF + b] instead (first pass of the two-pass load vector, see k_load_gather_ev)
+// STORE: entry b of the element vector goes to vec[dofs[cell * stride + b]] by a plain store -- first pass of the two-pass load vector:
+// `dofs` is then the position table of k_load_positions, `vec` the item-ordered array k_load_sum_items adds up
 template <int NSF, bool STORE = false>
 __global__ void __launch_bounds__(256) k_load_atomic(Tables hdr, const double* __restrict__ blob, MeshView mv, int64_t n_cells, int stride,
                                                      const int32_t* __restrict__ dofs, const uint8_t* __restrict__ nldof, DevCoeff f,
@@ -612,7 +613,15 @@ __global__ void __launch_bounds__(256) k_load_atomic(Tables hdr, const double* _
   load_tables(hdr, blob, smem, tt, tq);
   const int64_t cell = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (cell >= n_cells) return;
-  if (active != nullptr && active[cell] == 0) return;
+  if (active != nullptr && active[cell] == 0) {
+    if (STORE) {  // an inactive cell contributes zeros: the second pass adds whole item ranges
+      const int n0 = nldof[cell];
+#pragma unroll
+      for (int b = 0; b < NSF; ++b)
+        if (b < n0) vec[dofs[cell * stride + b]] = 0.0;
+    }
+    return;
+  }
   const CellGeom g = load_geom(mv, cell);
   const TabView& T = g.quad ? tq : tt;
   if (T.nsf == 0) {
@@ -632,9 +641,11 @@ __global__ void __launch_bounds__(256) k_load_atomic(Tables hdr, const double* _
       if (b < T.nsf) acc[b] += s * T.phi[b * T.nq + k];
     }
   }
-  if (STORE) {
+  if (STORE) {  // dofs = position of every (cell, local index) in the item list of its dof, stride = NSF
+    const int n0 = nldof[cell];
 #pragma unroll
-    for (int b = 0; b < NSF; ++b) vec[cell * NSF + b] = acc[b];
+    for (int b = 0; b < NSF; ++b)
+      if (b < n0) vec[dofs[cell * stride + b]] = acc[b];
     return;
   }
   const int n = nldof[cell];
@@ -644,23 +655,30 @@ __global__ void __launch_bounds__(256) k_load_atomic(Tables hdr, const double* _
   }
 }
 
-// Second pass of the two-pass load vector: one thread per dof adds the entries elem_vec_K[a] of its (cell, local index) items in
-// ascending cell order -- result[dof] += elem_vec[a] of assembler.h:322-324 in the reference's order, no atomics, bitwise repeatable.
-// Against k_load_gather (which recomputes geometry, source and shape functions once per item, i.e. every element vector once per local
-// dof) every cell is evaluated once; the price is the [n_cells][NSF] array of element vectors in between.
-__global__ void __launch_bounds__(256) k_load_gather_ev(int64_t n_dofs, const int32_t* __restrict__ ptr, const uint32_t* __restrict__ items,
-                                                        const double* __restrict__ ev, int ev_stride, const uint8_t* __restrict__ active,
+// Two-pass load vector.  k_load_positions (once per dof map): where entry (cell, a) of an element vector goes -- the index of the item
+// (cell << 4 | a) in the gather list of its dof, i.e. items of one dof are adjacent and in ascending cell order.  First pass
+// (k_load_atomic<NSF, true>): every element vector once, one thread per cell, stored there.  Second pass (k_load_sum_items): one
+// thread per dof adds its run of entries front to back -- result[dof] += elem_vec[a] of assembler.h:322-324 in the reference's
+// order, no atomics, bitwise repeatable, contiguous reads.  (k_load_gather evaluates geometry, source and shape functions once per
+// ITEM, i.e. every element vector once per local dof: 2.5 x slower at config C3, 3 x at C4's size; a first two-pass version that
+// kept the vectors cell by cell and gathered 8-byte entries out of 32-byte sectors was only 1.5 - 1.8 x faster than that.)
+__global__ void k_load_positions(int64_t n_dofs, const int32_t* __restrict__ ptr, const uint32_t* __restrict__ items, int nsf,
+                                 int32_t* __restrict__ pos) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= n_dofs) return;
+  for (int32_t t = ptr[r]; t < ptr[r + 1]; ++t) {
+    const uint32_t item = items[t];
+    pos[static_cast<int64_t>(item >> 4) * nsf + (item & 15U)] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_load_sum_items(int64_t n_dofs, const int32_t* __restrict__ ptr, const double* __restrict__ ev,
                                                         double beta, double* __restrict__ vec) {
   const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (r >= n_dofs) return;
   double sum = (beta == 0.0) ? 0.0 : beta * vec[r];
-  const int32_t t1 = ptr[r + 1];
-  for (int32_t t = ptr[r]; t < t1; ++t) {
-    const uint32_t item = __ldg(items + t);
-    const int64_t cell = item >> 4;
-    if (active != nullptr && active[cell] == 0) continue;
-    sum += __ldg(ev + cell * ev_stride + (item & 15U));
-  }
+  const int32_t t1 = __ldg(ptr + r + 1);
+  for (int32_t t = __ldg(ptr + r); t < t1; ++t) sum += __ldg(ev + t);
   vec[r] = sum;
 }
 
@@ -1203,8 +1221,8 @@ int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofm
   const size_t tab_bytes = sizeof(double) * ((ht.hdr.total + 1) & ~1);
   const unsigned grid = static_cast<unsigned>(cdiv(mesh->n_cells, 256));
   const bool has_quads = mesh->n_quad > 0;
-  // AUTO: two passes -- every element vector once (one thread per cell) into [n_cells][NSF], then one thread per dof adds its entries
-  // in the reference's order: deterministic like GATHER, every cell evaluated once like ATOMIC.  LFGPU_LOAD_TWOPASS=0: atomics.
+  // AUTO: two passes (see k_load_positions) -- every element vector once, one thread per cell, stored in item order; then one thread per
+  // dof adds its run: deterministic like GATHER, every cell evaluated once like ATOMIC.  LFGPU_LOAD_TWOPASS=0: atomics.
   static const bool twopass_env = [] { const char* e = std::getenv("LFGPU_LOAD_TWOPASS"); return e == nullptr || e[0] != '0'; }();
   if (algo == LFGPU_ALGO_AUTO && twopass_env) {
     const int nsf = degree == 1 ? (has_quads ? 4 : 3) : degree == 2 ? (has_quads ? 9 : 6) : (has_quads ? 16 : 10);
@@ -1212,13 +1230,22 @@ int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofm
     auto* dmut = const_cast<lfgpu_dofmap*>(dofmap);
     if (dmut->lv_ev == nullptr || dmut->lv_ev_stride != nsf) {
       cudaFree(dmut->lv_ev);
+      cudaFree(dmut->lv_pos);
       dmut->lv_ev = nullptr;
-      LFGPU_CUDA_CHECK(ctx, cudaMalloc(&dmut->lv_ev, sizeof(double) * static_cast<size_t>(nsf) * mesh->n_cells));
+      dmut->lv_pos = nullptr;
+      int32_t n_items = 0;
+      LFGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(&n_items, dofmap->g_ptr + dofmap->n_dofs, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      LFGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+      LFGPU_CUDA_CHECK(ctx, cudaMalloc(&dmut->lv_ev, sizeof(double) * std::max<int64_t>(n_items, 1)));
+      LFGPU_CUDA_CHECK(ctx, cudaMalloc(&dmut->lv_pos, sizeof(int32_t) * static_cast<size_t>(nsf) * mesh->n_cells));
+      k_load_positions<<<static_cast<unsigned>(cdiv(dofmap->n_dofs, 256)), 256, 0, ctx->stream>>>(dofmap->n_dofs, dofmap->g_ptr, dofmap->g_items, nsf,
+                                                                                                 dmut->lv_pos);
+      LFGPU_LAUNCH_CHECK(ctx);
       dmut->lv_ev_stride = nsf;
     }
-#define LFGPU_LOAD_EV(NSF)                                                                                                            \
-  k_load_atomic<NSF, true><<<grid, 256, tab_bytes, ctx->stream>>>(ht.hdr, blob.d, mv, mesh->n_cells, dofmap->stride, dofmap->cell_dofs, \
-                                                                  dofmap->n_ldof, df, active, dmut->lv_ev, d_flags)
+#define LFGPU_LOAD_EV(NSF)                                                                                                   \
+  k_load_atomic<NSF, true><<<grid, 256, tab_bytes, ctx->stream>>>(ht.hdr, blob.d, mv, mesh->n_cells, NSF, dmut->lv_pos, dofmap->n_ldof, df, \
+                                                                  active, dmut->lv_ev, d_flags)
     switch (nsf) {
       case 3: LFGPU_LOAD_EV(3); break;
       case 4: LFGPU_LOAD_EV(4); break;
@@ -1229,8 +1256,7 @@ int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofm
     }
 #undef LFGPU_LOAD_EV
     LFGPU_LAUNCH_CHECK(ctx);
-    k_load_gather_ev<<<static_cast<unsigned>(cdiv(dofmap->n_dofs, 256)), 256, 0, ctx->stream>>>(dofmap->n_dofs, dofmap->g_ptr, dofmap->g_items,
-                                                                                               dmut->lv_ev, nsf, active, beta, d_vec);
+    k_load_sum_items<<<static_cast<unsigned>(cdiv(dofmap->n_dofs, 256)), 256, 0, ctx->stream>>>(dofmap->n_dofs, dofmap->g_ptr, dmut->lv_ev, beta, d_vec);
     LFGPU_LAUNCH_CHECK(ctx);
     return LFGPU_OK;
   }

@@ -81,8 +81,10 @@ struct lfgpu_dofmap {
   uint8_t* lv_info = nullptr;      // [n_dofs] 0 open fan, 1 closed fan, 2 not a single fan (generic kernel), 3 no cells
   int32_t* lv_irregular = nullptr;
   int64_t n_lv_irregular = 0;
-  // element vectors of the two-pass load vector (assemble.cu: k_load_atomic<NSF, true> + k_load_gather_ev), [n_cells][lv_ev_stride]
+  // two-pass load vector (assemble.cu: k_load_positions): lv_pos [n_cells][lv_ev_stride] = index of (cell, a) in g_items,
+  // lv_ev [number of items] = the element-vector entries in item order
   double* lv_ev = nullptr;
+  int32_t* lv_pos = nullptr;
   int lv_ev_stride = 0;
 };
 

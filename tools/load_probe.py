@@ -18,7 +18,7 @@ dm = mesh.dofmap_lagrange(degree)
 vec = ctx.zeros(dm.num_dofs)
 source = sys.argv[3] if len(sys.argv) > 3 else "const"   # const | per_qp (tabulated at the quadrature points, as MeshFunctionGlobal is)
 if source == "per_qp":
-    nq = lf.default_quad_rule(3, 2 * degree).weights.size
+    nq = max(lf.default_quad_rule(3, 2 * degree).weights.size, lf.default_quad_rule(4, 2 * degree).weights.size)  # table stride
     xy = mesh.qp_coords(degree, nq).to_host().reshape(mesh.n_cells, nq, 2)
     f = lf.Coeff.per_qp(ctx.to_device(np.ascontiguousarray(1.0 + xy[..., 0] * xy[..., 1])), nq)
 else:
