@@ -213,11 +213,20 @@ int lfgpu_multi_setup(lfgpu_multi* m, int64_t n_nodes, const double* node_coords
   m->n_dofs = n_dofs;
   m->n_cells = n_cells;
   const int n_parts = static_cast<int>(m->parts.size());
-  std::vector<std::thread> th;
+  // one thread per distinct DEVICE; parts that share a device (a list may name one several times) are set up one after the other
+  std::vector<int> devices;
   for (int k = 0; k < n_parts; ++k) {
     m->parts[k].rc = LFGPU_OK;
+    const int dev = m->parts[k].ctx->device;
+    if (std::find(devices.begin(), devices.end(), dev) == devices.end()) devices.push_back(dev);
+  }
+  std::vector<std::thread> th;
+  for (const int dev : devices) {
     th.emplace_back([=]() {
-      setup_part(m->parts[k], k, n_parts, n_nodes, node_coords, n_cells, cell_nodes, cell_coords, n_dofs, stride, cell_dofs, n_ldof, major);
+      for (int k = 0; k < n_parts; ++k) {
+        if (m->parts[k].ctx->device != dev) continue;
+        setup_part(m->parts[k], k, n_parts, n_nodes, node_coords, n_cells, cell_nodes, cell_coords, n_dofs, stride, cell_dofs, n_ldof, major);
+      }
     });
   }
   for (auto& t : th) t.join();
