@@ -1165,37 +1165,6 @@ int lfgpu::assemble_rd_impl(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_
   return rc;
 }
 
-namespace lfgpu {
-// Node positions and cell corners for the kernels that run one thread per cell: where the mesh numbers cells and nodes in different
-// sweeps (the reference's builders) a copy of the positions in the order the cells use them, with cell_nodes rewritten to match
-// (plan_dict.cu: cell_node_order; refreshed when the mesh's coordinates have changed).  *mv keeps the mesh's own arrays otherwise.
-// Not for coefficients that are indexed by node number (LFGPU_COEFF_NODAL).  LFGPU_CELL_ORDER=0: never.
-int cell_order_view(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, MeshView* mv) {
-  *mv = MeshView{mesh->node_coords, mesh->cell_nodes, mesh->cell_coords};
-  static const bool env = [] { const char* e = std::getenv("LFGPU_CELL_ORDER"); return e == nullptr || e[0] != '0'; }();
-  if (!env || mesh->cell_coords != nullptr) return LFGPU_OK;
-  auto* m = const_cast<lfgpu_mesh*>(mesh);
-  if (m->co_state == 0) {
-    m->co_state = -1;
-    int rc = cell_node_order(ctx, m->n_nodes, m->n_cells, m->cell_nodes, &m->co_newid, &m->co_cells);
-    if (rc != LFGPU_OK) return rc;
-    if (m->co_newid != nullptr) {
-      LFGPU_CUDA_CHECK(ctx, cudaMalloc(&m->co_xy, sizeof(double) * 2 * m->n_nodes));
-      m->co_version = 0;
-      m->co_state = 1;
-    }
-  }
-  if (m->co_state != 1) return LFGPU_OK;
-  if (m->co_version != m->coords_version) {
-    int rc = permute_node_coords(ctx, m->n_nodes, m->co_newid, m->node_coords, m->co_xy);
-    if (rc != LFGPU_OK) return rc;
-    m->co_version = m->coords_version;
-  }
-  *mv = MeshView{m->co_xy, m->co_cells, nullptr};
-  return LFGPU_OK;
-}
-}  // namespace lfgpu
-
 extern "C" {
 
 int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* dofmap, int degree, const lfgpu_quad* qr_tria,
@@ -1248,8 +1217,7 @@ int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofm
       }
     }
   }
-  MeshView mv{mesh->node_coords, mesh->cell_nodes, mesh->cell_coords};
-  if (df.kind != LFGPU_COEFF_NODAL && (rc = cell_order_view(ctx, mesh, &mv)) != LFGPU_OK) return rc;
+  const MeshView mv{mesh->node_coords, mesh->cell_nodes, mesh->cell_coords};
   const size_t tab_bytes = sizeof(double) * ((ht.hdr.total + 1) & ~1);
   const unsigned grid = static_cast<unsigned>(cdiv(mesh->n_cells, 256));
   const bool has_quads = mesh->n_quad > 0;
@@ -1320,8 +1288,7 @@ int lfgpu_qp_coords(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, int degree, const lf
   if (rc != LFGPU_OK) return rc;
   DeviceBlob blob;
   if ((rc = upload_blob(ctx, ht, &blob)) != LFGPU_OK) return rc;
-  MeshView mv{mesh->node_coords, mesh->cell_nodes, mesh->cell_coords};
-  if ((rc = cell_order_view(ctx, mesh, &mv)) != LFGPU_OK) return rc;
+  const MeshView mv{mesh->node_coords, mesh->cell_nodes, mesh->cell_coords};
   const size_t tab_bytes = sizeof(double) * ((ht.hdr.total + 1) & ~1);
   k_qp_coords<<<static_cast<unsigned>(cdiv(mesh->n_cells, 256)), 256, tab_bytes, ctx->stream>>>(ht.hdr, blob.d, mv, mesh->n_cells, nq_stride, d_out);
   LFGPU_LAUNCH_CHECK(ctx);

@@ -46,12 +46,6 @@ struct lfgpu_mesh {
   uint32_t* cell_nodes = nullptr;   // [n_cells][4], NIL padded
   double* cell_coords = nullptr;    // [n_cells][4][2] or nullptr (corners == node positions)
   uint64_t coords_version = 1;      // bumped by every call that rewrites node_coords (the row-kernel plans keep reordered copies)
-  // view for the one-thread-per-cell kernels (plan_dict.cu: cell_node_order), built on first use: 0 = not tried, 1 = ready, -1 = not adopted
-  int co_state = 0;
-  uint32_t* co_newid = nullptr;     // [n_nodes] position of every node in co_xy
-  uint32_t* co_cells = nullptr;     // [n_cells][4] cell_nodes in those positions
-  double* co_xy = nullptr;          // [n_nodes][2]
-  uint64_t co_version = 0;
   // topology (optional, built by lfgpu_mesh_build_topology / tp generators)
   bool has_topology = false;
   uint32_t tp_nx = 0, tp_ny = 0;    // > 0: mesh of the triangle builder, whose explicit edge list is generated on demand
@@ -288,7 +282,6 @@ int p1h_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, c
 int p1_load_fan(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* d, double c, double beta, double* d_vec, int* handled);
 // P2 row kernels (assemble_p2.cu): k00 .. km = reference tensors of FeLagrangeO2Tria, [6 * 6] row-major each
 int queue_geometry_check(lfgpu_ctx* ctx, const lfgpu_mesh* mesh);
-int cell_node_order(lfgpu_ctx* ctx, int64_t nn, int64_t nc, const uint32_t* cell_nodes, uint32_t** new_id_out, uint32_t** cells_out);
 int edge_node_order(lfgpu_ctx* ctx, int64_t nn, int64_t ne, int32_t* enb, uint32_t** new_id_out);
 int permute_node_coords(lfgpu_ctx* ctx, int64_t nn, const uint32_t* new_id, const double* xy, double* xy_perm);
 int build_row_dict(lfgpu_ctx* ctx, int n_words, int64_t n, const uint32_t* words, uint16_t* idx, void** dict_out, int* n_dict);

@@ -361,9 +361,6 @@ void lfgpu_mesh_destroy(lfgpu_mesh* m) {
   cudaFree(m->edge_nodes);
   cudaFree(m->cell_edges);
   cudaFree(m->cell_edge_ori);
-  cudaFree(m->co_newid);
-  cudaFree(m->co_cells);
-  cudaFree(m->co_xy);
   delete m;
 }
 

@@ -245,106 +245,6 @@ int permute_node_coords(lfgpu_ctx* ctx, int64_t nn, const uint32_t* new_id, cons
   return LFGPU_OK;
 }
 
-// ---- node order of the cell list -----------------------------------------------------------------------------------------------
-// The same for the kernels that run one thread per CELL (element vectors of the load vector, quadrature-point coordinates): on the
-// builder's numbering consecutive cells (column by column) read their corners from nodes (row by row) that are a mesh row apart,
-// i.e. three 16-byte gathers per cell from three different lines.  cells_out: cell_nodes with the node numbers replaced by positions
-// in first-use order (NIL kept); *new_id_out as above.  Both null when the order would not cut the line changes between
-// consecutive cells by a quarter.
-namespace {
-__global__ void k_cell_first_use(int64_t nc, const uint32_t* __restrict__ cn, uint32_t* __restrict__ key) {
-  const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (c >= nc) return;
-  for (int k = 0; k < 4; ++k) {
-    const uint32_t v = cn[4 * c + k];
-    if (v != 0xFFFFFFFFU) atomicMin(key + v, static_cast<uint32_t>(4 * c + k));
-  }
-}
-__global__ void k_cell_line_changes(int64_t nc, const uint32_t* __restrict__ cn, const uint32_t* __restrict__ map, unsigned long long* __restrict__ count) {
-  const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  int n = 0;
-  if (c > 0 && c < nc) {
-    for (int k = 0; k < 3; ++k) {
-      uint32_t a = cn[4 * c + k], b = cn[4 * (c - 1) + k];
-      if (map != nullptr) {
-        a = map[a];
-        b = map[b];
-      }
-      n += (a >> 3) != (b >> 3);
-    }
-  }
-  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffU, n, o);
-  if ((threadIdx.x & 31) == 0 && n > 0) atomicAdd(count, static_cast<unsigned long long>(n));
-}
-__global__ void k_cell_remap(int64_t nc, const uint32_t* __restrict__ cn, const uint32_t* __restrict__ new_id, uint32_t* __restrict__ out) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= 4 * nc) return;
-  const uint32_t v = cn[i];
-  out[i] = v == 0xFFFFFFFFU ? v : new_id[v];
-}
-}  // namespace
-
-int cell_node_order(lfgpu_ctx* ctx, int64_t nn, int64_t nc, const uint32_t* cell_nodes, uint32_t** new_id_out, uint32_t** cells_out) {
-  *new_id_out = nullptr;
-  *cells_out = nullptr;
-  if (nn < 8 || nc <= 1 || nc >= (1LL << 30) || nn >= (1LL << 31)) return LFGPU_OK;
-  cudaStream_t st = ctx->stream;
-  uint32_t *key = nullptr, *key2 = nullptr, *new_id = nullptr, *cells = nullptr;
-  int32_t *ids = nullptr, *ids2 = nullptr;
-  void* tmp = nullptr;
-  auto cleanup = [&]() { cudaFree(key); cudaFree(key2); cudaFree(ids); cudaFree(ids2); cudaFree(tmp); };
-#define ORD_CHECK(expr)                                                           \
-  do {                                                                            \
-    cudaError_t _e = (expr);                                                      \
-    if (_e != cudaSuccess) {                                                      \
-      set_last_error(ctx, std::string(#expr) + ": " + cudaGetErrorString(_e));    \
-      cleanup();                                                                  \
-      cudaFree(new_id);                                                           \
-      cudaFree(cells);                                                            \
-      return LFGPU_ERR_CUDA;                                                      \
-    }                                                                             \
-  } while (0)
-  ORD_CHECK(cudaMalloc(&key, sizeof(uint32_t) * nn));
-  ORD_CHECK(cudaMalloc(&key2, sizeof(uint32_t) * nn));
-  ORD_CHECK(cudaMalloc(&ids, sizeof(int32_t) * nn));
-  ORD_CHECK(cudaMalloc(&ids2, sizeof(int32_t) * nn));
-  ORD_CHECK(cudaMalloc(&new_id, sizeof(uint32_t) * nn));
-  ORD_CHECK(cudaMemsetAsync(key, 0xFF, sizeof(uint32_t) * nn, st));
-  k_cell_first_use<<<static_cast<unsigned>(cdiv(nc, 256)), 256, 0, st>>>(nc, cell_nodes, key);
-  k_iota<<<static_cast<unsigned>(cdiv(nn, 256)), 256, 0, st>>>(nn, ids);
-  ctx->launches += 2;
-  size_t tb = 0;
-  ORD_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tb, key, key2, ids, ids2, nn, 0, 32, st));
-  ORD_CHECK(cudaMalloc(&tmp, std::max<size_t>(tb, 16)));
-  ORD_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tb, key, key2, ids, ids2, nn, 0, 32, st));
-  k_rank_of<<<static_cast<unsigned>(cdiv(nn, 256)), 256, 0, st>>>(nn, ids2, new_id);
-  ctx->launches++;
-  unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(key);
-  unsigned long long h_cnt[2] = {0ULL, 0ULL};
-  ORD_CHECK(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), st));
-  k_cell_line_changes<<<static_cast<unsigned>(cdiv(nc, 256)), 256, 0, st>>>(nc, cell_nodes, nullptr, d_cnt);
-  k_cell_line_changes<<<static_cast<unsigned>(cdiv(nc, 256)), 256, 0, st>>>(nc, cell_nodes, new_id, d_cnt + 1);
-  ctx->launches += 2;
-  ORD_CHECK(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
-  ORD_CHECK(cudaStreamSynchronize(st));
-  static const bool force = [] { const char* e = std::getenv("LFGPU_CELL_ORDER"); return e != nullptr && e[0] == '2'; }();
-  if (!force && 4 * h_cnt[1] > 3 * h_cnt[0]) {
-    cleanup();
-    cudaFree(new_id);
-    return LFGPU_OK;
-  }
-  ORD_CHECK(cudaMalloc(&cells, sizeof(uint32_t) * 4 * nc));
-  k_cell_remap<<<static_cast<unsigned>(cdiv(4 * nc, 256)), 256, 0, st>>>(nc, cell_nodes, new_id, cells);
-  ctx->launches++;
-  ORD_CHECK(cudaGetLastError());
-  ORD_CHECK(cudaStreamSynchronize(st));
-#undef ORD_CHECK
-  cleanup();
-  *new_id_out = new_id;
-  *cells_out = cells;
-  return LFGPU_OK;
-}
-
 // words: device [n_words][n] (slot-major), n_words in 1..4.  idx: device [n], receives the tuple number of every row; *dict_out:
 // device uint4 [*n_dict] (cudaMalloc, the caller frees), unused components zero.  *n_dict = -1: too many distinct tuples, idx untouched.
 int build_row_dict(lfgpu_ctx* ctx, int n_words, int64_t n, const uint32_t* words, uint16_t* idx, void** dict_out, int* n_dict) {
