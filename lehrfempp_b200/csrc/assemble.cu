@@ -1197,13 +1197,25 @@ int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofm
   // P1 triangles, constant source, every cell active: the vertex-ring kernel (assemble_p1.cu), deterministic, no atomics;
   // rows that are not a single fan go through the gather kernel.  LFGPU_LOAD_FAN=0 keeps the atomic kernel.
   static const bool lfan_env = [] { const char* e = std::getenv("LFGPU_LOAD_FAN"); return e == nullptr || e[0] != '0'; }();
-  if (algo == LFGPU_ALGO_AUTO && lfan_env && degree == 1 && df.kind == LFGPU_COEFF_CONST && active == nullptr && mesh->n_quad == 0 &&
-      mesh->cell_coords == nullptr && ht.hdr.nsf[0] == 3) {
+  const bool tabulated = df.kind == LFGPU_COEFF_PER_CELL || df.kind == LFGPU_COEFF_PER_QP;
+  if (algo == LFGPU_ALGO_AUTO && lfan_env && degree == 1 && (df.kind == LFGPU_COEFF_CONST || tabulated) && active == nullptr &&
+      mesh->n_quad == 0 && mesh->cell_coords == nullptr && ht.hdr.nsf[0] == 3) {
     const int nq = ht.hdr.nq[0];
     const double* l = ht.blob.data() + ht.hdr.off[0] + 3 * nq + 3 * 3 * nq + 5 * 9;  // pack_type: ... k00 k01 k10 k11 m | l
-    if (std::fabs(l[1] - l[0]) <= 1e-15 && std::fabs(l[2] - l[0]) <= 1e-15) {
+    if (tabulated ? nq <= 4 : (std::fabs(l[1] - l[0]) <= 1e-15 && std::fabs(l[2] - l[0]) <= 1e-15)) {
       int handled = 0;
-      if ((rc = p1_load_fan(ctx, mesh, dofmap, df.c[0] * l[0], beta, d_vec, &handled)) != LFGPU_OK) return rc;
+      if (tabulated) {
+        // w_q phi_a(x_q) of the rule in use (pack_type: w qx qy | phi[a][q] ...)
+        const double* w = ht.blob.data() + ht.hdr.off[0];
+        const double* phi = w + 3 * nq;
+        double wtab[12];
+        for (int a = 0; a < 3; ++a)
+          for (int q = 0; q < nq; ++q) wtab[a * nq + q] = w[q] * phi[a * nq + q];
+        rc = p1_load_fan(ctx, mesh, dofmap, 0.0, beta, d_vec, &handled, df.data, df.kind == LFGPU_COEFF_PER_CELL ? 1 : df.stride, nq, wtab);
+      } else {
+        rc = p1_load_fan(ctx, mesh, dofmap, df.c[0] * l[0], beta, d_vec, &handled);
+      }
+      if (rc != LFGPU_OK) return rc;
       if (handled) {
         if (dofmap->n_lv_irregular > 0) {
           const MeshView mvg{mesh->node_coords, mesh->cell_nodes, mesh->cell_coords};

@@ -30,8 +30,9 @@ constexpr uint32_t kNil = 0xFFFFFFFFu;
 // ---- plan construction --------------------------------------------------------------------------------------------
 // One thread per row: order the adjacent cells into a fan.  Returns the ring in `ring` (ids), its length, closed flag;
 // false if the cells do not form exactly one fan.
+// cell_item (optional): the adjacency item (cell << 4 | local index of the row's node) of the cell between ring[s] and ring[s + 1]
 __device__ bool build_ring(int32_t row, int m, const uint32_t* __restrict__ adj, int64_t it0, const uint32_t* __restrict__ cell_nodes,
-                           uint32_t* ring, int& len, bool& closed) {
+                           uint32_t* ring, int& len, bool& closed, uint32_t* cell_item = nullptr) {
   uint32_t ja[kMaxFan], ka[kMaxFan];
   for (int t = 0; t < m; ++t) {
     const uint32_t item = adj[it0 + t];
@@ -76,6 +77,7 @@ __device__ bool build_ring(int32_t row, int m, const uint32_t* __restrict__ adj,
   }
   used |= 1U << start;
   len = 1;
+  if (cell_item != nullptr) cell_item[0] = adj[it0 + start];
   for (int step = 1; step < m; ++step) {
     ring[len++] = cur;
     int nxt = -1;
@@ -87,6 +89,7 @@ __device__ bool build_ring(int32_t row, int m, const uint32_t* __restrict__ adj,
     }
     if (nxt < 0) return false;  // chain broken: more than one fan
     used |= 1U << nxt;
+    if (cell_item != nullptr) cell_item[step] = adj[it0 + nxt];
     cur = (ja[nxt] == cur) ? ka[nxt] : ja[nxt];
   }
   if (closed) {
@@ -577,6 +580,87 @@ __global__ void __launch_bounds__(128, 8) k_load_p1_fan(int n_rows, const void* 
   vec[r] = beta == 0.0 ? v : fma(beta, vec[r], v);
 }
 
+// ---- the same rings with a source that varies from cell to cell (tabulated per cell or per quadrature point) -----------------
+// Entry i = sum over the ring cells K of |det J_K| sum_q w_q phi_a(x_q) f_K(q), a = local index of node i in K: next to the ring
+// the plan holds, per ring position, the cell and that local index (cells[s][r] = cell << 2 | a; 24 B per row for rings of six),
+// and the kernel reads the cell's record of source values (one 32-byte sector for the default rule).  One thread per row, one
+// coalesced store per row, no atomics, fixed order of additions (ring order).  Against the two-pass scheme (assemble.cu), which
+// moves every element-vector entry through L2 by a scattered 8-byte store, at 1.0e8 triangles.
+__global__ void k_load_fan_cells(int64_t n_rows, int W, const int32_t* __restrict__ adj_ptr, const uint32_t* __restrict__ adj,
+                                 const uint32_t* __restrict__ cell_nodes, const uint8_t* __restrict__ info, uint32_t* __restrict__ cells) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  uint32_t ring[kMaxFan + 1], item[kMaxFan + 1];
+  int len = 0;
+  bool closed = false;
+  const int32_t it0 = adj_ptr[r];
+  const int m = adj_ptr[r + 1] - it0;
+  const bool planned = info[r] < 2 && m >= 1 && m <= W;
+  if (planned) build_ring(static_cast<int32_t>(r), m, adj, it0, cell_nodes, ring, len, closed, item);
+  for (int s = 0; s < W; ++s)
+    cells[static_cast<int64_t>(s) * n_rows + r] = (planned && s < m) ? (((item[s] >> 4) << 2) | (item[s] & 3U)) : kNil;
+}
+
+struct LoadSource {
+  const double* data;  // [n_cells][stride]
+  int stride;          // 1: one value per cell (nq entries of w below are then summed on the host into w[a][0])
+  int nq;
+  double w[3][4];      // w_q phi_a(x_q) of the rule in use
+};
+
+template <int W, bool COMPACT>
+__global__ void __launch_bounds__(128, 6) k_load_p1_fan_src(int n_rows, const void* __restrict__ nbr_any, const uint8_t* __restrict__ info,
+                                                          const uint32_t* __restrict__ cells, const double* __restrict__ node_coords,
+                                                          LoadSource S, double beta, double* __restrict__ vec) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const uint32_t* nbr = static_cast<const uint32_t*>(nbr_any);
+  const int16_t* nbr16 = static_cast<const int16_t*>(nbr_any);
+  const int inf = __ldg(info + r);
+  if (inf == 2) return;  // computed by the generic kernel
+  int32_t nid[W];
+  uint32_t cw[W];
+#pragma unroll
+  for (int s = 0; s < W; ++s) {
+    if (COMPACT) {
+      const int d = __ldg(nbr16 + static_cast<size_t>(s) * n_rows + r);
+      nid[s] = d == 0 ? -1 : r + d;
+    } else {
+      const uint32_t u = __ldg(nbr + static_cast<size_t>(s) * n_rows + r);
+      nid[s] = u == kNil ? -1 : static_cast<int32_t>(u);
+    }
+    cw[s] = __ldg(cells + static_cast<size_t>(s) * n_rows + r);
+  }
+  const double2* nc = reinterpret_cast<const double2*>(node_coords);
+  const double2 xi = __ldg(nc + r);
+  double dx[W], dy[W];
+#pragma unroll
+  for (int s = 0; s < W; ++s) {
+    const double2 p = __ldg(nc + (nid[s] >= 0 ? nid[s] : r));
+    dx[s] = p.x - xi.x;
+    dy[s] = p.y - xi.y;
+  }
+  double sum = 0.0;
+#pragma unroll
+  for (int s = 0; s < W; ++s) {
+    if (cw[s] != kNil) {  // cell s lies between ring[s] and ring[s + 1] (ring[0] for the cell that closes the ring)
+      const int u = (s + 1 < W && nid[s + 1 < W ? s + 1 : 0] >= 0) ? s + 1 : 0;
+      const double det = fabs(dx[s] * dy[u] - dy[s] * dx[u]);
+      const int a = static_cast<int>(cw[s] & 3U);
+      const double* f = S.data + static_cast<size_t>(cw[s] >> 2) * S.stride;
+      double e;
+      if (S.stride == 1) {
+        e = S.w[a][0] * __ldg(f);
+      } else {
+        e = 0.0;
+        for (int q = 0; q < S.nq; ++q) e += S.w[a][q] * __ldg(f + q);
+      }
+      sum += det * e;
+    }
+  }
+  vec[r] = beta == 0.0 ? sum : fma(beta, vec[r], sum);
+}
+
 }  // namespace
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
@@ -732,8 +816,12 @@ int p1_fan_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p
 
 // Load vector of FeLagrangeO1Tria with a constant source on the vertex rings.  *handled = 1 if the call was served here
 // (plan applicable); irregular rows (not a single fan) are returned in the dofmap's lv_irregular list for the generic kernel.
-int p1_load_fan(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* dc, double c, double beta, double* d_vec, int* handled) {
+// src_data != nullptr: source tabulated per cell (src_stride 1) or per quadrature point (src_stride >= nq), wtab = [3][nq] w_q phi_a(x_q);
+// c is then unused.
+int p1_load_fan(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* dc, double c, double beta, double* d_vec, int* handled,
+                const double* src_data, int src_stride, int nq, const double* wtab) {
   *handled = 0;
+  if (src_data != nullptr && (nq < 1 || nq > 4)) return LFGPU_OK;
   lfgpu_dofmap* d = const_cast<lfgpu_dofmap*>(dc);
   if (d->lv_state == 0) {
     d->lv_state = -1;
@@ -828,7 +916,38 @@ int p1_load_fan(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* dc, 
   const int n = static_cast<int>(d->n_dofs);
   const unsigned grid = static_cast<unsigned>(cdiv(n, threads));
   const int ipf = static_cast<int>((static_cast<int64_t>(ctx->sm_count) * 8 * threads) & ~static_cast<int64_t>(127));
-  if (d->lv_nbr16 != nullptr) {
+  if (src_data != nullptr) {
+    if (d->lv_cells == nullptr) {  // cell and local index per ring position, built when a tabulated source is first used
+      LFGPU_CUDA_CHECK(ctx, cudaMalloc(&d->lv_cells, sizeof(uint32_t) * (static_cast<size_t>(d->lv_w) * n + 128)));
+      // the ring ids as 32-bit words are gone if the compact form was adopted; the rings are rebuilt from the adjacency either way
+      k_load_fan_cells<<<static_cast<unsigned>(cdiv(n, 256)), 256, 0, ctx->stream>>>(n, d->lv_w, d->g_ptr, d->g_items, mesh->cell_nodes, d->lv_info,
+                                                                                    d->lv_cells);
+      LFGPU_LAUNCH_CHECK(ctx);
+    }
+    LoadSource S;
+    S.data = src_data;
+    S.stride = src_stride;
+    S.nq = nq;
+    for (int a = 0; a < 3; ++a)
+      for (int q = 0; q < 4; ++q) S.w[a][q] = q < nq ? wtab[a * nq + q] : 0.0;
+    if (src_stride == 1) {
+      for (int a = 0; a < 3; ++a) {
+        double t = 0.0;
+        for (int q = 0; q < nq; ++q) t += wtab[a * nq + q];
+        S.w[a][0] = t;
+      }
+    }
+    if (d->lv_nbr16 != nullptr) {
+      k_load_p1_fan_src<6, true><<<grid, threads, 0, ctx->stream>>>(n, d->lv_nbr16, d->lv_info, d->lv_cells, mesh->node_coords, S, beta, d_vec);
+    } else {
+      switch (d->lv_w) {
+        case 6: k_load_p1_fan_src<6, false><<<grid, threads, 0, ctx->stream>>>(n, d->lv_nbr, d->lv_info, d->lv_cells, mesh->node_coords, S, beta, d_vec); break;
+        case 8: k_load_p1_fan_src<8, false><<<grid, threads, 0, ctx->stream>>>(n, d->lv_nbr, d->lv_info, d->lv_cells, mesh->node_coords, S, beta, d_vec); break;
+        case 10: k_load_p1_fan_src<10, false><<<grid, threads, 0, ctx->stream>>>(n, d->lv_nbr, d->lv_info, d->lv_cells, mesh->node_coords, S, beta, d_vec); break;
+        default: k_load_p1_fan_src<12, false><<<grid, threads, 0, ctx->stream>>>(n, d->lv_nbr, d->lv_info, d->lv_cells, mesh->node_coords, S, beta, d_vec); break;
+      }
+    }
+  } else if (d->lv_nbr16 != nullptr) {
     k_load_p1_fan<6, true><<<grid, threads, 0, ctx->stream>>>(n, d->lv_nbr16, d->lv_info, mesh->node_coords, ipf, c, beta, d_vec);
   } else {
     switch (d->lv_w) {

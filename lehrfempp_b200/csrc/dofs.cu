@@ -313,6 +313,7 @@ void lfgpu_dofmap_destroy(lfgpu_dofmap* d) {
   cudaFree(d->lv_nbr16);
   cudaFree(d->lv_info);
   cudaFree(d->lv_irregular);
+  cudaFree(d->lv_cells);
   cudaFree(d->lv_ev);
   cudaFree(d->lv_pos);
   delete d;

@@ -79,6 +79,7 @@ struct lfgpu_dofmap {
   uint32_t* lv_nbr = nullptr;      // [lv_w][n_dofs] ring node ids (0xFFFFFFFF = empty), or
   int16_t* lv_nbr16 = nullptr;     // [6][n_dofs] ring ids as offsets from the row id (0 = empty)
   uint8_t* lv_info = nullptr;      // [n_dofs] 0 open fan, 1 closed fan, 2 not a single fan (generic kernel), 3 no cells
+  uint32_t* lv_cells = nullptr;    // [lv_w][n_dofs] cell << 2 | local index of the row's node, per ring position (tabulated sources)
   int32_t* lv_irregular = nullptr;
   int64_t n_lv_irregular = 0;
   // two-pass load vector (assemble.cu: k_load_positions): lv_pos [n_cells][lv_ev_stride] = index of (cell, a) in g_items,
@@ -279,7 +280,8 @@ int p1h_launch(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_pattern* p, c
                const lfgpu_coeff* gamma, const uint8_t* active, double beta, const int32_t* row_list, int64_t n_rows, int64_t row0,
                double* d_values);
 // P1 load vector with a constant source on the vertex rings (assemble_p1.cu)
-int p1_load_fan(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* d, double c, double beta, double* d_vec, int* handled);
+int p1_load_fan(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* d, double c, double beta, double* d_vec, int* handled,
+                const double* src_data = nullptr, int src_stride = 0, int nq = 0, const double* wtab = nullptr);
 // P2 row kernels (assemble_p2.cu): k00 .. km = reference tensors of FeLagrangeO2Tria, [6 * 6] row-major each
 int queue_geometry_check(lfgpu_ctx* ctx, const lfgpu_mesh* mesh);
 int edge_node_order(lfgpu_ctx* ctx, int64_t nn, int64_t ne, int32_t* enb, uint32_t** new_id_out);
