@@ -604,7 +604,10 @@ __global__ void __launch_bounds__(kItemThreads, MINB > 0 ? MINB : (TENSOR_ONLY ?
 // load vector: one thread per cell, FP64 atomics (assembler.h:322-324)
 // STORE: entry b of the element vector goes to vec[dofs[cell * stride + b]] by a plain store -- first pass of the two-pass load vector:
 // `dofs` is then the position table of k_load_positions, `vec` the item-ordered array k_load_sum_items adds up
-template <int NSF, bool STORE = false>
+// NODAL: the source is interpolated from values at the mesh nodes (LFGPU_COEFF_NODAL) -- its own instantiation: carrying the node
+// numbers and the branch through the quadrature loop cost every other source 15 registers and half the resident blocks
+// (64 -> 79 registers; 2.76 -> 4.28 ms at 1.0e8 triangles)
+template <int NSF, bool STORE = false, bool NODAL = false>
 __global__ void __launch_bounds__(256) k_load_atomic(Tables hdr, const double* __restrict__ blob, MeshView mv, int64_t n_cells, int stride,
                                                      const int32_t* __restrict__ dofs, const uint8_t* __restrict__ nldof, DevCoeff f,
                                                      const uint8_t* __restrict__ active, double* __restrict__ vec, int* __restrict__ flags) {
@@ -635,7 +638,7 @@ __global__ void __launch_bounds__(256) k_load_atomic(Tables hdr, const double* _
   if (!g.quad) jacobian(g, 0.0, 0.0, j00, j01, j10, j11);
   for (int k = 0; k < T.nq; ++k) {
     if (g.quad) jacobian(g, T.qx[k], T.qy[k], j00, j01, j10, j11);
-    const double s = T.w[k] * fabs(j00 * j11 - j01 * j10) * eval_scalar(f, cell, k, g, T);
+    const double s = T.w[k] * fabs(j00 * j11 - j01 * j10) * (NODAL ? eval_nodal(f, g, T.qx[k], T.qy[k]) : eval_scalar(f, cell, k));
 #pragma unroll
     for (int b = 0; b < NSF; ++b) {
       if (b < T.nsf) acc[b] += s * T.phi[b * T.nq + k];
@@ -686,6 +689,7 @@ __global__ void __launch_bounds__(256) k_load_sum_items(int64_t n_dofs, const in
 // the entries phi_K[a] = sum_k w_k |det J_k| f(x_k) phi_a(x_k) in that order -- result[dof] += elem_vec[a] of
 // assembler.h:322-324 with the additions in the reference's order: no atomics, no zero-fill, bitwise repeatable.
 // Every cell is visited once per local dof; the load vector is a small part of the traffic of the path.
+template <bool NODAL>
 __global__ void __launch_bounds__(256) k_load_gather(Tables hdr, const double* __restrict__ blob, MeshView mv, int64_t n_dofs,
                                                      const int32_t* __restrict__ ptr, const uint32_t* __restrict__ items, DevCoeff f,
                                                      const uint8_t* __restrict__ active, double beta, double* __restrict__ vec,
@@ -714,7 +718,7 @@ __global__ void __launch_bounds__(256) k_load_gather(Tables hdr, const double* _
     double e = 0.0;
     for (int k = 0; k < T.nq; ++k) {
       if (g.quad) jacobian(g, T.qx[k], T.qy[k], j00, j01, j10, j11);
-      const double s = T.w[k] * fabs(j00 * j11 - j01 * j10) * eval_scalar(f, cell, k, g, T);
+      const double s = T.w[k] * fabs(j00 * j11 - j01 * j10) * (NODAL ? eval_nodal(f, g, T.qx[k], T.qy[k]) : eval_scalar(f, cell, k));
       e += s * T.phi[a * T.nq + k];
     }
     sum += e;
@@ -1189,7 +1193,8 @@ int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofm
     if ((rc = dofmap_gather_plan(ctx, dofmap)) != LFGPU_OK) return rc;
     const MeshView mvg{mesh->node_coords, mesh->cell_nodes, mesh->cell_coords};
     const size_t tbg = sizeof(double) * ((ht.hdr.total + 1) & ~1);
-    k_load_gather<<<static_cast<unsigned>(cdiv(dofmap->n_dofs, 256)), 256, tbg, ctx->stream>>>(
+    auto kg = df.kind == LFGPU_COEFF_NODAL ? k_load_gather<true> : k_load_gather<false>;
+    kg<<<static_cast<unsigned>(cdiv(dofmap->n_dofs, 256)), 256, tbg, ctx->stream>>>(
         ht.hdr, blob.d, mvg, dofmap->n_dofs, dofmap->g_ptr, dofmap->g_items, df, active, beta, d_vec, d_flags, nullptr);
     LFGPU_LAUNCH_CHECK(ctx);
     return LFGPU_OK;
@@ -1220,7 +1225,7 @@ int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofm
         if (dofmap->n_lv_irregular > 0) {
           const MeshView mvg{mesh->node_coords, mesh->cell_nodes, mesh->cell_coords};
           const size_t tbg = sizeof(double) * ((ht.hdr.total + 1) & ~1);
-          k_load_gather<<<static_cast<unsigned>(cdiv(dofmap->n_lv_irregular, 256)), 256, tbg, ctx->stream>>>(
+          k_load_gather<false><<<static_cast<unsigned>(cdiv(dofmap->n_lv_irregular, 256)), 256, tbg, ctx->stream>>>(
               ht.hdr, blob.d, mvg, dofmap->n_lv_irregular, dofmap->g_ptr, dofmap->g_items, df, active, beta, d_vec, d_flags,
               dofmap->lv_irregular);
           LFGPU_LAUNCH_CHECK(ctx);
@@ -1256,8 +1261,8 @@ int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofm
       dmut->lv_ev_stride = nsf;
     }
 #define LFGPU_LOAD_EV(NSF)                                                                                                   \
-  k_load_atomic<NSF, true><<<grid, 256, tab_bytes, ctx->stream>>>(ht.hdr, blob.d, mv, mesh->n_cells, NSF, dmut->lv_pos, dofmap->n_ldof, df, \
-                                                                  active, dmut->lv_ev, d_flags)
+  (df.kind == LFGPU_COEFF_NODAL ? k_load_atomic<NSF, true, true> : k_load_atomic<NSF, true, false>)                          \
+      <<<grid, 256, tab_bytes, ctx->stream>>>(ht.hdr, blob.d, mv, mesh->n_cells, NSF, dmut->lv_pos, dofmap->n_ldof, df, active, dmut->lv_ev, d_flags)
     switch (nsf) {
       case 3: LFGPU_LOAD_EV(3); break;
       case 4: LFGPU_LOAD_EV(4); break;
@@ -1279,8 +1284,8 @@ int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofm
     LFGPU_LAUNCH_CHECK(ctx);
   }
 #define LFGPU_LOAD(NSF)                                                                                                         \
-  k_load_atomic<NSF><<<grid, 256, tab_bytes, ctx->stream>>>(ht.hdr, blob.d, mv, mesh->n_cells, dofmap->stride, dofmap->cell_dofs, \
-                                                            dofmap->n_ldof, df, active, d_vec, d_flags)
+  (df.kind == LFGPU_COEFF_NODAL ? k_load_atomic<NSF, false, true> : k_load_atomic<NSF, false, false>)                           \
+      <<<grid, 256, tab_bytes, ctx->stream>>>(ht.hdr, blob.d, mv, mesh->n_cells, dofmap->stride, dofmap->cell_dofs, dofmap->n_ldof, df, active, d_vec, d_flags)
   switch (degree) {
     case 1: if (has_quads) { LFGPU_LOAD(4); } else { LFGPU_LOAD(3); } break;
     case 2: if (has_quads) { LFGPU_LOAD(9); } else { LFGPU_LOAD(6); } break;
