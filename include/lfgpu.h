@@ -207,7 +207,9 @@ typedef struct {
 #define LFGPU_COEFF_NODAL 5        /* data[n_nodes]: a continuous piecewise (bi)linear function given by its values at the mesh
                                       nodes (lf::fe::MeshFunctionFE of a FeSpaceLagrangeO1 function, fe/mesh_function_fe.h),
                                       evaluated at the quadrature points with the cell's vertex shape functions; scalar.
-                                      8 B per node of traffic instead of 8 B per quadrature point.  Cell terms only.        */
+                                      The caller hands over 8 B per node; the library tabulates the values at the quadrature
+                                      points on the device (one small kernel per call) and runs the PER_QP kernels, the fast
+                                      P1 row kernel included.  Cell terms only.                                            */
 typedef struct {
   int kind;
   double c[4];

@@ -77,7 +77,6 @@ struct MeshView {
 
 struct CellGeom {
   double x[4], y[4];
-  uint32_t v[4];  // node indices (slot 3 = LFGPU_IDX_NIL for a triangle)
   bool quad;
 };
 
@@ -85,7 +84,6 @@ __device__ __forceinline__ CellGeom load_geom(const MeshView& mv, int64_t cell) 
   CellGeom g;
   const uint4 v = __ldg(reinterpret_cast<const uint4*>(mv.cell_nodes) + cell);
   g.quad = (v.w != LFGPU_IDX_NIL);
-  g.v[0] = v.x; g.v[1] = v.y; g.v[2] = v.z; g.v[3] = v.w;
   if (mv.cell_coords != nullptr) {
     const double2* cc = reinterpret_cast<const double2*>(mv.cell_coords) + 4 * cell;
 #pragma unroll
@@ -149,9 +147,6 @@ __device__ __forceinline__ void eval_alpha(const DevCoeff& A, int64_t cell, int 
     case LFGPU_COEFF_PER_QP:
       a00 = a11 = __ldg(A.data + cell * A.stride + k); a01 = a10 = 0.0;
       break;
-    case LFGPU_COEFF_NODAL:  // the caller overwrites a00 = a11 with the interpolated value (element_row)
-      a00 = a11 = 0.0; a01 = a10 = 0.0;
-      break;
     default: {  // PER_QP_2X2
       const double* p = A.data + (cell * A.stride + k) * 4;
       a00 = __ldg(p); a01 = __ldg(p + 1); a10 = __ldg(p + 2); a11 = __ldg(p + 3);
@@ -163,24 +158,12 @@ __device__ __forceinline__ void eval_alpha(const DevCoeff& A, int64_t cell, int 
     a10 = t;
   }
 }
-// LFGPU_COEFF_NODAL: sum over the cell's vertices of N_a(xhat) data[node_a], N_a = FeLagrangeO1Tria / Quad (lagr_fe.h:110-128,
-// 218-240) at the reference point (x0, x1) of quadrature point k
-__device__ __forceinline__ double eval_nodal(const DevCoeff& G, const CellGeom& g, double x0, double x1) {
-  if (!g.quad) return (1.0 - x0 - x1) * __ldg(G.data + g.v[0]) + x0 * __ldg(G.data + g.v[1]) + x1 * __ldg(G.data + g.v[2]);
-  return (1.0 - x0) * (1.0 - x1) * __ldg(G.data + g.v[0]) + x0 * (1.0 - x1) * __ldg(G.data + g.v[1]) + x0 * x1 * __ldg(G.data + g.v[2]) +
-         (1.0 - x0) * x1 * __ldg(G.data + g.v[3]);
-}
 __device__ __forceinline__ double eval_scalar(const DevCoeff& G, int64_t cell, int k) {
   switch (G.kind) {
     case LFGPU_COEFF_CONST: return G.c[0];
     case LFGPU_COEFF_PER_CELL: return __ldg(G.data + cell);
     default: return __ldg(G.data + cell * G.stride + k);  // PER_QP
   }
-}
-// with the cell at hand (needed by LFGPU_COEFF_NODAL)
-__device__ __forceinline__ double eval_scalar(const DevCoeff& G, int64_t cell, int k, const CellGeom& g, const TabView& T) {
-  if (G.kind == LFGPU_COEFF_NODAL) return eval_nodal(G, g, T.qx[k], T.qy[k]);
-  return eval_scalar(G, cell, k);
 }
 __device__ __forceinline__ bool cellwise_const(const DevCoeff& c) { return c.kind <= LFGPU_COEFF_PER_CELL; }
 __device__ __forceinline__ double fast_rcp(double x);
@@ -287,13 +270,12 @@ __device__ __forceinline__ void element_row(const CellGeom& g, const TabView& T,
     const double i00 = j11 * idet, i01 = -j01 * idet, i10 = -j10 * idet, i11 = j00 * idet;
     double a00, a01, a10, a11;
     eval_alpha(alpha, cell, k, transpose_alpha, a00, a01, a10, a11);
-    if (alpha.kind == LFGPU_COEFF_NODAL) a00 = a11 = eval_nodal(alpha, g, T.qx[k], T.qy[k]);
     const double gxa = T.gx[a * nq + k], gya = T.gy[a * nq + k];
     // G_a = Jinv^T ghat_a ; u = A G_a ; s = wd * Jinv u
     const double Gx = i00 * gxa + i10 * gya, Gy = i01 * gxa + i11 * gya;
     const double ux = a00 * Gx + a01 * Gy, uy = a10 * Gx + a11 * Gy;
     const double sx = wd * (i00 * ux + i01 * uy), sy = wd * (i10 * ux + i11 * uy);
-    const double mm = wd * eval_scalar(gamma, cell, k, g, T) * T.phi[a * nq + k];
+    const double mm = wd * eval_scalar(gamma, cell, k) * T.phi[a * nq + k];
 #pragma unroll
     for (int b = 0; b < NSF; ++b) {
       if (b < nsf) acc[b] += sx * T.gx[b * nq + k] + sy * T.gy[b * nq + k] + mm * T.phi[b * nq + k];
@@ -604,10 +586,7 @@ __global__ void __launch_bounds__(kItemThreads, MINB > 0 ? MINB : (TENSOR_ONLY ?
 // load vector: one thread per cell, FP64 atomics (assembler.h:322-324)
 // STORE: entry b of the element vector goes to vec[dofs[cell * stride + b]] by a plain store -- first pass of the two-pass load vector:
 // `dofs` is then the position table of k_load_positions, `vec` the item-ordered array k_load_sum_items adds up
-// NODAL: the source is interpolated from values at the mesh nodes (LFGPU_COEFF_NODAL) -- its own instantiation: carrying the node
-// numbers and the branch through the quadrature loop cost every other source 15 registers and half the resident blocks
-// (64 -> 79 registers; 2.76 -> 4.28 ms at 1.0e8 triangles)
-template <int NSF, bool STORE = false, bool NODAL = false>
+template <int NSF, bool STORE = false>
 __global__ void __launch_bounds__(256) k_load_atomic(Tables hdr, const double* __restrict__ blob, MeshView mv, int64_t n_cells, int stride,
                                                      const int32_t* __restrict__ dofs, const uint8_t* __restrict__ nldof, DevCoeff f,
                                                      const uint8_t* __restrict__ active, double* __restrict__ vec, int* __restrict__ flags) {
@@ -638,7 +617,7 @@ __global__ void __launch_bounds__(256) k_load_atomic(Tables hdr, const double* _
   if (!g.quad) jacobian(g, 0.0, 0.0, j00, j01, j10, j11);
   for (int k = 0; k < T.nq; ++k) {
     if (g.quad) jacobian(g, T.qx[k], T.qy[k], j00, j01, j10, j11);
-    const double s = T.w[k] * fabs(j00 * j11 - j01 * j10) * (NODAL ? eval_nodal(f, g, T.qx[k], T.qy[k]) : eval_scalar(f, cell, k));
+    const double s = T.w[k] * fabs(j00 * j11 - j01 * j10) * eval_scalar(f, cell, k);
 #pragma unroll
     for (int b = 0; b < NSF; ++b) {
       if (b < T.nsf) acc[b] += s * T.phi[b * T.nq + k];
@@ -689,7 +668,6 @@ __global__ void __launch_bounds__(256) k_load_sum_items(int64_t n_dofs, const in
 // the entries phi_K[a] = sum_k w_k |det J_k| f(x_k) phi_a(x_k) in that order -- result[dof] += elem_vec[a] of
 // assembler.h:322-324 with the additions in the reference's order: no atomics, no zero-fill, bitwise repeatable.
 // Every cell is visited once per local dof; the load vector is a small part of the traffic of the path.
-template <bool NODAL>
 __global__ void __launch_bounds__(256) k_load_gather(Tables hdr, const double* __restrict__ blob, MeshView mv, int64_t n_dofs,
                                                      const int32_t* __restrict__ ptr, const uint32_t* __restrict__ items, DevCoeff f,
                                                      const uint8_t* __restrict__ active, double beta, double* __restrict__ vec,
@@ -718,12 +696,40 @@ __global__ void __launch_bounds__(256) k_load_gather(Tables hdr, const double* _
     double e = 0.0;
     for (int k = 0; k < T.nq; ++k) {
       if (g.quad) jacobian(g, T.qx[k], T.qy[k], j00, j01, j10, j11);
-      const double s = T.w[k] * fabs(j00 * j11 - j01 * j10) * (NODAL ? eval_nodal(f, g, T.qx[k], T.qy[k]) : eval_scalar(f, cell, k));
+      const double s = T.w[k] * fabs(j00 * j11 - j01 * j10) * eval_scalar(f, cell, k);
       e += s * T.phi[a * T.nq + k];
     }
     sum += e;
   }
   vec[r] = sum;
+}
+
+// LFGPU_COEFF_NODAL (values at the mesh nodes, interpolated by the P1 shape functions: sum over the cell's vertices of N_a(xhat)
+// data[node_a], N_a = FeLagrangeO1Tria / Quad, lagr_fe.h:110-128, 258-284 -- what MeshFunctionFE of a P1 space evaluates to) is turned
+// into a per-point table on the device before the numeric kernels run: out[cell * stride + k] = value at quadrature point k.  A
+// first version evaluated it inside the quadrature loops; carrying the node numbers and the branch cost EVERY coefficient kind
+// registers (generic load kernels 64 -> 79, i.e. 2 resident blocks instead of 4: 2.76 -> 4.28 ms at 1.0e8 triangles; up to 130
+// bytes more spills in the generic matrix kernels).
+__global__ void k_nodal_tabulate(Tables hdr, const double* __restrict__ blob, const uint32_t* __restrict__ cell_nodes, int64_t n_cells, int stride,
+                                 const double* __restrict__ nodal, double* __restrict__ out) {
+  extern __shared__ double smem[];
+  TabView tt, tq;
+  load_tables(hdr, blob, smem, tt, tq);
+  const int64_t cell = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (cell >= n_cells) return;
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(cell_nodes) + cell);
+  const bool quad = v.w != LFGPU_IDX_NIL;
+  const TabView& T = quad ? tq : tt;
+  const double f0 = __ldg(nodal + v.x), f1 = __ldg(nodal + v.y), f2 = __ldg(nodal + v.z), f3 = quad ? __ldg(nodal + v.w) : 0.0;
+  for (int k = 0; k < stride; ++k) {
+    double val = 0.0;
+    if (k < T.nq) {
+      const double x0 = T.qx[k], x1 = T.qy[k];
+      val = quad ? (1.0 - x0) * (1.0 - x1) * f0 + x0 * (1.0 - x1) * f1 + x0 * x1 * f2 + (1.0 - x0) * x1 * f3
+                 : (1.0 - x0 - x1) * f0 + x0 * f1 + x1 * f2;
+    }
+    out[cell * stride + k] = val;
+  }
 }
 
 __global__ void k_qp_coords(Tables hdr, const double* __restrict__ blob, MeshView mv, int64_t n_cells, int nq_stride, double* __restrict__ out) {
@@ -863,6 +869,34 @@ int upload_blob(lfgpu_ctx* ctx, const HostTables& ht, DeviceBlob* b) {
 int check_rules(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const HostTables& ht) {
   if ((mesh->n_tria > 0 && ht.hdr.nsf[0] == 0) || (mesh->n_quad > 0 && ht.hdr.nsf[1] == 0))
     LFGPU_FAIL(ctx, LFGPU_ERR_MISSING_RULE, "No local shape function information or no quadrature rule for a reference element type present in the mesh");
+  return LFGPU_OK;
+}
+
+// LFGPU_COEFF_NODAL -> LFGPU_COEFF_PER_QP: tabulate the interpolated values at the quadrature points of the rule in use into a
+// buffer owned by the context (slot 0: diffusion / source, slot 1: reaction), see k_nodal_tabulate.  Stream-ordered: the table is
+// written right before the kernels of this call read it.
+int resolve_nodal(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const HostTables& ht, DevCoeff* c, int slot) {
+  if (c->kind != LFGPU_COEFF_NODAL) return LFGPU_OK;
+  DeviceBlob blob;
+  int rc = upload_blob(ctx, ht, &blob);
+  if (rc != LFGPU_OK) return rc;
+  const int stride = std::max(1, std::max(ht.hdr.nq[0], ht.hdr.nq[1]));
+  const size_t need = static_cast<size_t>(mesh->n_cells) * stride;
+  if (ctx->nodal_cap[slot] < need) {
+    LFGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));  // an earlier call may still read the old table
+    cudaFree(ctx->nodal_tab[slot]);
+    ctx->nodal_tab[slot] = nullptr;
+    ctx->nodal_cap[slot] = 0;
+    LFGPU_CUDA_CHECK(ctx, cudaMalloc(&ctx->nodal_tab[slot], sizeof(double) * std::max<size_t>(need, 1)));
+    ctx->nodal_cap[slot] = need;
+  }
+  const size_t tab_bytes = sizeof(double) * ((ht.hdr.total + 1) & ~1);
+  k_nodal_tabulate<<<static_cast<unsigned>(cdiv(mesh->n_cells, 256)), 256, tab_bytes, ctx->stream>>>(ht.hdr, blob.d, mesh->cell_nodes, mesh->n_cells,
+                                                                                                stride, c->data, ctx->nodal_tab[slot]);
+  LFGPU_LAUNCH_CHECK(ctx);
+  c->kind = LFGPU_COEFF_PER_QP;
+  c->data = ctx->nodal_tab[slot];
+  c->stride = stride;
   return LFGPU_OK;
 }
 
@@ -1023,6 +1057,10 @@ int lfgpu::assemble_rd_impl(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_
   if ((rc = check_coeff(ctx, alpha, true, ht, &da)) != LFGPU_OK) return rc;
   if ((rc = check_coeff(ctx, gamma, false, ht, &dg)) != LFGPU_OK) return rc;
   if ((rc = check_rules(ctx, mesh, ht)) != LFGPU_OK) return rc;
+  if (fan_query == nullptr) {  // (a query launches nothing; a node-interpolated coefficient never runs in the fan kernel)
+    if ((rc = resolve_nodal(ctx, mesh, ht, &da, 0)) != LFGPU_OK) return rc;
+    if ((rc = resolve_nodal(ctx, mesh, ht, &dg, 1)) != LFGPU_OK) return rc;
+  }
   if (algo == LFGPU_ALGO_AUTO || algo == LFGPU_ALGO_FAN) {
     // P1 vertex-fan kernel: triangles only, constant coefficients, every cell active, square nodal dof table
     bool ok = degree == 1 && active == nullptr && da.kind <= LFGPU_COEFF_CONST_2X2 && dg.kind == LFGPU_COEFF_CONST &&
@@ -1066,7 +1104,7 @@ int lfgpu::assemble_rd_impl(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_
     // P1 row kernel (assemble_p1h.cu): quadrilaterals / hybrid meshes, coefficients per cell or per quadrature point, activity
     // masks, cell corners that are not bitwise the node positions; rules invariant under the rotations of the reference cell
     static const bool p1h_env = [] { const char* e = std::getenv("LFGPU_P1_ROWS"); return e == nullptr || e[0] != '0'; }();
-    if (degree == 1 && fan_query == nullptr && p1h_env && da.kind != LFGPU_COEFF_NODAL && dg.kind != LFGPU_COEFF_NODAL) {
+    if (degree == 1 && fan_query == nullptr && p1h_env) {
       FeTable ft, fq;
       std::string err;
       const bool dflt = qr_tria == nullptr && qr_quad == nullptr;
@@ -1185,6 +1223,7 @@ int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofm
   DevCoeff df;
   if ((rc = check_coeff(ctx, f, false, ht, &df)) != LFGPU_OK) return rc;
   if ((rc = check_rules(ctx, mesh, ht)) != LFGPU_OK) return rc;
+  if ((rc = resolve_nodal(ctx, mesh, ht, &df, 0)) != LFGPU_OK) return rc;
   DeviceBlob blob;
   if ((rc = upload_blob(ctx, ht, &blob)) != LFGPU_OK) return rc;
   int* d_flags = reinterpret_cast<int*>(static_cast<char*>(ctx->d_scratch) + 128);
@@ -1193,8 +1232,7 @@ int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofm
     if ((rc = dofmap_gather_plan(ctx, dofmap)) != LFGPU_OK) return rc;
     const MeshView mvg{mesh->node_coords, mesh->cell_nodes, mesh->cell_coords};
     const size_t tbg = sizeof(double) * ((ht.hdr.total + 1) & ~1);
-    auto kg = df.kind == LFGPU_COEFF_NODAL ? k_load_gather<true> : k_load_gather<false>;
-    kg<<<static_cast<unsigned>(cdiv(dofmap->n_dofs, 256)), 256, tbg, ctx->stream>>>(
+    k_load_gather<<<static_cast<unsigned>(cdiv(dofmap->n_dofs, 256)), 256, tbg, ctx->stream>>>(
         ht.hdr, blob.d, mvg, dofmap->n_dofs, dofmap->g_ptr, dofmap->g_items, df, active, beta, d_vec, d_flags, nullptr);
     LFGPU_LAUNCH_CHECK(ctx);
     return LFGPU_OK;
@@ -1225,7 +1263,7 @@ int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofm
         if (dofmap->n_lv_irregular > 0) {
           const MeshView mvg{mesh->node_coords, mesh->cell_nodes, mesh->cell_coords};
           const size_t tbg = sizeof(double) * ((ht.hdr.total + 1) & ~1);
-          k_load_gather<false><<<static_cast<unsigned>(cdiv(dofmap->n_lv_irregular, 256)), 256, tbg, ctx->stream>>>(
+          k_load_gather<<<static_cast<unsigned>(cdiv(dofmap->n_lv_irregular, 256)), 256, tbg, ctx->stream>>>(
               ht.hdr, blob.d, mvg, dofmap->n_lv_irregular, dofmap->g_ptr, dofmap->g_items, df, active, beta, d_vec, d_flags,
               dofmap->lv_irregular);
           LFGPU_LAUNCH_CHECK(ctx);
@@ -1261,8 +1299,7 @@ int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofm
       dmut->lv_ev_stride = nsf;
     }
 #define LFGPU_LOAD_EV(NSF)                                                                                                   \
-  (df.kind == LFGPU_COEFF_NODAL ? k_load_atomic<NSF, true, true> : k_load_atomic<NSF, true, false>)                          \
-      <<<grid, 256, tab_bytes, ctx->stream>>>(ht.hdr, blob.d, mv, mesh->n_cells, NSF, dmut->lv_pos, dofmap->n_ldof, df, active, dmut->lv_ev, d_flags)
+  k_load_atomic<NSF, true><<<grid, 256, tab_bytes, ctx->stream>>>(ht.hdr, blob.d, mv, mesh->n_cells, NSF, dmut->lv_pos, dofmap->n_ldof, df, active, dmut->lv_ev, d_flags)
     switch (nsf) {
       case 3: LFGPU_LOAD_EV(3); break;
       case 4: LFGPU_LOAD_EV(4); break;
@@ -1284,8 +1321,7 @@ int lfgpu_assemble_load(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofm
     LFGPU_LAUNCH_CHECK(ctx);
   }
 #define LFGPU_LOAD(NSF)                                                                                                         \
-  (df.kind == LFGPU_COEFF_NODAL ? k_load_atomic<NSF, false, true> : k_load_atomic<NSF, false, false>)                           \
-      <<<grid, 256, tab_bytes, ctx->stream>>>(ht.hdr, blob.d, mv, mesh->n_cells, dofmap->stride, dofmap->cell_dofs, dofmap->n_ldof, df, active, d_vec, d_flags)
+  k_load_atomic<NSF, false><<<grid, 256, tab_bytes, ctx->stream>>>(ht.hdr, blob.d, mv, mesh->n_cells, dofmap->stride, dofmap->cell_dofs, dofmap->n_ldof, df, active, d_vec, d_flags)
   switch (degree) {
     case 1: if (has_quads) { LFGPU_LOAD(4); } else { LFGPU_LOAD(3); } break;
     case 2: if (has_quads) { LFGPU_LOAD(9); } else { LFGPU_LOAD(6); } break;

@@ -58,6 +58,8 @@ void lfgpu_ctx_destroy(lfgpu_ctx* ctx) {
   for (cudaEvent_t ev : ctx->pipe_events) cudaEventDestroy(ev);
   if (ctx->s_h2d != nullptr) cudaStreamDestroy(ctx->s_h2d);
   if (ctx->s_d2h != nullptr) cudaStreamDestroy(ctx->s_d2h);
+  cudaFree(ctx->nodal_tab[0]);
+  cudaFree(ctx->nodal_tab[1]);
   cudaFree(ctx->d_scratch);
   cudaStreamDestroy(ctx->stream);
   delete ctx;

@@ -28,6 +28,8 @@ struct lfgpu_ctx {
   int64_t launches = 0;
   std::string last_error;
   void* d_scratch = nullptr;  // small device scratch (flags, counters)
+  double* nodal_tab[2] = {nullptr, nullptr};  // per-point tables of node-interpolated coefficients (assemble.cu: resolve_nodal)
+  size_t nodal_cap[2] = {0, 0};
   bool geom_check_pending = false;  // a coordinate update queued a degeneracy check whose flag (scratch + 1024) is read at the next synchronize
   struct TableEntry {
     std::vector<double> host;
