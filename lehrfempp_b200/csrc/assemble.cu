@@ -1057,9 +1057,20 @@ int lfgpu::assemble_rd_impl(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_
   if ((rc = check_coeff(ctx, alpha, true, ht, &da)) != LFGPU_OK) return rc;
   if ((rc = check_coeff(ctx, gamma, false, ht, &dg)) != LFGPU_OK) return rc;
   if ((rc = check_rules(ctx, mesh, ht)) != LFGPU_OK) return rc;
+  lfgpu_coeff ra = *alpha, rg = *gamma;  // what the row kernels and the calls for irregular rows below are handed
   if (fan_query == nullptr) {  // (a query launches nothing; a node-interpolated coefficient never runs in the fan kernel)
     if ((rc = resolve_nodal(ctx, mesh, ht, &da, 0)) != LFGPU_OK) return rc;
     if ((rc = resolve_nodal(ctx, mesh, ht, &dg, 1)) != LFGPU_OK) return rc;
+    if (alpha->kind == LFGPU_COEFF_NODAL) {
+      ra.kind = da.kind;
+      ra.data = da.data;
+      ra.stride = static_cast<int>(da.stride);
+    }
+    if (gamma->kind == LFGPU_COEFF_NODAL) {
+      rg.kind = dg.kind;
+      rg.data = dg.data;
+      rg.stride = static_cast<int>(dg.stride);
+    }
   }
   if (algo == LFGPU_ALGO_AUTO || algo == LFGPU_ALGO_FAN) {
     // P1 vertex-fan kernel: triangles only, constant coefficients, every cell active, square nodal dof table
@@ -1122,11 +1133,11 @@ int lfgpu::assemble_rd_impl(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_
         const auto& irr = p->p1h_irregular_host;
         const int64_t i0 = std::lower_bound(irr.begin(), irr.end(), r0) - irr.begin(), i1 = std::lower_bound(irr.begin(), irr.end(), r1) - irr.begin();
         if (i1 > i0) {
-          rc = lfgpu_assemble_reaction_diffusion_rows(ctx, mesh, p, degree, qr_tria, qr_quad, alpha, gamma, active, beta, d_values,
+          rc = lfgpu_assemble_reaction_diffusion_rows(ctx, mesh, p, degree, qr_tria, qr_quad, &ra, &rg, active, beta, d_values,
                                                       LFGPU_ALGO_GATHER, p->p1h_irregular + i0, i1 - i0);
           if (rc != LFGPU_OK) return rc;
         }
-        return p1h_launch(ctx, mesh, p, have_t ? &ft : nullptr, have_q ? &fq : nullptr, alpha, gamma, active, beta, d_row_list, n_rows, row0,
+        return p1h_launch(ctx, mesh, p, have_t ? &ft : nullptr, have_q ? &fq : nullptr, &ra, &rg, active, beta, d_row_list, n_rows, row0,
                           d_values);
       }
     }
