@@ -113,7 +113,8 @@ int lfgpu_mesh_download(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, uint8_t* cell_ty
                         uint32_t* cell_edges, int8_t* cell_edge_ori, uint32_t* edge_nodes, double* node_coords);
 /* replace the node positions (per-step input of a moving-mesh / re-assembly loop); host array [n_nodes][2].  The copy is
  * asynchronous on the ctx stream: a page-locked host buffer must stay valid until lfgpu_ctx_synchronize.  The new geometry is
- * checked like that of lfgpu_mesh_upload; a degenerate cell makes the NEXT lfgpu_ctx_synchronize return LFGPU_ERR_DEGENERATE. */
+ * checked like that of lfgpu_mesh_upload; a degenerate cell makes the NEXT lfgpu_ctx_synchronize return LFGPU_ERR_DEGENERATE.
+ * (The host-buffer assembly calls, which take the positions of the step as an argument, check them before they return.)          */
 int lfgpu_mesh_update_node_coords(lfgpu_ctx* ctx, lfgpu_mesh* mesh, const double* node_coords);
 void lfgpu_mesh_destroy(lfgpu_mesh* mesh);
 
@@ -402,7 +403,9 @@ int lfgpu_multi_part_sizes(const lfgpu_multi* m, int k, int64_t* n_rows, int64_t
  * [n_rows + 1], cols [nnz] (global inner index, ascending inside a row = the reference's pattern), values [nnz]; every output
  * nullable.  The blocks of all devices together are the matrix makeSparse() returns (assemble/coomatrix.h:172-180).             */
 int lfgpu_multi_part_download(lfgpu_multi* m, int k, int64_t* rows, int64_t* row_ptr, int32_t* cols, double* values);
-/* read-only device views used by the host-side partitioner: gather lists (items = cell << 4 | local index), mesh arrays */
+/* read-only device views used by the host-side partitioner: gather lists (items = cell << 4 | local index), mesh arrays.
+ * READ-ONLY: node positions change only through lfgpu_mesh_update_node_coords or the host-buffer assembly calls -- the row-kernel
+ * plans keep their own reordered copies of the positions and refresh them when those calls have moved the mesh's version counter. */
 const int32_t* lfgpu_pattern_adj_ptr_device(const lfgpu_pattern* p);
 const uint32_t* lfgpu_pattern_adj_device(const lfgpu_pattern* p);
 int64_t lfgpu_pattern_num_items(const lfgpu_pattern* p);
