@@ -25,3 +25,13 @@ def test_plan_variants(variant):
     env = dict(os.environ, **variant)
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "plan_variants_check.py")], capture_output=True, text=True, timeout=600, env=env)
     assert "PLAN_VARIANTS_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+LOAD_VARIANTS = [{}, {"LFGPU_LOAD_ROWORDER": "0"}, {"LFGPU_LOAD_FAN": "0"}, {"LFGPU_LOAD_FAN": "0", "LFGPU_LOAD_TWOPASS": "0"}]
+
+
+@pytest.mark.parametrize("variant", LOAD_VARIANTS, ids=lambda v: ",".join("%s=%s" % kv for kv in sorted(v.items())) or "defaults")
+def test_load_vector_variants(variant):
+    env = dict(os.environ, **variant)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "load_variants_check.py")], capture_output=True, text=True, timeout=600, env=env)
+    assert "LOAD_VARIANTS_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
