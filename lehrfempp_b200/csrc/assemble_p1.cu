@@ -605,7 +605,8 @@ struct LoadSource {
   const double* data;  // [n_cells][stride]
   int stride;          // 1: one value per cell (nq entries of w below are then summed on the host into w[a][0])
   int nq;
-  double w[3][4];      // w_q phi_a(x_q) of the rule in use
+  int vec4;            // stride == 4 and a 32-byte aligned table: one 256-bit load per record
+  double w[3][4];      // w_q phi_a(x_q) of the rule in use (zero beyond nq)
 };
 
 template <int W, bool COMPACT>
@@ -651,6 +652,10 @@ __global__ void __launch_bounds__(128, 6) k_load_p1_fan_src(int n_rows, const vo
       double e;
       if (S.stride == 1) {
         e = S.w[a][0] * __ldg(f);
+      } else if (S.vec4) {  // the cell's record in one 256-bit load (four 8-byte loads at a 32-byte lane stride touch every sector four times)
+        double f0, f1, f2, f3;
+        asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(f0), "=d"(f1), "=d"(f2), "=d"(f3) : "l"(f));
+        e = S.w[a][0] * f0 + (S.nq > 1 ? S.w[a][1] * f1 : 0.0) + (S.nq > 2 ? S.w[a][2] * f2 : 0.0) + (S.nq > 3 ? S.w[a][3] * f3 : 0.0);  // (entries beyond the rule's points are the caller's padding: never multiplied)
       } else {
         e = 0.0;
         for (int q = 0; q < S.nq; ++q) e += S.w[a][q] * __ldg(f + q);
@@ -741,6 +746,10 @@ __global__ void __launch_bounds__(128, 6) k_load_p1_fan_src_ordered(int n_rows, 
       double e;
       if (S.stride == 1) {
         e = S.w[a][0] * __ldg(f);
+      } else if (S.vec4) {  // the cell's record in one 256-bit load (four 8-byte loads at a 32-byte lane stride touch every sector four times)
+        double f0, f1, f2, f3;
+        asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(f0), "=d"(f1), "=d"(f2), "=d"(f3) : "l"(f));
+        e = S.w[a][0] * f0 + (S.nq > 1 ? S.w[a][1] * f1 : 0.0) + (S.nq > 2 ? S.w[a][2] * f2 : 0.0) + (S.nq > 3 ? S.w[a][3] * f3 : 0.0);  // (entries beyond the rule's points are the caller's padding: never multiplied)
       } else {
         e = 0.0;
         for (int q = 0; q < S.nq; ++q) e += S.w[a][q] * __ldg(f + q);
@@ -1018,6 +1027,7 @@ int p1_load_fan(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* dc, 
     S.data = src_data;
     S.stride = src_stride;
     S.nq = nq;
+    S.vec4 = (src_stride == 4 && (reinterpret_cast<uintptr_t>(src_data) & 31) == 0) ? 1 : 0;
     for (int a = 0; a < 3; ++a)
       for (int q = 0; q < 4; ++q) S.w[a][q] = q < nq ? wtab[a * nq + q] : 0.0;
     if (src_stride == 1) {
