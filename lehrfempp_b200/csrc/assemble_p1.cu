@@ -666,100 +666,6 @@ __global__ void __launch_bounds__(128, 6) k_load_p1_fan_src(int n_rows, const vo
   vec[r] = beta == 0.0 ? sum : fma(beta, vec[r], sum);
 }
 
-// ---- the same kernel with the ROWS taken in the order of their cells ----------------------------------------------------------
-// Measured at 1.0e8 triangles: k_load_p1_fan_src needs 4.0 ms where the constant source needs 0.44 -- the reference's builder numbers
-// nodes (= rows) row by row and cells column by column, so the 32 rows of a warp read their six source records from 192 different
-// DRAM pages.  Here thread t handles row perm[t], rows sorted by the smallest cell of their ring: a warp's rows are neighbours in
-// the cells' numbering, their records are adjacent (and shared), and what is scattered instead is the 8-byte result per row.  Ring,
-// cell words and flags are stored in that order, ring entries are positions in a copy of the node positions kept in the same order
-// (refreshed when the mesh's coords_version moves, as for the edge rows of the P2 / P3 kernels).
-__global__ void k_row_first_cell(int64_t n, int W, const uint8_t* __restrict__ info, const uint32_t* __restrict__ cells, uint32_t* __restrict__ key,
-                                 int32_t* __restrict__ ids) {
-  const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (r >= n) return;
-  uint32_t k = 0xFFFFFFFFU;  // rows without a ring plan keep their relative order at the end
-  if (info[r] < 2)
-    for (int s = 0; s < W; ++s) {
-      const uint32_t c = cells[static_cast<int64_t>(s) * n + r];
-      if (c != kNil) k = min(k, c >> 2);
-    }
-  key[r] = k;
-  ids[r] = static_cast<int32_t>(r);
-}
-__global__ void k_inverse_perm(int64_t n, const int32_t* __restrict__ perm, uint32_t* __restrict__ newpos) {
-  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (t < n) newpos[perm[t]] = static_cast<uint32_t>(t);
-}
-__global__ void k_reorder_ring_plan(int64_t n, int W, const int32_t* __restrict__ perm, const uint32_t* __restrict__ newpos,
-                                    const uint32_t* __restrict__ nbr, const int16_t* __restrict__ nbr16, const uint8_t* __restrict__ info,
-                                    const uint32_t* __restrict__ cells, uint32_t* __restrict__ nbr_o, uint32_t* __restrict__ cells_o,
-                                    uint8_t* __restrict__ info_o) {
-  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (t >= n) return;
-  const int64_t r = perm[t];
-  for (int s = 0; s < W; ++s) {
-    uint32_t node = kNil;
-    if (nbr16 != nullptr) {
-      const int d = nbr16[static_cast<int64_t>(s) * n + r];
-      if (d != 0) node = static_cast<uint32_t>(r + d);
-    } else {
-      node = nbr[static_cast<int64_t>(s) * n + r];
-    }
-    nbr_o[static_cast<int64_t>(s) * n + t] = node == kNil ? kNil : newpos[node];
-    cells_o[static_cast<int64_t>(s) * n + t] = cells[static_cast<int64_t>(s) * n + r];
-  }
-  info_o[t] = info[r];
-}
-
-template <int W>
-__global__ void __launch_bounds__(128, 6) k_load_p1_fan_src_ordered(int n_rows, const int32_t* __restrict__ perm, const uint32_t* __restrict__ nbr_o,
-                                                                  const uint8_t* __restrict__ info_o, const uint32_t* __restrict__ cells_o,
-                                                                  const double* __restrict__ xy_o, LoadSource S, double beta,
-                                                                  double* __restrict__ vec) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_rows) return;
-  if (__ldg(info_o + t) == 2) return;  // computed by the generic kernel
-  const int r = __ldg(perm + t);
-  uint32_t nid[W], cw[W];
-#pragma unroll
-  for (int s = 0; s < W; ++s) {
-    nid[s] = __ldg(nbr_o + static_cast<size_t>(s) * n_rows + t);
-    cw[s] = __ldg(cells_o + static_cast<size_t>(s) * n_rows + t);
-  }
-  const double2* nc = reinterpret_cast<const double2*>(xy_o);
-  const double2 xi = __ldg(nc + t);
-  double dx[W], dy[W];
-#pragma unroll
-  for (int s = 0; s < W; ++s) {
-    const double2 p = __ldg(nc + (nid[s] != kNil ? nid[s] : static_cast<uint32_t>(t)));
-    dx[s] = p.x - xi.x;
-    dy[s] = p.y - xi.y;
-  }
-  double sum = 0.0;
-#pragma unroll
-  for (int s = 0; s < W; ++s) {
-    if (cw[s] != kNil) {
-      const int u = (s + 1 < W && nid[s + 1 < W ? s + 1 : 0] != kNil) ? s + 1 : 0;
-      const double det = fabs(dx[s] * dy[u] - dy[s] * dx[u]);
-      const int a = static_cast<int>(cw[s] & 3U);
-      const double* f = S.data + static_cast<size_t>(cw[s] >> 2) * S.stride;
-      double e;
-      if (S.stride == 1) {
-        e = S.w[a][0] * __ldg(f);
-      } else if (S.vec4) {  // the cell's record in one 256-bit load (four 8-byte loads at a 32-byte lane stride touch every sector four times)
-        double f0, f1, f2, f3;
-        asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(f0), "=d"(f1), "=d"(f2), "=d"(f3) : "l"(f));
-        e = S.w[a][0] * f0 + (S.nq > 1 ? S.w[a][1] * f1 : 0.0) + (S.nq > 2 ? S.w[a][2] * f2 : 0.0) + (S.nq > 3 ? S.w[a][3] * f3 : 0.0);  // (entries beyond the rule's points are the caller's padding: never multiplied)
-      } else {
-        e = 0.0;
-        for (int q = 0; q < S.nq; ++q) e += S.w[a][q] * __ldg(f + q);
-      }
-      sum += det * e;
-    }
-  }
-  vec[r] = beta == 0.0 ? sum : fma(beta, vec[r], sum);
-}
-
 }  // namespace
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
@@ -1037,73 +943,7 @@ int p1_load_fan(lfgpu_ctx* ctx, const lfgpu_mesh* mesh, const lfgpu_dofmap* dc, 
         S.w[a][0] = t;
       }
     }
-    // rows in the order of their cells (LFGPU_LOAD_ROWORDER=0: in their own order), see k_load_p1_fan_src_ordered
-    static const bool roworder_env = [] { const char* e = std::getenv("LFGPU_LOAD_ROWORDER"); return e == nullptr || e[0] != '0'; }();
-    if (roworder_env && d->lv_o_state == 0) {
-      d->lv_o_state = -1;
-      cudaStream_t st = ctx->stream;
-      const int W = d->lv_w;
-      uint32_t *key = nullptr, *key2 = nullptr;
-      int32_t *ids = nullptr;
-      void* tmp = nullptr;
-      auto cleanup = [&]() { cudaFree(key); cudaFree(key2); cudaFree(ids); cudaFree(tmp); };
-      auto drop = [&]() {
-        cudaFree(d->lv_perm); cudaFree(d->lv_newpos); cudaFree(d->lv_nbr_o); cudaFree(d->lv_cells_o); cudaFree(d->lv_info_o); cudaFree(d->lv_xy_o);
-        d->lv_perm = nullptr; d->lv_newpos = nullptr; d->lv_nbr_o = nullptr; d->lv_cells_o = nullptr; d->lv_info_o = nullptr; d->lv_xy_o = nullptr;
-      };
-#define LO_CHECK(expr)                                                              \
-  do {                                                                              \
-    cudaError_t _e = (expr);                                                        \
-    if (_e != cudaSuccess) {                                                        \
-      set_last_error(ctx, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
-      cleanup();                                                                    \
-      drop();                                                                       \
-      return LFGPU_ERR_CUDA;                                                        \
-    }                                                                               \
-  } while (0)
-      const unsigned gr = static_cast<unsigned>(cdiv(n, 256));
-      LO_CHECK(cudaMalloc(&key, sizeof(uint32_t) * n));
-      LO_CHECK(cudaMalloc(&key2, sizeof(uint32_t) * n));
-      LO_CHECK(cudaMalloc(&ids, sizeof(int32_t) * n));
-      LO_CHECK(cudaMalloc(&d->lv_perm, sizeof(int32_t) * n));
-      LO_CHECK(cudaMalloc(&d->lv_newpos, sizeof(uint32_t) * n));
-      k_row_first_cell<<<gr, 256, 0, st>>>(n, W, d->lv_info, d->lv_cells, key, ids);
-      ctx->launches++;
-      size_t tb = 0;
-      LO_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tb, key, key2, ids, d->lv_perm, n, 0, 32, st));
-      LO_CHECK(cudaMalloc(&tmp, std::max<size_t>(tb, 16)));
-      LO_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tb, key, key2, ids, d->lv_perm, n, 0, 32, st));  // stable
-      k_inverse_perm<<<gr, 256, 0, st>>>(n, d->lv_perm, d->lv_newpos);
-      ctx->launches++;
-      LO_CHECK(cudaMalloc(&d->lv_nbr_o, sizeof(uint32_t) * static_cast<size_t>(W) * n));
-      LO_CHECK(cudaMalloc(&d->lv_cells_o, sizeof(uint32_t) * static_cast<size_t>(W) * n));
-      LO_CHECK(cudaMalloc(&d->lv_info_o, n));
-      LO_CHECK(cudaMalloc(&d->lv_xy_o, sizeof(double) * 2 * static_cast<size_t>(n)));
-      k_reorder_ring_plan<<<gr, 256, 0, st>>>(n, W, d->lv_perm, d->lv_newpos, d->lv_nbr, d->lv_nbr16, d->lv_info, d->lv_cells, d->lv_nbr_o,
-                                              d->lv_cells_o, d->lv_info_o);
-      ctx->launches++;
-      LO_CHECK(cudaGetLastError());
-      LO_CHECK(cudaStreamSynchronize(st));
-#undef LO_CHECK
-      cleanup();
-      d->lv_o_version = 0;
-      d->lv_o_mesh = nullptr;
-      d->lv_o_state = 1;
-    }
-    if (roworder_env && d->lv_o_state == 1) {
-      if (d->lv_o_version != mesh->coords_version || d->lv_o_mesh != mesh) {
-        const int rc = permute_node_coords(ctx, n, d->lv_newpos, mesh->node_coords, d->lv_xy_o);
-        if (rc != LFGPU_OK) return rc;
-        d->lv_o_version = mesh->coords_version;
-        d->lv_o_mesh = mesh;
-      }
-      switch (d->lv_w) {
-        case 6: k_load_p1_fan_src_ordered<6><<<grid, threads, 0, ctx->stream>>>(n, d->lv_perm, d->lv_nbr_o, d->lv_info_o, d->lv_cells_o, d->lv_xy_o, S, beta, d_vec); break;
-        case 8: k_load_p1_fan_src_ordered<8><<<grid, threads, 0, ctx->stream>>>(n, d->lv_perm, d->lv_nbr_o, d->lv_info_o, d->lv_cells_o, d->lv_xy_o, S, beta, d_vec); break;
-        case 10: k_load_p1_fan_src_ordered<10><<<grid, threads, 0, ctx->stream>>>(n, d->lv_perm, d->lv_nbr_o, d->lv_info_o, d->lv_cells_o, d->lv_xy_o, S, beta, d_vec); break;
-        default: k_load_p1_fan_src_ordered<12><<<grid, threads, 0, ctx->stream>>>(n, d->lv_perm, d->lv_nbr_o, d->lv_info_o, d->lv_cells_o, d->lv_xy_o, S, beta, d_vec); break;
-      }
-    } else if (d->lv_nbr16 != nullptr) {
+    if (d->lv_nbr16 != nullptr) {
       k_load_p1_fan_src<6, true><<<grid, threads, 0, ctx->stream>>>(n, d->lv_nbr16, d->lv_info, d->lv_cells, mesh->node_coords, S, beta, d_vec);
     } else {
       switch (d->lv_w) {

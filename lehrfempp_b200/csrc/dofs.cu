@@ -314,12 +314,6 @@ void lfgpu_dofmap_destroy(lfgpu_dofmap* d) {
   cudaFree(d->lv_info);
   cudaFree(d->lv_irregular);
   cudaFree(d->lv_cells);
-  cudaFree(d->lv_perm);
-  cudaFree(d->lv_newpos);
-  cudaFree(d->lv_nbr_o);
-  cudaFree(d->lv_cells_o);
-  cudaFree(d->lv_info_o);
-  cudaFree(d->lv_xy_o);
   cudaFree(d->lv_ev);
   cudaFree(d->lv_pos);
   delete d;

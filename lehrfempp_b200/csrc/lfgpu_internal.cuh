@@ -82,16 +82,6 @@ struct lfgpu_dofmap {
   int16_t* lv_nbr16 = nullptr;     // [6][n_dofs] ring ids as offsets from the row id (0 = empty)
   uint8_t* lv_info = nullptr;      // [n_dofs] 0 open fan, 1 closed fan, 2 not a single fan (generic kernel), 3 no cells
   uint32_t* lv_cells = nullptr;    // [lv_w][n_dofs] cell << 2 | local index of the row's node, per ring position (tabulated sources)
-  // the ring plan with the rows in the order of their cells (assemble_p1.cu: k_load_p1_fan_src_ordered): 0 = not built, 1 = ready
-  int lv_o_state = 0;
-  int32_t* lv_perm = nullptr;      // [n_dofs] row handled at position t
-  uint32_t* lv_newpos = nullptr;   // [n_dofs] position of a row / node
-  uint32_t* lv_nbr_o = nullptr;    // [lv_w][n_dofs] ring as positions
-  uint32_t* lv_cells_o = nullptr;  // [lv_w][n_dofs]
-  uint8_t* lv_info_o = nullptr;    // [n_dofs]
-  double* lv_xy_o = nullptr;       // [n_dofs][2] node positions in that order
-  uint64_t lv_o_version = 0;
-  const void* lv_o_mesh = nullptr;
   int32_t* lv_irregular = nullptr;
   int64_t n_lv_irregular = 0;
   // two-pass load vector (assemble.cu: k_load_positions): lv_pos [n_cells][lv_ev_stride] = index of (cell, a) in g_items,

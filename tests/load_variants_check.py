@@ -1,4 +1,4 @@
-"""Run by tests/test_gpu_zz_plan_variants.py under LFGPU_LOAD_ROWORDER / LFGPU_LOAD_TWOPASS / LFGPU_LOAD_FAN settings (read once per
+"""Run by tests/test_gpu_zz_plan_variants.py under LFGPU_LOAD_TWOPASS / LFGPU_LOAD_FAN settings (read once per
 process): the load vector of LFGPU_ALGO_AUTO against the oracle and the gather kernel.  Prints LOAD_VARIANTS_OK."""
 import os
 import sys

@@ -27,7 +27,7 @@ def test_plan_variants(variant):
     assert "PLAN_VARIANTS_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
 
 
-LOAD_VARIANTS = [{}, {"LFGPU_LOAD_ROWORDER": "0"}, {"LFGPU_LOAD_FAN": "0"}, {"LFGPU_LOAD_FAN": "0", "LFGPU_LOAD_TWOPASS": "0"}]
+LOAD_VARIANTS = [{}, {"LFGPU_LOAD_FAN": "0"}, {"LFGPU_LOAD_FAN": "0", "LFGPU_LOAD_TWOPASS": "0"}]
 
 
 @pytest.mark.parametrize("variant", LOAD_VARIANTS, ids=lambda v: ",".join("%s=%s" % kv for kv in sorted(v.items())) or "defaults")
